@@ -1,0 +1,153 @@
+"""Pins oracle/ (the numpy restatement) to the fixtures the unmodified reference produced
+(oracle/make_golden.py), and -- when /root/reference is present -- to the live reference."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import philox_ref as P
+from oracle import ps_vae_oracle as O
+from tests.golden_util import GOLDEN, case_batch, case_params, check_summary, load, rel_err
+
+TRAIN_CASES = ["train_d256_c2", "train_d192_noclf", "train_d512_c3_mlp", "train_d256_norm_cos"]
+SAMPLE_CASES = ["sample_single", "sample_c3_mlp", "sample_multilabel", "sample_multilabel_1layer"]
+
+
+def _run_train(cfg, z, dtype, tag, tol_out, tol_grad):
+    params = case_params(cfg, dtype)
+    m = {k: np.zeros_like(v) for k, v in params.items()}
+    v = {k: np.zeros_like(p) for k, p in params.items()}
+    opt = cfg.get("optimizer", dict(lr=1e-3))
+    act = (cfg.get("clf") or {}).get("activation", "relu")
+    for s in range(cfg.get("steps", 3)):
+        x, y, eps = case_batch(cfg, s, dtype)
+        scal, out, grads = O.train_loss_and_grads(
+            params, x, y, eps, kl_loss_weight=cfg.get("kl_w", 1.0), classifier_loss_weight=cfg.get("clf_w", 1.0),
+            normalize_decoder=cfg.get("normalize_decoder", False), use_cos_loss=cfg.get("use_cos_loss", False),
+            classifier_activation=act)
+        st = f"{tag}/step{s}"
+        assert rel_err(out["x_hat"], z[f"{st}/x_hat"]) <= tol_out
+        assert rel_err(out["mu"], z[f"{st}/mu"]) <= tol_out
+        assert rel_err(out["log_sigma"], z[f"{st}/ls"]) <= tol_out
+        for ours, theirs in (("loss", "train_loss"), ("recon_loss", "train_recon_loss"), ("kl_loss", "train_kl_loss")):
+            ref = float(z[f"{st}/log/{theirs}"])
+            assert abs(float(scal[ours]) - ref) <= tol_out * max(1.0, abs(ref)), (ours, float(scal[ours]), ref)
+        if cfg.get("clf"):
+            assert abs(float(scal["classifier_loss"]) - float(z[f"{st}/log/train_classifier_loss"])) <= tol_out
+            assert abs(float(scal["classifier_acc"]) - float(z[f"{st}/log/train_classifier_acc"])) <= 1e-7
+        for k in params:
+            check_summary(z, f"{st}/grad", k, grads[k], tol_grad)
+        for k in params:
+            params[k], m[k], v[k] = O.adam_step(params[k], grads[k].astype(dtype), m[k], v[k], s + 1, lr=opt.get("lr", 1e-3),
+                                                weight_decay=opt.get("weight_decay", 0.0))
+            check_summary(z, f"{st}/param", k, params[k], tol_grad)
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_train_step_fp64_twin(name):
+    z, cfg = load(name)
+    _run_train(cfg, z, np.float64, "f64", 1e-12, 1e-10)
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_train_step_fp32(name):
+    """fp32 oracle vs fp32 reference at 'highest': the 1e-5 relative bar of north_star."""
+    z, cfg = load(name)
+    _run_train(cfg, z, np.float32, "f32", 1e-5, 1e-5)
+
+
+@pytest.mark.parametrize("name", SAMPLE_CASES)
+@pytest.mark.parametrize("dtype,tag,tol", [(np.float64, "f64", 1e-12), (np.float32, "f32", 1e-5)])
+def test_sampling(name, dtype, tag, tol):
+    z, cfg = load(name)
+    params = case_params(cfg, dtype)
+    z0 = z["z0"].astype(dtype)
+    noises = [n.astype(dtype) for n in z["noises"]]
+    nd = cfg.get("normalize_decoder", False)
+    act = cfg["clf"].get("activation", "relu")
+    xu = O.unconditional_synthesis(params, z0, nd)
+    assert rel_err(xu, z[f"{tag}/uncond"]) <= tol
+    xc, hist = O.conditional_synthesis(params, z0, noises, cfg["target"], cfg["step_size"], cfg["noise_weight"], nd, act, return_history=True)
+    assert rel_err(xc, z[f"{tag}/cond"]) <= tol
+    assert rel_err(np.stack(hist), z[f"{tag}/hist"]) <= tol
+
+
+def test_adam_and_cosine():
+    z = np.load(os.path.join(GOLDEN, "adam_cosine.npz"))
+    for wd, tag in ((0.0, "wd0"), (0.01, "wd01")):
+        for dtype, dt, tol in ((np.float32, "f32", 3e-7), (np.float64, "f64", 1e-14)):
+            p = z["p0"].astype(dtype)
+            m = np.zeros_like(p)
+            v = np.zeros_like(p)
+            for s, g in enumerate(z["grads"]):
+                p, m, v = O.adam_step(p, g.astype(dtype), m, v, s + 1, lr=3e-3, weight_decay=wd)
+                ref = z[f"{tag}/{dt}/p{s}"]
+                assert np.abs(p - ref).max() <= tol * np.abs(ref).max(), (tag, dt, s)
+            assert rel_err(m, z[f"{tag}/{dt}/m"]) <= 10 * tol
+            assert rel_err(v, z[f"{tag}/{dt}/v"]) <= 10 * tol
+    for T_max in (200, 3):
+        ref = z[f"cosine/T{T_max}"]
+        got = O.cosine_annealing_lr(1e-3, T_max, float(z[f"cosine/T{T_max}/eta_min"]), len(ref) - 1)
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-18)
+
+
+def test_label_tables_bit_exact():
+    with open(os.path.join(GOLDEN, "label_tables.json")) as f:
+        g = json.load(f)
+    t = g["tables"]
+    assert O.CV_AGE_TO_LABEL == t["map_cv_age_to_label"]
+    assert O.CV_GENDER_TO_LABEL == t["map_cv_gender_to_label"]
+    assert O.VCTK_GENDER_TO_LABEL == t["map_vctk_gender_to_label"]
+    for fn, key in ((O.map_cv_age_to_label, "map_cv_age_to_label"), (O.map_cv_gender_to_label, "map_cv_gender_to_label"),
+                    (O.map_vctk_gender_to_label, "map_vctk_gender_to_label")):
+        assert fn("no-such-key") == t[key + "::default"] == -1
+        assert fn(None) == -1
+        for k, v in t[key].items():
+            assert fn(k) == v
+    for text, val in g["parsed_targets"].items():
+        assert O.parse_classifier_target(text) == val
+    assert O.sample_filename(7) == g["sample_name_fmt"].format(i=7)
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    def run(c, k):
+        return tuple(int(x) for x in P.philox4x32_10(*[np.uint32(v) for v in c], k[0], k[1]))
+    assert run((0, 0, 0, 0), (0, 0)) == (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)
+    assert run((0xFFFFFFFF,) * 4, (0xFFFFFFFF, 0xFFFFFFFF)) == (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)
+    assert run((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0)) == (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)
+
+
+def test_philox_normal_sharding_and_moments():
+    full = P.philox_normal(64, 64, seed=99, offset=5)
+    part = P.philox_normal(16, 64, seed=99, offset=5, row0=32)
+    assert np.array_equal(full[32:48], part)          # counter = global element index
+    big = P.philox_normal(20000, 64, seed=1, offset=0)
+    assert abs(big.mean()) < 5e-3 and abs(big.std() - 1) < 5e-3
+    assert not np.array_equal(P.philox_normal(4, 64, 1, 0), P.philox_normal(4, 64, 1, 1))
+
+
+def test_live_reference_agrees_when_present():
+    """Belt and braces: run the unmodified reference right here and compare (skipped on the GPU box)."""
+    from oracle.ref_loader import reference_available
+
+    if not reference_available():
+        pytest.skip("/root/reference not present")
+    import torch
+    from oracle.ref_loader import injected_normals, load_reference
+
+    torch.set_float32_matmul_precision("highest")
+    ref = load_reference()
+    cfg = dict(D=256, L=64, B=20, wseed=5, dseed=9, clf=dict(input_dim=64, num_classes=3))
+    params = case_params(cfg, np.float64)
+    m = ref.PseudoSpeakerVAE(model=dict(input_dim=256, latent_dim=64), classifier=cfg["clf"], optimizer={}, scheduler=dict(T_max=1)).double()
+    m.load_state_dict({k: torch.from_numpy(v) for k, v in params.items()})
+    x, y, eps = case_batch(cfg, 0, np.float64)
+    with injected_normals([torch.from_numpy(eps)]):
+        loss = m.training_step((torch.from_numpy(x), torch.from_numpy(y)), 0)["loss"]
+    loss.backward()
+    scal, out, grads = O.train_loss_and_grads(params, x, y, eps)
+    assert abs(float(loss) - float(scal["loss"])) < 1e-12
+    for k, p in m.named_parameters():
+        assert rel_err(grads[k], p.grad.numpy()) < 1e-11, k
