@@ -1,0 +1,376 @@
+// Element-wise / reduction kernels of the hot path (everything that is not a GEMM):
+//   adam_kernel            torch.optim.Adam single-tensor update (torch/optim/adam.py:416-547) over the flat buffer
+//   philox_*_kernel        torch.randn / randn_like replacement (model.py:57, inference.py:23,73,95)
+//   cast_bf16_kernel       fp32 -> bf16 operand copies
+//   latent_fwd_kernel      sigma = exp(.5 ls); z = mu + sigma*eps; KL partial sums  (model.py:56-57, lightning.py:115-117)
+//   latent_bwd_kernel      dmu, dls from dz
+//   ce_kernel              F.cross_entropy + Accuracy + dlogits (lightning.py:79-80)
+//   colsum / reduce        bias gradients, split-K partial sums (deterministic two-stage)
+//   row_normalize_kernel   F.normalize(x_hat, p=2, dim=1) (model.py:60-61,67-68)
+//   finalize_losses_kernel total = recon + kl_w*kl + clf_w*clf (lightning.py:119-124)
+#pragma once
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace psvae {
+
+// ---------------------------------------------------------------- Adam
+// HBM-bound: 16 B read (p,g,m,v) + 12 B written per parameter (+2 B bf16 shadow).  One float4 per thread per
+// iteration, grid-stride, grid = multiple of the SM count.
+struct AdamArgs {
+  float lr_step;      // lr / (1 - beta1^t)          (torch: step_size)
+  float bc2_sqrt;     // sqrt(1 - beta2^t)
+  float beta1, beta2, one_minus_beta1, one_minus_beta2, eps, weight_decay, grad_scale;
+};
+
+__device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, const AdamArgs& a) {
+  g *= a.grad_scale;
+  if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
+  m = m + (g - m) * a.one_minus_beta1;                    // exp_avg.lerp_(grad, 1-beta1)
+  v = v * a.beta2 + a.one_minus_beta2 * g * g;            // mul_(beta2).addcmul_(g, g, 1-beta2)
+  const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+  p = p - a.lr_step * (m / denom);                        // addcdiv_(m, denom, value=-step_size)
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t n, AdamArgs a, bf16* __restrict__ shadow) {
+  const int64_t n4 = n >> 2;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    const float4 gg = __ldg(reinterpret_cast<const float4*>(g) + i);
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    adam_one(pp.x, gg.x, mm.x, vv.x, a);
+    adam_one(pp.y, gg.y, mm.y, vv.y, a);
+    adam_one(pp.z, gg.z, mm.z, vv.z, a);
+    adam_one(pp.w, gg.w, mm.w, vv.w, a);
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+    if (shadow) {
+      uint2 u;
+      u.x = pack_bf16x2(pp.x, pp.y);
+      u.y = pack_bf16x2(pp.z, pp.w);
+      reinterpret_cast<uint2*>(shadow)[i] = u;
+    }
+  }
+  // tail (n not a multiple of 4)
+  const int64_t t = (n4 << 2) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) {
+    float pp = p[t], mm = m[t], vv = v[t];
+    adam_one(pp, g[t], mm, vv, a);
+    p[t] = pp; m[t] = mm; v[t] = vv;
+    if (shadow) shadow[t] = __float2bfloat16_rn(pp);
+  }
+}
+
+// ---------------------------------------------------------------- Philox
+__global__ void __launch_bounds__(256) philox_u32_kernel(uint32_t* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset, int64_t first) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t q_first = first >> 2, q_last = (first + n - 1) >> 2;
+  for (int64_t q = q_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q <= q_last; q += stride) {
+    const uint4 r = philox4x32_10((uint32_t)q, (uint32_t)((uint64_t)q >> 32), (uint32_t)offset, (uint32_t)(offset >> 32), (uint32_t)seed, (uint32_t)(seed >> 32));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t e = (q << 2) + j - first;
+      if (e >= 0 && e < n) out[e] = w[j];
+    }
+  }
+}
+
+// [n_rows, n_cols] normals, element index g = (row0 + r) * n_cols + c  (n_cols % 4 == 0)
+template <typename T>
+__global__ void __launch_bounds__(256) philox_normal_kernel(T* __restrict__ out, int64_t n_elems, uint64_t seed, uint64_t offset, int64_t first_elem) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nq = n_elems >> 2;
+  const uint64_t q0 = (uint64_t)first_elem >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    const float4 z = philox_normal4(q0 + (uint64_t)i, seed, offset);
+    float v[4] = {z.x, z.y, z.z, z.w};
+    store_vec<4>(out + (i << 2), v);
+  }
+}
+
+// ---------------------------------------------------------------- casts
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n8 = n >> 3;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    float v[8];
+    load_vec<8>(in + (i << 3), v);
+    store_vec<8>(out + (i << 3), v);
+  }
+  const int64_t t = (n8 << 3) + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) out[t] = __float2bfloat16_rn(in[t]);
+}
+
+// ---------------------------------------------------------------- latent forward / backward
+// Thread = 4 consecutive latent elements (= one Philox block).  KL partial: one slot per block.
+template <typename TAct>
+__global__ void __launch_bounds__(256) latent_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ ls, const float* __restrict__ eps,
+                                                         uint64_t seed, uint64_t offset, int64_t first_elem, int64_t n_elems,
+                                                         TAct* __restrict__ z, float* __restrict__ z_f32, float* __restrict__ kl_partials) {
+  __shared__ float scratch[32];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nq = n_elems >> 2;
+  float kl = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    float m[4], l[4], e[4], zz[4];
+    load_vec<4>(mu + (i << 2), m);
+    load_vec<4>(ls + (i << 2), l);
+    if (eps) {
+      load_vec<4>(eps + (i << 2), e);
+    } else {
+      const float4 t = philox_normal4(((uint64_t)first_elem >> 2) + (uint64_t)i, seed, offset);
+      e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sigma = expf(0.5f * l[j]);
+      zz[j] = fmaf(sigma, e[j], m[j]);
+      kl += 1.f + l[j] - m[j] * m[j] - expf(l[j]);
+    }
+    if (z) store_vec<4>(z + (i << 2), zz);
+    if (z_f32) store_vec<4>(z_f32 + (i << 2), zz);
+  }
+  const float s = block_sum(kl, scratch);
+  if (threadIdx.x == 0 && kl_partials) kl_partials[blockIdx.x] = s;
+}
+
+// dmu = dz + (kl_w/B) mu + dmu_clf ;  dls = dz * eps * 0.5 sigma + (kl_w/2B)(exp(ls) - 1)
+template <typename TAct>
+__global__ void __launch_bounds__(256) latent_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
+                                                         const float* __restrict__ eps, uint64_t seed, uint64_t offset, int64_t first_elem,
+                                                         int64_t n_elems, const float* __restrict__ dmu_clf, float kl_over_b,
+                                                         TAct* __restrict__ dmu, TAct* __restrict__ dls) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nq = n_elems >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    float g[4], m[4], l[4], e[4], c[4] = {0.f, 0.f, 0.f, 0.f}, om[4], ol[4];
+    load_vec<4>(dz + (i << 2), g);
+    load_vec<4>(mu + (i << 2), m);
+    load_vec<4>(ls + (i << 2), l);
+    if (dmu_clf) load_vec<4>(dmu_clf + (i << 2), c);
+    if (eps) {
+      load_vec<4>(eps + (i << 2), e);
+    } else {
+      const float4 t = philox_normal4(((uint64_t)first_elem >> 2) + (uint64_t)i, seed, offset);
+      e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sigma = expf(0.5f * l[j]);
+      om[j] = g[j] + kl_over_b * m[j] + c[j];
+      ol[j] = g[j] * e[j] * (0.5f * sigma) + 0.5f * kl_over_b * (expf(l[j]) - 1.f);
+    }
+    store_vec<4>(dmu + (i << 2), om);
+    store_vec<4>(dls + (i << 2), ol);
+  }
+}
+
+// ---------------------------------------------------------------- cross entropy (one thread per row)
+// logits [rows, C] fp32 -> in place: dlogits = (softmax - onehot) * gscale ; partial sums of NLL and of (argmax == y)
+__global__ void __launch_bounds__(256) ce_kernel(float* __restrict__ logits, const int64_t* __restrict__ y, int64_t rows, int C, float gscale,
+                                                 int write_grad, float* __restrict__ nll_partials, float* __restrict__ acc_partials) {
+  __shared__ float scratch[32];
+  float nll = 0.f, correct = 0.f;
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < rows) {
+    float* lg = logits + r * C;
+    float mx = lg[0];
+    int arg = 0;
+    for (int c = 1; c < C; ++c)
+      if (lg[c] > mx) { mx = lg[c]; arg = c; }      // first maximum, like torch.argmax
+    float se = 0.f;
+    for (int c = 0; c < C; ++c) se += expf(lg[c] - mx);
+    const float lse = logf(se);
+    const int t = (int)y[r];
+    nll = -(lg[t] - mx - lse);
+    correct = (arg == t) ? 1.f : 0.f;
+    if (write_grad) {
+      for (int c = 0; c < C; ++c) {
+        const float p = expf(lg[c] - mx - lse);
+        lg[c] = (p - (c == t ? 1.f : 0.f)) * gscale;
+      }
+    }
+  }
+  const float s1 = block_sum(nll, scratch);
+  const float s2 = block_sum(correct, scratch);
+  if (threadIdx.x == 0) {
+    nll_partials[blockIdx.x] = s1;
+    acc_partials[blockIdx.x] = s2;
+  }
+}
+
+// ---------------------------------------------------------------- column sums (bias gradients)
+// partials[chunk][col] = sum over the chunk's rows of in[row, col];  block = 32 cols x 8 row-lanes
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int64_t ld, int64_t rows, int N, int64_t rows_per_chunk, float* __restrict__ partials) {
+  __shared__ float sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_chunk, r1 = min(rows, r0 + rows_per_chunk);
+  float s = 0.f;
+  if (col < N)
+    for (int64_t r = r0 + ty; r < r1; r += 8) s += to_f32<T>(in[r * ld + col]);
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && col < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += sm[j][tx];
+    partials[(int64_t)blockIdx.y * N + col] = t;
+  }
+}
+
+// out[i] = scale * sum_s partials[s][i]   (fixed order: deterministic)
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int64_t n, int S, int64_t stride_s, float scale, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float t = 0.f;
+  for (int s = 0; s < S; ++s) t += partials[(int64_t)s * stride_s + i];
+  out[i] = t * scale;
+}
+
+// ---------------------------------------------------------------- F.normalize(p=2, dim=1): one warp per row
+__global__ void __launch_bounds__(256) row_normalize_kernel(float* __restrict__ x, int64_t rows, int D) {
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float* p = x + r * D;
+  float ss = 0.f;
+  for (int c = lane; c < D; c += 32) ss = fmaf(p[c], p[c], ss);
+  ss = warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int c = lane; c < D; c += 32) p[c] *= inv;
+}
+
+// ---------------------------------------------------------------- loss scalars
+struct LossPartials {
+  const float* sse; int n_sse;           // sum of squared reconstruction errors
+  const float* kl; int n_kl;             // sum over elements of (1 + ls - mu^2 - e^ls)
+  const float* nll[4]; const float* acc[4]; int n_ce; int n_heads;
+  float recon_scale;                     // 1 / (B * D * 10) for MSE/10, 1 / B for the cosine loss
+  float inv_b;                           // 1 / B
+  float kl_w, clf_w;
+};
+
+__global__ void finalize_losses_kernel(LossPartials lp, float* __restrict__ losses) {
+  // single block of 32 threads; each sum is taken in a fixed order
+  const int lane = threadIdx.x;
+  auto sum = [&](const float* p, int n) {
+    float t = 0.f;
+    for (int i = lane; i < n; i += 32) t += p[i];
+    return warp_sum(t);
+  };
+  const float sse = lp.sse ? sum(lp.sse, lp.n_sse) : 0.f;
+  const float kls = lp.kl ? sum(lp.kl, lp.n_kl) : 0.f;
+  float nll[4], acc[4];
+  for (int h = 0; h < 4; ++h) {
+    nll[h] = (h < lp.n_heads) ? sum(lp.nll[h], lp.n_ce) : 0.f;
+    acc[h] = (h < lp.n_heads) ? sum(lp.acc[h], lp.n_ce) : 0.f;
+  }
+  if (lane == 0) {
+    const float recon = sse * lp.recon_scale;
+    const float kl = -0.5f * kls * lp.inv_b;
+    float clf = 0.f;
+    for (int h = 0; h < lp.n_heads; ++h) clf += nll[h] * lp.inv_b;
+    if (lp.n_heads > 0) clf /= (float)lp.n_heads;
+    for (int i = 0; i < 16; ++i) losses[i] = 0.f;
+    losses[0] = recon + lp.kl_w * kl + lp.clf_w * clf;
+    losses[1] = recon;
+    losses[2] = kl;
+    losses[3] = clf;
+    for (int h = 0; h < lp.n_heads; ++h) {
+      losses[4 + h] = nll[h] * lp.inv_b;
+      losses[8 + h] = acc[h] * lp.inv_b;
+    }
+  }
+}
+
+}  // namespace psvae
+
+namespace psvae {
+
+// ---------------------------------------------------------------- reconstruction tail, general form
+// One warp per row, used when normalize_decoder (model.py:60-61) or use_cos_loss (lightning.py:110-111) is on
+// (the plain MSE case is fused into the last decoder GEMM, EpiMse).  u = decoder output before normalisation.
+//   x_hat = normalize ? u / max(|u|, 1e-12) : u
+//   cos   : loss_row = 1 - <x_hat,x> / sqrt((|x_hat|^2+1e-12)(|x|^2+1e-12)) ; d/dx_hat as in F.cosine_embedding_loss
+//   mse   : loss_row = sum (x_hat-x)^2 ; d/dx_hat = (x_hat-x) * gscale
+//   du    = normalize ? (dxh - x_hat <x_hat,dxh>) / den : dxh
+template <typename TAct>
+__global__ void __launch_bounds__(256) recon_rows_kernel(const float* __restrict__ u, const float* __restrict__ x, int64_t rows, int D, int normalize,
+                                                         int use_cos, float gscale, float* __restrict__ x_hat, TAct* __restrict__ du,
+                                                         float* __restrict__ loss_partials) {
+  __shared__ float scratch[32];
+  const int lane = threadIdx.x & 31;
+  const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  float loss = 0.f;
+  if (r < rows) {
+    const float* ur = u + r * D;
+    const float* xr = x ? x + r * D : nullptr;
+    float inv_den = 1.f;
+    if (normalize) {
+      float ss = 0.f;
+      for (int c = lane; c < D; c += 32) ss = fmaf(ur[c], ur[c], ss);
+      ss = warp_sum(ss);
+      inv_den = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+    }
+    if (x_hat)
+      for (int c = lane; c < D; c += 32) x_hat[r * D + c] = ur[c] * inv_den;
+    if (xr) {
+      float dot = 0.f, m1 = 0.f, m2 = 0.f, sse = 0.f;
+      for (int c = lane; c < D; c += 32) {
+        const float h = ur[c] * inv_den, xv = xr[c];
+        dot = fmaf(h, xv, dot); m1 = fmaf(h, h, m1); m2 = fmaf(xv, xv, m2);
+        const float d = h - xv;
+        sse = fmaf(d, d, sse);
+      }
+      dot = warp_sum(dot); m1 = warp_sum(m1); m2 = warp_sum(m2); sse = warp_sum(sse);
+      float cosv = 0.f, inv_dn = 0.f, c_over_m1 = 0.f;
+      if (use_cos) {
+        m1 += 1e-12f; m2 += 1e-12f;
+        inv_dn = 1.f / sqrtf(m1 * m2);
+        cosv = dot * inv_dn;
+        c_over_m1 = cosv / m1;
+        loss = 1.f - cosv;
+      } else {
+        loss = sse;
+      }
+      if (du) {
+        // <x_hat, dxh> for the normalisation backward
+        float hd = 0.f;
+        if (normalize) {
+          for (int c = lane; c < D; c += 32) {
+            const float h = ur[c] * inv_den, xv = xr[c];
+            const float g = use_cos ? -(xv * inv_dn - c_over_m1 * h) * gscale : (h - xv) * gscale;
+            hd = fmaf(h, g, hd);
+          }
+          hd = warp_sum(hd);
+        }
+        for (int c = lane; c < D; c += 32) {
+          const float h = ur[c] * inv_den, xv = xr[c];
+          float g = use_cos ? -(xv * inv_dn - c_over_m1 * h) * gscale : (h - xv) * gscale;
+          if (normalize) g = (g - h * hd) * inv_den;
+          du[r * D + c] = from_f32<TAct>(g);
+        }
+      }
+    }
+  }
+  if (loss_partials) {
+    const float s = block_sum(lane == 0 ? loss : 0.f, scratch);
+    if (threadIdx.x == 0) loss_partials[blockIdx.x] = s;
+  }
+}
+
+// fp32 [rows][cols] -> TAct (same shape, contiguous): z handed to psvae_decode
+template <typename TAct>
+__global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ in, TAct* __restrict__ out, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = from_f32<TAct>(in[i]);
+}
+
+}  // namespace psvae

@@ -1,0 +1,238 @@
+// Classifier-guided Langevin dynamics in latent space: the loop of ps_vae/inference.py:77-103,
+//   z <- z + 0.5 s^2 * grad_z[ log p(y|z) - 0.5 |z|^2 ] + s * noise_weight * N(0, I),
+// with the gradient in closed form through the LatentClassifier chain (latent_classifier.py:58-70;
+// SURVEY 3.4) instead of autograd, all `num_steps` steps inside ONE launch: a CTA keeps a tile of 32
+// samples (z, activations, classifier weights) in shared memory for the whole loop, the noise comes from
+// the counter-based generator (philox.cuh), and nothing goes back to the host between steps (the
+// reference does a D2H copy of z and two .item() syncs per step).
+#pragma once
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "philox.cuh"
+
+namespace psvae {
+
+constexpr int LG_TILE = 32;      // samples per CTA
+constexpr int LG_THREADS = 256;  // 8 warps; lane = sample, warp = output-feature lane
+constexpr int LG_MAXC = 16;      // classes per head (padded row length in smem)
+
+struct LangevinClf {
+  int L, n_trunk, hidden, act, n_heads;
+  int head_classes[4];
+  int targets[4];                 // -1: head not named by the target dict -> skipped
+  int64_t g_trunk_w[4], g_trunk_b[4], g_head_w[4], g_head_b[4];   // offsets into the flat parameter buffer
+  int s_trunk_w[4], s_trunk_b[4], s_head_w[4], s_head_b[4];       // offsets (floats) into the smem weight area
+  int w_floats;                   // size of the smem weight area
+};
+
+__device__ __forceinline__ float lg_act(int act, float u) {
+  switch (act) {
+    case ACT_RELU: return fmaxf(u, 0.f);
+    case ACT_TANH: return tanhf(u);
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-u));
+    case ACT_LEAKY: return u > 0.f ? u : 0.01f * u;
+  }
+  return u;
+}
+__device__ __forceinline__ float lg_act_grad(int act, float a) {
+  switch (act) {
+    case ACT_RELU: return a > 0.f ? 1.f : 0.f;
+    case ACT_TANH: return 1.f - a * a;
+    case ACT_SIGMOID: return a * (1.f - a);
+    case ACT_LEAKY: return a > 0.f ? 1.f : 0.01f;
+  }
+  return 1.f;
+}
+
+static inline size_t langevin_smem_bytes(const LangevinClf& c) {
+  const int ldz = c.L + 1, ldh = c.hidden + 1;
+  size_t f = (size_t)c.w_floats + (size_t)LG_TILE * ldz                // weights, z
+             + (size_t)c.n_trunk * LG_TILE * ldh                       // trunk activations
+             + 2 * (size_t)LG_TILE * (c.hidden > c.L ? ldh : ldz)      // gradient ping-pong
+             + (size_t)4 * LG_TILE * (LG_MAXC + 1);                    // logits / dlogits per head
+  return f * sizeof(float);
+}
+
+__global__ void __launch_bounds__(LG_THREADS) langevin_kernel(LangevinClf c, const float* __restrict__ params, float* __restrict__ z_io,
+                                                              int64_t rows, float step_size, int num_steps, float noise_weight, uint64_t seed,
+                                                              uint64_t offset0, int64_t row0, int init_from_philox, const float* __restrict__ noise,
+                                                              float* __restrict__ history, float* __restrict__ stats) {
+  extern __shared__ float lg_smem[];
+  const int L = c.L, H = c.hidden;
+  const int ldz = L + 1, ldh = H + 1, ldd = (H > L ? ldh : ldz), ldc = LG_MAXC + 1;
+  float* W = lg_smem;
+  float* zs = W + c.w_floats;
+  float* acts = zs + LG_TILE * ldz;
+  float* d0 = acts + c.n_trunk * LG_TILE * ldh;
+  float* d1 = d0 + LG_TILE * ldd;
+  float* lgt = d1 + LG_TILE * ldd;
+
+  const int tid = threadIdx.x, s = tid & 31, g = tid >> 5;
+  const int64_t tile_row0 = (int64_t)blockIdx.x * LG_TILE;
+  const int64_t row = tile_row0 + s;
+  const bool live = row < rows;
+
+  // stage classifier weights once
+  for (int j = 0; j < c.n_trunk; ++j) {
+    const int K = j == 0 ? L : H;
+    for (int i = tid; i < H * K; i += LG_THREADS) W[c.s_trunk_w[j] + i] = params[c.g_trunk_w[j] + i];
+    for (int i = tid; i < H; i += LG_THREADS) W[c.s_trunk_b[j] + i] = params[c.g_trunk_b[j] + i];
+  }
+  const int Kf = c.n_trunk ? H : L;
+  for (int h = 0; h < c.n_heads; ++h) {
+    for (int i = tid; i < c.head_classes[h] * Kf; i += LG_THREADS) W[c.s_head_w[h] + i] = params[c.g_head_w[h] + i];
+    for (int i = tid; i < c.head_classes[h]; i += LG_THREADS) W[c.s_head_b[h] + i] = params[c.g_head_b[h] + i];
+  }
+  // z tile
+  const int quads = LG_TILE * (L >> 2);
+  for (int q = tid; q < quads; q += LG_THREADS) {
+    const int qs = q / (L >> 2), qk = (q % (L >> 2)) << 2;
+    const int64_t r = tile_row0 + qs;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (r < rows) {
+      if (init_from_philox) {
+        const float4 t = philox_normal4((uint64_t)((row0 + r) * L + qk) >> 2, seed, offset0);
+        v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+      } else {
+        load_vec<4>(z_io + r * L + qk, v);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) zs[qs * ldz + qk + j] = v[j];
+  }
+  __syncthreads();
+
+  const float half_s2 = 0.5f * step_size * step_size;
+  const float nscale = step_size * noise_weight;
+
+  for (int step = 0; step < num_steps; ++step) {
+    // 1. trunk forward
+    for (int j = 0; j < c.n_trunk; ++j) {
+      const float* in = j == 0 ? zs : acts + (j - 1) * LG_TILE * ldh;
+      const int ldi = j == 0 ? ldz : ldh, K = j == 0 ? L : H;
+      float* out = acts + j * LG_TILE * ldh;
+      const float* Wj = W + c.s_trunk_w[j];
+      const float* bj = W + c.s_trunk_b[j];
+      for (int o = g; o < H; o += 8) {
+        float a = bj[o];
+        const float* w = Wj + o * K;
+        const float* x = in + s * ldi;
+#pragma unroll 4
+        for (int k = 0; k < K; ++k) a = fmaf(x[k], w[k], a);
+        out[s * ldh + o] = lg_act(c.act, a);
+      }
+      __syncthreads();
+    }
+    // 2. heads
+    const float* feat = c.n_trunk ? acts + (c.n_trunk - 1) * LG_TILE * ldh : zs;
+    const int ldf = c.n_trunk ? ldh : ldz;
+    for (int h = 0; h < c.n_heads; ++h) {
+      if (c.targets[h] < 0) continue;
+      const float* Wh = W + c.s_head_w[h];
+      const float* bh = W + c.s_head_b[h];
+      for (int o = g; o < c.head_classes[h]; o += 8) {
+        float a = bh[o];
+        const float* w = Wh + o * Kf;
+        const float* x = feat + s * ldf;
+#pragma unroll 4
+        for (int k = 0; k < Kf; ++k) a = fmaf(x[k], w[k], a);
+        lgt[(h * LG_TILE + s) * ldc + o] = a;
+      }
+    }
+    __syncthreads();
+    // 3. softmax -> d log p(y|z) / d logits = onehot(target) - softmax   (warp 0: one sample per lane)
+    if (g == 0) {
+      float lp_y = 0.f;
+      for (int h = 0; h < c.n_heads; ++h) {
+        if (c.targets[h] < 0) continue;
+        float* lg = lgt + (h * LG_TILE + s) * ldc;
+        const int C = c.head_classes[h];
+        float mx = lg[0];
+        for (int k = 1; k < C; ++k) mx = fmaxf(mx, lg[k]);
+        float se = 0.f;
+        for (int k = 0; k < C; ++k) se += expf(lg[k] - mx);
+        const float lse = logf(se);
+        lp_y += lg[c.targets[h]] - mx - lse;
+        for (int k = 0; k < C; ++k) lg[k] = (k == c.targets[h] ? 1.f : 0.f) - expf(lg[k] - mx - lse);
+      }
+      if (stats) {
+        float lp_z = 0.f;
+        for (int k = 0; k < L; ++k) lp_z = fmaf(zs[s * ldz + k], zs[s * ldz + k], lp_z);
+        lp_z *= -0.5f;
+        const float a = warp_sum(live ? lp_y + lp_z : 0.f);
+        const float b = warp_sum(live ? expf(lp_y) : 0.f);
+        if (s == 0) {
+          atomicAdd(stats + 2 * step, a);
+          atomicAdd(stats + 2 * step + 1, b);
+        }
+      }
+    }
+    __syncthreads();
+    // 4. gradient w.r.t. the head input
+    float* dcur = d0;
+    float* dnext = d1;
+    for (int k = g; k < Kf; k += 8) {
+      float a = 0.f;
+      for (int h = 0; h < c.n_heads; ++h) {
+        if (c.targets[h] < 0) continue;
+        const float* Wh = W + c.s_head_w[h];
+        const float* dl = lgt + (h * LG_TILE + s) * ldc;
+        for (int o = 0; o < c.head_classes[h]; ++o) a = fmaf(dl[o], Wh[o * Kf + k], a);
+      }
+      if (c.n_trunk) a *= lg_act_grad(c.act, feat[s * ldf + k]);
+      dcur[s * ldd + k] = a;
+    }
+    __syncthreads();
+    // 5. trunk backward
+    for (int j = c.n_trunk - 1; j >= 0; --j) {
+      const int K = j == 0 ? L : H;
+      const float* Wj = W + c.s_trunk_w[j];
+      const float* prev = j == 0 ? nullptr : acts + (j - 1) * LG_TILE * ldh;
+      for (int k = g; k < K; k += 8) {
+        float a = 0.f;
+        const float* d = dcur + s * ldd;
+#pragma unroll 4
+        for (int o = 0; o < H; ++o) a = fmaf(d[o], Wj[o * K + k], a);
+        if (prev) a *= lg_act_grad(c.act, prev[s * ldh + k]);
+        dnext[s * ldd + k] = a;
+      }
+      __syncthreads();
+      float* t = dcur; dcur = dnext; dnext = t;
+    }
+    // 6. Langevin update (thread = 4 consecutive latent dims = one Philox block)
+    for (int q = tid; q < quads; q += LG_THREADS) {
+      const int qs = q / (L >> 2), qk = (q % (L >> 2)) << 2;
+      const int64_t r = tile_row0 + qs;
+      if (r >= rows) continue;
+      float nz[4];
+      if (noise) {
+        load_vec<4>(noise + ((int64_t)step * rows + r) * L + qk, nz);
+      } else {
+        const float4 t = philox_normal4((uint64_t)((row0 + r) * L + qk) >> 2, seed, offset0 + 1 + (uint64_t)step);
+        nz[0] = t.x; nz[1] = t.y; nz[2] = t.z; nz[3] = t.w;
+      }
+      float zn[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float zv = zs[qs * ldz + qk + j];
+        const float grad = dcur[qs * ldd + qk + j] - zv;
+        zn[j] = zv + half_s2 * grad + nscale * nz[j];
+        zs[qs * ldz + qk + j] = zn[j];
+      }
+      if (history) store_vec<4>(history + ((int64_t)step * rows + r) * L + qk, zn);
+    }
+    __syncthreads();
+  }
+
+  for (int q = tid; q < quads; q += LG_THREADS) {
+    const int qs = q / (L >> 2), qk = (q % (L >> 2)) << 2;
+    const int64_t r = tile_row0 + qs;
+    if (r >= rows) continue;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = zs[qs * ldz + qk + j];
+    store_vec<4>(z_io + r * L + qk, v);
+  }
+}
+
+}  // namespace psvae

@@ -1,0 +1,1088 @@
+// C-ABI of the B200-native hot path of pseudo_speaker_VAE (see include/psvae_b200.h).
+//
+// One translation unit: the kernels live in the .cuh files next to this one, this file is the host
+// side -- argument checks, workspace carving, tensor-map cache, and the launch sequences that replace
+//   VAEModel.forward / decode            (ps_vae/model.py:38-69)
+//   PseudoSpeakerVAE.training_step + autograd backward   (ps_vae/lightning.py:67-131)
+//   torch.optim.Adam.step                (driven from ps_vae/lightning.py:204-205)
+//   unconditional / conditional synthesis (ps_vae/inference.py:10-110)
+// Two GEMM engines sit behind every Linear: CUDA-core fp32 (sgemm.cuh, the 1e-5 parity mode) and
+// tcgen05/TMEM/TMA bf16 (gemm_tc.cuh, the speed mode).  There is no CPU path.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "../../include/psvae_b200.h"
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "gemm_tc.cuh"
+#include "kernels.cuh"
+#include "langevin.cuh"
+#include "philox.cuh"
+#include "sgemm.cuh"
+
+namespace psvae {
+
+// ------------------------------------------------------------------------------------------------
+// error text, launch counter, options
+// ------------------------------------------------------------------------------------------------
+static thread_local char g_err[768] = "";
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+  return (int)e > 0 ? (int)e : 1;
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+struct Options {
+  int64_t decode_chunk = 1 << 15;      // rows per pass of psvae_decode: keeps the hidden activations L2-resident
+  int64_t wgrad_split_cap = 64;        // split-K ceiling of the wgrad GEMMs
+  int64_t colsum_rows = 512;           // rows per bias-gradient partial
+  int64_t tc_force_bn = 0;             // tests: force the N tile of the tcgen05 engine
+  int64_t tc_grid_limit = 0;           // tests: cap the persistent grid
+};
+static Options g_opt;
+
+// ------------------------------------------------------------------------------------------------
+// device facts
+// ------------------------------------------------------------------------------------------------
+struct DevInfo { int checked = 0, ok = 0, sms = 0, major = 0, minor = 0; };
+static DevInfo g_dev[64];
+static std::mutex g_dev_mu;
+
+static int dev_info(DevInfo** out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); this library has no CPU path", cudaGetErrorString(e));
+    return -4;
+  }
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  DevInfo& d = g_dev[dev & 63];
+  if (!d.checked) {
+    PSVAE_CUDA(cudaDeviceGetAttribute(&d.major, cudaDevAttrComputeCapabilityMajor, dev));
+    PSVAE_CUDA(cudaDeviceGetAttribute(&d.minor, cudaDevAttrComputeCapabilityMinor, dev));
+    PSVAE_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+    d.ok = (d.major == 10);
+    d.checked = 1;
+  }
+  *out = &d;
+  return 0;
+}
+int tc_device_check() {
+  DevInfo* d = nullptr;
+  PSVAE_TRY(dev_info(&d));
+  if (!d->ok) {
+    set_error("device is sm_%d%d; this library is built for sm_100a (B200) only and has no fallback", d->major, d->minor);
+    return -4;
+  }
+  return 0;
+}
+int tc_grid_size() {
+  DevInfo* d = nullptr;
+  if (dev_info(&d) != 0) return PSVAE_NUM_SMS;
+  int g = d->sms > 0 ? d->sms : PSVAE_NUM_SMS;
+  if (g_opt.tc_grid_limit > 0 && g_opt.tc_grid_limit < g) g = (int)g_opt.tc_grid_limit;
+  return g;
+}
+static int ew_grid(int64_t work_items, int threads = 256) {   // element-wise grid: whole waves of the SM count
+  int64_t blocks = ceil_div64(work_items, threads);
+  const int64_t cap = (int64_t)PSVAE_NUM_SMS * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------------
+// TMA tensor maps (cuTensorMapEncodeTiled through the runtime's driver entry point: no -lcuda needed)
+// ------------------------------------------------------------------------------------------------
+static PFN_cuTensorMapEncodeTiled g_encode = nullptr;
+static std::mutex g_tm_mu;
+typedef std::tuple<const void*, int64_t, int64_t, int64_t, int, int> TmKey;
+static std::map<TmKey, CUtensorMap> g_tm_cache;
+
+int tc_tensor_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_tm_mu);
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    PSVAE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) {
+      set_error("cuTensorMapEncodeTiled not available from this driver");
+      return -3;
+    }
+    g_encode = (PFN_cuTensorMapEncodeTiled)fn;
+  }
+  const TmKey key(op.ptr, op.rows, op.ld, K, op.mn_major ? 1 : 0, box_rows);
+  auto it = g_tm_cache.find(key);
+  if (it != g_tm_cache.end()) {
+    *out = it->second;
+    return 0;
+  }
+  if ((reinterpret_cast<uintptr_t>(op.ptr) & 15) != 0 || (op.ld % 8) != 0) {
+    set_error("tcgen05 operand must be 16-byte aligned with a leading dimension that is a multiple of 8 (ptr=%p ld=%lld)", op.ptr, (long long)op.ld);
+    return -2;
+  }
+  cuuint64_t gdim[2], gstride[1];
+  cuuint32_t box[2], estr[2] = {1, 1};
+  if (!op.mn_major) {            // row-major [rows][K]: inner = K
+    gdim[0] = (cuuint64_t)K; gdim[1] = (cuuint64_t)op.rows;
+    box[0] = TC_BK; box[1] = (cuuint32_t)box_rows;
+  } else {                       // stored [K][rows]: inner = rows (M or N)
+    gdim[0] = (cuuint64_t)op.rows; gdim[1] = (cuuint64_t)K;
+    box[0] = 64; box[1] = (cuuint32_t)box_rows;
+  }
+  gstride[0] = (cuuint64_t)op.ld * sizeof(bf16);
+  alignas(64) CUtensorMap tm;
+  CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.ptr), gdim, gstride, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p dims=[%llu,%llu] stride=%llu box=[%u,%u]", (int)r, op.ptr,
+              (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gstride[0], box[0], box[1]);
+    return -3;
+  }
+  if (g_tm_cache.size() > 8192) g_tm_cache.clear();
+  g_tm_cache[key] = tm;
+  *out = tm;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM front end: C[M,N] = A[M,K] * B[N,K]^T through `epi`, on the engine the activation type selects
+// ------------------------------------------------------------------------------------------------
+enum GemmMode { G_FWD = 0 /* A K-major, B K-major */, G_DGRAD = 1 /* A K-major, B MN-major */, G_WGRAD = 2 /* both MN-major */ };
+
+template <typename T> struct Engine;
+
+template <> struct Engine<float> {
+  template <int MODE, class Epi>
+  static int gemm(const float* A, int64_t lda, const float* B, int64_t ldb, int64_t M, int N, int64_t K, int splits, bool vec_ok,
+                  const Epi& epi, cudaStream_t st) {
+    constexpr bool a_mn = (MODE == G_WGRAD), b_mn = (MODE != G_FWD);
+    SgemmOperand a{A, a_mn ? 1 : lda, a_mn ? lda : 1};
+    SgemmOperand b{B, b_mn ? 1 : ldb, b_mn ? ldb : 1};
+    return sgemm_launch(a, b, M, N, K, splits, vec_ok, epi, st);
+  }
+  static int wgrad_splits(int64_t M, int64_t N, int64_t K) {
+    const int64_t tiles = ceil_div64(M, SG_BM) * ceil_div64(N, SG_BN);
+    int64_t s = ceil_div64(2 * PSVAE_NUM_SMS, tiles);
+    if (s < ceil_div64(K, 2048)) s = ceil_div64(K, 2048);  // parity engine: short fp32 accumulation chains (<= 2048 rows per partial)
+    const int64_t max_s = K / 128 > 1 ? K / 128 : 1;      // at least 128 rows per split
+    if (s > max_s) s = max_s;
+    if (s > g_opt.wgrad_split_cap) s = g_opt.wgrad_split_cap;
+    if (s < 1) s = 1;
+    const int64_t chunk = align_up64(ceil_div64(K, s), SG_BK);
+    return (int)ceil_div64(K, chunk);
+  }
+};
+
+template <> struct Engine<bf16> {
+  template <int MODE, class Epi>
+  static int gemm(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int64_t M, int N, int64_t K, int splits, bool /*vec_ok*/,
+                  const Epi& epi, cudaStream_t st) {
+    constexpr bool a_mn = (MODE == G_WGRAD), b_mn = (MODE != G_FWD);
+    TcOperand a{A, M, lda, a_mn};
+    TcOperand b{B, (int64_t)N, ldb, b_mn};
+    return gemm_tc_launch<a_mn, b_mn, Epi>(a, b, M, N, K, splits, epi, st, (int)g_opt.tc_force_bn);
+  }
+  static int wgrad_splits(int64_t M, int64_t N, int64_t K) {
+    const int bn = g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn((int)N);
+    const int64_t tiles = ceil_div64(M, TC_BM) * ceil_div64(N, bn);
+    const int64_t kb = ceil_div64(K, TC_BK);
+    int64_t s = PSVAE_NUM_SMS / tiles;
+    if (s > kb) s = kb;
+    if (s > g_opt.wgrad_split_cap) s = g_opt.wgrad_split_cap;
+    if (s < 1) s = 1;
+    const int64_t per = ceil_div64(kb, s);
+    return (int)ceil_div64(kb, per);          // no empty split
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// model shape helpers
+// ------------------------------------------------------------------------------------------------
+struct Net {
+  const psvae_model_desc* d;
+  int D, L, H, nh;             // nh hidden layers => nh + 1 Linear layers per MLP
+  explicit Net(const psvae_model_desc* desc) : d(desc), D(desc->input_dim), L(desc->latent_dim), H(desc->hidden_dim), nh(desc->num_hidden) {}
+  int enc_in(int j) const { return j == 0 ? D : H; }
+  int enc_out(int j) const { return j == nh ? L : H; }
+  int dec_in(int j) const { return j == 0 ? L : H; }
+  int dec_out(int j) const { return j == nh ? D : H; }
+  bool has_clf() const { return d->clf_num_heads > 0; }
+  int clf_feat() const { return d->clf_num_trunk > 0 ? d->clf_hidden : L; }
+  int clf_trunk_in(int t) const { return t == 0 ? L : d->clf_hidden; }
+};
+
+static int check_desc(const psvae_model_desc* d, int precision) {
+  if (!d) { set_error("desc is NULL"); return -1; }
+  if (d->input_dim < 4 || d->input_dim % 4) { set_error("input_dim=%d must be a positive multiple of 4", d->input_dim); return -2; }
+  if (d->latent_dim < 4 || d->latent_dim % 4 || d->latent_dim > 256) { set_error("latent_dim=%d must be a multiple of 4 in [4,256]", d->latent_dim); return -2; }
+  if (d->hidden_dim < 4 || d->hidden_dim % 4) { set_error("hidden_dim=%d must be a positive multiple of 4", d->hidden_dim); return -2; }
+  if (d->num_hidden < 1 || d->num_hidden + 1 > PSVAE_MAX_LAYERS) { set_error("num_hidden=%d out of range [1,%d]", d->num_hidden, PSVAE_MAX_LAYERS - 1); return -2; }
+  if (d->clf_num_heads < 0 || d->clf_num_heads > PSVAE_MAX_CLF_HEADS) { set_error("clf_num_heads=%d out of range", d->clf_num_heads); return -2; }
+  if (d->clf_num_trunk < 0 || d->clf_num_trunk > PSVAE_MAX_CLF_TRUNK) { set_error("clf_num_trunk=%d out of range", d->clf_num_trunk); return -2; }
+  if (d->clf_num_heads > 0) {
+    if (d->clf_num_trunk > 0 && (d->clf_hidden < 1 || d->clf_hidden > 1024)) { set_error("clf_hidden=%d out of range [1,1024]", d->clf_hidden); return -2; }
+    if (d->clf_activation < 0 || d->clf_activation > 3) { set_error("clf_activation=%d unknown", d->clf_activation); return -2; }
+    for (int h = 0; h < d->clf_num_heads; ++h) {
+      if (d->clf_head_classes[h] < 2) {
+        // the reference's 1-logit "binary" branch is degenerate (log_softmax of one logit == 0)
+        set_error("classifier head %d has %d classes; at least 2 are required", h, d->clf_head_classes[h]);
+        return -2;
+      }
+      if (d->clf_head_classes[h] > LG_MAXC) { set_error("classifier head %d has %d classes; at most %d are supported", h, d->clf_head_classes[h], LG_MAXC); return -2; }
+    }
+  }
+  if (precision == PSVAE_BF16) {
+    if (d->input_dim % 8 || d->latent_dim % 8 || d->hidden_dim % 64) {
+      set_error("PSVAE_BF16 needs input_dim %% 8 == 0, latent_dim %% 8 == 0, hidden_dim %% 64 == 0 (got %d, %d, %d)", d->input_dim, d->latent_dim, d->hidden_dim);
+      return -2;
+    }
+  } else if (precision != PSVAE_FP32) {
+    set_error("unknown precision %d", precision);
+    return -2;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace carving (the caller owns the memory; the same function sizes and carves)
+// ------------------------------------------------------------------------------------------------
+struct Bump {
+  char* base;
+  int64_t used = 0;
+  explicit Bump(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T> T* take(int64_t n) {
+    const int64_t off = used;
+    used = align_up64(used + n * (int64_t)sizeof(T), 256);
+    return base ? reinterpret_cast<T*>(base + off) : nullptr;
+  }
+};
+
+template <typename TAct> struct StepBufs {
+  TAct* xa = nullptr;
+  TAct* he[PSVAE_MAX_LAYERS] = {};
+  float *mu = nullptr, *ls = nullptr;
+  TAct* z = nullptr;
+  TAct* hd[PSVAE_MAX_LAYERS] = {};
+  float* u = nullptr;
+  TAct* dxh = nullptr;
+  TAct* gd[2] = {};
+  float *dz = nullptr, *dmu_clf = nullptr;
+  TAct *dmu = nullptr, *dls = nullptr;
+  TAct* ge[2] = {};
+  float* clf_act[PSVAE_MAX_CLF_TRUNK] = {};
+  float* logits[PSVAE_MAX_CLF_HEADS] = {};
+  float* clf_g[2] = {};
+  float *wpart = nullptr, *cpart = nullptr;
+  float *sse_part = nullptr, *kl_part = nullptr, *nll_part[PSVAE_MAX_CLF_HEADS] = {}, *acc_part[PSVAE_MAX_CLF_HEADS] = {};
+  int64_t n_sse = 0, n_kl = 0, n_ce = 0;
+};
+
+static int64_t sse_slots(int64_t rows, int D) {
+  int64_t a = sgemm_red_slots(rows, D);
+  int64_t b = ceil_div64(rows * 32, 256);     // recon_rows_kernel: 8 rows per block
+  int64_t c = PSVAE_NUM_SMS * 2;              // tcgen05 engine: one per CTA
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
+}
+
+template <typename TAct>
+static void plan(const psvae_model_desc* d, int64_t rows, int mode, Bump& b, StepBufs<TAct>& w) {
+  Net n(d);
+  const bool is_bf16 = sizeof(TAct) == 2;
+  if (mode == PSVAE_MODE_DECODE) {
+    w.z = b.take<TAct>(rows * n.L);
+    for (int j = 0; j < n.nh; ++j) w.hd[j] = b.take<TAct>(rows * n.H);
+    return;
+  }
+  const bool train = (mode == PSVAE_MODE_TRAIN);
+  if (is_bf16) w.xa = b.take<TAct>(rows * n.D);
+  for (int j = 0; j < n.nh; ++j) w.he[j] = b.take<TAct>(rows * 2 * n.H);
+  w.mu = b.take<float>(rows * n.L);
+  w.ls = b.take<float>(rows * n.L);
+  w.z = b.take<TAct>(rows * n.L);
+  for (int j = 0; j < n.nh; ++j) w.hd[j] = b.take<TAct>(rows * n.H);
+  w.u = b.take<float>(rows * n.D);
+  w.n_sse = sse_slots(rows, n.D);
+  w.n_kl = ew_grid(rows * n.L / 4);
+  w.n_ce = ceil_div64(rows, 256);
+  w.sse_part = b.take<float>(w.n_sse);
+  w.kl_part = b.take<float>(w.n_kl);
+  if (n.has_clf()) {
+    for (int t = 0; t < d->clf_num_trunk; ++t) w.clf_act[t] = b.take<float>(rows * d->clf_hidden);
+    for (int h = 0; h < d->clf_num_heads; ++h) {
+      w.logits[h] = b.take<float>(rows * d->clf_head_classes[h]);
+      w.nll_part[h] = b.take<float>(w.n_ce);
+      w.acc_part[h] = b.take<float>(w.n_ce);
+    }
+  }
+  if (!train) return;
+  w.dxh = b.take<TAct>(rows * n.D);
+  for (int i = 0; i < 2; ++i) w.gd[i] = b.take<TAct>(rows * n.H);
+  w.dz = b.take<float>(rows * n.L);
+  w.dmu = b.take<TAct>(rows * n.L);
+  w.dls = b.take<TAct>(rows * n.L);
+  for (int i = 0; i < 2; ++i) w.ge[i] = b.take<TAct>(rows * 2 * n.H);
+  int64_t wmax = 0, cmax = 2 * n.H > n.D ? 2 * n.H : n.D;
+  auto upd = [&](int64_t M, int64_t N, bool clf) {
+    const int s = clf ? Engine<float>::wgrad_splits(M, N, rows) : Engine<TAct>::wgrad_splits(M, N, rows);
+    if (s * M * N > wmax) wmax = s * M * N;
+  };
+  upd(2 * n.enc_out(0), n.enc_in(0), false);
+  for (int j = 1; j <= n.nh; ++j) upd(n.enc_out(j), n.enc_in(j), false);
+  for (int j = 0; j <= n.nh; ++j) upd(n.dec_out(j), n.dec_in(j), false);
+  if (n.has_clf()) {
+    w.dmu_clf = b.take<float>(rows * n.L);
+    const int gw = d->clf_hidden > n.L ? d->clf_hidden : n.L;
+    for (int i = 0; i < 2; ++i) w.clf_g[i] = b.take<float>(rows * gw);
+    for (int t = 0; t < d->clf_num_trunk; ++t) upd(d->clf_hidden, n.clf_trunk_in(t), true);
+    for (int h = 0; h < d->clf_num_heads; ++h) upd(d->clf_head_classes[h], n.clf_feat(), true);
+    if (d->clf_hidden > cmax) cmax = d->clf_hidden;
+  }
+  w.wpart = b.take<float>(wmax);
+  w.cpart = b.take<float>(ceil_div64(rows, g_opt.colsum_rows) * cmax);
+}
+
+// ------------------------------------------------------------------------------------------------
+// small launch helpers
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+static int launch_colsum(const T* in, int64_t ld, int64_t rows, int N, float* cpart, float* out, cudaStream_t st) {
+  const int64_t rpc = g_opt.colsum_rows;
+  const int chunks = (int)ceil_div64(rows, rpc);
+  dim3 grid((unsigned)ceil_div64(N, 32), (unsigned)chunks);
+  colsum_kernel<T><<<grid, 256, 0, st>>>(in, ld, rows, N, rpc, cpart);
+  count_launch();
+  PSVAE_LAUNCH_CHECK("colsum_kernel");
+  reduce_partials_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(cpart, N, chunks, N, 1.f, out);
+  count_launch();
+  PSVAE_LAUNCH_CHECK("reduce_partials_kernel");
+  return 0;
+}
+static int launch_reduce(const float* partials, int64_t n, int S, float* out, cudaStream_t st) {
+  reduce_partials_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(partials, n, S, n, 1.f, out);
+  count_launch();
+  PSVAE_LAUNCH_CHECK("reduce_partials_kernel");
+  return 0;
+}
+
+// dW[M=out][N=in] = dY[B][out]^T * A[B][in]   (+ bias gradient = column sums of dY)
+template <typename TAct>
+static int wgrad(const TAct* dY, int64_t ldy, const TAct* A, int64_t lda, int64_t rows, int out, int in, float* gW, float* gb,
+                 StepBufs<TAct>& w, cudaStream_t st) {
+  const int splits = Engine<TAct>::wgrad_splits(out, in, rows);
+  if (splits == 1) {
+    EpiStore e{gW, in, 0, 1.f, 0.f, nullptr};
+    PSVAE_TRY((Engine<TAct>::template gemm<G_WGRAD>(dY, ldy, A, lda, out, in, rows, 1, in % 4 == 0, e, st)));
+  } else {
+    EpiStore e{w.wpart, in, (int64_t)out * in, 1.f, 0.f, nullptr};
+    PSVAE_TRY((Engine<TAct>::template gemm<G_WGRAD>(dY, ldy, A, lda, out, in, rows, splits, in % 4 == 0, e, st)));
+    PSVAE_TRY(launch_reduce(w.wpart, (int64_t)out * in, splits, gW, st));
+  }
+  return launch_colsum<TAct>(dY, ldy, rows, out, w.cpart, gb, st);
+}
+// classifier wgrad: always fp32 on the CUDA cores
+template <typename TAct>
+static int wgrad_clf(const float* dY, int64_t ldy, const float* A, int64_t lda, int64_t rows, int out, int in, float* gW, float* gb,
+                     StepBufs<TAct>& w, cudaStream_t st) {
+  const int splits = Engine<float>::wgrad_splits(out, in, rows);
+  const bool vec = (in % 4 == 0);
+  if (splits == 1) {
+    EpiStore e{gW, in, 0, 1.f, 0.f, nullptr};
+    PSVAE_TRY((Engine<float>::gemm<G_WGRAD>(dY, ldy, A, lda, out, in, rows, 1, vec, e, st)));
+  } else {
+    EpiStore e{w.wpart, in, (int64_t)out * in, 1.f, 0.f, nullptr};
+    PSVAE_TRY((Engine<float>::gemm<G_WGRAD>(dY, ldy, A, lda, out, in, rows, splits, vec, e, st)));
+    PSVAE_TRY(launch_reduce(w.wpart, (int64_t)out * in, splits, gW, st));
+  }
+  return launch_colsum<float>(dY, ldy, rows, out, w.cpart, gb, st);
+}
+
+template <int ACT>
+static int clf_linear_act(const float* a, int64_t lda, const float* W, const float* b, float* out, int64_t rows, int N, int K, cudaStream_t st) {
+  EpiBiasAct<float, ACT> e{b, out, N, nullptr};
+  return Engine<float>::gemm<G_FWD>(a, lda, W, K, rows, N, K, 1, N % 4 == 0, e, st);
+}
+static int clf_linear(int act, const float* a, int64_t lda, const float* W, const float* b, float* out, int64_t rows, int N, int K, cudaStream_t st) {
+  switch (act) {
+    case ACT_NONE: return clf_linear_act<ACT_NONE>(a, lda, W, b, out, rows, N, K, st);
+    case ACT_RELU: return clf_linear_act<ACT_RELU>(a, lda, W, b, out, rows, N, K, st);
+    case ACT_TANH: return clf_linear_act<ACT_TANH>(a, lda, W, b, out, rows, N, K, st);
+    case ACT_SIGMOID: return clf_linear_act<ACT_SIGMOID>(a, lda, W, b, out, rows, N, K, st);
+    case ACT_LEAKY: return clf_linear_act<ACT_LEAKY>(a, lda, W, b, out, rows, N, K, st);
+  }
+  set_error("unknown activation %d", act);
+  return -2;
+}
+// out[B][in] = (dY[B][out] * W[out][in]) .* act'(A[B][in]) + beta * out
+template <int ACT>
+static int clf_dgrad_act(const float* dY, int out_dim, const float* W, int in_dim, const float* A, float* out, float beta, int64_t rows, cudaStream_t st) {
+  EpiActGrad<float, float, ACT> e{A, in_dim, out, in_dim, beta, nullptr};
+  return Engine<float>::gemm<G_DGRAD>(dY, out_dim, W, in_dim, rows, in_dim, out_dim, 1, in_dim % 4 == 0, e, st);
+}
+static int clf_dgrad(int act, const float* dY, int out_dim, const float* W, int in_dim, const float* A, float* out, float beta, int64_t rows, cudaStream_t st) {
+  if (!A) {
+    EpiStore e{out, in_dim, 0, 1.f, beta, nullptr};
+    return Engine<float>::gemm<G_DGRAD>(dY, out_dim, W, in_dim, rows, in_dim, out_dim, 1, in_dim % 4 == 0, e, st);
+  }
+  switch (act) {
+    case ACT_RELU: return clf_dgrad_act<ACT_RELU>(dY, out_dim, W, in_dim, A, out, beta, rows, st);
+    case ACT_TANH: return clf_dgrad_act<ACT_TANH>(dY, out_dim, W, in_dim, A, out, beta, rows, st);
+    case ACT_SIGMOID: return clf_dgrad_act<ACT_SIGMOID>(dY, out_dim, W, in_dim, A, out, beta, rows, st);
+    case ACT_LEAKY: return clf_dgrad_act<ACT_LEAKY>(dY, out_dim, W, in_dim, A, out, beta, rows, st);
+  }
+  set_error("unknown activation %d", act);
+  return -2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the step: forward (+ losses) (+ backward)
+// ------------------------------------------------------------------------------------------------
+struct StepArgs {
+  const psvae_model_desc* d;
+  const float* params;
+  const bf16* shadow;
+  float* grads;
+  const float* x;
+  const int64_t* y;
+  const float* eps;
+  uint64_t seed, offset;
+  int64_t row0, rows;
+  float kl_w, clf_w;
+  int use_cos, want_loss, want_grads;
+  float *x_hat, *mu, *ls, *losses;
+  void* ws;
+  int64_t ws_bytes;
+  cudaStream_t st;
+};
+
+template <typename TAct> static const TAct* weights_of(const StepArgs& a);
+template <> const float* weights_of<float>(const StepArgs& a) { return a.params; }
+template <> const bf16* weights_of<bf16>(const StepArgs& a) { return a.shadow; }
+
+// decoder chain z -> pre-normalisation output; the last layer goes through `last_epi`
+template <typename TAct, class LastEpi>
+static int decoder_forward(const Net& n, const TAct* Wt, const float* params, const TAct* z, TAct* const* hd, int64_t rows, const LastEpi& last_epi,
+                           cudaStream_t st) {
+  const TAct* a = z;
+  for (int j = 0; j < n.nh; ++j) {
+    EpiBiasAct<TAct, ACT_RELU> e{params + n.d->dec_b[j], hd[j], n.H, nullptr};
+    PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(a, n.dec_in(j), Wt + n.d->dec_w[j], n.dec_in(j), rows, n.H, n.dec_in(j), 1, true, e, st)));
+    a = hd[j];
+  }
+  return Engine<TAct>::template gemm<G_FWD>(a, n.H, Wt + n.d->dec_w[n.nh], n.H, rows, n.D, n.H, 1, n.D % 4 == 0, last_epi, st);
+}
+
+template <typename TAct>
+static int run_step(const StepArgs& a) {
+  PSVAE_TRY(tc_device_check());
+  const psvae_model_desc* d = a.d;
+  Net n(d);
+  const int64_t B = a.rows;
+  cudaStream_t st = a.st;
+  if (B <= 0) { set_error("rows=%lld must be positive", (long long)B); return -2; }
+  if (!a.params || !a.x) { set_error("params and x must not be NULL"); return -1; }
+  if (sizeof(TAct) == 2 && !a.shadow) { set_error("PSVAE_BF16 needs the bf16 shadow copy of the parameters (psvae_refresh_shadow)"); return -1; }
+  if (a.want_grads && !a.grads) { set_error("grads must not be NULL when compute_grads != 0"); return -1; }
+  if (a.want_loss && !a.losses) { set_error("losses must not be NULL"); return -1; }
+  if (a.want_loss && n.has_clf() && !a.y) { set_error("y must not be NULL when the model has a classifier"); return -1; }
+  const int mode = a.want_grads ? PSVAE_MODE_TRAIN : PSVAE_MODE_FORWARD;
+  StepBufs<TAct> w;
+  {
+    Bump sz(nullptr);
+    StepBufs<TAct> tmp;
+    plan<TAct>(d, B, mode, sz, tmp);
+    if (sz.used > a.ws_bytes || !a.ws) {
+      set_error("workspace too small: need %lld bytes, got %lld", (long long)sz.used, (long long)a.ws_bytes);
+      return -2;
+    }
+    Bump b(a.ws);
+    plan<TAct>(d, B, mode, b, w);
+  }
+  const TAct* Wt = weights_of<TAct>(a);
+  const float* P = a.params;
+  float* mu = a.mu ? a.mu : w.mu;
+  float* ls = a.ls ? a.ls : w.ls;
+  const int64_t first_elem = a.row0 * n.L;
+
+  // ---- encoders (model.py:54-55).  Layer 0 of both encoders is one [2H, D] GEMM.
+  const TAct* xa;
+  if constexpr (sizeof(TAct) == 2) {
+    cast_bf16_kernel<<<ew_grid(B * n.D / 8), 256, 0, st>>>(a.x, w.xa, B * n.D);
+    count_launch();
+    PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
+    xa = w.xa;
+  } else {
+    xa = a.x;
+  }
+  {
+    EpiBiasAct<TAct, ACT_RELU> e{P + d->enc_b[0], w.he[0], 2 * n.H, nullptr};
+    PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(xa, n.D, Wt + d->enc_w[0], n.D, B, 2 * n.H, n.D, 1, true, e, st)));
+  }
+  for (int j = 1; j < n.nh; ++j) {
+    for (int s = 0; s < 2; ++s) {      // s = 0: encoder_mu, 1: encoder_sigma
+      EpiBiasAct<TAct, ACT_RELU> e{P + d->enc_b[j] + s * n.H, w.he[j] + s * n.H, 2 * n.H, nullptr};
+      PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(w.he[j - 1] + s * n.H, 2 * n.H, Wt + d->enc_w[j] + (int64_t)s * n.H * n.H, n.H, B, n.H, n.H, 1, true, e, st)));
+    }
+  }
+  for (int s = 0; s < 2; ++s) {
+    EpiBiasAct<float, ACT_NONE> e{P + d->enc_b[n.nh] + s * n.L, s == 0 ? mu : ls, n.L, nullptr};
+    PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(w.he[n.nh - 1] + s * n.H, 2 * n.H, Wt + d->enc_w[n.nh] + (int64_t)s * n.L * n.H, n.H, B, n.L, n.H, 1, true, e, st)));
+  }
+  // ---- reparameterisation + KL partial sums (model.py:56-57, lightning.py:115-117)
+  latent_fwd_kernel<TAct><<<(unsigned)w.n_kl, 256, 0, st>>>(mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, w.z, nullptr, w.kl_part);
+  count_launch();
+  PSVAE_LAUNCH_CHECK("latent_fwd_kernel");
+
+  // ---- latent classifier on mu (lightning.py:73-83), fp32 on the CUDA cores (C is 2..3)
+  const int feat_dim = n.clf_feat();
+  const float* feat = mu;
+  if (n.has_clf() && a.want_loss) {
+    for (int t = 0; t < d->clf_num_trunk; ++t) {
+      PSVAE_TRY(clf_linear(d->clf_activation, feat, t == 0 ? n.L : d->clf_hidden, P + d->clf_trunk_w[t], P + d->clf_trunk_b[t], w.clf_act[t], B,
+                           d->clf_hidden, n.clf_trunk_in(t), st));
+      feat = w.clf_act[t];
+    }
+    for (int h = 0; h < d->clf_num_heads; ++h) {
+      const int C = d->clf_head_classes[h];
+      PSVAE_TRY(clf_linear(ACT_NONE, feat, feat_dim, P + d->clf_head_w[h], P + d->clf_head_b[h], w.logits[h], B, C, feat_dim, st));
+      const float gscale = a.clf_w / ((float)B * (float)d->clf_num_heads);
+      ce_kernel<<<(unsigned)w.n_ce, 256, 0, st>>>(w.logits[h], a.y + (int64_t)h * B, B, C, gscale, a.want_grads, w.nll_part[h], w.acc_part[h]);
+      count_launch();
+      PSVAE_LAUNCH_CHECK("ce_kernel");
+    }
+  }
+
+  // ---- decoder (model.py:58-61) + reconstruction loss (lightning.py:110-113)
+  const bool general_tail = d->normalize_decoder || a.use_cos;
+  int n_sse_used = 0;
+  if (a.want_loss && !general_tail) {
+    const float scale = 2.f / ((float)B * (float)n.D * 10.f);
+    EpiMse<TAct> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, a.want_grads ? w.dxh : nullptr, n.D, scale, w.sse_part};
+    PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
+    n_sse_used = sizeof(TAct) == 2 ? tc_grid_size() : (int)sgemm_red_slots(B, n.D);
+    if (sizeof(TAct) == 2) {
+      // the persistent grid may be smaller than the SM count when there are few tiles: clear the unused slots' contribution
+      const int64_t tiles = ceil_div64(B, TC_BM) * ceil_div64(n.D, g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(n.D));
+      if (tiles < n_sse_used) n_sse_used = (int)tiles;
+    }
+  } else {
+    float* u = general_tail ? w.u : (a.x_hat ? a.x_hat : w.u);
+    EpiBiasAct<float, ACT_NONE> e{P + d->dec_b[n.nh], u, n.D, nullptr};
+    PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
+    if (general_tail) {
+      const float gscale = a.use_cos ? 1.f / (float)B : 2.f / ((float)B * (float)n.D * 10.f);
+      const int blocks = (int)ceil_div64(B * 32, 256);
+      recon_rows_kernel<TAct><<<blocks, 256, 0, st>>>(w.u, a.want_loss ? a.x : nullptr, B, n.D, d->normalize_decoder, a.use_cos, gscale, a.x_hat,
+                                                      a.want_grads ? w.dxh : nullptr, a.want_loss ? w.sse_part : nullptr);
+      count_launch();
+      PSVAE_LAUNCH_CHECK("recon_rows_kernel");
+      n_sse_used = blocks;
+    }
+  }
+  if (a.want_loss) {
+    LossPartials lp;
+    memset(&lp, 0, sizeof(lp));
+    lp.sse = w.sse_part; lp.n_sse = n_sse_used;
+    lp.kl = w.kl_part; lp.n_kl = (int)w.n_kl;
+    lp.n_ce = (int)w.n_ce;
+    lp.n_heads = n.has_clf() ? d->clf_num_heads : 0;
+    for (int h = 0; h < lp.n_heads; ++h) { lp.nll[h] = w.nll_part[h]; lp.acc[h] = w.acc_part[h]; }
+    lp.recon_scale = a.use_cos ? 1.f / (float)B : 1.f / ((float)B * (float)n.D * 10.f);
+    lp.inv_b = 1.f / (float)B;
+    lp.kl_w = a.kl_w; lp.clf_w = a.clf_w;
+    finalize_losses_kernel<<<1, 32, 0, st>>>(lp, a.losses);
+    count_launch();
+    PSVAE_LAUNCH_CHECK("finalize_losses_kernel");
+  }
+  if (!a.want_grads) return 0;
+
+  // =================================== backward ===================================
+  float* G = a.grads;
+  if (d->total_numel > d->vae_numel)
+    PSVAE_CUDA(cudaMemsetAsync(G + d->vae_numel, 0, (size_t)(d->total_numel - d->vae_numel) * sizeof(float), st));
+
+  // ---- classifier backward -> dmu_clf
+  const float* dmu_clf = nullptr;
+  if (n.has_clf()) {
+    const int T = d->clf_num_trunk;
+    const float* featp = T > 0 ? w.clf_act[T - 1] : mu;
+    for (int h = 0; h < d->clf_num_heads; ++h) {
+      const int C = d->clf_head_classes[h];
+      PSVAE_TRY(wgrad_clf<TAct>(w.logits[h], C, featp, feat_dim, B, C, feat_dim, G + d->clf_head_w[h], G + d->clf_head_b[h], w, st));
+    }
+    if (T == 0) {
+      for (int h = 0; h < d->clf_num_heads; ++h)
+        PSVAE_TRY(clf_dgrad(ACT_NONE, w.logits[h], d->clf_head_classes[h], P + d->clf_head_w[h], n.L, nullptr, w.dmu_clf, h > 0 ? 1.f : 0.f, B, st));
+    } else {
+      float* cur = w.clf_g[0];
+      float* nxt = w.clf_g[1];
+      for (int h = 0; h < d->clf_num_heads; ++h)   // dU_{T-1} = sum_h (dlogits_h W_h) .* act'(A_{T-1})
+        PSVAE_TRY(clf_dgrad(d->clf_activation, w.logits[h], d->clf_head_classes[h], P + d->clf_head_w[h], d->clf_hidden, w.clf_act[T - 1], cur,
+                            h > 0 ? 1.f : 0.f, B, st));
+      for (int t = T - 1; t >= 0; --t) {
+        const float* ain = t == 0 ? mu : w.clf_act[t - 1];
+        const int in_dim = n.clf_trunk_in(t);
+        PSVAE_TRY(wgrad_clf<TAct>(cur, d->clf_hidden, ain, in_dim, B, d->clf_hidden, in_dim, G + d->clf_trunk_w[t], G + d->clf_trunk_b[t], w, st));
+        if (t > 0) {
+          PSVAE_TRY(clf_dgrad(d->clf_activation, cur, d->clf_hidden, P + d->clf_trunk_w[t], in_dim, w.clf_act[t - 1], nxt, 0.f, B, st));
+          float* tmp = cur; cur = nxt; nxt = tmp;
+        } else {
+          PSVAE_TRY(clf_dgrad(ACT_NONE, cur, d->clf_hidden, P + d->clf_trunk_w[0], n.L, nullptr, w.dmu_clf, 0.f, B, st));
+        }
+      }
+    }
+    dmu_clf = w.dmu_clf;
+  }
+
+  // ---- decoder backward: dY starts as d loss / d (decoder output)
+  {
+    const TAct* dY = w.dxh;
+    int out_dim = n.D;
+    int pp = 0;
+    for (int j = n.nh; j >= 0; --j) {
+      const TAct* ain = j == 0 ? w.z : w.hd[j - 1];
+      const int in_dim = n.dec_in(j);
+      PSVAE_TRY(wgrad<TAct>(dY, out_dim, ain, in_dim, B, out_dim, in_dim, G + d->dec_w[j], G + d->dec_b[j], w, st));
+      if (j > 0) {
+        EpiActGrad<TAct, TAct, ACT_RELU> e{w.hd[j - 1], n.H, w.gd[pp], n.H, 0.f, nullptr};
+        PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, out_dim, Wt + d->dec_w[j], in_dim, B, in_dim, out_dim, 1, true, e, st)));
+        dY = w.gd[pp];
+        out_dim = n.H;
+        pp ^= 1;
+      } else {
+        EpiStore e{w.dz, n.L, 0, 1.f, 0.f, nullptr};
+        PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, out_dim, Wt + d->dec_w[0], n.L, B, n.L, out_dim, 1, true, e, st)));
+      }
+    }
+  }
+  // ---- through the reparameterisation and the KL term
+  latent_bwd_kernel<TAct><<<ew_grid(B * n.L / 4), 256, 0, st>>>(w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, dmu_clf, a.kl_w / (float)B,
+                                                                w.dmu, w.dls);
+  count_launch();
+  PSVAE_LAUNCH_CHECK("latent_bwd_kernel");
+
+  // ---- encoders backward
+  {
+    int pp = 0;
+    // last layer: two separate GEMM pairs (mu / sigma)
+    for (int s = 0; s < 2; ++s) {
+      const TAct* dY = s == 0 ? w.dmu : w.dls;
+      PSVAE_TRY(wgrad<TAct>(dY, n.L, w.he[n.nh - 1] + s * n.H, 2 * n.H, B, n.L, n.H, G + d->enc_w[n.nh] + (int64_t)s * n.L * n.H,
+                            G + d->enc_b[n.nh] + s * n.L, w, st));
+      EpiActGrad<TAct, TAct, ACT_RELU> e{w.he[n.nh - 1] + s * n.H, 2 * n.H, w.ge[pp] + s * n.H, 2 * n.H, 0.f, nullptr};
+      PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, n.L, Wt + d->enc_w[n.nh] + (int64_t)s * n.L * n.H, n.H, B, n.H, n.L, 1, true, e, st)));
+    }
+    for (int j = n.nh - 1; j >= 1; --j) {
+      for (int s = 0; s < 2; ++s) {
+        const TAct* dY = w.ge[pp] + s * n.H;
+        PSVAE_TRY(wgrad<TAct>(dY, 2 * n.H, w.he[j - 1] + s * n.H, 2 * n.H, B, n.H, n.H, G + d->enc_w[j] + (int64_t)s * n.H * n.H,
+                              G + d->enc_b[j] + s * n.H, w, st));
+        EpiActGrad<TAct, TAct, ACT_RELU> e{w.he[j - 1] + s * n.H, 2 * n.H, w.ge[pp ^ 1] + s * n.H, 2 * n.H, 0.f, nullptr};
+        PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, 2 * n.H, Wt + d->enc_w[j] + (int64_t)s * n.H * n.H, n.H, B, n.H, n.H, 1, true, e, st)));
+      }
+      pp ^= 1;
+    }
+    // layer 0: both encoders in one wgrad ([2H, D]); x needs no gradient
+    PSVAE_TRY(wgrad<TAct>(w.ge[pp], 2 * n.H, xa, n.D, B, 2 * n.H, n.D, G + d->enc_w[0], G + d->enc_b[0], w, st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// decode / sampling
+// ------------------------------------------------------------------------------------------------
+template <typename TAct>
+static int run_decode(const psvae_model_desc* d, const float* params, const bf16* shadow, const float* z, uint64_t seed, uint64_t offset, int64_t row0,
+                      int64_t rows, float* x_hat, float* z_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  PSVAE_TRY(tc_device_check());
+  Net n(d);
+  if (rows <= 0) { set_error("rows=%lld must be positive", (long long)rows); return -2; }
+  if (!params || !x_hat) { set_error("params and x_hat must not be NULL"); return -1; }
+  if (sizeof(TAct) == 2 && !shadow) { set_error("PSVAE_BF16 needs the bf16 shadow copy of the parameters (psvae_refresh_shadow)"); return -1; }
+  const int64_t chunk = rows < g_opt.decode_chunk ? rows : g_opt.decode_chunk;
+  StepBufs<TAct> w;
+  {
+    Bump sz(nullptr);
+    StepBufs<TAct> tmp;
+    plan<TAct>(d, chunk, PSVAE_MODE_DECODE, sz, tmp);
+    if (sz.used > ws_bytes || !ws) {
+      set_error("workspace too small: need %lld bytes, got %lld", (long long)sz.used, (long long)ws_bytes);
+      return -2;
+    }
+    Bump b(ws);
+    plan<TAct>(d, chunk, PSVAE_MODE_DECODE, b, w);
+  }
+  const TAct* Wt;
+  if constexpr (sizeof(TAct) == 2) Wt = shadow; else Wt = params;
+  for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
+    const int64_t m = rows - r0 < chunk ? rows - r0 : chunk;
+    const int64_t nel = m * n.L;
+    const TAct* zin;
+    if (z) {
+      if constexpr (sizeof(TAct) == 2) {
+        cast_bf16_kernel<<<ew_grid(nel / 8), 256, 0, st>>>(z + r0 * n.L, w.z, nel);
+        count_launch();
+        PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
+        zin = w.z;
+      } else {
+        zin = z + r0 * n.L;
+      }
+      if (z_out && z_out != z) PSVAE_CUDA(cudaMemcpyAsync(z_out + r0 * n.L, z + r0 * n.L, (size_t)nel * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    } else {
+      const int64_t first = (row0 + r0) * n.L;
+      if (z_out) {
+        philox_normal_kernel<float><<<ew_grid(nel / 4), 256, 0, st>>>(z_out + r0 * n.L, nel, seed, offset, first);
+        count_launch();
+        PSVAE_LAUNCH_CHECK("philox_normal_kernel");
+        if constexpr (sizeof(TAct) == 2) {
+          cast_bf16_kernel<<<ew_grid(nel / 8), 256, 0, st>>>(z_out + r0 * n.L, w.z, nel);
+          count_launch();
+          PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
+          zin = w.z;
+        } else {
+          zin = z_out + r0 * n.L;
+        }
+      } else {
+        philox_normal_kernel<TAct><<<ew_grid(nel / 4), 256, 0, st>>>(w.z, nel, seed, offset, first);
+        count_launch();
+        PSVAE_LAUNCH_CHECK("philox_normal_kernel");
+        zin = w.z;
+      }
+    }
+    float* out = x_hat + r0 * n.D;
+    EpiBiasAct<float, ACT_NONE> e{params + d->dec_b[n.nh], out, n.D, nullptr};
+    PSVAE_TRY(decoder_forward<TAct>(n, Wt, params, zin, w.hd, m, e, st));
+    if (d->normalize_decoder) {
+      row_normalize_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, st>>>(out, m, n.D);
+      count_launch();
+      PSVAE_LAUNCH_CHECK("row_normalize_kernel");
+    }
+  }
+  return 0;
+}
+
+}  // namespace psvae
+
+// =================================================================================================
+// extern "C"
+// =================================================================================================
+using namespace psvae;
+
+extern "C" {
+
+int psvae_abi_version(void) { return PSVAE_ABI_VERSION; }
+const char* psvae_last_error_string(void) { return g_err; }
+int64_t psvae_launch_count(void) { return g_launches.load(); }
+
+int psvae_set_option(const char* name, int64_t value) {
+  if (!name) { set_error("option name is NULL"); return -1; }
+  if (!strcmp(name, "decode_chunk")) { if (value < 128) value = 128; g_opt.decode_chunk = value; return 0; }
+  if (!strcmp(name, "wgrad_split_cap")) { if (value < 1) value = 1; g_opt.wgrad_split_cap = value; return 0; }
+  if (!strcmp(name, "colsum_rows")) { if (value < 8) value = 8; g_opt.colsum_rows = value; return 0; }
+  if (!strcmp(name, "tc_force_bn")) {
+    if (value != 0 && value != 64 && value != 128 && value != 256) { set_error("tc_force_bn must be 0, 64, 128 or 256"); return -2; }
+    g_opt.tc_force_bn = value; return 0;
+  }
+  if (!strcmp(name, "tc_grid_limit")) { g_opt.tc_grid_limit = value < 0 ? 0 : value; return 0; }
+  set_error("unknown option '%s'", name);
+  return -2;
+}
+int64_t psvae_get_option(const char* name) {
+  if (!name) return -1;
+  if (!strcmp(name, "decode_chunk")) return g_opt.decode_chunk;
+  if (!strcmp(name, "wgrad_split_cap")) return g_opt.wgrad_split_cap;
+  if (!strcmp(name, "colsum_rows")) return g_opt.colsum_rows;
+  if (!strcmp(name, "tc_force_bn")) return g_opt.tc_force_bn;
+  if (!strcmp(name, "tc_grid_limit")) return g_opt.tc_grid_limit;
+  return -1;
+}
+
+int psvae_model_desc_init(psvae_model_desc* desc, int32_t input_dim, int32_t latent_dim, int32_t hidden_dim, int32_t num_hidden,
+                          int32_t normalize_decoder, int32_t clf_num_trunk, int32_t clf_hidden, int32_t clf_activation, int32_t clf_num_heads,
+                          int32_t clf_single_label, const int32_t* clf_head_classes) {
+  if (!desc) { set_error("desc is NULL"); return -1; }
+  memset(desc, 0, sizeof(*desc));
+  desc->input_dim = input_dim; desc->latent_dim = latent_dim; desc->hidden_dim = hidden_dim; desc->num_hidden = num_hidden;
+  desc->normalize_decoder = normalize_decoder ? 1 : 0;
+  desc->clf_num_trunk = clf_num_trunk; desc->clf_hidden = clf_hidden; desc->clf_activation = clf_activation;
+  desc->clf_num_heads = clf_num_heads; desc->clf_single_label = clf_single_label ? 1 : 0;
+  if (clf_num_heads > 0 && clf_num_heads <= PSVAE_MAX_CLF_HEADS) {
+    if (!clf_head_classes) { set_error("clf_head_classes is NULL"); return -1; }
+    for (int h = 0; h < clf_num_heads; ++h) desc->clf_head_classes[h] = clf_head_classes[h];
+  }
+  PSVAE_TRY(check_desc(desc, PSVAE_FP32));
+  Net n(desc);
+  int64_t off = 0;
+  auto put = [&](int64_t numel) { const int64_t o = off; off = align_up64(off + numel, 8); return o; };
+  for (int j = 0; j <= n.nh; ++j) {
+    desc->enc_w[j] = put(2ll * n.enc_out(j) * n.enc_in(j));
+    desc->enc_b[j] = put(2ll * n.enc_out(j));
+  }
+  for (int j = 0; j <= n.nh; ++j) {
+    desc->dec_w[j] = put((int64_t)n.dec_out(j) * n.dec_in(j));
+    desc->dec_b[j] = put(n.dec_out(j));
+  }
+  desc->vae_numel = off;
+  if (clf_num_heads > 0) {
+    for (int t = 0; t < clf_num_trunk; ++t) {
+      desc->clf_trunk_w[t] = put((int64_t)clf_hidden * n.clf_trunk_in(t));
+      desc->clf_trunk_b[t] = put(clf_hidden);
+    }
+    for (int h = 0; h < clf_num_heads; ++h) {
+      desc->clf_head_w[h] = put((int64_t)desc->clf_head_classes[h] * n.clf_feat());
+      desc->clf_head_b[h] = put(desc->clf_head_classes[h]);
+    }
+  }
+  desc->total_numel = align_up64(off, 64);
+  return 0;
+}
+
+int64_t psvae_workspace_bytes(const psvae_model_desc* desc, int64_t rows, int32_t precision, int32_t mode) {
+  if (check_desc(desc, precision) != 0) return -1;
+  if (rows <= 0 || mode < 0 || mode > 2) { set_error("bad rows/mode"); return -1; }
+  if (mode == PSVAE_MODE_DECODE && rows > g_opt.decode_chunk) rows = g_opt.decode_chunk;
+  Bump b(nullptr);
+  if (precision == PSVAE_BF16) { StepBufs<bf16> w; plan<bf16>(desc, rows, mode, b, w); }
+  else { StepBufs<float> w; plan<float>(desc, rows, mode, b, w); }
+  return b.used + 256;
+}
+int64_t psvae_shadow_bytes(const psvae_model_desc* desc) { return desc ? desc->total_numel * (int64_t)sizeof(bf16) : -1; }
+
+int64_t psvae_flops_per_sample(const psvae_model_desc* desc, int32_t mode) {
+  if (!desc) return -1;
+  Net n(desc);
+  int64_t enc = 0, enc_first = 0, dec = 0;
+  for (int j = 0; j <= n.nh; ++j) {
+    enc += 2ll * n.enc_out(j) * n.enc_in(j);
+    dec += (int64_t)n.dec_out(j) * n.dec_in(j);
+  }
+  enc_first = 2ll * n.enc_out(0) * n.enc_in(0);
+  int64_t clf = 0;
+  if (n.has_clf()) {
+    for (int t = 0; t < desc->clf_num_trunk; ++t) clf += (int64_t)desc->clf_hidden * n.clf_trunk_in(t);
+    for (int h = 0; h < desc->clf_num_heads; ++h) clf += (int64_t)desc->clf_head_classes[h] * n.clf_feat();
+  }
+  if (mode == 2) return 2 * dec;
+  if (mode == 1) return 2 * (enc + dec);
+  // train: forward + wgrad (same MACs as forward) + dgrad (forward minus the encoders' first layers); classifier fwd + wgrad + dgrad
+  return 2 * ((enc + dec) * 3 - enc_first + 3 * clf);
+}
+
+int psvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                    int64_t step, float grad_scale, void* shadow_bf16, void* stream) {
+  PSVAE_TRY(tc_device_check());
+  if (!p || !g || !m || !v) { set_error("p, g, m, v must not be NULL"); return -1; }
+  if (n <= 0) return 0;
+  if (step < 1) { set_error("step=%lld must be >= 1 (count after increment)", (long long)step); return -2; }
+  if (((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) != 0) {
+    set_error("Adam buffers must be 16-byte aligned");
+    return -2;
+  }
+  // host scalars exactly as torch's single-tensor Adam computes them (python doubles, torch/optim/adam.py:476-547)
+  const double bc1 = 1.0 - pow((double)beta1, (double)step);
+  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  AdamArgs a;
+  a.lr_step = (float)((double)lr / bc1);
+  a.bc2_sqrt = (float)sqrt(bc2);
+  a.beta1 = beta1; a.beta2 = beta2;
+  a.one_minus_beta1 = (float)(1.0 - (double)beta1);
+  a.one_minus_beta2 = (float)(1.0 - (double)beta2);
+  a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = grad_scale;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  adam_kernel<<<ew_grid(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, a, static_cast<bf16*>(shadow_bf16));
+  count_launch();
+  PSVAE_LAUNCH_CHECK("adam_kernel");
+  return 0;
+}
+
+int psvae_philox_uint32(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, int64_t first_elem, void* stream) {
+  PSVAE_TRY(tc_device_check());
+  if (!out) { set_error("out is NULL"); return -1; }
+  if (n <= 0) return 0;
+  philox_u32_kernel<<<ew_grid(n / 4 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, offset, first_elem);
+  count_launch();
+  PSVAE_LAUNCH_CHECK("philox_u32_kernel");
+  return 0;
+}
+
+int psvae_philox_normal(float* out, int64_t n_rows, int32_t n_cols, uint64_t seed, uint64_t offset, int64_t row0, void* stream) {
+  PSVAE_TRY(tc_device_check());
+  if (!out) { set_error("out is NULL"); return -1; }
+  if (n_rows <= 0) return 0;
+  if (n_cols <= 0 || n_cols % 4) { set_error("n_cols=%d must be a positive multiple of 4", n_cols); return -2; }
+  const int64_t n = n_rows * n_cols;
+  philox_normal_kernel<float><<<ew_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, offset, row0 * n_cols);
+  count_launch();
+  PSVAE_LAUNCH_CHECK("philox_normal_kernel");
+  return 0;
+}
+
+int psvae_refresh_shadow(const psvae_model_desc* desc, const float* params, void* shadow_bf16, void* stream) {
+  PSVAE_TRY(tc_device_check());
+  if (!desc || !params || !shadow_bf16) { set_error("desc, params, shadow must not be NULL"); return -1; }
+  const int64_t n = desc->total_numel;
+  cast_bf16_kernel<<<ew_grid(n / 8 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, static_cast<bf16*>(shadow_bf16), n);
+  count_launch();
+  PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
+  return 0;
+}
+
+int psvae_train_fwd_bwd(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const float* x, const int64_t* y,
+                        const float* eps, uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, float kl_weight, float clf_weight,
+                        int32_t use_cos_loss, int32_t compute_grads, int32_t precision, float* x_hat, float* mu, float* log_sigma, float* losses,
+                        void* workspace, int64_t workspace_bytes, void* stream) {
+  PSVAE_TRY(check_desc(desc, precision));
+  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, x, y, eps, seed, offset, row0, rows, kl_weight, clf_weight,
+             use_cos_loss ? 1 : 0, 1, compute_grads ? 1 : 0, x_hat, mu, log_sigma, losses, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)};
+  return precision == PSVAE_BF16 ? run_step<bf16>(a) : run_step<float>(a);
+}
+
+int psvae_forward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, const float* x, const float* eps, uint64_t seed,
+                  uint64_t offset, int64_t row0, int64_t rows, int32_t precision, float* x_hat, float* mu, float* log_sigma, void* workspace,
+                  int64_t workspace_bytes, void* stream) {
+  PSVAE_TRY(check_desc(desc, precision));
+  if (!x_hat) { set_error("x_hat must not be NULL"); return -1; }
+  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), nullptr, x, nullptr, eps, seed, offset, row0, rows, 0.f, 0.f,
+             0, 0, 0, x_hat, mu, log_sigma, nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)};
+  return precision == PSVAE_BF16 ? run_step<bf16>(a) : run_step<float>(a);
+}
+
+int psvae_decode(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, const float* z, uint64_t seed, uint64_t offset,
+                 int64_t row0, int64_t rows, int32_t precision, float* x_hat, float* z_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  PSVAE_TRY(check_desc(desc, precision));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return precision == PSVAE_BF16
+             ? run_decode<bf16>(desc, params, static_cast<const bf16*>(shadow_bf16), z, seed, offset, row0, rows, x_hat, z_out, workspace, workspace_bytes, st)
+             : run_decode<float>(desc, params, nullptr, z, seed, offset, row0, rows, x_hat, z_out, workspace, workspace_bytes, st);
+}
+
+int psvae_langevin(const psvae_model_desc* desc, const float* params, float* z_io, int64_t rows, const int32_t* targets_host, float step_size,
+                   int32_t num_steps, float noise_weight, uint64_t seed, uint64_t offset0, int64_t row0, int32_t init_from_philox,
+                   const float* noise, float* history, float* stats, void* stream) {
+  PSVAE_TRY(check_desc(desc, PSVAE_FP32));
+  PSVAE_TRY(tc_device_check());
+  if (!params || !z_io || !targets_host) { set_error("params, z_io, targets must not be NULL"); return -1; }
+  if (desc->clf_num_heads <= 0) { set_error("conditional synthesis needs a latent classifier (ps_vae/inference.py:80)"); return -2; }
+  if (rows <= 0) { set_error("rows must be positive"); return -2; }
+  if (num_steps < 0) { set_error("num_steps must be >= 0"); return -2; }
+  Net n(desc);
+  LangevinClf c;
+  memset(&c, 0, sizeof(c));
+  c.L = n.L; c.n_trunk = desc->clf_num_trunk; c.hidden = desc->clf_num_trunk ? desc->clf_hidden : 0;
+  c.act = desc->clf_activation; c.n_heads = desc->clf_num_heads;
+  int any = 0, off = 0;
+  for (int t = 0; t < c.n_trunk; ++t) {
+    c.g_trunk_w[t] = desc->clf_trunk_w[t]; c.g_trunk_b[t] = desc->clf_trunk_b[t];
+    c.s_trunk_w[t] = off; off += desc->clf_hidden * n.clf_trunk_in(t);
+    c.s_trunk_b[t] = off; off += desc->clf_hidden;
+  }
+  for (int h = 0; h < c.n_heads; ++h) {
+    c.head_classes[h] = desc->clf_head_classes[h];
+    c.targets[h] = targets_host[h];
+    if (c.targets[h] >= c.head_classes[h]) { set_error("target %d of head %d is out of range (%d classes)", c.targets[h], h, c.head_classes[h]); return -2; }
+    if (c.targets[h] >= 0) any = 1;
+    c.g_head_w[h] = desc->clf_head_w[h]; c.g_head_b[h] = desc->clf_head_b[h];
+    c.s_head_w[h] = off; off += c.head_classes[h] * n.clf_feat();
+    c.s_head_b[h] = off; off += c.head_classes[h];
+  }
+  for (int h = c.n_heads; h < 4; ++h) c.targets[h] = -1;
+  if (!any) { set_error("classifier_target selects no head"); return -2; }
+  c.w_floats = off;
+  const size_t smem = langevin_smem_bytes(c);
+  if (smem > 227 * 1024) { set_error("classifier too large for the Langevin kernel's shared memory (%zu bytes)", smem); return -2; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  PSVAE_CUDA(cudaFuncSetAttribute(langevin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (stats && num_steps > 0) PSVAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)num_steps, st));
+  const unsigned grid = (unsigned)ceil_div64(rows, LG_TILE);
+  langevin_kernel<<<grid, LG_THREADS, smem, st>>>(c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox,
+                                                  noise, history, stats);
+  count_launch();
+  PSVAE_LAUNCH_CHECK("langevin_kernel");
+  return 0;
+}
+
+int psvae_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, float* c, int64_t m, int32_t n, int64_t k, int32_t a_mn, int32_t b_mn,
+                    int32_t relu, int32_t split_k, void* workspace, int64_t workspace_bytes, void* stream) {
+  PSVAE_TRY(tc_device_check());
+  if (!a_bf16 || !b_bf16 || !c) { set_error("a, b, c must not be NULL"); return -1; }
+  if (m <= 0 || n <= 0 || k <= 0) { set_error("m, n, k must be positive"); return -2; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bf16* A = static_cast<const bf16*>(a_bf16);
+  const bf16* B = static_cast<const bf16*>(b_bf16);
+  TcOperand oa{A, m, a_mn ? m : k, a_mn != 0};
+  TcOperand ob{B, (int64_t)n, b_mn ? (int64_t)n : k, b_mn != 0};
+  const int fbn = (int)g_opt.tc_force_bn;
+  if (split_k > 1) {
+    const int64_t kb = ceil_div64(k, TC_BK);
+    int64_t s = split_k > kb ? kb : split_k;
+    const int64_t per = ceil_div64(kb, s);
+    s = ceil_div64(kb, per);
+    if (!workspace || workspace_bytes < (int64_t)(s * m * n * (int64_t)sizeof(float))) {
+      set_error("split-K needs %lld bytes of workspace", (long long)(s * m * n * (int64_t)sizeof(float)));
+      return -2;
+    }
+    float* part = static_cast<float*>(workspace);
+    EpiStore e{part, n, m * n, 1.f, 0.f, nullptr};
+    int r;
+    if (a_mn && b_mn) r = gemm_tc_launch<true, true>(oa, ob, m, n, k, (int)s, e, st, fbn);
+    else if (!a_mn && b_mn) r = gemm_tc_launch<false, true>(oa, ob, m, n, k, (int)s, e, st, fbn);
+    else if (!a_mn && !b_mn) r = gemm_tc_launch<false, false>(oa, ob, m, n, k, (int)s, e, st, fbn);
+    else { set_error("a_mn && !b_mn is not used by this library"); return -2; }
+    PSVAE_TRY(r);
+    return launch_reduce(part, m * n, (int)s, c, st);
+  }
+  if (a_mn && b_mn) {
+    EpiStore e{c, n, 0, 1.f, 0.f, nullptr};
+    return gemm_tc_launch<true, true>(oa, ob, m, n, k, 1, e, st, fbn);
+  }
+  if (a_mn) { set_error("a_mn && !b_mn is not used by this library"); return -2; }
+  if (b_mn) {
+    if (relu || bias) { set_error("bias/relu are only wired for the K-major x K-major form"); return -2; }
+    EpiStore e{c, n, 0, 1.f, 0.f, nullptr};
+    return gemm_tc_launch<false, true>(oa, ob, m, n, k, 1, e, st, fbn);
+  }
+  if (relu) {
+    EpiBiasAct<float, ACT_RELU> e{bias, c, n, nullptr};
+    return gemm_tc_launch<false, false>(oa, ob, m, n, k, 1, e, st, fbn);
+  }
+  EpiBiasAct<float, ACT_NONE> e{bias, c, n, nullptr};
+  return gemm_tc_launch<false, false>(oa, ob, m, n, k, 1, e, st, fbn);
+}
+
+int psvae_gemm_fp32(const float* a, const float* b, const float* bias, float* c, int64_t m, int32_t n, int64_t k, int32_t a_mn, int32_t b_mn,
+                    int32_t relu, void* stream) {
+  PSVAE_TRY(tc_device_check());
+  if (!a || !b || !c) { set_error("a, b, c must not be NULL"); return -1; }
+  if (m <= 0 || n <= 0 || k <= 0) { set_error("m, n, k must be positive"); return -2; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  SgemmOperand oa{a, a_mn ? 1 : k, a_mn ? m : 1};
+  SgemmOperand ob{b, b_mn ? 1 : k, b_mn ? (int64_t)n : 1};
+  const bool vec = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0) && (!bias || (reinterpret_cast<uintptr_t>(bias) & 15) == 0);
+  if (relu) {
+    EpiBiasAct<float, ACT_RELU> e{bias, c, n, nullptr};
+    return sgemm_launch(oa, ob, m, n, k, 1, vec, e, st);
+  }
+  EpiBiasAct<float, ACT_NONE> e{bias, c, n, nullptr};
+  return sgemm_launch(oa, ob, m, n, k, 1, vec, e, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,425 @@
+"""Host side of the hot path: flat parameter arena + the calls into the C-ABI.
+
+The reference keeps 18 (+2..6) separate ``nn.Parameter`` tensors and lets autograd / ``torch.optim.Adam`` /
+DDP walk them (ps_vae/lightning.py:204-205, ps_vae/training.py:78).  Here every parameter of the VAE and of
+the latent classifier is a *view* into one flat fp32 buffer whose layout ``psvae_model_desc_init`` defines,
+with sibling flat buffers for the gradients (and, in optim.py, Adam's moments).  State-dict keys, shapes and
+values are unchanged -- the modules still own ordinary ``nn.Parameter`` objects -- but the fused train step,
+the Adam update and the data-parallel all-reduce each become one pass over one buffer.
+
+``HotPath`` is the object the drop-in modules (model.py, lightning.py, inference.py) delegate to.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+PRECISIONS = {"fp32": L.FP32, "float32": L.FP32, "32": L.FP32, "highest": L.FP32,
+              "bf16": L.BF16, "bfloat16": L.BF16, "medium": L.BF16, "bf16-mixed": L.BF16}
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class ParamArena:
+    """One flat fp32 buffer holding every parameter; the modules' ``nn.Parameter``s are views into it."""
+
+    def __init__(self, desc: L.ModelDesc, entries: Sequence[Tuple[nn.Parameter, int]]):
+        self.desc = desc
+        self.entries: List[Tuple[nn.Parameter, int]] = list(entries)
+        self.numel = int(desc.total_numel)
+        self.flat: Optional[torch.Tensor] = None
+        self._gbuf: List[Optional[torch.Tensor]] = [None, None]   # two gradient buffers (see stage_buffer)
+        self.shadow: Optional[torch.Tensor] = None               # bf16 operand copy for the tcgen05 engine
+        self._shadow_versions: Optional[Tuple[int, ...]] = None
+        self._shadow_epoch = -1
+        self.epoch = 0    # bumped whenever the library itself rewrites the parameters (fused Adam)
+        self._attach(self.entries[0][0].device)
+
+    # ---- layout ---------------------------------------------------------------------------------
+    def _attach(self, device: torch.device) -> None:
+        flat = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        with torch.no_grad():
+            for p, off in self.entries:
+                n = p.numel()
+                flat[off:off + n].copy_(p.detach().reshape(-1).to(device=device, dtype=torch.float32))
+                p.data = flat[off:off + n].view(p.shape)
+        self.flat = flat
+        self._gbuf = [None, None]
+        self.shadow = None
+        self._shadow_versions = None
+
+    def attached(self) -> bool:
+        base = self.flat.data_ptr()
+        dev = self.flat.device
+        for p, off in self.entries:
+            if p.device != dev or p.dtype != torch.float32 or p.data_ptr() != base + 4 * off or not p.is_contiguous():
+                return False
+        return True
+
+    def ensure(self) -> torch.Tensor:
+        """(Re)build the arena if a ``.to()`` / ``.double()`` / foreign optimiser moved the parameters out of it."""
+        if not self.attached():
+            p0 = self.entries[0][0]
+            if p0.dtype != torch.float32:
+                raise TypeError(f"pseudo_speaker_vae_b200 kernels run on float32 parameters, got {p0.dtype}")
+            self._attach(p0.device)
+        return self.flat
+
+    @property
+    def device(self) -> torch.device:
+        return self.entries[0][0].device
+
+    # ---- gradients ------------------------------------------------------------------------------
+    def stage_buffer(self) -> torch.Tensor:
+        """A flat gradient buffer no live ``p.grad`` aliases (gradient accumulation keeps the other one alive)."""
+        dev = self.flat.device
+        live = None
+        for p, _ in self.entries:
+            if p.grad is not None:
+                live = p.grad.data_ptr()
+                break
+        for i in range(2):
+            g = self._gbuf[i]
+            if g is None or g.device != dev:
+                g = self._gbuf[i] = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+            if live is None or not (g.data_ptr() <= live < g.data_ptr() + 4 * self.numel):
+                return g
+        raise RuntimeError("both gradient buffers are aliased by live .grad tensors")
+
+    def grad_views(self, gflat: torch.Tensor) -> List[torch.Tensor]:
+        return [gflat[off:off + p.numel()].view(p.shape) for p, off in self.entries]
+
+    def flat_grad(self) -> Optional[torch.Tensor]:
+        """The flat buffer the current ``.grad`` tensors live in (None if they do not all alias one buffer)."""
+        for g in self._gbuf:
+            if g is None:
+                continue
+            base = g.data_ptr()
+            ok = True
+            for p, off in self.entries:
+                if p.requires_grad and (p.grad is None or p.grad.data_ptr() != base + 4 * off):
+                    ok = False
+                    break
+            if ok:
+                return g
+        return None
+
+    # ---- bf16 operand copy ----------------------------------------------------------------------
+    def shadow_ptr(self, desc_ref) -> int:
+        self.ensure()
+        versions = tuple(p._version for p, _ in self.entries)
+        if self.shadow is None or self.shadow.device != self.flat.device or versions != self._shadow_versions or self._shadow_epoch != self.epoch:
+            if self.shadow is None or self.shadow.device != self.flat.device:
+                self.shadow = torch.empty(self.numel, dtype=torch.bfloat16, device=self.flat.device)
+            L.check(L.lib().psvae_refresh_shadow(desc_ref, self.flat.data_ptr(), self.shadow.data_ptr(), _stream_ptr(self.flat.device)),
+                    "psvae_refresh_shadow")
+            self._shadow_versions = versions
+            self._shadow_epoch = self.epoch
+        return self.shadow.data_ptr()
+
+    def mark_shadow_current(self) -> None:
+        """Called by the fused Adam, which writes the bf16 copy itself."""
+        self._shadow_versions = tuple(p._version for p, _ in self.entries)
+        self._shadow_epoch = self.epoch
+
+
+class _FusedLoss(torch.autograd.Function):
+    """Gives ``loss.backward()`` its meaning: the gradients were already computed by the fused kernel call."""
+
+    @staticmethod
+    def forward(ctx, loss_value: torch.Tensor, gflat: torch.Tensor, arena: ParamArena, *params):
+        ctx.arena = arena
+        ctx.gflat = gflat
+        ctx.needs = [p.requires_grad for p in params]
+        return loss_value.clone()
+
+    @staticmethod
+    def backward(ctx, gout):
+        g = ctx.gflat
+        g.mul_(gout)     # d(total)/d(loss); a ones tensor for a plain loss.backward()
+        views = ctx.arena.grad_views(g)   # fresh views: AccumulateGrad adopts them without a copy
+        return (None, None, None) + tuple(v if need else None for v, need in zip(views, ctx.needs))
+
+
+class HotPath:
+    """Everything the drop-in modules ask of the CUDA library, for one (VAE [+ latent classifier]) pair."""
+
+    def __init__(self, vae: nn.Module, classifier: Optional[nn.Module] = None, precision: str = "fp32"):
+        self.vae = vae
+        self.classifier = classifier
+        self.set_precision(precision)
+        heads: List[int] = []
+        self.head_names: List[Optional[str]] = []
+        n_trunk, c_hidden, act, single = 0, 0, "relu", True
+        if classifier is not None:
+            n_trunk = classifier.num_trunk_linears
+            c_hidden = classifier.hidden_dim if n_trunk else 0
+            act = classifier.activation
+            single = classifier.single_label_mode
+            heads = list(classifier.head_classes)
+            self.head_names = list(classifier.head_names)
+            if classifier.input_dim != vae.latent_dim:
+                raise ValueError(f"classifier input_dim={classifier.input_dim} must equal the VAE latent_dim={vae.latent_dim}")
+        self.desc = L.make_desc(vae.input_dim, vae.latent_dim, vae.hidden_dim, vae.num_hidden_layers, vae.normalize_decoder,
+                                n_trunk, c_hidden, act, heads, single)
+        self._dref = C.byref(self.desc)
+        self.arena = ParamArena(self.desc, self._entries())
+        self._ws: Dict[torch.device, torch.Tensor] = {}
+        self._losses: Dict[torch.device, torch.Tensor] = {}
+        self.seed: Optional[int] = None
+        self.offset = 0            # Philox offset: one per stochastic call
+        self.row0 = 0              # global index of this rank's first row (data parallel: rank * local_batch)
+        self.flops_train = int(L.lib().psvae_flops_per_sample(self._dref, 0))
+        self.flops_forward = int(L.lib().psvae_flops_per_sample(self._dref, 1))
+        self.flops_decode = int(L.lib().psvae_flops_per_sample(self._dref, 2))
+
+    # ---- plumbing -------------------------------------------------------------------------------
+    def set_precision(self, precision: str) -> None:
+        key = str(precision).lower()
+        if key not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(set(PRECISIONS))}, got {precision!r}")
+        self.precision = PRECISIONS[key]
+        self.precision_name = "bf16" if self.precision == L.BF16 else "fp32"
+
+    def _entries(self) -> List[Tuple[nn.Parameter, int]]:
+        d, v = self.desc, self.vae
+        out: List[Tuple[nn.Parameter, int]] = []
+        mu_lin, sg_lin, dec_lin = v.linears("encoder_mu"), v.linears("encoder_sigma"), v.linears("decoder")
+        for j, (a, b) in enumerate(zip(mu_lin, sg_lin)):
+            out += [(a.weight, d.enc_w[j]), (b.weight, d.enc_w[j] + a.weight.numel()), (a.bias, d.enc_b[j]), (b.bias, d.enc_b[j] + a.bias.numel())]
+        for j, a in enumerate(dec_lin):
+            out += [(a.weight, d.dec_w[j]), (a.bias, d.dec_b[j])]
+        c = self.classifier
+        if c is not None:
+            for t, lin in enumerate(c.trunk_linears()):
+                out += [(lin.weight, d.clf_trunk_w[t]), (lin.bias, d.clf_trunk_b[t])]
+            for h, lin in enumerate(c.head_linears()):
+                out += [(lin.weight, d.clf_head_w[h]), (lin.bias, d.clf_head_b[h])]
+        return out
+
+    def parameters(self) -> List[nn.Parameter]:
+        return [p for p, _ in self.arena.entries]
+
+    def _device(self) -> torch.device:
+        dev = self.arena.device
+        if dev.type != "cuda":
+            raise RuntimeError(
+                f"pseudo_speaker_vae_b200 runs on a B200 only (module is on {dev}); move it with .to('cuda'). There is no CPU fallback.")
+        return dev
+
+    def _workspace(self, dev: torch.device, rows: int, mode: int) -> torch.Tensor:
+        need = int(L.lib().psvae_workspace_bytes(self._dref, rows, self.precision, mode))
+        if need < 0:
+            raise ValueError(L.last_error())
+        ws = self._ws.get(dev)
+        if ws is None or ws.numel() < need:
+            self._ws[dev] = ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        return ws
+
+    def _rng(self) -> Tuple[int, int]:
+        if self.seed is None:
+            self.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        off = self.offset
+        self.offset += 1
+        return self.seed, off
+
+    def manual_seed(self, seed: int, offset: int = 0) -> None:
+        self.seed, self.offset = int(seed) & 0xFFFFFFFFFFFFFFFF, int(offset)
+
+    def _shadow(self) -> Optional[int]:
+        return self.arena.shadow_ptr(self._dref) if self.precision == L.BF16 else None
+
+    @staticmethod
+    def _f32(t: torch.Tensor, dev: torch.device, what: str) -> torch.Tensor:
+        if t.device != dev:
+            raise ValueError(f"{what} is on {t.device}, the model on {dev}")
+        return t.detach().to(torch.float32).contiguous()
+
+    # ---- VAEModel.forward (ps_vae/model.py:38-63) -------------------------------------------------
+    def forward(self, x: torch.Tensor, eps: Optional[torch.Tensor] = None):
+        dev = self._device()
+        flat = self.arena.ensure()
+        if x.dim() != 2 or x.shape[1] != self.desc.input_dim:
+            raise ValueError(f"x must be [batch, {self.desc.input_dim}], got {tuple(x.shape)}")
+        x = self._f32(x, dev, "x")
+        B = x.shape[0]
+        D, Lz = self.desc.input_dim, self.desc.latent_dim
+        x_hat = torch.empty(B, D, dtype=torch.float32, device=dev)
+        mu = torch.empty(B, Lz, dtype=torch.float32, device=dev)
+        ls = torch.empty(B, Lz, dtype=torch.float32, device=dev)
+        if B == 0:
+            return x_hat, mu, ls
+        if eps is not None:
+            eps = self._f32(eps, dev, "eps")
+            if tuple(eps.shape) != (B, Lz):
+                raise ValueError(f"eps must be [{B}, {Lz}], got {tuple(eps.shape)}")
+            seed, off = 0, 0
+        else:
+            seed, off = self._rng()
+        ws = self._workspace(dev, B, L.MODE_FORWARD)
+        rc = L.lib().psvae_forward(self._dref, flat.data_ptr(), self._shadow(), x.data_ptr(), L.ptr(eps), seed, off, self.row0, B, self.precision,
+                                   x_hat.data_ptr(), mu.data_ptr(), ls.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        L.check(rc, "psvae_forward")
+        return x_hat, mu, ls
+
+    # ---- VAEModel.decode (model.py:65-69) / unconditional_synthesis (inference.py:22-25) ----------
+    def decode(self, z: Optional[torch.Tensor], num_samples: Optional[int] = None, out: Optional[torch.Tensor] = None,
+               return_z: bool = False, row0: Optional[int] = None):
+        dev = self._device()
+        flat = self.arena.ensure()
+        D, Lz = self.desc.input_dim, self.desc.latent_dim
+        if z is not None:
+            if z.dim() != 2 or z.shape[1] != Lz:
+                raise ValueError(f"z must be [n, {Lz}], got {tuple(z.shape)}")
+            z = self._f32(z, dev, "z")
+            N = z.shape[0]
+            seed, off = 0, 0
+        else:
+            N = int(num_samples)
+            seed, off = self._rng()
+        if out is None:
+            out = torch.empty(N, D, dtype=torch.float32, device=dev)
+        elif tuple(out.shape) != (N, D) or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+            raise ValueError(f"out must be a contiguous float32 [{N}, {D}] tensor on {dev}")
+        z_out = torch.empty(N, Lz, dtype=torch.float32, device=dev) if (return_z and z is None) else None
+        if N > 0:
+            ws = self._workspace(dev, N, L.MODE_DECODE)
+            rc = L.lib().psvae_decode(self._dref, flat.data_ptr(), self._shadow(), L.ptr(z), seed, off, self.row0 if row0 is None else row0, N,
+                                      self.precision, out.data_ptr(), L.ptr(z_out), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            L.check(rc, "psvae_decode")
+        if return_z:
+            return out, (z if z is not None else z_out)
+        return out
+
+    # ---- training_step / validation_step (lightning.py:67-197) + backward -------------------------
+    def pack_labels(self, y, rows: int, dev: torch.device) -> Optional[torch.Tensor]:
+        """int64 [num_heads][rows]; single-label: the tensor itself; multi-label: {label: tensor} in head order."""
+        if self.classifier is None:
+            return None
+        if isinstance(y, dict):
+            if self.classifier.single_label_mode:
+                raise ValueError("labels must be a tensor for a single-label classifier")
+            cols = [y[name] for name in self.head_names]
+            y = torch.stack([c.to(device=dev, dtype=torch.int64).reshape(-1) for c in cols], 0)
+        else:
+            if not self.classifier.single_label_mode:
+                raise ValueError("labels must be a dict {label: tensor} for a multi-label classifier")
+            y = y.to(device=dev, dtype=torch.int64).reshape(1, -1)
+        if y.shape[1] != rows:
+            raise ValueError(f"labels have {y.shape[1]} rows, x has {rows}")
+        return y.contiguous()
+
+    def step(self, x: torch.Tensor, y=None, eps: Optional[torch.Tensor] = None, *, kl_weight: float = 1.0, clf_weight: float = 1.0,
+             use_cos_loss: bool = False, compute_grads: bool = True, grads: Optional[torch.Tensor] = None, want_outputs: bool = False):
+        """One fused forward(+backward).  Returns (losses[16] device tensor, flat grads or None, outputs or None).
+
+        losses slots: _lib.LOSS_*; nothing here synchronises with the host."""
+        dev = self._device()
+        flat = self.arena.ensure()
+        D, Lz = self.desc.input_dim, self.desc.latent_dim
+        if x.dim() != 2 or x.shape[1] != D:
+            raise ValueError(f"x must be [batch, {D}], got {tuple(x.shape)}")
+        x = self._f32(x, dev, "x")
+        B = x.shape[0]
+        if B == 0:
+            raise ValueError("empty batch")
+        yy = self.pack_labels(y, B, dev)
+        if eps is not None:
+            eps = self._f32(eps, dev, "eps")
+            if tuple(eps.shape) != (B, Lz):
+                raise ValueError(f"eps must be [{B}, {Lz}], got {tuple(eps.shape)}")
+            seed, off = 0, 0
+        else:
+            seed, off = self._rng()
+        losses = torch.empty(L.NUM_LOSSES, dtype=torch.float32, device=dev)
+        if compute_grads and grads is None:
+            grads = self.arena.stage_buffer()
+        outs = None
+        xh = mu = ls = None
+        if want_outputs:
+            xh = torch.empty(B, D, dtype=torch.float32, device=dev)
+            mu = torch.empty(B, Lz, dtype=torch.float32, device=dev)
+            ls = torch.empty(B, Lz, dtype=torch.float32, device=dev)
+            outs = (xh, mu, ls)
+        ws = self._workspace(dev, B, L.MODE_TRAIN if compute_grads else L.MODE_FORWARD)
+        rc = L.lib().psvae_train_fwd_bwd(self._dref, flat.data_ptr(), self._shadow(), L.ptr(grads) if compute_grads else None, x.data_ptr(), L.ptr(yy),
+                                         L.ptr(eps), seed, off, self.row0, B, float(kl_weight), float(clf_weight), int(bool(use_cos_loss)),
+                                         int(bool(compute_grads)), self.precision, L.ptr(xh), L.ptr(mu), L.ptr(ls), losses.data_ptr(),
+                                         ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        L.check(rc, "psvae_train_fwd_bwd")
+        return losses, (grads if compute_grads else None), outs
+
+    def loss_with_grad(self, losses: torch.Tensor, gflat: torch.Tensor) -> torch.Tensor:
+        """The scalar a LightningModule returns from training_step: ``.backward()`` hands the fused gradients to autograd."""
+        params = self.parameters()
+        return _FusedLoss.apply(losses[L.LOSS_TOTAL], gflat, self.arena, *params)
+
+    # ---- conditional_synthesis Langevin loop (inference.py:72-103) --------------------------------
+    def targets_for(self, classifier_target) -> List[int]:
+        c = self.classifier
+        if c is None:
+            raise ValueError("conditional synthesis needs a model with a latent classifier")
+        if c.single_label_mode:
+            if isinstance(classifier_target, dict):
+                raise ValueError("classifier_target must be an int for a single-label classifier")
+            t = int(classifier_target)
+            if not 0 <= t < c.head_classes[0]:
+                raise IndexError(f"classifier_target {t} is out of range for {c.head_classes[0]} classes")
+            return [t]
+        assert isinstance(classifier_target, dict), "classifier_target must be a dict for multi-label classifier"
+        out = []
+        for name, ncls in zip(self.head_names, c.head_classes):
+            if name in classifier_target:
+                t = int(classifier_target[name])
+                if not 0 <= t < ncls:
+                    raise IndexError(f"classifier_target[{name!r}]={t} is out of range for {ncls} classes")
+                out.append(t)
+            else:
+                out.append(-1)
+        unknown = [k for k in classifier_target if k not in self.head_names]
+        if unknown:
+            raise KeyError(unknown[0])
+        return out
+
+    def langevin(self, num_samples: int, classifier_target, step_size: float = 0.01, num_steps: int = 100, noise_weight: float = 1.0,
+                 z0: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None, return_history: bool = False, return_stats: bool = False,
+                 row0: Optional[int] = None):
+        dev = self._device()
+        flat = self.arena.ensure()
+        Lz = self.desc.latent_dim
+        targets = self.targets_for(classifier_target)
+        tarr = (C.c_int32 * L.MAX_CLF_HEADS)(*(targets + [-1] * (L.MAX_CLF_HEADS - len(targets))))
+        N = int(num_samples)
+        if z0 is not None:
+            z = self._f32(z0, dev, "z0").clone()
+            if tuple(z.shape) != (N, Lz):
+                raise ValueError(f"z0 must be [{N}, {Lz}]")
+            init = 0
+        else:
+            z = torch.empty(N, Lz, dtype=torch.float32, device=dev)
+            init = 1
+        if noise is not None:
+            noise = self._f32(noise, dev, "noise")
+            if tuple(noise.shape) != (num_steps, N, Lz):
+                raise ValueError(f"noise must be [{num_steps}, {N}, {Lz}]")
+        if self.seed is None:
+            self.seed = int(torch.initial_seed()) & 0xFFFFFFFFFFFFFFFF
+        off0 = self.offset
+        self.offset += num_steps + 1
+        hist = torch.empty(num_steps, N, Lz, dtype=torch.float32, device=dev) if return_history else None
+        stats = torch.empty(num_steps, 2, dtype=torch.float32, device=dev) if return_stats else None
+        if N > 0:
+            rc = L.lib().psvae_langevin(self._dref, flat.data_ptr(), z.data_ptr(), N, tarr, float(step_size), int(num_steps), float(noise_weight),
+                                        self.seed, off0, self.row0 if row0 is None else row0, init, L.ptr(noise), L.ptr(hist), L.ptr(stats),
+                                        _stream_ptr(dev))
+            L.check(rc, "psvae_langevin")
+        if stats is not None and N > 0:
+            stats = stats / N
+        return z, hist, stats

@@ -1,0 +1,470 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C-ABI via the drop-in modules, against
+  * the golden fixtures the unmodified reference produced (tests/golden/, oracle/make_golden.py),
+  * the numpy oracle (oracle/ps_vae_oracle.py) on the same seeded inputs,
+  * size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (north_star): fp32 mode <= 1e-5 relative (per-tensor ||a-b||/||b||) for forward, losses, gradients and
+post-Adam parameters; Philox words, sample indexing and conditioning lookup bit-exact; bf16 tensor-core mode:
+forward <= 1e-2, loss <= 3e-3, gradients <= 3e-2 relative against the fp64 twin (bf16 operands carry 8 mantissa
+bits: 2^-9 = 2e-3 per rounding, SURVEY F8 measured 2.4e-3 per Linear for the reference's own 'medium' setting).
+"""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import philox_ref as PR
+from oracle import ps_vae_oracle as O
+from tests.golden_util import GOLDEN, case_batch, case_params, check_summary, load, rel_err
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TRAIN_CASES = ["train_d256_c2", "train_d192_noclf", "train_d512_c3_mlp", "train_d256_norm_cos"]
+SAMPLE_CASES = ["sample_single", "sample_c3_mlp", "sample_multilabel", "sample_multilabel_1layer"]
+FP32_TOL = 1e-5
+BF16_FWD_TOL, BF16_LOSS_TOL, BF16_GRAD_TOL = 1e-2, 3e-3, 3e-2
+
+
+def _gu():
+    from tests import gpu_util
+
+    return gpu_util
+
+
+# ------------------------------------------------------------------------------------------------
+# generator (bit-exact) and Adam
+# ------------------------------------------------------------------------------------------------
+def test_philox_words_bit_exact():
+    G = _gu()
+    L = G.L
+    for n, seed, offset, first in [(4096, 0, 0, 0), (1001, 0xDEADBEEF12345678, 7, 13), (64, 1, 2 ** 40 + 3, 2 ** 34 + 2)]:
+        out = torch.empty(n, dtype=torch.int32, device=G.DEV)
+        L.check(L.lib().psvae_philox_uint32(out.data_ptr(), n, seed, offset, first, G.stream()))
+        got = out.cpu().numpy().view(np.uint32)
+        ref = PR.philox_uint32(n, seed, offset, first)
+        assert np.array_equal(got, ref), (n, seed, offset, first)
+
+
+def test_philox_normal_matches_spec_and_shards():
+    G = _gu()
+    L = G.L
+    out = torch.empty(512, 64, dtype=torch.float32, device=G.DEV)
+    L.check(L.lib().psvae_philox_normal(out.data_ptr(), 512, 64, 99, 5, 0, G.stream()))
+    ref = PR.philox_normal(512, 64, 99, 5, 0)
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() < 5e-6          # fast sincos on [-pi, pi] + accurate log: ~1e-6 absolute
+    part = torch.empty(128, 64, dtype=torch.float32, device=G.DEV)
+    L.check(L.lib().psvae_philox_normal(part.data_ptr(), 128, 64, 99, 5, 256, G.stream()))
+    assert torch.equal(part, out[256:384])          # counter = global element index: shards are bit-identical
+
+
+def test_adam_matches_torch_golden():
+    G = _gu()
+    L = G.L
+    z = np.load(os.path.join(GOLDEN, "adam_cosine.npz"))
+    for wd, tag in ((0.0, "wd0"), (0.01, "wd01")):
+        p = torch.from_numpy(z["p0"].copy()).to(G.DEV)
+        m = torch.zeros_like(p)
+        v = torch.zeros_like(p)
+        shadow = torch.empty(p.numel(), dtype=torch.bfloat16, device=G.DEV)
+        for s, g in enumerate(z["grads"]):
+            gt = torch.from_numpy(g.astype(np.float32)).to(G.DEV)
+            L.check(L.lib().psvae_adam_step(p.data_ptr(), gt.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 3e-3, 0.9, 0.999, 1e-8, wd, s + 1,
+                                            1.0, shadow.data_ptr(), G.stream()))
+            ref = z[f"{tag}/f32/p{s}"]
+            assert np.abs(p.cpu().numpy() - ref).max() <= 3e-7 * np.abs(ref).max(), (tag, s)
+            assert torch.equal(shadow, p.to(torch.bfloat16))
+        assert rel_err(m.cpu().numpy(), z[f"{tag}/f32/m"]) <= 3e-6
+        assert rel_err(v.cpu().numpy(), z[f"{tag}/f32/v"]) <= 3e-6
+    # grad_scale folds the 1/world averaging in
+    p = torch.from_numpy(z["p0"].copy()).to(G.DEV)
+    m = torch.zeros_like(p)
+    v = torch.zeros_like(p)
+    gt = torch.from_numpy((z["grads"][0] * 4).astype(np.float32)).to(G.DEV)
+    L.check(L.lib().psvae_adam_step(p.data_ptr(), gt.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), 3e-3, 0.9, 0.999, 1e-8, 0.0, 1, 0.25, None,
+                                    G.stream()))
+    assert np.abs(p.cpu().numpy() - z["wd0/f32/p0"]).max() <= 1e-6 * np.abs(z["wd0/f32/p0"]).max()
+
+
+# ------------------------------------------------------------------------------------------------
+# GEMM engines
+# ------------------------------------------------------------------------------------------------
+def test_sgemm_engine_all_layouts():
+    G = _gu()
+    L = G.L
+    torch.manual_seed(3)
+    for (M, N, K) in [(70, 66, 50), (256, 64, 512), (33, 3, 64), (2, 64, 1000)]:
+        for a_mn in (0, 1):
+            for b_mn in (0, 1):
+                A = torch.randn(M, K, device=G.DEV)
+                B = torch.randn(N, K, device=G.DEV)
+                bias = torch.randn(N, device=G.DEV)
+                As = A.t().contiguous() if a_mn else A
+                Bs = B.t().contiguous() if b_mn else B
+                c = torch.empty(M, N, device=G.DEV)
+                L.check(L.lib().psvae_gemm_fp32(As.data_ptr(), Bs.data_ptr(), bias.data_ptr(), c.data_ptr(), M, N, K, a_mn, b_mn, 1, G.stream()))
+                ref = (A.double() @ B.double().t() + bias.double()).clamp_min(0)
+                assert ((c.double() - ref).norm() / ref.norm()).item() < 2e-6, (M, N, K, a_mn, b_mn)
+
+
+TC_VARIANTS = [
+    # m, n, k, a_mn, b_mn, bn, split, relu, bias, grid
+    (256, 256, 256, 0, 0, 0, 1, 0, 0, 0),      # the forward form, one tile per CTA
+    (1000, 512, 320, 0, 0, 0, 1, 1, 1, 0),     # ragged M, bias + ReLU epilogue
+    (4096, 1024, 256, 0, 0, 256, 1, 0, 1, 8),  # many tiles per CTA: TMEM double buffering + smem ring wrap-around
+    (300, 192, 520, 0, 0, 64, 1, 0, 0, 0),     # BN = 64, ragged K (zero-filled by TMA)
+    (384, 128, 64, 0, 0, 128, 1, 0, 0, 0),     # BN = 128, a single K block (decoder layer 0: K = latent)
+    (512, 64, 512, 0, 0, 0, 1, 0, 1, 0),       # N = latent
+    (640, 512, 256, 0, 1, 0, 1, 0, 0, 0),      # dgrad form: B (= W as stored) MN-major
+    (640, 64, 512, 0, 1, 0, 1, 0, 0, 0),
+    (200, 192, 64, 0, 1, 64, 1, 0, 0, 0),
+    (512, 256, 4096, 1, 1, 0, 1, 0, 0, 0),     # wgrad form: both MN-major, contraction over the batch
+    (512, 512, 8192, 1, 1, 0, 8, 0, 0, 0),     # + split-K
+    (64, 512, 3000, 1, 1, 0, 5, 0, 0, 0),      # M = latent < tile, ragged K
+    (1024, 256, 2048, 1, 1, 128, 3, 0, 0, 0),
+]
+
+
+@pytest.mark.parametrize("v", TC_VARIANTS, ids=lambda v: "m%d_n%d_k%d_a%d_b%d_bn%d_s%d" % v[:7])
+def test_tcgen05_gemm_variant(v):
+    m, n, k, a_mn, b_mn, bn, split, relu, bias, grid = v
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "gpu_case.py"), "gemm", "--m", str(m), "--n", str(n), "--k", str(k), "--a_mn", str(a_mn),
+           "--b_mn", str(b_mn), "--bn", str(bn), "--split", str(split), "--relu", str(relu), "--bias", str(bias), "--grid", str(grid)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
+    line = [l for l in res.stdout.splitlines() if l.startswith("RESULT ")]
+    assert res.returncode == 0 and line, f"rc={res.returncode}\n{res.stdout[-2000:]}\n{res.stderr[-3000:]}"
+    out = json.loads(line[-1][7:])
+    assert out["finite"] and out["rel_err"] < 1e-5, out     # exact bf16 products, fp32 accumulation: only summation order differs
+
+
+# ------------------------------------------------------------------------------------------------
+# train step against the reference's golden outputs
+# ------------------------------------------------------------------------------------------------
+def _train_case(name, precision, tol_fwd, tol_loss, tol_grad, check_params):
+    G = _gu()
+    z, cfg = load(name)
+    module = G.module_from_cfg(cfg, precision)
+    opt = module.configure_optimizers()["optimizer"]
+    worst = {}
+    tag = "f64"        # the truth both the reference's fp32 run and ours approximate
+    for s in range(cfg.get("steps", 3)):
+        x, y, eps = case_batch(cfg, s, np.float32)
+        xt, et = torch.from_numpy(x).to(G.DEV), torch.from_numpy(eps).to(G.DEV)
+        yt = G.labels_to_torch(y) if cfg.get("clf") else torch.zeros(x.shape[0], dtype=torch.int64, device=G.DEV)
+        st = f"{tag}/step{s}"
+        x_hat, mu, ls = module(xt, eps=et)
+        for nm, got in (("x_hat", x_hat), ("mu", mu), ("ls", ls)):
+            e = rel_err(got.cpu().numpy(), z[f"{st}/{nm}"])
+            worst[nm] = max(worst.get(nm, 0), e)
+            assert e <= tol_fwd, (name, precision, s, nm, e)
+        opt.zero_grad()
+        loss = module.training_step((xt, yt), s, eps=et)["loss"]
+        loss.backward()
+        logged = {k: float(v) for k, v in module.logged.items()}
+        for ours in ("train_loss", "train_recon_loss", "train_kl_loss") + (("train_classifier_loss",) if cfg.get("clf") else ()):
+            ref = float(z[f"{st}/log/{ours}"])
+            e = abs(logged[ours] - ref) / max(1.0, abs(ref))
+            worst[ours] = max(worst.get(ours, 0), e)
+            assert e <= tol_loss, (name, precision, s, ours, logged[ours], ref)
+        assert abs(float(loss) - logged["train_loss"]) == 0
+        if cfg.get("clf") and precision == "fp32":
+            assert abs(logged["train_classifier_acc"] - float(z[f"{st}/log/train_classifier_acc"])) <= 1e-6
+        for k, p in module.named_parameters():
+            worst["grad"] = max(worst.get("grad", 0), check_summary(z, f"{st}/grad", k, p.grad.cpu().numpy(), tol_grad))
+        opt.step()
+        if check_params:
+            for k, p in module.named_parameters():
+                worst["param"] = max(worst.get("param", 0), check_summary(z, f"{st}/param", k, p.detach().cpu().numpy(), tol_grad))
+    return worst
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_train_step_fp32_vs_reference_golden(name):
+    """forward, every loss term, every gradient and the post-Adam parameters over 2-3 optimiser steps, <= 1e-5 relative."""
+    worst = _train_case(name, "fp32", FP32_TOL, FP32_TOL, FP32_TOL, True)
+    print(name, {k: f"{v:.2e}" for k, v in worst.items()})
+
+
+@pytest.mark.parametrize("name", TRAIN_CASES)
+def test_train_step_bf16_vs_reference_golden(name):
+    worst = _train_case(name, "bf16", BF16_FWD_TOL, BF16_LOSS_TOL, BF16_GRAD_TOL, False)
+    print(name, {k: f"{v:.2e}" for k, v in worst.items()})
+
+
+def test_validation_step_and_no_grad():
+    G = _gu()
+    z, cfg = load("train_d256_c2")
+    module = G.module_from_cfg(cfg, "fp32")
+    x, y, eps = case_batch(cfg, 0, np.float32)
+    batch = (torch.from_numpy(x).to(G.DEV), G.labels_to_torch(y))
+    out = module.validation_step(batch, 0, eps=torch.from_numpy(eps).to(G.DEV))
+    assert not out["loss"].requires_grad
+    assert abs(float(module.logged["val_loss"]) - float(z["f64/step0/log/train_loss"])) <= FP32_TOL
+    assert all(p.grad is None for p in module.parameters())
+    # the model stays stochastic in eval mode: two calls without injected eps differ, same seed/offset repeat
+    module.hot_path.manual_seed(123, 0)
+    a = module(batch[0])[0]
+    b = module(batch[0])[0]
+    module.hot_path.manual_seed(123, 0)
+    c = module(batch[0])[0]
+    assert not torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_gradient_accumulation_and_loss_scaling():
+    """loss.backward() semantics survive the fused step: two backward calls accumulate, a scaled loss scales the gradients."""
+    G = _gu()
+    z, cfg = load("train_d192_noclf")
+    module = G.module_from_cfg(cfg, "fp32")
+    x, y, eps = case_batch(cfg, 0, np.float32)
+    xt, et = torch.from_numpy(x).to(G.DEV), torch.from_numpy(eps).to(G.DEV)
+    yt = torch.zeros(x.shape[0], dtype=torch.int64, device=G.DEV)
+    module.training_step((xt, yt), 0, eps=et)["loss"].backward()
+    g1 = {k: p.grad.clone() for k, p in module.named_parameters()}
+    (module.training_step((xt, yt), 0, eps=et)["loss"] * 0.5).backward()
+    for k, p in module.named_parameters():
+        assert torch.allclose(p.grad, g1[k] * 1.5, rtol=1e-6, atol=1e-9), k
+
+
+def test_freeze_vae_trains_only_the_classifier():
+    G = _gu()
+    z, cfg = load("train_d256_c2")
+    module = G.module_from_cfg(cfg, "fp32", freeze_vae=True)
+    before = {k: p.detach().clone() for k, p in module.named_parameters()}
+    opt = module.configure_optimizers()["optimizer"]
+    x, y, eps = case_batch(cfg, 0, np.float32)
+    module.training_step((torch.from_numpy(x).to(G.DEV), G.labels_to_torch(y)), 0, eps=torch.from_numpy(eps).to(G.DEV))["loss"].backward()
+    opt.step()
+    for k, p in module.named_parameters():
+        if k.startswith("model."):
+            assert p.grad is None and torch.equal(p, before[k]), k
+        else:
+            assert p.grad is not None and not torch.equal(p, before[k]), k
+            check_summary(z, "f64/step0/grad", k, p.grad.cpu().numpy(), FP32_TOL)
+
+
+# ------------------------------------------------------------------------------------------------
+# sampling against the reference's golden outputs (z0 and the per-step noise injected)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", SAMPLE_CASES)
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_FWD_TOL)])
+def test_sampling_vs_reference_golden(name, precision, tol):
+    G = _gu()
+    import pseudo_speaker_vae_b200 as P
+
+    z, cfg = load(name)
+    module = G.module_from_cfg(cfg, precision)
+    z0 = torch.from_numpy(z["z0"]).to(G.DEV)
+    noises = torch.from_numpy(z["noises"]).to(G.DEV)
+    xu = module.decode(z0)
+    assert rel_err(xu.cpu().numpy(), z["f64/uncond"]) <= tol
+    xc, hist = P.conditional_synthesis(module, cfg["N"], cfg["target"], cfg["step_size"], cfg["steps"], cfg["noise_weight"], True, G.DEV,
+                                       z0=z0, noise=noises)
+    assert isinstance(hist, list) and len(hist) == cfg["steps"] and hist[0].shape == (cfg["N"], cfg["L"])
+    assert rel_err(np.stack(hist), z["f64/hist"]) <= FP32_TOL          # the Langevin loop is fp32 in both modes
+    assert rel_err(xc.numpy(), z["f64/cond"]) <= tol
+    assert xc.device.type == "cpu" and xc.shape == (cfg["N"], cfg["D"])
+
+
+def test_sampling_indexing_is_bit_exact_under_sharding(tmp_path):
+    """Row i of the output <-> sample_{i}.pt, and a run sharded over W ranks reproduces the single-GPU batch bit for bit."""
+    G = _gu()
+    import pseudo_speaker_vae_b200 as P
+
+    z, cfg = load("sample_single")
+    for precision in ("fp32", "bf16"):
+        module = G.module_from_cfg(cfg, precision)
+        N = 1000
+        module.hot_path.manual_seed(77, 0)
+        full = P.sample_on_device(module, N)
+        module.hot_path.manual_seed(77, 0)
+        full_c = P.sample_on_device(module, N, classifier_target=1, num_steps=5, step_size=0.05)
+        for W in (3, 8):
+            parts, parts_c = [], []
+            for r in range(W):
+                row0, rows = P.shard_rows(N, r, W)
+                module.hot_path.manual_seed(77, 0)
+                parts.append(P.sample_on_device(module, rows, row0=row0))
+                module.hot_path.manual_seed(77, 0)
+                parts_c.append(P.sample_on_device(module, rows, classifier_target=1, num_steps=5, step_size=0.05, row0=row0))
+            if precision == "fp32":
+                assert torch.equal(torch.cat(parts), full) and torch.equal(torch.cat(parts_c), full_c), (precision, W)
+            else:   # the tcgen05 tiles see different row groupings; the products are exact, only fp32 summation order may differ: it does not here
+                assert torch.allclose(torch.cat(parts), full, rtol=0, atol=0) and torch.allclose(torch.cat(parts_c), full_c, rtol=0, atol=0)
+    paths = P.save_samples(full[:5].cpu(), str(tmp_path))
+    assert [os.path.basename(p) for p in paths] == [f"sample_{i}.pt" for i in range(5)]
+    for i, p in enumerate(paths):
+        assert torch.equal(torch.load(p), full[i].cpu())
+
+
+def test_unconditional_synthesis_distribution_and_api():
+    G = _gu()
+    import pseudo_speaker_vae_b200 as P
+
+    z, cfg = load("sample_single")
+    module = G.module_from_cfg(cfg, "fp32")
+    module.hot_path.manual_seed(5, 0)
+    x, zz = module.hot_path.decode(None, num_samples=4096, return_z=True)
+    assert abs(zz.mean().item()) < 0.02 and abs(zz.std().item() - 1) < 0.02
+    ref = PR.philox_normal(4096, cfg["L"], 5, 0, 0)
+    assert np.abs(zz.cpu().numpy() - ref).max() < 5e-6
+    params = case_params(cfg, np.float64)
+    assert rel_err(x.cpu().numpy(), O.decode(params, zz.cpu().numpy().astype(np.float64))) <= FP32_TOL
+    out = P.unconditional_synthesis(module, 7, G.DEV)
+    assert out.device.type == "cpu" and out.shape == (7, cfg["D"])
+    with pytest.raises(RuntimeError):
+        P.unconditional_synthesis(module, 7, "cpu")          # no CPU fallback
+
+
+def test_conditional_target_lookup_errors():
+    G = _gu()
+    import pseudo_speaker_vae_b200 as P
+
+    _, cfg = load("sample_multilabel")
+    module = G.module_from_cfg(cfg, "fp32")
+    with pytest.raises(AssertionError):
+        P.conditional_synthesis(module, 4, 1, device=G.DEV)                 # multi-label needs a dict (inference.py:82)
+    with pytest.raises(IndexError):
+        P.conditional_synthesis(module, 4, {"age": 3}, device=G.DEV)
+    with pytest.raises(KeyError):
+        P.conditional_synthesis(module, 4, {"height": 0}, device=G.DEV)
+    x = P.conditional_synthesis(module, 4, {"gender": 1}, num_steps=3, device=G.DEV)   # a dict naming only some labels
+    assert x.shape == (4, cfg["D"]) and torch.isfinite(x).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json full sizes: oracle on the same inputs + size-independent properties
+# ------------------------------------------------------------------------------------------------
+def _big_module(G, precision, D=256, clf=True):
+    cfg = dict(D=D, L=64, wseed=3, clf=dict(input_dim=64, num_classes=2) if clf else None)
+    return G.module_from_cfg(cfg, precision), cfg
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_full_batch_65536_losses_vs_oracle_and_shard_linearity(precision):
+    """B = 65,536 (BASELINE config 2): loss scalars against the numpy oracle with the same Philox eps, and
+    grad(full batch) == mean of grad(shards) with world-size-independent eps (what the DP all-reduce relies on)."""
+    G = _gu()
+    module, cfg = _big_module(G, precision)
+    B = 65536
+    x, y, _ = O.synth_batch(B, 256, 64, 2, seed=1234)
+    xt, yt = torch.from_numpy(x).to(G.DEV), torch.from_numpy(y).to(G.DEV)
+    hot = module.hot_path
+    hot.manual_seed(2024, 9)
+    hot.row0 = 0
+    g_full = torch.empty(hot.arena.numel, device=G.DEV)
+    losses, _, outs = hot.step(xt, yt, grads=g_full, want_outputs=True)
+    eps = PR.philox_normal(B, 64, 2024, 9, 0)
+    params = case_params(cfg, np.float64)
+    scal, out, grads = O.train_loss_and_grads(params, x.astype(np.float64), y, eps.astype(np.float64))   # fp64 twin: the truth
+    lt = losses.cpu().numpy()
+    tol_l = FP32_TOL if precision == "fp32" else BF16_LOSS_TOL
+    tol_f = FP32_TOL if precision == "fp32" else BF16_FWD_TOL
+    tol_g = FP32_TOL if precision == "fp32" else BF16_GRAD_TOL
+    assert abs(lt[0] - float(scal["loss"])) <= tol_l * max(1, abs(float(scal["loss"])))
+    assert abs(lt[1] - float(scal["recon_loss"])) <= tol_l and abs(lt[2] - float(scal["kl_loss"])) <= tol_l * max(1, float(scal["kl_loss"]))
+    assert abs(lt[3] - float(scal["classifier_loss"])) <= tol_l
+    assert abs(lt[8] - float(scal["classifier_acc"])) <= (1e-6 if precision == "fp32" else 2e-3)
+    assert rel_err(outs[0].cpu().numpy(), out["x_hat"]) <= tol_f
+    assert rel_err(outs[1].cpu().numpy(), out["mu"]) <= tol_f
+    gd = G.flat_to_dict(module, g_full)
+    for k in grads:
+        assert rel_err(gd[k], grads[k]) <= tol_g, (k, rel_err(gd[k], grads[k]))
+    # shard linearity, W = 4
+    acc = torch.zeros_like(g_full)
+    lsum = torch.zeros_like(losses)
+    W = 4
+    for r in range(W):
+        hot.manual_seed(2024, 9)
+        hot.row0 = r * (B // W)
+        sl = slice(r * (B // W), (r + 1) * (B // W))
+        g = torch.empty_like(g_full)
+        l, _, _ = hot.step(xt[sl], yt[sl], grads=g)
+        acc += g
+        lsum += l
+    hot.row0 = 0
+    acc /= W
+    lsum /= W
+    e = ((acc.double() - g_full.double()).norm() / g_full.double().norm()).item()
+    assert e <= (2e-6 if precision == "fp32" else 2e-3), e     # bf16: dxh is rounded to bf16 after scaling by 1/B_local vs 1/B
+    assert torch.allclose(lsum[:4], losses[:4], rtol=2e-6 if precision == "fp32" else 1e-5, atol=1e-7)
+
+
+def test_widened_config5_small_batch_vs_oracle():
+    """BASELINE config 5 shape (D=512, 4 x 2048 hidden, latent classifier) at a batch the oracle finishes quickly."""
+    G = _gu()
+    cfg = dict(D=512, L=64, H=2048, nh=4, wseed=8, clf=dict(input_dim=64, num_classes=2))
+    shapes = O.vae_param_shapes(512, 64, 2048, 4) + O.classifier_param_shapes(64, 2)
+    params = {k: v.astype(np.float32) for k, v in O.synth_params(shapes, seed=8, dtype=np.float64).items()}
+    B = 512
+    x, y, eps = O.synth_batch(B, 512, 64, 2, seed=42)
+    scal, out, grads = O.train_loss_and_grads({k: v.astype(np.float64) for k, v in params.items()}, x.astype(np.float64), y, eps.astype(np.float64))
+    for precision, tf, tl, tg in (("fp32", FP32_TOL, FP32_TOL, FP32_TOL), ("bf16", BF16_FWD_TOL, BF16_LOSS_TOL, BF16_GRAD_TOL)):
+        module = G.module_from_cfg(cfg, precision, params=params)
+        hot = module.hot_path
+        g = torch.empty(hot.arena.numel, device=G.DEV)
+        losses, _, outs = hot.step(torch.from_numpy(x).to(G.DEV), torch.from_numpy(y).to(G.DEV), torch.from_numpy(eps).to(G.DEV), grads=g,
+                                   want_outputs=True)
+        assert abs(float(losses[0]) - float(scal["loss"])) <= tl * max(1, abs(float(scal["loss"]))), precision
+        assert rel_err(outs[0].cpu().numpy(), out["x_hat"]) <= tf, precision
+        gd = G.flat_to_dict(module, g)
+        for k in grads:
+            assert rel_err(gd[k], grads[k]) <= tg, (precision, k, rel_err(gd[k], grads[k]))
+
+
+def test_ragged_and_tiny_batches():
+    """B = 1, odd B, B not a multiple of any tile: the edge cases of the row dimension."""
+    G = _gu()
+    cfg = dict(D=256, L=64, wseed=3, clf=dict(input_dim=64, num_classes=3))
+    params = case_params(cfg, np.float64)
+    for precision, tf, tg in (("fp32", FP32_TOL, FP32_TOL), ("bf16", BF16_FWD_TOL, BF16_GRAD_TOL)):
+        module = G.module_from_cfg(cfg, precision)
+        hot = module.hot_path
+        for B in (1, 3, 129, 1000):
+            x, y, eps = O.synth_batch(B, 256, 64, 3, seed=B)
+            scal, out, grads = O.train_loss_and_grads(params, x.astype(np.float64), y, eps.astype(np.float64))
+            g = torch.empty(hot.arena.numel, device=G.DEV)
+            losses, _, outs = hot.step(torch.from_numpy(x).to(G.DEV), torch.from_numpy(y).to(G.DEV), torch.from_numpy(eps).to(G.DEV), grads=g,
+                                       want_outputs=True)
+            assert rel_err(outs[0].cpu().numpy(), out["x_hat"]) <= tf, (precision, B)
+            gd = G.flat_to_dict(module, g)
+            worst = max(rel_err(gd[k], grads[k]) for k in grads)
+            assert worst <= tg, (precision, B, worst)
+        with pytest.raises(ValueError):
+            hot.step(torch.empty(0, 256, device=G.DEV), torch.empty(0, dtype=torch.int64, device=G.DEV))
+        assert module(torch.empty(0, 256, device=G.DEV))[0].shape == (0, 256)
+
+
+def test_reference_shape_smoke_784_20():
+    """The reference's own __main__ smoke (ps_vae/model.py:71-75): VAEModel(784, 20) on a [32, 784] batch."""
+    G = _gu()
+    import pseudo_speaker_vae_b200 as P
+
+    torch.manual_seed(0)
+    model = P.VAEModel(784, 20).to(G.DEV)
+    x = torch.randn(32, 784, device=G.DEV)
+    eps = torch.randn(32, 20, device=G.DEV)
+    x_hat, mu, sigma = model(x, eps=eps)
+    assert x_hat.shape == (32, 784) and mu.shape == (32, 20) and sigma.shape == (32, 20)
+    params = {"model." + k: v.detach().cpu().double().numpy() for k, v in model.state_dict().items()}
+    xr, mr, lr_, _ = O.vae_forward(params, x.cpu().double().numpy(), eps.cpu().double().numpy())
+    assert rel_err(x_hat.cpu().numpy(), xr) <= FP32_TOL and rel_err(mu.cpu().numpy(), mr) <= FP32_TOL
+
+
+def test_data_parallel_trainer_single_process_matches_manual_steps():
+    G = _gu()
+    import pseudo_speaker_vae_b200 as P
+
+    z, cfg = load("train_d256_c2")
+    module = G.module_from_cfg(cfg, "fp32")
+    trainer = P.DataParallelTrainer(module)
+    for s in range(3):
+        x, y, eps = case_batch(cfg, s, np.float32)
+        trainer.set_shard(x.shape[0])
+        trainer.train_step(torch.from_numpy(x).to(G.DEV), G.labels_to_torch(y), torch.from_numpy(eps).to(G.DEV))
+        for k, p in module.named_parameters():
+            check_summary(z, f"f64/step{s}/param", k, p.detach().cpu().numpy(), FP32_TOL)

@@ -1,0 +1,255 @@
+"""CPU-side tests (-m "not gpu"): the C-ABI library loads and exports what include/psvae_b200.h declares, the host
+logic around it (flat parameter arena, state-dict compatibility with the reference, optimiser plumbing, sharding
+arithmetic, integer tables) and the loud failure without a GPU.  No compute entry point is exercised here."""
+import ctypes as C
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import pseudo_speaker_vae_b200 as P
+from oracle import ps_vae_oracle as O
+from pseudo_speaker_vae_b200 import _lib as L
+from pseudo_speaker_vae_b200 import parallel
+from tests.golden_util import GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _module(**extra):
+    hp = dict(model=dict(input_dim=256, latent_dim=64), classifier=dict(input_dim=64, num_classes=2), optimizer=dict(lr=1e-3),
+              scheduler=dict(T_max=200))
+    hp.update(extra)
+    return P.PseudoSpeakerVAE(**hp)
+
+
+def test_library_exports_every_declared_symbol():
+    with open(os.path.join(ROOT, "include", "psvae_b200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    declared = sorted(set(re.findall(r"\b(psvae_[a-z0-9_]+)\s*\(", text)))
+    assert declared == sorted(L.EXPORTS)
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.psvae_abi_version() == L.PSVAE_ABI_VERSION
+    assert C.sizeof(L.ModelDesc) == 4 * 16 + 8 * (4 * 8 + 4 * 4 + 2)
+
+
+def test_desc_layout_covers_the_state_dict_without_overlap():
+    for hp in (dict(), dict(classifier=dict(input_dim=64, num_classes={"age": 3, "gender": 2}, num_layers=3, hidden_dim=128, activation="tanh")),
+               dict(model=dict(input_dim=512, latent_dim=64, hidden_dim=2048, num_hidden_layers=4))):
+        m = _module(**hp)
+        hot = m.hot_path
+        spans = sorted((off, off + p.numel()) for p, off in hot.arena.entries)
+        assert spans[0][0] == 0
+        for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+            assert a1 <= b0 and b0 - a1 < 8 and b0 % 8 == 0
+        assert spans[-1][1] <= hot.desc.total_numel
+        n_vae = sum(p.numel() for p in m.model.parameters())
+        assert hot.desc.vae_numel == n_vae
+        assert len(hot.arena.entries) == len(list(m.parameters()))
+        assert hot.arena.attached()
+    assert _module().hot_path.desc.vae_numel == 1281408          # P at the primary config
+
+
+def test_flop_counts_match_baseline_md():
+    d = L.make_desc(256, 64)
+    assert L.lib().psvae_flops_per_sample(C.byref(d), 0) == 7143424
+    assert L.lib().psvae_flops_per_sample(C.byref(d), 2) == 851968
+    assert L.lib().psvae_flops_per_sample(C.byref(d), 1) == 2 * 1277952
+    d = L.make_desc(256, 64, clf_head_classes=[2])
+    assert L.lib().psvae_flops_per_sample(C.byref(d), 0) == 7143424 + 768
+    d = L.make_desc(192, 64)
+    assert L.lib().psvae_flops_per_sample(C.byref(d), 0) == 6684672
+    d = L.make_desc(512, 64)
+    assert L.lib().psvae_flops_per_sample(C.byref(d), 0) == 8978432
+    d = L.make_desc(512, 64, 2048, 4, clf_head_classes=[2])      # BASELINE config 5 (with its latent classifier)
+    assert L.lib().psvae_flops_per_sample(C.byref(d), 0) == 243532544 and L.lib().psvae_flops_per_sample(C.byref(d), 2) == 27525120
+
+
+def test_host_helpers_report_errors_without_a_gpu():
+    with pytest.raises(ValueError):
+        L.make_desc(255, 64)
+    with pytest.raises(ValueError):
+        L.make_desc(256, 64, clf_head_classes=[1])               # the reference's degenerate 1-logit branch
+    with pytest.raises(ValueError):
+        L.make_desc(256, 64, clf_activation="gelu")
+    d = L.make_desc(256, 64, clf_head_classes=[2])
+    w1 = L.lib().psvae_workspace_bytes(C.byref(d), 256, L.FP32, L.MODE_TRAIN)
+    w2 = L.lib().psvae_workspace_bytes(C.byref(d), 65536, L.FP32, L.MODE_TRAIN)
+    w3 = L.lib().psvae_workspace_bytes(C.byref(d), 65536, L.BF16, L.MODE_TRAIN)
+    assert 0 < w1 < w3 < w2
+    assert L.lib().psvae_workspace_bytes(C.byref(d), 0, L.FP32, L.MODE_TRAIN) == -1 and "rows" in L.last_error()
+    d2 = L.make_desc(784, 20)                                      # fine in fp32, not tensor-core tileable
+    assert L.lib().psvae_workspace_bytes(C.byref(d2), 32, L.BF16, L.MODE_FORWARD) == -1 and "PSVAE_BF16" in L.last_error()
+    L.set_option("decode_chunk", 4096)
+    assert L.get_option("decode_chunk") == 4096
+    L.set_option("decode_chunk", 1 << 15)
+    with pytest.raises(ValueError):
+        L.set_option("no_such_option", 1)
+
+
+def test_state_dict_is_the_references():
+    m = _module(classifier=dict(input_dim=64, num_classes={"age": 3, "gender": 2}, num_layers=2))
+    keys = list(m.state_dict().keys())
+    shapes = O.vae_param_shapes(256, 64) + O.classifier_param_shapes(64, {"age": 3, "gender": 2}, 2, 128)
+    assert keys == [k for k, _ in shapes]
+    assert [tuple(v.shape) for v in m.state_dict().values()] == [s for _, s in shapes]
+    from oracle.ref_loader import load_reference, reference_available
+
+    if reference_available():
+        ref = load_reference()
+        for hp in (dict(classifier=dict(input_dim=64, num_classes=3, num_layers=3, hidden_dim=32)), dict()):
+            torch.manual_seed(7)
+            ours = _module(**hp)
+            torch.manual_seed(7)
+            base = dict(model=dict(input_dim=256, latent_dim=64), classifier=dict(input_dim=64, num_classes=2), optimizer=dict(lr=1e-3),
+                        scheduler=dict(T_max=200))
+            base.update(hp)
+            theirs = ref.PseudoSpeakerVAE(**base)
+            a, b = ours.state_dict(), theirs.state_dict()
+            assert list(a.keys()) == list(b.keys())
+            assert all(torch.equal(a[k], b[k]) for k in a)        # same init order -> same weights for a given seed
+            theirs.load_state_dict(a)
+            ours.load_state_dict(b)
+
+
+def test_arena_follows_load_state_dict_and_casts():
+    m = _module()
+    hot = m.hot_path
+    sd = {k: torch.randn_like(v) for k, v in m.state_dict().items()}
+    m.load_state_dict(sd)
+    assert hot.arena.attached()
+    flat = hot.arena.flat
+    for p, off in hot.arena.entries:
+        assert torch.equal(flat[off:off + p.numel()].view(p.shape), p.detach())
+    names = {id(p): k for k, p in m.named_parameters()}
+    for p, off in hot.arena.entries:
+        assert torch.equal(p.detach(), sd[names[id(p)]])
+    # padding stays zero
+    mask = torch.ones(hot.arena.numel, dtype=torch.bool)
+    for p, off in hot.arena.entries:
+        mask[off:off + p.numel()] = False
+    assert float(flat[mask].abs().sum()) == 0
+    m.double()
+    with pytest.raises(TypeError):
+        hot.arena.ensure()
+    m.float()
+    hot.arena.ensure()
+    assert hot.arena.attached()
+    for p, off in hot.arena.entries:
+        assert torch.equal(p.detach(), sd[names[id(p)]])
+
+
+def test_no_cpu_fallback_anywhere():
+    m = _module()
+    x = torch.randn(4, 256)
+    for call in (lambda: m(x), lambda: m.decode(torch.randn(4, 64)), lambda: m.training_step((x, torch.zeros(4, dtype=torch.long)), 0),
+                 lambda: m.model(x), lambda: P.unconditional_synthesis(m, 4, "cpu"), lambda: P.conditional_synthesis(m, 4, 1, device="cpu")):
+        with pytest.raises(RuntimeError, match="no CPU fallback|B200 only"):
+            call()
+    opt = m.configure_optimizers()["optimizer"]
+    for p in m.parameters():
+        p.grad = torch.zeros_like(p)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        opt.step()
+
+
+def test_configure_optimizers_surface_and_state_dict():
+    m = _module(optimizer=dict(lr=2e-3, weight_decay=0.01), scheduler=dict(T_max=3, eta_min=1e-5))
+    cfg = m.configure_optimizers()
+    opt, sched = cfg["optimizer"], cfg["lr_scheduler"]["scheduler"]
+    assert isinstance(opt, torch.optim.Optimizer) and isinstance(opt, P.FusedAdam)
+    assert cfg["lr_scheduler"]["interval"] == "epoch" and cfg["lr_scheduler"]["frequency"] == 1
+    assert isinstance(sched, torch.optim.lr_scheduler.CosineAnnealingLR)
+    z = np.load(os.path.join(GOLDEN, "adam_cosine.npz"))
+    ours = O.cosine_annealing_lr(2e-3, 3, 1e-5, 6)
+    got = [opt.param_groups[0]["lr"]]
+    for _ in range(6):
+        opt._opt_called = True   # silence the "scheduler before optimizer" warning: no GPU here to step on
+        sched.step()
+        got.append(opt.param_groups[0]["lr"])
+    np.testing.assert_allclose(got, ours, rtol=1e-12)
+    opt._moments()
+    sd = opt.state_dict()
+    assert len(sd["state"]) == 20 and set(sd["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+    assert sd["param_groups"][0]["lr"] == got[-1] and sd["param_groups"][0]["weight_decay"] == 0.01
+    opt.load_state_dict(sd)
+    assert opt.state[next(iter(m.parameters()))]["exp_avg"].data_ptr() == opt._m.data_ptr()
+    with pytest.raises(NotImplementedError):
+        P.FusedAdam(m.parameters(), amsgrad=True, arena=m.hot_path.arena)
+    with pytest.raises(NotImplementedError):
+        _module(consistency_classifier_ckpt="x.ckpt")
+
+
+def test_attribute_surface_of_the_lightning_module():
+    m = _module(kl_loss_weight=0.5, classifier_loss_weight=2.0, use_cos_loss=True)
+    assert (m.kl_loss_weight, m.classifier_loss_weight, m.consitency_loss_weight, m.use_cos_loss) == (0.5, 2.0, 1.0, True)
+    assert m.multilabel is False and m.consistency_classifier is None
+    assert m.hparams.model["latent_dim"] == 64 and m.hparams["optimizer"] == dict(lr=1e-3)
+    assert isinstance(m.model, P.VAEModel) and isinstance(m.classifier, P.LatentClassifier)
+    ml = _module(classifier=dict(input_dim=64, num_classes={"age": 3, "gender": 2}))
+    assert ml.multilabel is True and set(ml.accuracy.keys()) == {"age", "gender"}
+    assert ml.classifier.label_classes == {"age": 3, "gender": 2}
+    none = P.PseudoSpeakerVAE(model=dict(input_dim=192, latent_dim=64), optimizer={}, scheduler=dict(T_max=1))
+    assert none.classifier is None
+    with pytest.raises(ValueError):
+        P.LatentClassifier(64, 2, activation="gelu")
+
+
+def test_checkpoint_round_trip(tmp_path):
+    m = _module()
+    path = str(tmp_path / "best-checkpoint.ckpt")
+    torch.save({"state_dict": m.state_dict(), "hyper_parameters": dict(m.hparams)}, path)
+    m2 = P.PseudoSpeakerVAE.load_from_checkpoint(path)
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    m3 = _module(vae_checkpoint=path, freeze_vae=True)
+    assert all(torch.equal(a, b) for a, b in zip(m.model.state_dict().values(), m3.model.state_dict().values()))
+    assert not any(p.requires_grad for p in m3.model.parameters()) and all(p.requires_grad for p in m3.classifier.parameters())
+
+
+def test_integer_tables_and_target_parsing_are_bit_exact():
+    with open(os.path.join(GOLDEN, "label_tables.json")) as f:
+        g = json.load(f)
+    t = g["tables"]
+    for fn, key in ((P.map_cv_age_to_label, "map_cv_age_to_label"), (P.map_cv_gender_to_label, "map_cv_gender_to_label"),
+                    (P.map_vctk_gender_to_label, "map_vctk_gender_to_label")):
+        assert fn("no-such-key") == -1 and fn(None) == -1
+        for k, v in t[key].items():
+            assert fn(k) == v
+    for text, val in g["parsed_targets"].items():
+        assert P.parse_classifier_target(text) == val
+    assert P.sample_filename(7) == g["sample_name_fmt"].format(i=7)
+
+
+def test_target_lookup_and_sharding_arithmetic():
+    ml = _module(classifier=dict(input_dim=64, num_classes={"age": 3, "gender": 2}))
+    hot = ml.hot_path
+    assert hot.head_names == ["age", "gender"]
+    assert hot.targets_for({"gender": 1, "age": 2}) == [2, 1]
+    assert hot.targets_for({"gender": 0}) == [-1, 0]
+    with pytest.raises(IndexError):
+        hot.targets_for({"age": 3})
+    with pytest.raises(KeyError):
+        hot.targets_for({"height": 0})
+    with pytest.raises(AssertionError):
+        hot.targets_for(1)
+    single = _module().hot_path
+    assert single.targets_for(1) == [1]
+    with pytest.raises(IndexError):
+        single.targets_for(2)
+    y = ml.hot_path.pack_labels({"gender": torch.tensor([1, 0, 1]), "age": torch.tensor([2, 2, 0])}, 3, torch.device("cpu"))
+    assert y.tolist() == [[2, 2, 0], [1, 0, 1]]                       # head order, not dict order
+    for N, W in ((100_000_000, 8), (1000, 3), (5, 8)):
+        spans = [P.shard_rows(N, r, W) for r in range(W)]
+        assert spans[0][0] == 0 and sum(r for _, r in spans) == N
+        assert all(a0 + ar == b0 for (a0, ar), (b0, _) in zip(spans, spans[1:]))
+    assert parallel.shard_batch(65536 * 8, 3, 8) == (3 * 65536, 65536)
+    with pytest.raises(ValueError):
+        parallel.shard_batch(10, 0, 3)
+    sl = parallel.bucket_slices(1281600, 1 << 20)
+    assert sl[0] == (0, 262144) and sl[-1][1] == 1281600 and all(a1 == b0 for (_, a1), (b0, _) in zip(sl, sl[1:]))
+    assert len(parallel.bucket_slices(1281600)) == 1 and len(parallel.bucket_slices(41313026)) == 7
