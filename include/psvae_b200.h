@@ -113,9 +113,11 @@ int64_t psvae_get_option(const char* name);
 /* ---- optimiser: replaces torch.optim.Adam.step() driven by ps_vae/lightning.py:204-205 ------- */
 /* One vectorised pass over the flat buffers (28 B/param).  `step` is the 1-based count after increment;
  * g is read as g*grad_scale (1/world_size after a sum all-reduce).  If shadow_bf16 != NULL the updated
- * parameter is also written there as bf16 (the tcgen05 operand copy). */
-int psvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                    float eps, float weight_decay, int64_t step, float grad_scale, void* shadow_bf16, void* stream);
+ * parameter is also written there as bf16 (the tcgen05 operand copy).  The hyper-parameters are doubles because torch
+ * derives its fp32 scalars (1-beta, lr/(1-beta1^t), sqrt(1-beta2^t)) from python doubles; passing floats would not
+ * reproduce them. */
+int psvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                    double eps, double weight_decay, int64_t step, double grad_scale, void* shadow_bf16, void* stream);
 
 /* ---- generator: replaces torch.randn / randn_like (model.py:57, inference.py:23,73,95) -------- */
 int psvae_philox_uint32(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, int64_t first_elem, void* stream);

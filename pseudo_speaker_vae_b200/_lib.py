@@ -50,7 +50,7 @@ _lib: Optional[C.CDLL] = None
 
 
 def _declare(l: C.CDLL) -> None:
-    P, I32, I64, U64, F, VP = C.POINTER, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p
+    P, I32, I64, U64, F, VP, DBL = C.POINTER, C.c_int32, C.c_int64, C.c_uint64, C.c_float, C.c_void_p, C.c_double
     D = P(ModelDesc)
     l.psvae_abi_version.restype = C.c_int
     l.psvae_abi_version.argtypes = []
@@ -71,7 +71,7 @@ def _declare(l: C.CDLL) -> None:
     l.psvae_flops_per_sample.restype = I64
     l.psvae_flops_per_sample.argtypes = [D, I32]
     l.psvae_adam_step.restype = C.c_int
-    l.psvae_adam_step.argtypes = [VP, VP, VP, VP, I64, F, F, F, F, F, I64, F, VP, VP]
+    l.psvae_adam_step.argtypes = [VP, VP, VP, VP, I64, DBL, DBL, DBL, DBL, DBL, I64, DBL, VP, VP]
     l.psvae_philox_uint32.restype = C.c_int
     l.psvae_philox_uint32.argtypes = [VP, I64, U64, U64, I64, VP]
     l.psvae_philox_normal.restype = C.c_int

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const float* __restrict
     for (int j = 0; j < 4; ++j) {
       const float sigma = expf(0.5f * l[j]);
       om[j] = g[j] + kl_over_b * m[j] + c[j];
-      ol[j] = g[j] * e[j] * (0.5f * sigma) + 0.5f * kl_over_b * (expf(l[j]) - 1.f);
+      ol[j] = g[j] * e[j] * (0.5f * sigma) + 0.5f * kl_over_b * expm1f(l[j]);   // expm1: no cancellation for ls ~ 0
     }
     store_vec<4>(dmu + (i << 2), om);
     store_vec<4>(dls + (i << 2), ol);

@@ -887,8 +887,8 @@ int64_t psvae_flops_per_sample(const psvae_model_desc* desc, int32_t mode) {
   return 2 * ((enc + dec) * 3 - enc_first + 3 * clf);
 }
 
-int psvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                    int64_t step, float grad_scale, void* shadow_bf16, void* stream) {
+int psvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2, double eps, double weight_decay,
+                    int64_t step, double grad_scale, void* shadow_bf16, void* stream) {
   PSVAE_TRY(tc_device_check());
   if (!p || !g || !m || !v) { set_error("p, g, m, v must not be NULL"); return -1; }
   if (n <= 0) return 0;
@@ -897,16 +897,17 @@ int psvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, flo
     set_error("Adam buffers must be 16-byte aligned");
     return -2;
   }
-  // host scalars exactly as torch's single-tensor Adam computes them (python doubles, torch/optim/adam.py:476-547)
-  const double bc1 = 1.0 - pow((double)beta1, (double)step);
-  const double bc2 = 1.0 - pow((double)beta2, (double)step);
+  // host scalars exactly as torch's single-tensor Adam computes them: in python doubles, each rounded to fp32 once where
+  // the tensor op consumes it (torch/optim/adam.py:476-547)
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
   AdamArgs a;
-  a.lr_step = (float)((double)lr / bc1);
+  a.lr_step = (float)(lr / bc1);
   a.bc2_sqrt = (float)sqrt(bc2);
-  a.beta1 = beta1; a.beta2 = beta2;
-  a.one_minus_beta1 = (float)(1.0 - (double)beta1);
-  a.one_minus_beta2 = (float)(1.0 - (double)beta2);
-  a.eps = eps; a.weight_decay = weight_decay; a.grad_scale = grad_scale;
+  a.beta1 = (float)beta1; a.beta2 = (float)beta2;
+  a.one_minus_beta1 = (float)(1.0 - beta1);
+  a.one_minus_beta2 = (float)(1.0 - beta2);
+  a.eps = (float)eps; a.weight_decay = (float)weight_decay; a.grad_scale = (float)grad_scale;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   adam_kernel<<<ew_grid(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, a, static_cast<bf16*>(shadow_bf16));
   count_launch();

@@ -151,3 +151,30 @@ def test_live_reference_agrees_when_present():
     assert abs(float(loss) - float(scal["loss"])) < 1e-12
     for k, p in m.named_parameters():
         assert rel_err(grads[k], p.grad.numpy()) < 1e-11, k
+
+
+def test_torch_port_matches_golden():
+    """oracle/torch_port.py (the CPU baseline bench.py times) against the fixtures from the unmodified reference."""
+    import torch
+
+    from oracle import torch_port as T
+
+    torch.set_float32_matmul_precision("highest")
+    z, cfg = load("train_d256_c2")
+    params = case_params(cfg, np.float64)
+    mod = T.TorchStep(cfg["D"], cfg["L"], 2).double()
+    sd = {}
+    for k, v in params.items():
+        sd[k.replace("classifier.layers.0", "classifier")] = torch.from_numpy(v)
+    mod.load_state_dict(sd)
+    opt = torch.optim.Adam(mod.parameters(), lr=1e-3)
+    for s in range(cfg.get("steps", 3)):
+        x, y, eps = case_batch(cfg, s, np.float64)
+        opt.zero_grad()
+        loss = mod.loss(torch.from_numpy(x), torch.from_numpy(y), torch.from_numpy(eps))
+        loss.backward()
+        assert abs(float(loss) - float(z[f"f64/step{s}/log/train_loss"])) < 1e-12
+        opt.step()
+        for k, p in mod.named_parameters():
+            key = k.replace("classifier.", "classifier.layers.0.") if k.startswith("classifier.") else k
+            check_summary(z, f"f64/step{s}/param", key, p.detach().numpy(), 1e-10)
