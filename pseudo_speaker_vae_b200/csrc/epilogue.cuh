@@ -34,6 +34,7 @@ template <int ACT> __device__ __forceinline__ float act_grad_from_out(float a) {
 template <typename TOut, int ACT>
 struct EpiBiasAct {
   static constexpr bool kReduce = false;
+  static constexpr bool kColSum = false;
   const float* bias;   // [N] or nullptr
   TOut* out;
   int64_t ldo;
@@ -46,9 +47,11 @@ struct EpiBiasAct {
   }
 };
 
-template <typename TOut>
+// CS: the tcgen05 engine also emits the column sums of the stored gradient (= the bias gradient of the last decoder layer)
+template <typename TOut, bool CS = false>
 struct EpiMse {
   static constexpr bool kReduce = true;
+  static constexpr bool kColSum = CS;
   const float* bias;   // [N]
   const float* x;      // [M, ldx] fp32 target
   int64_t ldx;
@@ -58,6 +61,7 @@ struct EpiMse {
   int64_t ldd;
   float scale;
   float* red_out;      // one slot per CTA: sum of squared differences
+  float* colsum;       // CS: [CTAs][N] partial column sums of dxh
   template <int NV>
   __device__ __forceinline__ void apply(int64_t row, int col, float (&v)[NV], float& red, int split) const {
     float xv[NV];
@@ -75,15 +79,18 @@ struct EpiMse {
   }
 };
 
-template <typename TAct, typename TOut, int ACT>
+// CS: also emit the column sums of the stored gradient (= the bias gradient of the layer below)
+template <typename TAct, typename TOut, int ACT, bool CS = false>
 struct EpiActGrad {
   static constexpr bool kReduce = false;
+  static constexpr bool kColSum = CS;
   const TAct* act;     // forward activation (post-activation) [M, lda]
   int64_t lda;
   TOut* out;
   int64_t ldo;
   float beta;          // out = acc * act'(.) + beta * out   (sum over classifier heads)
   float* red_out;
+  float* colsum;       // CS: [CTAs][N] partial column sums of the output
   template <int NV>
   __device__ __forceinline__ void apply(int64_t row, int col, float (&v)[NV], float& red, int split) const {
     float a[NV];
@@ -102,6 +109,7 @@ struct EpiActGrad {
 
 struct EpiStore {
   static constexpr bool kReduce = false;
+  static constexpr bool kColSum = false;
   float* out;
   int64_t ldo;
   int64_t split_stride;  // elements between split-K partials

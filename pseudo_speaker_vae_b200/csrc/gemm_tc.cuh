@@ -14,6 +14,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "ptx.cuh"
@@ -32,6 +34,25 @@ template <int BN> struct TcCfg {
   static constexpr int kTmemCols = 2 * BN;     // power of two >= 32 for BN in {64,128,256}
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
+
+// Column sums of a 32(lanes = rows) x 32(registers = columns) block: afterwards lane l holds sum over the 32 lanes of v[l].
+// Butterfly that halves the number of live values per lane at every step: 16+8+4+2+1 = 31 shuffles.
+__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool upper = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < off; ++i) {
+      const float send = upper ? v[i] : v[i + off];
+      const float keep = upper ? v[i + off] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+template <class Epi, class = void> struct epi_colsum : std::false_type {};
+template <class Epi> struct epi_colsum<Epi, std::enable_if_t<Epi::kColSum>> : std::true_type {};
 
 struct TcShape {
   int64_t M;        // rows of C
@@ -56,6 +77,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
   float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);
+  // bias-gradient column sums (Epi::kColSum): one private slice per epilogue warp, [TC_EPI_WARPS][n_tiles * BN/2] floats,
+  // accumulated in program order over the CTA's static tile sequence -> deterministic
+  constexpr bool kCS = epi_colsum<Epi>::value;
+  float* cs_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -86,6 +111,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int64_t kb_total = (s.K + TC_BK - 1) / TC_BK;
   const int64_t kb_per_split = (kb_total + s.splits - 1) / s.splits;
   const int64_t num_tiles = m_tiles * n_tiles * s.splits;
+  const int cs_slice = (int)n_tiles * (BN / 2);
+  if constexpr (kCS) {
+    for (int i = threadIdx.x; i < TC_EPI_WARPS * cs_slice; i += TC_THREADS) cs_smem[i] = 0.f;
+    __syncthreads();
+  }
 
   float red = 0.f;
 
@@ -203,6 +233,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
         }
+        if constexpr (kCS) {
+          // v now holds what apply<32> stored (the host enables kColSum only when N % 32 == 0); rows past M contribute zeros.
+          // Whole-warp shuffle: outside any lane-divergent branch.
+          if (row >= s.M) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          }
+          const float cs = warp_transpose_reduce32(v, lane);
+          cs_smem[ew * cs_slice + (int)n_t * (BN / 2) + c + lane] += cs;
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -213,6 +253,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   // ============================ teardown ==================================
   ptx::tc_fence_before();
   __syncthreads();
+  if constexpr (kCS) {
+    // fixed-order sum of the four row-quarter slices that saw each column -> one partial row per CTA
+    for (int cidx = threadIdx.x; cidx < s.N; cidx += TC_THREADS) {
+      const int nt = cidx / BN, within = cidx % BN, hf = within / (BN / 2), idx = nt * (BN / 2) + within % (BN / 2);
+      float t = 0.f;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) t += cs_smem[(hf * 4 + q) * cs_slice + idx];
+      epi.colsum[(int64_t)blockIdx.x * s.N + cidx] = t;
+    }
+  }
   if constexpr (Epi::kReduce) {
     const float ws = warp_sum(red);
     if (lane == 0) red_smem[warp] = ws;
@@ -272,18 +322,32 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
   if (!(attr_mask >> (dev & 63) & 1ull)) {
-    PSVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    PSVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_mask |= 1ull << (dev & 63);
   }
   const int64_t tiles = ceil_div64(M, TC_BM) * ceil_div64(N, BN) * s.splits;
+  int smem_bytes = Cfg::kSmemBytes;
+  if constexpr (epi_colsum<Epi>::value) {
+    const int64_t cs_bytes = (int64_t)TC_EPI_WARPS * ceil_div64(N, BN) * (BN / 2) * (int64_t)sizeof(float);
+    if (N % 32 != 0 || smem_bytes + cs_bytes > 227 * 1024) { set_error("gemm_tc: column sums need N %% 32 == 0 and N <= ~2048 (N=%d)", N); return -2; }
+    smem_bytes += (int)cs_bytes;
+  }
   int grid = tc_grid_size();
   if (grid_limit > 0 && grid_limit < grid) grid = grid_limit;
   if (tiles < grid) grid = (int)tiles;
   if (grid < 1) return 0;
-  kern<<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, s, epi);
+  kern<<<grid, TC_THREADS, smem_bytes, st>>>(ta, tb, s, epi);
   count_launch();
   PSVAE_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
+}
+
+// can the tcgen05 epilogue produce the column sums of an [M, N] output? (see gemm_tc_launch_bn)
+static inline bool tc_colsum_ok(int N, int force_bn = 0) {
+  const int bn = force_bn ? force_bn : tc_pick_bn(N);
+  const int64_t cs_bytes = (int64_t)TC_EPI_WARPS * ceil_div64(N, bn) * (bn / 2) * (int64_t)sizeof(float);
+  const int base = bn == 256 ? TcCfg<256>::kSmemBytes : (bn == 128 ? TcCfg<128>::kSmemBytes : TcCfg<64>::kSmemBytes);
+  return N % 32 == 0 && base + cs_bytes <= 227 * 1024;
 }
 
 // number of reduction slots a kReduce epilogue needs (one per CTA of the persistent grid)

@@ -374,3 +374,185 @@ __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ 
 }
 
 }  // namespace psvae
+
+namespace psvae {
+
+// ---------------------------------------------------------------- fused latent classifier (no trunk: Linear(L, C) heads)
+// lightning.py:73-83 + its backward in one pass over mu: logits, log-softmax, NLL, accuracy, dlogits, dmu_clf = sum_h dlogits_h W_h,
+// and per-block partial sums of dW_h = dlogits_h^T mu, db_h = colsum(dlogits_h).  One warp per row, lane l owns latent dims
+// [l*LPL, (l+1)*LPL).  C is 2..3 per head: far below any tensor-core tile, and the whole thing is one read of mu.
+constexpr int CLF_MAXC = 8;     // classes summed over all heads
+struct ClfFusedArgs {
+  int n_heads, total_classes;
+  int head_classes[4], head_off[4];
+  int64_t w_off[4], b_off[4];
+  float gscale;                 // clf_w / (B * n_heads)
+  int write_grad;
+};
+__host__ __device__ __forceinline__ int clf_part_len(int L) { return 8 + CLF_MAXC * L + CLF_MAXC; }   // nll[4] acc[4] dW[8][L] db[8]
+
+template <int LPL>
+__global__ void __launch_bounds__(256) clf_fused_kernel(const float* __restrict__ params, const float* __restrict__ mu, const int64_t* __restrict__ y,
+                                                        int64_t B, ClfFusedArgs a, float* __restrict__ dmu_clf, float* __restrict__ part) {
+  constexpr int L = 32 * LPL;
+  extern __shared__ float clf_smem[];       // [8 warps][clf_part_len(L)]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int PART = clf_part_len(L);
+  float W[CLF_MAXC][LPL], bias[CLF_MAXC], accW[CLF_MAXC][LPL], accb[CLF_MAXC], nll[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int c = 0; c < CLF_MAXC; ++c) {
+    bias[c] = 0.f; accb[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < LPL; ++i) { W[c][i] = 0.f; accW[c][i] = 0.f; }
+  }
+  for (int h = 0; h < a.n_heads; ++h)
+    for (int cc = 0; cc < a.head_classes[h]; ++cc) {
+      const int c = a.head_off[h] + cc;
+#pragma unroll
+      for (int k = 0; k < CLF_MAXC; ++k)
+        if (k == c) {
+          bias[k] = params[a.b_off[h] + cc];
+#pragma unroll
+          for (int i = 0; i < LPL; ++i) W[k][i] = params[a.w_off[h] + (int64_t)cc * L + lane * LPL + i];
+        }
+    }
+  const int64_t warps_total = (int64_t)gridDim.x * 8;
+  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < B; r += warps_total) {
+    float m[LPL];
+    load_vec<LPL>(mu + r * L + lane * LPL, m);
+    float logit[CLF_MAXC];
+#pragma unroll
+    for (int c = 0; c < CLF_MAXC; ++c) {
+      float t = 0.f;
+#pragma unroll
+      for (int i = 0; i < LPL; ++i) t = fmaf(m[i], W[c][i], t);
+      logit[c] = (c < a.total_classes) ? warp_sum(t) + bias[c] : 0.f;     // total_classes is warp-uniform
+    }
+    float dmu[LPL];
+#pragma unroll
+    for (int i = 0; i < LPL; ++i) dmu[i] = 0.f;
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      if (h >= a.n_heads) break;
+      const int c0 = a.head_off[h], C = a.head_classes[h];
+      const int t = (int)y[(int64_t)h * B + r];
+      float mx = -INFINITY, lt = 0.f;
+      int arg = 0;
+#pragma unroll
+      for (int c = 0; c < CLF_MAXC; ++c)
+        if (c >= c0 && c < c0 + C) {
+          if (logit[c] > mx) { mx = logit[c]; arg = c - c0; }       // first maximum, like torch.argmax
+          if (c - c0 == t) lt = logit[c];
+        }
+      float se = 0.f;
+#pragma unroll
+      for (int c = 0; c < CLF_MAXC; ++c)
+        if (c >= c0 && c < c0 + C) se += expf(logit[c] - mx);
+      const float lse = logf(se);
+      nll[h] += -(lt - mx - lse);
+      acc[h] += (arg == t) ? 1.f : 0.f;
+      if (a.write_grad) {
+#pragma unroll
+        for (int c = 0; c < CLF_MAXC; ++c)
+          if (c >= c0 && c < c0 + C) {
+            const float g = (expf(logit[c] - mx - lse) - ((c - c0) == t ? 1.f : 0.f)) * a.gscale;
+            accb[c] += g;
+#pragma unroll
+            for (int i = 0; i < LPL; ++i) {
+              dmu[i] = fmaf(g, W[c][i], dmu[i]);
+              accW[c][i] = fmaf(g, m[i], accW[c][i]);
+            }
+          }
+      }
+    }
+    if (a.write_grad && dmu_clf) store_vec<LPL>(dmu_clf + r * L + lane * LPL, dmu);
+  }
+  // per-warp slices -> fixed-order block sum -> one partial row per block
+  float* mine = clf_smem + warp * PART;
+  if (lane == 0) {
+#pragma unroll
+    for (int h = 0; h < 4; ++h) { mine[h] = nll[h]; mine[4 + h] = acc[h]; }
+#pragma unroll
+    for (int c = 0; c < CLF_MAXC; ++c) mine[8 + CLF_MAXC * L + c] = accb[c];
+  }
+#pragma unroll
+  for (int c = 0; c < CLF_MAXC; ++c)
+#pragma unroll
+    for (int i = 0; i < LPL; ++i) mine[8 + c * L + lane * LPL + i] = accW[c][i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < PART; i += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int w8 = 0; w8 < 8; ++w8) t += clf_smem[w8 * PART + i];
+    part[(int64_t)blockIdx.x * PART + i] = t;
+  }
+}
+
+// sum the per-block partials in block order and scatter: nll/acc sums -> sums[8], dW/db -> the flat gradient buffer
+__global__ void __launch_bounds__(256) clf_fused_finish_kernel(const float* __restrict__ part, int blocks, int L, ClfFusedArgs a, float* __restrict__ sums,
+                                                               float* __restrict__ grads) {
+  const int PART = clf_part_len(L);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= PART) return;
+  float t = 0.f;
+  for (int b = 0; b < blocks; ++b) t += part[(int64_t)b * PART + i];
+  if (i < 8) { sums[i] = t; return; }
+  if (!a.write_grad || !grads) return;
+  int c, k = -1;
+  if (i < 8 + CLF_MAXC * L) { c = (i - 8) / L; k = (i - 8) % L; } else { c = i - 8 - CLF_MAXC * L; }
+  for (int h = 0; h < a.n_heads; ++h)
+    if (c >= a.head_off[h] && c < a.head_off[h] + a.head_classes[h]) {
+      const int cc = c - a.head_off[h];
+      if (k >= 0) grads[a.w_off[h] + (int64_t)cc * L + k] = t;
+      else grads[a.b_off[h] + cc] = t;
+    }
+}
+
+// ---------------------------------------------------------------- latent backward with fused bias gradients
+// As latent_bwd_kernel, plus the column sums of dmu and dls (= bias gradients of the encoders' last Linear): every thread always
+// owns the same 4 latent columns (the grid stride is a multiple of L/4), so it sums them privately; block partials [blocks][2L].
+template <typename TAct>
+__global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
+                                                            const float* __restrict__ eps, uint64_t seed, uint64_t offset, int64_t first_elem,
+                                                            int64_t n_elems, int L, const float* __restrict__ dmu_clf, float kl_over_b,
+                                                            TAct* __restrict__ dmu, TAct* __restrict__ dls, float* __restrict__ partials) {
+  extern __shared__ float lb_smem[];        // [256][8]
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nq = n_elems >> 2;
+  float sm_[4] = {0.f, 0.f, 0.f, 0.f}, sl_[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    float g[4], m[4], l[4], e[4], c[4] = {0.f, 0.f, 0.f, 0.f}, om[4], ol[4];
+    load_vec<4>(dz + (i << 2), g);
+    load_vec<4>(mu + (i << 2), m);
+    load_vec<4>(ls + (i << 2), l);
+    if (dmu_clf) load_vec<4>(dmu_clf + (i << 2), c);
+    if (eps) {
+      load_vec<4>(eps + (i << 2), e);
+    } else {
+      const float4 t = philox_normal4(((uint64_t)first_elem >> 2) + (uint64_t)i, seed, offset);
+      e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float sigma = expf(0.5f * l[j]);
+      om[j] = g[j] + kl_over_b * m[j] + c[j];
+      ol[j] = g[j] * e[j] * (0.5f * sigma) + 0.5f * kl_over_b * expm1f(l[j]);
+      sm_[j] += om[j];
+      sl_[j] += ol[j];
+    }
+    store_vec<4>(dmu + (i << 2), om);
+    store_vec<4>(dls + (i << 2), ol);
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { lb_smem[threadIdx.x * 8 + j] = sm_[j]; lb_smem[threadIdx.x * 8 + 4 + j] = sl_[j]; }
+  __syncthreads();
+  const int qpr = L >> 2;                   // quads per row; 256 % qpr == 0 (host-checked)
+  if ((int)threadIdx.x < 2 * L) {
+    const int which = threadIdx.x / L, col = threadIdx.x % L, quad = col >> 2, j = col & 3;
+    float t = 0.f;
+    for (int th = quad; th < 256; th += qpr) t += lb_smem[th * 8 + which * 4 + j];
+    partials[(int64_t)blockIdx.x * 2 * L + threadIdx.x] = t;
+  }
+}
+
+}  // namespace psvae

