@@ -1,13 +1,17 @@
-// Fused GEMM epilogues shared by the fp32 CUDA-core engine (sgemm.cuh) and the tcgen05 engine
-// (gemm_tc.cuh).  An epilogue sees one row fragment at a time: NV consecutive accumulator columns
-// of one output row, fully inside the matrix, and may add to a per-thread reduction value that the
-// engine sums over the CTA and stores (deterministically, one slot per CTA / tile).
+// Fused GEMM epilogues shared by the fp32 CUDA-core engine (sgemm.cuh) and the tcgen05 engine (gemm_tc.cuh).
 //
 // They implement, in the producing kernel, the element-wise tail of each reference op:
 //   EpiBiasAct   nn.Linear bias + ReLU (model.py:14-36) / classifier activations (latent_classifier.py:18-23)
 //   EpiMse       mse_loss(x_hat, x)/10 and its gradient 2(x_hat-x)/(B*D*10) (lightning.py:113)
 //   EpiActGrad   dgrad * act'(.) (autograd of ReLU etc.)
 //   EpiStore     plain alpha*acc (+ beta*old): split-K wgrad partials, classifier dgrads
+//
+// Two entry points per functor:
+//   apply<NV>(row, col, v, red, split)      -- sgemm: transform NV consecutive accumulator columns of one row AND store them;
+//   tc_transform(row, col, N, valid, v, aux, red) -- tcgen05: transform 32 columns in registers only.  The engine then rounds to
+//       TOut, stages the 32x32 block in shared memory and writes it with one TMA store (coalesced, clipped at the matrix edge);
+//       `aux` is the functor's auxiliary 32x32 bf16 tile (kAux: the forward activation for EpiActGrad) which the engine fetched by
+//       TMA load.  kColSum: the engine also emits the column sums of what was stored (bias gradients); kReduce: per-CTA sum of `red`.
 #pragma once
 #include "common.cuh"
 
@@ -31,10 +35,10 @@ template <int ACT> __device__ __forceinline__ float act_grad_from_out(float a) {
   else return 1.f;
 }
 
-template <typename TOut, int ACT>
+template <typename TOut_, int ACT>
 struct EpiBiasAct {
-  static constexpr bool kReduce = false;
-  static constexpr bool kColSum = false;
+  using TOut = TOut_;
+  static constexpr bool kReduce = false, kColSum = false, kAux = false, kSplit = false;
   const float* bias;   // [N] or nullptr
   TOut* out;
   int64_t ldo;
@@ -45,23 +49,27 @@ struct EpiBiasAct {
     for (int i = 0; i < NV; ++i) v[i] = act_fwd<ACT>(v[i] + (bias ? __ldg(bias + col + i) : 0.f));
     store_vec<NV>(out + row * ldo + col, v);
   }
+  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], float& red) const {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i] + ((bias && col + i < N) ? __ldg(bias + col + i) : 0.f));
+  }
 };
 
 // CS: the tcgen05 engine also emits the column sums of the stored gradient (= the bias gradient of the last decoder layer)
-template <typename TOut, bool CS = false>
+template <typename TOut_, bool CS = false>
 struct EpiMse {
-  static constexpr bool kReduce = true;
-  static constexpr bool kColSum = CS;
+  using TOut = TOut_;
+  static constexpr bool kReduce = true, kColSum = CS, kAux = false, kSplit = false;
   const float* bias;   // [N]
   const float* x;      // [M, ldx] fp32 target
   int64_t ldx;
   float* x_hat;        // optional fp32 output [M, ldxh]
   int64_t ldxh;
-  TOut* dxh;           // optional gradient output (x_hat - x) * scale
-  int64_t ldd;
+  TOut* out;           // gradient output (x_hat - x) * scale   (may be nullptr for sgemm when no gradients are wanted)
+  int64_t ldo;
   float scale;
   float* red_out;      // one slot per CTA: sum of squared differences
-  float* colsum;       // CS: [CTAs][N] partial column sums of dxh
+  float* colsum;       // CS: [4 * CTAs][N] partial column sums of the gradient
   template <int NV>
   __device__ __forceinline__ void apply(int64_t row, int col, float (&v)[NV], float& red, int split) const {
     float xv[NV];
@@ -75,22 +83,51 @@ struct EpiMse {
       red = fmaf(d, d, red);
       v[i] = d * scale;
     }
-    if (dxh) store_vec<NV>(dxh + row * ldd + col, v);
+    if (out) store_vec<NV>(out + row * ldo + col, v);
+  }
+  // x is read (and x_hat written) straight from/to global memory here: one GEMM per step, and x is fp32 (twice the tile bytes)
+  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], float& red) const {
+    if (valid && col + 32 <= N) {
+      float xv[32];
+      load_vec<32>(x + row * ldx + col, xv);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] += __ldg(bias + col + i);
+      if (x_hat) store_vec<32>(x_hat + row * ldxh + col, v);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float d = v[i] - xv[i];
+        red = fmaf(d, d, red);
+        v[i] = d * scale;
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float o = 0.f;
+        if (valid && col + i < N) {
+          const float h = v[i] + __ldg(bias + col + i);
+          if (x_hat) x_hat[row * ldxh + col + i] = h;
+          const float d = h - x[row * ldx + col + i];
+          red = fmaf(d, d, red);
+          o = d * scale;
+        }
+        v[i] = o;
+      }
+    }
   }
 };
 
 // CS: also emit the column sums of the stored gradient (= the bias gradient of the layer below)
-template <typename TAct, typename TOut, int ACT, bool CS = false>
+template <typename TAct, typename TOut_, int ACT, bool CS = false>
 struct EpiActGrad {
-  static constexpr bool kReduce = false;
-  static constexpr bool kColSum = CS;
+  using TOut = TOut_;
+  static constexpr bool kReduce = false, kColSum = CS, kAux = true, kSplit = false;
   const TAct* act;     // forward activation (post-activation) [M, lda]
   int64_t lda;
   TOut* out;
   int64_t ldo;
-  float beta;          // out = acc * act'(.) + beta * out   (sum over classifier heads)
+  float beta;          // sgemm only: out = acc * act'(.) + beta * out   (sum over classifier heads)
   float* red_out;
-  float* colsum;       // CS: [CTAs][N] partial column sums of the output
+  float* colsum;       // CS: [4 * CTAs][N] partial column sums of the output
   template <int NV>
   __device__ __forceinline__ void apply(int64_t row, int col, float (&v)[NV], float& red, int split) const {
     float a[NV];
@@ -105,15 +142,19 @@ struct EpiActGrad {
     }
     store_vec<NV>(out + row * ldo + col, v);
   }
+  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], float& red) const {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= act_grad_from_out<ACT>(aux[i]);
+  }
 };
 
 struct EpiStore {
-  static constexpr bool kReduce = false;
-  static constexpr bool kColSum = false;
+  using TOut = float;
+  static constexpr bool kReduce = false, kColSum = false, kAux = false, kSplit = true;
   float* out;
   int64_t ldo;
   int64_t split_stride;  // elements between split-K partials
-  float alpha, beta;
+  float alpha, beta;     // beta is honoured by the sgemm engine only
   float* red_out;
   template <int NV>
   __device__ __forceinline__ void apply(int64_t row, int col, float (&v)[NV], float& red, int split) const {
@@ -128,6 +169,10 @@ struct EpiStore {
       for (int i = 0; i < NV; ++i) v[i] *= alpha;
     }
     store_vec<NV>(p, v);
+  }
+  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], float& red) const {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] *= alpha;
   }
 };
 

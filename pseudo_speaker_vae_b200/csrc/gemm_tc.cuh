@@ -1,14 +1,20 @@
 // tcgen05 GEMM engine for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  through a fused epilogue.
 //
-//   * persistent, one CTA per SM, static round-robin tile schedule;
+//   * persistent, one CTA per SM, static round-robin tile schedule (m fastest, so a CTA walks the N tiles in order);
 //   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one thread issues
-//     tcgen05.mma), warps 2..9 = epilogue (TMEM -> registers -> fused epilogue -> global);
+//     tcgen05.mma), warps 2..9 = epilogue;
 //   * operands bf16, staged by TMA (cp.async.bulk.tensor, 128B swizzle) through a STAGES-deep mbarrier
 //     ring; fp32 accumulators live in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i
 //     overlaps the MMAs of tile i+1;
 //   * both operands may be K-major (row-major [rows][K]) or MN-major (stored [K][rows]): dgrad consumes W
 //     as stored and wgrad contracts over the batch, so no transposed copies exist anywhere;
-//   * optional split-K (wgrad: K = batch) -- partials go through EpiStore's split slot.
+//   * optional split-K (wgrad: K = batch) -- partials go to a [splits][M][N] buffer through a 3-D store map;
+//   * epilogue: TMEM -> registers (tcgen05.ld, lane = row) -> functor -> round to the output type -> 32x32 block
+//     staged in a per-warp swizzled shared-memory buffer -> ONE TMA store per block (coalesced 64/128-byte rows,
+//     clipped at the matrix edge by the hardware).  A row-per-lane st.global would cost 32 L1 wavefronts per
+//     instruction and made the first version of this kernel LSU-bound (profiles/r01_notes.md).  The auxiliary
+//     tile of EpiActGrad (the forward activation) comes in the same way by TMA load.  Bias-gradient column sums
+//     (kColSum) are read back out of the staged block and kept in registers across the CTA's tiles.
 //
 // Tile: 128 x BN x 64 (UMMA 128 x BN x 16, cta_group::1).
 #pragma once
@@ -25,6 +31,8 @@ namespace psvae {
 constexpr int TC_BM = 128, TC_BK = 64, TC_UMMA_K = 16;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);
+constexpr int TC_EPI_WARP_BYTES = 4096;   // per epilogue warp: fp32 block (32 x 128 B) or bf16 block + bf16 aux block (2 x 32 x 64 B)
+constexpr int TC_BAR_BYTES = 512;
 
 template <int BN> struct TcCfg {
   static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
@@ -32,27 +40,10 @@ template <int BN> struct TcCfg {
   static constexpr int kBBytes = BN * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BN;     // power of two >= 32 for BN in {64,128,256}
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kEpiOff = kStages * kStageBytes;
+  static constexpr int kBarOff = kEpiOff + TC_EPI_WARPS * TC_EPI_WARP_BYTES;
+  static constexpr int kSmemBytes = kBarOff + TC_BAR_BYTES + 1024 /*align slack*/;
 };
-
-// Column sums of a 32(lanes = rows) x 32(registers = columns) block: afterwards lane l holds sum over the 32 lanes of v[l].
-// Butterfly that halves the number of live values per lane at every step: 16+8+4+2+1 = 31 shuffles.
-__device__ __forceinline__ float warp_transpose_reduce32(float (&v)[32], int lane) {
-#pragma unroll
-  for (int off = 16; off >= 1; off >>= 1) {
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < off; ++i) {
-      const float send = upper ? v[i] : v[i + off];
-      const float keep = upper ? v[i + off] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  return v[0];
-}
-
-template <class Epi, class = void> struct epi_colsum : std::false_type {};
-template <class Epi> struct epi_colsum<Epi, std::enable_if_t<Epi::kColSum>> : std::true_type {};
 
 struct TcShape {
   int64_t M;        // rows of C
@@ -62,31 +53,42 @@ struct TcShape {
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // UMMA smem-descriptor strides (bytes)
 };
 
+// byte offset of 16-byte chunk j of row r inside a staged 32-row block whose rows are ROWB bytes (TMA swizzle = ROWB)
+template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
+  if constexpr (ROWB == 128) return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));       // SWIZZLE_128B: addr[4:6] ^= addr[7:9]
+  else return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));                      // SWIZZLE_64B:  addr[4:5] ^= addr[7:8]
+}
+
 template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, TcShape s, Epi epi) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
+               const __grid_constant__ CUtensorMap tma_aux, TcShape s, Epi epi) {
   using Cfg = TcCfg<BN>;
+  using TOut = typename Epi::TOut;
   constexpr int STAGES = Cfg::kStages;
+  constexpr int ROWB = 32 * (int)sizeof(TOut);            // bytes per staged row: 64 (bf16) or 128 (fp32)
+  constexpr int OUT_BYTES = 32 * ROWB;
+  static_assert(!(Epi::kAux && sizeof(TOut) != 2), "an auxiliary tile needs the 2 KB bf16 output block");
+  static_assert(!(Epi::kColSum && sizeof(TOut) != 2), "column sums are read back from a bf16 block");
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOff);
   uint64_t* full_bar = bars;                 // [STAGES]  TMA -> MMA
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* aux_bar = bars + 2 * STAGES + 4;     // [TC_EPI_WARPS] aux tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + TC_EPI_WARPS);
   float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);
-  // bias-gradient column sums (Epi::kColSum): one private slice per epilogue warp, [TC_EPI_WARPS][n_tiles * BN/2] floats,
-  // accumulated in program order over the CTA's static tile sequence -> deterministic
-  constexpr bool kCS = epi_colsum<Epi>::value;
-  float* cs_smem = reinterpret_cast<float*>(smem + STAGES * Cfg::kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tma_a);
     ptx::prefetch_tensormap(&tma_b);
+    ptx::prefetch_tensormap(&tma_out);
+    if constexpr (Epi::kAux) ptx::prefetch_tensormap(&tma_aux);
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
@@ -95,6 +97,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], TC_EPI_WARPS);
     }
+    for (int i = 0; i < TC_EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -111,11 +114,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int64_t kb_total = (s.K + TC_BK - 1) / TC_BK;
   const int64_t kb_per_split = (kb_total + s.splits - 1) / s.splits;
   const int64_t num_tiles = m_tiles * n_tiles * s.splits;
-  const int cs_slice = (int)n_tiles * (BN / 2);
-  if constexpr (kCS) {
-    for (int i = threadIdx.x; i < TC_EPI_WARPS * cs_slice; i += TC_THREADS) cs_smem[i] = 0.f;
-    __syncthreads();
-  }
 
   float red = 0.f;
 
@@ -125,7 +123,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int64_t n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, sp = tile / (n_tiles * m_tiles);
+        const int64_t m_t = tile % m_tiles, n_t = (tile / m_tiles) % n_tiles, sp = tile / (n_tiles * m_tiles);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         for (int64_t kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
@@ -169,8 +167,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         if (kb0 >= kb1) {
-          // empty K range (more splits than K blocks): the epilogue must still see zeros -- issue nothing,
-          // signal immediately; the epilogue treats `kb0 >= kb1` as an all-zero accumulator.
+          // empty K range (the host never asks for one): the epilogue treats it as an all-zero accumulator
           ptx::umma_commit(&tfull_bar[acc]);
           continue;
         }
@@ -197,72 +194,150 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int quarter = warp & 3;            // TMEM lane quarter this warp may touch (warp id % 4)
     const int half = ew >> 2;                // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int CH = COLS_PER_WARP / 32;   // 32-column blocks per tile for this warp
+    uint8_t* obuf = smem + Cfg::kEpiOff + ew * TC_EPI_WARP_BYTES;     // staged output block
+    uint8_t* abuf = obuf + 2048;                                       // staged auxiliary block (kAux, bf16)
+    uint32_t aux_phase = 0;
+    const bool do_store = epi.out != nullptr;
+    float cs_acc[CH][2];                     // kColSum: this lane's two columns of every block of the current N tile
+#pragma unroll
+    for (int c = 0; c < CH; ++c) cs_acc[c][0] = cs_acc[c][1] = 0.f;
+    int64_t cs_nt = -1;
+    auto cs_flush = [&]() {
+      if constexpr (Epi::kColSum) {
+        if (cs_nt >= 0 && lane < 16) {
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const int col = (int)(cs_nt * BN) + half * COLS_PER_WARP + c * 32 + 2 * lane;
+            if (col + 1 < s.N) {
+              float* p = epi.colsum + ((int64_t)blockIdx.x * 4 + quarter) * s.N + col;
+              *reinterpret_cast<float2*>(p) = make_float2(cs_acc[c][0], cs_acc[c][1]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) cs_acc[c][0] = cs_acc[c][1] = 0.f;
+      }
+    };
     int64_t it = 0;
     for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int64_t n_t = tile % n_tiles, m_t = (tile / n_tiles) % m_tiles, sp = tile / (n_tiles * m_tiles);
+      const int64_t m_t = tile % m_tiles, n_t = (tile / m_tiles) % n_tiles, sp = tile / (n_tiles * m_tiles);
       const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
+      const int32_t row_base = (int32_t)(m_t * TC_BM) + quarter * 32;
+      const int64_t row = (int64_t)row_base + lane;
+      const bool valid = row < s.M;
+      const int col_base = (int)(n_t * BN) + half * COLS_PER_WARP;
+      if constexpr (Epi::kColSum) {
+        if (n_t != cs_nt) { cs_flush(); cs_nt = n_t; }
+      }
+      if constexpr (Epi::kAux) {             // fetch the first auxiliary block while the MMAs of this tile are still running
+        if (col_base < s.N && lane == 0) {
+          ptx::mbar_arrive_expect_tx(&aux_bar[ew], 2048);
+          ptx::tma_load_2d(abuf, &tma_aux, &aux_bar[ew], col_base, row_base);
+        }
+      }
       ptx::mbar_wait(&tfull_bar[acc], acc_phase, 4);
       ptx::tc_fence_after();
-      const int64_t row = m_t * TC_BM + quarter * 32 + lane;
       const bool zero_acc = kb0 >= kb1;
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += 32) {
-        const int col_in_tile = half * COLS_PER_WARP + c;
-        const int col = (int)(n_t * BN) + col_in_tile;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int col_in_tile = half * COLS_PER_WARP + c * 32;
+        const int col = col_base + c * 32;
+        if (col >= s.N) continue;            // warp-uniform
         float v[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_in_tile);
-        ptx::tmem_ld_32x32(taddr, v);         // warp-collective: executed by all lanes regardless of bounds
+        ptx::tmem_ld_32x32(taddr, v);
         if (zero_acc) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
-        if (row < s.M) {
-          if (col + 32 <= s.N) {
-            epi.template apply<32>(row, col, v, red, (int)sp);
-          } else {
+        float aux[32];
+        if constexpr (Epi::kAux) {
+          ptx::mbar_wait(&aux_bar[ew], aux_phase, 5);
+          aux_phase ^= 1;
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col + j + 8 <= s.N) {
-                float w[8];
+          for (int j = 0; j < 4; ++j) {
+            const uint4 u = *reinterpret_cast<const uint4*>(abuf + swz_off<64>(lane, j));
+            const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = v[j + i];
-                epi.template apply<8>(row, col + j, w, red, (int)sp);
-              }
+            for (int q = 0; q < 4; ++q) {
+              aux[j * 8 + 2 * q] = __uint_as_float(wv[q] << 16);
+              aux[j * 8 + 2 * q + 1] = __uint_as_float(wv[q] & 0xFFFF0000u);
             }
           }
-        }
-        if constexpr (kCS) {
-          // v now holds what apply<32> stored (the host enables kColSum only when N % 32 == 0); rows past M contribute zeros.
-          // Whole-warp shuffle: outside any lane-divergent branch.
-          if (row >= s.M) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) v[i] = 0.f;
+          __syncwarp();                      // every lane has read the block: it may be overwritten
+          if (col + 32 < s.N && c + 1 < CH && lane == 0) {
+            ptx::mbar_arrive_expect_tx(&aux_bar[ew], 2048);
+            ptx::tma_load_2d(abuf, &tma_aux, &aux_bar[ew], col + 32, row_base);
           }
-          const float cs = warp_transpose_reduce32(v, lane);
-          cs_smem[ew * cs_slice + (int)n_t * (BN / 2) + c + lane] += cs;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) aux[i] = 0.f;
+        }
+        epi.tc_transform(row, col, s.N, valid, v, aux, red);
+        if (do_store) {
+          if constexpr (Epi::kColSum) {      // rows past M must not reach the column sums
+            if (!valid) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            }
+          }
+          // the previous TMA store of this warp must have finished reading the staging block
+          if (lane == 0) ptx::bulk_wait_read0();
+          __syncwarp();
+          if constexpr (sizeof(TOut) == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 u;
+              u.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
+              u.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+              u.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
+              u.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+              *reinterpret_cast<uint4*>(obuf + swz_off<64>(lane, j)) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(obuf + swz_off<128>(lane, j)) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+          }
+          ptx::fence_proxy_async_smem();     // generic-proxy writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if constexpr (Epi::kColSum) {
+            // lanes 0-15 walk the even rows, 16-31 the odd rows; lane (l & 15) owns columns 2w, 2w+1 of the block
+            const int hw = lane >> 4, w = lane & 15;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+              const int r = 2 * rr + hw;
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(obuf + swz_off<64>(r, w >> 2) + (w & 3) * 4);
+              s0 += __uint_as_float(u << 16);
+              s1 += __uint_as_float(u & 0xFFFF0000u);
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            cs_acc[c][0] += s0;
+            cs_acc[c][1] += s1;
+          }
+          if (lane == 0) {
+            if constexpr (Epi::kSplit) ptx::tma_store_3d(&tma_out, obuf, col, row_base, (int32_t)sp);
+            else ptx::tma_store_2d(&tma_out, obuf, col, row_base);
+            ptx::bulk_commit();
+          }
         }
       }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
     }
+    cs_flush();
+    if (lane == 0) ptx::bulk_wait_all();     // shared memory must outlive the last store's read
   }
 
   // ============================ teardown ==================================
   ptx::tc_fence_before();
   __syncthreads();
-  if constexpr (kCS) {
-    // fixed-order sum of the four row-quarter slices that saw each column -> one partial row per CTA
-    for (int cidx = threadIdx.x; cidx < s.N; cidx += TC_THREADS) {
-      const int nt = cidx / BN, within = cidx % BN, hf = within / (BN / 2), idx = nt * (BN / 2) + within % (BN / 2);
-      float t = 0.f;
-#pragma unroll
-      for (int q = 0; q < 4; ++q) t += cs_smem[(hf * 4 + q) * cs_slice + idx];
-      epi.colsum[(int64_t)blockIdx.x * s.N + cidx] = t;
-    }
-  }
   if constexpr (Epi::kReduce) {
     const float ws = warp_sum(red);
     if (lane == 0) red_smem[warp] = ws;
@@ -292,9 +367,12 @@ struct TcOperand {
 
 // Encodes (and caches by value) the 2D tensor map of one operand.  Returns 0, or < 0 with the error text set.
 int tc_tensor_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out);
+// Tensor map of an epilogue block: [32 rows][32 cols] of a row-major [rows][cols] (x splits) matrix of 2- or 4-byte elements.
+int tc_block_map(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int64_t splits, int64_t split_stride, CUtensorMap* out);
 int tc_grid_size();       // number of SMs of the current device (persistent grid)
 int tc_device_check();    // 0 when the current device is sm_100
 void count_launch();
+
 // UMMA smem-descriptor strides of one staged operand tile (see the canonical layouts in ptx.cuh)
 static inline void tc_desc_strides(bool mn_major, uint32_t* lbo, uint32_t* sbo) {
   if (!mn_major) { *lbo = 16; *sbo = 8 * 128; }                 // K-major SW128: 8-row groups 1024 B apart; LBO unused
@@ -306,61 +384,79 @@ static inline int tc_pick_bn(int N) {
   if (N % 128 == 0) return 128;
   return 64;
 }
+// CTAs a launch uses (= rows / 4 of the kColSum partial buffer, = slots of a kReduce epilogue)
+static inline int64_t tc_ctas(int64_t M, int N, int splits, int force_bn = 0) {
+  const int bn = force_bn ? force_bn : tc_pick_bn(N);
+  int64_t tiles = ceil_div64(M, TC_BM) * ceil_div64(N, bn) * (splits < 1 ? 1 : splits);
+  const int64_t g = tc_grid_size();
+  return tiles < g ? tiles : g;
+}
+
+template <class Epi, class = void> struct epi_aux_ptr {
+  static const void* get(const Epi&) { return nullptr; }
+  static int64_t ld(const Epi&) { return 0; }
+};
+template <class Epi> struct epi_aux_ptr<Epi, std::enable_if_t<Epi::kAux>> {
+  static const void* get(const Epi& e) { return e.act; }
+  static int64_t ld(const Epi& e) { return e.lda; }
+};
+template <class Epi, class = void> struct epi_split_stride { static int64_t get(const Epi&) { return 0; } };
+template <class Epi> struct epi_split_stride<Epi, std::enable_if_t<Epi::kSplit>> { static int64_t get(const Epi& e) { return e.split_stride; } };
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
-int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, int grid_limit, cudaStream_t st) {
+int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
-  CUtensorMap ta, tb;
+  using TOut = typename Epi::TOut;
+  CUtensorMap ta, tb, tout, taux;
   PSVAE_TRY(tc_tensor_map(A, K, A_MN ? TC_BK : TC_BM, &ta));
   PSVAE_TRY(tc_tensor_map(B, K, B_MN ? TC_BK : BN, &tb));
   TcShape s;
   s.M = M; s.N = N; s.K = K; s.splits = splits < 1 ? 1 : splits;
   tc_desc_strides(A_MN, &s.a_lbo, &s.a_sbo);
   tc_desc_strides(B_MN, &s.b_lbo, &s.b_sbo);
+  if (epi.out) {
+    PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, N, epi.ldo, Epi::kSplit ? s.splits : 0, epi_split_stride<Epi>::get(epi), &tout));
+  } else {
+    tout = ta;   // never dereferenced: the kernel skips the store
+  }
+  if constexpr (Epi::kAux) {
+    PSVAE_TRY(tc_block_map(epi_aux_ptr<Epi>::get(epi), 2, M, N, epi_aux_ptr<Epi>::ld(epi), 0, 0, &taux));
+  } else {
+    taux = ta;
+  }
   auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi>;
   static unsigned long long attr_mask = 0;   // per instantiation, one bit per device
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
   if (!(attr_mask >> (dev & 63) & 1ull)) {
-    PSVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    PSVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_mask |= 1ull << (dev & 63);
   }
   const int64_t tiles = ceil_div64(M, TC_BM) * ceil_div64(N, BN) * s.splits;
-  int smem_bytes = Cfg::kSmemBytes;
-  if constexpr (epi_colsum<Epi>::value) {
-    const int64_t cs_bytes = (int64_t)TC_EPI_WARPS * ceil_div64(N, BN) * (BN / 2) * (int64_t)sizeof(float);
-    if (N % 32 != 0 || smem_bytes + cs_bytes > 227 * 1024) { set_error("gemm_tc: column sums need N %% 32 == 0 and N <= ~2048 (N=%d)", N); return -2; }
-    smem_bytes += (int)cs_bytes;
-  }
   int grid = tc_grid_size();
-  if (grid_limit > 0 && grid_limit < grid) grid = grid_limit;
   if (tiles < grid) grid = (int)tiles;
   if (grid < 1) return 0;
-  kern<<<grid, TC_THREADS, smem_bytes, st>>>(ta, tb, s, epi);
+  if constexpr (Epi::kColSum) {
+    // every (CTA, row-quarter) writes only the columns of the N tiles it saw: the rest of the partial buffer must read as zero
+    PSVAE_CUDA(cudaMemsetAsync(epi.colsum, 0, (size_t)grid * 4 * (size_t)N * sizeof(float), st));
+  }
+  kern<<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, tout, taux, s, epi);
   count_launch();
   PSVAE_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
 }
 
-// can the tcgen05 epilogue produce the column sums of an [M, N] output? (see gemm_tc_launch_bn)
-static inline bool tc_colsum_ok(int N, int force_bn = 0) {
-  const int bn = force_bn ? force_bn : tc_pick_bn(N);
-  const int64_t cs_bytes = (int64_t)TC_EPI_WARPS * ceil_div64(N, bn) * (bn / 2) * (int64_t)sizeof(float);
-  const int base = bn == 256 ? TcCfg<256>::kSmemBytes : (bn == 128 ? TcCfg<128>::kSmemBytes : TcCfg<64>::kSmemBytes);
-  return N % 32 == 0 && base + cs_bytes <= 227 * 1024;
-}
-
-// number of reduction slots a kReduce epilogue needs (one per CTA of the persistent grid)
-static inline int tc_red_slots() { return tc_grid_size(); }
+// can the tcgen05 epilogue produce the column sums of an [M, N] bf16 output?  (pairs of columns: N even; N % 8 is required anyway)
+static inline bool tc_colsum_ok(int N) { return N % 2 == 0; }
 
 template <bool A_MN, bool B_MN, class Epi>
 int gemm_tc_launch(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st, int force_bn = 0) {
   if (N % 8 != 0) { set_error("gemm_tc: N=%d must be a multiple of 8", N); return -2; }
   const int bn = force_bn ? force_bn : tc_pick_bn(N);
   switch (bn) {
-    case 256: return gemm_tc_launch_bn<256, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, 0, st);
-    case 128: return gemm_tc_launch_bn<128, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, 0, st);
-    case 64: return gemm_tc_launch_bn<64, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, 0, st);
+    case 256: return gemm_tc_launch_bn<256, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, st);
+    case 128: return gemm_tc_launch_bn<128, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, st);
+    case 64: return gemm_tc_launch_bn<64, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, st);
   }
   set_error("gemm_tc: unsupported BN=%d", bn);
   return -2;

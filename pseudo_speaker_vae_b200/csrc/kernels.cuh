@@ -234,6 +234,31 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
   out[i] = t * scale;
 }
 
+// out[i] = sum_s partials[s][i] for S >= 32 partial rows and few columns: block = 32 columns x 32 row lanes; row lane y sums rows
+// y, y+32, ... in order, then the 32 lane sums are added in a fixed order (deterministic)
+__global__ void __launch_bounds__(1024) reduce_tall_kernel(const float* __restrict__ partials, int n, int S, int64_t stride_s, float* __restrict__ out) {
+  __shared__ float sm[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  float t0 = 0.f, t1 = 0.f;
+  if (col < n) {
+    int s = ty;
+    for (; s + 32 < S; s += 64) {
+      t0 += partials[(int64_t)s * stride_s + col];
+      t1 += partials[(int64_t)(s + 32) * stride_s + col];
+    }
+    if (s < S) t0 += partials[(int64_t)s * stride_s + col];
+  }
+  sm[ty][tx] = t0 + t1;
+  __syncthreads();
+  if (ty == 0 && col < n) {
+    float t = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) t += sm[j][tx];
+    out[col] = t;
+  }
+}
+
 // ---------------------------------------------------------------- F.normalize(p=2, dim=1): one warp per row
 __global__ void __launch_bounds__(256) row_normalize_kernel(float* __restrict__ x, int64_t rows, int D) {
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -391,111 +416,150 @@ struct ClfFusedArgs {
 };
 __host__ __device__ __forceinline__ int clf_part_len(int L) { return 8 + CLF_MAXC * L + CLF_MAXC; }   // nll[4] acc[4] dW[8][L] db[8]
 
-template <int LPL>
-__global__ void __launch_bounds__(256) clf_fused_kernel(const float* __restrict__ params, const float* __restrict__ mu, const int64_t* __restrict__ y,
-                                                        int64_t B, ClfFusedArgs a, float* __restrict__ dmu_clf, float* __restrict__ part) {
-  constexpr int L = 32 * LPL;
-  extern __shared__ float clf_smem[];       // [8 warps][clf_part_len(L)]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+constexpr int CLF_TILE = 256;   // rows per block pass (= threads per block)
+static inline size_t clf_fused_smem_bytes(int L) { return ((size_t)CLF_TILE * (L + 1) + (size_t)CLF_TILE * CLF_MAXC + (size_t)CLF_MAXC * L + CLF_MAXC) * sizeof(float); }
+
+// A block stages a tile of 256 rows of mu in shared memory (read once from HBM, coalesced); then
+//   phase 2: thread = row: logits, log-softmax, NLL / accuracy, dlogits -> smem;
+//   phase 3: dmu_clf[row][k] = sum_c dlogits[row][c] W[c][k] written coalesced; thread = (class, latent dim): dW[c][k] += sum_rows dlogits[row][c] mu[row][k].
+__global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __restrict__ params, const float* __restrict__ mu, const int64_t* __restrict__ y,
+                                                             int64_t B, int L, ClfFusedArgs a, float* __restrict__ dmu_clf, float* __restrict__ part) {
+  extern __shared__ float clf_smem[];
+  __shared__ float scratch[32];
+  const int ldm = L + 1;
+  float* mu_s = clf_smem;                               // [256][L+1]
+  float* g_s = mu_s + CLF_TILE * ldm;                   // [256][8]
+  float* W_s = g_s + CLF_TILE * CLF_MAXC;               // [8][L]
+  float* b_s = W_s + CLF_MAXC * L;                      // [8]
+  const int t = threadIdx.x;
   const int PART = clf_part_len(L);
-  float W[CLF_MAXC][LPL], bias[CLF_MAXC], accW[CLF_MAXC][LPL], accb[CLF_MAXC], nll[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int c = 0; c < CLF_MAXC; ++c) {
-    bias[c] = 0.f; accb[c] = 0.f;
-#pragma unroll
-    for (int i = 0; i < LPL; ++i) { W[c][i] = 0.f; accW[c][i] = 0.f; }
+  for (int i = t; i < CLF_MAXC * L; i += CLF_TILE) W_s[i] = 0.f;
+  if (t < CLF_MAXC) b_s[t] = 0.f;
+  __syncthreads();
+  for (int h = 0; h < a.n_heads; ++h) {
+    for (int i = t; i < a.head_classes[h] * L; i += CLF_TILE) W_s[a.head_off[h] * L + i] = params[a.w_off[h] + i];
+    if (t < a.head_classes[h]) b_s[a.head_off[h] + t] = params[a.b_off[h] + t];
   }
-  for (int h = 0; h < a.n_heads; ++h)
-    for (int cc = 0; cc < a.head_classes[h]; ++cc) {
-      const int c = a.head_off[h] + cc;
-#pragma unroll
-      for (int k = 0; k < CLF_MAXC; ++k)
-        if (k == c) {
-          bias[k] = params[a.b_off[h] + cc];
-#pragma unroll
-          for (int i = 0; i < LPL; ++i) W[k][i] = params[a.w_off[h] + (int64_t)cc * L + lane * LPL + i];
-        }
+  float nll[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
+  float accW[2] = {0.f, 0.f}, accb = 0.f;
+  const int n_out = a.total_classes * L;                // dW elements; thread t owns t and t + 256
+  const int64_t tiles = (B + CLF_TILE - 1) / CLF_TILE;
+  const int qpr = L >> 2;
+  for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * CLF_TILE;
+    __syncthreads();                                    // previous pass is done with the tile buffers (and W_s is loaded)
+    for (int i = t; i < CLF_TILE * qpr; i += CLF_TILE) {
+      const int r = i / qpr, q = i % qpr;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + r < B) v = *reinterpret_cast<const float4*>(mu + (row0 + r) * L + 4 * q);
+      float* d = mu_s + r * ldm + 4 * q;
+      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
     }
-  const int64_t warps_total = (int64_t)gridDim.x * 8;
-  for (int64_t r = (int64_t)blockIdx.x * 8 + warp; r < B; r += warps_total) {
-    float m[LPL];
-    load_vec<LPL>(mu + r * L + lane * LPL, m);
-    float logit[CLF_MAXC];
+    __syncthreads();
+    {   // phase 2: one row per thread
+      const int64_t r = row0 + t;
+      float g[CLF_MAXC];
 #pragma unroll
-    for (int c = 0; c < CLF_MAXC; ++c) {
-      float t = 0.f;
+      for (int c = 0; c < CLF_MAXC; ++c) g[c] = 0.f;
+      if (r < B) {
+        float logit[CLF_MAXC];
 #pragma unroll
-      for (int i = 0; i < LPL; ++i) t = fmaf(m[i], W[c][i], t);
-      logit[c] = (c < a.total_classes) ? warp_sum(t) + bias[c] : 0.f;     // total_classes is warp-uniform
-    }
-    float dmu[LPL];
+        for (int c = 0; c < CLF_MAXC; ++c) logit[c] = b_s[c];
+        const float* m = mu_s + t * ldm;
+        for (int k = 0; k < L; ++k) {
+          const float mv = m[k];
 #pragma unroll
-    for (int i = 0; i < LPL; ++i) dmu[i] = 0.f;
-#pragma unroll
-    for (int h = 0; h < 4; ++h) {
-      if (h >= a.n_heads) break;
-      const int c0 = a.head_off[h], C = a.head_classes[h];
-      const int t = (int)y[(int64_t)h * B + r];
-      float mx = -INFINITY, lt = 0.f;
-      int arg = 0;
-#pragma unroll
-      for (int c = 0; c < CLF_MAXC; ++c)
-        if (c >= c0 && c < c0 + C) {
-          if (logit[c] > mx) { mx = logit[c]; arg = c - c0; }       // first maximum, like torch.argmax
-          if (c - c0 == t) lt = logit[c];
+          for (int c = 0; c < CLF_MAXC; ++c) logit[c] = fmaf(mv, W_s[c * L + k], logit[c]);
         }
-      float se = 0.f;
 #pragma unroll
-      for (int c = 0; c < CLF_MAXC; ++c)
-        if (c >= c0 && c < c0 + C) se += expf(logit[c] - mx);
-      const float lse = logf(se);
-      nll[h] += -(lt - mx - lse);
-      acc[h] += (arg == t) ? 1.f : 0.f;
-      if (a.write_grad) {
+        for (int h = 0; h < 4; ++h) {
+          if (h < a.n_heads) {
+            const int c0 = a.head_off[h], C = a.head_classes[h];
+            const int tgt = (int)y[(int64_t)h * B + r];
+            float mx = -INFINITY, lt = 0.f;
+            int arg = 0;
 #pragma unroll
-        for (int c = 0; c < CLF_MAXC; ++c)
-          if (c >= c0 && c < c0 + C) {
-            const float g = (expf(logit[c] - mx - lse) - ((c - c0) == t ? 1.f : 0.f)) * a.gscale;
-            accb[c] += g;
+            for (int c = 0; c < CLF_MAXC; ++c)
+              if (c >= c0 && c < c0 + C) {
+                if (logit[c] > mx) { mx = logit[c]; arg = c - c0; }        // first maximum, like torch.argmax
+                if (c - c0 == tgt) lt = logit[c];
+              }
+            float se = 0.f;
 #pragma unroll
-            for (int i = 0; i < LPL; ++i) {
-              dmu[i] = fmaf(g, W[c][i], dmu[i]);
-              accW[c][i] = fmaf(g, m[i], accW[c][i]);
-            }
+            for (int c = 0; c < CLF_MAXC; ++c)
+              if (c >= c0 && c < c0 + C) se += expf(logit[c] - mx);
+            const float lse = logf(se);
+            nll[h] += -(lt - mx - lse);
+            acc[h] += (arg == tgt) ? 1.f : 0.f;
+#pragma unroll
+            for (int c = 0; c < CLF_MAXC; ++c)
+              if (c >= c0 && c < c0 + C) g[c] = (expf(logit[c] - mx - lse) - ((c - c0) == tgt ? 1.f : 0.f)) * a.gscale;
           }
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < CLF_MAXC; ++c) g_s[t * CLF_MAXC + c] = g[c];
+    }
+    __syncthreads();
+    if (a.write_grad) {
+      if (dmu_clf) {
+        for (int i = t; i < CLF_TILE * L; i += CLF_TILE) {
+          const int r = i / L, k = i % L;
+          if (row0 + r < B) {
+            float v = 0.f;
+#pragma unroll
+            for (int c = 0; c < CLF_MAXC; ++c) v = fmaf(g_s[r * CLF_MAXC + c], W_s[c * L + k], v);
+            dmu_clf[(row0 + r) * L + k] = v;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int o = t + j * CLF_TILE;
+        if (o < n_out) {
+          const int c = o / L, k = o % L;
+          float v = 0.f;
+          for (int r = 0; r < CLF_TILE; ++r) v = fmaf(g_s[r * CLF_MAXC + c], mu_s[r * ldm + k], v);
+          accW[j] += v;
+        }
+      }
+      if (t < a.total_classes) {
+        float v = 0.f;
+        for (int r = 0; r < CLF_TILE; ++r) v += g_s[r * CLF_MAXC + t];
+        accb += v;
       }
     }
-    if (a.write_grad && dmu_clf) store_vec<LPL>(dmu_clf + r * L + lane * LPL, dmu);
   }
-  // per-warp slices -> fixed-order block sum -> one partial row per block
-  float* mine = clf_smem + warp * PART;
-  if (lane == 0) {
-#pragma unroll
-    for (int h = 0; h < 4; ++h) { mine[h] = nll[h]; mine[4 + h] = acc[h]; }
-#pragma unroll
-    for (int c = 0; c < CLF_MAXC; ++c) mine[8 + CLF_MAXC * L + c] = accb[c];
+  float* mine = part + (int64_t)blockIdx.x * PART;
+  for (int h = 0; h < 4; ++h) {
+    const float s1 = block_sum(nll[h], scratch);
+    const float s2 = block_sum(acc[h], scratch);
+    if (t == 0) { mine[h] = s1; mine[4 + h] = s2; }
   }
-#pragma unroll
-  for (int c = 0; c < CLF_MAXC; ++c)
-#pragma unroll
-    for (int i = 0; i < LPL; ++i) mine[8 + c * L + lane * LPL + i] = accW[c][i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < PART; i += 256) {
-    float t = 0.f;
-#pragma unroll
-    for (int w8 = 0; w8 < 8; ++w8) t += clf_smem[w8 * PART + i];
-    part[(int64_t)blockIdx.x * PART + i] = t;
+  for (int o = t; o < CLF_MAXC * L; o += CLF_TILE) mine[8 + o] = 0.f;
+  for (int j = 0; j < 2; ++j) {
+    const int o = t + j * CLF_TILE;
+    if (o < n_out) mine[8 + o] = accW[j];      // same thread wrote the zero above: program order
   }
+  if (t < CLF_MAXC) mine[8 + CLF_MAXC * L + t] = (t < a.total_classes) ? accb : 0.f;
 }
 
-// sum the per-block partials in block order and scatter: nll/acc sums -> sums[8], dW/db -> the flat gradient buffer
-__global__ void __launch_bounds__(256) clf_fused_finish_kernel(const float* __restrict__ part, int blocks, int L, ClfFusedArgs a, float* __restrict__ sums,
-                                                               float* __restrict__ grads) {
+// sum the per-block partials in block order (32 row lanes, fixed-order tree) and scatter: nll/acc sums -> sums[8], dW/db -> the flat gradient buffer
+__global__ void __launch_bounds__(1024) clf_fused_finish_kernel(const float* __restrict__ part, int blocks, int L, ClfFusedArgs a, float* __restrict__ sums,
+                                                                float* __restrict__ grads) {
+  __shared__ float sm[32][33];
   const int PART = clf_part_len(L);
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= PART) return;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + tx;
   float t = 0.f;
-  for (int b = 0; b < blocks; ++b) t += part[(int64_t)b * PART + i];
+  if (i < PART)
+    for (int b = ty; b < blocks; b += 32) t += part[(int64_t)b * PART + i];
+  sm[ty][tx] = t;
+  __syncthreads();
+  if (ty != 0 || i >= PART) return;
+  t = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) t += sm[j][tx];
   if (i < 8) { sums[i] = t; return; }
   if (!a.write_grad || !grads) return;
   int c, k = -1;

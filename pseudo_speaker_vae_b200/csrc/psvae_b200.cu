@@ -164,6 +164,46 @@ int tc_tensor_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out
   return 0;
 }
 
+typedef std::tuple<const void*, int, int64_t, int64_t, int64_t, int64_t, int64_t> BmKey;
+static std::map<BmKey, CUtensorMap> g_bm_cache;
+
+int tc_block_map(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int64_t splits, int64_t split_stride, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_tm_mu);
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    PSVAE_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+    if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available from this driver"); return -3; }
+    g_encode = (PFN_cuTensorMapEncodeTiled)fn;
+  }
+  const BmKey key(ptr, elem_bytes, rows, cols, ld, splits, split_stride);
+  auto it = g_bm_cache.find(key);
+  if (it != g_bm_cache.end()) { *out = it->second; return 0; }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * elem_bytes) % 16 != 0) {
+    set_error("tcgen05 epilogue tensors must be 16-byte aligned with 16-byte-multiple row pitch (ptr=%p ld=%lld elem=%d)", ptr, (long long)ld, elem_bytes);
+    return -2;
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(splits > 0 ? splits : 1)};
+  if (split_stride <= 0) split_stride = rows * ld;
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * elem_bytes, (cuuint64_t)split_stride * elem_bytes};
+  cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+  const int rank = splits > 0 ? 3 : 2;
+  alignas(64) CUtensorMap tm;
+  CUresult r = g_encode(&tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, elem_bytes == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (epilogue block) failed (%d): ptr=%p elem=%d dims=[%llu,%llu,%llu] strides=[%llu,%llu]", (int)r, ptr, elem_bytes,
+              (unsigned long long)gdim[0], (unsigned long long)gdim[1], (unsigned long long)gdim[2], (unsigned long long)gstride[0],
+              (unsigned long long)gstride[1]);
+    return -3;
+  }
+  if (g_bm_cache.size() > 8192) g_bm_cache.clear();
+  g_bm_cache[key] = tm;
+  *out = tm;
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // GEMM front end: C[M,N] = A[M,K] * B[N,K]^T through `epi`, on the engine the activation type selects
 // ------------------------------------------------------------------------------------------------
@@ -301,13 +341,13 @@ template <typename TAct> struct StepBufs {
 // the fused classifier kernel covers the common shape: heads directly on mu (no trunk), L = 32/64/96/128, <= 8 classes in total
 static bool clf_fused_ok(const psvae_model_desc* d) {
   if (d->clf_num_heads <= 0 || d->clf_num_trunk != 0) return false;
-  if (d->latent_dim % 32 != 0 || d->latent_dim > 128) return false;
+  if (d->latent_dim % 4 != 0 || d->latent_dim > 128) return false;      // dW: 8 classes x L <= 2 outputs per thread of a 256-thread block
   int total = 0;
   for (int h = 0; h < d->clf_num_heads; ++h) total += d->clf_head_classes[h];
-  return total <= CLF_MAXC;
+  return total <= CLF_MAXC && total * d->latent_dim <= 2 * CLF_TILE;
 }
 static int clf_fused_blocks(int64_t rows) {
-  int64_t b = ceil_div64(rows, 8 * 4);          // >= 4 rows per warp
+  int64_t b = ceil_div64(rows, CLF_TILE);
   if (b > 2 * PSVAE_NUM_SMS) b = 2 * PSVAE_NUM_SMS;
   return b < 1 ? 1 : (int)b;
 }
@@ -383,7 +423,7 @@ static void plan(const psvae_model_desc* d, int64_t rows, int mode, Bump& b, Ste
   w.wpart = b.take<float>(wmax);
   // bias-gradient partials: [row chunks][N] from colsum_kernel, [CTAs][N] from the tcgen05 epilogues, [blocks][2L] from latent_bwd_cs
   int64_t cslots = ceil_div64(rows, g_opt.colsum_rows);
-  if (cslots < 2 * PSVAE_NUM_SMS) cslots = 2 * PSVAE_NUM_SMS;
+  if (cslots < 4 * 160) cslots = 4 * 160;        // tcgen05 epilogues: one partial row per (CTA, TMEM lane quarter)
   const int64_t lat = (int64_t)PSVAE_NUM_SMS * 8 * 2 * n.L;
   w.cpart = b.take<float>(cslots * cmax > lat ? cslots * cmax : lat);
 }
@@ -391,6 +431,7 @@ static void plan(const psvae_model_desc* d, int64_t rows, int mode, Bump& b, Ste
 // ------------------------------------------------------------------------------------------------
 // small launch helpers
 // ------------------------------------------------------------------------------------------------
+static int launch_reduce(const float* partials, int64_t n, int S, float* out, cudaStream_t st);
 template <typename T>
 static int launch_colsum(const T* in, int64_t ld, int64_t rows, int N, float* cpart, float* out, cudaStream_t st) {
   const int64_t rpc = g_opt.colsum_rows;
@@ -399,12 +440,15 @@ static int launch_colsum(const T* in, int64_t ld, int64_t rows, int N, float* cp
   colsum_kernel<T><<<grid, 256, 0, st>>>(in, ld, rows, N, rpc, cpart);
   count_launch();
   PSVAE_LAUNCH_CHECK("colsum_kernel");
-  reduce_partials_kernel<<<(unsigned)ceil_div64(N, 256), 256, 0, st>>>(cpart, N, chunks, N, 1.f, out);
-  count_launch();
-  PSVAE_LAUNCH_CHECK("reduce_partials_kernel");
-  return 0;
+  return launch_reduce(cpart, N, chunks, out, st);
 }
 static int launch_reduce(const float* partials, int64_t n, int S, float* out, cudaStream_t st) {
+  if (S >= 32 && n <= 65536) {       // many partial rows, few columns: spread the rows over the block (fixed-order tree)
+    reduce_tall_kernel<<<(unsigned)ceil_div64(n, 32), 1024, 0, st>>>(partials, (int)n, S, n, out);
+    count_launch();
+    PSVAE_LAUNCH_CHECK("reduce_tall_kernel");
+    return 0;
+  }
   reduce_partials_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(partials, n, S, n, 1.f, out);
   count_launch();
   PSVAE_LAUNCH_CHECK("reduce_partials_kernel");
@@ -435,13 +479,11 @@ static int dgrad_hidden(const TAct* dY, int64_t ldy, const TAct* W, int out_dim,
                         int64_t rows, float* bias_grad, StepBufs<TAct>& w, bool* bias_done, cudaStream_t st) {
   *bias_done = false;
   if constexpr (sizeof(TAct) == 2) {
-    if (bias_grad && tc_colsum_ok(in_dim, (int)g_opt.tc_force_bn)) {
+    if (bias_grad && tc_colsum_ok(in_dim)) {
       EpiActGrad<TAct, TAct, ACT_RELU, true> e{act, lda, out, ldo, 0.f, nullptr, w.cpart};
       PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, ldy, W, in_dim, rows, in_dim, out_dim, 1, true, e, st)));
-      const int bn = g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(in_dim);
-      int64_t ctas = ceil_div64(rows, TC_BM) * ceil_div64(in_dim, bn);
-      if (ctas > tc_grid_size()) ctas = tc_grid_size();
-      PSVAE_TRY(launch_reduce(w.cpart, in_dim, (int)ctas, bias_grad, st));
+      const int64_t ctas = tc_ctas(rows, in_dim, 1, (int)g_opt.tc_force_bn);
+      PSVAE_TRY(launch_reduce(w.cpart, in_dim, (int)ctas * 4, bias_grad, st));
       *bias_done = true;
       return 0;
     }
@@ -621,19 +663,15 @@ static int run_step(const StepArgs& a) {
     ca.gscale = a.clf_w / ((float)B * (float)d->clf_num_heads);
     ca.write_grad = a.want_grads;
     const int blocks = clf_fused_blocks(B);
-    const size_t smem = 8 * (size_t)clf_part_len(n.L) * sizeof(float);
+    const size_t smem = clf_fused_smem_bytes(n.L);
     float* dmu_out = a.want_grads ? w.dmu_clf : nullptr;
-    switch (n.L / 32) {
-      case 1: clf_fused_kernel<1><<<blocks, 256, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part); break;
-      case 2: clf_fused_kernel<2><<<blocks, 256, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part); break;
-      case 3: clf_fused_kernel<3><<<blocks, 256, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part); break;
-      default: clf_fused_kernel<4><<<blocks, 256, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part); break;
-    }
+    PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    clf_fused_kernel<<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, n.L, ca, dmu_out, w.clf_part);
     count_launch();
     PSVAE_LAUNCH_CHECK("clf_fused_kernel");
     if (a.want_grads && d->total_numel > d->vae_numel)     // classifier region of the gradient buffer: padding must read as zero
       PSVAE_CUDA(cudaMemsetAsync(a.grads + d->vae_numel, 0, (size_t)(d->total_numel - d->vae_numel) * sizeof(float), st));
-    clf_fused_finish_kernel<<<(unsigned)ceil_div64(clf_part_len(n.L), 256), 256, 0, st>>>(w.clf_part, blocks, n.L, ca, w.clf_sums,
+    clf_fused_finish_kernel<<<(unsigned)ceil_div64(clf_part_len(n.L), 32), 1024, 0, st>>>(w.clf_part, blocks, n.L, ca, w.clf_sums,
                                                                                              a.want_grads ? a.grads : nullptr);
     count_launch();
     PSVAE_LAUNCH_CHECK("clf_fused_finish_kernel");
@@ -661,7 +699,7 @@ static int run_step(const StepArgs& a) {
     const float scale = 2.f / ((float)B * (float)n.D * 10.f);
     bool launched = false;
     if constexpr (sizeof(TAct) == 2) {
-      if (a.want_grads && tc_colsum_ok(n.D, (int)g_opt.tc_force_bn)) {     // + column sums of dxh = bias gradient of the last decoder layer
+      if (a.want_grads && tc_colsum_ok(n.D)) {     // + column sums of dxh = bias gradient of the last decoder layer
         EpiMse<TAct, true> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, w.dxh, n.D, scale, w.sse_part, w.cpart};
         PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
         launched = dec_last_bias_done = true;
@@ -677,7 +715,7 @@ static int run_step(const StepArgs& a) {
       const int64_t tiles = ceil_div64(B, TC_BM) * ceil_div64(n.D, g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(n.D));
       if (tiles < n_sse_used) n_sse_used = (int)tiles;
     }
-    if (dec_last_bias_done) PSVAE_TRY(launch_reduce(w.cpart, n.D, n_sse_used, a.grads + d->dec_b[n.nh], st));
+    if (dec_last_bias_done) PSVAE_TRY(launch_reduce(w.cpart, n.D, n_sse_used * 4, a.grads + d->dec_b[n.nh], st));
   } else {
     float* u = general_tail ? w.u : (a.x_hat ? a.x_hat : w.u);
     EpiBiasAct<float, ACT_NONE> e{P + d->dec_b[n.nh], u, n.D, nullptr};
@@ -775,7 +813,8 @@ static int run_step(const StepArgs& a) {
   // ---- through the reparameterisation and the KL term (+ the bias gradients of the encoders' last Linear)
   bool last_bias_done = false;
   if (latent_cs_ok(n.L)) {
-    const int blocks = ew_grid(B * n.L / 4);
+    int blocks = ew_grid(B * n.L / 4);
+    if (blocks > 2 * PSVAE_NUM_SMS) blocks = 2 * PSVAE_NUM_SMS;
     latent_bwd_cs_kernel<TAct><<<blocks, 256, 256 * 8 * sizeof(float), st>>>(w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, n.L, dmu_clf,
                                                                              a.kl_w / (float)B, w.dmu, w.dls, w.cpart);
     count_launch();
