@@ -10,7 +10,7 @@
 //   apply<NV>(row, col, v, red, split)      -- sgemm: transform NV consecutive accumulator columns of one row AND store them;
 //   tc_transform(row, col, N, valid, v, aux, red) -- tcgen05: transform 32 columns in registers only.  The engine then rounds to
 //       TOut, stages the 32x32 block in shared memory and writes it with one TMA store (coalesced, clipped at the matrix edge);
-//       `aux` is the functor's auxiliary 32x32 bf16 tile (kAux: the forward activation for EpiActGrad) which the engine fetched by
+//       `aux` is the functor's auxiliary 32x32 bf16 tile (kAuxBytes > 0: the forward activation for EpiActGrad, the target x for EpiMse) which the engine fetched by
 //       TMA load.  kColSum: the engine also emits the column sums of what was stored (bias gradients); kReduce: per-CTA sum of `red`.
 #pragma once
 #include "common.cuh"
@@ -38,7 +38,8 @@ template <int ACT> __device__ __forceinline__ float act_grad_from_out(float a) {
 template <typename TOut_, int ACT>
 struct EpiBiasAct {
   using TOut = TOut_;
-  static constexpr bool kReduce = false, kColSum = false, kAux = false, kSplit = false;
+  static constexpr bool kReduce = false, kColSum = false, kSplit = false;
+  static constexpr int kAuxBytes = 0;
   const float* bias;   // [N] or nullptr
   TOut* out;
   int64_t ldo;
@@ -59,7 +60,10 @@ struct EpiBiasAct {
 template <typename TOut_, bool CS = false>
 struct EpiMse {
   using TOut = TOut_;
-  static constexpr bool kReduce = true, kColSum = CS, kAux = false, kSplit = false;
+  static constexpr bool kReduce = true, kColSum = CS, kSplit = false;
+  static constexpr int kAuxBytes = 4096;      // tcgen05 engine: the fp32 target tile x[32 rows][32 cols] arrives by TMA
+  __host__ const void* aux_ptr() const { return x; }
+  __host__ int64_t aux_ld() const { return ldx; }
   const float* bias;   // [N]
   const float* x;      // [M, ldx] fp32 target
   int64_t ldx;
@@ -69,7 +73,8 @@ struct EpiMse {
   int64_t ldo;
   float scale;
   float* red_out;      // one slot per CTA: sum of squared differences
-  float* colsum;       // CS: [4 * CTAs][N] partial column sums of the gradient
+  float* colsum;       // CS: [4 * CTAs][N] partial column sums of the gradient, or (colsum_atomic) the [N] bias gradient itself
+  int colsum_atomic;
   template <int NV>
   __device__ __forceinline__ void apply(int64_t row, int col, float (&v)[NV], float& red, int split) const {
     float xv[NV];
@@ -85,17 +90,15 @@ struct EpiMse {
     }
     if (out) store_vec<NV>(out + row * ldo + col, v);
   }
-  // x is read (and x_hat written) straight from/to global memory here: one GEMM per step, and x is fp32 (twice the tile bytes)
+  // aux = the x tile (fp32, fetched by TMA; zero outside the matrix); x_hat (optional) is written straight to global memory
   __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], float& red) const {
     if (valid && col + 32 <= N) {
-      float xv[32];
-      load_vec<32>(x + row * ldx + col, xv);
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] += __ldg(bias + col + i);
       if (x_hat) store_vec<32>(x_hat + row * ldxh + col, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const float d = v[i] - xv[i];
+        const float d = v[i] - aux[i];
         red = fmaf(d, d, red);
         v[i] = d * scale;
       }
@@ -106,7 +109,7 @@ struct EpiMse {
         if (valid && col + i < N) {
           const float h = v[i] + __ldg(bias + col + i);
           if (x_hat) x_hat[row * ldxh + col + i] = h;
-          const float d = h - x[row * ldx + col + i];
+          const float d = h - aux[i];
           red = fmaf(d, d, red);
           o = d * scale;
         }
@@ -120,14 +123,18 @@ struct EpiMse {
 template <typename TAct, typename TOut_, int ACT, bool CS = false>
 struct EpiActGrad {
   using TOut = TOut_;
-  static constexpr bool kReduce = false, kColSum = CS, kAux = true, kSplit = false;
+  static constexpr bool kReduce = false, kColSum = CS, kSplit = false;
+  static constexpr int kAuxBytes = sizeof(TAct) == 2 ? 2048 : 4096;   // tcgen05 engine: the forward-activation tile arrives by TMA
+  __host__ const void* aux_ptr() const { return act; }
+  __host__ int64_t aux_ld() const { return lda; }
   const TAct* act;     // forward activation (post-activation) [M, lda]
   int64_t lda;
   TOut* out;
   int64_t ldo;
   float beta;          // sgemm only: out = acc * act'(.) + beta * out   (sum over classifier heads)
   float* red_out;
-  float* colsum;       // CS: [4 * CTAs][N] partial column sums of the output
+  float* colsum;       // CS: [4 * CTAs][N] partial column sums of the output, or (colsum_atomic) the [N] bias gradient itself
+  int colsum_atomic;
   template <int NV>
   __device__ __forceinline__ void apply(int64_t row, int col, float (&v)[NV], float& red, int split) const {
     float a[NV];
@@ -150,12 +157,14 @@ struct EpiActGrad {
 
 struct EpiStore {
   using TOut = float;
-  static constexpr bool kReduce = false, kColSum = false, kAux = false, kSplit = true;
+  static constexpr bool kReduce = false, kColSum = false, kSplit = true;
+  static constexpr int kAuxBytes = 0;
   float* out;
   int64_t ldo;
   int64_t split_stride;  // elements between split-K partials
   float alpha, beta;     // beta is honoured by the sgemm engine only
   float* red_out;
+  int reduce_add;        // tcgen05 engine only: accumulate into `out` ([M][N], no split slots) with TMA reduce-add instead of storing
   template <int NV>
   __device__ __forceinline__ void apply(int64_t row, int col, float (&v)[NV], float& red, int split) const {
     float* p = out + (int64_t)split * split_stride + row * ldo + col;

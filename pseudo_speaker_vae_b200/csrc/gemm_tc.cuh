@@ -31,17 +31,25 @@ namespace psvae {
 constexpr int TC_BM = 128, TC_BK = 64, TC_UMMA_K = 16;
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);
-constexpr int TC_EPI_WARP_BYTES = 4096;   // per epilogue warp: fp32 block (32 x 128 B) or bf16 block + bf16 aux block (2 x 32 x 64 B)
 constexpr int TC_BAR_BYTES = 512;
+constexpr int TC_SMEM_MAX = 227 * 1024;
 
-template <int BN> struct TcCfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+// Shared-memory plan of one instantiation.  Per epilogue warp: the staged output block (32 rows x 32 cols of TOut: 2 KB bf16 / 4 KB fp32)
+// followed by the auxiliary block (Epi::kAuxBytes: 2 KB bf16 activation tile, 4 KB fp32 target tile); the operand ring gets the rest.
+template <int BN, class Epi> struct TcCfg {
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = BN * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutBytes = 32 * 32 * (int)sizeof(typename Epi::TOut);
+  static constexpr int kEpiWarpBytes = kOutBytes + Epi::kAuxBytes;
+  static constexpr int kEpiBytes = TC_EPI_WARPS * kEpiWarpBytes;
+  static constexpr int kMaxStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kFit = (TC_SMEM_MAX - 1024 - TC_BAR_BYTES - kEpiBytes) / kStageBytes;
+  static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
+  static_assert(kStages >= 2, "operand ring too shallow");
   static constexpr int kTmemCols = 2 * BN;     // power of two >= 32 for BN in {64,128,256}
   static constexpr int kEpiOff = kStages * kStageBytes;
-  static constexpr int kBarOff = kEpiOff + TC_EPI_WARPS * TC_EPI_WARP_BYTES;
+  static constexpr int kBarOff = kEpiOff + kEpiBytes;
   static constexpr int kSmemBytes = kBarOff + TC_BAR_BYTES + 1024 /*align slack*/;
 };
 
@@ -63,12 +71,12 @@ template <int BN, bool A_MN, bool B_MN, class Epi>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
                const __grid_constant__ CUtensorMap tma_aux, TcShape s, Epi epi) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, Epi>;
   using TOut = typename Epi::TOut;
   constexpr int STAGES = Cfg::kStages;
   constexpr int ROWB = 32 * (int)sizeof(TOut);            // bytes per staged row: 64 (bf16) or 128 (fp32)
-  constexpr int OUT_BYTES = 32 * ROWB;
-  static_assert(!(Epi::kAux && sizeof(TOut) != 2), "an auxiliary tile needs the 2 KB bf16 output block");
+  constexpr bool kAux = Epi::kAuxBytes > 0;
+  static_assert(Epi::kAuxBytes == 0 || Epi::kAuxBytes == 2048 || Epi::kAuxBytes == 4096, "aux block: 32x32 bf16 or fp32");
   static_assert(!(Epi::kColSum && sizeof(TOut) != 2), "column sums are read back from a bf16 block");
   extern __shared__ uint8_t smem_raw[];
   // 128B-swizzled tiles need 1024-byte alignment
@@ -88,7 +96,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     ptx::prefetch_tensormap(&tma_a);
     ptx::prefetch_tensormap(&tma_b);
     ptx::prefetch_tensormap(&tma_out);
-    if constexpr (Epi::kAux) ptx::prefetch_tensormap(&tma_aux);
+    if constexpr (kAux) ptx::prefetch_tensormap(&tma_aux);
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
       ptx::mbar_init(&empty_bar[i], 1);
@@ -195,8 +203,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int half = ew >> 2;                // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
     constexpr int CH = COLS_PER_WARP / 32;   // 32-column blocks per tile for this warp
-    uint8_t* obuf = smem + Cfg::kEpiOff + ew * TC_EPI_WARP_BYTES;     // staged output block
-    uint8_t* abuf = obuf + 2048;                                       // staged auxiliary block (kAux, bf16)
+    uint8_t* obuf = smem + Cfg::kEpiOff + ew * Cfg::kEpiWarpBytes;    // staged output block
+    uint8_t* abuf = obuf + Cfg::kOutBytes;                             // staged auxiliary block
     uint32_t aux_phase = 0;
     const bool do_store = epi.out != nullptr;
     float cs_acc[CH][2];                     // kColSum: this lane's two columns of every block of the current N tile
@@ -210,8 +218,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int c = 0; c < CH; ++c) {
             const int col = (int)(cs_nt * BN) + half * COLS_PER_WARP + c * 32 + 2 * lane;
             if (col + 1 < s.N) {
-              float* p = epi.colsum + ((int64_t)blockIdx.x * 4 + quarter) * s.N + col;
-              *reinterpret_cast<float2*>(p) = make_float2(cs_acc[c][0], cs_acc[c][1]);
+              if (epi.colsum_atomic) {          // fast mode: straight into the (zeroed) bias gradient
+                atomicAdd(epi.colsum + col, cs_acc[c][0]);
+                atomicAdd(epi.colsum + col + 1, cs_acc[c][1]);
+              } else {                          // deterministic mode: one partial row per (CTA, row quarter)
+                float* p = epi.colsum + ((int64_t)blockIdx.x * 4 + quarter) * s.N + col;
+                *reinterpret_cast<float2*>(p) = make_float2(cs_acc[c][0], cs_acc[c][1]);
+              }
             }
           }
         }
@@ -232,9 +245,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       if constexpr (Epi::kColSum) {
         if (n_t != cs_nt) { cs_flush(); cs_nt = n_t; }
       }
-      if constexpr (Epi::kAux) {             // fetch the first auxiliary block while the MMAs of this tile are still running
+      if constexpr (kAux) {                  // fetch the first auxiliary block while the MMAs of this tile are still running
         if (col_base < s.N && lane == 0) {
-          ptx::mbar_arrive_expect_tx(&aux_bar[ew], 2048);
+          ptx::mbar_arrive_expect_tx(&aux_bar[ew], Epi::kAuxBytes);
           ptx::tma_load_2d(abuf, &tma_aux, &aux_bar[ew], col_base, row_base);
         }
       }
@@ -254,22 +267,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int i = 0; i < 32; ++i) v[i] = 0.f;
         }
         float aux[32];
-        if constexpr (Epi::kAux) {
+        if constexpr (kAux) {
           ptx::mbar_wait(&aux_bar[ew], aux_phase, 5);
           aux_phase ^= 1;
+          if constexpr (Epi::kAuxBytes == 2048) {          // bf16 tile, 64-byte rows
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 u = *reinterpret_cast<const uint4*>(abuf + swz_off<64>(lane, j));
-            const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+            for (int j = 0; j < 4; ++j) {
+              const uint4 u = *reinterpret_cast<const uint4*>(abuf + swz_off<64>(lane, j));
+              const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              aux[j * 8 + 2 * q] = __uint_as_float(wv[q] << 16);
-              aux[j * 8 + 2 * q + 1] = __uint_as_float(wv[q] & 0xFFFF0000u);
+              for (int q = 0; q < 4; ++q) {
+                aux[j * 8 + 2 * q] = __uint_as_float(wv[q] << 16);
+                aux[j * 8 + 2 * q + 1] = __uint_as_float(wv[q] & 0xFFFF0000u);
+              }
+            }
+          } else {                                         // fp32 tile, 128-byte rows
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 u = *reinterpret_cast<const float4*>(abuf + swz_off<128>(lane, j));
+              aux[j * 4] = u.x; aux[j * 4 + 1] = u.y; aux[j * 4 + 2] = u.z; aux[j * 4 + 3] = u.w;
             }
           }
           __syncwarp();                      // every lane has read the block: it may be overwritten
           if (col + 32 < s.N && c + 1 < CH && lane == 0) {
-            ptx::mbar_arrive_expect_tx(&aux_bar[ew], 2048);
+            ptx::mbar_arrive_expect_tx(&aux_bar[ew], Epi::kAuxBytes);
             ptx::tma_load_2d(abuf, &tma_aux, &aux_bar[ew], col + 32, row_base);
           }
         } else {
@@ -321,8 +342,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             cs_acc[c][1] += s1;
           }
           if (lane == 0) {
-            if constexpr (Epi::kSplit) ptx::tma_store_3d(&tma_out, obuf, col, row_base, (int32_t)sp);
-            else ptx::tma_store_2d(&tma_out, obuf, col, row_base);
+            if constexpr (Epi::kSplit) {
+              if (epi.reduce_add) ptx::tma_reduce_add_2d(&tma_out, obuf, col, row_base);
+              else ptx::tma_store_3d(&tma_out, obuf, col, row_base, (int32_t)sp);
+            } else {
+              ptx::tma_store_2d(&tma_out, obuf, col, row_base);
+            }
             ptx::bulk_commit();
           }
         }
@@ -396,16 +421,24 @@ template <class Epi, class = void> struct epi_aux_ptr {
   static const void* get(const Epi&) { return nullptr; }
   static int64_t ld(const Epi&) { return 0; }
 };
-template <class Epi> struct epi_aux_ptr<Epi, std::enable_if_t<Epi::kAux>> {
-  static const void* get(const Epi& e) { return e.act; }
-  static int64_t ld(const Epi& e) { return e.lda; }
+template <class Epi> struct epi_aux_ptr<Epi, std::enable_if_t<(Epi::kAuxBytes > 0)>> {
+  static const void* get(const Epi& e) { return e.aux_ptr(); }
+  static int64_t ld(const Epi& e) { return e.aux_ld(); }
 };
-template <class Epi, class = void> struct epi_split_stride { static int64_t get(const Epi&) { return 0; } };
-template <class Epi> struct epi_split_stride<Epi, std::enable_if_t<Epi::kSplit>> { static int64_t get(const Epi& e) { return e.split_stride; } };
+template <class Epi, class = void> struct epi_split_stride {
+  static int64_t get(const Epi&) { return 0; }
+  static bool reduce(const Epi&) { return false; }
+};
+template <class Epi> struct epi_split_stride<Epi, std::enable_if_t<Epi::kSplit>> {
+  static int64_t get(const Epi& e) { return e.split_stride; }
+  static bool reduce(const Epi& e) { return e.reduce_add != 0; }
+};
+template <class Epi, class = void> struct epi_cs_atomic { static bool get(const Epi&) { return false; } };
+template <class Epi> struct epi_cs_atomic<Epi, std::enable_if_t<Epi::kColSum>> { static bool get(const Epi& e) { return e.colsum_atomic != 0; } };
 
 template <int BN, bool A_MN, bool B_MN, class Epi>
 int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, Epi>;
   using TOut = typename Epi::TOut;
   CUtensorMap ta, tb, tout, taux;
   PSVAE_TRY(tc_tensor_map(A, K, A_MN ? TC_BK : TC_BM, &ta));
@@ -415,12 +448,13 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   tc_desc_strides(A_MN, &s.a_lbo, &s.a_sbo);
   tc_desc_strides(B_MN, &s.b_lbo, &s.b_sbo);
   if (epi.out) {
-    PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, N, epi.ldo, Epi::kSplit ? s.splits : 0, epi_split_stride<Epi>::get(epi), &tout));
+    const bool split_slots = Epi::kSplit && !epi_split_stride<Epi>::reduce(epi);
+    PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, N, epi.ldo, split_slots ? s.splits : 0, epi_split_stride<Epi>::get(epi), &tout));
   } else {
     tout = ta;   // never dereferenced: the kernel skips the store
   }
-  if constexpr (Epi::kAux) {
-    PSVAE_TRY(tc_block_map(epi_aux_ptr<Epi>::get(epi), 2, M, N, epi_aux_ptr<Epi>::ld(epi), 0, 0, &taux));
+  if constexpr (Epi::kAuxBytes > 0) {
+    PSVAE_TRY(tc_block_map(epi_aux_ptr<Epi>::get(epi), Epi::kAuxBytes == 2048 ? 2 : 4, M, N, epi_aux_ptr<Epi>::ld(epi), 0, 0, &taux));
   } else {
     taux = ta;
   }
@@ -438,7 +472,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   if (grid < 1) return 0;
   if constexpr (Epi::kColSum) {
     // every (CTA, row-quarter) writes only the columns of the N tiles it saw: the rest of the partial buffer must read as zero
-    PSVAE_CUDA(cudaMemsetAsync(epi.colsum, 0, (size_t)grid * 4 * (size_t)N * sizeof(float), st));
+    if (!epi_cs_atomic<Epi>::get(epi)) PSVAE_CUDA(cudaMemsetAsync(epi.colsum, 0, (size_t)grid * 4 * (size_t)N * sizeof(float), st));
   }
   kern<<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, tout, taux, s, epi);
   count_launch();

@@ -55,6 +55,7 @@ struct Options {
   int64_t colsum_rows = 512;           // rows per bias-gradient partial
   int64_t tc_force_bn = 0;             // tests: force the N tile of the tcgen05 engine
   int64_t tc_grid_limit = 0;           // tests: cap the persistent grid
+  int64_t deterministic = 0;           // 1: split-K / bias partials go through ordered two-stage sums instead of TMA reduce-add / atomics
 };
 static Options g_opt;
 
@@ -460,11 +461,15 @@ template <typename TAct>
 static int wgrad(const TAct* dY, int64_t ldy, const TAct* A, int64_t lda, int64_t rows, int out, int in, float* gW, float* gb,
                  StepBufs<TAct>& w, cudaStream_t st) {
   const int splits = Engine<TAct>::wgrad_splits(out, in, rows);
-  if (splits == 1) {
-    EpiStore e{gW, in, 0, 1.f, 0.f, nullptr};
+  if (sizeof(TAct) == 2 && !g_opt.deterministic) {
+    // fast mode: every split-K tile adds its block into the (zeroed) gradient with a TMA reduce-add -- no partial buffers, no second pass
+    EpiStore e{gW, in, 0, 1.f, 0.f, nullptr, 1};
+    PSVAE_TRY((Engine<TAct>::template gemm<G_WGRAD>(dY, ldy, A, lda, out, in, rows, splits, in % 4 == 0, e, st)));
+  } else if (splits == 1) {
+    EpiStore e{gW, in, 0, 1.f, 0.f, nullptr, 0};
     PSVAE_TRY((Engine<TAct>::template gemm<G_WGRAD>(dY, ldy, A, lda, out, in, rows, 1, in % 4 == 0, e, st)));
   } else {
-    EpiStore e{w.wpart, in, (int64_t)out * in, 1.f, 0.f, nullptr};
+    EpiStore e{w.wpart, in, (int64_t)out * in, 1.f, 0.f, nullptr, 0};
     PSVAE_TRY((Engine<TAct>::template gemm<G_WGRAD>(dY, ldy, A, lda, out, in, rows, splits, in % 4 == 0, e, st)));
     PSVAE_TRY(launch_reduce(w.wpart, (int64_t)out * in, splits, gW, st));
   }
@@ -480,15 +485,18 @@ static int dgrad_hidden(const TAct* dY, int64_t ldy, const TAct* W, int out_dim,
   *bias_done = false;
   if constexpr (sizeof(TAct) == 2) {
     if (bias_grad && tc_colsum_ok(in_dim)) {
-      EpiActGrad<TAct, TAct, ACT_RELU, true> e{act, lda, out, ldo, 0.f, nullptr, w.cpart};
+      const bool atomic = !g_opt.deterministic;
+      EpiActGrad<TAct, TAct, ACT_RELU, true> e{act, lda, out, ldo, 0.f, nullptr, atomic ? bias_grad : w.cpart, atomic ? 1 : 0};
       PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, ldy, W, in_dim, rows, in_dim, out_dim, 1, true, e, st)));
-      const int64_t ctas = tc_ctas(rows, in_dim, 1, (int)g_opt.tc_force_bn);
-      PSVAE_TRY(launch_reduce(w.cpart, in_dim, (int)ctas * 4, bias_grad, st));
+      if (!atomic) {
+        const int64_t ctas = tc_ctas(rows, in_dim, 1, (int)g_opt.tc_force_bn);
+        PSVAE_TRY(launch_reduce(w.cpart, in_dim, (int)ctas * 4, bias_grad, st));
+      }
       *bias_done = true;
       return 0;
     }
   }
-  EpiActGrad<TAct, TAct, ACT_RELU, false> e{act, lda, out, ldo, 0.f, nullptr, nullptr};
+  EpiActGrad<TAct, TAct, ACT_RELU, false> e{act, lda, out, ldo, 0.f, nullptr, nullptr, 0};
   return Engine<TAct>::template gemm<G_DGRAD>(dY, ldy, W, in_dim, rows, in_dim, out_dim, 1, true, e, st);
 }
 // classifier wgrad: always fp32 on the CUDA cores
@@ -498,10 +506,10 @@ static int wgrad_clf(const float* dY, int64_t ldy, const float* A, int64_t lda, 
   const int splits = Engine<float>::wgrad_splits(out, in, rows);
   const bool vec = (in % 4 == 0);
   if (splits == 1) {
-    EpiStore e{gW, in, 0, 1.f, 0.f, nullptr};
+    EpiStore e{gW, in, 0, 1.f, 0.f, nullptr, 0};
     PSVAE_TRY((Engine<float>::gemm<G_WGRAD>(dY, ldy, A, lda, out, in, rows, 1, vec, e, st)));
   } else {
-    EpiStore e{w.wpart, in, (int64_t)out * in, 1.f, 0.f, nullptr};
+    EpiStore e{w.wpart, in, (int64_t)out * in, 1.f, 0.f, nullptr, 0};
     PSVAE_TRY((Engine<float>::gemm<G_WGRAD>(dY, ldy, A, lda, out, in, rows, splits, vec, e, st)));
     PSVAE_TRY(launch_reduce(w.wpart, (int64_t)out * in, splits, gW, st));
   }
@@ -527,12 +535,12 @@ static int clf_linear(int act, const float* a, int64_t lda, const float* W, cons
 // out[B][in] = (dY[B][out] * W[out][in]) .* act'(A[B][in]) + beta * out
 template <int ACT>
 static int clf_dgrad_act(const float* dY, int out_dim, const float* W, int in_dim, const float* A, float* out, float beta, int64_t rows, cudaStream_t st) {
-  EpiActGrad<float, float, ACT> e{A, in_dim, out, in_dim, beta, nullptr, nullptr};
+  EpiActGrad<float, float, ACT> e{A, in_dim, out, in_dim, beta, nullptr, nullptr, 0};
   return Engine<float>::gemm<G_DGRAD>(dY, out_dim, W, in_dim, rows, in_dim, out_dim, 1, in_dim % 4 == 0, e, st);
 }
 static int clf_dgrad(int act, const float* dY, int out_dim, const float* W, int in_dim, const float* A, float* out, float beta, int64_t rows, cudaStream_t st) {
   if (!A) {
-    EpiStore e{out, in_dim, 0, 1.f, beta, nullptr};
+    EpiStore e{out, in_dim, 0, 1.f, beta, nullptr, 0};
     return Engine<float>::gemm<G_DGRAD>(dY, out_dim, W, in_dim, rows, in_dim, out_dim, 1, in_dim % 4 == 0, e, st);
   }
   switch (act) {
@@ -611,6 +619,8 @@ static int run_step(const StepArgs& a) {
   }
   const TAct* Wt = weights_of<TAct>(a);
   const float* P = a.params;
+  // gradients are accumulated into (TMA reduce-add / atomics in fast tcgen05 mode) or written into a zeroed buffer; padding reads as zero
+  if (a.want_grads) PSVAE_CUDA(cudaMemsetAsync(a.grads, 0, (size_t)d->total_numel * sizeof(float), st));
   float* mu = a.mu ? a.mu : w.mu;
   float* ls = a.ls ? a.ls : w.ls;
   const int64_t first_elem = a.row0 * n.L;
@@ -669,8 +679,6 @@ static int run_step(const StepArgs& a) {
     clf_fused_kernel<<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, n.L, ca, dmu_out, w.clf_part);
     count_launch();
     PSVAE_LAUNCH_CHECK("clf_fused_kernel");
-    if (a.want_grads && d->total_numel > d->vae_numel)     // classifier region of the gradient buffer: padding must read as zero
-      PSVAE_CUDA(cudaMemsetAsync(a.grads + d->vae_numel, 0, (size_t)(d->total_numel - d->vae_numel) * sizeof(float), st));
     clf_fused_finish_kernel<<<(unsigned)ceil_div64(clf_part_len(n.L), 32), 1024, 0, st>>>(w.clf_part, blocks, n.L, ca, w.clf_sums,
                                                                                              a.want_grads ? a.grads : nullptr);
     count_launch();
@@ -694,19 +702,22 @@ static int run_step(const StepArgs& a) {
   // ---- decoder (model.py:58-61) + reconstruction loss (lightning.py:110-113)
   const bool general_tail = d->normalize_decoder || a.use_cos;
   int n_sse_used = 0;
-  bool dec_last_bias_done = false;
+  bool dec_last_bias_done = false, dec_last_bias_reduce = false;
   if (a.want_loss && !general_tail) {
     const float scale = 2.f / ((float)B * (float)n.D * 10.f);
     bool launched = false;
     if constexpr (sizeof(TAct) == 2) {
       if (a.want_grads && tc_colsum_ok(n.D)) {     // + column sums of dxh = bias gradient of the last decoder layer
-        EpiMse<TAct, true> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, w.dxh, n.D, scale, w.sse_part, w.cpart};
+        const bool atomic = !g_opt.deterministic;
+        EpiMse<TAct, true> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, w.dxh, n.D, scale, w.sse_part, atomic ? a.grads + d->dec_b[n.nh] : w.cpart,
+                             atomic ? 1 : 0};
         PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
         launched = dec_last_bias_done = true;
+        dec_last_bias_reduce = !atomic;
       }
     }
     if (!launched) {
-      EpiMse<TAct> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, a.want_grads ? w.dxh : nullptr, n.D, scale, w.sse_part, nullptr};
+      EpiMse<TAct> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, a.want_grads ? w.dxh : nullptr, n.D, scale, w.sse_part, nullptr, 0};
       PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
     }
     n_sse_used = sizeof(TAct) == 2 ? tc_grid_size() : (int)sgemm_red_slots(B, n.D);
@@ -715,7 +726,7 @@ static int run_step(const StepArgs& a) {
       const int64_t tiles = ceil_div64(B, TC_BM) * ceil_div64(n.D, g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(n.D));
       if (tiles < n_sse_used) n_sse_used = (int)tiles;
     }
-    if (dec_last_bias_done) PSVAE_TRY(launch_reduce(w.cpart, n.D, n_sse_used * 4, a.grads + d->dec_b[n.nh], st));
+    if (dec_last_bias_reduce) PSVAE_TRY(launch_reduce(w.cpart, n.D, n_sse_used * 4, a.grads + d->dec_b[n.nh], st));
   } else {
     float* u = general_tail ? w.u : (a.x_hat ? a.x_hat : w.u);
     EpiBiasAct<float, ACT_NONE> e{P + d->dec_b[n.nh], u, n.D, nullptr};
@@ -752,8 +763,6 @@ static int run_step(const StepArgs& a) {
 
   // =================================== backward ===================================
   float* G = a.grads;
-  if (d->total_numel > d->vae_numel && !clf_fused)
-    PSVAE_CUDA(cudaMemsetAsync(G + d->vae_numel, 0, (size_t)(d->total_numel - d->vae_numel) * sizeof(float), st));
 
   // ---- classifier backward -> dmu_clf (the fused kernel already produced it together with the classifier's gradients)
   const float* dmu_clf = clf_fused ? w.dmu_clf : nullptr;
@@ -805,7 +814,7 @@ static int run_step(const StepArgs& a) {
         out_dim = n.H;
         pp ^= 1;
       } else {
-        EpiStore e{w.dz, n.L, 0, 1.f, 0.f, nullptr};
+        EpiStore e{w.dz, n.L, 0, 1.f, 0.f, nullptr, 0};
         PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, out_dim, Wt + d->dec_w[0], n.L, B, n.L, out_dim, 1, true, e, st)));
       }
     }
@@ -956,6 +965,7 @@ int psvae_set_option(const char* name, int64_t value) {
     g_opt.tc_force_bn = value; return 0;
   }
   if (!strcmp(name, "tc_grid_limit")) { g_opt.tc_grid_limit = value < 0 ? 0 : value; return 0; }
+  if (!strcmp(name, "deterministic")) { g_opt.deterministic = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
   return -2;
 }
@@ -966,6 +976,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "colsum_rows")) return g_opt.colsum_rows;
   if (!strcmp(name, "tc_force_bn")) return g_opt.tc_force_bn;
   if (!strcmp(name, "tc_grid_limit")) return g_opt.tc_grid_limit;
+  if (!strcmp(name, "deterministic")) return g_opt.deterministic;
   return -1;
 }
 
@@ -1195,7 +1206,7 @@ int psvae_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, f
       return -2;
     }
     float* part = static_cast<float*>(workspace);
-    EpiStore e{part, n, m * n, 1.f, 0.f, nullptr};
+    EpiStore e{part, n, m * n, 1.f, 0.f, nullptr, 0};
     int r;
     if (a_mn && b_mn) r = gemm_tc_launch<true, true>(oa, ob, m, n, k, (int)s, e, st, fbn);
     else if (!a_mn && b_mn) r = gemm_tc_launch<false, true>(oa, ob, m, n, k, (int)s, e, st, fbn);
@@ -1205,13 +1216,13 @@ int psvae_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, f
     return launch_reduce(part, m * n, (int)s, c, st);
   }
   if (a_mn && b_mn) {
-    EpiStore e{c, n, 0, 1.f, 0.f, nullptr};
+    EpiStore e{c, n, 0, 1.f, 0.f, nullptr, 0};
     return gemm_tc_launch<true, true>(oa, ob, m, n, k, 1, e, st, fbn);
   }
   if (a_mn) { set_error("a_mn && !b_mn is not used by this library"); return -2; }
   if (b_mn) {
     if (relu || bias) { set_error("bias/relu are only wired for the K-major x K-major form"); return -2; }
-    EpiStore e{c, n, 0, 1.f, 0.f, nullptr};
+    EpiStore e{c, n, 0, 1.f, 0.f, nullptr, 0};
     return gemm_tc_launch<false, true>(oa, ob, m, n, k, 1, e, st, fbn);
   }
   if (relu) {

@@ -523,3 +523,38 @@ def test_data_parallel_trainer_single_process_matches_manual_steps():
         trainer.train_step(torch.from_numpy(x).to(G.DEV), G.labels_to_torch(y), torch.from_numpy(eps).to(G.DEV))
         for k, p in module.named_parameters():
             check_summary(z, f"f64/step{s}/param", k, p.detach().cpu().numpy(), FP32_TOL)
+
+
+def test_deterministic_option_and_fast_mode_agree():
+    """Default (fast) tcgen05 mode accumulates split-K / bias partials with TMA reduce-add and atomics (order not fixed);
+    the "deterministic" option routes them through ordered two-stage sums: bit-identical from run to run, and within fp32
+    summation noise of the fast mode."""
+    G = _gu()
+    module, cfg = _big_module(G, "bf16")
+    hot = module.hot_path
+    B = 8192
+    x, y, eps = O.synth_batch(B, 256, 64, 2, seed=77)
+    xt, yt, et = torch.from_numpy(x).to(G.DEV), torch.from_numpy(y).to(G.DEV), torch.from_numpy(eps).to(G.DEV)
+
+    def run():
+        g = torch.empty(hot.arena.numel, device=G.DEV)
+        losses, _, _ = hot.step(xt, yt, et, grads=g)
+        return g, losses
+
+    try:
+        G.L.set_option("deterministic", 1)
+        g1, l1 = run()
+        g2, l2 = run()
+        assert torch.equal(g1, g2) and torch.equal(l1, l2)
+        G.L.set_option("deterministic", 0)
+        f1, lf = run()
+        f2, _ = run()
+        assert torch.equal(lf, l1)
+        for f in (f1, f2):
+            assert ((f.double() - g1.double()).norm() / g1.double().norm()).item() <= 1e-6
+        names = G.flat_to_dict(module, f1)
+        det = G.flat_to_dict(module, g1)
+        for k in names:
+            assert rel_err(names[k], det[k]) <= 2e-6, k
+    finally:
+        G.L.set_option("deterministic", 0)
