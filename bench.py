@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the sampling / e2e / CPU legs")
     ap.add_argument("--sample-n", type=int, default=4 * 1024 * 1024)
     ap.add_argument("--cond-n", type=int, default=1024 * 1024)
+    ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (psvae_set_option), repeatable")
     args = ap.parse_args()
     args.steps_given = args.steps is not None
     if args.steps is None:
@@ -247,6 +248,9 @@ def main():
     if args.gpus != world and rank == 0 and dist_on:
         print(f"warning: --gpus {args.gpus} but WORLD_SIZE {world}", file=sys.stderr)
     n_gpus = world
+    for kv in args.opt:
+        k, v = kv.split("=")
+        L.set_option(k, int(v))
     peaks = measured_peaks()
     B, K, W = args.batch, args.steps, max(3, args.warmup)
 
@@ -297,7 +301,7 @@ def main():
                 config=dict(workload=f"ps_vae conditional VAE train step fwd+bwd+Adam, D={D} L={LAT} hidden {HID}x{NH}, 2-class latent classifier, "
                                      f"batch {B} per GPU ({B * n_gpus} global), {args.precision}",
                             global_batch=B * n_gpus, parallelism=f"dp{n_gpus}", l2="4 distinct 67 MB input batches rotated (268 MB > 126 MB L2)",
-                            eps="in-kernel Philox4x32-10", allreduce="1 bucket, flat fp32 grads 5.13 MB, NCCL" if dist_on else "none (1 GPU)"),
+                            eps="in-kernel Philox4x32-10", options={kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt}, allreduce="1 bucket, flat fp32 grads 5.13 MB, NCCL" if dist_on else "none (1 GPU)"),
                 clocks=clocks, gpu_launches=launches, roofline=roofline)
 
     if not args.no_secondary:

@@ -55,6 +55,7 @@ struct Options {
   int64_t colsum_rows = 512;           // rows per bias-gradient partial
   int64_t tc_force_bn = 0;             // tests: force the N tile of the tcgen05 engine
   int64_t tc_grid_limit = 0;           // tests: cap the persistent grid
+  int64_t tc_prefetch = 8;             // k-blocks (64 wide) the operand L2 prefetch runs ahead of the smem ring; 0 = off
   int64_t deterministic = 0;           // 1: split-K / bias partials go through ordered two-stage sums instead of TMA reduce-add / atomics
 };
 static Options g_opt;
@@ -95,6 +96,7 @@ int tc_device_check() {
   }
   return 0;
 }
+int tc_prefetch_distance() { return (int)g_opt.tc_prefetch; }
 int tc_grid_size() {
   DevInfo* d = nullptr;
   if (dev_info(&d) != 0) return PSVAE_NUM_SMS;
@@ -966,6 +968,7 @@ int psvae_set_option(const char* name, int64_t value) {
   }
   if (!strcmp(name, "tc_grid_limit")) { g_opt.tc_grid_limit = value < 0 ? 0 : value; return 0; }
   if (!strcmp(name, "deterministic")) { g_opt.deterministic = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_prefetch")) { g_opt.tc_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
   set_error("unknown option '%s'", name);
   return -2;
 }
@@ -977,6 +980,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_force_bn")) return g_opt.tc_force_bn;
   if (!strcmp(name, "tc_grid_limit")) return g_opt.tc_grid_limit;
   if (!strcmp(name, "deterministic")) return g_opt.deterministic;
+  if (!strcmp(name, "tc_prefetch")) return g_opt.tc_prefetch;
   return -1;
 }
 
