@@ -20,6 +20,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <string.h>
+
 #include <type_traits>
 
 #include "common.cuh"
@@ -36,14 +38,16 @@ constexpr int TC_SMEM_MAX = 227 * 1024;
 
 // Shared-memory plan of one instantiation.  Per epilogue warp: the staged output block (32 rows x 32 cols of TOut: 2 KB bf16 / 4 KB fp32)
 // followed by the auxiliary block (Epi::kAuxBytes: 2 KB bf16 activation tile, 4 KB fp32 target tile); the operand ring gets the rest.
-template <int BN, class Epi> struct TcCfg {
+// CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on one 256 x BN tile: each CTA stages its own 128 rows of A and its
+// half of the B tile (BN/2 rows), so the operand bytes per SM and per FLOP drop by a third and the ring gets 6 stages instead of 4.
+template <int BN, class Epi, int CG = 1> struct TcCfg {
   static constexpr int kABytes = TC_BM * TC_BK * 2;
-  static constexpr int kBBytes = BN * TC_BK * 2;
+  static constexpr int kBBytes = (BN / CG) * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBytes = 32 * 32 * (int)sizeof(typename Epi::TOut);
   static constexpr int kEpiWarpBytes = kOutBytes + Epi::kAuxBytes;
   static constexpr int kEpiBytes = TC_EPI_WARPS * kEpiWarpBytes;
-  static constexpr int kMaxStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kMaxStages = CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kFit = (TC_SMEM_MAX - 1024 - TC_BAR_BYTES - kEpiBytes) / kStageBytes;
   static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
   static_assert(kStages >= 2, "operand ring too shallow");
@@ -68,13 +72,14 @@ template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
   else return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));                      // SWIZZLE_64B:  addr[4:5] ^= addr[7:8]
 }
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
                const __grid_constant__ CUtensorMap tma_aux, TcShape s, Epi epi) {
-  using Cfg = TcCfg<BN, Epi>;
+  using Cfg = TcCfg<BN, Epi, CG>;
   using TOut = typename Epi::TOut;
   constexpr int STAGES = Cfg::kStages;
+  constexpr int TM = TC_BM * CG;                           // rows of one (cluster) tile
   constexpr int ROWB = 32 * (int)sizeof(TOut);            // bytes per staged row: 64 (bf16) or 128 (fp32)
   constexpr bool kAux = Epi::kAuxBytes > 0;
   static_assert(Epi::kAuxBytes == 0 || Epi::kAuxBytes == 2048 || Epi::kAuxBytes == 4096, "aux block: 32x32 bf16 or fp32");
@@ -92,6 +97,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;    // cluster dims (2,1,1): rank = blockIdx.x & 1
+  const bool leader = cta_rank == 0;
+  const int64_t work_id = CG == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t work_stride = CG == 2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tma_a);
@@ -104,21 +113,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], TC_EPI_WARPS);
+      ptx::mbar_init(&tempty_bar[i], TC_EPI_WARPS * CG);      // CG = 2: the peer's epilogue warps arrive remotely on the leader's barrier
     }
     for (int i = 0; i < TC_EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
-    ptx::tmem_relinquish();
+    if constexpr (CG == 2) {
+      ptx::tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish_cg2();
+    } else {
+      ptx::tmem_alloc(tmem_slot, Cfg::kTmemCols);
+      ptx::tmem_relinquish();
+    }
   }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync();             // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int64_t m_tiles = (s.M + TC_BM - 1) / TC_BM;
+  const int64_t m_tiles = (s.M + TM - 1) / TM;
   const int64_t n_tiles = (s.N + BN - 1) / BN;
   const int64_t kb_total = (s.K + TC_BK - 1) / TC_BK;
   const int64_t kb_per_split = (kb_total + s.splits - 1) / s.splits;
@@ -132,32 +147,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       // issue (load into stage `dst`) or prefetch-to-L2 (dst == nullptr) the two operand boxes of k-block kb of a tile
       auto fetch = [&](int64_t m_t, int64_t n_t, int64_t kb, uint8_t* dst, uint64_t* bar) {
         const int32_t k_el = (int32_t)(kb * TC_BK);
+        // CG = 2: the bytes of BOTH CTAs are counted on the leader's barrier (only the leader issues MMAs)
+        const uint32_t bar_addr = (CG == 2 && bar) ? ptx::mapa_u32(ptx::smem_u32(bar), 0) : 0u;
         uint8_t* sa = dst;
         uint8_t* sb = dst + Cfg::kABytes;
+        const int32_t a_row = (int32_t)(m_t * TM) + (int32_t)cta_rank * TC_BM;          // this CTA's 128 rows of the tile
+        const int32_t b_row = (int32_t)(n_t * BN) + (int32_t)cta_rank * (BN / CG);        // this CTA's share of the B tile
+        auto ld = [&](void* d, const CUtensorMap* m, int32_t c0, int32_t c1) {
+          if constexpr (CG == 2) ptx::tma_load_2d_cg2(d, m, bar_addr, c0, c1);
+          else ptx::tma_load_2d(d, m, bar, c0, c1);
+        };
         if constexpr (!A_MN) {
-          if (dst) ptx::tma_load_2d(sa, &tma_a, bar, k_el, (int32_t)(m_t * TC_BM));
-          else ptx::tma_prefetch_2d(&tma_a, k_el, (int32_t)(m_t * TC_BM));
+          if (dst) ld(sa, &tma_a, k_el, a_row);
+          else ptx::tma_prefetch_2d(&tma_a, k_el, a_row);
         } else {
 #pragma unroll
           for (int j = 0; j < TC_BM / 64; ++j) {
-            if (dst) ptx::tma_load_2d(sa + j * (64 * TC_BK * 2), &tma_a, bar, (int32_t)(m_t * TC_BM + j * 64), k_el);
-            else ptx::tma_prefetch_2d(&tma_a, (int32_t)(m_t * TC_BM + j * 64), k_el);
+            if (dst) ld(sa + j * (64 * TC_BK * 2), &tma_a, a_row + j * 64, k_el);
+            else ptx::tma_prefetch_2d(&tma_a, a_row + j * 64, k_el);
           }
         }
         if constexpr (!B_MN) {
-          if (dst) ptx::tma_load_2d(sb, &tma_b, bar, k_el, (int32_t)(n_t * BN));
-          else ptx::tma_prefetch_2d(&tma_b, k_el, (int32_t)(n_t * BN));
+          if (dst) ld(sb, &tma_b, k_el, b_row);
+          else ptx::tma_prefetch_2d(&tma_b, k_el, b_row);
         } else {
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j) {
-            if (dst) ptx::tma_load_2d(sb + j * (64 * TC_BK * 2), &tma_b, bar, (int32_t)(n_t * BN + j * 64), k_el);
-            else ptx::tma_prefetch_2d(&tma_b, (int32_t)(n_t * BN + j * 64), k_el);
+          for (int j = 0; j < (BN / CG) / 64; ++j) {
+            if (dst) ld(sb + j * (64 * TC_BK * 2), &tma_b, b_row + j * 64, k_el);
+            else ptx::tma_prefetch_2d(&tma_b, b_row + j * 64, k_el);
           }
         }
       };
       // L2 prefetch cursor: runs s.pf_dist k-blocks ahead of the load cursor through this CTA's (tile, k-block) sequence, so the loads
       // that fill the smem ring hit L2 (~700 cycles) instead of HBM (~2000+): the 4-stage ring alone cannot cover DRAM latency
-      int64_t p_tile = blockIdx.x, p_kb = 0, p_kb1 = 0;
+      int64_t p_tile = work_id, p_kb = 0, p_kb1 = 0;
       bool p_live = s.pf_dist > 0 && p_tile < num_tiles;
       auto p_range = [&]() {
         const int64_t sp = p_tile / (n_tiles * m_tiles);
@@ -166,7 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       };
       auto p_step = [&]() {         // prefetch the cursor's k-block, then advance it
         while (p_live && p_kb >= p_kb1) {
-          p_tile += gridDim.x;
+          p_tile += work_stride;
           p_live = p_tile < num_tiles;
           if (p_live) p_range();
         }
@@ -180,13 +203,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int64_t tile = work_id; tile < num_tiles; tile += work_stride) {
         const int64_t m_t = tile % m_tiles, n_t = (tile / m_tiles) % n_tiles, sp = tile / (n_tiles * m_tiles);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         for (int64_t kb = kb0; kb < kb1; ++kb) {
           p_step();
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
           fetch(m_t, n_t, kb, smem + stage * Cfg::kStageBytes, &full_bar[stage]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -194,14 +217,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0) {
-      const uint32_t idesc = ptx::make_idesc_bf16(TC_BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = ptx::make_idesc_bf16(TM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      auto commit = [&](uint64_t* bar) {          // CG = 2: the same barrier in both CTAs of the pair
+        if constexpr (CG == 2) ptx::umma_commit_cg2_mc(bar, (uint16_t)3);
+        else ptx::umma_commit(bar);
+      };
       constexpr uint32_t a_kstep = A_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;   // bytes to the next K=16 slice
       constexpr uint32_t b_kstep = B_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
-      for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
         const int64_t sp = tile / (n_tiles * m_tiles);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         const int acc = (int)(it & 1);
@@ -211,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         if (kb0 >= kb1) {
           // empty K range (the host never asks for one): the epilogue treats it as an all-zero accumulator
-          ptx::umma_commit(&tfull_bar[acc]);
+          commit(&tfull_bar[acc]);
           continue;
         }
         for (int64_t kb = kb0; kb < kb1; ++kb) {
@@ -223,12 +250,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
             const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * a_kstep, s.a_lbo, s.a_sbo);
             const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * b_kstep, s.b_lbo, s.b_sbo);
-            ptx::umma_f16(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            if constexpr (CG == 2) ptx::umma_f16_cg2(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            else ptx::umma_f16(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
-          ptx::umma_commit(&empty_bar[stage]);      // smem slot free once these MMAs retire
+          commit(&empty_bar[stage]);                // smem slot free (in both CTAs) once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::umma_commit(&tfull_bar[acc]);          // accumulator complete
+        commit(&tfull_bar[acc]);                    // accumulator complete
       }
     }
   } else {
@@ -268,12 +296,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
     };
     int64_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
       const int64_t m_t = tile % m_tiles, n_t = (tile / m_tiles) % n_tiles, sp = tile / (n_tiles * m_tiles);
       const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-      const int32_t row_base = (int32_t)(m_t * TC_BM) + quarter * 32;
+      const int32_t row_base = (int32_t)(m_t * TM) + (int32_t)cta_rank * TC_BM + quarter * 32;
       const int64_t row = (int64_t)row_base + lane;
       const bool valid = row < s.M;
       const int col_base = (int)(n_t * BN) + half * COLS_PER_WARP;
@@ -286,9 +314,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           ptx::tma_load_2d(abuf, &tma_aux, &aux_bar[ew], col_base, row_base);
         }
         // and pull this warp's auxiliary blocks of the CTA's NEXT tile into L2 (they stream from HBM otherwise)
-        const int64_t nxt = tile + gridDim.x;
+        const int64_t nxt = tile + work_stride;
         if (s.pf_dist > 0 && nxt < num_tiles && lane < CH) {
-          const int32_t nrow = (int32_t)((nxt % m_tiles) * TC_BM) + quarter * 32;
+          const int32_t nrow = (int32_t)((nxt % m_tiles) * TM) + (int32_t)cta_rank * TC_BM + quarter * 32;
           const int ncol = (int)(((nxt / m_tiles) % n_tiles) * BN) + half * COLS_PER_WARP + lane * 32;
           if (ncol < s.N) ptx::tma_prefetch_2d(&tma_aux, ncol, nrow);
         }
@@ -396,7 +424,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty_bar[acc]), 0));
+        else ptx::mbar_arrive(&tempty_bar[acc]);
+      }
     }
     cs_flush();
     if (lane == 0) ptx::bulk_wait_all();     // shared memory must outlive the last store's read
@@ -404,7 +435,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   // ============================ teardown ==================================
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (CG == 2) ptx::cluster_sync();     // neither CTA may retire while the pair's MMAs / multicast commits can still touch it
+  else __syncthreads();
   if constexpr (Epi::kReduce) {
     const float ws = warp_sum(red);
     if (lane == 0) red_smem[warp] = ws;
@@ -418,7 +450,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   if (warp == 1) {
     __syncwarp();
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if constexpr (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+    else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
@@ -453,11 +486,18 @@ static inline int tc_pick_bn(int N) {
   return 64;
 }
 // CTAs a launch uses (= rows / 4 of the kColSum partial buffer, = slots of a kReduce epilogue)
+int tc_two_cta();         // option "tc_two_cta": use CTA pairs (cta_group::2) where the shape allows
+// does this shape run as CTA pairs?  (BN = 256 tiles and more than one 128-row block of M)
+static inline bool tc_use_pair(int64_t M, int N, int force_bn = 0) {
+  const int bn = force_bn ? force_bn : tc_pick_bn(N);
+  return tc_two_cta() && bn == 256 && M > TC_BM;
+}
 static inline int64_t tc_ctas(int64_t M, int N, int splits, int force_bn = 0) {
   const int bn = force_bn ? force_bn : tc_pick_bn(N);
-  int64_t tiles = ceil_div64(M, TC_BM) * ceil_div64(N, bn) * (splits < 1 ? 1 : splits);
-  const int64_t g = tc_grid_size();
-  return tiles < g ? tiles : g;
+  const int cg = tc_use_pair(M, N, force_bn) ? 2 : 1;
+  int64_t tiles = ceil_div64(M, TC_BM * cg) * ceil_div64(N, bn) * (splits < 1 ? 1 : splits);
+  const int64_t g = tc_grid_size() / cg;
+  return (tiles < g ? tiles : g) * cg;
 }
 
 template <class Epi, class = void> struct epi_aux_ptr {
@@ -479,13 +519,13 @@ template <class Epi> struct epi_split_stride<Epi, std::enable_if_t<Epi::kSplit>>
 template <class Epi, class = void> struct epi_cs_atomic { static bool get(const Epi&) { return false; } };
 template <class Epi> struct epi_cs_atomic<Epi, std::enable_if_t<Epi::kColSum>> { static bool get(const Epi& e) { return e.colsum_atomic != 0; } };
 
-template <int BN, bool A_MN, bool B_MN, class Epi>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1>
 int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st) {
-  using Cfg = TcCfg<BN, Epi>;
+  using Cfg = TcCfg<BN, Epi, CG>;
   using TOut = typename Epi::TOut;
   CUtensorMap ta, tb, tout, taux;
   PSVAE_TRY(tc_tensor_map(A, K, A_MN ? TC_BK : TC_BM, &ta));
-  PSVAE_TRY(tc_tensor_map(B, K, B_MN ? TC_BK : BN, &tb));
+  PSVAE_TRY(tc_tensor_map(B, K, B_MN ? TC_BK : BN / CG, &tb));
   TcShape s;
   s.M = M; s.N = N; s.K = K; s.splits = splits < 1 ? 1 : splits;
   tc_desc_strides(A_MN, &s.a_lbo, &s.a_sbo);
@@ -502,7 +542,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   } else {
     taux = ta;
   }
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG>;
   static unsigned long long attr_mask = 0;   // per instantiation, one bit per device
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
@@ -510,15 +550,31 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
     PSVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_mask |= 1ull << (dev & 63);
   }
-  const int64_t tiles = ceil_div64(M, TC_BM) * ceil_div64(N, BN) * s.splits;
-  int grid = tc_grid_size();
+  const int64_t tiles = ceil_div64(M, TC_BM * CG) * ceil_div64(N, BN) * s.splits;
+  int grid = tc_grid_size() / CG;            // CG = 2: one CTA pair per tile
   if (tiles < grid) grid = (int)tiles;
+  grid *= CG;
   if (grid < 1) return 0;
   if constexpr (Epi::kColSum) {
     // every (CTA, row-quarter) writes only the columns of the N tiles it saw: the rest of the partial buffer must read as zero
     if (!epi_cs_atomic<Epi>::get(epi)) PSVAE_CUDA(cudaMemsetAsync(epi.colsum, 0, (size_t)grid * 4 * (size_t)N * sizeof(float), st));
   }
-  kern<<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, tout, taux, s, epi);
+  if constexpr (CG == 2) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, s, epi));
+  } else {
+    kern<<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, tout, taux, s, epi);
+  }
   count_launch();
   PSVAE_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
@@ -532,7 +588,9 @@ int gemm_tc_launch(const TcOperand& A, const TcOperand& B, int64_t M, int N, int
   if (N % 8 != 0) { set_error("gemm_tc: N=%d must be a multiple of 8", N); return -2; }
   const int bn = force_bn ? force_bn : tc_pick_bn(N);
   switch (bn) {
-    case 256: return gemm_tc_launch_bn<256, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, st);
+    case 256:
+      if (tc_use_pair(M, N, force_bn)) return gemm_tc_launch_bn<256, A_MN, B_MN, Epi, 2>(A, B, M, N, K, splits, epi, st);
+      return gemm_tc_launch_bn<256, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, st);
     case 128: return gemm_tc_launch_bn<128, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, st);
     case 64: return gemm_tc_launch_bn<64, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, st);
   }

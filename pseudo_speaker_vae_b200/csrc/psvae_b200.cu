@@ -56,6 +56,7 @@ struct Options {
   int64_t tc_force_bn = 0;             // tests: force the N tile of the tcgen05 engine
   int64_t tc_grid_limit = 0;           // tests: cap the persistent grid
   int64_t tc_prefetch = 0;             // k-blocks the operand L2 prefetch runs ahead of the smem ring (measured: 0.99 ms off vs 1.19-1.26 ms on -- the mainloop is L2->SM bandwidth-bound, not latency-bound; kept as an experiment knob)
+  int64_t tc_two_cta = 0;              // 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2) for BN = 256 shapes
   int64_t deterministic = 0;           // 1: split-K / bias partials go through ordered two-stage sums instead of TMA reduce-add / atomics
 };
 static Options g_opt;
@@ -97,6 +98,7 @@ int tc_device_check() {
   return 0;
 }
 int tc_prefetch_distance() { return (int)g_opt.tc_prefetch; }
+int tc_two_cta() { return (int)g_opt.tc_two_cta; }
 int tc_grid_size() {
   DevInfo* d = nullptr;
   if (dev_info(&d) != 0) return PSVAE_NUM_SMS;
@@ -247,9 +249,10 @@ template <> struct Engine<bf16> {
   }
   static int wgrad_splits(int64_t M, int64_t N, int64_t K) {
     const int bn = g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn((int)N);
-    const int64_t tiles = ceil_div64(M, TC_BM) * ceil_div64(N, bn);
+    const int cg = tc_use_pair(M, (int)N, (int)g_opt.tc_force_bn) ? 2 : 1;
+    const int64_t tiles = ceil_div64(M, TC_BM * cg) * ceil_div64(N, bn);
     const int64_t kb = ceil_div64(K, TC_BK);
-    int64_t s = PSVAE_NUM_SMS / tiles;
+    int64_t s = (PSVAE_NUM_SMS / cg) / tiles;
     if (s > kb) s = kb;
     if (s > g_opt.wgrad_split_cap) s = g_opt.wgrad_split_cap;
     if (s < 1) s = 1;
@@ -722,12 +725,7 @@ static int run_step(const StepArgs& a) {
       EpiMse<TAct> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, a.want_grads ? w.dxh : nullptr, n.D, scale, w.sse_part, nullptr, 0};
       PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
     }
-    n_sse_used = sizeof(TAct) == 2 ? tc_grid_size() : (int)sgemm_red_slots(B, n.D);
-    if (sizeof(TAct) == 2) {
-      // the persistent grid may be smaller than the SM count when there are few tiles: clear the unused slots' contribution
-      const int64_t tiles = ceil_div64(B, TC_BM) * ceil_div64(n.D, g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(n.D));
-      if (tiles < n_sse_used) n_sse_used = (int)tiles;
-    }
+    n_sse_used = sizeof(TAct) == 2 ? (int)tc_ctas(B, n.D, 1, (int)g_opt.tc_force_bn) : (int)sgemm_red_slots(B, n.D);   // one slot per CTA / per tile
     if (dec_last_bias_reduce) PSVAE_TRY(launch_reduce(w.cpart, n.D, n_sse_used * 4, a.grads + d->dec_b[n.nh], st));
   } else {
     float* u = general_tail ? w.u : (a.x_hat ? a.x_hat : w.u);
@@ -968,6 +966,7 @@ int psvae_set_option(const char* name, int64_t value) {
   }
   if (!strcmp(name, "tc_grid_limit")) { g_opt.tc_grid_limit = value < 0 ? 0 : value; return 0; }
   if (!strcmp(name, "deterministic")) { g_opt.deterministic = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_two_cta")) { g_opt.tc_two_cta = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_prefetch")) { g_opt.tc_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
   set_error("unknown option '%s'", name);
   return -2;
@@ -980,6 +979,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_force_bn")) return g_opt.tc_force_bn;
   if (!strcmp(name, "tc_grid_limit")) return g_opt.tc_grid_limit;
   if (!strcmp(name, "deterministic")) return g_opt.deterministic;
+  if (!strcmp(name, "tc_two_cta")) return g_opt.tc_two_cta;
   if (!strcmp(name, "tc_prefetch")) return g_opt.tc_prefetch;
   return -1;
 }

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--relu", type=int, default=0)
     ap.add_argument("--bias", type=int, default=0)
     ap.add_argument("--grid", type=int, default=0)
+    ap.add_argument("--cg", type=int, default=0, help="1: CTA pairs (tcgen05 cta_group::2)")
     a = ap.parse_args()
     import torch
 
@@ -39,6 +40,7 @@ def main():
         bias = torch.randn(a.n, device="cuda") if a.bias else None
         L.set_option("tc_force_bn", a.bn)
         L.set_option("tc_grid_limit", a.grid)
+        L.set_option("tc_two_cta", a.cg)
         c, ref = gemm_bf16(A, B, bias, bool(a.a_mn), bool(a.b_mn), bool(a.relu), a.split)
         torch.cuda.synchronize()
         err = ((c.double() - ref).norm() / ref.norm()).item()

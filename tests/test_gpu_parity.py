@@ -147,6 +147,26 @@ def test_tcgen05_gemm_variant(v):
     assert out["finite"] and out["rel_err"] < 1e-5, out     # exact bf16 products, fp32 accumulation: only summation order differs
 
 
+PAIR_VARIANTS = [v for v in TC_VARIANTS if v[0] > 128 and (v[5] == 256 or (v[5] == 0 and v[1] % 256 == 0))] + [
+    (65536, 512, 512, 0, 0, 0, 1, 1, 1, 0),     # the encoder hidden layer at full batch
+    (1000, 256, 200, 0, 1, 0, 1, 0, 0, 0),      # ragged M (the peer CTA's rows run past the matrix), ragged K
+    (300, 512, 64, 0, 0, 0, 1, 0, 1, 0),        # second half of the pair entirely outside M on the last tile
+]
+
+
+@pytest.mark.parametrize("v", PAIR_VARIANTS, ids=lambda v: "pair_m%d_n%d_k%d_a%d_b%d_bn%d_s%d" % v[:7])
+def test_tcgen05_gemm_cta_pair_variant(v):
+    """The same GEMM forms on CTA pairs (cluster of 2, tcgen05 cta_group::2, 256-row tiles)."""
+    m, n, k, a_mn, b_mn, bn, split, relu, bias, grid = v
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "gpu_case.py"), "gemm", "--m", str(m), "--n", str(n), "--k", str(k), "--a_mn", str(a_mn),
+           "--b_mn", str(b_mn), "--bn", str(bn), "--split", str(split), "--relu", str(relu), "--bias", str(bias), "--grid", str(grid), "--cg", "1"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240, cwd=ROOT)
+    line = [l for l in res.stdout.splitlines() if l.startswith("RESULT ")]
+    assert res.returncode == 0 and line, f"rc={res.returncode}\n{res.stdout[-2000:]}\n{res.stderr[-3000:]}"
+    out = json.loads(line[-1][7:])
+    assert out["finite"] and out["rel_err"] < 1e-5, out
+
+
 # ------------------------------------------------------------------------------------------------
 # train step against the reference's golden outputs
 # ------------------------------------------------------------------------------------------------
