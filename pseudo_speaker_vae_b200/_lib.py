@@ -105,6 +105,10 @@ def lib() -> C.CDLL:
         v = l.psvae_abi_version()
         if v != PSVAE_ABI_VERSION:
             raise RuntimeError(f"ABI mismatch: library {v}, binding {PSVAE_ABI_VERSION}; rebuild the extension")
+        for key, val in os.environ.items():          # PSVAE_OPT_<NAME>=<int>: tuning options without touching code
+            if key.startswith("PSVAE_OPT_"):
+                if l.psvae_set_option(key[len("PSVAE_OPT_"):].lower().encode(), int(val)) != 0:
+                    raise ValueError(f"{key}: {l.psvae_last_error_string().decode()}")
         _lib = l
     return _lib
 

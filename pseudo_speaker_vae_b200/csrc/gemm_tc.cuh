@@ -64,6 +64,7 @@ struct TcShape {
   int32_t splits;   // split-K factor (>= 1)
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // UMMA smem-descriptor strides (bytes)
   int32_t pf_dist;  // k-blocks the L2 prefetch cursor leads the load cursor by (0 = off)
+  int32_t reverse;  // walk the M tiles (and the split-K ranges) from the end: the rows the previous kernel wrote last are still in L2
 };
 
 // byte offset of 16-byte chunk j of row r inside a staged 32-row block whose rows are ROWB bytes (TMA swizzle = ROWB)
@@ -183,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int64_t p_tile = work_id, p_kb = 0, p_kb1 = 0;
       bool p_live = s.pf_dist > 0 && p_tile < num_tiles;
       auto p_range = [&]() {
-        const int64_t sp = p_tile / (n_tiles * m_tiles);
+        const int64_t sp = s.reverse ? s.splits - 1 - p_tile / (n_tiles * m_tiles) : p_tile / (n_tiles * m_tiles);
         p_kb = sp * kb_per_split;
         p_kb1 = min(kb_total, p_kb + kb_per_split);
       };
@@ -194,7 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (p_live) p_range();
         }
         if (!p_live) return;
-        fetch(p_tile % m_tiles, (p_tile / m_tiles) % n_tiles, p_kb, nullptr, nullptr);
+        fetch(s.reverse ? m_tiles - 1 - p_tile % m_tiles : p_tile % m_tiles, (p_tile / m_tiles) % n_tiles, p_kb, nullptr, nullptr);
         ++p_kb;
       };
       if (p_live) {
@@ -204,7 +205,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t tile = work_id; tile < num_tiles; tile += work_stride) {
-        const int64_t m_t = tile % m_tiles, n_t = (tile / m_tiles) % n_tiles, sp = tile / (n_tiles * m_tiles);
+        const int64_t m_t = s.reverse ? m_tiles - 1 - tile % m_tiles : tile % m_tiles, n_t = (tile / m_tiles) % n_tiles,
+                      sp = s.reverse ? s.splits - 1 - tile / (n_tiles * m_tiles) : tile / (n_tiles * m_tiles);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         for (int64_t kb = kb0; kb < kb1; ++kb) {
           p_step();
@@ -229,7 +231,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       uint32_t phase = 0;
       int64_t it = 0;
       for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
-        const int64_t sp = tile / (n_tiles * m_tiles);
+        const int64_t sp = s.reverse ? s.splits - 1 - tile / (n_tiles * m_tiles) : tile / (n_tiles * m_tiles);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         const int acc = (int)(it & 1);
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
@@ -297,7 +299,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     };
     int64_t it = 0;
     for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
-      const int64_t m_t = tile % m_tiles, n_t = (tile / m_tiles) % n_tiles, sp = tile / (n_tiles * m_tiles);
+      const int64_t m_t = s.reverse ? m_tiles - 1 - tile % m_tiles : tile % m_tiles, n_t = (tile / m_tiles) % n_tiles,
+                      sp = s.reverse ? s.splits - 1 - tile / (n_tiles * m_tiles) : tile / (n_tiles * m_tiles);
       const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
@@ -316,7 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // and pull this warp's auxiliary blocks of the CTA's NEXT tile into L2 (they stream from HBM otherwise)
         const int64_t nxt = tile + work_stride;
         if (s.pf_dist > 0 && nxt < num_tiles && lane < CH) {
-          const int32_t nrow = (int32_t)((nxt % m_tiles) * TM) + (int32_t)cta_rank * TC_BM + quarter * 32;
+          const int32_t nrow = (int32_t)((s.reverse ? m_tiles - 1 - nxt % m_tiles : nxt % m_tiles) * TM) + (int32_t)cta_rank * TC_BM + quarter * 32;
           const int ncol = (int)(((nxt / m_tiles) % n_tiles) * BN) + half * COLS_PER_WARP + lane * 32;
           if (ncol < s.N) ptx::tma_prefetch_2d(&tma_aux, ncol, nrow);
         }
@@ -486,6 +489,7 @@ static inline int tc_pick_bn(int N) {
   return 64;
 }
 // CTAs a launch uses (= rows / 4 of the kColSum partial buffer, = slots of a kReduce epilogue)
+int tc_next_direction();  // option "tc_zigzag": successive GEMM launches alternate the direction in which they walk the batch
 int tc_two_cta();         // option "tc_two_cta": use CTA pairs (cta_group::2) where the shape allows
 // does this shape run as CTA pairs?  (BN = 256 tiles and more than one 128-row block of M)
 static inline bool tc_use_pair(int64_t M, int N, int force_bn = 0) {
@@ -531,6 +535,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   tc_desc_strides(A_MN, &s.a_lbo, &s.a_sbo);
   tc_desc_strides(B_MN, &s.b_lbo, &s.b_sbo);
   s.pf_dist = tc_prefetch_distance();
+  s.reverse = tc_next_direction();
   if (epi.out) {
     const bool split_slots = Epi::kSplit && !epi_split_stride<Epi>::reduce(epi);
     PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, N, epi.ldo, split_slots ? s.splits : 0, epi_split_stride<Epi>::get(epi), &tout));

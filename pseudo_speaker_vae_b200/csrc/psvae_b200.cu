@@ -57,6 +57,7 @@ struct Options {
   int64_t tc_grid_limit = 0;           // tests: cap the persistent grid
   int64_t tc_prefetch = 0;             // k-blocks the operand L2 prefetch runs ahead of the smem ring (measured: 0.99 ms off vs 1.19-1.26 ms on -- the mainloop is L2->SM bandwidth-bound, not latency-bound; kept as an experiment knob)
   int64_t tc_two_cta = 0;              // 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2) for BN = 256 shapes
+  int64_t tc_zigzag = 1;               // successive GEMM launches walk the batch in alternating directions (L2 reuse of the rows written last)
   int64_t deterministic = 0;           // 1: split-K / bias partials go through ordered two-stage sums instead of TMA reduce-add / atomics
 };
 static Options g_opt;
@@ -99,6 +100,8 @@ int tc_device_check() {
 }
 int tc_prefetch_distance() { return (int)g_opt.tc_prefetch; }
 int tc_two_cta() { return (int)g_opt.tc_two_cta; }
+static thread_local unsigned g_dir = 0;
+int tc_next_direction() { return g_opt.tc_zigzag ? (int)(g_dir++ & 1u) : 0; }
 int tc_grid_size() {
   DevInfo* d = nullptr;
   if (dev_info(&d) != 0) return PSVAE_NUM_SMS;
@@ -967,6 +970,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_grid_limit")) { g_opt.tc_grid_limit = value < 0 ? 0 : value; return 0; }
   if (!strcmp(name, "deterministic")) { g_opt.deterministic = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_two_cta")) { g_opt.tc_two_cta = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_zigzag")) { g_opt.tc_zigzag = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_prefetch")) { g_opt.tc_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
   set_error("unknown option '%s'", name);
   return -2;
@@ -980,6 +984,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_grid_limit")) return g_opt.tc_grid_limit;
   if (!strcmp(name, "deterministic")) return g_opt.deterministic;
   if (!strcmp(name, "tc_two_cta")) return g_opt.tc_two_cta;
+  if (!strcmp(name, "tc_zigzag")) return g_opt.tc_zigzag;
   if (!strcmp(name, "tc_prefetch")) return g_opt.tc_prefetch;
   return -1;
 }
