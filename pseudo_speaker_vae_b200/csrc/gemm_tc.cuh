@@ -144,7 +144,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   if (warp == 0) {
     // ============================ TMA producer ============================
-    if (lane == 0) {
+    // warp-uniform loop; the TMA instructions of one k-block are issued by one elected lane
+    {
       // issue (load into stage `dst`) or prefetch-to-L2 (dst == nullptr) the two operand boxes of k-block kb of a tile
       auto fetch = [&](int64_t m_t, int64_t n_t, int64_t kb, uint8_t* dst, uint64_t* bar) {
         const int32_t k_el = (int32_t)(kb * TC_BK);
@@ -195,7 +196,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (p_live) p_range();
         }
         if (!p_live) return;
-        fetch(s.reverse ? m_tiles - 1 - p_tile % m_tiles : p_tile % m_tiles, (p_tile / m_tiles) % n_tiles, p_kb, nullptr, nullptr);
+        if (ptx::elect_one()) fetch(s.reverse ? m_tiles - 1 - p_tile % m_tiles : p_tile % m_tiles, (p_tile / m_tiles) % n_tiles, p_kb, nullptr, nullptr);
+        __syncwarp();
         ++p_kb;
       };
       if (p_live) {
@@ -209,24 +211,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                       sp = s.reverse ? s.splits - 1 - tile / (n_tiles * m_tiles) : tile / (n_tiles * m_tiles);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         for (int64_t kb = kb0; kb < kb1; ++kb) {
-          p_step();
+          if (s.pf_dist > 0) p_step();
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
-          fetch(m_t, n_t, kb, smem + stage * Cfg::kStageBytes, &full_bar[stage]);
+          if (ptx::elect_one()) {
+            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
+            fetch(m_t, n_t, kb, smem + stage * Cfg::kStageBytes, &full_bar[stage]);
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ============================ MMA issuer ==============================
-    if (lane == 0 && leader) {
+    // The whole warp walks the loop (warp-uniform control flow and operands); only the tcgen05 instructions are predicated on one
+    // elected lane.  Descriptors are a precomputed base + a stage / k-slice offset in the 14-bit address field.
+    if (leader) {
       const uint32_t idesc = ptx::make_idesc_bf16(TM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      auto commit = [&](uint64_t* bar) {          // CG = 2: the same barrier in both CTAs of the pair
-        if constexpr (CG == 2) ptx::umma_commit_cg2_mc(bar, (uint16_t)3);
-        else ptx::umma_commit(bar);
-      };
       constexpr uint32_t a_kstep = A_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;   // bytes to the next K=16 slice
       constexpr uint32_t b_kstep = B_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;
+      const uint64_t da0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem), s.a_lbo, s.a_sbo);
+      const uint64_t db0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem) + Cfg::kABytes, s.b_lbo, s.b_sbo);
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
@@ -238,27 +243,31 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        if (kb0 >= kb1) {
-          // empty K range (the host never asks for one): the epilogue treats it as an all-zero accumulator
-          commit(&tfull_bar[acc]);
-          continue;
-        }
         for (int64_t kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase, 3);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::kStageBytes);
-          const uint32_t sb = sa + Cfg::kABytes;
+          const uint64_t soff = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
-            const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * a_kstep, s.a_lbo, s.a_sbo);
-            const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * b_kstep, s.b_lbo, s.b_sbo);
-            if constexpr (CG == 2) ptx::umma_f16_cg2(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-            else ptx::umma_f16(tmem_d, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
+              const uint64_t da = da0 + soff + (uint64_t)((kk * a_kstep) >> 4);
+              const uint64_t db = db0 + soff + (uint64_t)((kk * b_kstep) >> 4);
+              const uint32_t accum = (kb > kb0 || kk > 0) ? 1u : 0u;
+              if constexpr (CG == 2) ptx::umma_f16_cg2(tmem_d, da, db, idesc, accum);
+              else ptx::umma_f16(tmem_d, da, db, idesc, accum);
+            }
+            // smem slot free (in both CTAs of a pair) once these MMAs retire
+            if constexpr (CG == 2) ptx::umma_commit_cg2_mc(&empty_bar[stage], (uint16_t)3);
+            else ptx::umma_commit(&empty_bar[stage]);
           }
-          commit(&empty_bar[stage]);                // smem slot free (in both CTAs) once these MMAs retire
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        commit(&tfull_bar[acc]);                    // accumulator complete
+        if (ptx::elect_one()) {                   // accumulator complete (also for an empty K range: the epilogue then sees zeros)
+          if constexpr (CG == 2) ptx::umma_commit_cg2_mc(&tfull_bar[acc], (uint16_t)3);
+          else ptx::umma_commit(&tfull_bar[acc]);
+        }
+        __syncwarp();
       }
     }
   } else {

@@ -57,7 +57,7 @@ struct Options {
   int64_t tc_grid_limit = 0;           // tests: cap the persistent grid
   int64_t tc_prefetch = 0;             // k-blocks the operand L2 prefetch runs ahead of the smem ring (measured: 0.99 ms off vs 1.19-1.26 ms on -- the mainloop is L2->SM bandwidth-bound, not latency-bound; kept as an experiment knob)
   int64_t tc_two_cta = 0;              // 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2) for BN = 256 shapes
-  int64_t tc_zigzag = 1;               // successive GEMM launches walk the batch in alternating directions (L2 reuse of the rows written last)
+  int64_t tc_zigzag = 0;               // successive GEMM launches walk the batch in alternating directions (L2 reuse of the rows written last)
   int64_t deterministic = 0;           // 1: split-K / bias partials go through ordered two-stage sums instead of TMA reduce-add / atomics
 };
 static Options g_opt;

@@ -12,6 +12,15 @@ namespace ptx {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
+// One lane of a converged warp (elect.sync).  Code that issues TMA / tcgen05 instructions runs warp-uniformly and predicates only the
+// instruction itself on this: inside an `if (lane == 0)` region the compiler has to move every operand into uniform registers with an
+// ELECT / R2UR.BROADCAST waterfall loop per instruction (~30 dependent instructions per UTCHMMA -- it capped the tensor pipe at ~45 %).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- mbarrier -----------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
