@@ -15,6 +15,7 @@ namespace psvae {
 constexpr int LG_TILE = 32;      // samples per CTA
 constexpr int LG_THREADS = 256;  // 8 warps; lane = sample, warp = output-feature lane
 constexpr int LG_MAXC = 16;      // classes per head (padded row length in smem)
+constexpr int CLF_LG_MAXC = 8;   // fast path: classes summed over the targeted heads
 
 struct LangevinClf {
   int L, n_trunk, hidden, act, n_heads;
@@ -232,6 +233,147 @@ __global__ void __launch_bounds__(LG_THREADS) langevin_kernel(LangevinClf c, con
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = zs[qs * ldz + qk + j];
     store_vec<4>(z_io + r * L + qk, v);
+  }
+}
+
+}  // namespace psvae
+
+namespace psvae {
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: linear heads directly on z (no trunk -- the reference's default LatentClassifier(num_layers=1)), latent_dim in {16,32,64}.
+// ONE THREAD PER SAMPLE: z lives in registers for all steps, the head weights are broadcast reads from shared memory, the noise comes
+// from the same counter-based generator with the same counters as the generic kernel (so both produce the same z up to fp32 summation
+// order).  No __syncthreads and no shared-memory traffic for z inside the loop: the step is pure ALU/SFU work (Philox + Box-Muller).
+// ------------------------------------------------------------------------------------------------
+constexpr int LGF_THREADS = 128;
+
+template <int L>
+__global__ void __launch_bounds__(LGF_THREADS) langevin_fast_kernel(LangevinClf c, const float* __restrict__ params, float* __restrict__ z_io, int64_t rows,
+                                                                    float step_size, int num_steps, float noise_weight, uint64_t seed, uint64_t offset0,
+                                                                    int64_t row0, int init_from_philox, const float* __restrict__ noise,
+                                                                    float* __restrict__ history, float* __restrict__ stats) {
+  __shared__ __align__(16) float W[CLF_LG_MAXC * L];
+  __shared__ float bias[CLF_LG_MAXC];
+  __shared__ int cls_head[CLF_LG_MAXC];
+  // flatten the targeted heads' rows: class index cc -> (head, class)
+  int n_cls = 0;
+  for (int h = 0; h < c.n_heads; ++h) {
+    if (c.targets[h] < 0) continue;
+    for (int i = threadIdx.x; i < c.head_classes[h] * L; i += LGF_THREADS) W[n_cls * L + i] = params[c.g_head_w[h] + i];
+    if ((int)threadIdx.x < c.head_classes[h]) {
+      bias[n_cls + threadIdx.x] = params[c.g_head_b[h] + threadIdx.x];
+      cls_head[n_cls + threadIdx.x] = h;
+    }
+    n_cls += c.head_classes[h];
+  }
+  __syncthreads();
+  const int64_t r = (int64_t)blockIdx.x * LGF_THREADS + threadIdx.x;
+  const bool live = r < rows;
+  const int64_t rr = live ? r : rows - 1;                 // dead lanes shadow the last row (no stores) so that warp-collectives stay converged
+  const uint64_t q0 = (uint64_t)((row0 + rr) * L) >> 2;   // first Philox block of this row
+  float z[L];
+  if (init_from_philox) {
+#pragma unroll
+    for (int q = 0; q < L / 4; ++q) {
+      const float4 t = philox_normal4(q0 + q, seed, offset0);
+      z[4 * q] = t.x; z[4 * q + 1] = t.y; z[4 * q + 2] = t.z; z[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < L / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(z_io + rr * L + 4 * q);
+      z[4 * q] = t.x; z[4 * q + 1] = t.y; z[4 * q + 2] = t.z; z[4 * q + 3] = t.w;
+    }
+  }
+  const float half_s2 = 0.5f * step_size * step_size;
+  const float nscale = step_size * noise_weight;
+  for (int step = 0; step < num_steps; ++step) {
+    // logits of the targeted heads
+    float coef[CLF_LG_MAXC];
+#pragma unroll
+    for (int cc = 0; cc < CLF_LG_MAXC; ++cc) {
+      float a = 0.f;
+      if (cc < n_cls) {
+        a = bias[cc];
+#pragma unroll
+        for (int k = 0; k < L; k += 4) {
+          const float4 w = *reinterpret_cast<const float4*>(&W[cc * L + k]);
+          a = fmaf(z[k], w.x, a); a = fmaf(z[k + 1], w.y, a); a = fmaf(z[k + 2], w.z, a); a = fmaf(z[k + 3], w.w, a);
+        }
+      }
+      coef[cc] = a;
+    }
+    // per head: coef <- onehot(target) - softmax ; lp_y += log p(target)
+    float lp_y = 0.f;
+    {
+      int base = 0;
+      for (int h = 0; h < c.n_heads; ++h) {
+        if (c.targets[h] < 0) continue;
+        const int C = c.head_classes[h];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int cc = 0; cc < CLF_LG_MAXC; ++cc)
+          if (cc >= base && cc < base + C) mx = fmaxf(mx, coef[cc]);
+        float se = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < CLF_LG_MAXC; ++cc)
+          if (cc >= base && cc < base + C) se += expf(coef[cc] - mx);
+        const float lse = logf(se);
+#pragma unroll
+        for (int cc = 0; cc < CLF_LG_MAXC; ++cc)
+          if (cc >= base && cc < base + C) {
+            const float lp = coef[cc] - mx - lse;
+            const bool tgt = (cc - base) == c.targets[h];
+            if (tgt) lp_y += lp;
+            coef[cc] = (tgt ? 1.f : 0.f) - expf(lp);
+          }
+        base += C;
+      }
+    }
+    if (stats) {
+      float lp_z = 0.f;
+#pragma unroll
+      for (int k = 0; k < L; ++k) lp_z = fmaf(z[k], z[k], lp_z);
+      lp_z *= -0.5f;
+      const float a = warp_sum(live ? lp_y + lp_z : 0.f);
+      const float b = warp_sum(live ? expf(lp_y) : 0.f);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(stats + 2 * step, a);
+        atomicAdd(stats + 2 * step + 1, b);
+      }
+    }
+    // z <- z + 0.5 s^2 (W^T coef - z) + s * noise_weight * N(0, I)
+#pragma unroll
+    for (int q = 0; q < L / 4; ++q) {
+      float nz[4];
+      if (noise) {
+        const float4 t = *reinterpret_cast<const float4*>(noise + ((int64_t)step * rows + rr) * L + 4 * q);
+        nz[0] = t.x; nz[1] = t.y; nz[2] = t.z; nz[3] = t.w;
+      } else {
+        const float4 t = philox_normal4(q0 + q, seed, offset0 + 1 + (uint64_t)step);
+        nz[0] = t.x; nz[1] = t.y; nz[2] = t.z; nz[3] = t.w;
+      }
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int cc = 0; cc < CLF_LG_MAXC; ++cc)
+        if (cc < n_cls) {
+          const float4 w = *reinterpret_cast<const float4*>(&W[cc * L + 4 * q]);
+          g[0] = fmaf(coef[cc], w.x, g[0]); g[1] = fmaf(coef[cc], w.y, g[1]); g[2] = fmaf(coef[cc], w.z, g[2]); g[3] = fmaf(coef[cc], w.w, g[3]);
+        }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float zv = z[4 * q + j];
+        z[4 * q + j] = zv + half_s2 * (g[j] - zv) + nscale * nz[j];
+      }
+      if (history && live)
+        *reinterpret_cast<float4*>(history + ((int64_t)step * rows + r) * L + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int q = 0; q < L / 4; ++q)
+      *reinterpret_cast<float4*>(z_io + r * L + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
   }
 }
 

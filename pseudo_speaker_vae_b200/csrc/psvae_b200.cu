@@ -58,6 +58,7 @@ struct Options {
   int64_t tc_prefetch = 0;             // k-blocks the operand L2 prefetch runs ahead of the smem ring (measured: 0.99 ms off vs 1.19-1.26 ms on -- the mainloop is L2->SM bandwidth-bound, not latency-bound; kept as an experiment knob)
   int64_t tc_two_cta = 0;              // 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2) for BN = 256 shapes
   int64_t tc_zigzag = 0;               // successive GEMM launches walk the batch in alternating directions (L2 reuse of the rows written last)
+  int64_t langevin_generic = 0;        // tests: force the generic (tile-in-smem) Langevin kernel even where the thread-per-sample one applies
   int64_t deterministic = 0;           // 1: split-K / bias partials go through ordered two-stage sums instead of TMA reduce-add / atomics
 };
 static Options g_opt;
@@ -971,6 +972,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "deterministic")) { g_opt.deterministic = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_two_cta")) { g_opt.tc_two_cta = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_zigzag")) { g_opt.tc_zigzag = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "langevin_generic")) { g_opt.langevin_generic = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_prefetch")) { g_opt.tc_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
   set_error("unknown option '%s'", name);
   return -2;
@@ -985,6 +987,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "deterministic")) return g_opt.deterministic;
   if (!strcmp(name, "tc_two_cta")) return g_opt.tc_two_cta;
   if (!strcmp(name, "tc_zigzag")) return g_opt.tc_zigzag;
+  if (!strcmp(name, "langevin_generic")) return g_opt.langevin_generic;
   if (!strcmp(name, "tc_prefetch")) return g_opt.tc_prefetch;
   return -1;
 }
@@ -1181,11 +1184,26 @@ int psvae_langevin(const psvae_model_desc* desc, const float* params, float* z_i
   for (int h = c.n_heads; h < 4; ++h) c.targets[h] = -1;
   if (!any) { set_error("classifier_target selects no head"); return -2; }
   c.w_floats = off;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (stats && num_steps > 0) PSVAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)num_steps, st));
+  // fast path: linear heads on z, one thread per sample (langevin_fast_kernel)
+  int targeted_classes = 0;
+  for (int h = 0; h < c.n_heads; ++h)
+    if (c.targets[h] >= 0) targeted_classes += c.head_classes[h];
+  if (c.n_trunk == 0 && targeted_classes <= CLF_LG_MAXC && (n.L == 16 || n.L == 32 || n.L == 64) && !g_opt.langevin_generic) {
+    const unsigned gridf = (unsigned)ceil_div64(rows, LGF_THREADS);
+    switch (n.L) {
+      case 16: langevin_fast_kernel<16><<<gridf, LGF_THREADS, 0, st>>>(c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
+      case 32: langevin_fast_kernel<32><<<gridf, LGF_THREADS, 0, st>>>(c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
+      default: langevin_fast_kernel<64><<<gridf, LGF_THREADS, 0, st>>>(c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
+    }
+    count_launch();
+    PSVAE_LAUNCH_CHECK("langevin_fast_kernel");
+    return 0;
+  }
   const size_t smem = langevin_smem_bytes(c);
   if (smem > 227 * 1024) { set_error("classifier too large for the Langevin kernel's shared memory (%zu bytes)", smem); return -2; }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   PSVAE_CUDA(cudaFuncSetAttribute(langevin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  if (stats && num_steps > 0) PSVAE_CUDA(cudaMemsetAsync(stats, 0, sizeof(float) * 2 * (size_t)num_steps, st));
   const unsigned grid = (unsigned)ceil_div64(rows, LG_TILE);
   langevin_kernel<<<grid, LG_THREADS, smem, st>>>(c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox,
                                                   noise, history, stats);

@@ -578,3 +578,25 @@ def test_deterministic_option_and_fast_mode_agree():
             assert rel_err(names[k], det[k]) <= 2e-6, k
     finally:
         G.L.set_option("deterministic", 0)
+
+
+def test_langevin_fast_kernel_matches_generic_kernel():
+    """Linear heads on z take the thread-per-sample kernel; it must reproduce the generic tile kernel (same Philox counters)."""
+    G = _gu()
+    import pseudo_speaker_vae_b200 as P
+
+    for name in ("sample_single", "sample_multilabel_1layer"):
+        _, cfg = load(name)
+        module = G.module_from_cfg(cfg, "fp32")
+        hot = module.hot_path
+        outs = []
+        for generic in (1, 0):
+            G.L.set_option("langevin_generic", generic)
+            try:
+                hot.manual_seed(4242, 3)
+                z, hist, stats = hot.langevin(1000, cfg["target"], 0.05, 7, 0.8, return_history=True, return_stats=True)
+            finally:
+                G.L.set_option("langevin_generic", 0)
+            outs.append((z.cpu().numpy(), hist.cpu().numpy(), stats.cpu().numpy()))
+        assert rel_err(outs[1][0], outs[0][0]) <= 2e-6 and rel_err(outs[1][1], outs[0][1]) <= 2e-6, name
+        assert np.abs(outs[1][2] - outs[0][2]).max() <= 1e-4 * max(1.0, np.abs(outs[0][2]).max()), name
