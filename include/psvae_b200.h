@@ -104,9 +104,10 @@ int64_t psvae_shadow_bytes(const psvae_model_desc* desc);
 /* algorithmic FLOPs per sample (2 x MAC): mode 0 = train fwd+bwd, 1 = forward, 2 = decode */
 int64_t psvae_flops_per_sample(const psvae_model_desc* desc, int32_t mode);
 
-/* Tuning knobs (process-wide, set before sizing workspaces): "decode_chunk" rows per decode pass (default 32768,
- * sized so the hidden activations of a pass stay in the 126 MB L2), "wgrad_split_cap", "colsum_rows",
- * and for tests "tc_force_bn" (0|64|128|256), "tc_grid_limit". */
+/* Tuning knobs (process-wide, set before sizing workspaces): "decode_chunk" rows per decode pass (default 131072),
+ * "wgrad_split_cap", "colsum_rows", "deterministic" (1: ordered two-stage sums instead of TMA reduce-add / atomics),
+ * "tc_two_cta" (CTA pairs, tcgen05 cta_group::2; default 1), "tc_prefetch", "tc_zigzag" (experiments, default 0), and for
+ * tests "tc_force_bn" (0|64|128|256), "tc_grid_limit", "langevin_generic".  Env PSVAE_OPT_<NAME>=<int> sets them at load. */
 int psvae_set_option(const char* name, int64_t value);
 int64_t psvae_get_option(const char* name);
 

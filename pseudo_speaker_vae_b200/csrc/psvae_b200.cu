@@ -50,13 +50,13 @@ int cuda_fail(cudaError_t e, const char* what) {
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 struct Options {
-  int64_t decode_chunk = 1 << 15;      // rows per pass of psvae_decode: keeps the hidden activations L2-resident
+  int64_t decode_chunk = 1 << 17;      // rows per pass of psvae_decode (bounds the scratch; measured 347 / 490 / 628 / 696 M samples/s at 16k / 32k / 64k / 128k rows)
   int64_t wgrad_split_cap = 64;        // split-K ceiling of the wgrad GEMMs
   int64_t colsum_rows = 512;           // rows per bias-gradient partial
   int64_t tc_force_bn = 0;             // tests: force the N tile of the tcgen05 engine
   int64_t tc_grid_limit = 0;           // tests: cap the persistent grid
   int64_t tc_prefetch = 0;             // k-blocks the operand L2 prefetch runs ahead of the smem ring (measured: 0.99 ms off vs 1.19-1.26 ms on -- the mainloop is L2->SM bandwidth-bound, not latency-bound; kept as an experiment knob)
-  int64_t tc_two_cta = 0;              // 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2) for BN = 256 shapes
+  int64_t tc_two_cta = 1;              // 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2) for BN = 256 shapes
   int64_t tc_zigzag = 0;               // successive GEMM launches walk the batch in alternating directions (L2 reuse of the rows written last)
   int64_t langevin_generic = 0;        // tests: force the generic (tile-in-smem) Langevin kernel even where the thread-per-sample one applies
   int64_t deterministic = 0;           // 1: split-K / bias partials go through ordered two-stage sums instead of TMA reduce-add / atomics
