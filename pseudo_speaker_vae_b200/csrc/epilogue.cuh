@@ -44,15 +44,25 @@ struct EpiBiasAct {
   TOut* out;
   int64_t ldo;
   float* red_out;      // unused
+  uint32_t* mask;      // tcgen05 engine, optional: bit i of mask[(col/32) * mask_ld + row] = (output[row][col + i] > 0) -- the ReLU
+  int64_t mask_ld;     //   derivative the backward pass needs, 1 bit per element instead of re-reading the bf16 activation
   template <int NV>
   __device__ __forceinline__ void apply(int64_t row, int col, float (&v)[NV], float& red, int split) const {
 #pragma unroll
     for (int i = 0; i < NV; ++i) v[i] = act_fwd<ACT>(v[i] + (bias ? __ldg(bias + col + i) : 0.f));
     store_vec<NV>(out + row * ldo + col, v);
   }
-  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], float& red) const {
+  __device__ __forceinline__ uint32_t tc_pre(int64_t row, int col, bool valid) const { return 0u; }
+  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], uint32_t pre,
+                                               float& red) const {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i] + ((bias && col + i < N) ? __ldg(bias + col + i) : 0.f));
+    if (mask) {
+      uint32_t bits = 0;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+      if (valid) mask[(int64_t)(col >> 5) * mask_ld + row] = bits;      // lanes = consecutive rows: one coalesced 128-byte store per warp
+    }
   }
 };
 
@@ -90,8 +100,10 @@ struct EpiMse {
     }
     if (out) store_vec<NV>(out + row * ldo + col, v);
   }
+  __device__ __forceinline__ uint32_t tc_pre(int64_t row, int col, bool valid) const { return 0u; }
   // aux = the x tile (fp32, fetched by TMA; zero outside the matrix); x_hat (optional) is written straight to global memory
-  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], float& red) const {
+  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], uint32_t pre,
+                                               float& red) const {
     if (valid && col + 32 <= N) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) v[i] += __ldg(bias + col + i);
@@ -124,11 +136,11 @@ template <typename TAct, typename TOut_, int ACT, bool CS = false>
 struct EpiActGrad {
   using TOut = TOut_;
   static constexpr bool kReduce = false, kColSum = CS, kSplit = false;
-  static constexpr int kAuxBytes = sizeof(TAct) == 2 ? 2048 : 4096;   // tcgen05 engine: the forward-activation tile arrives by TMA
-  __host__ const void* aux_ptr() const { return act; }
-  __host__ int64_t aux_ld() const { return lda; }
-  const TAct* act;     // forward activation (post-activation) [M, lda]
+  static constexpr int kAuxBytes = 0;
+  const TAct* act;     // sgemm engine: forward activation (post-activation) [M, lda]
   int64_t lda;
+  const uint32_t* mask;   // tcgen05 engine: the bit mask EpiBiasAct wrote in the forward pass, [N/32][mask_ld]
+  int64_t mask_ld;
   TOut* out;
   int64_t ldo;
   float beta;          // sgemm only: out = acc * act'(.) + beta * out   (sum over classifier heads)
@@ -149,9 +161,15 @@ struct EpiActGrad {
     }
     store_vec<NV>(out + row * ldo + col, v);
   }
-  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], float& red) const {
+  // issued for every block of the tile BEFORE the accumulator is awaited: the (coalesced) mask loads hide behind the MMAs
+  __device__ __forceinline__ uint32_t tc_pre(int64_t row, int col, bool valid) const {
+    return valid ? __ldg(mask + (int64_t)(col >> 5) * mask_ld + row) : 0u;
+  }
+  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], uint32_t pre,
+                                               float& red) const {
+    static_assert(ACT == ACT_RELU, "the bit mask encodes the ReLU derivative");
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= act_grad_from_out<ACT>(aux[i]);
+    for (int i = 0; i < 32; ++i) v[i] = (pre >> i) & 1u ? v[i] : 0.f;
   }
 };
 
@@ -179,7 +197,9 @@ struct EpiStore {
     }
     store_vec<NV>(p, v);
   }
-  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], float& red) const {
+  __device__ __forceinline__ uint32_t tc_pre(int64_t row, int col, bool valid) const { return 0u; }
+  __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], uint32_t pre,
+                                               float& red) const {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] *= alpha;
   }

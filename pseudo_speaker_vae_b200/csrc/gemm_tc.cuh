@@ -333,6 +333,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (ncol < s.N) ptx::tma_prefetch_2d(&tma_aux, ncol, nrow);
         }
       }
+      uint32_t pre[CH];                      // per-block words the functor wants early (EpiActGrad: the ReLU bit masks)
+#pragma unroll
+      for (int c = 0; c < CH; ++c) pre[c] = (col_base + c * 32 < s.N) ? epi.tc_pre(row, col_base + c * 32, valid) : 0u;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase, 4);
       ptx::tc_fence_after();
       const bool zero_acc = kb0 >= kb1;
@@ -379,7 +382,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; ++i) aux[i] = 0.f;
         }
-        epi.tc_transform(row, col, s.N, valid, v, aux, red);
+        epi.tc_transform(row, col, s.N, valid, v, aux, pre[c], red);
         if (do_store) {
           if constexpr (Epi::kColSum) {      // rows past M must not reach the column sums
             if (!valid) {

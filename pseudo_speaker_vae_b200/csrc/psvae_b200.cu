@@ -343,7 +343,9 @@ template <typename TAct> struct StepBufs {
   float* logits[PSVAE_MAX_CLF_HEADS] = {};
   float* clf_g[2] = {};
   float *wpart = nullptr, *cpart = nullptr;
-  float *clf_part = nullptr, *clf_sums = nullptr;     // fused classifier: per-block partials, summed nll/acc
+  float *clf_part = nullptr, *clf_sums = nullptr;
+  uint32_t* mhe[PSVAE_MAX_LAYERS] = {};   // ReLU bit masks of the hidden activations (tcgen05 training): [features/32][rows]
+  uint32_t* mhd[PSVAE_MAX_LAYERS] = {};     // fused classifier: per-block partials, summed nll/acc
   float *sse_part = nullptr, *kl_part = nullptr, *nll_part[PSVAE_MAX_CLF_HEADS] = {}, *acc_part[PSVAE_MAX_CLF_HEADS] = {};
   int64_t n_sse = 0, n_kl = 0, n_ce = 0;
 };
@@ -406,6 +408,12 @@ static void plan(const psvae_model_desc* d, int64_t rows, int mode, Bump& b, Ste
     }
   }
   if (!train) return;
+  if (is_bf16) {
+    for (int j = 0; j < n.nh; ++j) {
+      w.mhe[j] = b.take<uint32_t>((int64_t)(2 * n.H / 32) * rows);
+      w.mhd[j] = b.take<uint32_t>((int64_t)(n.H / 32) * rows);
+    }
+  }
   w.dxh = b.take<TAct>(rows * n.D);
   for (int i = 0; i < 2; ++i) w.gd[i] = b.take<TAct>(rows * n.H);
   w.dz = b.take<float>(rows * n.L);
@@ -489,13 +497,13 @@ static int wgrad(const TAct* dY, int64_t ldy, const TAct* A, int64_t lda, int64_
 // dgrad through a hidden Linear: out[B][in] = (dY[B][out] W[out][in]) .* relu'(act).  In tcgen05 mode the epilogue also emits the
 // column sums of `out` (= bias gradient of the layer below) into `bias_grad`; *bias_done tells the caller whether it did.
 template <typename TAct>
-static int dgrad_hidden(const TAct* dY, int64_t ldy, const TAct* W, int out_dim, int in_dim, const TAct* act, int64_t lda, TAct* out, int64_t ldo,
-                        int64_t rows, float* bias_grad, StepBufs<TAct>& w, bool* bias_done, cudaStream_t st) {
+static int dgrad_hidden(const TAct* dY, int64_t ldy, const TAct* W, int out_dim, int in_dim, const TAct* act, int64_t lda, const uint32_t* mask,
+                        TAct* out, int64_t ldo, int64_t rows, float* bias_grad, StepBufs<TAct>& w, bool* bias_done, cudaStream_t st) {
   *bias_done = false;
   if constexpr (sizeof(TAct) == 2) {
     if (bias_grad && tc_colsum_ok(in_dim)) {
       const bool atomic = !g_opt.deterministic;
-      EpiActGrad<TAct, TAct, ACT_RELU, true> e{act, lda, out, ldo, 0.f, nullptr, atomic ? bias_grad : w.cpart, atomic ? 1 : 0};
+      EpiActGrad<TAct, TAct, ACT_RELU, true> e{act, lda, mask, rows, out, ldo, 0.f, nullptr, atomic ? bias_grad : w.cpart, atomic ? 1 : 0};
       PSVAE_TRY((Engine<TAct>::template gemm<G_DGRAD>(dY, ldy, W, in_dim, rows, in_dim, out_dim, 1, true, e, st)));
       if (!atomic) {
         const int64_t ctas = tc_ctas(rows, in_dim, 1, (int)g_opt.tc_force_bn);
@@ -505,7 +513,7 @@ static int dgrad_hidden(const TAct* dY, int64_t ldy, const TAct* W, int out_dim,
       return 0;
     }
   }
-  EpiActGrad<TAct, TAct, ACT_RELU, false> e{act, lda, out, ldo, 0.f, nullptr, nullptr, 0};
+  EpiActGrad<TAct, TAct, ACT_RELU, false> e{act, lda, mask, rows, out, ldo, 0.f, nullptr, nullptr, 0};
   return Engine<TAct>::template gemm<G_DGRAD>(dY, ldy, W, in_dim, rows, in_dim, out_dim, 1, true, e, st);
 }
 // classifier wgrad: always fp32 on the CUDA cores
@@ -544,7 +552,7 @@ static int clf_linear(int act, const float* a, int64_t lda, const float* W, cons
 // out[B][in] = (dY[B][out] * W[out][in]) .* act'(A[B][in]) + beta * out
 template <int ACT>
 static int clf_dgrad_act(const float* dY, int out_dim, const float* W, int in_dim, const float* A, float* out, float beta, int64_t rows, cudaStream_t st) {
-  EpiActGrad<float, float, ACT> e{A, in_dim, out, in_dim, beta, nullptr, nullptr, 0};
+  EpiActGrad<float, float, ACT> e{A, in_dim, nullptr, 0, out, in_dim, beta, nullptr, nullptr, 0};
   return Engine<float>::gemm<G_DGRAD>(dY, out_dim, W, in_dim, rows, in_dim, out_dim, 1, in_dim % 4 == 0, e, st);
 }
 static int clf_dgrad(int act, const float* dY, int out_dim, const float* W, int in_dim, const float* A, float* out, float beta, int64_t rows, cudaStream_t st) {
@@ -590,10 +598,10 @@ template <> const bf16* weights_of<bf16>(const StepArgs& a) { return a.shadow; }
 // decoder chain z -> pre-normalisation output; the last layer goes through `last_epi`
 template <typename TAct, class LastEpi>
 static int decoder_forward(const Net& n, const TAct* Wt, const float* params, const TAct* z, TAct* const* hd, int64_t rows, const LastEpi& last_epi,
-                           cudaStream_t st) {
+                           cudaStream_t st, uint32_t* const* mhd = nullptr) {
   const TAct* a = z;
   for (int j = 0; j < n.nh; ++j) {
-    EpiBiasAct<TAct, ACT_RELU> e{params + n.d->dec_b[j], hd[j], n.H, nullptr};
+    EpiBiasAct<TAct, ACT_RELU> e{params + n.d->dec_b[j], hd[j], n.H, nullptr, mhd ? mhd[j] : nullptr, rows};
     PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(a, n.dec_in(j), Wt + n.d->dec_w[j], n.dec_in(j), rows, n.H, n.dec_in(j), 1, true, e, st)));
     a = hd[j];
   }
@@ -645,12 +653,13 @@ static int run_step(const StepArgs& a) {
     xa = a.x;
   }
   {
-    EpiBiasAct<TAct, ACT_RELU> e{P + d->enc_b[0], w.he[0], 2 * n.H, nullptr};
+    EpiBiasAct<TAct, ACT_RELU> e{P + d->enc_b[0], w.he[0], 2 * n.H, nullptr, a.want_grads ? w.mhe[0] : nullptr, B};
     PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(xa, n.D, Wt + d->enc_w[0], n.D, B, 2 * n.H, n.D, 1, true, e, st)));
   }
   for (int j = 1; j < n.nh; ++j) {
     for (int s = 0; s < 2; ++s) {      // s = 0: encoder_mu, 1: encoder_sigma
-      EpiBiasAct<TAct, ACT_RELU> e{P + d->enc_b[j] + s * n.H, w.he[j] + s * n.H, 2 * n.H, nullptr};
+      EpiBiasAct<TAct, ACT_RELU> e{P + d->enc_b[j] + s * n.H, w.he[j] + s * n.H, 2 * n.H, nullptr,
+                                   (a.want_grads && w.mhe[j]) ? w.mhe[j] + (int64_t)s * (n.H / 32) * B : nullptr, B};
       PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(w.he[j - 1] + s * n.H, 2 * n.H, Wt + d->enc_w[j] + (int64_t)s * n.H * n.H, n.H, B, n.H, n.H, 1, true, e, st)));
     }
   }
@@ -720,21 +729,21 @@ static int run_step(const StepArgs& a) {
         const bool atomic = !g_opt.deterministic;
         EpiMse<TAct, true> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, w.dxh, n.D, scale, w.sse_part, atomic ? a.grads + d->dec_b[n.nh] : w.cpart,
                              atomic ? 1 : 0};
-        PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
+        PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st, (a.want_grads && w.mhd[0]) ? w.mhd : nullptr));
         launched = dec_last_bias_done = true;
         dec_last_bias_reduce = !atomic;
       }
     }
     if (!launched) {
       EpiMse<TAct> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, a.want_grads ? w.dxh : nullptr, n.D, scale, w.sse_part, nullptr, 0};
-      PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
+      PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st, (a.want_grads && w.mhd[0]) ? w.mhd : nullptr));
     }
     n_sse_used = sizeof(TAct) == 2 ? (int)tc_ctas(B, n.D, 1, (int)g_opt.tc_force_bn) : (int)sgemm_red_slots(B, n.D);   // one slot per CTA / per tile
     if (dec_last_bias_reduce) PSVAE_TRY(launch_reduce(w.cpart, n.D, n_sse_used * 4, a.grads + d->dec_b[n.nh], st));
   } else {
     float* u = general_tail ? w.u : (a.x_hat ? a.x_hat : w.u);
     EpiBiasAct<float, ACT_NONE> e{P + d->dec_b[n.nh], u, n.D, nullptr};
-    PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st));
+    PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st, (a.want_grads && w.mhd[0]) ? w.mhd : nullptr));
     if (general_tail) {
       const float gscale = a.use_cos ? 1.f / (float)B : 2.f / ((float)B * (float)n.D * 10.f);
       const int blocks = (int)ceil_div64(B * 32, 256);
@@ -812,8 +821,8 @@ static int run_step(const StepArgs& a) {
       const int in_dim = n.dec_in(j);
       PSVAE_TRY(wgrad<TAct>(dY, out_dim, ain, in_dim, B, out_dim, in_dim, G + d->dec_w[j], bias_done ? nullptr : G + d->dec_b[j], w, st));
       if (j > 0) {
-        PSVAE_TRY(dgrad_hidden<TAct>(dY, out_dim, Wt + d->dec_w[j], out_dim, in_dim, w.hd[j - 1], n.H, w.gd[pp], n.H, B, G + d->dec_b[j - 1], w,
-                                     &bias_done, st));
+        PSVAE_TRY(dgrad_hidden<TAct>(dY, out_dim, Wt + d->dec_w[j], out_dim, in_dim, w.hd[j - 1], n.H, w.mhd[j - 1], w.gd[pp], n.H, B,
+                                     G + d->dec_b[j - 1], w, &bias_done, st));
         dY = w.gd[pp];
         out_dim = n.H;
         pp ^= 1;
@@ -851,7 +860,8 @@ static int run_step(const StepArgs& a) {
       PSVAE_TRY(wgrad<TAct>(dY, n.L, w.he[n.nh - 1] + s * n.H, 2 * n.H, B, n.L, n.H, G + d->enc_w[n.nh] + (int64_t)s * n.L * n.H,
                             last_bias_done ? nullptr : G + d->enc_b[n.nh] + s * n.L, w, st));
       PSVAE_TRY(dgrad_hidden<TAct>(dY, n.L, Wt + d->enc_w[n.nh] + (int64_t)s * n.L * n.H, n.L, n.H, w.he[n.nh - 1] + s * n.H, 2 * n.H,
-                                   w.ge[pp] + s * n.H, 2 * n.H, B, G + d->enc_b[n.nh - 1] + s * n.H, w, &bias_done[s], st));
+                                   w.mhe[n.nh - 1] ? w.mhe[n.nh - 1] + (int64_t)s * (n.H / 32) * B : nullptr, w.ge[pp] + s * n.H, 2 * n.H, B,
+                                   G + d->enc_b[n.nh - 1] + s * n.H, w, &bias_done[s], st));
     }
     for (int j = n.nh - 1; j >= 1; --j) {
       for (int s = 0; s < 2; ++s) {
@@ -859,7 +869,8 @@ static int run_step(const StepArgs& a) {
         PSVAE_TRY(wgrad<TAct>(dY, 2 * n.H, w.he[j - 1] + s * n.H, 2 * n.H, B, n.H, n.H, G + d->enc_w[j] + (int64_t)s * n.H * n.H,
                               bias_done[s] ? nullptr : G + d->enc_b[j] + s * n.H, w, st));
         PSVAE_TRY(dgrad_hidden<TAct>(dY, 2 * n.H, Wt + d->enc_w[j] + (int64_t)s * n.H * n.H, n.H, n.H, w.he[j - 1] + s * n.H, 2 * n.H,
-                                     w.ge[pp ^ 1] + s * n.H, 2 * n.H, B, G + d->enc_b[j - 1] + s * n.H, w, &bias_done[s], st));
+                                     w.mhe[j - 1] ? w.mhe[j - 1] + (int64_t)s * (n.H / 32) * B : nullptr, w.ge[pp ^ 1] + s * n.H, 2 * n.H, B,
+                                     G + d->enc_b[j - 1] + s * n.H, w, &bias_done[s], st));
       }
       pp ^= 1;
     }
