@@ -1,6 +1,6 @@
 // tcgen05 GEMM engine for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  through a fused epilogue.
 //
-//   * persistent, one CTA per SM, static round-robin tile schedule (m fastest, so a CTA walks the N tiles in order);
+//   * persistent, one CTA per SM, static round-robin tile schedule (n fastest: CTAs sharing a row tile run together);
 //   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one thread issues
 //     tcgen05.mma), warps 2..9 = epilogue;
 //   * operands bf16, staged by TMA (cp.async.bulk.tensor, 128B swizzle) through a STAGES-deep mbarrier
@@ -139,6 +139,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int64_t kb_total = (s.K + TC_BK - 1) / TC_BK;
   const int64_t kb_per_split = (kb_total + s.splits - 1) / s.splits;
   const int64_t num_tiles = m_tiles * n_tiles * s.splits;
+  // tile order: n fastest -- the CTAs that share an A (row) tile run at the same time, so its second..n-th reads hit L2 instead of HBM;
+  // with gridDim.x a multiple of n_tiles every CTA keeps one n_t for all of its tiles
+  auto tile_m = [&](int64_t t) { const int64_t m = (t / n_tiles) % m_tiles; return s.reverse ? m_tiles - 1 - m : m; };
+  auto tile_n = [&](int64_t t) { return t % n_tiles; };
 
   float red = 0.f;
 
@@ -196,7 +200,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (p_live) p_range();
         }
         if (!p_live) return;
-        if (ptx::elect_one()) fetch(s.reverse ? m_tiles - 1 - p_tile % m_tiles : p_tile % m_tiles, (p_tile / m_tiles) % n_tiles, p_kb, nullptr, nullptr);
+        if (ptx::elect_one()) fetch(tile_m(p_tile), tile_n(p_tile), p_kb, nullptr, nullptr);
         __syncwarp();
         ++p_kb;
       };
@@ -207,7 +211,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t tile = work_id; tile < num_tiles; tile += work_stride) {
-        const int64_t m_t = s.reverse ? m_tiles - 1 - tile % m_tiles : tile % m_tiles, n_t = (tile / m_tiles) % n_tiles,
+        const int64_t m_t = tile_m(tile), n_t = tile_n(tile),
                       sp = s.reverse ? s.splits - 1 - tile / (n_tiles * m_tiles) : tile / (n_tiles * m_tiles);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         for (int64_t kb = kb0; kb < kb1; ++kb) {
@@ -296,8 +300,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 atomicAdd(epi.colsum + col, cs_acc[c][0]);
                 atomicAdd(epi.colsum + col + 1, cs_acc[c][1]);
               } else {                          // deterministic mode: one partial row per (CTA, row quarter)
-                float* p = epi.colsum + ((int64_t)blockIdx.x * 4 + quarter) * s.N + col;
-                *reinterpret_cast<float2*>(p) = make_float2(cs_acc[c][0], cs_acc[c][1]);
+                // the slot is private to this warp and zeroed before the launch; += because a CTA can come back to an N tile
+                float2* p = reinterpret_cast<float2*>(epi.colsum + ((int64_t)blockIdx.x * 4 + quarter) * s.N + col);
+                float2 o = *p;
+                o.x += cs_acc[c][0]; o.y += cs_acc[c][1];
+                *p = o;
               }
             }
           }
@@ -308,7 +315,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     };
     int64_t it = 0;
     for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
-      const int64_t m_t = s.reverse ? m_tiles - 1 - tile % m_tiles : tile % m_tiles, n_t = (tile / m_tiles) % n_tiles,
+      const int64_t m_t = tile_m(tile), n_t = tile_n(tile),
                       sp = s.reverse ? s.splits - 1 - tile / (n_tiles * m_tiles) : tile / (n_tiles * m_tiles);
       const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
       const int acc = (int)(it & 1);
@@ -328,8 +335,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         // and pull this warp's auxiliary blocks of the CTA's NEXT tile into L2 (they stream from HBM otherwise)
         const int64_t nxt = tile + work_stride;
         if (s.pf_dist > 0 && nxt < num_tiles && lane < CH) {
-          const int32_t nrow = (int32_t)((s.reverse ? m_tiles - 1 - nxt % m_tiles : nxt % m_tiles) * TM) + (int32_t)cta_rank * TC_BM + quarter * 32;
-          const int ncol = (int)(((nxt / m_tiles) % n_tiles) * BN) + half * COLS_PER_WARP + lane * 32;
+          const int32_t nrow = (int32_t)(tile_m(nxt) * TM) + (int32_t)cta_rank * TC_BM + quarter * 32;
+          const int ncol = (int)(tile_n(nxt) * BN) + half * COLS_PER_WARP + lane * 32;
           if (ncol < s.N) ptx::tma_prefetch_2d(&tma_aux, ncol, nrow);
         }
       }
