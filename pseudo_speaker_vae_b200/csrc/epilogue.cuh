@@ -55,8 +55,15 @@ struct EpiBiasAct {
   __device__ __forceinline__ uint32_t tc_pre(int64_t row, int col, bool valid) const { return 0u; }
   __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], uint32_t pre,
                                                float& red) const {
+    if (bias && col + 32 <= N) {            // 8 x 16-byte broadcast loads instead of 32 scalar ones
+      float bv[32];
+      load_vec<32>(bias + col, bv);
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i] + ((bias && col + i < N) ? __ldg(bias + col + i) : 0.f));
+      for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i] + bv[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i] + ((bias && col + i < N) ? __ldg(bias + col + i) : 0.f));
+    }
     if (mask) {
       uint32_t bits = 0;
 #pragma unroll
@@ -105,8 +112,10 @@ struct EpiMse {
   __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], uint32_t pre,
                                                float& red) const {
     if (valid && col + 32 <= N) {
+      float bv[32];
+      load_vec<32>(bias + col, bv);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += __ldg(bias + col + i);
+      for (int i = 0; i < 32; ++i) v[i] += bv[i];
       if (x_hat) store_vec<32>(x_hat + row * ldxh + col, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {

@@ -45,7 +45,8 @@ template <int BN, class Epi, int CG = 1> struct TcCfg {
   static constexpr int kBBytes = (BN / CG) * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBytes = 32 * 32 * (int)sizeof(typename Epi::TOut);
-  static constexpr int kEpiWarpBytes = kOutBytes + Epi::kAuxBytes;
+  static constexpr int kOutBufs = (kOutBytes + Epi::kAuxBytes <= 2048) ? 2 : 1;   // bf16 block without an aux block: double-buffer the staging
+  static constexpr int kEpiWarpBytes = kOutBufs * kOutBytes + Epi::kAuxBytes;
   static constexpr int kEpiBytes = TC_EPI_WARPS * kEpiWarpBytes;
   static constexpr int kMaxStages = CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kFit = (TC_SMEM_MAX - 1024 - TC_BAR_BYTES - kEpiBytes) / kStageBytes;
@@ -281,8 +282,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     const int half = ew >> 2;                // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
     constexpr int CH = COLS_PER_WARP / 32;   // 32-column blocks per tile for this warp
-    uint8_t* obuf = smem + Cfg::kEpiOff + ew * Cfg::kEpiWarpBytes;    // staged output block
-    uint8_t* abuf = obuf + Cfg::kOutBytes;                             // staged auxiliary block
+    uint8_t* const obuf0 = smem + Cfg::kEpiOff + ew * Cfg::kEpiWarpBytes;   // staged output block(s)
+    uint8_t* abuf = obuf0 + Cfg::kOutBufs * Cfg::kOutBytes;                  // staged auxiliary block
+    uint32_t ochunk = 0;                                                     // blocks stored so far (selects the staging buffer)
     uint32_t aux_phase = 0;
     const bool do_store = epi.out != nullptr;
     float cs_acc[CH][2];                     // kColSum: this lane's two columns of every block of the current N tile
@@ -397,8 +399,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               for (int i = 0; i < 32; ++i) v[i] = 0.f;
             }
           }
-          // the previous TMA store of this warp must have finished reading the staging block
-          if (lane == 0) ptx::bulk_wait_read0();
+          // the TMA store that last used this staging block must have finished reading it
+          uint8_t* const obuf = obuf0 + (Cfg::kOutBufs == 2 ? (ochunk & 1u) * Cfg::kOutBytes : 0);
+          ++ochunk;
+          if (lane == 0) {
+            if constexpr (Cfg::kOutBufs == 2) ptx::bulk_wait_read1();
+            else ptx::bulk_wait_read0();
+          }
           __syncwarp();
           if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
