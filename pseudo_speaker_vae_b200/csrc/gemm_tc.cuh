@@ -44,8 +44,12 @@ template <int BN, class Epi, int CG = 1> struct TcCfg {
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = (BN / CG) * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutBytes = 32 * 32 * (int)sizeof(typename Epi::TOut);
-  static constexpr int kOutBufs = (kOutBytes + Epi::kAuxBytes <= 2048) ? 2 : 1;   // bf16 block without an aux block: double-buffer the staging
+  // staged output block of one epilogue warp: 32 rows x 128 bytes (fp32: 32 columns; bf16: 64 columns = two tcgen05.ld chunks per
+  // fence / TMA store) -- except BN = 64 with bf16 output, where a warp owns only 32 columns (32 rows x 64 bytes)
+  static constexpr bool kWide = sizeof(typename Epi::TOut) == 2 && BN >= 128;
+  static constexpr int kBlockCols = kWide ? 64 : 32;
+  static constexpr int kOutBytes = 32 * kBlockCols * (int)sizeof(typename Epi::TOut);
+  static constexpr int kOutBufs = 1;
   static constexpr int kEpiWarpBytes = kOutBufs * kOutBytes + Epi::kAuxBytes;
   static constexpr int kEpiBytes = TC_EPI_WARPS * kEpiWarpBytes;
   static constexpr int kMaxStages = CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
@@ -82,7 +86,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   using TOut = typename Epi::TOut;
   constexpr int STAGES = Cfg::kStages;
   constexpr int TM = TC_BM * CG;                           // rows of one (cluster) tile
-  constexpr int ROWB = 32 * (int)sizeof(TOut);            // bytes per staged row: 64 (bf16) or 128 (fp32)
+  constexpr bool WIDE = Cfg::kWide;
+  constexpr int ROWB = Cfg::kBlockCols * (int)sizeof(TOut);   // bytes per staged row: 128, or 64 (bf16 at BN = 64)
   constexpr bool kAux = Epi::kAuxBytes > 0;
   static_assert(Epi::kAuxBytes == 0 || Epi::kAuxBytes == 2048 || Epi::kAuxBytes == 4096, "aux block: 32x32 bf16 or fp32");
   static_assert(!(Epi::kColSum && sizeof(TOut) != 2), "column sums are read back from a bf16 block");
@@ -284,7 +289,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     constexpr int CH = COLS_PER_WARP / 32;   // 32-column blocks per tile for this warp
     uint8_t* const obuf0 = smem + Cfg::kEpiOff + ew * Cfg::kEpiWarpBytes;   // staged output block(s)
     uint8_t* abuf = obuf0 + Cfg::kOutBufs * Cfg::kOutBytes;                  // staged auxiliary block
-    uint32_t ochunk = 0;                                                     // blocks stored so far (selects the staging buffer)
     uint32_t aux_phase = 0;
     const bool do_store = epi.out != nullptr;
     float cs_acc[CH][2];                     // kColSum: this lane's two columns of every block of the current N tile
@@ -293,10 +297,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int64_t cs_nt = -1;
     auto cs_flush = [&]() {
       if constexpr (Epi::kColSum) {
-        if (cs_nt >= 0 && lane < 16) {
+        if (cs_nt >= 0 && (WIDE || lane < 16)) {
 #pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const int col = (int)(cs_nt * BN) + half * COLS_PER_WARP + c * 32 + 2 * lane;
+          for (int c = 0; c < (WIDE ? CH / 2 : CH); ++c) {
+            const int col = (int)(cs_nt * BN) + half * COLS_PER_WARP + c * Cfg::kBlockCols + 2 * lane;
             if (col + 1 < s.N) {
               if (epi.colsum_atomic) {          // fast mode: straight into the (zeroed) bias gradient
                 atomicAdd(epi.colsum + col, cs_acc[c][0]);
@@ -399,14 +403,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               for (int i = 0; i < 32; ++i) v[i] = 0.f;
             }
           }
-          // the TMA store that last used this staging block must have finished reading it
-          uint8_t* const obuf = obuf0 + (Cfg::kOutBufs == 2 ? (ochunk & 1u) * Cfg::kOutBytes : 0);
-          ++ochunk;
-          if (lane == 0) {
-            if constexpr (Cfg::kOutBufs == 2) ptx::bulk_wait_read1();
-            else ptx::bulk_wait_read0();
+          // WIDE (bf16, BN >= 128): two consecutive 32-column chunks share one 32 x 128-byte block, one fence and one TMA store
+          uint8_t* const obuf = obuf0;
+          const int part = WIDE ? (c & 1) : 0;
+          const bool opens = !WIDE || part == 0;
+          const bool closes = !WIDE || part == 1 || col + 32 >= s.N || c + 1 == CH;
+          if (opens) {          // the TMA store that last used this staging block must have finished reading it
+            if (lane == 0) ptx::bulk_wait_read0();
+            __syncwarp();
           }
-          __syncwarp();
           if constexpr (sizeof(TOut) == 2) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -415,39 +420,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               u.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
               u.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
               u.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
-              *reinterpret_cast<uint4*>(obuf + swz_off<64>(lane, j)) = u;
+              if constexpr (WIDE) *reinterpret_cast<uint4*>(obuf + swz_off<128>(lane, part * 4 + j)) = u;
+              else *reinterpret_cast<uint4*>(obuf + swz_off<64>(lane, j)) = u;
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(obuf + swz_off<128>(lane, j)) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
           }
-          ptx::fence_proxy_async_smem();     // generic-proxy writes -> visible to the TMA (async proxy)
-          __syncwarp();
-          if constexpr (Epi::kColSum) {
-            // lanes 0-15 walk the even rows, 16-31 the odd rows; lane (l & 15) owns columns 2w, 2w+1 of the block
-            const int hw = lane >> 4, w = lane & 15;
-            float s0 = 0.f, s1 = 0.f;
+          if (closes) {
+            ptx::fence_proxy_async_smem();     // generic-proxy writes -> visible to the TMA (async proxy)
+            __syncwarp();
+            if constexpr (Epi::kColSum) {
+              float s0 = 0.f, s1 = 0.f;
+              if constexpr (WIDE) {
+                // lane l owns columns 2l, 2l+1 of the 64-column block (a half-filled block adds stale-but-unused columns: see flush guard)
+                const bool have = part == 1 || lane < 16;
 #pragma unroll
-            for (int rr = 0; rr < 16; ++rr) {
-              const int r = 2 * rr + hw;
-              const uint32_t u = *reinterpret_cast<const uint32_t*>(obuf + swz_off<64>(r, w >> 2) + (w & 3) * 4);
-              s0 += __uint_as_float(u << 16);
-              s1 += __uint_as_float(u & 0xFFFF0000u);
+                for (int r = 0; r < 32; ++r) {
+                  const uint32_t u = *reinterpret_cast<const uint32_t*>(obuf + swz_off<128>(r, lane >> 2) + (lane & 3) * 4);
+                  s0 += __uint_as_float(u << 16);
+                  s1 += __uint_as_float(u & 0xFFFF0000u);
+                }
+                if (have) { cs_acc[c >> 1][0] += s0; cs_acc[c >> 1][1] += s1; }
+              } else {
+                // lanes 0-15 walk the even rows, 16-31 the odd rows; lane (l & 15) owns columns 2w, 2w+1 of the block
+                const int hw = lane >> 4, w = lane & 15;
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr) {
+                  const int r = 2 * rr + hw;
+                  const uint32_t u = *reinterpret_cast<const uint32_t*>(obuf + swz_off<64>(r, w >> 2) + (w & 3) * 4);
+                  s0 += __uint_as_float(u << 16);
+                  s1 += __uint_as_float(u & 0xFFFF0000u);
+                }
+                s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+                s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+                cs_acc[c][0] += s0;
+                cs_acc[c][1] += s1;
+              }
             }
-            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-            cs_acc[c][0] += s0;
-            cs_acc[c][1] += s1;
-          }
-          if (lane == 0) {
-            if constexpr (Epi::kSplit) {
-              if (epi.reduce_add) ptx::tma_reduce_add_2d(&tma_out, obuf, col, row_base);
-              else ptx::tma_store_3d(&tma_out, obuf, col, row_base, (int32_t)sp);
-            } else {
-              ptx::tma_store_2d(&tma_out, obuf, col, row_base);
+            if (lane == 0) {
+              const int bcol = WIDE ? col - part * 32 : col;
+              if constexpr (Epi::kSplit) {
+                if (epi.reduce_add) ptx::tma_reduce_add_2d(&tma_out, obuf, bcol, row_base);
+                else ptx::tma_store_3d(&tma_out, obuf, bcol, row_base, (int32_t)sp);
+              } else {
+                ptx::tma_store_2d(&tma_out, obuf, bcol, row_base);
+              }
+              ptx::bulk_commit();
             }
-            ptx::bulk_commit();
           }
         }
       }
@@ -497,7 +518,8 @@ struct TcOperand {
 // Encodes (and caches by value) the 2D tensor map of one operand.  Returns 0, or < 0 with the error text set.
 int tc_tensor_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out);
 // Tensor map of an epilogue block: [32 rows][32 cols] of a row-major [rows][cols] (x splits) matrix of 2- or 4-byte elements.
-int tc_block_map(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int64_t splits, int64_t split_stride, CUtensorMap* out);
+int tc_block_map(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int64_t splits, int64_t split_stride, CUtensorMap* out,
+                 int box_cols = 32);
 int tc_grid_size();       // number of SMs of the current device (persistent grid)
 int tc_prefetch_distance();   // option "tc_prefetch": k-blocks of L2 prefetch lead
 int tc_device_check();    // 0 when the current device is sm_100
@@ -564,7 +586,8 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   s.reverse = tc_next_direction();
   if (epi.out) {
     const bool split_slots = Epi::kSplit && !epi_split_stride<Epi>::reduce(epi);
-    PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, N, epi.ldo, split_slots ? s.splits : 0, epi_split_stride<Epi>::get(epi), &tout));
+    PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, N, epi.ldo, split_slots ? s.splits : 0, epi_split_stride<Epi>::get(epi), &tout,
+                           Cfg::kBlockCols));
   } else {
     tout = ta;   // never dereferenced: the kernel skips the store
   }

@@ -442,7 +442,9 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
   }
   float nll[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
   float accW[2] = {0.f, 0.f}, accb = 0.f;
-  const int n_out = a.total_classes * L;                // dW elements; thread t owns t and t + 256
+  const int n_out = a.total_classes * L;                // dW elements; thread t owns t and t + 256 ...
+  const int n_parts = (n_out <= CLF_TILE / 2) ? CLF_TILE / n_out : 1;   // ... or, when there are few, (element, row range) pairs
+  const int rows_per_part = CLF_TILE / n_parts;         // n_parts in {2,4,..}: CLF_TILE / n_out rounded down; leftover threads idle
   const int64_t tiles = (B + CLF_TILE - 1) / CLF_TILE;
   const int qpr = L >> 2;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -466,10 +468,12 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
 #pragma unroll
         for (int c = 0; c < CLF_MAXC; ++c) logit[c] = b_s[c];
         const float* m = mu_s + t * ldm;
+        const int nc = a.total_classes;
         for (int k = 0; k < L; ++k) {
           const float mv = m[k];
 #pragma unroll
-          for (int c = 0; c < CLF_MAXC; ++c) logit[c] = fmaf(mv, W_s[c * L + k], logit[c]);
+          for (int c = 0; c < CLF_MAXC; ++c)
+            if (c < nc) logit[c] = fmaf(mv, W_s[c * L + k], logit[c]);
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -513,14 +517,25 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
           }
         }
       }
-#pragma unroll
-      for (int j = 0; j < 2; ++j) {
-        const int o = t + j * CLF_TILE;
-        if (o < n_out) {
-          const int c = o / L, k = o % L;
+      if (n_parts > 1) {
+        // few classes: every thread owns one dW element and one of n_parts row ranges of the tile (summed in a fixed order at the end)
+        const int o = t % n_out, part = t / n_out;
+        if (part < n_parts) {
+          const int c = o / L, k = o % L, r0 = part * rows_per_part;
           float v = 0.f;
-          for (int r = 0; r < CLF_TILE; ++r) v = fmaf(g_s[r * CLF_MAXC + c], mu_s[r * ldm + k], v);
-          accW[j] += v;
+          for (int r = r0; r < r0 + rows_per_part; ++r) v = fmaf(g_s[r * CLF_MAXC + c], mu_s[r * ldm + k], v);
+          accW[0] += v;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int o = t + j * CLF_TILE;
+          if (o < n_out) {
+            const int c = o / L, k = o % L;
+            float v = 0.f;
+            for (int r = 0; r < CLF_TILE; ++r) v = fmaf(g_s[r * CLF_MAXC + c], mu_s[r * ldm + k], v);
+            accW[j] += v;
+          }
         }
       }
       if (t < a.total_classes) {
@@ -537,9 +552,21 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
     if (t == 0) { mine[h] = s1; mine[4 + h] = s2; }
   }
   for (int o = t; o < CLF_MAXC * L; o += CLF_TILE) mine[8 + o] = 0.f;
-  for (int j = 0; j < 2; ++j) {
-    const int o = t + j * CLF_TILE;
-    if (o < n_out) mine[8 + o] = accW[j];      // same thread wrote the zero above: program order
+  if (n_parts > 1) {
+    __syncthreads();                           // the tile buffers are free now: reuse g_s to combine the row-range partials
+    float* comb = clf_smem;                    // [n_parts][n_out] <= 256 floats
+    if (t < n_parts * n_out) comb[(t / n_out) * n_out + t % n_out] = accW[0];
+    __syncthreads();
+    if (t < n_out) {
+      float v = 0.f;
+      for (int p = 0; p < n_parts; ++p) v += comb[p * n_out + t];
+      mine[8 + t] = v;
+    }
+  } else {
+    for (int j = 0; j < 2; ++j) {
+      const int o = t + j * CLF_TILE;
+      if (o < n_out) mine[8 + o] = accW[j];    // same thread wrote the zero above: program order
+    }
   }
   if (t < CLF_MAXC) mine[8 + CLF_MAXC * L + t] = (t < a.total_classes) ? accb : 0.f;
 }

@@ -173,10 +173,11 @@ int tc_tensor_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out
   return 0;
 }
 
-typedef std::tuple<const void*, int, int64_t, int64_t, int64_t, int64_t, int64_t> BmKey;
+typedef std::tuple<const void*, int, int64_t, int64_t, int64_t, int64_t, int64_t, int> BmKey;
 static std::map<BmKey, CUtensorMap> g_bm_cache;
 
-int tc_block_map(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int64_t splits, int64_t split_stride, CUtensorMap* out) {
+int tc_block_map(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int64_t splits, int64_t split_stride, CUtensorMap* out,
+                 int box_cols) {
   std::lock_guard<std::mutex> lk(g_tm_mu);
   if (!g_encode) {
     void* fn = nullptr;
@@ -185,7 +186,7 @@ int tc_block_map(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, in
     if (!fn || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available from this driver"); return -3; }
     g_encode = (PFN_cuTensorMapEncodeTiled)fn;
   }
-  const BmKey key(ptr, elem_bytes, rows, cols, ld, splits, split_stride);
+  const BmKey key(ptr, elem_bytes, rows, cols, ld, splits, split_stride, box_cols);
   auto it = g_bm_cache.find(key);
   if (it != g_bm_cache.end()) { *out = it->second; return 0; }
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (ld * elem_bytes) % 16 != 0) {
@@ -195,11 +196,11 @@ int tc_block_map(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, in
   cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)rows, (cuuint64_t)(splits > 0 ? splits : 1)};
   if (split_stride <= 0) split_stride = rows * ld;
   cuuint64_t gstride[2] = {(cuuint64_t)ld * elem_bytes, (cuuint64_t)split_stride * elem_bytes};
-  cuuint32_t box[3] = {32, 32, 1}, estr[3] = {1, 1, 1};
+  cuuint32_t box[3] = {(cuuint32_t)box_cols, 32, 1}, estr[3] = {1, 1, 1};
   const int rank = splits > 0 ? 3 : 2;
   alignas(64) CUtensorMap tm;
   CUresult r = g_encode(&tm, elem_bytes == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, rank, const_cast<void*>(ptr), gdim,
-                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, elem_bytes == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols * elem_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (epilogue block) failed (%d): ptr=%p elem=%d dims=[%llu,%llu,%llu] strides=[%llu,%llu]", (int)r, ptr, elem_bytes,
