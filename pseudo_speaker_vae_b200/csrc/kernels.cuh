@@ -450,12 +450,22 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * CLF_TILE;
     __syncthreads();                                    // previous pass is done with the tile buffers (and W_s is loaded)
-    for (int i = t; i < CLF_TILE * qpr; i += CLF_TILE) {
-      const int r = i / qpr, q = i % qpr;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (row0 + r < B) v = *reinterpret_cast<const float4*>(mu + (row0 + r) * L + 4 * q);
-      float* d = mu_s + r * ldm + 4 * q;
-      d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    for (int base = 0; base < CLF_TILE * qpr; base += 8 * CLF_TILE) {     // 8 independent 16-byte loads in flight per thread
+      float4 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = base + j * CLF_TILE + t;
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (i < CLF_TILE * qpr && row0 + i / qpr < B) v[j] = __ldg(reinterpret_cast<const float4*>(mu + (row0 + i / qpr) * L + 4 * (i % qpr)));
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int i = base + j * CLF_TILE + t;
+        if (i < CLF_TILE * qpr) {
+          float* d = mu_s + (i / qpr) * ldm + 4 * (i % qpr);
+          d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
+        }
+      }
     }
     __syncthreads();
     {   // phase 2: one row per thread

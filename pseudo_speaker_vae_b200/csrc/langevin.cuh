@@ -249,7 +249,7 @@ namespace psvae {
 constexpr int LGF_THREADS = 128;
 
 template <int L>
-__global__ void __launch_bounds__(LGF_THREADS, 4) langevin_fast_kernel(LangevinClf c, const float* __restrict__ params, float* __restrict__ z_io, int64_t rows,
+__global__ void __launch_bounds__(LGF_THREADS) langevin_fast_kernel(LangevinClf c, const float* __restrict__ params, float* __restrict__ z_io, int64_t rows,
                                                                     float step_size, int num_steps, float noise_weight, uint64_t seed, uint64_t offset0,
                                                                     int64_t row0, int init_from_philox, const float* __restrict__ noise,
                                                                     float* __restrict__ history, float* __restrict__ stats) {
