@@ -340,7 +340,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         // and pull this warp's auxiliary blocks of the CTA's NEXT tile into L2 (they stream from HBM otherwise)
         const int64_t nxt = tile + work_stride;
-        if (s.pf_dist > 0 && nxt < num_tiles && lane < CH) {
+        if (nxt < num_tiles && lane < CH) {
           const int32_t nrow = (int32_t)(tile_m(nxt) * TM) + (int32_t)cta_rank * TC_BM + quarter * 32;
           const int ncol = (int)(tile_n(nxt) * BN) + half * COLS_PER_WARP + lane * 32;
           if (ncol < s.N) ptx::tma_prefetch_2d(&tma_aux, ncol, nrow);
