@@ -417,22 +417,27 @@ struct ClfFusedArgs {
 __host__ __device__ __forceinline__ int clf_part_len(int L) { return 8 + CLF_MAXC * L + CLF_MAXC; }   // nll[4] acc[4] dW[8][L] db[8]
 
 constexpr int CLF_TILE = 256;   // rows per block pass (= threads per block)
-static inline size_t clf_fused_smem_bytes(int L) { return ((size_t)CLF_TILE * (L + 1) + (size_t)CLF_TILE * CLF_MAXC + (size_t)CLF_MAXC * L + CLF_MAXC) * sizeof(float); }
+static inline size_t clf_fused_smem_bytes(int L) { return ((size_t)CLF_TILE * (L + 4) + (size_t)CLF_TILE * CLF_MAXC + (size_t)CLF_MAXC * L + CLF_MAXC) * sizeof(float); }
 
 // A block stages a tile of 256 rows of mu in shared memory (read once from HBM, coalesced); then
 //   phase 2: thread = row: logits, log-softmax, NLL / accuracy, dlogits -> smem;
 //   phase 3: dmu_clf[row][k] = sum_c dlogits[row][c] W[c][k] written coalesced; thread = (class, latent dim): dW[c][k] += sum_rows dlogits[row][c] mu[row][k].
+// L is a template parameter (16/32/64/128) so that the row/column index arithmetic is shifts and everything moves as float4; class
+// loops run over the classes that exist (2..3 per head), not over the CLF_MAXC slots.
+template <int L>
 __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __restrict__ params, const float* __restrict__ mu, const int64_t* __restrict__ y,
-                                                             int64_t B, int L, ClfFusedArgs a, float* __restrict__ dmu_clf, float* __restrict__ part) {
-  extern __shared__ float clf_smem[];
+                                                             int64_t B, ClfFusedArgs a, float* __restrict__ dmu_clf, float* __restrict__ part) {
+  extern __shared__ __align__(16) float clf_smem[];
   __shared__ float scratch[32];
-  const int ldm = L + 1;
-  float* mu_s = clf_smem;                               // [256][L+1]
+  constexpr int ldm = L + 4;                            // 16-byte aligned rows; row-per-lane float4 reads are conflict-free per quarter warp
+  constexpr int QPR = L / 4;
+  float* mu_s = clf_smem;                               // [256][L+4]
   float* g_s = mu_s + CLF_TILE * ldm;                   // [256][8]
   float* W_s = g_s + CLF_TILE * CLF_MAXC;               // [8][L]
   float* b_s = W_s + CLF_MAXC * L;                      // [8]
   const int t = threadIdx.x;
   const int PART = clf_part_len(L);
+  const int nc = a.total_classes;
   for (int i = t; i < CLF_MAXC * L; i += CLF_TILE) W_s[i] = 0.f;
   if (t < CLF_MAXC) b_s[t] = 0.f;
   __syncthreads();
@@ -442,29 +447,26 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
   }
   float nll[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
   float accW[2] = {0.f, 0.f}, accb = 0.f;
-  const int n_out = a.total_classes * L;                // dW elements; thread t owns t and t + 256 ...
+  const int n_out = nc * L;                             // dW elements; thread t owns t and t + 256 ...
   const int n_parts = (n_out <= CLF_TILE / 2) ? CLF_TILE / n_out : 1;   // ... or, when there are few, (element, row range) pairs
-  const int rows_per_part = CLF_TILE / n_parts;         // n_parts in {2,4,..}: CLF_TILE / n_out rounded down; leftover threads idle
+  const int rows_per_part = CLF_TILE / n_parts;
   const int64_t tiles = (B + CLF_TILE - 1) / CLF_TILE;
-  const int qpr = L >> 2;
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * CLF_TILE;
     __syncthreads();                                    // previous pass is done with the tile buffers (and W_s is loaded)
-    for (int base = 0; base < CLF_TILE * qpr; base += 8 * CLF_TILE) {     // 8 independent 16-byte loads in flight per thread
+#pragma unroll
+    for (int base = 0; base < CLF_TILE * QPR; base += 8 * CLF_TILE) {     // 8 independent 16-byte loads in flight per thread
       float4 v[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int i = base + j * CLF_TILE + t;
         v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < CLF_TILE * qpr && row0 + i / qpr < B) v[j] = __ldg(reinterpret_cast<const float4*>(mu + (row0 + i / qpr) * L + 4 * (i % qpr)));
+        if (i < CLF_TILE * QPR && row0 + i / QPR < B) v[j] = __ldg(reinterpret_cast<const float4*>(mu + (row0 + i / QPR) * L + 4 * (i % QPR)));
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int i = base + j * CLF_TILE + t;
-        if (i < CLF_TILE * qpr) {
-          float* d = mu_s + (i / qpr) * ldm + 4 * (i % qpr);
-          d[0] = v[j].x; d[1] = v[j].y; d[2] = v[j].z; d[3] = v[j].w;
-        }
+        if (i < CLF_TILE * QPR) *reinterpret_cast<float4*>(mu_s + (i / QPR) * ldm + 4 * (i % QPR)) = v[j];
       }
     }
     __syncthreads();
@@ -478,12 +480,16 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
 #pragma unroll
         for (int c = 0; c < CLF_MAXC; ++c) logit[c] = b_s[c];
         const float* m = mu_s + t * ldm;
-        const int nc = a.total_classes;
-        for (int k = 0; k < L; ++k) {
-          const float mv = m[k];
+#pragma unroll 4
+        for (int k = 0; k < L; k += 4) {
+          const float4 mv = *reinterpret_cast<const float4*>(m + k);
 #pragma unroll
           for (int c = 0; c < CLF_MAXC; ++c)
-            if (c < nc) logit[c] = fmaf(mv, W_s[c * L + k], logit[c]);
+            if (c < nc) {
+              const float4 w = *reinterpret_cast<const float4*>(W_s + c * L + k);
+              logit[c] = fmaf(mv.x, w.x, logit[c]); logit[c] = fmaf(mv.y, w.y, logit[c]);
+              logit[c] = fmaf(mv.z, w.z, logit[c]); logit[c] = fmaf(mv.w, w.w, logit[c]);
+            }
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -511,28 +517,34 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
           }
         }
       }
-#pragma unroll
-      for (int c = 0; c < CLF_MAXC; ++c) g_s[t * CLF_MAXC + c] = g[c];
+      *reinterpret_cast<float4*>(g_s + t * CLF_MAXC) = make_float4(g[0], g[1], g[2], g[3]);
+      *reinterpret_cast<float4*>(g_s + t * CLF_MAXC + 4) = make_float4(g[4], g[5], g[6], g[7]);
     }
     __syncthreads();
     if (a.write_grad) {
       if (dmu_clf) {
-        for (int i = t; i < CLF_TILE * L; i += CLF_TILE) {
-          const int r = i / L, k = i % L;
+        for (int i = t; i < CLF_TILE * QPR; i += CLF_TILE) {      // thread = (row, 4 latent dims): one 16-byte coalesced store
+          const int r = i / QPR, k = 4 * (i % QPR);
           if (row0 + r < B) {
-            float v = 0.f;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int c = 0; c < CLF_MAXC; ++c) v = fmaf(g_s[r * CLF_MAXC + c], W_s[c * L + k], v);
-            dmu_clf[(row0 + r) * L + k] = v;
+            for (int c = 0; c < CLF_MAXC; ++c)
+              if (c < nc) {
+                const float gc = g_s[r * CLF_MAXC + c];
+                const float4 w = *reinterpret_cast<const float4*>(W_s + c * L + k);
+                v.x = fmaf(gc, w.x, v.x); v.y = fmaf(gc, w.y, v.y); v.z = fmaf(gc, w.z, v.z); v.w = fmaf(gc, w.w, v.w);
+              }
+            *reinterpret_cast<float4*>(dmu_clf + (row0 + r) * L + k) = v;
           }
         }
       }
       if (n_parts > 1) {
         // few classes: every thread owns one dW element and one of n_parts row ranges of the tile (summed in a fixed order at the end)
-        const int o = t % n_out, part = t / n_out;
-        if (part < n_parts) {
-          const int c = o / L, k = o % L, r0 = part * rows_per_part;
+        const int o = t % n_out, part_i = t / n_out;
+        if (part_i < n_parts) {
+          const int c = o / L, k = o % L, r0 = part_i * rows_per_part;
           float v = 0.f;
+#pragma unroll 4
           for (int r = r0; r < r0 + rows_per_part; ++r) v = fmaf(g_s[r * CLF_MAXC + c], mu_s[r * ldm + k], v);
           accW[0] += v;
         }
@@ -543,12 +555,13 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
           if (o < n_out) {
             const int c = o / L, k = o % L;
             float v = 0.f;
+#pragma unroll 4
             for (int r = 0; r < CLF_TILE; ++r) v = fmaf(g_s[r * CLF_MAXC + c], mu_s[r * ldm + k], v);
             accW[j] += v;
           }
         }
       }
-      if (t < a.total_classes) {
+      if (t < nc) {
         float v = 0.f;
         for (int r = 0; r < CLF_TILE; ++r) v += g_s[r * CLF_MAXC + t];
         accb += v;
@@ -563,7 +576,7 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
   }
   for (int o = t; o < CLF_MAXC * L; o += CLF_TILE) mine[8 + o] = 0.f;
   if (n_parts > 1) {
-    __syncthreads();                           // the tile buffers are free now: reuse g_s to combine the row-range partials
+    __syncthreads();                           // the tile buffers are free now: reuse them to combine the row-range partials
     float* comb = clf_smem;                    // [n_parts][n_out] <= 256 floats
     if (t < n_parts * n_out) comb[(t / n_out) * n_out + t % n_out] = accW[0];
     __syncthreads();
@@ -578,7 +591,7 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
       if (o < n_out) mine[8 + o] = accW[j];    // same thread wrote the zero above: program order
     }
   }
-  if (t < CLF_MAXC) mine[8 + CLF_MAXC * L + t] = (t < a.total_classes) ? accb : 0.f;
+  if (t < CLF_MAXC) mine[8 + CLF_MAXC * L + t] = (t < nc) ? accb : 0.f;
 }
 
 // sum the per-block partials in block order (32 row lanes, fixed-order tree) and scatter: nll/acc sums -> sums[8], dW/db -> the flat gradient buffer

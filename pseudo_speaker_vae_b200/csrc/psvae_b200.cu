@@ -354,7 +354,7 @@ template <typename TAct> struct StepBufs {
 // the fused classifier kernel covers the common shape: heads directly on mu (no trunk), L = 32/64/96/128, <= 8 classes in total
 static bool clf_fused_ok(const psvae_model_desc* d) {
   if (d->clf_num_heads <= 0 || d->clf_num_trunk != 0) return false;
-  if (d->latent_dim % 4 != 0 || d->latent_dim > 128) return false;      // dW: 8 classes x L <= 2 outputs per thread of a 256-thread block
+  if (d->latent_dim != 16 && d->latent_dim != 32 && d->latent_dim != 64 && d->latent_dim != 128) return false;   // kernel instantiations
   int total = 0;
   for (int h = 0; h < d->clf_num_heads; ++h) total += d->clf_head_classes[h];
   return total <= CLF_MAXC && total * d->latent_dim <= 2 * CLF_TILE;
@@ -694,8 +694,24 @@ static int run_step(const StepArgs& a) {
     const int blocks = clf_fused_blocks(B);
     const size_t smem = clf_fused_smem_bytes(n.L);
     float* dmu_out = a.want_grads ? w.dmu_clf : nullptr;
-    PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    clf_fused_kernel<<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, n.L, ca, dmu_out, w.clf_part);
+    switch (n.L) {
+      case 16:
+        PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        clf_fused_kernel<16><<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part);
+        break;
+      case 32:
+        PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        clf_fused_kernel<32><<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part);
+        break;
+      case 64:
+        PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        clf_fused_kernel<64><<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part);
+        break;
+      default:
+        PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        clf_fused_kernel<128><<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part);
+        break;
+    }
     count_launch();
     PSVAE_LAUNCH_CHECK("clf_fused_kernel");
     clf_fused_finish_kernel<<<(unsigned)ceil_div64(clf_part_len(n.L), 32), 1024, 0, st>>>(w.clf_part, blocks, n.L, ca, w.clf_sums,
