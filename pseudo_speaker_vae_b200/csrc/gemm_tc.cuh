@@ -147,8 +147,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int64_t num_tiles = m_tiles * n_tiles * s.splits;
   // tile order: n fastest -- the CTAs that share an A (row) tile run at the same time, so its second..n-th reads hit L2 instead of HBM;
   // with gridDim.x a multiple of n_tiles every CTA keeps one n_t for all of its tiles
-  auto tile_m = [&](int64_t t) { const int64_t m = (t / n_tiles) % m_tiles; return s.reverse ? m_tiles - 1 - m : m; };
-  auto tile_n = [&](int64_t t) { return t % n_tiles; };
+  // (32-bit arithmetic: a 64-bit division here cost 7 % of the epilogue warps' issue slots)
+  const uint32_t m_tiles32 = (uint32_t)m_tiles, n_tiles32 = (uint32_t)n_tiles;
+  auto tile_m = [&](int64_t t) { const uint32_t m = ((uint32_t)t / n_tiles32) % m_tiles32; return (int64_t)(s.reverse ? m_tiles32 - 1 - m : m); };
+  auto tile_n = [&](int64_t t) { return (int64_t)((uint32_t)t % n_tiles32); };
+  auto tile_sp = [&](int64_t t) { const uint32_t sp = (uint32_t)t / (n_tiles32 * m_tiles32); return (int64_t)(s.reverse ? (uint32_t)s.splits - 1 - sp : sp); };
 
   float red = 0.f;
 
@@ -195,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       int64_t p_tile = work_id, p_kb = 0, p_kb1 = 0;
       bool p_live = s.pf_dist > 0 && p_tile < num_tiles;
       auto p_range = [&]() {
-        const int64_t sp = s.reverse ? s.splits - 1 - p_tile / (n_tiles * m_tiles) : p_tile / (n_tiles * m_tiles);
+        const int64_t sp = tile_sp(p_tile);
         p_kb = sp * kb_per_split;
         p_kb1 = min(kb_total, p_kb + kb_per_split);
       };
@@ -218,7 +221,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       uint32_t phase = 0;
       for (int64_t tile = work_id; tile < num_tiles; tile += work_stride) {
         const int64_t m_t = tile_m(tile), n_t = tile_n(tile),
-                      sp = s.reverse ? s.splits - 1 - tile / (n_tiles * m_tiles) : tile / (n_tiles * m_tiles);
+                      sp = tile_sp(tile);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         for (int64_t kb = kb0; kb < kb1; ++kb) {
           if (s.pf_dist > 0) p_step();
@@ -246,7 +249,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       uint32_t phase = 0;
       int64_t it = 0;
       for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
-        const int64_t sp = s.reverse ? s.splits - 1 - tile / (n_tiles * m_tiles) : tile / (n_tiles * m_tiles);
+        const int64_t sp = tile_sp(tile);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         const int acc = (int)(it & 1);
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
@@ -322,7 +325,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     int64_t it = 0;
     for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
       const int64_t m_t = tile_m(tile), n_t = tile_n(tile),
-                      sp = s.reverse ? s.splits - 1 - tile / (n_tiles * m_tiles) : tile / (n_tiles * m_tiles);
+                      sp = tile_sp(tile);
       const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
       const int acc = (int)(it & 1);
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
