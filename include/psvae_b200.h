@@ -166,6 +166,12 @@ int psvae_langevin(const psvae_model_desc* desc, const float* params, float* z_i
 int psvae_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, float* c, int64_t m, int32_t n,
                     int64_t k, int32_t a_mn, int32_t b_mn, int32_t relu, int32_t split_k, void* workspace,
                     int64_t workspace_bytes, void* stream);
+/* profiling probe: the two hot epilogue forms of the train step on free-standing operands.
+ * form 0: out = relu(A[m,k] W[n,k]^T + bias) in bf16 (+ 1-bit ReLU mask [n/32][m] when mask != NULL);
+ * form 1: out = (A[m,k] W[k,n]) .* mask in bf16 (+ column sums accumulated into colsum[n] when != NULL).
+ * out == NULL skips the store. */
+int psvae_gemm_probe(const void* a_bf16, const void* w_bf16, const float* bias, void* out_bf16, uint32_t* mask,
+                     float* colsum, int64_t m, int32_t n, int64_t k, int32_t form, void* stream);
 /* same contract on the CUDA cores in fp32 (the parity engine) */
 int psvae_gemm_fp32(const float* a, const float* b, const float* bias, float* c, int64_t m, int32_t n, int64_t k,
                     int32_t a_mn, int32_t b_mn, int32_t relu, void* stream);

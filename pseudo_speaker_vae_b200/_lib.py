@@ -27,7 +27,7 @@ EXPORTS = [
     "psvae_abi_version", "psvae_last_error_string", "psvae_model_desc_init", "psvae_workspace_bytes", "psvae_shadow_bytes",
     "psvae_flops_per_sample", "psvae_set_option", "psvae_get_option", "psvae_adam_step", "psvae_philox_uint32", "psvae_philox_normal",
     "psvae_refresh_shadow", "psvae_forward", "psvae_decode", "psvae_train_fwd_bwd", "psvae_langevin", "psvae_gemm_bf16",
-    "psvae_gemm_fp32", "psvae_launch_count",
+    "psvae_gemm_fp32", "psvae_gemm_probe", "psvae_launch_count",
 ]
 
 
@@ -88,6 +88,8 @@ def _declare(l: C.CDLL) -> None:
     l.psvae_langevin.argtypes = [D, VP, VP, I64, P(I32), F, I32, F, U64, U64, I64, I32, VP, VP, VP, VP]
     l.psvae_gemm_bf16.restype = C.c_int
     l.psvae_gemm_bf16.argtypes = [VP, VP, VP, VP, I64, I32, I64, I32, I32, I32, I32, VP, I64, VP]
+    l.psvae_gemm_probe.restype = C.c_int
+    l.psvae_gemm_probe.argtypes = [VP, VP, VP, VP, VP, VP, I64, I32, I64, I32, VP]
     l.psvae_gemm_fp32.restype = C.c_int
     l.psvae_gemm_fp32.argtypes = [VP, VP, VP, VP, I64, I32, I64, I32, I32, I32, VP]
 

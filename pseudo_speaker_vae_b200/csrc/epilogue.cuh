@@ -39,6 +39,7 @@ template <typename TOut_, int ACT>
 struct EpiBiasAct {
   using TOut = TOut_;
   static constexpr bool kReduce = false, kColSum = false, kSplit = false;
+  static constexpr bool kBias = true, kReluPack = (ACT == ACT_RELU) && sizeof(TOut_) == 2;
   static constexpr int kAuxBytes = 0;
   const float* bias;   // [N] or nullptr
   TOut* out;
@@ -53,22 +54,36 @@ struct EpiBiasAct {
     store_vec<NV>(out + row * ldo + col, v);
   }
   __device__ __forceinline__ uint32_t tc_pre(int64_t row, int col, bool valid) const { return 0u; }
+  // The engine has already added the bias (kBias: it loads the block's 32 bias values while the TMEM read is in flight).
+  // kReluPack (bf16 output + ReLU): v leaves as the PRE-activation; the engine's cvt.rn.relu.bf16x2 clamps while it packs, and the mask
+  // comes from sign bits gathered with funnel shifts (one ALU op per element instead of FMNMX + FSETP + SEL + IADD3).
   __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], uint32_t pre,
                                                float& red) const {
-    if (bias && col + 32 <= N) {            // 8 x 16-byte broadcast loads instead of 32 scalar ones
-      float bv[32];
-      load_vec<32>(bias + col, bv);
+    if constexpr (kReluPack) {
+      if (mask) {
+        uint32_t w[4];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i] + bv[i]);
+        for (int k = 0; k < 4; ++k) {
+          uint32_t b = 0;
+#pragma unroll
+          for (int i = 7; i >= 0; --i) {
+            const float ns = 0.f - v[8 * k + i];                     // sign bit set  <=>  v > 0  (exact, also for +-0)
+            b = __funnelshift_l(__float_as_uint(ns), b, 1);
+          }
+          w[k] = b;
+        }
+        const uint32_t bits = w[0] | (w[1] << 8) | (w[2] << 16) | (w[3] << 24);
+        if (valid) mask[(int64_t)(col >> 5) * mask_ld + row] = bits;      // lanes = consecutive rows: one coalesced 128-byte store per warp
+      }
     } else {
 #pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i] + ((bias && col + i < N) ? __ldg(bias + col + i) : 0.f));
-    }
-    if (mask) {
-      uint32_t bits = 0;
+      for (int i = 0; i < 32; ++i) v[i] = act_fwd<ACT>(v[i]);
+      if (ACT == ACT_RELU && mask) {
+        uint32_t bits = 0;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
-      if (valid) mask[(int64_t)(col >> 5) * mask_ld + row] = bits;      // lanes = consecutive rows: one coalesced 128-byte store per warp
+        for (int i = 0; i < 32; ++i) bits |= (v[i] > 0.f ? 1u : 0u) << i;
+        if (valid) mask[(int64_t)(col >> 5) * mask_ld + row] = bits;
+      }
     }
   }
 };
@@ -78,6 +93,7 @@ template <typename TOut_, bool CS = false>
 struct EpiMse {
   using TOut = TOut_;
   static constexpr bool kReduce = true, kColSum = CS, kSplit = false;
+  static constexpr bool kBias = true, kReluPack = false;
   static constexpr int kAuxBytes = 4096;      // tcgen05 engine: the fp32 target tile x[32 rows][32 cols] arrives by TMA
   __host__ const void* aux_ptr() const { return x; }
   __host__ int64_t aux_ld() const { return ldx; }
@@ -112,10 +128,6 @@ struct EpiMse {
   __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], uint32_t pre,
                                                float& red) const {
     if (valid && col + 32 <= N) {
-      float bv[32];
-      load_vec<32>(bias + col, bv);
-#pragma unroll
-      for (int i = 0; i < 32; ++i) v[i] += bv[i];
       if (x_hat) store_vec<32>(x_hat + row * ldxh + col, v);
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -128,7 +140,7 @@ struct EpiMse {
       for (int i = 0; i < 32; ++i) {
         float o = 0.f;
         if (valid && col + i < N) {
-          const float h = v[i] + __ldg(bias + col + i);
+          const float h = v[i];
           if (x_hat) x_hat[row * ldxh + col + i] = h;
           const float d = h - aux[i];
           red = fmaf(d, d, red);
@@ -145,6 +157,7 @@ template <typename TAct, typename TOut_, int ACT, bool CS = false>
 struct EpiActGrad {
   using TOut = TOut_;
   static constexpr bool kReduce = false, kColSum = CS, kSplit = false;
+  static constexpr bool kBias = false, kReluPack = false;
   static constexpr int kAuxBytes = 0;
   const TAct* act;     // sgemm engine: forward activation (post-activation) [M, lda]
   int64_t lda;
@@ -185,6 +198,7 @@ struct EpiActGrad {
 struct EpiStore {
   using TOut = float;
   static constexpr bool kReduce = false, kColSum = false, kSplit = true;
+  static constexpr bool kBias = false, kReluPack = false;
   static constexpr int kAuxBytes = 0;
   float* out;
   int64_t ldo;

@@ -31,8 +31,10 @@
 namespace psvae {
 
 constexpr int TC_BM = 128, TC_BK = 64, TC_UMMA_K = 16;
-constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 32 * (2 + TC_EPI_WARPS);
+// epilogue warps: 4 TMEM lane quarters x (BN / kColsPerWarp) column groups.  BN = 256 runs 16 of them (4 per SM sub-partition): with 8 the
+// epilogue was latency-bound (2 warps per scheduler, ~8 cycles per instruction) and set the tile time of every K <= 512 GEMM.
+constexpr int tc_epi_warps(int bn) { return bn == 256 ? 16 : 8; }
+constexpr int TC_MAX_EPI_WARPS = 16;
 constexpr int TC_BAR_BYTES = 512;
 constexpr int TC_SMEM_MAX = 227 * 1024;
 
@@ -41,6 +43,9 @@ constexpr int TC_SMEM_MAX = 227 * 1024;
 // CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on one 256 x BN tile: each CTA stages its own 128 rows of A and its
 // half of the B tile (BN/2 rows), so the operand bytes per SM and per FLOP drop by a third and the ring gets 6 stages instead of 4.
 template <int BN, class Epi, int CG = 1> struct TcCfg {
+  static constexpr int kEpiWarps = tc_epi_warps(BN);
+  static constexpr int kThreads = 32 * (2 + kEpiWarps);
+  static constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = (BN / CG) * TC_BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -51,7 +56,7 @@ template <int BN, class Epi, int CG = 1> struct TcCfg {
   static constexpr int kOutBytes = 32 * kBlockCols * (int)sizeof(typename Epi::TOut);
   static constexpr int kOutBufs = 1;
   static constexpr int kEpiWarpBytes = kOutBufs * kOutBytes + Epi::kAuxBytes;
-  static constexpr int kEpiBytes = TC_EPI_WARPS * kEpiWarpBytes;
+  static constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
   static constexpr int kMaxStages = CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kFit = (TC_SMEM_MAX - 1024 - TC_BAR_BYTES - kEpiBytes) / kStageBytes;
   static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
@@ -69,6 +74,7 @@ struct TcShape {
   int32_t splits;   // split-K factor (>= 1)
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // UMMA smem-descriptor strides (bytes)
   int32_t pf_dist;  // k-blocks the L2 prefetch cursor leads the load cursor by (0 = off)
+  int32_t stages;   // depth of the operand ring actually used (<= the compiled kStages; option "tc_max_stages")
   int32_t reverse;  // walk the M tiles (and the split-K ranges) from the end: the rows the previous kernel wrote last are still in L2
 };
 
@@ -79,12 +85,13 @@ template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
 }
 
 template <int BN, bool A_MN, bool B_MN, class Epi, int CG>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
                const __grid_constant__ CUtensorMap tma_aux, TcShape s, Epi epi) {
   using Cfg = TcCfg<BN, Epi, CG>;
   using TOut = typename Epi::TOut;
   constexpr int STAGES = Cfg::kStages;
+  constexpr int EPI_WARPS = Cfg::kEpiWarps;
   constexpr int TM = TC_BM * CG;                           // rows of one (cluster) tile
   constexpr bool WIDE = Cfg::kWide;
   constexpr int ROWB = Cfg::kBlockCols * (int)sizeof(TOut);   // bytes per staged row: 128, or 64 (bf16 at BN = 64)
@@ -99,8 +106,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* empty_bar = bars + STAGES;       // [STAGES]  MMA -> TMA
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
-  uint64_t* aux_bar = bars + 2 * STAGES + 4;     // [TC_EPI_WARPS] aux tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + TC_EPI_WARPS);
+  uint64_t* aux_bar = bars + 2 * STAGES + 4;     // [EPI_WARPS] aux tile landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + EPI_WARPS);
   float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -120,9 +127,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], TC_EPI_WARPS * CG);      // CG = 2: the peer's epilogue warps arrive remotely on the leader's barrier
+      ptx::mbar_init(&tempty_bar[i], EPI_WARPS * CG);      // CG = 2: the peer's epilogue warps arrive remotely on the leader's barrier
     }
-    for (int i = 0; i < TC_EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
+    for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -231,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             fetch(m_t, n_t, kb, smem + stage * Cfg::kStageBytes, &full_bar[stage]);
           }
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == s.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -274,7 +281,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             else ptx::umma_commit(&empty_bar[stage]);
           }
           __syncwarp();
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == s.stages) { stage = 0; phase ^= 1; }
         }
         if (ptx::elect_one()) {                   // accumulator complete (also for an empty K range: the epilogue then sees zeros)
           if constexpr (CG == 2) ptx::umma_commit_cg2_mc(&tfull_bar[acc], (uint16_t)3);
@@ -285,10 +292,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
   } else {
     // ============================ epilogue ================================
-    const int ew = warp - 2;                 // 0..7
+    const int ew = warp - 2;                 // 0..EPI_WARPS-1
     const int quarter = warp & 3;            // TMEM lane quarter this warp may touch (warp id % 4)
-    const int half = ew >> 2;                // which half of the BN columns
-    constexpr int COLS_PER_WARP = BN / 2;
+    const int half = ew >> 2;                // which column group of the BN columns
+    constexpr int COLS_PER_WARP = Cfg::kColsPerWarp;
     constexpr int CH = COLS_PER_WARP / 32;   // 32-column blocks per tile for this warp
     uint8_t* const obuf0 = smem + Cfg::kEpiOff + ew * Cfg::kEpiWarpBytes;   // staged output block(s)
     uint8_t* abuf = obuf0 + Cfg::kOutBufs * Cfg::kOutBytes;                  // staged auxiliary block
@@ -360,12 +367,24 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int col_in_tile = half * COLS_PER_WARP + c * 32;
         const int col = col_base + c * 32;
         if (col >= s.N) continue;            // warp-uniform
-        float v[32];
+        uint32_t acc_r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_in_tile);
-        ptx::tmem_ld_32x32(taddr, v);
-        if (zero_acc) {
+        ptx::tmem_ld_32x32_issue(taddr, acc_r);
+        float bv[32];                        // the block's bias values: loaded while the TMEM read is in flight
+        if constexpr (Epi::kBias) {
+          if (epi.bias && col + 32 <= s.N) {
+            load_vec<32>(epi.bias + col, bv);
+          } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = 0.f;
+            for (int i = 0; i < 32; ++i) bv[i] = (epi.bias && col + i < s.N) ? __ldg(epi.bias + col + i) : 0.f;
+          }
+        }
+        ptx::tmem_ld_wait(acc_r);
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          v[i] = zero_acc ? 0.f : __uint_as_float(acc_r[i]);
+          if constexpr (Epi::kBias) v[i] += bv[i];
         }
         float aux[32];
         if constexpr (kAux) {
@@ -394,9 +413,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             ptx::mbar_arrive_expect_tx(&aux_bar[ew], Epi::kAuxBytes);
             ptx::tma_load_2d(abuf, &tma_aux, &aux_bar[ew], col + 32, row_base);
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) aux[i] = 0.f;
         }
         epi.tc_transform(row, col, s.N, valid, v, aux, pre[c], red);
         if (do_store) {
@@ -419,10 +435,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint4 u;
-              u.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
-              u.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
-              u.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
-              u.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+              if constexpr (Epi::kReluPack) {          // the functor left the pre-activation: clamp while packing
+                u.x = ptx::pack_bf16x2_relu(v[j * 8 + 0], v[j * 8 + 1]);
+                u.y = ptx::pack_bf16x2_relu(v[j * 8 + 2], v[j * 8 + 3]);
+                u.z = ptx::pack_bf16x2_relu(v[j * 8 + 4], v[j * 8 + 5]);
+                u.w = ptx::pack_bf16x2_relu(v[j * 8 + 6], v[j * 8 + 7]);
+              } else {
+                u.x = pack_bf16x2(v[j * 8 + 0], v[j * 8 + 1]);
+                u.y = pack_bf16x2(v[j * 8 + 2], v[j * 8 + 3]);
+                u.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
+                u.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
+              }
               if constexpr (WIDE) *reinterpret_cast<uint4*>(obuf + swz_off<128>(lane, part * 4 + j)) = u;
               else *reinterpret_cast<uint4*>(obuf + swz_off<64>(lane, j)) = u;
             }
@@ -496,7 +519,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     __syncthreads();
     if (threadIdx.x == 0) {
       float t = 0.f;
-      for (int w = 0; w < TC_THREADS / 32; ++w) t += red_smem[w];
+      for (int w = 0; w < Cfg::kThreads / 32; ++w) t += red_smem[w];
       epi.red_out[blockIdx.x] = t;
     }
   }
@@ -542,6 +565,7 @@ static inline int tc_pick_bn(int N) {
 // CTAs a launch uses (= rows / 4 of the kColSum partial buffer, = slots of a kReduce epilogue)
 int tc_next_direction();  // option "tc_zigzag": successive GEMM launches alternate the direction in which they walk the batch
 int tc_two_cta();         // option "tc_two_cta": use CTA pairs (cta_group::2) where the shape allows
+int tc_max_stages();      // option "tc_max_stages": cap of the operand ring depth (0 = none)
 // does this shape run as CTA pairs?  (BN = 256 tiles and more than one 128-row block of M)
 static inline bool tc_use_pair(int64_t M, int N, int force_bn = 0) {
   const int bn = force_bn ? force_bn : tc_pick_bn(N);
@@ -586,6 +610,8 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   tc_desc_strides(A_MN, &s.a_lbo, &s.a_sbo);
   tc_desc_strides(B_MN, &s.b_lbo, &s.b_sbo);
   s.pf_dist = tc_prefetch_distance();
+  s.stages = Cfg::kStages;
+  if (tc_max_stages() >= 2 && tc_max_stages() < s.stages) s.stages = tc_max_stages();
   s.reverse = tc_next_direction();
   if (epi.out) {
     const bool split_slots = Epi::kSplit && !epi_split_stride<Epi>::reduce(epi);
@@ -620,7 +646,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
-    cfg.blockDim = dim3(TC_THREADS);
+    cfg.blockDim = dim3(Cfg::kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -630,7 +656,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
     cfg.numAttrs = 1;
     PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, s, epi));
   } else {
-    kern<<<grid, TC_THREADS, Cfg::kSmemBytes, st>>>(ta, tb, tout, taux, s, epi);
+    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, tout, taux, s, epi);
   }
   count_launch();
   PSVAE_LAUNCH_CHECK("gemm_tc_kernel");

@@ -59,6 +59,7 @@ struct Options {
   int64_t tc_two_cta = 1;              // 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2) for BN = 256 shapes
   int64_t tc_zigzag = 0;               // successive GEMM launches walk the batch in alternating directions (L2 reuse of the rows written last)
   int64_t langevin_generic = 0;        // tests: force the generic (tile-in-smem) Langevin kernel even where the thread-per-sample one applies
+  int64_t tc_max_stages = 0;           // experiments: cap the depth of the operand ring (0 = what fits)
   int64_t deterministic = 0;           // 1: split-K / bias partials go through ordered two-stage sums instead of TMA reduce-add / atomics
 };
 static Options g_opt;
@@ -101,6 +102,7 @@ int tc_device_check() {
 }
 int tc_prefetch_distance() { return (int)g_opt.tc_prefetch; }
 int tc_two_cta() { return (int)g_opt.tc_two_cta; }
+int tc_max_stages() { return (int)g_opt.tc_max_stages; }
 static thread_local unsigned g_dir = 0;
 int tc_next_direction() { return g_opt.tc_zigzag ? (int)(g_dir++ & 1u) : 0; }
 int tc_grid_size() {
@@ -1002,6 +1004,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_zigzag")) { g_opt.tc_zigzag = value ? 1 : 0; return 0; }
   if (!strcmp(name, "langevin_generic")) { g_opt.langevin_generic = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_prefetch")) { g_opt.tc_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
+  if (!strcmp(name, "tc_max_stages")) { g_opt.tc_max_stages = value < 0 ? 0 : value; return 0; }
   set_error("unknown option '%s'", name);
   return -2;
 }
@@ -1017,6 +1020,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_zigzag")) return g_opt.tc_zigzag;
   if (!strcmp(name, "langevin_generic")) return g_opt.langevin_generic;
   if (!strcmp(name, "tc_prefetch")) return g_opt.tc_prefetch;
+  if (!strcmp(name, "tc_max_stages")) return g_opt.tc_max_stages;
   return -1;
 }
 
@@ -1286,6 +1290,41 @@ int psvae_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, f
   }
   EpiBiasAct<float, ACT_NONE> e{bias, c, n, nullptr};
   return gemm_tc_launch<false, false>(oa, ob, m, n, k, 1, e, st, fbn);
+}
+
+// Profiling probe: the two hot epilogue forms of the train step on free-standing operands.
+//   form 0: out = relu(A W^T + bias) in bf16 (+ ReLU bit mask when mask != NULL)          (forward Linear, model.py:14-36)
+//   form 1: out = (A W) .* mask in bf16 (+ column sums into colsum when colsum != NULL)   (dgrad through a hidden Linear)
+// out == NULL skips the store (mainloop + TMEM read only).
+int psvae_gemm_probe(const void* a_bf16, const void* w_bf16, const float* bias, void* out_bf16, uint32_t* mask, float* colsum, int64_t m, int32_t n,
+                     int64_t k, int32_t form, void* stream) {
+  PSVAE_TRY(tc_device_check());
+  if (!a_bf16 || !w_bf16) { set_error("a, w must not be NULL"); return -1; }
+  if (m <= 0 || n <= 0 || k <= 0) { set_error("m, n, k must be positive"); return -2; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const bf16* A = static_cast<const bf16*>(a_bf16);
+  const bf16* W = static_cast<const bf16*>(w_bf16);
+  bf16* out = static_cast<bf16*>(out_bf16);
+  const int fbn = (int)g_opt.tc_force_bn;
+  if (form == 0) {
+    TcOperand oa{A, m, k, false};
+    TcOperand ob{W, (int64_t)n, k, false};          // W [n][k]
+    EpiBiasAct<bf16, ACT_RELU> e{bias, out, n, nullptr, mask, m};
+    return gemm_tc_launch<false, false>(oa, ob, m, n, k, 1, e, st, fbn);
+  }
+  if (form == 1) {
+    if (!mask) { set_error("form 1 needs a mask"); return -1; }
+    TcOperand oa{A, m, k, false};
+    TcOperand ob{W, (int64_t)n, (int64_t)n, true};  // W [k][n] as stored (out = k, in = n)
+    if (colsum) {
+      EpiActGrad<bf16, bf16, ACT_RELU, true> e{nullptr, 0, mask, m, out, n, 0.f, nullptr, colsum, 1};
+      return gemm_tc_launch<false, true>(oa, ob, m, n, k, 1, e, st, fbn);
+    }
+    EpiActGrad<bf16, bf16, ACT_RELU, false> e{nullptr, 0, mask, m, out, n, 0.f, nullptr, nullptr, 0};
+    return gemm_tc_launch<false, true>(oa, ob, m, n, k, 1, e, st, fbn);
+  }
+  set_error("unknown probe form %d", form);
+  return -2;
 }
 
 int psvae_gemm_fp32(const float* a, const float* b, const float* bias, float* c, int64_t m, int32_t n, int64_t k, int32_t a_mn, int32_t b_mn,
