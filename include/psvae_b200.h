@@ -169,7 +169,8 @@ int psvae_gemm_bf16(const void* a_bf16, const void* b_bf16, const float* bias, f
 /* profiling probe: the two hot epilogue forms of the train step on free-standing operands.
  * form 0: out = relu(A[m,k] W[n,k]^T + bias) in bf16 (+ 1-bit ReLU mask [n/32][m] when mask != NULL);
  * form 1: out = (A[m,k] W[k,n]) .* mask in bf16 (+ column sums accumulated into colsum[n] when != NULL).
- * out == NULL skips the store. */
+ * form 2: wgrad, out[n][k] (fp32) += A[m,n]^T W[m,k] (contraction over the m batch rows, split-K with TMA reduce-add).
+ * out == NULL skips the store (forms 0, 1). */
 int psvae_gemm_probe(const void* a_bf16, const void* w_bf16, const float* bias, void* out_bf16, uint32_t* mask,
                      float* colsum, int64_t m, int32_t n, int64_t k, int32_t form, void* stream);
 /* same contract on the CUDA cores in fp32 (the parity engine) */

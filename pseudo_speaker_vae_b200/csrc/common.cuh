@@ -31,6 +31,32 @@ int cuda_fail(cudaError_t e, const char* what);
     if (_r != 0) return _r;                                                  \
   } while (0)
 
+// Programmatic dependent launch (PDL): every kernel of the step is launched with programmaticStreamSerialization, so its CTAs may be
+// scheduled (and run their prologue) while the previous kernel drains; PSVAE_GRID_DEP() at the top of a kernel lets ITS successor do the
+// same and then waits until the predecessor has completed and its writes are visible.  No-ops when the kernel was launched normally.
+#define PSVAE_GRID_DEP()                                                   \
+  do {                                                                     \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");        \
+    asm volatile("griddepcontrol.wait;" ::: "memory");                     \
+  } while (0)
+
+// launch with the PDL attribute (option "pdl", default on) -- kernels launched this way MUST start with PSVAE_GRID_DEP()
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_dep(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t align_up64(int64_t a, int64_t b) { return ceil_div64(a, b) * b; }
 

@@ -35,36 +35,51 @@ constexpr int TC_BM = 128, TC_BK = 64, TC_UMMA_K = 16;
 // epilogue was latency-bound (2 warps per scheduler, ~8 cycles per instruction) and set the tile time of every K <= 512 GEMM.
 constexpr int tc_epi_warps(int bn) { return bn == 256 ? 16 : 8; }
 constexpr int TC_MAX_EPI_WARPS = 16;
-constexpr int TC_BAR_BYTES = 512;
+constexpr int TC_BAR_BYTES = 1024;
 constexpr int TC_SMEM_MAX = 227 * 1024;
+constexpr int TC_MAX_STAGES = 12;          // barrier slots of the operand ring
 
 // Shared-memory plan of one instantiation.  Per epilogue warp: the staged output block (32 rows x 32 cols of TOut: 2 KB bf16 / 4 KB fp32)
 // followed by the auxiliary block (Epi::kAuxBytes: 2 KB bf16 activation tile, 4 KB fp32 target tile); the operand ring gets the rest.
 // CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on one 256 x BN tile: each CTA stages its own 128 rows of A and its
 // half of the B tile (BN/2 rows), so the operand bytes per SM and per FLOP drop by a third and the ring gets 6 stages instead of 4.
-template <int BN, class Epi, int CG = 1> struct TcCfg {
+// BRES ("B resident"): the whole [BN/CG x K] weight block of the CTA's N tile is loaded ONCE into shared memory and stays there for all of
+// the CTA's row tiles (every CTA keeps one N tile: the grid is a multiple of the number of N tiles); only the activation tile streams
+// through the ring.  Per 256 x 256 x 512 tile this takes the weight re-read (256 KB per tile and pair) out of the L2 -> SM traffic, which
+// is what bounds these GEMMs.  The staged output block shrinks to 32 columns to make room.
+template <int BN, class Epi, int CG = 1, bool BRES = false> struct TcCfg {
   static constexpr int kEpiWarps = tc_epi_warps(BN);
   static constexpr int kThreads = 32 * (2 + kEpiWarps);
   static constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = (BN / CG) * TC_BK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes = BRES ? kABytes : kABytes + kBBytes;
   // staged output block of one epilogue warp: 32 rows x 128 bytes (fp32: 32 columns; bf16: 64 columns = two tcgen05.ld chunks per
   // fence / TMA store) -- except BN = 64 with bf16 output, where a warp owns only 32 columns (32 rows x 64 bytes)
-  static constexpr bool kWide = sizeof(typename Epi::TOut) == 2 && BN >= 128;
+  static constexpr bool kWide = sizeof(typename Epi::TOut) == 2 && BN >= 128 && !BRES;
   static constexpr int kBlockCols = kWide ? 64 : 32;
   static constexpr int kOutBytes = 32 * kBlockCols * (int)sizeof(typename Epi::TOut);
   static constexpr int kOutBufs = 1;
   static constexpr int kEpiWarpBytes = kOutBufs * kOutBytes + Epi::kAuxBytes;
   static constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
-  static constexpr int kMaxStages = CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
-  static constexpr int kFit = (TC_SMEM_MAX - 1024 - TC_BAR_BYTES - kEpiBytes) / kStageBytes;
-  static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
-  static_assert(kStages >= 2, "operand ring too shallow");
   static constexpr int kTmemCols = 2 * BN;     // power of two >= 32 for BN in {64,128,256}
-  static constexpr int kEpiOff = kStages * kStageBytes;
-  static constexpr int kBarOff = kEpiOff + kEpiBytes;
-  static constexpr int kSmemBytes = kBarOff + TC_BAR_BYTES + 1024 /*align slack*/;
+  // layout: [barriers][epilogue staging][resident B (BRES; runtime size)][operand ring]
+  static constexpr int kBarOff = 0;
+  static constexpr int kEpiOff = TC_BAR_BYTES;
+  static constexpr int kOpOff = kEpiOff + kEpiBytes;
+  static_assert(kOpOff % 1024 == 0, "operand tiles need 1024-byte alignment");
+  static constexpr int kOpBudget = TC_SMEM_MAX - 1024 /*align slack*/ - kOpOff;
+  static constexpr int kMaxStages = BRES ? TC_MAX_STAGES : (CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
+  static constexpr int kFit = kOpBudget / kStageBytes;          // !BRES: stages that fit
+  static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
+  static_assert(BRES || kStages >= 2, "operand ring too shallow");
+  static constexpr int kSmemBytes = BRES ? TC_SMEM_MAX : kOpOff + kStages * kStageBytes + 1024 /*align slack*/;
+  // BRES: ring depth left after kb_total resident k-blocks of B (host side; < 3 means: use the streaming kernel)
+  static constexpr int res_stages(int64_t kb_total) {
+    const int64_t left = (int64_t)kOpBudget - kb_total * kBBytes;
+    const int64_t st = left / kABytes;
+    return st < 0 ? 0 : (st > TC_MAX_STAGES ? TC_MAX_STAGES : (int)st);
+  }
 };
 
 struct TcShape {
@@ -75,6 +90,8 @@ struct TcShape {
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // UMMA smem-descriptor strides (bytes)
   int32_t pf_dist;  // k-blocks the L2 prefetch cursor leads the load cursor by (0 = off)
   int32_t stages;   // depth of the operand ring actually used (<= the compiled kStages; option "tc_max_stages")
+  unsigned long long* trace;   // profiling (option "tc_trace_ptr"): per CTA 16 cycle counters -- see tools/tc_trace.py; nullptr = off
+  int32_t tile_pf;  // 1: prefetch the next tile's A panel into L2 (tma_apf) at the start of each tile
   int32_t reverse;  // walk the M tiles (and the split-K ranges) from the end: the rows the previous kernel wrote last are still in L2
 };
 
@@ -84,13 +101,13 @@ template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
   else return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));                      // SWIZZLE_64B:  addr[4:5] ^= addr[7:8]
 }
 
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES>
 __global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
-               const __grid_constant__ CUtensorMap tma_aux, TcShape s, Epi epi) {
-  using Cfg = TcCfg<BN, Epi, CG>;
+               const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_apf, TcShape s, Epi epi) {
+  using Cfg = TcCfg<BN, Epi, CG, BRES>;
   using TOut = typename Epi::TOut;
-  constexpr int STAGES = Cfg::kStages;
+  constexpr int STAGES = TC_MAX_STAGES;                    // barrier slots; s.stages of them are in use
   constexpr int EPI_WARPS = Cfg::kEpiWarps;
   constexpr int TM = TC_BM * CG;                           // rows of one (cluster) tile
   constexpr bool WIDE = Cfg::kWide;
@@ -107,10 +124,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
   uint64_t* aux_bar = bars + 2 * STAGES + 4;     // [EPI_WARPS] aux tile landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + EPI_WARPS);
+  uint64_t* bfull_bar = bars + 2 * STAGES + 4 + EPI_WARPS;       // BRES: resident B landed
+  uint64_t* bempty_bar = bfull_bar + 1;                          // BRES: every MMA that reads the resident B has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty_bar + 1);
+  uint8_t* const sres = smem + Cfg::kOpOff;                                        // resident B (BRES)
+  uint8_t* const sring = sres + (BRES ? (int)((s.K + TC_BK - 1) / TC_BK) * Cfg::kBBytes : 0);   // operand ring
   float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // PDL: the next kernel's CTAs may be scheduled as SMs free up
+  if (s.trace != nullptr && threadIdx.x == 0) s.trace[(size_t)blockIdx.x * 16 + 12] = ptx::globaltimer_ns();      // kernel entry
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;    // cluster dims (2,1,1): rank = blockIdx.x & 1
   const bool leader = cta_rank == 0;
   const int64_t work_id = CG == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
@@ -130,6 +153,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       ptx::mbar_init(&tempty_bar[i], EPI_WARPS * CG);      // CG = 2: the peer's epilogue warps arrive remotely on the leader's barrier
     }
     for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
+    ptx::mbar_init(bfull_bar, 1);
+    ptx::mbar_init(bempty_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -146,6 +171,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail; its results
+  // (and the weights Adam wrote) may only be touched from here on
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   const int64_t m_tiles = (s.M + TM - 1) / TM;
   const int64_t n_tiles = (s.N + BN - 1) / BN;
@@ -161,42 +189,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto tile_sp = [&](int64_t t) { const uint32_t sp = (uint32_t)t / (n_tiles32 * m_tiles32); return (int64_t)(s.reverse ? (uint32_t)s.splits - 1 - sp : sp); };
 
   float red = 0.f;
+  // profiling: cycles this warp spent inside a class of barrier waits (accumulated per warp, written by lane 0 at the end)
+  const bool tracing = s.trace != nullptr;
+  long long tw0 = 0, tw1 = 0, tw2 = 0;
+  const long long t_begin = tracing ? clock64() : 0;
+  const unsigned long long g_begin = tracing ? ptx::globaltimer_ns() : 0ull;
+  auto twait = [&](uint64_t* bar, uint32_t parity, int tag, long long& acc_cycles) {
+    if (tracing) {
+      const long long t0 = clock64();
+      ptx::mbar_wait(bar, parity, tag);
+      acc_cycles += clock64() - t0;
+    } else {
+      ptx::mbar_wait(bar, parity, tag);
+    }
+  };
 
   if (warp == 0) {
     // ============================ TMA producer ============================
     // warp-uniform loop; the TMA instructions of one k-block are issued by one elected lane
     {
-      // issue (load into stage `dst`) or prefetch-to-L2 (dst == nullptr) the two operand boxes of k-block kb of a tile
-      auto fetch = [&](int64_t m_t, int64_t n_t, int64_t kb, uint8_t* dst, uint64_t* bar) {
+      // issue (load into sa / sb) or prefetch-to-L2 (null destination with want_* set) the operand boxes of k-block kb of a tile
+      auto fetch = [&](int64_t m_t, int64_t n_t, int64_t kb, uint8_t* sa, uint8_t* sb, uint64_t* bar, bool want_a, bool want_b) {
         const int32_t k_el = (int32_t)(kb * TC_BK);
         // CG = 2: the bytes of BOTH CTAs are counted on the leader's barrier (only the leader issues MMAs)
         const uint32_t bar_addr = (CG == 2 && bar) ? ptx::mapa_u32(ptx::smem_u32(bar), 0) : 0u;
-        uint8_t* sa = dst;
-        uint8_t* sb = dst + Cfg::kABytes;
         const int32_t a_row = (int32_t)(m_t * TM) + (int32_t)cta_rank * TC_BM;          // this CTA's 128 rows of the tile
         const int32_t b_row = (int32_t)(n_t * BN) + (int32_t)cta_rank * (BN / CG);        // this CTA's share of the B tile
         auto ld = [&](void* d, const CUtensorMap* m, int32_t c0, int32_t c1) {
           if constexpr (CG == 2) ptx::tma_load_2d_cg2(d, m, bar_addr, c0, c1);
           else ptx::tma_load_2d(d, m, bar, c0, c1);
         };
-        if constexpr (!A_MN) {
-          if (dst) ld(sa, &tma_a, k_el, a_row);
-          else ptx::tma_prefetch_2d(&tma_a, k_el, a_row);
-        } else {
+        if (want_a) {
+          if constexpr (!A_MN) {
+            if (sa) ld(sa, &tma_a, k_el, a_row);
+            else ptx::tma_prefetch_2d(&tma_a, k_el, a_row);
+          } else {
 #pragma unroll
-          for (int j = 0; j < TC_BM / 64; ++j) {
-            if (dst) ld(sa + j * (64 * TC_BK * 2), &tma_a, a_row + j * 64, k_el);
-            else ptx::tma_prefetch_2d(&tma_a, a_row + j * 64, k_el);
+            for (int j = 0; j < TC_BM / 64; ++j) {
+              if (sa) ld(sa + j * (64 * TC_BK * 2), &tma_a, a_row + j * 64, k_el);
+              else ptx::tma_prefetch_2d(&tma_a, a_row + j * 64, k_el);
+            }
           }
         }
-        if constexpr (!B_MN) {
-          if (dst) ld(sb, &tma_b, k_el, b_row);
-          else ptx::tma_prefetch_2d(&tma_b, k_el, b_row);
-        } else {
+        if (want_b) {
+          if constexpr (!B_MN) {
+            if (sb) ld(sb, &tma_b, k_el, b_row);
+            else ptx::tma_prefetch_2d(&tma_b, k_el, b_row);
+          } else {
 #pragma unroll
-          for (int j = 0; j < (BN / CG) / 64; ++j) {
-            if (dst) ld(sb + j * (64 * TC_BK * 2), &tma_b, b_row + j * 64, k_el);
-            else ptx::tma_prefetch_2d(&tma_b, b_row + j * 64, k_el);
+            for (int j = 0; j < (BN / CG) / 64; ++j) {
+              if (sb) ld(sb + j * (64 * TC_BK * 2), &tma_b, b_row + j * 64, k_el);
+              else ptx::tma_prefetch_2d(&tma_b, b_row + j * 64, k_el);
+            }
           }
         }
       };
@@ -216,7 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (p_live) p_range();
         }
         if (!p_live) return;
-        if (ptx::elect_one()) fetch(tile_m(p_tile), tile_n(p_tile), p_kb, nullptr, nullptr);
+        if (ptx::elect_one()) fetch(tile_m(p_tile), tile_n(p_tile), p_kb, nullptr, nullptr, nullptr, true, !BRES);
         __syncwarp();
         ++p_kb;
       };
@@ -226,16 +270,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       int stage = 0;
       uint32_t phase = 0;
+      int64_t res_nt = -1;                 // BRES: the N tile whose weights are resident
+      uint32_t res_loads = 0;
       for (int64_t tile = work_id; tile < num_tiles; tile += work_stride) {
         const int64_t m_t = tile_m(tile), n_t = tile_n(tile),
                       sp = tile_sp(tile);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+        if constexpr (!A_MN) {
+          // next tile's activation panel -> L2, whole rows at a time (DRAM-page order; the ring's narrow 128-byte-per-row boxes then hit L2)
+          const int64_t nxt = tile + work_stride;
+          if (s.tile_pf && nxt < num_tiles && ptx::elect_one()) {
+            const int32_t nrow = (int32_t)(tile_m(nxt) * TM) + (int32_t)cta_rank * TC_BM;
+            for (int32_t c = (int32_t)(kb0 * TC_BK); c < (int32_t)min(s.K, kb1 * TC_BK); c += 256) ptx::tma_prefetch_2d(&tma_apf, c, nrow);
+          }
+          __syncwarp();
+        }
+        if constexpr (BRES) {
+          if (n_t != res_nt) {             // (re)load the resident weight block: once per CTA when the grid is a multiple of n_tiles
+            if (res_loads > 0) twait(bempty_bar, (res_loads - 1) & 1, 6, tw1);      // the MMAs reading the old block have retired
+            if (ptx::elect_one()) {
+              if (leader) ptx::mbar_arrive_expect_tx(bfull_bar, (uint32_t)kb_total * Cfg::kBBytes * CG);
+              for (int64_t kb = 0; kb < kb_total; ++kb) fetch(m_t, n_t, kb, nullptr, sres + kb * Cfg::kBBytes, bfull_bar, false, true);
+            }
+            __syncwarp();
+            res_nt = n_t;
+            ++res_loads;
+          }
+        }
         for (int64_t kb = kb0; kb < kb1; ++kb) {
           if (s.pf_dist > 0) p_step();
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          twait(&empty_bar[stage], phase ^ 1, 1, tw0);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
-            fetch(m_t, n_t, kb, smem + stage * Cfg::kStageBytes, &full_bar[stage]);
+            uint8_t* const st_base = sring + stage * Cfg::kStageBytes;
+            fetch(m_t, n_t, kb, st_base, st_base + Cfg::kABytes, &full_bar[stage], true, !BRES);
           }
           __syncwarp();
           if (++stage == s.stages) { stage = 0; phase ^= 1; }
@@ -250,28 +318,47 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t idesc = ptx::make_idesc_bf16(TM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       constexpr uint32_t a_kstep = A_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;   // bytes to the next K=16 slice
       constexpr uint32_t b_kstep = B_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;
-      const uint64_t da0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem), s.a_lbo, s.a_sbo);
-      const uint64_t db0 = ptx::make_smem_desc_sw128(ptx::smem_u32(smem) + Cfg::kABytes, s.b_lbo, s.b_sbo);
+      const uint64_t da0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sring), s.a_lbo, s.a_sbo);
+      const uint64_t db0 = ptx::make_smem_desc_sw128(BRES ? ptx::smem_u32(sres) : ptx::smem_u32(sring) + Cfg::kABytes, s.b_lbo, s.b_sbo);
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
+      int64_t res_nt = -1;
+      uint32_t res_loads = 0;
       for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
         const int64_t sp = tile_sp(tile);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         const int acc = (int)(it & 1);
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+        if constexpr (BRES) {
+          const int64_t n_t = tile_n(tile);
+          if (n_t != res_nt) {
+            if (res_loads > 0) {           // hand the old block back once everything issued so far has retired
+              if (ptx::elect_one()) {
+                if constexpr (CG == 2) ptx::umma_commit_cg2_mc(bempty_bar, (uint16_t)3);
+                else ptx::umma_commit(bempty_bar);
+              }
+              __syncwarp();
+            }
+            twait(bfull_bar, res_loads & 1, 7, tw2);
+            ptx::tc_fence_after();
+            res_nt = n_t;
+            ++res_loads;
+          }
+        }
+        twait(&tempty_bar[acc], acc_phase ^ 1, 2, tw1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
         for (int64_t kb = kb0; kb < kb1; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase, 3);
+          twait(&full_bar[stage], phase, 3, tw0);
           ptx::tc_fence_after();
           const uint64_t soff = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
+          const uint64_t boff = BRES ? (uint64_t)((uint32_t)(kb * Cfg::kBBytes) >> 4) : soff;
           if (ptx::elect_one()) {
 #pragma unroll
             for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
               const uint64_t da = da0 + soff + (uint64_t)((kk * a_kstep) >> 4);
-              const uint64_t db = db0 + soff + (uint64_t)((kk * b_kstep) >> 4);
+              const uint64_t db = db0 + boff + (uint64_t)((kk * b_kstep) >> 4);
               const uint32_t accum = (kb > kb0 || kk > 0) ? 1u : 0u;
               if constexpr (CG == 2) ptx::umma_f16_cg2(tmem_d, da, db, idesc, accum);
               else ptx::umma_f16(tmem_d, da, db, idesc, accum);
@@ -359,7 +446,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       uint32_t pre[CH];                      // per-block words the functor wants early (EpiActGrad: the ReLU bit masks)
 #pragma unroll
       for (int c = 0; c < CH; ++c) pre[c] = (col_base + c * 32 < s.N) ? epi.tc_pre(row, col_base + c * 32, valid) : 0u;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      twait(&tfull_bar[acc], acc_phase, 4, tw0);
       ptx::tc_fence_after();
       const bool zero_acc = kb0 >= kb1;
 #pragma unroll
@@ -388,7 +475,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         float aux[32];
         if constexpr (kAux) {
-          ptx::mbar_wait(&aux_bar[ew], aux_phase, 5);
+          twait(&aux_bar[ew], aux_phase, 5, tw1);
           aux_phase ^= 1;
           if constexpr (Epi::kAuxBytes == 2048) {          // bf16 tile, 64-byte rows
 #pragma unroll
@@ -510,6 +597,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   }
 
   // ============================ teardown ==================================
+  if (tracing && lane == 0) {
+    unsigned long long* t = s.trace + (size_t)blockIdx.x * 16;
+    const long long total = clock64() - t_begin;
+    if (warp == 0) { t[0] = (unsigned long long)total; t[1] = (unsigned long long)tw0; t[2] = (unsigned long long)tw1; }            // producer: total, wait empty, wait bempty
+    if (warp == 1) { t[3] = (unsigned long long)total; t[4] = (unsigned long long)tw0; t[5] = (unsigned long long)tw1; t[6] = (unsigned long long)tw2; }   // MMA: total, wait full, wait tempty, wait bfull
+    if (warp == 2) { t[7] = (unsigned long long)total; t[8] = (unsigned long long)tw0; t[9] = (unsigned long long)tw1; }            // epilogue warp 0: total, wait tfull, wait aux
+    if (warp == 5) { t[10] = (unsigned long long)total; t[11] = (unsigned long long)tw0; }
+    if (warp == 0) t[13] = g_begin;                                                   // role loops start (ns)
+    if (warp == 2) t[14] = ptx::globaltimer_ns();                                     // epilogue warp 0 done (ns)
+  }
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync();     // neither CTA may retire while the pair's MMAs / multicast commits can still touch it
   else __syncthreads();
@@ -528,6 +625,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     ptx::tc_fence_after();
     if constexpr (CG == 2) ptx::tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
     else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    if (tracing && lane == 0) s.trace[(size_t)blockIdx.x * 16 + 15] = ptx::globaltimer_ns();     // kernel exit
   }
 }
 
@@ -566,11 +664,16 @@ static inline int tc_pick_bn(int N) {
 int tc_next_direction();  // option "tc_zigzag": successive GEMM launches alternate the direction in which they walk the batch
 int tc_two_cta();         // option "tc_two_cta": use CTA pairs (cta_group::2) where the shape allows
 int tc_max_stages();      // option "tc_max_stages": cap of the operand ring depth (0 = none)
+unsigned long long* tc_trace_ptr();   // option "tc_trace_ptr": device buffer of gridDim.x * 16 counters, or nullptr
+int tc_tile_prefetch();   // option "tc_tile_prefetch"
+int tc_prefetch_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out);
+int tc_b_resident();      // option "tc_b_resident": keep the weight block of the CTA's N tile in shared memory where it fits
 // does this shape run as CTA pairs?  (BN = 256 tiles and more than one 128-row block of M)
 static inline bool tc_use_pair(int64_t M, int N, int force_bn = 0) {
   const int bn = force_bn ? force_bn : tc_pick_bn(N);
   return tc_two_cta() && bn == 256 && M > TC_BM;
 }
+// upper bound of the CTAs a launch uses (the B-resident variant may trim the grid to a multiple of the N tiles)
 static inline int64_t tc_ctas(int64_t M, int N, int splits, int force_bn = 0) {
   const int bn = force_bn ? force_bn : tc_pick_bn(N);
   const int cg = tc_use_pair(M, N, force_bn) ? 2 : 1;
@@ -598,21 +701,27 @@ template <class Epi> struct epi_split_stride<Epi, std::enable_if_t<Epi::kSplit>>
 template <class Epi, class = void> struct epi_cs_atomic { static bool get(const Epi&) { return false; } };
 template <class Epi> struct epi_cs_atomic<Epi, std::enable_if_t<Epi::kColSum>> { static bool get(const Epi& e) { return e.colsum_atomic != 0; } };
 
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false>
 int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st) {
-  using Cfg = TcCfg<BN, Epi, CG>;
+  using Cfg = TcCfg<BN, Epi, CG, BRES>;
   using TOut = typename Epi::TOut;
-  CUtensorMap ta, tb, tout, taux;
+  CUtensorMap ta, tb, tout, taux, tapf;
   PSVAE_TRY(tc_tensor_map(A, K, A_MN ? TC_BK : TC_BM, &ta));
+  tapf = ta;
+  if constexpr (!A_MN) {
+    if (tc_tile_prefetch()) PSVAE_TRY(tc_prefetch_map(A, K, TC_BM, &tapf));
+  }
   PSVAE_TRY(tc_tensor_map(B, K, B_MN ? TC_BK : BN / CG, &tb));
   TcShape s;
   s.M = M; s.N = N; s.K = K; s.splits = splits < 1 ? 1 : splits;
   tc_desc_strides(A_MN, &s.a_lbo, &s.a_sbo);
   tc_desc_strides(B_MN, &s.b_lbo, &s.b_sbo);
   s.pf_dist = tc_prefetch_distance();
-  s.stages = Cfg::kStages;
+  s.stages = BRES ? Cfg::res_stages(ceil_div64(K, TC_BK)) : Cfg::kStages;
   if (tc_max_stages() >= 2 && tc_max_stages() < s.stages) s.stages = tc_max_stages();
   s.reverse = tc_next_direction();
+  s.trace = tc_trace_ptr();
+  s.tile_pf = (!A_MN && tc_tile_prefetch()) ? 1 : 0;
   if (epi.out) {
     const bool split_slots = Epi::kSplit && !epi_split_stride<Epi>::reduce(epi);
     PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, N, epi.ldo, split_slots ? s.splits : 0, epi_split_stride<Epi>::get(epi), &tout,
@@ -625,7 +734,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   } else {
     taux = ta;
   }
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, BRES>;
   static unsigned long long attr_mask = 0;   // per instantiation, one bit per device
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
@@ -633,34 +742,57 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
     PSVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_mask |= 1ull << (dev & 63);
   }
-  const int64_t tiles = ceil_div64(M, TC_BM * CG) * ceil_div64(N, BN) * s.splits;
+  const int64_t n_tiles = ceil_div64(N, BN);
+  const int64_t tiles = ceil_div64(M, TC_BM * CG) * n_tiles * s.splits;
   int grid = tc_grid_size() / CG;            // CG = 2: one CTA pair per tile
+  const int64_t cs_rows = (tiles < grid ? tiles : (int64_t)grid) * CG * 4;     // = 4 * tc_ctas(): what the caller's ordered reduce reads
+  if (BRES) grid = (int)((grid / n_tiles) * n_tiles);     // every CTA (pair) keeps one N tile: its weight block is loaded once
   if (tiles < grid) grid = (int)tiles;
   grid *= CG;
   if (grid < 1) return 0;
   if constexpr (Epi::kColSum) {
     // every (CTA, row-quarter) writes only the columns of the N tiles it saw: the rest of the partial buffer must read as zero
-    if (!epi_cs_atomic<Epi>::get(epi)) PSVAE_CUDA(cudaMemsetAsync(epi.colsum, 0, (size_t)grid * 4 * (size_t)N * sizeof(float), st));
+    if (!epi_cs_atomic<Epi>::get(epi)) PSVAE_CUDA(cudaMemsetAsync(epi.colsum, 0, (size_t)cs_rows * (size_t)N * sizeof(float), st));
   }
-  if constexpr (CG == 2) {
+  {
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof(cfg));
     cfg.gridDim = dim3((unsigned)grid);
     cfg.blockDim = dim3(Cfg::kThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute at[2];
+    int na = 0;
+    if constexpr (CG == 2) {
+      at[na].id = cudaLaunchAttributeClusterDimension;
+      at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (pdl_enabled()) {
+      at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = at;
-    cfg.numAttrs = 1;
-    PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, s, epi));
-  } else {
-    kern<<<grid, Cfg::kThreads, Cfg::kSmemBytes, st>>>(ta, tb, tout, taux, s, epi);
+    cfg.numAttrs = na;
+    PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, tapf, s, epi));
   }
   count_launch();
   PSVAE_LAUNCH_CHECK("gemm_tc_kernel");
   return 0;
+}
+
+// B-resident variant where it applies: forward / dgrad forms (A K-major), no split-K, no auxiliary tile, every N tile gets at least one
+// CTA (pair), and at least 3 ring stages are left next to the weight block
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG>
+int gemm_tc_launch_pick(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st) {
+  if constexpr (!A_MN && !Epi::kSplit && Epi::kAuxBytes == 0) {
+    using CfgR = TcCfg<BN, Epi, CG, true>;
+    const int64_t n_tiles = ceil_div64(N, BN);
+    if (tc_b_resident() && splits <= 1 && n_tiles <= tc_grid_size() / CG && CfgR::res_stages(ceil_div64(K, TC_BK)) >= 3)
+      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, true>(A, B, M, N, K, splits, epi, st);
+  }
+  return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false>(A, B, M, N, K, splits, epi, st);
 }
 
 // can the tcgen05 epilogue produce the column sums of an [M, N] bf16 output?  (pairs of columns: N even; N % 8 is required anyway)
@@ -672,10 +804,10 @@ int gemm_tc_launch(const TcOperand& A, const TcOperand& B, int64_t M, int N, int
   const int bn = force_bn ? force_bn : tc_pick_bn(N);
   switch (bn) {
     case 256:
-      if (tc_use_pair(M, N, force_bn)) return gemm_tc_launch_bn<256, A_MN, B_MN, Epi, 2>(A, B, M, N, K, splits, epi, st);
-      return gemm_tc_launch_bn<256, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, st);
-    case 128: return gemm_tc_launch_bn<128, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, st);
-    case 64: return gemm_tc_launch_bn<64, A_MN, B_MN, Epi>(A, B, M, N, K, splits, epi, st);
+      if (tc_use_pair(M, N, force_bn)) return gemm_tc_launch_pick<256, A_MN, B_MN, Epi, 2>(A, B, M, N, K, splits, epi, st);
+      return gemm_tc_launch_pick<256, A_MN, B_MN, Epi, 1>(A, B, M, N, K, splits, epi, st);
+    case 128: return gemm_tc_launch_pick<128, A_MN, B_MN, Epi, 1>(A, B, M, N, K, splits, epi, st);
+    case 64: return gemm_tc_launch_pick<64, A_MN, B_MN, Epi, 1>(A, B, M, N, K, splits, epi, st);
   }
   set_error("gemm_tc: unsupported BN=%d", bn);
   return -2;

@@ -34,6 +34,7 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, AdamArgs a, bf16* __restrict__ shadow) {
+  PSVAE_GRID_DEP();
   const int64_t n4 = n >> 2;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -67,6 +68,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 
 // ---------------------------------------------------------------- Philox
 __global__ void __launch_bounds__(256) philox_u32_kernel(uint32_t* __restrict__ out, int64_t n, uint64_t seed, uint64_t offset, int64_t first) {
+  PSVAE_GRID_DEP();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t q_first = first >> 2, q_last = (first + n - 1) >> 2;
   for (int64_t q = q_first + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q <= q_last; q += stride) {
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) philox_u32_kernel(uint32_t* __restrict__ 
 // [n_rows, n_cols] normals, element index g = (row0 + r) * n_cols + c  (n_cols % 4 == 0)
 template <typename T>
 __global__ void __launch_bounds__(256) philox_normal_kernel(T* __restrict__ out, int64_t n_elems, uint64_t seed, uint64_t offset, int64_t first_elem) {
+  PSVAE_GRID_DEP();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t nq = n_elems >> 2;
   const uint64_t q0 = (uint64_t)first_elem >> 2;
@@ -95,6 +98,7 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(T* __restrict__ out,
 
 // ---------------------------------------------------------------- casts
 __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+  PSVAE_GRID_DEP();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t n8 = n >> 3;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
@@ -112,6 +116,7 @@ template <typename TAct>
 __global__ void __launch_bounds__(256) latent_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ ls, const float* __restrict__ eps,
                                                          uint64_t seed, uint64_t offset, int64_t first_elem, int64_t n_elems,
                                                          TAct* __restrict__ z, float* __restrict__ z_f32, float* __restrict__ kl_partials) {
+  PSVAE_GRID_DEP();
   __shared__ float scratch[32];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t nq = n_elems >> 2;
@@ -145,6 +150,7 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const float* __restrict
                                                          const float* __restrict__ eps, uint64_t seed, uint64_t offset, int64_t first_elem,
                                                          int64_t n_elems, const float* __restrict__ dmu_clf, float kl_over_b,
                                                          TAct* __restrict__ dmu, TAct* __restrict__ dls) {
+  PSVAE_GRID_DEP();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t nq = n_elems >> 2;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
@@ -174,6 +180,7 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const float* __restrict
 // logits [rows, C] fp32 -> in place: dlogits = (softmax - onehot) * gscale ; partial sums of NLL and of (argmax == y)
 __global__ void __launch_bounds__(256) ce_kernel(float* __restrict__ logits, const int64_t* __restrict__ y, int64_t rows, int C, float gscale,
                                                  int write_grad, float* __restrict__ nll_partials, float* __restrict__ acc_partials) {
+  PSVAE_GRID_DEP();
   __shared__ float scratch[32];
   float nll = 0.f, correct = 0.f;
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -208,6 +215,7 @@ __global__ void __launch_bounds__(256) ce_kernel(float* __restrict__ logits, con
 // partials[chunk][col] = sum over the chunk's rows of in[row, col];  block = 32 cols x 8 row-lanes
 template <typename T>
 __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, int64_t ld, int64_t rows, int N, int64_t rows_per_chunk, float* __restrict__ partials) {
+  PSVAE_GRID_DEP();
   __shared__ float sm[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
@@ -227,6 +235,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ in, i
 
 // out[i] = scale * sum_s partials[s][i]   (fixed order: deterministic)
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __restrict__ partials, int64_t n, int S, int64_t stride_s, float scale, float* __restrict__ out) {
+  PSVAE_GRID_DEP();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float t = 0.f;
@@ -237,6 +246,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float* __res
 // out[i] = sum_s partials[s][i] for S >= 32 partial rows and few columns: block = 32 columns x 32 row lanes; row lane y sums rows
 // y, y+32, ... in order, then the 32 lane sums are added in a fixed order (deterministic)
 __global__ void __launch_bounds__(1024) reduce_tall_kernel(const float* __restrict__ partials, int n, int S, int64_t stride_s, float* __restrict__ out) {
+  PSVAE_GRID_DEP();
   __shared__ float sm[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
@@ -261,6 +271,7 @@ __global__ void __launch_bounds__(1024) reduce_tall_kernel(const float* __restri
 
 // ---------------------------------------------------------------- F.normalize(p=2, dim=1): one warp per row
 __global__ void __launch_bounds__(256) row_normalize_kernel(float* __restrict__ x, int64_t rows, int D) {
+  PSVAE_GRID_DEP();
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -283,6 +294,7 @@ struct LossPartials {
 };
 
 __global__ void finalize_losses_kernel(LossPartials lp, float* __restrict__ losses) {
+  PSVAE_GRID_DEP();
   // single block of 32 threads; each sum is taken in a fixed order
   const int lane = threadIdx.x;
   auto sum = [&](const float* p, int n) {
@@ -330,6 +342,7 @@ template <typename TAct>
 __global__ void __launch_bounds__(256) recon_rows_kernel(const float* __restrict__ u, const float* __restrict__ x, int64_t rows, int D, int normalize,
                                                          int use_cos, float gscale, float* __restrict__ x_hat, TAct* __restrict__ du,
                                                          float* __restrict__ loss_partials) {
+  PSVAE_GRID_DEP();
   __shared__ float scratch[32];
   const int lane = threadIdx.x & 31;
   const int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -394,6 +407,7 @@ __global__ void __launch_bounds__(256) recon_rows_kernel(const float* __restrict
 // fp32 [rows][cols] -> TAct (same shape, contiguous): z handed to psvae_decode
 template <typename TAct>
 __global__ void __launch_bounds__(256) convert_kernel(const float* __restrict__ in, TAct* __restrict__ out, int64_t n) {
+  PSVAE_GRID_DEP();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = from_f32<TAct>(in[i]);
 }
@@ -427,6 +441,7 @@ static inline size_t clf_fused_smem_bytes(int L) { return ((size_t)CLF_TILE * (L
 template <int L>
 __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __restrict__ params, const float* __restrict__ mu, const int64_t* __restrict__ y,
                                                              int64_t B, ClfFusedArgs a, float* __restrict__ dmu_clf, float* __restrict__ part) {
+  PSVAE_GRID_DEP();
   extern __shared__ __align__(16) float clf_smem[];
   __shared__ float scratch[32];
   constexpr int ldm = L + 4;                            // 16-byte aligned rows; row-per-lane float4 reads are conflict-free per quarter warp
@@ -597,6 +612,7 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
 // sum the per-block partials in block order (32 row lanes, fixed-order tree) and scatter: nll/acc sums -> sums[8], dW/db -> the flat gradient buffer
 __global__ void __launch_bounds__(1024) clf_fused_finish_kernel(const float* __restrict__ part, int blocks, int L, ClfFusedArgs a, float* __restrict__ sums,
                                                                 float* __restrict__ grads) {
+  PSVAE_GRID_DEP();
   __shared__ float sm[32][33];
   const int PART = clf_part_len(L);
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -630,6 +646,7 @@ __global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restr
                                                             const float* __restrict__ eps, uint64_t seed, uint64_t offset, int64_t first_elem,
                                                             int64_t n_elems, int L, const float* __restrict__ dmu_clf, float kl_over_b,
                                                             TAct* __restrict__ dmu, TAct* __restrict__ dls, float* __restrict__ partials) {
+  PSVAE_GRID_DEP();
   extern __shared__ float lb_smem[];        // [256][8]
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t nq = n_elems >> 2;

@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(LG_THREADS) langevin_kernel(LangevinClf c, con
                                                               int64_t rows, float step_size, int num_steps, float noise_weight, uint64_t seed,
                                                               uint64_t offset0, int64_t row0, int init_from_philox, const float* __restrict__ noise,
                                                               float* __restrict__ history, float* __restrict__ stats) {
+  PSVAE_GRID_DEP();
   extern __shared__ float lg_smem[];
   const int L = c.L, H = c.hidden;
   const int ldz = L + 1, ldh = H + 1, ldd = (H > L ? ldh : ldz), ldc = LG_MAXC + 1;
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(LGF_THREADS) langevin_fast_kernel(LangevinClf 
                                                                     float step_size, int num_steps, float noise_weight, uint64_t seed, uint64_t offset0,
                                                                     int64_t row0, int init_from_philox, const float* __restrict__ noise,
                                                                     float* __restrict__ history, float* __restrict__ stats) {
+  PSVAE_GRID_DEP();
   __shared__ __align__(16) float W[CLF_LG_MAXC * L];
   __shared__ float bias[CLF_LG_MAXC];
   __shared__ int cls_head[CLF_LG_MAXC];

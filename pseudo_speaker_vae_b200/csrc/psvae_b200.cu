@@ -59,6 +59,10 @@ struct Options {
   int64_t tc_two_cta = 1;              // 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2) for BN = 256 shapes
   int64_t tc_zigzag = 0;               // successive GEMM launches walk the batch in alternating directions (L2 reuse of the rows written last)
   int64_t langevin_generic = 0;        // tests: force the generic (tile-in-smem) Langevin kernel even where the thread-per-sample one applies
+  int64_t tc_b_resident = 0;           // 1: forward / dgrad GEMMs keep the weight block of their N tile resident in shared memory (where it fits)
+  int64_t tc_tile_prefetch = 0;        // 1: the producer pulls the NEXT tile's whole activation panel into L2 with wide-box prefetches at the start of each tile
+  int64_t pdl = 1;                     // 1: kernels are launched with programmatic stream serialization (their prologue overlaps the predecessor's tail)
+  int64_t tc_trace_ptr = 0;            // profiling: device pointer of gridDim.x * 16 cycle counters the GEMM kernels fill (0 = off)
   int64_t tc_max_stages = 0;           // experiments: cap the depth of the operand ring (0 = what fits)
   int64_t deterministic = 0;           // 1: split-K / bias partials go through ordered two-stage sums instead of TMA reduce-add / atomics
 };
@@ -103,6 +107,10 @@ int tc_device_check() {
 int tc_prefetch_distance() { return (int)g_opt.tc_prefetch; }
 int tc_two_cta() { return (int)g_opt.tc_two_cta; }
 int tc_max_stages() { return (int)g_opt.tc_max_stages; }
+int tc_b_resident() { return (int)g_opt.tc_b_resident; }
+bool pdl_enabled() { return g_opt.pdl != 0; }
+int tc_tile_prefetch() { return (int)g_opt.tc_tile_prefetch; }
+unsigned long long* tc_trace_ptr() { return reinterpret_cast<unsigned long long*>(static_cast<uintptr_t>(g_opt.tc_trace_ptr)); }
 static thread_local unsigned g_dir = 0;
 int tc_next_direction() { return g_opt.tc_zigzag ? (int)(g_dir++ & 1u) : 0; }
 int tc_grid_size() {
@@ -170,6 +178,25 @@ int tc_tensor_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out
     return -3;
   }
   if (g_tm_cache.size() > 8192) g_tm_cache.clear();
+  g_tm_cache[key] = tm;
+  *out = tm;
+  return 0;
+}
+
+// L2-prefetch map of a K-major operand: wide boxes ([box_rows][up to 256 columns], no swizzle -- nothing lands in shared memory) so that one
+// instruction pulls a whole row panel of the next tile from HBM in DRAM-page order
+int tc_prefetch_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lk(g_tm_mu);
+  if (!g_encode) { set_error("tc_prefetch_map before tc_tensor_map"); return -3; }
+  const TmKey key(op.ptr, op.rows, op.ld, K, 2, box_rows);
+  auto it = g_tm_cache.find(key);
+  if (it != g_tm_cache.end()) { *out = it->second; return 0; }
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)op.rows}, gstride[1] = {(cuuint64_t)op.ld * sizeof(bf16)};
+  cuuint32_t box[2] = {(cuuint32_t)(K < 256 ? K : 256), (cuuint32_t)box_rows}, estr[2] = {1, 1};
+  alignas(64) CUtensorMap tm;
+  CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (prefetch map) failed (%d)", (int)r); return -3; }
   g_tm_cache[key] = tm;
   *out = tm;
   return 0;
@@ -458,19 +485,19 @@ static int launch_colsum(const T* in, int64_t ld, int64_t rows, int N, float* cp
   const int64_t rpc = g_opt.colsum_rows;
   const int chunks = (int)ceil_div64(rows, rpc);
   dim3 grid((unsigned)ceil_div64(N, 32), (unsigned)chunks);
-  colsum_kernel<T><<<grid, 256, 0, st>>>(in, ld, rows, N, rpc, cpart);
+  launch_dep(colsum_kernel<T>, dim3(grid), dim3(256), 0, st, in, ld, rows, N, rpc, cpart);
   count_launch();
   PSVAE_LAUNCH_CHECK("colsum_kernel");
   return launch_reduce(cpart, N, chunks, out, st);
 }
 static int launch_reduce(const float* partials, int64_t n, int S, float* out, cudaStream_t st) {
   if (S >= 32 && n <= 65536) {       // many partial rows, few columns: spread the rows over the block (fixed-order tree)
-    reduce_tall_kernel<<<(unsigned)ceil_div64(n, 32), 1024, 0, st>>>(partials, (int)n, S, n, out);
+    launch_dep(reduce_tall_kernel, dim3((unsigned)ceil_div64(n, 32)), dim3(1024), 0, st, partials, (int)n, S, n, out);
     count_launch();
     PSVAE_LAUNCH_CHECK("reduce_tall_kernel");
     return 0;
   }
-  reduce_partials_kernel<<<(unsigned)ceil_div64(n, 256), 256, 0, st>>>(partials, n, S, n, 1.f, out);
+  launch_dep(reduce_partials_kernel, dim3((unsigned)ceil_div64(n, 256)), dim3(256), 0, st, partials, n, S, n, 1.f, out);
   count_launch();
   PSVAE_LAUNCH_CHECK("reduce_partials_kernel");
   return 0;
@@ -648,7 +675,7 @@ static int run_step(const StepArgs& a) {
   // ---- encoders (model.py:54-55).  Layer 0 of both encoders is one [2H, D] GEMM.
   const TAct* xa;
   if constexpr (sizeof(TAct) == 2) {
-    cast_bf16_kernel<<<ew_grid(B * n.D / 8), 256, 0, st>>>(a.x, w.xa, B * n.D);
+    launch_dep(cast_bf16_kernel, dim3(ew_grid(B * n.D / 8)), dim3(256), 0, st, a.x, w.xa, B * n.D);
     count_launch();
     PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
     xa = w.xa;
@@ -671,7 +698,7 @@ static int run_step(const StepArgs& a) {
     PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(w.he[n.nh - 1] + s * n.H, 2 * n.H, Wt + d->enc_w[n.nh] + (int64_t)s * n.L * n.H, n.H, B, n.L, n.H, 1, true, e, st)));
   }
   // ---- reparameterisation + KL partial sums (model.py:56-57, lightning.py:115-117)
-  latent_fwd_kernel<TAct><<<(unsigned)w.n_kl, 256, 0, st>>>(mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, w.z, nullptr, w.kl_part);
+  launch_dep(latent_fwd_kernel<TAct>, dim3((unsigned)w.n_kl), dim3(256), 0, st, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, w.z, nullptr, w.kl_part);
   count_launch();
   PSVAE_LAUNCH_CHECK("latent_fwd_kernel");
 
@@ -699,24 +726,24 @@ static int run_step(const StepArgs& a) {
     switch (n.L) {
       case 16:
         PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        clf_fused_kernel<16><<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part);
+        launch_dep(clf_fused_kernel<16>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part);
         break;
       case 32:
         PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        clf_fused_kernel<32><<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part);
+        launch_dep(clf_fused_kernel<32>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part);
         break;
       case 64:
         PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        clf_fused_kernel<64><<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part);
+        launch_dep(clf_fused_kernel<64>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part);
         break;
       default:
         PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        clf_fused_kernel<128><<<blocks, CLF_TILE, smem, st>>>(P, mu, a.y, B, ca, dmu_out, w.clf_part);
+        launch_dep(clf_fused_kernel<128>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part);
         break;
     }
     count_launch();
     PSVAE_LAUNCH_CHECK("clf_fused_kernel");
-    clf_fused_finish_kernel<<<(unsigned)ceil_div64(clf_part_len(n.L), 32), 1024, 0, st>>>(w.clf_part, blocks, n.L, ca, w.clf_sums,
+    launch_dep(clf_fused_finish_kernel, dim3((unsigned)ceil_div64(clf_part_len(n.L), 32)), dim3(1024), 0, st, w.clf_part, blocks, n.L, ca, w.clf_sums,
                                                                                              a.want_grads ? a.grads : nullptr);
     count_launch();
     PSVAE_LAUNCH_CHECK("clf_fused_finish_kernel");
@@ -730,7 +757,7 @@ static int run_step(const StepArgs& a) {
       const int C = d->clf_head_classes[h];
       PSVAE_TRY(clf_linear(ACT_NONE, feat, feat_dim, P + d->clf_head_w[h], P + d->clf_head_b[h], w.logits[h], B, C, feat_dim, st));
       const float gscale = a.clf_w / ((float)B * (float)d->clf_num_heads);
-      ce_kernel<<<(unsigned)w.n_ce, 256, 0, st>>>(w.logits[h], a.y + (int64_t)h * B, B, C, gscale, a.want_grads, w.nll_part[h], w.acc_part[h]);
+      launch_dep(ce_kernel, dim3((unsigned)w.n_ce), dim3(256), 0, st, w.logits[h], a.y + (int64_t)h * B, B, C, gscale, a.want_grads, w.nll_part[h], w.acc_part[h]);
       count_launch();
       PSVAE_LAUNCH_CHECK("ce_kernel");
     }
@@ -766,7 +793,7 @@ static int run_step(const StepArgs& a) {
     if (general_tail) {
       const float gscale = a.use_cos ? 1.f / (float)B : 2.f / ((float)B * (float)n.D * 10.f);
       const int blocks = (int)ceil_div64(B * 32, 256);
-      recon_rows_kernel<TAct><<<blocks, 256, 0, st>>>(w.u, a.want_loss ? a.x : nullptr, B, n.D, d->normalize_decoder, a.use_cos, gscale, a.x_hat,
+      launch_dep(recon_rows_kernel<TAct>, dim3(blocks), dim3(256), 0, st, w.u, a.want_loss ? a.x : nullptr, B, n.D, d->normalize_decoder, a.use_cos, gscale, a.x_hat,
                                                       a.want_grads ? w.dxh : nullptr, a.want_loss ? w.sse_part : nullptr);
       count_launch();
       PSVAE_LAUNCH_CHECK("recon_rows_kernel");
@@ -787,7 +814,7 @@ static int run_step(const StepArgs& a) {
     lp.recon_scale = a.use_cos ? 1.f / (float)B : 1.f / ((float)B * (float)n.D * 10.f);
     lp.inv_b = 1.f / (float)B;
     lp.kl_w = a.kl_w; lp.clf_w = a.clf_w;
-    finalize_losses_kernel<<<1, 32, 0, st>>>(lp, a.losses);
+    launch_dep(finalize_losses_kernel, dim3(1), dim3(32), 0, st, lp, a.losses);
     count_launch();
     PSVAE_LAUNCH_CHECK("finalize_losses_kernel");
   }
@@ -856,14 +883,14 @@ static int run_step(const StepArgs& a) {
   if (latent_cs_ok(n.L)) {
     int blocks = ew_grid(B * n.L / 4);
     if (blocks > 2 * PSVAE_NUM_SMS) blocks = 2 * PSVAE_NUM_SMS;
-    latent_bwd_cs_kernel<TAct><<<blocks, 256, 256 * 8 * sizeof(float), st>>>(w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, n.L, dmu_clf,
+    launch_dep(latent_bwd_cs_kernel<TAct>, dim3(blocks), dim3(256), 256 * 8 * sizeof(float), st, w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, n.L, dmu_clf,
                                                                              a.kl_w / (float)B, w.dmu, w.dls, w.cpart);
     count_launch();
     PSVAE_LAUNCH_CHECK("latent_bwd_cs_kernel");
     PSVAE_TRY(launch_reduce(w.cpart, 2 * n.L, blocks, G + d->enc_b[n.nh], st));
     last_bias_done = true;
   } else {
-    latent_bwd_kernel<TAct><<<ew_grid(B * n.L / 4), 256, 0, st>>>(w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, dmu_clf, a.kl_w / (float)B,
+    launch_dep(latent_bwd_kernel<TAct>, dim3(ew_grid(B * n.L / 4)), dim3(256), 0, st, w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, dmu_clf, a.kl_w / (float)B,
                                                                   w.dmu, w.dls);
     count_launch();
     PSVAE_LAUNCH_CHECK("latent_bwd_kernel");
@@ -935,7 +962,7 @@ static int run_decode(const psvae_model_desc* d, const float* params, const bf16
     const TAct* zin;
     if (z) {
       if constexpr (sizeof(TAct) == 2) {
-        cast_bf16_kernel<<<ew_grid(nel / 8), 256, 0, st>>>(z + r0 * n.L, w.z, nel);
+        launch_dep(cast_bf16_kernel, dim3(ew_grid(nel / 8)), dim3(256), 0, st, z + r0 * n.L, w.z, nel);
         count_launch();
         PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
         zin = w.z;
@@ -946,11 +973,11 @@ static int run_decode(const psvae_model_desc* d, const float* params, const bf16
     } else {
       const int64_t first = (row0 + r0) * n.L;
       if (z_out) {
-        philox_normal_kernel<float><<<ew_grid(nel / 4), 256, 0, st>>>(z_out + r0 * n.L, nel, seed, offset, first);
+        launch_dep(philox_normal_kernel<float>, dim3(ew_grid(nel / 4)), dim3(256), 0, st, z_out + r0 * n.L, nel, seed, offset, first);
         count_launch();
         PSVAE_LAUNCH_CHECK("philox_normal_kernel");
         if constexpr (sizeof(TAct) == 2) {
-          cast_bf16_kernel<<<ew_grid(nel / 8), 256, 0, st>>>(z_out + r0 * n.L, w.z, nel);
+          launch_dep(cast_bf16_kernel, dim3(ew_grid(nel / 8)), dim3(256), 0, st, z_out + r0 * n.L, w.z, nel);
           count_launch();
           PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
           zin = w.z;
@@ -958,7 +985,7 @@ static int run_decode(const psvae_model_desc* d, const float* params, const bf16
           zin = z_out + r0 * n.L;
         }
       } else {
-        philox_normal_kernel<TAct><<<ew_grid(nel / 4), 256, 0, st>>>(w.z, nel, seed, offset, first);
+        launch_dep(philox_normal_kernel<TAct>, dim3(ew_grid(nel / 4)), dim3(256), 0, st, w.z, nel, seed, offset, first);
         count_launch();
         PSVAE_LAUNCH_CHECK("philox_normal_kernel");
         zin = w.z;
@@ -968,7 +995,7 @@ static int run_decode(const psvae_model_desc* d, const float* params, const bf16
     EpiBiasAct<float, ACT_NONE> e{params + d->dec_b[n.nh], out, n.D, nullptr};
     PSVAE_TRY(decoder_forward<TAct>(n, Wt, params, zin, w.hd, m, e, st));
     if (d->normalize_decoder) {
-      row_normalize_kernel<<<(unsigned)ceil_div64(m * 32, 256), 256, 0, st>>>(out, m, n.D);
+      launch_dep(row_normalize_kernel, dim3((unsigned)ceil_div64(m * 32, 256)), dim3(256), 0, st, out, m, n.D);
       count_launch();
       PSVAE_LAUNCH_CHECK("row_normalize_kernel");
     }
@@ -1005,6 +1032,10 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "langevin_generic")) { g_opt.langevin_generic = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_prefetch")) { g_opt.tc_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
   if (!strcmp(name, "tc_max_stages")) { g_opt.tc_max_stages = value < 0 ? 0 : value; return 0; }
+  if (!strcmp(name, "tc_b_resident")) { g_opt.tc_b_resident = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_trace_ptr")) { g_opt.tc_trace_ptr = value; return 0; }
+  if (!strcmp(name, "pdl")) { g_opt.pdl = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
   return -2;
 }
@@ -1021,6 +1052,9 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "langevin_generic")) return g_opt.langevin_generic;
   if (!strcmp(name, "tc_prefetch")) return g_opt.tc_prefetch;
   if (!strcmp(name, "tc_max_stages")) return g_opt.tc_max_stages;
+  if (!strcmp(name, "tc_b_resident")) return g_opt.tc_b_resident;
+  if (!strcmp(name, "pdl")) return g_opt.pdl;
+  if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;
 }
 
@@ -1117,7 +1151,7 @@ int psvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, dou
   a.one_minus_beta2 = (float)(1.0 - beta2);
   a.eps = (float)eps; a.weight_decay = (float)weight_decay; a.grad_scale = (float)grad_scale;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  adam_kernel<<<ew_grid(n / 4 + 1), 256, 0, st>>>(p, g, m, v, n, a, static_cast<bf16*>(shadow_bf16));
+  launch_dep(adam_kernel, dim3(ew_grid(n / 4 + 1)), dim3(256), 0, st, p, g, m, v, n, a, static_cast<bf16*>(shadow_bf16));
   count_launch();
   PSVAE_LAUNCH_CHECK("adam_kernel");
   return 0;
@@ -1127,7 +1161,7 @@ int psvae_philox_uint32(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset
   PSVAE_TRY(tc_device_check());
   if (!out) { set_error("out is NULL"); return -1; }
   if (n <= 0) return 0;
-  philox_u32_kernel<<<ew_grid(n / 4 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, offset, first_elem);
+  launch_dep(philox_u32_kernel, dim3(ew_grid(n / 4 + 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), out, n, seed, offset, first_elem);
   count_launch();
   PSVAE_LAUNCH_CHECK("philox_u32_kernel");
   return 0;
@@ -1139,7 +1173,7 @@ int psvae_philox_normal(float* out, int64_t n_rows, int32_t n_cols, uint64_t see
   if (n_rows <= 0) return 0;
   if (n_cols <= 0 || n_cols % 4) { set_error("n_cols=%d must be a positive multiple of 4", n_cols); return -2; }
   const int64_t n = n_rows * n_cols;
-  philox_normal_kernel<float><<<ew_grid(n / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, n, seed, offset, row0 * n_cols);
+  launch_dep(philox_normal_kernel<float>, dim3(ew_grid(n / 4)), dim3(256), 0, static_cast<cudaStream_t>(stream), out, n, seed, offset, row0 * n_cols);
   count_launch();
   PSVAE_LAUNCH_CHECK("philox_normal_kernel");
   return 0;
@@ -1149,7 +1183,7 @@ int psvae_refresh_shadow(const psvae_model_desc* desc, const float* params, void
   PSVAE_TRY(tc_device_check());
   if (!desc || !params || !shadow_bf16) { set_error("desc, params, shadow must not be NULL"); return -1; }
   const int64_t n = desc->total_numel;
-  cast_bf16_kernel<<<ew_grid(n / 8 + 1), 256, 0, static_cast<cudaStream_t>(stream)>>>(params, static_cast<bf16*>(shadow_bf16), n);
+  launch_dep(cast_bf16_kernel, dim3(ew_grid(n / 8 + 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), params, static_cast<bf16*>(shadow_bf16), n);
   count_launch();
   PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
   return 0;
@@ -1225,9 +1259,9 @@ int psvae_langevin(const psvae_model_desc* desc, const float* params, float* z_i
   if (c.n_trunk == 0 && targeted_classes <= CLF_LG_MAXC && (n.L == 16 || n.L == 32 || n.L == 64) && !g_opt.langevin_generic) {
     const unsigned gridf = (unsigned)ceil_div64(rows, LGF_THREADS);
     switch (n.L) {
-      case 16: langevin_fast_kernel<16><<<gridf, LGF_THREADS, 0, st>>>(c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
-      case 32: langevin_fast_kernel<32><<<gridf, LGF_THREADS, 0, st>>>(c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
-      default: langevin_fast_kernel<64><<<gridf, LGF_THREADS, 0, st>>>(c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
+      case 16: launch_dep(langevin_fast_kernel<16>, dim3(gridf), dim3(LGF_THREADS), 0, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
+      case 32: launch_dep(langevin_fast_kernel<32>, dim3(gridf), dim3(LGF_THREADS), 0, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
+      default: launch_dep(langevin_fast_kernel<64>, dim3(gridf), dim3(LGF_THREADS), 0, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
     }
     count_launch();
     PSVAE_LAUNCH_CHECK("langevin_fast_kernel");
@@ -1237,7 +1271,7 @@ int psvae_langevin(const psvae_model_desc* desc, const float* params, float* z_i
   if (smem > 227 * 1024) { set_error("classifier too large for the Langevin kernel's shared memory (%zu bytes)", smem); return -2; }
   PSVAE_CUDA(cudaFuncSetAttribute(langevin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)ceil_div64(rows, LG_TILE);
-  langevin_kernel<<<grid, LG_THREADS, smem, st>>>(c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox,
+  launch_dep(langevin_kernel, dim3(grid), dim3(LG_THREADS), smem, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox,
                                                   noise, history, stats);
   count_launch();
   PSVAE_LAUNCH_CHECK("langevin_kernel");
@@ -1322,6 +1356,14 @@ int psvae_gemm_probe(const void* a_bf16, const void* w_bf16, const float* bias, 
     }
     EpiActGrad<bf16, bf16, ACT_RELU, false> e{nullptr, 0, mask, m, out, n, 0.f, nullptr, nullptr, 0};
     return gemm_tc_launch<false, true>(oa, ob, m, n, k, 1, e, st, fbn);
+  }
+  if (form == 2) {      // wgrad: out[n_out = n][n_in = k] (fp32, accumulated by TMA reduce-add) = A[m][n]^T * W[m][k]   (m = batch rows)
+    float* gw = static_cast<float*>(out_bf16);
+    if (!gw) { set_error("form 2 needs an output"); return -1; }
+    const int out_dim = n, in_dim = (int)k;
+    const int splits = Engine<bf16>::wgrad_splits(out_dim, in_dim, m);
+    EpiStore e{gw, in_dim, 0, 1.f, 0.f, nullptr, 1};
+    return Engine<bf16>::gemm<G_WGRAD>(A, out_dim, W, in_dim, out_dim, in_dim, m, splits, true, e, st);
   }
   set_error("unknown probe form %d", form);
   return -2;

@@ -20,6 +20,7 @@ struct SgemmOperand {
 
 template <class Epi>
 __global__ void __launch_bounds__(SG_THREADS) sgemm_kernel(SgemmOperand A, SgemmOperand B, int M, int N, int64_t K, int64_t k_chunk, int vec_ok, Epi epi) {
+  PSVAE_GRID_DEP();
   __shared__ __align__(16) float As[2][SG_BK][SG_LD];
   __shared__ __align__(16) float Bs[2][SG_BK][SG_LD];
   __shared__ float red_scratch[32];
@@ -121,7 +122,7 @@ int sgemm_launch(const SgemmOperand& A, const SgemmOperand& B, int64_t M, int N,
   if (splits < 1) splits = 1;
   int64_t k_chunk = align_up64(ceil_div64(K, splits), SG_BK);
   dim3 grid((unsigned)ceil_div64(M, SG_BM), (unsigned)ceil_div64(N, SG_BN), (unsigned)splits);
-  sgemm_kernel<Epi><<<grid, SG_THREADS, 0, st>>>(A, B, (int)M, N, K, k_chunk, vec_ok ? 1 : 0, epi);
+  launch_dep(sgemm_kernel<Epi>, dim3(grid), dim3(SG_THREADS), 0, st, A, B, (int)M, N, K, k_chunk, vec_ok ? 1 : 0, epi);
   count_launch();
   PSVAE_LAUNCH_CHECK("sgemm_kernel");
   return 0;
