@@ -219,6 +219,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the sampling / e2e / CPU legs")
     ap.add_argument("--sample-n", type=int, default=4 * 1024 * 1024)
     ap.add_argument("--cond-n", type=int, default=1024 * 1024)
+    ap.add_argument("--wide-batch", type=int, default=32768, help="rows per GPU of the widened-VAE secondary line (BASELINE configs[4])")
     ap.add_argument("--opt", action="append", default=[], help="library tuning option name=value (psvae_set_option), repeatable")
     args = ap.parse_args()
     args.steps_given = args.steps is not None
@@ -368,6 +369,30 @@ def main():
             del out
         except Exception as e:  # noqa: BLE001
             sec["error"] = repr(e)
+        # ---- secondary: the widened VAE of BASELINE configs[4] (512-d, 4 x 2048 hidden, latent classifier) ------------------------
+        try:
+            Dw, Hw, NHw, Bw = 512, 2048, 4, args.wide_batch
+            torch.manual_seed(0)
+            wide = P.PseudoSpeakerVAE(model=dict(input_dim=Dw, latent_dim=LAT, hidden_dim=Hw, num_hidden_layers=NHw),
+                                      classifier=dict(input_dim=LAT, num_classes=NCLS), optimizer=dict(lr=1e-3), scheduler=dict(T_max=200),
+                                      precision=args.precision).to(dev)
+            wtr = P.DataParallelTrainer(wide)
+            wtr.set_shard(Bw * n_gpus)
+            wide.hot_path.manual_seed(1236, 0)
+            xw, yw, _ = O.synth_batch(Bw, Dw, LAT, NCLS, seed=4321 + rank)
+            wb = [(torch.from_numpy(xw).to(dev), torch.from_numpy(yw).to(dev)), (torch.from_numpy(xw[::-1].copy()).to(dev), torch.from_numpy(yw[::-1].copy()).to(dev))]
+            for i in range(3):
+                wtr.train_step(*wb[i % 2])
+            Kw = 10
+            ms_w = time_events(lambda: [wtr.train_step(*wb[i % 2]) for i in range(Kw)], torch, dist_on)
+            fl = float(wide.hot_path.flops_train)            # psvae_flops_per_sample: 243,532,544 (+768 classifier), SURVEY 8(d)
+            wps = Bw * n_gpus * Kw / (ms_w * 1e-3)
+            sec["widened_config5"] = dict(value=wps, unit=UNIT, batch_per_gpu=Bw, ms_per_step=ms_w / Kw, flops_per_sample=fl,
+                                          tensor_frac=wps * fl / 1e12 / (peaks["bf16_sustained"] * n_gpus),
+                                          note="D=512, 4 x 2048 hidden, L=64, 2-class latent classifier, fwd+bwd+Adam, same fused step")
+            del wide, wtr, wb
+        except Exception as e:  # noqa: BLE001
+            sec["widened_config5"] = dict(error=repr(e))
         line["secondary"] = sec
 
         # ---- CPU baseline on this box's host cores (rank 0, N = 1 only) -----------------------------------------------

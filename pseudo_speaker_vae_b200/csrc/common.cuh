@@ -33,11 +33,12 @@ int cuda_fail(cudaError_t e, const char* what);
 
 // Programmatic dependent launch (PDL): every kernel of the step is launched with programmaticStreamSerialization, so its CTAs may be
 // scheduled (and run their prologue) while the previous kernel drains; PSVAE_GRID_DEP() at the top of a kernel lets ITS successor do the
-// same and then waits until the predecessor has completed and its writes are visible.  No-ops when the kernel was launched normally.
+// same -- but only AFTER it has itself waited for its predecessor, so that a kernel that starts early knows: everything up to its
+// predecessor's predecessor is complete and visible (the GEMM engine relies on this to preload weights).  No-ops when launched normally.
 #define PSVAE_GRID_DEP()                                                   \
   do {                                                                     \
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");        \
     asm volatile("griddepcontrol.wait;" ::: "memory");                     \
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");        \
   } while (0)
 
 // launch with the PDL attribute (option "pdl", default on) -- kernels launched this way MUST start with PSVAE_GRID_DEP()

@@ -91,6 +91,7 @@ struct TcShape {
   int32_t pf_dist;  // k-blocks the L2 prefetch cursor leads the load cursor by (0 = off)
   int32_t stages;   // depth of the operand ring actually used (<= the compiled kStages; option "tc_max_stages")
   unsigned long long* trace;   // profiling (option "tc_trace_ptr"): per CTA 16 cycle counters -- see tools/tc_trace.py; nullptr = off
+  int32_t b_stable; // BRES: B was written at least two kernels before this one (weights): its resident block is loaded before griddepcontrol.wait
   int32_t tile_pf;  // 1: prefetch the next tile's A panel into L2 (tma_apf) at the start of each tile
   int32_t reverse;  // walk the M tiles (and the split-K ranges) from the end: the rows the previous kernel wrote last are still in L2
 };
@@ -132,7 +133,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // PDL: the next kernel's CTAs may be scheduled as SMs free up
   if (s.trace != nullptr && threadIdx.x == 0) s.trace[(size_t)blockIdx.x * 16 + 12] = ptx::globaltimer_ns();      // kernel entry
   const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;    // cluster dims (2,1,1): rank = blockIdx.x & 1
   const bool leader = cta_rank == 0;
@@ -171,9 +171,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // BRES + b_stable: B (the weights) was written at least two kernels ago, so under PDL it is safe to pull the CTA's resident weight block
+  // in NOW, while the predecessor kernel is still draining -- the one-off 256 KB load per CTA pair then costs nothing on the critical path
+  if constexpr (BRES) {
+    if (s.b_stable && warp == 0) {
+      const int64_t n_tiles0 = (s.N + BN - 1) / BN;
+      const int64_t w0 = CG == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+      const int64_t kbt = (s.K + TC_BK - 1) / TC_BK;
+      if (ptx::elect_one()) {
+        const int32_t b_row = (int32_t)((w0 % n_tiles0) * BN) + (int32_t)cta_rank * (BN / CG);
+        const uint32_t bar_addr = CG == 2 ? ptx::mapa_u32(ptx::smem_u32(bfull_bar), 0) : 0u;
+        if (leader) ptx::mbar_arrive_expect_tx(bfull_bar, (uint32_t)kbt * Cfg::kBBytes * CG);
+        for (int64_t kb = 0; kb < kbt; ++kb) {
+          uint8_t* sb = sres + kb * Cfg::kBBytes;
+          const int32_t k_el = (int32_t)(kb * TC_BK);
+          if constexpr (!B_MN) {
+            if constexpr (CG == 2) ptx::tma_load_2d_cg2(sb, &tma_b, bar_addr, k_el, b_row);
+            else ptx::tma_load_2d(sb, &tma_b, bfull_bar, k_el, b_row);
+          } else {
+#pragma unroll
+            for (int j = 0; j < (BN / CG) / 64; ++j) {
+              if constexpr (CG == 2) ptx::tma_load_2d_cg2(sb + j * (64 * TC_BK * 2), &tma_b, bar_addr, b_row + j * 64, k_el);
+              else ptx::tma_load_2d(sb + j * (64 * TC_BK * 2), &tma_b, bfull_bar, b_row + j * 64, k_el);
+            }
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail; its results
-  // (and the weights Adam wrote) may only be touched from here on
+  // may only be touched from here on.  The successor may be scheduled once every CTA has passed this point.
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const int64_t m_tiles = (s.M + TM - 1) / TM;
   const int64_t n_tiles = (s.N + BN - 1) / BN;
@@ -270,8 +300,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       }
       int stage = 0;
       uint32_t phase = 0;
-      int64_t res_nt = -1;                 // BRES: the N tile whose weights are resident
-      uint32_t res_loads = 0;
+      int64_t res_nt = (BRES && s.b_stable) ? tile_n(work_id) : -1;     // BRES: the N tile whose weights are resident (b_stable: preloaded above)
+      uint32_t res_loads = (BRES && s.b_stable) ? 1 : 0;
       for (int64_t tile = work_id; tile < num_tiles; tile += work_stride) {
         const int64_t m_t = tile_m(tile), n_t = tile_n(tile),
                       sp = tile_sp(tile);
@@ -666,6 +696,7 @@ int tc_two_cta();         // option "tc_two_cta": use CTA pairs (cta_group::2) w
 int tc_max_stages();      // option "tc_max_stages": cap of the operand ring depth (0 = none)
 unsigned long long* tc_trace_ptr();   // option "tc_trace_ptr": device buffer of gridDim.x * 16 counters, or nullptr
 int tc_tile_prefetch();   // option "tc_tile_prefetch"
+int tc_b_stable();        // set by the train step / decode around GEMMs whose B operand is the (long since written) weight arena
 int tc_prefetch_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out);
 int tc_b_resident();      // option "tc_b_resident": keep the weight block of the CTA's N tile in shared memory where it fits
 // does this shape run as CTA pairs?  (BN = 256 tiles and more than one 128-row block of M)
@@ -721,6 +752,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   if (tc_max_stages() >= 2 && tc_max_stages() < s.stages) s.stages = tc_max_stages();
   s.reverse = tc_next_direction();
   s.trace = tc_trace_ptr();
+  s.b_stable = (BRES && tc_b_stable()) ? 1 : 0;
   s.tile_pf = (!A_MN && tc_tile_prefetch()) ? 1 : 0;
   if (epi.out) {
     const bool split_slots = Epi::kSplit && !epi_split_stride<Epi>::reduce(epi);
@@ -789,7 +821,8 @@ int gemm_tc_launch_pick(const TcOperand& A, const TcOperand& B, int64_t M, int N
   if constexpr (!A_MN && !Epi::kSplit && Epi::kAuxBytes == 0) {
     using CfgR = TcCfg<BN, Epi, CG, true>;
     const int64_t n_tiles = ceil_div64(N, BN);
-    if (tc_b_resident() && splits <= 1 && n_tiles <= tc_grid_size() / CG && CfgR::res_stages(ceil_div64(K, TC_BK)) >= 3)
+    if (tc_b_resident() && splits <= 1 && (tc_grid_size() / CG) % n_tiles == 0 && ceil_div64(M, TC_BM * CG) * n_tiles >= tc_grid_size() / CG &&
+        CfgR::res_stages(ceil_div64(K, TC_BK)) >= 3)
       return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, true>(A, B, M, N, K, splits, epi, st);
   }
   return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false>(A, B, M, N, K, splits, epi, st);

@@ -288,26 +288,30 @@ struct LossPartials {
   const float* sse; int n_sse;           // sum of squared reconstruction errors
   const float* kl; int n_kl;             // sum over elements of (1 + ls - mu^2 - e^ls)
   const float* nll[4]; const float* acc[4]; int n_ce; int n_heads;
+  int ce_stride;                         // elements between consecutive nll / acc partials (1, or the per-block record length of the fused classifier pass)
   float recon_scale;                     // 1 / (B * D * 10) for MSE/10, 1 / B for the cosine loss
   float inv_b;                           // 1 / B
   float kl_w, clf_w;
 };
 
-__global__ void finalize_losses_kernel(LossPartials lp, float* __restrict__ losses) {
+__global__ void __launch_bounds__(1024) finalize_losses_kernel(LossPartials lp, float* __restrict__ losses) {
   PSVAE_GRID_DEP();
-  // single block of 32 threads; each sum is taken in a fixed order
+  // single block of 1024 threads; each sum is taken in a fixed order (thread-strided partials, then the fixed block tree)
+  __shared__ float scratch[32];
   const int lane = threadIdx.x;
-  auto sum = [&](const float* p, int n) {
+  auto sum = [&](const float* p, int n, int stride = 1) {
     float t = 0.f;
-    for (int i = lane; i < n; i += 32) t += p[i];
-    return warp_sum(t);
+    for (int i = lane; i < n; i += 1024) t += p[(int64_t)i * stride];
+    const float r = block_sum(t, scratch);
+    __syncthreads();
+    return r;
   };
   const float sse = lp.sse ? sum(lp.sse, lp.n_sse) : 0.f;
   const float kls = lp.kl ? sum(lp.kl, lp.n_kl) : 0.f;
   float nll[4], acc[4];
   for (int h = 0; h < 4; ++h) {
-    nll[h] = (h < lp.n_heads) ? sum(lp.nll[h], lp.n_ce) : 0.f;
-    acc[h] = (h < lp.n_heads) ? sum(lp.acc[h], lp.n_ce) : 0.f;
+    nll[h] = (h < lp.n_heads) ? sum(lp.nll[h], lp.n_ce, lp.ce_stride) : 0.f;
+    acc[h] = (h < lp.n_heads) ? sum(lp.acc[h], lp.n_ce, lp.ce_stride) : 0.f;
   }
   if (lane == 0) {
     const float recon = sse * lp.recon_scale;
@@ -427,10 +431,27 @@ struct ClfFusedArgs {
   int64_t w_off[4], b_off[4];
   float gscale;                 // clf_w / (B * n_heads)
   int write_grad;
+  // fast (non-deterministic) mode: the blocks add their dW / db / nll / acc partials straight into the zeroed gradient buffer / sums[8]
+  // with atomics and the finish kernel is not launched
+  int atomic_out;
+  float* grads;
+  float* sums;
+};
+// REPARAM: the same pass over mu also does the reparameterisation (model.py:56-57) and the KL partial sums (lightning.py:115-117):
+// z = mu + exp(ls/2) * eps with eps from `eps` or the counter-based Philox stream (counter = global quad index), one read of ls, z written once
+struct ReparamArgs {
+  const float* ls;
+  const float* eps;             // optional injected noise [B][L]
+  uint64_t seed, offset;
+  int64_t first_quad;           // global index of this shard's first group of 4 latent elements (row0 * L / 4)
+  void* z;                      // [B][L] TZ
+  float* kl_part;               // one slot per block
 };
 __host__ __device__ __forceinline__ int clf_part_len(int L) { return 8 + CLF_MAXC * L + CLF_MAXC; }   // nll[4] acc[4] dW[8][L] db[8]
 
-constexpr int CLF_TILE = 256;   // rows per block pass (= threads per block)
+constexpr int CLF_TILE = 128;   // rows per block pass (= threads per block): small tiles, 4-5 blocks resident per SM -- the phases of one block
+                                // (load, row pass, gradient pass) are serial, so latency is hidden across blocks
+constexpr int CLF_ACCW = 4;     // dW elements a thread may own (total_classes * L <= CLF_ACCW * CLF_TILE)
 static inline size_t clf_fused_smem_bytes(int L) { return ((size_t)CLF_TILE * (L + 4) + (size_t)CLF_TILE * CLF_MAXC + (size_t)CLF_MAXC * L + CLF_MAXC) * sizeof(float); }
 
 // A block stages a tile of 256 rows of mu in shared memory (read once from HBM, coalesced); then
@@ -438,10 +459,11 @@ static inline size_t clf_fused_smem_bytes(int L) { return ((size_t)CLF_TILE * (L
 //   phase 3: dmu_clf[row][k] = sum_c dlogits[row][c] W[c][k] written coalesced; thread = (class, latent dim): dW[c][k] += sum_rows dlogits[row][c] mu[row][k].
 // L is a template parameter (16/32/64/128) so that the row/column index arithmetic is shifts and everything moves as float4; class
 // loops run over the classes that exist (2..3 per head), not over the CLF_MAXC slots.
-template <int L>
+template <int L, typename TZ, bool REPARAM>
 __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __restrict__ params, const float* __restrict__ mu, const int64_t* __restrict__ y,
-                                                             int64_t B, ClfFusedArgs a, float* __restrict__ dmu_clf, float* __restrict__ part) {
+                                                             int64_t B, ClfFusedArgs a, float* __restrict__ dmu_clf, float* __restrict__ part, ReparamArgs rp) {
   PSVAE_GRID_DEP();
+  float kl = 0.f;
   extern __shared__ __align__(16) float clf_smem[];
   __shared__ float scratch[32];
   constexpr int ldm = L + 4;                            // 16-byte aligned rows; row-per-lane float4 reads are conflict-free per quarter warp
@@ -461,7 +483,7 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
     if (t < a.head_classes[h]) b_s[a.head_off[h] + t] = params[a.b_off[h] + t];
   }
   float nll[4] = {0.f, 0.f, 0.f, 0.f}, acc[4] = {0.f, 0.f, 0.f, 0.f};
-  float accW[2] = {0.f, 0.f}, accb = 0.f;
+  float accW[CLF_ACCW] = {0.f, 0.f, 0.f, 0.f}, accb = 0.f;
   const int n_out = nc * L;                             // dW elements; thread t owns t and t + 256 ...
   const int n_parts = (n_out <= CLF_TILE / 2) ? CLF_TILE / n_out : 1;   // ... or, when there are few, (element, row range) pairs
   const int rows_per_part = CLF_TILE / n_parts;
@@ -477,6 +499,34 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
         const int i = base + j * CLF_TILE + t;
         v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (i < CLF_TILE * QPR && row0 + i / QPR < B) v[j] = __ldg(reinterpret_cast<const float4*>(mu + (row0 + i / QPR) * L + 4 * (i % QPR)));
+      }
+      if constexpr (REPARAM) {
+        float4 lv[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = base + j * CLF_TILE + t;
+          lv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (i < CLF_TILE * QPR && row0 + i / QPR < B) lv[j] = __ldg(reinterpret_cast<const float4*>(rp.ls + (row0 + i / QPR) * L + 4 * (i % QPR)));
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int i = base + j * CLF_TILE + t;
+          if (i < CLF_TILE * QPR && row0 + i / QPR < B) {
+            const int64_t el = (row0 + i / QPR) * L + 4 * (i % QPR);
+            float4 e;
+            if (rp.eps) e = __ldg(reinterpret_cast<const float4*>(rp.eps + el));
+            else e = philox_normal4((uint64_t)rp.first_quad + (uint64_t)(el >> 2), rp.seed, rp.offset);
+            const float m[4] = {v[j].x, v[j].y, v[j].z, v[j].w}, l[4] = {lv[j].x, lv[j].y, lv[j].z, lv[j].w}, ee[4] = {e.x, e.y, e.z, e.w};
+            float zz[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float sigma = expf(0.5f * l[q]);
+              zz[q] = fmaf(sigma, ee[q], m[q]);
+              kl += 1.f + l[q] - m[q] * m[q] - expf(l[q]);
+            }
+            store_vec<4>(static_cast<TZ*>(rp.z) + el, zz);
+          }
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -565,7 +615,7 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
         }
       } else {
 #pragma unroll
-        for (int j = 0; j < 2; ++j) {
+        for (int j = 0; j < CLF_ACCW; ++j) {
           const int o = t + j * CLF_TILE;
           if (o < n_out) {
             const int c = o / L, k = o % L;
@@ -582,6 +632,44 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
         accb += v;
       }
     }
+  }
+  if constexpr (REPARAM) {
+    const float ks = block_sum(kl, scratch);
+    if (t == 0) rp.kl_part[blockIdx.x] = ks;
+  }
+  // where one accumulated dW / db element goes in the flat gradient buffer (atomic_out)
+  auto grad_slot = [&](int c, int k) -> float* {
+    for (int h = 0; h < a.n_heads; ++h)
+      if (c >= a.head_off[h] && c < a.head_off[h] + a.head_classes[h])
+        return k >= 0 ? a.grads + a.w_off[h] + (int64_t)(c - a.head_off[h]) * L + k : a.grads + a.b_off[h] + (c - a.head_off[h]);
+    return nullptr;
+  };
+  if (a.atomic_out) {
+    for (int h = 0; h < 4; ++h) {
+      const float s1 = block_sum(nll[h], scratch);
+      const float s2 = block_sum(acc[h], scratch);
+      if (t == 0) { part[(int64_t)blockIdx.x * PART + h] = s1; part[(int64_t)blockIdx.x * PART + 4 + h] = s2; }   // losses stay order-fixed: summed by finalize_losses
+    }
+    if (!a.write_grad) return;
+    if (n_parts > 1) {
+      __syncthreads();
+      float* comb = clf_smem;
+      if (t < n_parts * n_out) comb[(t / n_out) * n_out + t % n_out] = accW[0];
+      __syncthreads();
+      if (t < n_out) {
+        float v = 0.f;
+        for (int p = 0; p < n_parts; ++p) v += comb[p * n_out + t];
+        atomicAdd(grad_slot(t / L, t % L), v);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CLF_ACCW; ++j) {
+        const int o = t + j * CLF_TILE;
+        if (o < n_out) atomicAdd(grad_slot(o / L, o % L), accW[j]);
+      }
+    }
+    if (t < nc) atomicAdd(grad_slot(t, -1), accb);
+    return;
   }
   float* mine = part + (int64_t)blockIdx.x * PART;
   for (int h = 0; h < 4; ++h) {
@@ -601,7 +689,8 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
       mine[8 + t] = v;
     }
   } else {
-    for (int j = 0; j < 2; ++j) {
+#pragma unroll
+    for (int j = 0; j < CLF_ACCW; ++j) {
       const int o = t + j * CLF_TILE;
       if (o < n_out) mine[8 + o] = accW[j];    // same thread wrote the zero above: program order
     }

@@ -109,6 +109,12 @@ int tc_two_cta() { return (int)g_opt.tc_two_cta; }
 int tc_max_stages() { return (int)g_opt.tc_max_stages; }
 int tc_b_resident() { return (int)g_opt.tc_b_resident; }
 bool pdl_enabled() { return g_opt.pdl != 0; }
+static thread_local int g_b_stable = 0;
+int tc_b_stable() { return g_b_stable && g_opt.pdl != 0; }
+struct StableWeights {        // RAII: GEMMs launched in this scope read weights that no kernel of the last two launches wrote
+  StableWeights() { g_b_stable = 1; }
+  ~StableWeights() { g_b_stable = 0; }
+};
 int tc_tile_prefetch() { return (int)g_opt.tc_tile_prefetch; }
 unsigned long long* tc_trace_ptr() { return reinterpret_cast<unsigned long long*>(static_cast<uintptr_t>(g_opt.tc_trace_ptr)); }
 static thread_local unsigned g_dir = 0;
@@ -386,11 +392,11 @@ static bool clf_fused_ok(const psvae_model_desc* d) {
   if (d->latent_dim != 16 && d->latent_dim != 32 && d->latent_dim != 64 && d->latent_dim != 128) return false;   // kernel instantiations
   int total = 0;
   for (int h = 0; h < d->clf_num_heads; ++h) total += d->clf_head_classes[h];
-  return total <= CLF_MAXC && total * d->latent_dim <= 2 * CLF_TILE;
+  return total <= CLF_MAXC && total * d->latent_dim <= CLF_ACCW * CLF_TILE;
 }
 static int clf_fused_blocks(int64_t rows) {
   int64_t b = ceil_div64(rows, CLF_TILE);
-  if (b > 2 * PSVAE_NUM_SMS) b = 2 * PSVAE_NUM_SMS;
+  if (b > 4 * PSVAE_NUM_SMS) b = 4 * PSVAE_NUM_SMS;
   return b < 1 ? 1 : (int)b;
 }
 static bool latent_cs_ok(int L) { return L % 4 == 0 && 256 % (L / 4) == 0 && 2 * L <= 256; }
@@ -641,6 +647,7 @@ static int decoder_forward(const Net& n, const TAct* Wt, const float* params, co
 template <typename TAct>
 static int run_step(const StepArgs& a) {
   PSVAE_TRY(tc_device_check());
+  StableWeights stable_weights;      // every GEMM below has at least one kernel between it and the last writer of the weights (Adam)
   const psvae_model_desc* d = a.d;
   Net n(d);
   const int64_t B = a.rows;
@@ -697,17 +704,19 @@ static int run_step(const StepArgs& a) {
     EpiBiasAct<float, ACT_NONE> e{P + d->enc_b[n.nh] + s * n.L, s == 0 ? mu : ls, n.L, nullptr};
     PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(w.he[n.nh - 1] + s * n.H, 2 * n.H, Wt + d->enc_w[n.nh] + (int64_t)s * n.L * n.H, n.H, B, n.L, n.H, 1, true, e, st)));
   }
-  // ---- reparameterisation + KL partial sums (model.py:56-57, lightning.py:115-117)
-  launch_dep(latent_fwd_kernel<TAct>, dim3((unsigned)w.n_kl), dim3(256), 0, st, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, w.z, nullptr, w.kl_part);
-  count_launch();
-  PSVAE_LAUNCH_CHECK("latent_fwd_kernel");
-
-  // ---- latent classifier on mu (lightning.py:73-83), fp32 on the CUDA cores (C is 2..3)
+  // ---- reparameterisation + KL partial sums (model.py:56-57, lightning.py:115-117) and the latent classifier on mu (lightning.py:73-83,
+  //      fp32 on the CUDA cores: C is 2..3).  With linear heads both happen in ONE pass over mu / log_sigma (clf_fused_kernel<REPARAM>).
   const int feat_dim = n.clf_feat();
   const float* feat = mu;
   const bool clf_fused = n.has_clf() && clf_fused_ok(d);
-  if (n.has_clf() && a.want_loss && clf_fused) {
-    // one pass over mu: logits, CE, accuracy, dlogits, dmu_clf and the classifier's own weight/bias gradients
+  const bool fuse_latent = clf_fused && a.want_loss;
+  int n_kl_used = (int)w.n_kl;
+  if (!fuse_latent) {
+    launch_dep(latent_fwd_kernel<TAct>, dim3((unsigned)w.n_kl), dim3(256), 0, st, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, w.z, nullptr, w.kl_part);
+    count_launch();
+    PSVAE_LAUNCH_CHECK("latent_fwd_kernel");
+  } else {
+    // one pass: z, KL partials, logits, CE, accuracy, dlogits, dmu_clf and the classifier's own weight/bias gradients
     ClfFusedArgs ca;
     memset(&ca, 0, sizeof(ca));
     ca.n_heads = d->clf_num_heads;
@@ -720,33 +729,37 @@ static int run_step(const StepArgs& a) {
     }
     ca.gscale = a.clf_w / ((float)B * (float)d->clf_num_heads);
     ca.write_grad = a.want_grads;
+    ca.atomic_out = g_opt.deterministic ? 0 : 1;
+    ca.grads = a.want_grads ? a.grads : nullptr;
+    ca.sums = w.clf_sums;
     const int blocks = clf_fused_blocks(B);
     const size_t smem = clf_fused_smem_bytes(n.L);
     float* dmu_out = a.want_grads ? w.dmu_clf : nullptr;
+    ReparamArgs rp{ls, a.eps, a.seed, a.offset, first_elem >> 2, w.z, w.kl_part};
+    n_kl_used = blocks;
     switch (n.L) {
-      case 16:
-        PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        launch_dep(clf_fused_kernel<16>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part);
+#define PSVAE_CLF_CASE(LL)                                                                                                              \
+      case LL:                                                                                                                          \
+        PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<LL, TAct, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+        launch_dep(clf_fused_kernel<LL, TAct, true>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part, rp); \
         break;
-      case 32:
-        PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        launch_dep(clf_fused_kernel<32>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part);
-        break;
-      case 64:
-        PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        launch_dep(clf_fused_kernel<64>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part);
-        break;
+      PSVAE_CLF_CASE(16)
+      PSVAE_CLF_CASE(32)
+      PSVAE_CLF_CASE(64)
       default:
-        PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        launch_dep(clf_fused_kernel<128>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part);
-        break;
+      PSVAE_CLF_CASE(128)
+#undef PSVAE_CLF_CASE
     }
     count_launch();
     PSVAE_LAUNCH_CHECK("clf_fused_kernel");
-    launch_dep(clf_fused_finish_kernel, dim3((unsigned)ceil_div64(clf_part_len(n.L), 32)), dim3(1024), 0, st, w.clf_part, blocks, n.L, ca, w.clf_sums,
+    if (!ca.atomic_out) {
+      launch_dep(clf_fused_finish_kernel, dim3((unsigned)ceil_div64(clf_part_len(n.L), 32)), dim3(1024), 0, st, w.clf_part, blocks, n.L, ca, w.clf_sums,
                                                                                              a.want_grads ? a.grads : nullptr);
-    count_launch();
-    PSVAE_LAUNCH_CHECK("clf_fused_finish_kernel");
+      count_launch();
+      PSVAE_LAUNCH_CHECK("clf_fused_finish_kernel");
+    }
+  }
+  if (fuse_latent) {
   } else if (n.has_clf() && a.want_loss) {
     for (int t = 0; t < d->clf_num_trunk; ++t) {
       PSVAE_TRY(clf_linear(d->clf_activation, feat, t == 0 ? n.L : d->clf_hidden, P + d->clf_trunk_w[t], P + d->clf_trunk_b[t], w.clf_act[t], B,
@@ -804,17 +817,19 @@ static int run_step(const StepArgs& a) {
     LossPartials lp;
     memset(&lp, 0, sizeof(lp));
     lp.sse = w.sse_part; lp.n_sse = n_sse_used;
-    lp.kl = w.kl_part; lp.n_kl = (int)w.n_kl;
-    lp.n_ce = clf_fused ? 1 : (int)w.n_ce;
+    lp.kl = w.kl_part; lp.n_kl = n_kl_used;
+    const bool ce_from_blocks = clf_fused && !g_opt.deterministic;     // fused pass, fast mode: one (nll, acc) record per block
+    lp.n_ce = clf_fused ? (ce_from_blocks ? clf_fused_blocks(B) : 1) : (int)w.n_ce;
+    lp.ce_stride = ce_from_blocks ? clf_part_len(n.L) : 1;
     lp.n_heads = n.has_clf() ? d->clf_num_heads : 0;
     for (int h = 0; h < lp.n_heads; ++h) {
-      lp.nll[h] = clf_fused ? w.clf_sums + h : w.nll_part[h];
-      lp.acc[h] = clf_fused ? w.clf_sums + 4 + h : w.acc_part[h];
+      lp.nll[h] = clf_fused ? (ce_from_blocks ? w.clf_part + h : w.clf_sums + h) : w.nll_part[h];
+      lp.acc[h] = clf_fused ? (ce_from_blocks ? w.clf_part + 4 + h : w.clf_sums + 4 + h) : w.acc_part[h];
     }
     lp.recon_scale = a.use_cos ? 1.f / (float)B : 1.f / ((float)B * (float)n.D * 10.f);
     lp.inv_b = 1.f / (float)B;
     lp.kl_w = a.kl_w; lp.clf_w = a.clf_w;
-    launch_dep(finalize_losses_kernel, dim3(1), dim3(32), 0, st, lp, a.losses);
+    launch_dep(finalize_losses_kernel, dim3(1), dim3(1024), 0, st, lp, a.losses);
     count_launch();
     PSVAE_LAUNCH_CHECK("finalize_losses_kernel");
   }
@@ -937,6 +952,7 @@ template <typename TAct>
 static int run_decode(const psvae_model_desc* d, const float* params, const bf16* shadow, const float* z, uint64_t seed, uint64_t offset, int64_t row0,
                       int64_t rows, float* x_hat, float* z_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
   PSVAE_TRY(tc_device_check());
+  StableWeights stable_weights;      // the Philox / cast kernel of each chunk sits between the weights' last writer and the first GEMM
   Net n(d);
   if (rows <= 0) { set_error("rows=%lld must be positive", (long long)rows); return -2; }
   if (!params || !x_hat) { set_error("params and x_hat must not be NULL"); return -1; }
