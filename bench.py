@@ -293,7 +293,10 @@ def main():
     value = B * n_gpus * K / (ms * 1e-3)
     tflops = value * FLOPS_PER_SAMPLE / 1e12
     peak = peaks["bf16_sustained"] * n_gpus
-    roofline = dict(bound="tensor", achieved=tflops, peak=peak, unit="TFLOP/s", frac=tflops / peak, traffic=None,
+    # dram__bytes_read.sum + dram__bytes_write.sum over the 29 launches of one step, from the ncu pass of this same command
+    # (profiles/r01_launches_v11_time_dram.csv: 1.961 GB read + 0.261 GB written at B = 65,536, bf16, one GPU); null for any other config
+    traffic = 2_222_543_104 if (B == 65536 and args.precision == "bf16" and not args.opt) else None
+    roofline = dict(bound="tensor", achieved=tflops, peak=peak, unit="TFLOP/s", frac=tflops / peak, traffic=traffic,
                     note=f"whole fused step (all launches): {FLOPS_PER_SAMPLE} algorithmic FLOP/sample x {B * n_gpus} samples / measured step time; "
                          f"peak = sustained bf16 {peaks['source']}" + ("" if args.precision == "bf16" else " [fp32 parity mode runs on CUDA cores]"))
 
