@@ -20,6 +20,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <type_traits>
@@ -102,7 +104,10 @@ template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
   else return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));                      // SWIZZLE_64B:  addr[4:5] ^= addr[7:8]
 }
 
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES>
+// CL = 2 (only with CG = 2, K-major A, streaming B): clusters of two CTA pairs that work on the same row tile and adjacent N tiles; every CTA
+// loads HALF of its 128 activation rows per k-block and multicasts them to its twin in the other pair, so the activation tile crosses the
+// L2 -> SM fabric once per cluster instead of once per pair (-25 % operand traffic per pair, ring depth unchanged).
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL>
 __global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
                const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_apf, TcShape s, Epi epi) {
@@ -134,7 +139,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (s.trace != nullptr && threadIdx.x == 0) s.trace[(size_t)blockIdx.x * 16 + 12] = ptx::globaltimer_ns();      // kernel entry
-  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;    // cluster dims (2,1,1): rank = blockIdx.x & 1
+  static_assert(CL == 1 || (CL == 2 && CG == 2 && !A_MN && !BRES), "pair clusters: CTA pairs, K-major A, streaming B");
+  const uint32_t crank = CG == 2 ? ptx::cluster_ctarank() : 0u;       // cluster dims (2 * CL,1,1): rank = blockIdx.x % (2 * CL)
+  const uint32_t cta_rank = crank & 1u;                                // rank inside the CTA pair
+  const uint32_t pidx = crank >> 1;                                    // pair inside the cluster (CL = 2)
+  const uint32_t lead_rank = crank & ~1u;                              // cluster rank of this pair's leader
   const bool leader = cta_rank == 0;
   const int64_t work_id = CG == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
   const int64_t work_stride = CG == 2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
@@ -146,7 +155,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if constexpr (kAux) ptx::prefetch_tensormap(&tma_aux);
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], 1);
+      ptx::mbar_init(&empty_bar[i], CL);                   // CL = 2: both pairs' MMAs must have released the stage (the twin writes into it)
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
@@ -180,7 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int64_t kbt = (s.K + TC_BK - 1) / TC_BK;
       if (ptx::elect_one()) {
         const int32_t b_row = (int32_t)((w0 % n_tiles0) * BN) + (int32_t)cta_rank * (BN / CG);
-        const uint32_t bar_addr = CG == 2 ? ptx::mapa_u32(ptx::smem_u32(bfull_bar), 0) : 0u;
+        const uint32_t bar_addr = CG == 2 ? ptx::mapa_u32(ptx::smem_u32(bfull_bar), lead_rank) : 0u;
         if (leader) ptx::mbar_arrive_expect_tx(bfull_bar, (uint32_t)kbt * Cfg::kBBytes * CG);
         for (int64_t kb = 0; kb < kbt; ++kb) {
           uint8_t* sb = sres + kb * Cfg::kBBytes;
@@ -242,7 +251,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       auto fetch = [&](int64_t m_t, int64_t n_t, int64_t kb, uint8_t* sa, uint8_t* sb, uint64_t* bar, bool want_a, bool want_b) {
         const int32_t k_el = (int32_t)(kb * TC_BK);
         // CG = 2: the bytes of BOTH CTAs are counted on the leader's barrier (only the leader issues MMAs)
-        const uint32_t bar_addr = (CG == 2 && bar) ? ptx::mapa_u32(ptx::smem_u32(bar), 0) : 0u;
+        const uint32_t bar_addr = (CG == 2 && bar) ? ptx::mapa_u32(ptx::smem_u32(bar), lead_rank) : 0u;
         const int32_t a_row = (int32_t)(m_t * TM) + (int32_t)cta_rank * TC_BM;          // this CTA's 128 rows of the tile
         const int32_t b_row = (int32_t)(n_t * BN) + (int32_t)cta_rank * (BN / CG);        // this CTA's share of the B tile
         auto ld = [&](void* d, const CUtensorMap* m, int32_t c0, int32_t c1) {
@@ -250,7 +259,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           else ptx::tma_load_2d(d, m, bar, c0, c1);
         };
         if (want_a) {
-          if constexpr (!A_MN) {
+          if constexpr (CL == 2) {
+            // this CTA's half (64 rows) of the pair-rank's 128 rows, delivered to itself and to its twin in the other pair
+            if (sa) ptx::tma_load_2d_cg2_mc(sa + pidx * (64 * TC_BK * 2), &tma_a, bar_addr, k_el, a_row + (int32_t)pidx * 64,
+                                            (uint16_t)((1u << cta_rank) | (1u << (cta_rank + 2))));
+            else ptx::tma_prefetch_2d(&tma_a, k_el, a_row + (int32_t)pidx * 64);
+          } else if constexpr (!A_MN) {
             if (sa) ld(sa, &tma_a, k_el, a_row);
             else ptx::tma_prefetch_2d(&tma_a, k_el, a_row);
           } else {
@@ -365,7 +379,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           if (n_t != res_nt) {
             if (res_loads > 0) {           // hand the old block back once everything issued so far has retired
               if (ptx::elect_one()) {
-                if constexpr (CG == 2) ptx::umma_commit_cg2_mc(bempty_bar, (uint16_t)3);
+                if constexpr (CG == 2) ptx::umma_commit_cg2_mc(bempty_bar, (uint16_t)(3u << lead_rank));
                 else ptx::umma_commit(bempty_bar);
               }
               __syncwarp();
@@ -394,14 +408,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               else ptx::umma_f16(tmem_d, da, db, idesc, accum);
             }
             // smem slot free (in both CTAs of a pair) once these MMAs retire
-            if constexpr (CG == 2) ptx::umma_commit_cg2_mc(&empty_bar[stage], (uint16_t)3);
+            if constexpr (CG == 2) ptx::umma_commit_cg2_mc(&empty_bar[stage], (uint16_t)(CL == 2 ? 0xF : 3));
             else ptx::umma_commit(&empty_bar[stage]);
           }
           __syncwarp();
           if (++stage == s.stages) { stage = 0; phase ^= 1; }
         }
         if (ptx::elect_one()) {                   // accumulator complete (also for an empty K range: the epilogue then sees zeros)
-          if constexpr (CG == 2) ptx::umma_commit_cg2_mc(&tfull_bar[acc], (uint16_t)3);
+          if constexpr (CG == 2) ptx::umma_commit_cg2_mc(&tfull_bar[acc], (uint16_t)(3u << lead_rank));
           else ptx::umma_commit(&tfull_bar[acc]);
         }
         __syncwarp();
@@ -525,13 +539,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               aux[j * 4] = u.x; aux[j * 4 + 1] = u.y; aux[j * 4 + 2] = u.z; aux[j * 4 + 3] = u.w;
             }
           }
-          __syncwarp();                      // every lane has read the block: it may be overwritten
+        }
+        epi.tc_transform(row, col, s.N, valid, v, aux, pre[c], red);
+        if constexpr (kAux) {
+          // The staged auxiliary block may be overwritten by the next TMA load only once every lane HOLDS its values: issuing the loads from
+          // shared memory is not enough (the last 16-byte chunk of a row was occasionally still in the LSU queue when the next block landed --
+          // 32 x 4 wrong targets in one tile of a cold run).  `red` depends on every auxiliary value a lane uses, so pinning it here keeps the
+          // consuming FMAs -- which cannot issue before their operands have arrived -- ahead of the TMA instruction in program order.
+          static_assert(Epi::kReduce, "the release of the auxiliary block is ordered through the functor's reduction value");
+          asm volatile("" ::"f"(red) : "memory");
+          __syncwarp();
           if (col + 32 < s.N && c + 1 < CH && lane == 0) {
             ptx::mbar_arrive_expect_tx(&aux_bar[ew], Epi::kAuxBytes);
             ptx::tma_load_2d(abuf, &tma_aux, &aux_bar[ew], col + 32, row_base);
           }
         }
-        epi.tc_transform(row, col, s.N, valid, v, aux, pre[c], red);
         if (do_store) {
           if constexpr (Epi::kColSum) {      // rows past M must not reach the column sums
             if (!valid) {
@@ -618,7 +640,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if constexpr (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty_bar[acc]), 0));
+        if constexpr (CG == 2) ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&tempty_bar[acc]), lead_rank));
         else ptx::mbar_arrive(&tempty_bar[acc]);
       }
     }
@@ -696,6 +718,7 @@ int tc_two_cta();         // option "tc_two_cta": use CTA pairs (cta_group::2) w
 int tc_max_stages();      // option "tc_max_stages": cap of the operand ring depth (0 = none)
 unsigned long long* tc_trace_ptr();   // option "tc_trace_ptr": device buffer of gridDim.x * 16 counters, or nullptr
 int tc_tile_prefetch();   // option "tc_tile_prefetch"
+int tc_pair_cluster();    // option "tc_pair_cluster": clusters of two CTA pairs with the activation tile multicast between them
 int tc_b_stable();        // set by the train step / decode around GEMMs whose B operand is the (long since written) weight arena
 int tc_prefetch_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out);
 int tc_b_resident();      // option "tc_b_resident": keep the weight block of the CTA's N tile in shared memory where it fits
@@ -732,12 +755,12 @@ template <class Epi> struct epi_split_stride<Epi, std::enable_if_t<Epi::kSplit>>
 template <class Epi, class = void> struct epi_cs_atomic { static bool get(const Epi&) { return false; } };
 template <class Epi> struct epi_cs_atomic<Epi, std::enable_if_t<Epi::kColSum>> { static bool get(const Epi& e) { return e.colsum_atomic != 0; } };
 
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false, int CL = 1>
 int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st) {
   using Cfg = TcCfg<BN, Epi, CG, BRES>;
   using TOut = typename Epi::TOut;
   CUtensorMap ta, tb, tout, taux, tapf;
-  PSVAE_TRY(tc_tensor_map(A, K, A_MN ? TC_BK : TC_BM, &ta));
+  PSVAE_TRY(tc_tensor_map(A, K, A_MN ? TC_BK : TC_BM / CL, &ta));      // CL = 2: every CTA loads (and multicasts) half of its 128 rows
   tapf = ta;
   if constexpr (!A_MN) {
     if (tc_tile_prefetch()) PSVAE_TRY(tc_prefetch_map(A, K, TC_BM, &tapf));
@@ -766,7 +789,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   } else {
     taux = ta;
   }
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, BRES>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, BRES, CL>;
   static unsigned long long attr_mask = 0;   // per instantiation, one bit per device
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
@@ -780,6 +803,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   const int64_t cs_rows = (tiles < grid ? tiles : (int64_t)grid) * CG * 4;     // = 4 * tc_ctas(): what the caller's ordered reduce reads
   if (BRES) grid = (int)((grid / n_tiles) * n_tiles);     // every CTA (pair) keeps one N tile: its weight block is loaded once
   if (tiles < grid) grid = (int)tiles;
+  grid = grid / CL * CL;                     // whole clusters of CL pairs (the caller guarantees an even tile count for CL = 2)
   grid *= CG;
   if (grid < 1) return 0;
   if constexpr (Epi::kColSum) {
@@ -797,7 +821,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
     int na = 0;
     if constexpr (CG == 2) {
       at[na].id = cudaLaunchAttributeClusterDimension;
-      at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+      at[na].val.clusterDim.x = 2 * CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
       ++na;
     }
     if (pdl_enabled()) {
@@ -807,6 +831,21 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
     }
     cfg.attrs = at;
     cfg.numAttrs = na;
+    if constexpr (CL == 2) {
+      // clusters of 4 must sit inside one GPC: fewer of them are co-resident than 148 / 4.  A persistent grid larger than that would run
+      // in two waves, so it is cut to what fits (queried once per instantiation and device).
+      static int max_clusters[64] = {0};
+      if (max_clusters[dev & 63] == 0) {
+        int nc = 0;
+        cudaLaunchConfig_t q = cfg;
+        q.numAttrs = CG == 2 ? 1 : 0;       // the cluster dimension only
+        PSVAE_CUDA(cudaOccupancyMaxActiveClusters(&nc, kern, &q));
+        max_clusters[dev & 63] = nc > 0 ? nc : 1;
+        if (getenv("PSVAE_DEBUG")) fprintf(stderr, "psvae: %d clusters of %d CTAs co-resident (BN=%d)\n", nc, 2 * CL, BN);
+      }
+      const int fit = max_clusters[dev & 63] * 2 * CL;
+      if (grid > fit) cfg.gridDim = dim3((unsigned)fit);
+    }
     PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, tapf, s, epi));
   }
   count_launch();
@@ -824,6 +863,12 @@ int gemm_tc_launch_pick(const TcOperand& A, const TcOperand& B, int64_t M, int N
     if (tc_b_resident() && splits <= 1 && (tc_grid_size() / CG) % n_tiles == 0 && ceil_div64(M, TC_BM * CG) * n_tiles >= tc_grid_size() / CG &&
         CfgR::res_stages(ceil_div64(K, TC_BK)) >= 3)
       return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, true>(A, B, M, N, K, splits, epi, st);
+  }
+  if constexpr (!A_MN && CG == 2) {
+    // clusters of two pairs sharing the activation tile: an even number of N tiles, whole clusters, and enough tiles to fill the grid
+    const int64_t n_tiles = ceil_div64(N, BN), m_tiles = ceil_div64(M, TC_BM * CG);
+    if (tc_pair_cluster() && splits <= 1 && n_tiles % 2 == 0 && (tc_grid_size() / CG) % 2 == 0 && m_tiles * n_tiles >= 2)
+      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 2>(A, B, M, N, K, splits, epi, st);
   }
   return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false>(A, B, M, N, K, splits, epi, st);
 }

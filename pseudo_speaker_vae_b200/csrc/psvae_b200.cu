@@ -61,6 +61,8 @@ struct Options {
   int64_t langevin_generic = 0;        // tests: force the generic (tile-in-smem) Langevin kernel even where the thread-per-sample one applies
   int64_t tc_b_resident = 0;           // 1: forward / dgrad GEMMs keep the weight block of their N tile resident in shared memory (where it fits)
   int64_t tc_tile_prefetch = 0;        // 1: the producer pulls the NEXT tile's whole activation panel into L2 with wide-box prefetches at the start of each tile
+  int64_t tc_pair_cluster = 0;         // 1: forward / dgrad GEMMs with an even number of N tiles run as clusters of two CTA pairs (activation tile multicast).
+                                       //    Measured: +7 % per SM, but only 33 clusters of 4 are co-resident (132 of 148 SMs) -> 39.3 vs 37.4 us; off by default
   int64_t pdl = 1;                     // 1: kernels are launched with programmatic stream serialization (their prologue overlaps the predecessor's tail)
   int64_t tc_trace_ptr = 0;            // profiling: device pointer of gridDim.x * 16 cycle counters the GEMM kernels fill (0 = off)
   int64_t tc_max_stages = 0;           // experiments: cap the depth of the operand ring (0 = what fits)
@@ -109,6 +111,7 @@ int tc_two_cta() { return (int)g_opt.tc_two_cta; }
 int tc_max_stages() { return (int)g_opt.tc_max_stages; }
 int tc_b_resident() { return (int)g_opt.tc_b_resident; }
 bool pdl_enabled() { return g_opt.pdl != 0; }
+int tc_pair_cluster() { return (int)g_opt.tc_pair_cluster; }
 static thread_local int g_b_stable = 0;
 int tc_b_stable() { return g_b_stable && g_opt.pdl != 0; }
 struct StableWeights {        // RAII: GEMMs launched in this scope read weights that no kernel of the last two launches wrote
@@ -1051,6 +1054,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_b_resident")) { g_opt.tc_b_resident = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_trace_ptr")) { g_opt.tc_trace_ptr = value; return 0; }
   if (!strcmp(name, "pdl")) { g_opt.pdl = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_pair_cluster")) { g_opt.tc_pair_cluster = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
   return -2;
@@ -1070,6 +1074,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_max_stages")) return g_opt.tc_max_stages;
   if (!strcmp(name, "tc_b_resident")) return g_opt.tc_b_resident;
   if (!strcmp(name, "pdl")) return g_opt.pdl;
+  if (!strcmp(name, "tc_pair_cluster")) return g_opt.tc_pair_cluster;
   if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;
 }

@@ -582,6 +582,46 @@ def test_deterministic_option_and_fast_mode_agree():
         G.L.set_option("deterministic", 0)
 
 
+@pytest.mark.parametrize("opts", [dict(tc_pair_cluster=1), dict(tc_b_resident=1), dict(tc_b_resident=1, tc_tile_prefetch=1), dict(pdl=0),
+                                  dict(tc_two_cta=0), dict(tc_max_stages=2)])
+def test_engine_variants_reproduce_the_default_path(opts):
+    """The tuning variants of the tcgen05 engine (clusters of two CTA pairs with the activation tile multicast, weight block resident in
+    shared memory, next-tile L2 prefetch, no programmatic dependent launch, 1-CTA tiles, a 2-deep ring) change the schedule, not the
+    arithmetic: in deterministic mode the forward outputs must be bit-identical to the default configuration and the losses / gradients
+    identical up to the order of the per-CTA partial sums, at a batch with ragged tiles."""
+    G = _gu()
+    module, cfg = _big_module(G, "bf16")
+    hot = module.hot_path
+    B = 8192 + 77
+    x, y, eps = O.synth_batch(B, 256, 64, 2, seed=78)
+    xt, yt, et = torch.from_numpy(x).to(G.DEV), torch.from_numpy(y).to(G.DEV), torch.from_numpy(eps).to(G.DEV)
+    defaults = {k: G.L.get_option(k) for k in opts}
+
+    def run():
+        g = torch.empty(hot.arena.numel, device=G.DEV)
+        losses, _, outs = hot.step(xt, yt, et, grads=g, want_outputs=True)
+        torch.cuda.synchronize()
+        return g, losses, outs
+
+    try:
+        G.L.set_option("deterministic", 1)
+        g0, l0, o0 = run()
+        for k, v in opts.items():
+            G.L.set_option(k, v)
+        g1, l1, o1 = run()
+        assert all(torch.equal(a, b) for a, b in zip(o0, o1))           # forward outputs: element-wise identical arithmetic
+        same_mapping = set(opts) <= {"pdl", "tc_max_stages"}            # same tile -> CTA mapping: same partial-sum order everywhere
+        if same_mapping:
+            assert torch.equal(l0, l1) and torch.equal(g0, g1)
+        else:       # per-CTA loss / bias partials are grouped differently: fp32 summation order only
+            assert torch.allclose(l0, l1, rtol=2e-6, atol=1e-7)
+            assert ((g1.double() - g0.double()).norm() / g0.double().norm()).item() <= 2e-6
+    finally:
+        G.L.set_option("deterministic", 0)
+        for k, v in defaults.items():
+            G.L.set_option(k, v)
+
+
 def test_langevin_fast_kernel_matches_generic_kernel():
     """Linear heads on z take the thread-per-sample kernel; it must reproduce the generic tile kernel (same Philox counters)."""
     G = _gu()
