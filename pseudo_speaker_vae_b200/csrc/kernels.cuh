@@ -734,7 +734,10 @@ template <typename TAct>
 __global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
                                                             const float* __restrict__ eps, uint64_t seed, uint64_t offset, int64_t first_elem,
                                                             int64_t n_elems, int L, const float* __restrict__ dmu_clf, float kl_over_b,
-                                                            TAct* __restrict__ dmu, TAct* __restrict__ dls, float* __restrict__ partials) {
+                                                            TAct* __restrict__ dmu, TAct* __restrict__ dls, float* __restrict__ partials,
+                                                            float* __restrict__ bias_grad) {
+  // bias_grad != nullptr (fast mode): the block's 2L column sums are added straight into the zeroed [mu | sigma] bias gradient with atomics;
+  // otherwise one partial row per block for the ordered reduce
   PSVAE_GRID_DEP();
   extern __shared__ float lb_smem[];        // [256][8]
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -771,7 +774,8 @@ __global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restr
     const int which = threadIdx.x / L, col = threadIdx.x % L, quad = col >> 2, j = col & 3;
     float t = 0.f;
     for (int th = quad; th < 256; th += qpr) t += lb_smem[th * 8 + which * 4 + j];
-    partials[(int64_t)blockIdx.x * 2 * L + threadIdx.x] = t;
+    if (bias_grad) atomicAdd(bias_grad + threadIdx.x, t);
+    else partials[(int64_t)blockIdx.x * 2 * L + threadIdx.x] = t;
   }
 }
 

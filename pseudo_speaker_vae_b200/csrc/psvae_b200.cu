@@ -900,12 +900,13 @@ static int run_step(const StepArgs& a) {
   bool last_bias_done = false;
   if (latent_cs_ok(n.L)) {
     int blocks = ew_grid(B * n.L / 4);
-    if (blocks > 2 * PSVAE_NUM_SMS) blocks = 2 * PSVAE_NUM_SMS;
+    if (blocks > 4 * PSVAE_NUM_SMS) blocks = 4 * PSVAE_NUM_SMS;
+    float* bias_atomic = g_opt.deterministic ? nullptr : G + d->enc_b[n.nh];      // fast mode: atomics into the zeroed gradient, no reduce launch
     launch_dep(latent_bwd_cs_kernel<TAct>, dim3(blocks), dim3(256), 256 * 8 * sizeof(float), st, w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, n.L, dmu_clf,
-                                                                             a.kl_w / (float)B, w.dmu, w.dls, w.cpart);
+                                                                             a.kl_w / (float)B, w.dmu, w.dls, w.cpart, bias_atomic);
     count_launch();
     PSVAE_LAUNCH_CHECK("latent_bwd_cs_kernel");
-    PSVAE_TRY(launch_reduce(w.cpart, 2 * n.L, blocks, G + d->enc_b[n.nh], st));
+    if (!bias_atomic) PSVAE_TRY(launch_reduce(w.cpart, 2 * n.L, blocks, G + d->enc_b[n.nh], st));
     last_bias_done = true;
   } else {
     launch_dep(latent_bwd_kernel<TAct>, dim3(ew_grid(B * n.L / 4)), dim3(256), 0, st, w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, dmu_clf, a.kl_w / (float)B,
