@@ -492,6 +492,41 @@ def test_widened_config5_small_batch_vs_oracle():
         assert max(errs.values()) <= tg, (precision, {k: f"{v:.1e}" for k, v in errs.items()})
 
 
+@pytest.mark.parametrize("heads", [{"age": 3, "gender": 2}, {"a": 3, "b": 3, "c": 2}, {"gender": 3}])
+def test_multi_head_linear_classifier_train_step_vs_oracle(heads):
+    """Linear heads directly on mu (latent_classifier.py:42-56 with num_layers = 1) go through the fused reparam + classifier pass; with 5
+    and 8 classes in total a thread owns several dW elements (CLF_ACCW).  CE is the mean over heads (the reference's own multi-label
+    Lightning branch is broken; this is the oracle's documented reading).  Fast (atomic) and deterministic mode both."""
+    G = _gu()
+    single = len(heads) == 1
+    nc = list(heads.values())[0] if single else heads
+    cfg = dict(D=256, L=64, wseed=11, clf=dict(input_dim=64, num_classes=nc))
+    shapes = O.vae_param_shapes(256, 64) + O.classifier_param_shapes(64, nc)
+    params = {k: v.astype(np.float32) for k, v in O.synth_params(shapes, seed=11, dtype=np.float64).items()}
+    B = 1000
+    x, y, eps = O.synth_batch(B, 256, 64, nc, seed=5)
+    scal, out, grads = O.train_loss_and_grads({k: v.astype(np.float64) for k, v in params.items()}, x.astype(np.float64), y, eps.astype(np.float64))
+    for det in (0, 1):
+        try:
+            G.L.set_option("deterministic", det)
+            for precision, tl, tg in (("fp32", FP32_TOL, FP32_FLIP_TOL), ("bf16", BF16_LOSS_TOL, BF16_GRAD_TOL_SMALL)):
+                module = G.module_from_cfg(cfg, precision, params=params)
+                hot = module.hot_path
+                g = torch.empty(hot.arena.numel, device=G.DEV)
+                yt = G.labels_to_torch(y)                          # {label: tensor} for several heads: packed [heads][B] by HotPath.pack_labels
+                losses, _, _ = hot.step(torch.from_numpy(x).to(G.DEV), yt, torch.from_numpy(eps).to(G.DEV), grads=g)
+                lt = losses.cpu().numpy()
+                assert abs(lt[0] - float(scal["loss"])) <= tl * max(1, abs(float(scal["loss"]))), (precision, det)
+                assert abs(lt[3] - float(scal["classifier_loss"])) <= tl, (precision, det)
+                gd = G.flat_to_dict(module, g)
+                errs = {k: rel_err(gd[k], grads[k]) for k in grads}
+                assert max(errs.values()) <= tg, (precision, det, {k: f"{v:.1e}" for k, v in errs.items()})
+                if precision == "fp32":
+                    assert all(v <= FP32_TOL for k, v in errs.items() if "classifier" in k), {k: f"{v:.1e}" for k, v in errs.items()}
+        finally:
+            G.L.set_option("deterministic", 0)
+
+
 def test_ragged_and_tiny_batches():
     """B = 1, odd B, B not a multiple of any tile: the edge cases of the row dimension."""
     G = _gu()
