@@ -84,6 +84,13 @@ template <int BN, class Epi, int CG = 1, bool BRES = false> struct TcCfg {
   }
 };
 
+// host-side description of a grouped launch (see TcShape::groups)
+struct TcGroup {
+  int groups = 1;
+  int grp_n = 0, grp_k = 0;
+  int64_t out_group_stride = 0;      // elements between the groups' output buffers; 0: column ranges of one [M][groups * grp_n] buffer
+};
+
 struct TcShape {
   int64_t M;        // rows of C
   int32_t N;        // cols of C
@@ -93,6 +100,11 @@ struct TcShape {
   int32_t pf_dist;  // k-blocks the L2 prefetch cursor leads the load cursor by (0 = off)
   int32_t stages;   // depth of the operand ring actually used (<= the compiled kStages; option "tc_max_stages")
   unsigned long long* trace;   // profiling (option "tc_trace_ptr"): per CTA 16 cycle counters -- see tools/tc_trace.py; nullptr = off
+  // grouped (block-diagonal) launch: `groups` independent GEMMs laid side by side.  A is [M][groups * grp_k] (group g owns the k range
+  // [g * grp_k, (g+1) * grp_k)), C is [M][groups * grp_n]; B stacks the groups' weights along its row dimension: K-major B
+  // [groups * grp_n][grp_k] (forward Linear) or MN-major B [groups * grp_k][grp_n] (dgrad).  K above is grp_k.  out3d: the groups' outputs
+  // are separate [M][grp_n] buffers a fixed stride apart (third coordinate of the output map) instead of column ranges of one buffer.
+  int32_t groups, grp_n, grp_k, out3d;
   int32_t b_stable; // BRES: B was written at least two kernels before this one (weights): its resident block is loaded before griddepcontrol.wait
   int32_t tile_pf;  // 1: prefetch the next tile's A panel into L2 (tma_apf) at the start of each tile
   int32_t reverse;  // walk the M tiles (and the split-K ranges) from the end: the rows the previous kernel wrote last are still in L2
@@ -227,6 +239,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto tile_n = [&](int64_t t) { return (int64_t)((uint32_t)t % n_tiles32); };
   auto tile_sp = [&](int64_t t) { const uint32_t sp = (uint32_t)t / (n_tiles32 * m_tiles32); return (int64_t)(s.reverse ? (uint32_t)s.splits - 1 - sp : sp); };
 
+  auto tile_g = [&](int64_t n_t) { return s.groups > 1 ? (int32_t)(((uint32_t)n_t * (uint32_t)BN) / (uint32_t)s.grp_n) : 0; };
+
   float red = 0.f;
   // profiling: cycles this warp spent inside a class of barrier waits (accumulated per warp, written by lane 0 at the end)
   const bool tracing = s.trace != nullptr;
@@ -249,11 +263,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     {
       // issue (load into sa / sb) or prefetch-to-L2 (null destination with want_* set) the operand boxes of k-block kb of a tile
       auto fetch = [&](int64_t m_t, int64_t n_t, int64_t kb, uint8_t* sa, uint8_t* sb, uint64_t* bar, bool want_a, bool want_b) {
-        const int32_t k_el = (int32_t)(kb * TC_BK);
+        const int32_t g = tile_g(n_t);
+        const int32_t k_el = (int32_t)(kb * TC_BK) + g * s.grp_k;                        // A: group g owns columns [g * grp_k, (g+1) * grp_k)
+        const int32_t k_el_b = (int32_t)(kb * TC_BK) + (B_MN ? g * s.grp_k : 0);         // B stacked along k (MN-major) or along n (K-major)
         // CG = 2: the bytes of BOTH CTAs are counted on the leader's barrier (only the leader issues MMAs)
         const uint32_t bar_addr = (CG == 2 && bar) ? ptx::mapa_u32(ptx::smem_u32(bar), lead_rank) : 0u;
         const int32_t a_row = (int32_t)(m_t * TM) + (int32_t)cta_rank * TC_BM;          // this CTA's 128 rows of the tile
-        const int32_t b_row = (int32_t)(n_t * BN) + (int32_t)cta_rank * (BN / CG);        // this CTA's share of the B tile
+        const int32_t b_row = (int32_t)(n_t * BN) + (int32_t)cta_rank * (BN / CG) - (B_MN ? g * s.grp_n : 0);   // this CTA's share of the B tile
         auto ld = [&](void* d, const CUtensorMap* m, int32_t c0, int32_t c1) {
           if constexpr (CG == 2) ptx::tma_load_2d_cg2(d, m, bar_addr, c0, c1);
           else ptx::tma_load_2d(d, m, bar, c0, c1);
@@ -277,13 +293,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         if (want_b) {
           if constexpr (!B_MN) {
-            if (sb) ld(sb, &tma_b, k_el, b_row);
-            else ptx::tma_prefetch_2d(&tma_b, k_el, b_row);
+            if (sb) ld(sb, &tma_b, k_el_b, b_row);
+            else ptx::tma_prefetch_2d(&tma_b, k_el_b, b_row);
           } else {
 #pragma unroll
             for (int j = 0; j < (BN / CG) / 64; ++j) {
-              if (sb) ld(sb + j * (64 * TC_BK * 2), &tma_b, b_row + j * 64, k_el);
-              else ptx::tma_prefetch_2d(&tma_b, b_row + j * 64, k_el);
+              if (sb) ld(sb + j * (64 * TC_BK * 2), &tma_b, b_row + j * 64, k_el_b);
+              else ptx::tma_prefetch_2d(&tma_b, b_row + j * 64, k_el_b);
             }
           }
         }
@@ -629,6 +645,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               if constexpr (Epi::kSplit) {
                 if (epi.reduce_add) ptx::tma_reduce_add_2d(&tma_out, obuf, bcol, row_base);
                 else ptx::tma_store_3d(&tma_out, obuf, bcol, row_base, (int32_t)sp);
+              } else if (s.out3d) {
+                const int32_t g = tile_g(n_t);
+                ptx::tma_store_3d(&tma_out, obuf, bcol - g * s.grp_n, row_base, g);
               } else {
                 ptx::tma_store_2d(&tma_out, obuf, bcol, row_base);
               }
@@ -756,16 +775,18 @@ template <class Epi, class = void> struct epi_cs_atomic { static bool get(const 
 template <class Epi> struct epi_cs_atomic<Epi, std::enable_if_t<Epi::kColSum>> { static bool get(const Epi& e) { return e.colsum_atomic != 0; } };
 
 template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false, int CL = 1>
-int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st) {
+int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st,
+                      const TcGroup& grp = TcGroup()) {
   using Cfg = TcCfg<BN, Epi, CG, BRES>;
   using TOut = typename Epi::TOut;
   CUtensorMap ta, tb, tout, taux, tapf;
-  PSVAE_TRY(tc_tensor_map(A, K, A_MN ? TC_BK : TC_BM / CL, &ta));      // CL = 2: every CTA loads (and multicasts) half of its 128 rows
+  // grouped: K is one group's contraction length; A spans all groups' k ranges, an MN-major B all groups' k rows
+  PSVAE_TRY(tc_tensor_map(A, K * grp.groups, A_MN ? TC_BK : TC_BM / CL, &ta));      // CL = 2: every CTA loads (and multicasts) half of its 128 rows
   tapf = ta;
   if constexpr (!A_MN) {
     if (tc_tile_prefetch()) PSVAE_TRY(tc_prefetch_map(A, K, TC_BM, &tapf));
   }
-  PSVAE_TRY(tc_tensor_map(B, K, B_MN ? TC_BK : BN / CG, &tb));
+  PSVAE_TRY(tc_tensor_map(B, B_MN ? K * grp.groups : K, B_MN ? TC_BK : BN / CG, &tb));
   TcShape s;
   s.M = M; s.N = N; s.K = K; s.splits = splits < 1 ? 1 : splits;
   tc_desc_strides(A_MN, &s.a_lbo, &s.a_sbo);
@@ -775,12 +796,15 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   if (tc_max_stages() >= 2 && tc_max_stages() < s.stages) s.stages = tc_max_stages();
   s.reverse = tc_next_direction();
   s.trace = tc_trace_ptr();
+  s.groups = grp.groups; s.grp_n = grp.grp_n; s.grp_k = grp.grp_k;
+  s.out3d = (grp.groups > 1 && grp.out_group_stride != 0) ? 1 : 0;
   s.b_stable = (BRES && tc_b_stable()) ? 1 : 0;
-  s.tile_pf = (!A_MN && tc_tile_prefetch()) ? 1 : 0;
+  s.tile_pf = (!A_MN && tc_tile_prefetch() && grp.groups == 1) ? 1 : 0;
   if (epi.out) {
     const bool split_slots = Epi::kSplit && !epi_split_stride<Epi>::reduce(epi);
-    PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, N, epi.ldo, split_slots ? s.splits : 0, epi_split_stride<Epi>::get(epi), &tout,
-                           Cfg::kBlockCols));
+    if (s.out3d) PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, grp.grp_n, epi.ldo, grp.groups, grp.out_group_stride, &tout, Cfg::kBlockCols));
+    else PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, N, epi.ldo, split_slots ? s.splits : 0, epi_split_stride<Epi>::get(epi), &tout,
+                                Cfg::kBlockCols));
   } else {
     tout = ta;   // never dereferenced: the kernel skips the store
   }
@@ -856,36 +880,43 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
 // B-resident variant where it applies: forward / dgrad forms (A K-major), no split-K, no auxiliary tile, every N tile gets at least one
 // CTA (pair), and at least 3 ring stages are left next to the weight block
 template <int BN, bool A_MN, bool B_MN, class Epi, int CG>
-int gemm_tc_launch_pick(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st) {
+int gemm_tc_launch_pick(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st,
+                        const TcGroup& grp = TcGroup()) {
   if constexpr (!A_MN && !Epi::kSplit && Epi::kAuxBytes == 0) {
     using CfgR = TcCfg<BN, Epi, CG, true>;
     const int64_t n_tiles = ceil_div64(N, BN);
-    if (tc_b_resident() && splits <= 1 && (tc_grid_size() / CG) % n_tiles == 0 && ceil_div64(M, TC_BM * CG) * n_tiles >= tc_grid_size() / CG &&
+    if (tc_b_resident() && grp.groups == 1 && splits <= 1 && (tc_grid_size() / CG) % n_tiles == 0 && ceil_div64(M, TC_BM * CG) * n_tiles >= tc_grid_size() / CG &&
         CfgR::res_stages(ceil_div64(K, TC_BK)) >= 3)
       return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, true>(A, B, M, N, K, splits, epi, st);
   }
   if constexpr (!A_MN && CG == 2) {
     // clusters of two pairs sharing the activation tile: an even number of N tiles, whole clusters, and enough tiles to fill the grid
     const int64_t n_tiles = ceil_div64(N, BN), m_tiles = ceil_div64(M, TC_BM * CG);
-    if (tc_pair_cluster() && splits <= 1 && n_tiles % 2 == 0 && (tc_grid_size() / CG) % 2 == 0 && m_tiles * n_tiles >= 2)
-      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 2>(A, B, M, N, K, splits, epi, st);
+    if (tc_pair_cluster() && grp.groups == 1 && splits <= 1 && n_tiles % 2 == 0 && (tc_grid_size() / CG) % 2 == 0 && m_tiles * n_tiles >= 2)
+      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 2>(A, B, M, N, K, splits, epi, st, grp);
   }
-  return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false>(A, B, M, N, K, splits, epi, st);
+  return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false>(A, B, M, N, K, splits, epi, st, grp);
 }
 
 // can the tcgen05 epilogue produce the column sums of an [M, N] bf16 output?  (pairs of columns: N even; N % 8 is required anyway)
 static inline bool tc_colsum_ok(int N) { return N % 2 == 0; }
 
+// N = all groups' columns, K = one group's contraction length (grp.groups == 1: the plain GEMM)
 template <bool A_MN, bool B_MN, class Epi>
-int gemm_tc_launch(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st, int force_bn = 0) {
+int gemm_tc_launch(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st, int force_bn = 0,
+                   const TcGroup& grp = TcGroup()) {
   if (N % 8 != 0) { set_error("gemm_tc: N=%d must be a multiple of 8", N); return -2; }
-  const int bn = force_bn ? force_bn : tc_pick_bn(N);
+  const int bn = force_bn ? force_bn : tc_pick_bn(grp.groups > 1 ? grp.grp_n : N);      // a tile never straddles two groups
+  if (grp.groups > 1 && (A_MN || splits > 1 || grp.grp_n % bn != 0 || grp.grp_k % TC_BK != 0 || N != grp.groups * grp.grp_n)) {
+    set_error("gemm_tc: grouped launch needs K-major A, no split-K, grp_n %% %d == 0 and grp_k %% %d == 0", bn, TC_BK);
+    return -2;
+  }
   switch (bn) {
     case 256:
-      if (tc_use_pair(M, N, force_bn)) return gemm_tc_launch_pick<256, A_MN, B_MN, Epi, 2>(A, B, M, N, K, splits, epi, st);
-      return gemm_tc_launch_pick<256, A_MN, B_MN, Epi, 1>(A, B, M, N, K, splits, epi, st);
-    case 128: return gemm_tc_launch_pick<128, A_MN, B_MN, Epi, 1>(A, B, M, N, K, splits, epi, st);
-    case 64: return gemm_tc_launch_pick<64, A_MN, B_MN, Epi, 1>(A, B, M, N, K, splits, epi, st);
+      if (tc_use_pair(M, N, bn)) return gemm_tc_launch_pick<256, A_MN, B_MN, Epi, 2>(A, B, M, N, K, splits, epi, st, grp);
+      return gemm_tc_launch_pick<256, A_MN, B_MN, Epi, 1>(A, B, M, N, K, splits, epi, st, grp);
+    case 128: return gemm_tc_launch_pick<128, A_MN, B_MN, Epi, 1>(A, B, M, N, K, splits, epi, st, grp);
+    case 64: return gemm_tc_launch_pick<64, A_MN, B_MN, Epi, 1>(A, B, M, N, K, splits, epi, st, grp);
   }
   set_error("gemm_tc: unsupported BN=%d", bn);
   return -2;

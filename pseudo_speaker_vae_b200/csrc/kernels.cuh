@@ -149,7 +149,8 @@ template <typename TAct>
 __global__ void __launch_bounds__(256) latent_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
                                                          const float* __restrict__ eps, uint64_t seed, uint64_t offset, int64_t first_elem,
                                                          int64_t n_elems, const float* __restrict__ dmu_clf, float kl_over_b,
-                                                         TAct* __restrict__ dmu, TAct* __restrict__ dls) {
+                                                         TAct* __restrict__ dmu, TAct* __restrict__ dls, int qpr, int64_t ld_d) {
+  // dmu / dls are [rows][L] views with row stride ld_d (the two halves of one [rows][2L] buffer); qpr = L / 4
   PSVAE_GRID_DEP();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t nq = n_elems >> 2;
@@ -171,8 +172,9 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const float* __restrict
       om[j] = g[j] + kl_over_b * m[j] + c[j];
       ol[j] = g[j] * e[j] * (0.5f * sigma) + 0.5f * kl_over_b * expm1f(l[j]);   // expm1: no cancellation for ls ~ 0
     }
-    store_vec<4>(dmu + (i << 2), om);
-    store_vec<4>(dls + (i << 2), ol);
+    const int64_t o = (int64_t)((uint32_t)i / (uint32_t)qpr) * ld_d + (((uint32_t)i % (uint32_t)qpr) << 2);
+    store_vec<4>(dmu + o, om);
+    store_vec<4>(dls + o, ol);
   }
 }
 
@@ -735,7 +737,8 @@ __global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restr
                                                             const float* __restrict__ eps, uint64_t seed, uint64_t offset, int64_t first_elem,
                                                             int64_t n_elems, int L, const float* __restrict__ dmu_clf, float kl_over_b,
                                                             TAct* __restrict__ dmu, TAct* __restrict__ dls, float* __restrict__ partials,
-                                                            float* __restrict__ bias_grad) {
+                                                            float* __restrict__ bias_grad, int64_t ld_d) {
+  // dmu / dls: [rows][L] views with row stride ld_d (the two halves of one [rows][2L] buffer)
   // bias_grad != nullptr (fast mode): the block's 2L column sums are added straight into the zeroed [mu | sigma] bias gradient with atomics;
   // otherwise one partial row per block for the ordered reduce
   PSVAE_GRID_DEP();
@@ -763,8 +766,10 @@ __global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restr
       sm_[j] += om[j];
       sl_[j] += ol[j];
     }
-    store_vec<4>(dmu + (i << 2), om);
-    store_vec<4>(dls + (i << 2), ol);
+    const uint32_t qpr_ = (uint32_t)L >> 2;
+    const int64_t o = (int64_t)((uint32_t)i / qpr_) * ld_d + (((uint32_t)i % qpr_) << 2);
+    store_vec<4>(dmu + o, om);
+    store_vec<4>(dls + o, ol);
   }
 #pragma unroll
   for (int j = 0; j < 4; ++j) { lb_smem[threadIdx.x * 8 + j] = sm_[j]; lb_smem[threadIdx.x * 8 + 4 + j] = sl_[j]; }

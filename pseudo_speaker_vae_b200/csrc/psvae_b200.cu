@@ -63,6 +63,7 @@ struct Options {
   int64_t tc_tile_prefetch = 0;        // 1: the producer pulls the NEXT tile's whole activation panel into L2 with wide-box prefetches at the start of each tile
   int64_t tc_pair_cluster = 0;         // 1: forward / dgrad GEMMs with an even number of N tiles run as clusters of two CTA pairs (activation tile multicast).
                                        //    Measured: +7 % per SM, but only 33 clusters of 4 are co-resident (132 of 148 SMs) -> 39.3 vs 37.4 us; off by default
+  int64_t tc_grouped = 1;              // 1: layers 1..n of the two encoders run as ONE block-diagonal launch each (forward and dgrad) instead of one per encoder
   int64_t pdl = 1;                     // 1: kernels are launched with programmatic stream serialization (their prologue overlaps the predecessor's tail)
   int64_t tc_trace_ptr = 0;            // profiling: device pointer of gridDim.x * 16 cycle counters the GEMM kernels fill (0 = off)
   int64_t tc_max_stages = 0;           // experiments: cap the depth of the operand ring (0 = what fits)
@@ -290,6 +291,22 @@ template <> struct Engine<bf16> {
     TcOperand b{B, (int64_t)N, ldb, b_mn};
     return gemm_tc_launch<a_mn, b_mn, Epi>(a, b, M, N, K, splits, epi, st, (int)g_opt.tc_force_bn);
   }
+  // block-diagonal pair (the two encoders): A [M][groups * Kg], C [M][groups * Ng], weights stacked; see TcShape::groups
+  template <int MODE, class Epi>
+  static int gemm_grouped(const bf16* A, int64_t lda, const bf16* B, int64_t ldb, int64_t M, int groups, int Ng, int Kg, int64_t out_group_stride,
+                          const Epi& epi, cudaStream_t st) {
+    static_assert(MODE != G_WGRAD, "grouped launches: forward and dgrad forms");
+    constexpr bool b_mn = (MODE != G_FWD);
+    TcOperand a{A, M, lda, false};
+    TcOperand b{B, b_mn ? (int64_t)Ng : (int64_t)groups * Ng, ldb, b_mn};
+    TcGroup g;
+    g.groups = groups; g.grp_n = Ng; g.grp_k = Kg; g.out_group_stride = out_group_stride;
+    return gemm_tc_launch<false, b_mn, Epi>(a, b, M, groups * Ng, Kg, 1, epi, st, (int)g_opt.tc_force_bn, g);
+  }
+  static bool grouped_ok(int Ng, int Kg) {
+    const int bn = g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(Ng);
+    return g_opt.tc_grouped && Ng % bn == 0 && Kg % TC_BK == 0;
+  }
   static int wgrad_splits(int64_t M, int64_t N, int64_t K) {
     const int bn = g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn((int)N);
     const int cg = tc_use_pair(M, (int)N, (int)g_opt.tc_force_bn) ? 2 : 1;
@@ -456,8 +473,8 @@ static void plan(const psvae_model_desc* d, int64_t rows, int mode, Bump& b, Ste
   w.dxh = b.take<TAct>(rows * n.D);
   for (int i = 0; i < 2; ++i) w.gd[i] = b.take<TAct>(rows * n.H);
   w.dz = b.take<float>(rows * n.L);
-  w.dmu = b.take<TAct>(rows * n.L);
-  w.dls = b.take<TAct>(rows * n.L);
+  w.dmu = b.take<TAct>(rows * 2 * n.L);        // [rows][2L]: dmu | dls side by side (one A operand for the grouped encoder-head dgrad)
+  w.dls = w.dmu ? w.dmu + n.L : nullptr;
   for (int i = 0; i < 2; ++i) w.ge[i] = b.take<TAct>(rows * 2 * n.H);
   int64_t wmax = 0, cmax = 2 * n.H > n.D ? 2 * n.H : n.D;
   auto upd = [&](int64_t M, int64_t N, bool clf) {
@@ -696,14 +713,37 @@ static int run_step(const StepArgs& a) {
     EpiBiasAct<TAct, ACT_RELU> e{P + d->enc_b[0], w.he[0], 2 * n.H, nullptr, a.want_grads ? w.mhe[0] : nullptr, B};
     PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(xa, n.D, Wt + d->enc_w[0], n.D, B, 2 * n.H, n.D, 1, true, e, st)));
   }
+  // Layers 1..n of the two encoders are block-diagonal: in tcgen05 mode both encoders' layer j is ONE grouped launch (group = encoder:
+  // its own k range of the shared [B, 2H] activation buffer, its own rows of the stacked weights, its own column range of the output).
+  bool grouped_hidden = false, grouped_head = false;
+  if constexpr (sizeof(TAct) == 2) {
+    grouped_hidden = Engine<TAct>::grouped_ok(n.H, n.H);
+    // mu / log_sigma are two buffers: the output map's third coordinate steps from one to the other (16-byte multiple, forward only)
+    grouped_head = Engine<TAct>::grouped_ok(n.L, n.H) && ls > mu && ((ls - mu) % 4) == 0;
+  }
   for (int j = 1; j < n.nh; ++j) {
+    if constexpr (sizeof(TAct) == 2) {
+      if (grouped_hidden) {
+        EpiBiasAct<TAct, ACT_RELU> e{P + d->enc_b[j], w.he[j], 2 * n.H, nullptr, (a.want_grads && w.mhe[j]) ? w.mhe[j] : nullptr, B};
+        PSVAE_TRY((Engine<TAct>::template gemm_grouped<G_FWD>(w.he[j - 1], 2 * n.H, Wt + d->enc_w[j], n.H, B, 2, n.H, n.H, 0, e, st)));
+        continue;
+      }
+    }
     for (int s = 0; s < 2; ++s) {      // s = 0: encoder_mu, 1: encoder_sigma
       EpiBiasAct<TAct, ACT_RELU> e{P + d->enc_b[j] + s * n.H, w.he[j] + s * n.H, 2 * n.H, nullptr,
                                    (a.want_grads && w.mhe[j]) ? w.mhe[j] + (int64_t)s * (n.H / 32) * B : nullptr, B};
       PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(w.he[j - 1] + s * n.H, 2 * n.H, Wt + d->enc_w[j] + (int64_t)s * n.H * n.H, n.H, B, n.H, n.H, 1, true, e, st)));
     }
   }
-  for (int s = 0; s < 2; ++s) {
+  bool head_done = false;
+  if constexpr (sizeof(TAct) == 2) {
+    if (grouped_head) {
+      EpiBiasAct<float, ACT_NONE> e{P + d->enc_b[n.nh], mu, n.L, nullptr};
+      PSVAE_TRY((Engine<TAct>::template gemm_grouped<G_FWD>(w.he[n.nh - 1], 2 * n.H, Wt + d->enc_w[n.nh], n.H, B, 2, n.L, n.H, (int64_t)(ls - mu), e, st)));
+      head_done = true;
+    }
+  }
+  for (int s = 0; s < 2 && !head_done; ++s) {
     EpiBiasAct<float, ACT_NONE> e{P + d->enc_b[n.nh] + s * n.L, s == 0 ? mu : ls, n.L, nullptr};
     PSVAE_TRY((Engine<TAct>::template gemm<G_FWD>(w.he[n.nh - 1] + s * n.H, 2 * n.H, Wt + d->enc_w[n.nh] + (int64_t)s * n.L * n.H, n.H, B, n.L, n.H, 1, true, e, st)));
   }
@@ -903,14 +943,14 @@ static int run_step(const StepArgs& a) {
     if (blocks > 4 * PSVAE_NUM_SMS) blocks = 4 * PSVAE_NUM_SMS;
     float* bias_atomic = g_opt.deterministic ? nullptr : G + d->enc_b[n.nh];      // fast mode: atomics into the zeroed gradient, no reduce launch
     launch_dep(latent_bwd_cs_kernel<TAct>, dim3(blocks), dim3(256), 256 * 8 * sizeof(float), st, w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, n.L, dmu_clf,
-                                                                             a.kl_w / (float)B, w.dmu, w.dls, w.cpart, bias_atomic);
+                                                                             a.kl_w / (float)B, w.dmu, w.dls, w.cpart, bias_atomic, (int64_t)2 * n.L);
     count_launch();
     PSVAE_LAUNCH_CHECK("latent_bwd_cs_kernel");
     if (!bias_atomic) PSVAE_TRY(launch_reduce(w.cpart, 2 * n.L, blocks, G + d->enc_b[n.nh], st));
     last_bias_done = true;
   } else {
     launch_dep(latent_bwd_kernel<TAct>, dim3(ew_grid(B * n.L / 4)), dim3(256), 0, st, w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, dmu_clf, a.kl_w / (float)B,
-                                                                  w.dmu, w.dls);
+                                                                  w.dmu, w.dls, n.L / 4, (int64_t)2 * n.L);
     count_launch();
     PSVAE_LAUNCH_CHECK("latent_bwd_kernel");
   }
@@ -919,12 +959,38 @@ static int run_step(const StepArgs& a) {
   {
     int pp = 0;
     bool bias_done[2] = {false, false};
-    // last layer: two separate GEMM pairs (mu / sigma)
+    // grouped dgrad of both encoders' layer j (tcgen05 mode): dY [B][2 Kg] x stacked W [2 Kg][H] -> [B][2H] .* ReLU' (+ bias gradient of layer j-1)
+    auto dgrad_pair = [&](const TAct* dY, int64_t ldy, int Kg, int layer, TAct* out) -> int {
+      if constexpr (sizeof(TAct) == 2) {
+        const bool atomic = !g_opt.deterministic;
+        EpiActGrad<TAct, TAct, ACT_RELU, true> e{w.he[layer - 1], 2 * n.H, w.mhe[layer - 1], B, out, 2 * n.H, 0.f, nullptr,
+                                                 atomic ? G + d->enc_b[layer - 1] : w.cpart, atomic ? 1 : 0};
+        PSVAE_TRY((Engine<TAct>::template gemm_grouped<G_DGRAD>(dY, ldy, Wt + d->enc_w[layer], n.H, B, 2, n.H, Kg, 0, e, st)));
+        if (!atomic) {
+          const int64_t ctas = tc_ctas(B, 2 * n.H, 1, (int)g_opt.tc_force_bn);
+          PSVAE_TRY(launch_reduce(w.cpart, 2 * n.H, (int)ctas * 4, G + d->enc_b[layer - 1], st));
+        }
+        bias_done[0] = bias_done[1] = true;
+      }
+      return 0;
+    };
+    const int64_t ld_lat = 2 * n.L;      // dmu | dls share one [B][2L] buffer
+    // last layer (mu / sigma heads): wgrad per encoder, dgrad grouped where it can be
     for (int s = 0; s < 2; ++s) {
       const TAct* dY = s == 0 ? w.dmu : w.dls;
-      PSVAE_TRY(wgrad<TAct>(dY, n.L, w.he[n.nh - 1] + s * n.H, 2 * n.H, B, n.L, n.H, G + d->enc_w[n.nh] + (int64_t)s * n.L * n.H,
+      PSVAE_TRY(wgrad<TAct>(dY, ld_lat, w.he[n.nh - 1] + s * n.H, 2 * n.H, B, n.L, n.H, G + d->enc_w[n.nh] + (int64_t)s * n.L * n.H,
                             last_bias_done ? nullptr : G + d->enc_b[n.nh] + s * n.L, w, st));
-      PSVAE_TRY(dgrad_hidden<TAct>(dY, n.L, Wt + d->enc_w[n.nh] + (int64_t)s * n.L * n.H, n.L, n.H, w.he[n.nh - 1] + s * n.H, 2 * n.H,
+    }
+    bool head_grouped = false;
+    if constexpr (sizeof(TAct) == 2) {
+      if (Engine<TAct>::grouped_ok(n.H, n.L) && w.mhe[n.nh - 1] && tc_colsum_ok(n.H)) {
+        PSVAE_TRY(dgrad_pair(w.dmu, ld_lat, n.L, n.nh, w.ge[pp]));
+        head_grouped = true;
+      }
+    }
+    for (int s = 0; s < 2 && !head_grouped; ++s) {
+      const TAct* dY = s == 0 ? w.dmu : w.dls;
+      PSVAE_TRY(dgrad_hidden<TAct>(dY, ld_lat, Wt + d->enc_w[n.nh] + (int64_t)s * n.L * n.H, n.L, n.H, w.he[n.nh - 1] + s * n.H, 2 * n.H,
                                    w.mhe[n.nh - 1] ? w.mhe[n.nh - 1] + (int64_t)s * (n.H / 32) * B : nullptr, w.ge[pp] + s * n.H, 2 * n.H, B,
                                    G + d->enc_b[n.nh - 1] + s * n.H, w, &bias_done[s], st));
     }
@@ -933,6 +999,16 @@ static int run_step(const StepArgs& a) {
         const TAct* dY = w.ge[pp] + s * n.H;
         PSVAE_TRY(wgrad<TAct>(dY, 2 * n.H, w.he[j - 1] + s * n.H, 2 * n.H, B, n.H, n.H, G + d->enc_w[j] + (int64_t)s * n.H * n.H,
                               bias_done[s] ? nullptr : G + d->enc_b[j] + s * n.H, w, st));
+      }
+      bool pair_done = false;
+      if constexpr (sizeof(TAct) == 2) {
+        if (grouped_hidden && w.mhe[j - 1] && tc_colsum_ok(n.H)) {
+          PSVAE_TRY(dgrad_pair(w.ge[pp], 2 * n.H, n.H, j, w.ge[pp ^ 1]));
+          pair_done = true;
+        }
+      }
+      for (int s = 0; s < 2 && !pair_done; ++s) {
+        const TAct* dY = w.ge[pp] + s * n.H;
         PSVAE_TRY(dgrad_hidden<TAct>(dY, 2 * n.H, Wt + d->enc_w[j] + (int64_t)s * n.H * n.H, n.H, n.H, w.he[j - 1] + s * n.H, 2 * n.H,
                                      w.mhe[j - 1] ? w.mhe[j - 1] + (int64_t)s * (n.H / 32) * B : nullptr, w.ge[pp ^ 1] + s * n.H, 2 * n.H, B,
                                      G + d->enc_b[j - 1] + s * n.H, w, &bias_done[s], st));
@@ -1055,6 +1131,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_b_resident")) { g_opt.tc_b_resident = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_trace_ptr")) { g_opt.tc_trace_ptr = value; return 0; }
   if (!strcmp(name, "pdl")) { g_opt.pdl = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_grouped")) { g_opt.tc_grouped = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_pair_cluster")) { g_opt.tc_pair_cluster = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
@@ -1075,6 +1152,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_max_stages")) return g_opt.tc_max_stages;
   if (!strcmp(name, "tc_b_resident")) return g_opt.tc_b_resident;
   if (!strcmp(name, "pdl")) return g_opt.pdl;
+  if (!strcmp(name, "tc_grouped")) return g_opt.tc_grouped;
   if (!strcmp(name, "tc_pair_cluster")) return g_opt.tc_pair_cluster;
   if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;
