@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PSVAE_ABI_VERSION 1
+#define PSVAE_ABI_VERSION 2
 #define PSVAE_MAX_LAYERS 8      /* Linear layers per MLP (num_hidden + 1) */
 #define PSVAE_MAX_CLF_TRUNK 4   /* hidden Linear layers of the latent classifier */
 #define PSVAE_MAX_CLF_HEADS 4   /* output heads of the latent classifier */
@@ -52,6 +52,8 @@ extern "C" {
 #define PSVAE_LOSS_CLF 3       /* mean over heads of the cross entropies                      */
 #define PSVAE_LOSS_CLF_HEAD0 4 /* +h : cross entropy of head h                                */
 #define PSVAE_LOSS_ACC_HEAD0 8 /* +h : accuracy of head h (argmax == y)                       */
+#define PSVAE_LOSS_CONS 12     /* cross entropy of the consistency classifier on x_hat (train_consistency_loss, lightning.py:100-108) */
+#define PSVAE_LOSS_CONS_ACC 13 /* its accuracy (train_consistency)                            */
 
 /* Shape of the model plus the layout of the flat fp32 parameter buffer (element offsets).
  * VAEModel: ps_vae/model.py:8-36 generalised by hidden_dim / num_hidden (reference: 512 / 2).
@@ -84,6 +86,19 @@ typedef struct psvae_model_desc {
   int64_t vae_numel;   /* elements [0, vae_numel) hold the VAE, classifier follows */
   int64_t total_numel; /* length of the flat buffer (padded; padding stays zero)  */
 } psvae_model_desc;
+
+/* The frozen EmbeddingClassifier the reference loads as `consistency_classifier` (ps_vae/lightning.py:44-52;
+ * ps_vae/embedding_classifier/embedding_classifier.py:29-62): fc1 [hidden, input] -> ReLU -> fc2 [hidden, hidden]
+ * -> ReLU -> fc3 [classes, hidden], in its own flat fp32 buffer (element offsets below).  It receives no gradient. */
+typedef struct psvae_consistency_desc {
+  int32_t input_dim;   /* = psvae_model_desc.input_dim (multiple of 4) */
+  int32_t hidden_dim;  /* multiple of 4                                 */
+  int32_t num_classes; /* >= 2                                          */
+  int32_t reserved_;
+  int64_t w[3];
+  int64_t b[3];
+  int64_t total_numel;
+} psvae_consistency_desc;
 
 /* ---- host-only helpers (work without a GPU) ------------------------------------------------- */
 int psvae_abi_version(void);
@@ -149,6 +164,26 @@ int psvae_train_fwd_bwd(const psvae_model_desc* desc, const float* params, const
                         int64_t row0, int64_t rows, float kl_weight, float clf_weight, int32_t use_cos_loss,
                         int32_t compute_grads, int32_t precision, float* x_hat, float* mu, float* log_sigma,
                         float* losses, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- the same step with the consistency term (lightning.py:44-52, 100-108, 119-124) ------------ */
+int psvae_consistency_desc_init(psvae_consistency_desc* cons, int32_t input_dim, int32_t hidden_dim, int32_t num_classes);
+/* scratch the consistency chain needs ON TOP of psvae_workspace_bytes(...) for the same rows / mode (TRAIN or FORWARD) */
+int64_t psvae_consistency_workspace_bytes(const psvae_consistency_desc* cons, int64_t rows, int32_t mode);
+/* EmbeddingClassifier.forward (embedding_classifier.py:50-62): logits [rows][num_classes] = fc3(relu(fc2(relu(fc1(x))))); fp32 on
+ * the CUDA cores.  workspace >= psvae_consistency_workspace_bytes(cons, rows, PSVAE_MODE_FORWARD). */
+int psvae_consistency_forward(const psvae_consistency_desc* cons, const float* cons_params, const float* x, int64_t rows,
+                              float* logits, void* workspace, int64_t workspace_bytes, void* stream);
+/* psvae_train_fwd_bwd plus  cons_weight * CE(consistency_classifier(x_hat), cons_y)  in the total loss; its gradient reaches the
+ * decoder through x_hat (through the L2 normalisation when normalize_decoder is set).  cons_y: int64 [rows] (the single-label y of
+ * the batch).  losses[PSVAE_LOSS_CONS], [PSVAE_LOSS_CONS_ACC] are filled.  workspace >= psvae_workspace_bytes(...) +
+ * psvae_consistency_workspace_bytes(...).  The classifier runs in fp32 on the CUDA cores in both precisions. */
+int psvae_train_fwd_bwd_consistency(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads,
+                                    const float* x, const int64_t* y, const float* eps, uint64_t seed, uint64_t offset,
+                                    int64_t row0, int64_t rows, float kl_weight, float clf_weight, int32_t use_cos_loss,
+                                    int32_t compute_grads, int32_t precision, float* x_hat, float* mu, float* log_sigma,
+                                    float* losses, void* workspace, int64_t workspace_bytes, void* stream,
+                                    const psvae_consistency_desc* cons, const float* cons_params, const int64_t* cons_y,
+                                    float cons_weight);
 
 /* ---- conditional_synthesis Langevin loop (ps_vae/inference.py:72-103) --------------------------- */
 /* z_io [rows][L]: z0 == NULL-initialised by the caller or (init_from_philox != 0) drawn in-kernel with

@@ -44,7 +44,7 @@ def build_module(ref, cfg, dtype):
     hp = dict(model=dict(input_dim=cfg["D"], latent_dim=cfg["L"], normalize_decoder=cfg.get("normalize_decoder", False)),
               optimizer=cfg.get("optimizer", dict(lr=1e-3)), scheduler=dict(T_max=200),
               kl_loss_weight=cfg.get("kl_w", 1.0), classifier_loss_weight=cfg.get("clf_w", 1.0),
-              use_cos_loss=cfg.get("use_cos_loss", False))
+              use_cos_loss=cfg.get("use_cos_loss", False), consistency_loss_weight=cfg.get("cons_w", 1.0))
     if cfg.get("clf"):
         hp["classifier"] = dict(cfg["clf"])
     if isinstance(hp.get("classifier", {}).get("num_classes"), dict):
@@ -61,6 +61,20 @@ def build_module(ref, cfg, dtype):
     params = O.synth_params(shapes, seed=cfg["wseed"], dtype=np.float64)
     sd = {k: torch.from_numpy(v.astype(np.float32)) for k, v in params.items()}
     missing = m.load_state_dict(sd, strict=True)
+    if cfg.get("cons"):
+        # lightning.py:44-52 loads a frozen EmbeddingClassifier from a Lightning checkpoint; the stub has no checkpoint reader, so the
+        # (unmodified) reference class is built here, given synthetic weights, frozen and put in eval mode exactly as those lines do
+        import importlib
+
+        EC = importlib.import_module("ps_vae.embedding_classifier.embedding_classifier").EmbeddingClassifier
+        c = cfg["cons"]
+        ec = EC(input_dim=cfg["D"], num_classes=c["num_classes"], hidden_dim=c.get("hidden_dim", 128))
+        cp = O.synth_params(O.embedding_classifier_param_shapes(cfg["D"], c["num_classes"], c.get("hidden_dim", 128)), seed=c["wseed"], dtype=np.float64)
+        ec.load_state_dict({k: torch.from_numpy(v.astype(np.float32)) for k, v in cp.items()}, strict=False)
+        for p in ec.parameters():
+            p.requires_grad = False
+        ec.eval()
+        m.consistency_classifier = ec
     m = m.to(dtype)
     if dtype == torch.float64:
         # fp64 twin holds the same fp32-rounded values
@@ -91,9 +105,13 @@ def train_case(ref, name, cfg):
             for k, v in m.logged.items():
                 store[f"{st}/log/{k}"] = float(v)
             for pn, p in m.named_parameters():
+                if p.grad is None:      # the frozen consistency classifier
+                    continue
                 summarize(store, f"{st}/grad", pn, p.grad.detach().numpy())
             opt.step()
             for pn, p in m.named_parameters():
+                if pn.startswith("consistency_classifier."):
+                    continue
                 summarize(store, f"{st}/param", pn, p.detach().numpy())
     np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **store)
     print("wrote", name, len(store))
@@ -191,6 +209,14 @@ def main():
     torch.manual_seed(0)
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
+    # consistency-classifier cases (lightning.py:44-52,100-108), added after the first fixture set: `--only-cons` writes just these
+    train_case(ref, "train_d256_c2_cons", dict(D=256, L=64, B=24, wseed=15, dseed=910, steps=2, cons_w=0.7,
+                                               clf=dict(input_dim=64, num_classes=2), cons=dict(num_classes=2, hidden_dim=128, wseed=31)))
+    train_case(ref, "train_d192_c3_cons_norm_cos", dict(D=192, L=64, B=16, wseed=16, dseed=950, steps=2, cons_w=1.5, normalize_decoder=True,
+                                                        use_cos_loss=True, clf=dict(input_dim=64, num_classes=3),
+                                                        cons=dict(num_classes=3, hidden_dim=64, wseed=32)))
+    if "--only-cons" in sys.argv:
+        return
     train_case(ref, "train_d256_c2", dict(D=256, L=64, B=32, wseed=11, dseed=100, clf=dict(input_dim=64, num_classes=2)))
     train_case(ref, "train_d192_noclf", dict(D=192, L=64, B=16, wseed=12, dseed=200, kl_w=0.5, steps=2))
     train_case(ref, "train_d512_c3_mlp", dict(D=512, L=64, B=24, wseed=13, dseed=300, clf_w=2.0, steps=2,

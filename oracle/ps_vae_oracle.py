@@ -236,6 +236,29 @@ def classifier_backward(params: Params, cache, dlogits, grads: Optional[Params],
     return d
 
 
+def embedding_classifier_forward(params: Params, x: np.ndarray):
+    """EmbeddingClassifier.forward (ps_vae/embedding_classifier/embedding_classifier.py:50-62):
+    fc3(relu(fc2(relu(fc1(x))))).  Returns (logits, cache)."""
+    a1 = np.maximum(x @ params["fc1.weight"].T + params["fc1.bias"], 0)
+    a2 = np.maximum(a1 @ params["fc2.weight"].T + params["fc2.bias"], 0)
+    logits = a2 @ params["fc3.weight"].T + params["fc3.bias"]
+    return logits, (a1, a2)
+
+
+def embedding_classifier_input_grad(params: Params, cache, dlogits: np.ndarray) -> np.ndarray:
+    """d loss / d x of the frozen EmbeddingClassifier (no parameter gradients: lightning.py:48-49 freezes it)."""
+    a1, a2 = cache
+    d2 = (dlogits @ params["fc3.weight"]) * (a2 > 0)
+    d1 = (d2 @ params["fc2.weight"]) * (a1 > 0)
+    return d1 @ params["fc1.weight"]
+
+
+def embedding_classifier_param_shapes(input_dim: int, num_classes: int, hidden_dim: int = 128):
+    """state_dict keys / shapes of EmbeddingClassifier (embedding_classifier.py:29-32)."""
+    return [("fc1.weight", (hidden_dim, input_dim)), ("fc1.bias", (hidden_dim,)), ("fc2.weight", (hidden_dim, hidden_dim)),
+            ("fc2.bias", (hidden_dim,)), ("fc3.weight", (num_classes, hidden_dim)), ("fc3.bias", (num_classes,))]
+
+
 def log_softmax(logits: np.ndarray) -> np.ndarray:
     m = logits.max(axis=-1, keepdims=True)
     s = logits - m
@@ -267,8 +290,14 @@ def train_loss_and_grads(
     use_cos_loss: bool = False,
     classifier_activation: str = "relu",
     compute_grads: bool = True,
+    consistency_params: Optional[Params] = None,
+    consistency_loss_weight: float = 1.0,
 ):
     """Returns (scalars: dict, outputs: dict, grads: dict|None).
+
+    consistency_params: the frozen EmbeddingClassifier (``fc1/fc2/fc3`` state-dict keys) of lightning.py:44-52; its
+    cross entropy on x_hat is added with ``consistency_loss_weight`` (lightning.py:100-108,119-124) and its
+    gradient flows into the decoder through x_hat (the classifier itself gets no gradient).
 
     scalars: loss, recon_loss, kl_loss, classifier_loss, classifier_acc (names follow the ``train_*`` /
     ``val_*`` metric names of lightning.py:82-83,127-129).  y: int array [B] (single label) or
@@ -319,8 +348,17 @@ def train_loss_and_grads(
         if compute_grads:
             dmu_clf = classifier_backward(params, ccache, dlog, grads, classifier_activation)
 
-    total = recon + dt(kl_loss_weight) * kl + dt(classifier_loss_weight) * clf_loss
-    scal.update(loss=total, recon_loss=recon, kl_loss=kl, classifier_loss=clf_loss)
+    cons_loss = dt(0)
+    if consistency_params is not None:
+        # lightning.py:100-108: CE(consistency_classifier(x_hat), y); y is the single-label tensor
+        logits_c, c_cons = embedding_classifier_forward(consistency_params, x_hat)
+        cons_loss, dlog_c = cross_entropy(logits_c, y)
+        scal["consistency_acc"] = (logits_c.argmax(-1) == y).mean()
+        if compute_grads:
+            dxh = dxh + embedding_classifier_input_grad(consistency_params, c_cons, dlog_c * dt(consistency_loss_weight))
+
+    total = recon + dt(kl_loss_weight) * kl + dt(classifier_loss_weight) * clf_loss + dt(consistency_loss_weight) * cons_loss
+    scal.update(loss=total, recon_loss=recon, kl_loss=kl, classifier_loss=clf_loss, consistency_loss=cons_loss)
     outputs = dict(x_hat=x_hat, mu=mu, log_sigma=ls, z=c["z"])
     if not compute_grads:
         return scal, outputs, None

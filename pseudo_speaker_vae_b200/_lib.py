@@ -12,7 +12,7 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libpsvae_b200.so")
 
-PSVAE_ABI_VERSION = 1
+PSVAE_ABI_VERSION = 2
 MAX_LAYERS = 8
 MAX_CLF_TRUNK = 4
 MAX_CLF_HEADS = 4
@@ -21,13 +21,15 @@ FP32, BF16 = 0, 1
 MODE_TRAIN, MODE_FORWARD, MODE_DECODE = 0, 1, 2
 ACTIVATIONS = {"relu": 0, "tanh": 1, "sigmoid": 2, "leaky_relu": 3}
 LOSS_TOTAL, LOSS_RECON, LOSS_KL, LOSS_CLF, LOSS_CLF_HEAD0, LOSS_ACC_HEAD0 = 0, 1, 2, 3, 4, 8
+LOSS_CONS, LOSS_CONS_ACC = 12, 13
 
 #: every symbol include/psvae_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "psvae_abi_version", "psvae_last_error_string", "psvae_model_desc_init", "psvae_workspace_bytes", "psvae_shadow_bytes",
     "psvae_flops_per_sample", "psvae_set_option", "psvae_get_option", "psvae_adam_step", "psvae_philox_uint32", "psvae_philox_normal",
     "psvae_refresh_shadow", "psvae_forward", "psvae_decode", "psvae_train_fwd_bwd", "psvae_langevin", "psvae_gemm_bf16",
-    "psvae_gemm_fp32", "psvae_gemm_probe", "psvae_launch_count",
+    "psvae_gemm_fp32", "psvae_gemm_probe", "psvae_launch_count", "psvae_consistency_desc_init", "psvae_consistency_workspace_bytes",
+    "psvae_consistency_forward", "psvae_train_fwd_bwd_consistency",
 ]
 
 
@@ -44,6 +46,13 @@ class ModelDesc(C.Structure):
         ("clf_head_w", C.c_int64 * MAX_CLF_HEADS), ("clf_head_b", C.c_int64 * MAX_CLF_HEADS),
         ("vae_numel", C.c_int64), ("total_numel", C.c_int64),
     ]
+
+
+class ConsistencyDesc(C.Structure):
+    """Mirror of ``psvae_consistency_desc``."""
+
+    _fields_ = [("input_dim", C.c_int32), ("hidden_dim", C.c_int32), ("num_classes", C.c_int32), ("reserved_", C.c_int32),
+                ("w", C.c_int64 * 3), ("b", C.c_int64 * 3), ("total_numel", C.c_int64)]
 
 
 _lib: Optional[C.CDLL] = None
@@ -84,6 +93,15 @@ def _declare(l: C.CDLL) -> None:
     l.psvae_decode.argtypes = [D, VP, VP, VP, U64, U64, I64, I64, I32, VP, VP, VP, I64, VP]
     l.psvae_train_fwd_bwd.restype = C.c_int
     l.psvae_train_fwd_bwd.argtypes = [D, VP, VP, VP, VP, VP, VP, U64, U64, I64, I64, F, F, I32, I32, I32, VP, VP, VP, VP, VP, I64, VP]
+    CD = P(ConsistencyDesc)
+    l.psvae_consistency_desc_init.restype = C.c_int
+    l.psvae_consistency_desc_init.argtypes = [CD, I32, I32, I32]
+    l.psvae_consistency_workspace_bytes.restype = I64
+    l.psvae_consistency_workspace_bytes.argtypes = [CD, I64, I32]
+    l.psvae_consistency_forward.restype = C.c_int
+    l.psvae_consistency_forward.argtypes = [CD, VP, VP, I64, VP, VP, I64, VP]
+    l.psvae_train_fwd_bwd_consistency.restype = C.c_int
+    l.psvae_train_fwd_bwd_consistency.argtypes = l.psvae_train_fwd_bwd.argtypes + [CD, VP, VP, F]
     l.psvae_langevin.restype = C.c_int
     l.psvae_langevin.argtypes = [D, VP, VP, I64, P(I32), F, I32, F, U64, U64, I64, I32, VP, VP, VP, VP]
     l.psvae_gemm_bf16.restype = C.c_int
@@ -142,6 +160,12 @@ def set_option(name: str, value: int) -> None:
 
 def get_option(name: str) -> int:
     return int(lib().psvae_get_option(name.encode()))
+
+
+def make_consistency_desc(input_dim: int, hidden_dim: int, num_classes: int) -> ConsistencyDesc:
+    d = ConsistencyDesc()
+    check(lib().psvae_consistency_desc_init(C.byref(d), int(input_dim), int(hidden_dim), int(num_classes)), "psvae_consistency_desc_init")
+    return d
 
 
 def make_desc(input_dim: int, latent_dim: int, hidden_dim: int = 512, num_hidden: int = 2, normalize_decoder: bool = False,

@@ -294,6 +294,8 @@ struct LossPartials {
   float recon_scale;                     // 1 / (B * D * 10) for MSE/10, 1 / B for the cosine loss
   float inv_b;                           // 1 / B
   float kl_w, clf_w;
+  const float* cons_nll; const float* cons_acc; int n_cons;     // consistency classifier on x_hat (lightning.py:100-108); n_cons = 0: none
+  float cons_w;
 };
 
 __global__ void __launch_bounds__(1024) finalize_losses_kernel(LossPartials lp, float* __restrict__ losses) {
@@ -315,6 +317,8 @@ __global__ void __launch_bounds__(1024) finalize_losses_kernel(LossPartials lp, 
     nll[h] = (h < lp.n_heads) ? sum(lp.nll[h], lp.n_ce, lp.ce_stride) : 0.f;
     acc[h] = (h < lp.n_heads) ? sum(lp.acc[h], lp.n_ce, lp.ce_stride) : 0.f;
   }
+  const float cons_nll = lp.n_cons > 0 ? sum(lp.cons_nll, lp.n_cons) : 0.f;
+  const float cons_acc = lp.n_cons > 0 ? sum(lp.cons_acc, lp.n_cons) : 0.f;
   if (lane == 0) {
     const float recon = sse * lp.recon_scale;
     const float kl = -0.5f * kls * lp.inv_b;
@@ -322,13 +326,18 @@ __global__ void __launch_bounds__(1024) finalize_losses_kernel(LossPartials lp, 
     for (int h = 0; h < lp.n_heads; ++h) clf += nll[h] * lp.inv_b;
     if (lp.n_heads > 0) clf /= (float)lp.n_heads;
     for (int i = 0; i < 16; ++i) losses[i] = 0.f;
-    losses[0] = recon + lp.kl_w * kl + lp.clf_w * clf;
+    const float cons = cons_nll * lp.inv_b;
+    losses[0] = recon + lp.kl_w * kl + lp.clf_w * clf + (lp.n_cons > 0 ? lp.cons_w * cons : 0.f);
     losses[1] = recon;
     losses[2] = kl;
     losses[3] = clf;
     for (int h = 0; h < lp.n_heads; ++h) {
       losses[4 + h] = nll[h] * lp.inv_b;
       losses[8 + h] = acc[h] * lp.inv_b;
+    }
+    if (lp.n_cons > 0) {
+      losses[12] = cons;
+      losses[13] = cons_acc * lp.inv_b;
     }
   }
 }
@@ -344,10 +353,12 @@ namespace psvae {
 //   cos   : loss_row = 1 - <x_hat,x> / sqrt((|x_hat|^2+1e-12)(|x|^2+1e-12)) ; d/dx_hat as in F.cosine_embedding_loss
 //   mse   : loss_row = sum (x_hat-x)^2 ; d/dx_hat = (x_hat-x) * gscale
 //   du    = normalize ? (dxh - x_hat <x_hat,dxh>) / den : dxh
+// gx (optional, [rows][D] fp32): a further d loss / d x_hat added to dxh before the normalisation backward -- the gradient of the
+// consistency classifier's cross entropy (lightning.py:100-108).  x == nullptr: only x_hat is written.
 template <typename TAct>
 __global__ void __launch_bounds__(256) recon_rows_kernel(const float* __restrict__ u, const float* __restrict__ x, int64_t rows, int D, int normalize,
                                                          int use_cos, float gscale, float* __restrict__ x_hat, TAct* __restrict__ du,
-                                                         float* __restrict__ loss_partials) {
+                                                         float* __restrict__ loss_partials, const float* __restrict__ gx) {
   PSVAE_GRID_DEP();
   __shared__ float scratch[32];
   const int lane = threadIdx.x & 31;
@@ -390,7 +401,8 @@ __global__ void __launch_bounds__(256) recon_rows_kernel(const float* __restrict
         if (normalize) {
           for (int c = lane; c < D; c += 32) {
             const float h = ur[c] * inv_den, xv = xr[c];
-            const float g = use_cos ? -(xv * inv_dn - c_over_m1 * h) * gscale : (h - xv) * gscale;
+            float g = use_cos ? -(xv * inv_dn - c_over_m1 * h) * gscale : (h - xv) * gscale;
+            if (gx) g += gx[r * D + c];
             hd = fmaf(h, g, hd);
           }
           hd = warp_sum(hd);
@@ -398,6 +410,7 @@ __global__ void __launch_bounds__(256) recon_rows_kernel(const float* __restrict
         for (int c = lane; c < D; c += 32) {
           const float h = ur[c] * inv_den, xv = xr[c];
           float g = use_cos ? -(xv * inv_dn - c_over_m1 * h) * gscale : (h - xv) * gscale;
+          if (gx) g += gx[r * D + c];
           if (normalize) g = (g - h * hd) * inv_den;
           du[r * D + c] = from_f32<TAct>(g);
         }

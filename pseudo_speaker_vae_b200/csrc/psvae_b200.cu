@@ -627,6 +627,49 @@ static int clf_dgrad(int act, const float* dY, int out_dim, const float* W, int 
 }
 
 // ------------------------------------------------------------------------------------------------
+// consistency classifier (frozen EmbeddingClassifier, embedding_classifier.py:29-62): fp32 on the CUDA cores in both precisions
+// ------------------------------------------------------------------------------------------------
+struct ConsBufs {
+  float* xh = nullptr;            // normalised x_hat when the caller did not ask for it
+  float *a1 = nullptr, *a2 = nullptr, *logits = nullptr;
+  float *g2 = nullptr, *g1 = nullptr, *gx = nullptr;
+  float *nll_part = nullptr, *acc_part = nullptr;
+  int64_t n_ce = 0;
+};
+static int check_cons(const psvae_consistency_desc* c) {
+  if (!c) { set_error("consistency desc is NULL"); return -1; }
+  if (c->input_dim < 4 || c->input_dim % 4) { set_error("consistency input_dim=%d must be a positive multiple of 4", c->input_dim); return -2; }
+  if (c->hidden_dim < 4 || c->hidden_dim % 4) { set_error("consistency hidden_dim=%d must be a positive multiple of 4", c->hidden_dim); return -2; }
+  if (c->num_classes < 2) { set_error("consistency num_classes=%d must be at least 2", c->num_classes); return -2; }
+  return 0;
+}
+static void plan_cons(const psvae_consistency_desc* c, int64_t rows, bool train, Bump& b, ConsBufs& w) {
+  w.xh = b.take<float>(rows * c->input_dim);
+  w.a1 = b.take<float>(rows * c->hidden_dim);
+  w.a2 = b.take<float>(rows * c->hidden_dim);
+  w.logits = b.take<float>(rows * c->num_classes);
+  w.n_ce = ceil_div64(rows, 256);
+  w.nll_part = b.take<float>(w.n_ce);
+  w.acc_part = b.take<float>(w.n_ce);
+  if (!train) return;
+  w.g2 = b.take<float>(rows * c->hidden_dim);
+  w.g1 = b.take<float>(rows * c->hidden_dim);
+  w.gx = b.take<float>(rows * c->input_dim);
+}
+// logits = fc3(relu(fc2(relu(fc1(xh)))))
+static int cons_forward(const psvae_consistency_desc* c, const float* cp, const float* xh, int64_t rows, ConsBufs& w, float* logits, cudaStream_t st) {
+  PSVAE_TRY(clf_linear(ACT_RELU, xh, c->input_dim, cp + c->w[0], cp + c->b[0], w.a1, rows, c->hidden_dim, c->input_dim, st));
+  PSVAE_TRY(clf_linear(ACT_RELU, w.a1, c->hidden_dim, cp + c->w[1], cp + c->b[1], w.a2, rows, c->hidden_dim, c->hidden_dim, st));
+  return clf_linear(ACT_NONE, w.a2, c->hidden_dim, cp + c->w[2], cp + c->b[2], logits, rows, c->num_classes, c->hidden_dim, st);
+}
+// gx = d loss / d x_hat given dlogits (in w.logits); no parameter gradients (the classifier is frozen)
+static int cons_input_grad(const psvae_consistency_desc* c, const float* cp, int64_t rows, ConsBufs& w, cudaStream_t st) {
+  PSVAE_TRY(clf_dgrad(ACT_RELU, w.logits, c->num_classes, cp + c->w[2], c->hidden_dim, w.a2, w.g2, 0.f, rows, st));
+  PSVAE_TRY(clf_dgrad(ACT_RELU, w.g2, c->hidden_dim, cp + c->w[1], c->hidden_dim, w.a1, w.g1, 0.f, rows, st));
+  return clf_dgrad(ACT_NONE, w.g1, c->hidden_dim, cp + c->w[0], c->input_dim, nullptr, w.gx, 0.f, rows, st);
+}
+
+// ------------------------------------------------------------------------------------------------
 // the step: forward (+ losses) (+ backward)
 // ------------------------------------------------------------------------------------------------
 struct StepArgs {
@@ -645,6 +688,11 @@ struct StepArgs {
   void* ws;
   int64_t ws_bytes;
   cudaStream_t st;
+  // consistency classifier on x_hat (lightning.py:44-52, 100-108); cons == nullptr: none
+  const psvae_consistency_desc* cons = nullptr;
+  const float* cons_params = nullptr;
+  const int64_t* cons_y = nullptr;
+  float cons_w = 0.f;
 };
 
 template <typename TAct> static const TAct* weights_of(const StepArgs& a);
@@ -679,17 +727,27 @@ static int run_step(const StepArgs& a) {
   if (a.want_loss && !a.losses) { set_error("losses must not be NULL"); return -1; }
   if (a.want_loss && n.has_clf() && !a.y) { set_error("y must not be NULL when the model has a classifier"); return -1; }
   const int mode = a.want_grads ? PSVAE_MODE_TRAIN : PSVAE_MODE_FORWARD;
+  const bool cons_on = a.cons != nullptr && a.want_loss;
+  if (cons_on) {
+    PSVAE_TRY(check_cons(a.cons));
+    if (a.cons->input_dim != n.D) { set_error("consistency classifier input_dim=%d, the VAE's is %d", a.cons->input_dim, n.D); return -2; }
+    if (!a.cons_params || !a.cons_y) { set_error("cons_params and cons_y must not be NULL"); return -1; }
+  }
   StepBufs<TAct> w;
+  ConsBufs cw;
   {
     Bump sz(nullptr);
     StepBufs<TAct> tmp;
+    ConsBufs ctmp;
     plan<TAct>(d, B, mode, sz, tmp);
+    if (cons_on) plan_cons(a.cons, B, a.want_grads != 0, sz, ctmp);
     if (sz.used > a.ws_bytes || !a.ws) {
       set_error("workspace too small: need %lld bytes, got %lld", (long long)sz.used, (long long)a.ws_bytes);
       return -2;
     }
     Bump b(a.ws);
     plan<TAct>(d, B, mode, b, w);
+    if (cons_on) plan_cons(a.cons, B, a.want_grads != 0, b, cw);
   }
   const TAct* Wt = weights_of<TAct>(a);
   const float* P = a.params;
@@ -820,7 +878,8 @@ static int run_step(const StepArgs& a) {
   }
 
   // ---- decoder (model.py:58-61) + reconstruction loss (lightning.py:110-113)
-  const bool general_tail = d->normalize_decoder || a.use_cos;
+  // the consistency term needs x_hat before its gradient can join d loss / d x_hat: it goes through the general (unfused) tail
+  const bool general_tail = d->normalize_decoder || a.use_cos || cons_on;
   int n_sse_used = 0;
   bool dec_last_bias_done = false, dec_last_bias_reduce = false;
   if (a.want_loss && !general_tail) {
@@ -849,8 +908,30 @@ static int run_step(const StepArgs& a) {
     if (general_tail) {
       const float gscale = a.use_cos ? 1.f / (float)B : 2.f / ((float)B * (float)n.D * 10.f);
       const int blocks = (int)ceil_div64(B * 32, 256);
+      const float* gx = nullptr;
+      if (cons_on) {
+        // x_hat first (a pass of its own only when it differs from u), then CE(consistency_classifier(x_hat), y) and its gradient w.r.t. x_hat
+        const float* xh = w.u;
+        if (d->normalize_decoder) {
+          float* xh_out = a.x_hat ? a.x_hat : cw.xh;
+          launch_dep(recon_rows_kernel<TAct>, dim3(blocks), dim3(256), 0, st, w.u, (const float*)nullptr, B, n.D, 1, 0, 0.f, xh_out, (TAct*)nullptr,
+                                                          (float*)nullptr, (const float*)nullptr);
+          count_launch();
+          PSVAE_LAUNCH_CHECK("recon_rows_kernel");
+          xh = xh_out;
+        }
+        PSVAE_TRY(cons_forward(a.cons, a.cons_params, xh, B, cw, cw.logits, st));
+        launch_dep(ce_kernel, dim3((unsigned)cw.n_ce), dim3(256), 0, st, cw.logits, a.cons_y, B, a.cons->num_classes, a.cons_w / (float)B, a.want_grads,
+                                                cw.nll_part, cw.acc_part);
+        count_launch();
+        PSVAE_LAUNCH_CHECK("ce_kernel");
+        if (a.want_grads) {
+          PSVAE_TRY(cons_input_grad(a.cons, a.cons_params, B, cw, st));
+          gx = cw.gx;
+        }
+      }
       launch_dep(recon_rows_kernel<TAct>, dim3(blocks), dim3(256), 0, st, w.u, a.want_loss ? a.x : nullptr, B, n.D, d->normalize_decoder, a.use_cos, gscale, a.x_hat,
-                                                      a.want_grads ? w.dxh : nullptr, a.want_loss ? w.sse_part : nullptr);
+                                                      a.want_grads ? w.dxh : nullptr, a.want_loss ? w.sse_part : nullptr, gx);
       count_launch();
       PSVAE_LAUNCH_CHECK("recon_rows_kernel");
       n_sse_used = blocks;
@@ -872,6 +953,7 @@ static int run_step(const StepArgs& a) {
     lp.recon_scale = a.use_cos ? 1.f / (float)B : 1.f / ((float)B * (float)n.D * 10.f);
     lp.inv_b = 1.f / (float)B;
     lp.kl_w = a.kl_w; lp.clf_w = a.clf_w;
+    if (cons_on) { lp.cons_nll = cw.nll_part; lp.cons_acc = cw.acc_part; lp.n_cons = (int)cw.n_ce; lp.cons_w = a.cons_w; }
     launch_dep(finalize_losses_kernel, dim3(1), dim3(1024), 0, st, lp, a.losses);
     count_launch();
     PSVAE_LAUNCH_CHECK("finalize_losses_kernel");
@@ -1296,6 +1378,64 @@ int psvae_train_fwd_bwd(const psvae_model_desc* desc, const float* params, const
   PSVAE_TRY(check_desc(desc, precision));
   StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, x, y, eps, seed, offset, row0, rows, kl_weight, clf_weight,
              use_cos_loss ? 1 : 0, 1, compute_grads ? 1 : 0, x_hat, mu, log_sigma, losses, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)};
+  return precision == PSVAE_BF16 ? run_step<bf16>(a) : run_step<float>(a);
+}
+
+int psvae_consistency_desc_init(psvae_consistency_desc* cons, int32_t input_dim, int32_t hidden_dim, int32_t num_classes) {
+  if (!cons) { set_error("consistency desc is NULL"); return -1; }
+  memset(cons, 0, sizeof(*cons));
+  cons->input_dim = input_dim; cons->hidden_dim = hidden_dim; cons->num_classes = num_classes;
+  PSVAE_TRY(check_cons(cons));
+  const int64_t outs[3] = {hidden_dim, hidden_dim, num_classes}, ins[3] = {input_dim, hidden_dim, hidden_dim};
+  int64_t off = 0;
+  for (int j = 0; j < 3; ++j) {      // 16-byte aligned blocks (the fp32 engine reads float4)
+    cons->w[j] = off; off = align_up64(off + outs[j] * ins[j], 4);
+    cons->b[j] = off; off = align_up64(off + outs[j], 4);
+  }
+  cons->total_numel = align_up64(off, 64);
+  return 0;
+}
+
+int64_t psvae_consistency_workspace_bytes(const psvae_consistency_desc* cons, int64_t rows, int32_t mode) {
+  if (check_cons(cons) != 0) return -1;
+  if (rows <= 0 || (mode != PSVAE_MODE_TRAIN && mode != PSVAE_MODE_FORWARD)) { set_error("bad rows/mode"); return -1; }
+  Bump b(nullptr);
+  ConsBufs w;
+  plan_cons(cons, rows, mode == PSVAE_MODE_TRAIN, b, w);
+  return b.used + 256;
+}
+
+int psvae_consistency_forward(const psvae_consistency_desc* cons, const float* cons_params, const float* x, int64_t rows, float* logits,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
+  PSVAE_TRY(tc_device_check());
+  PSVAE_TRY(check_cons(cons));
+  if (rows <= 0) { set_error("rows=%lld must be positive", (long long)rows); return -2; }
+  if (!cons_params || !x || !logits) { set_error("cons_params, x and logits must not be NULL"); return -1; }
+  ConsBufs w;
+  {
+    Bump sz(nullptr);
+    ConsBufs tmp;
+    plan_cons(cons, rows, false, sz, tmp);
+    if (sz.used > workspace_bytes || !workspace) {
+      set_error("workspace too small: need %lld bytes, got %lld", (long long)sz.used, (long long)workspace_bytes);
+      return -2;
+    }
+    Bump b(workspace);
+    plan_cons(cons, rows, false, b, w);
+  }
+  return cons_forward(cons, cons_params, x, rows, w, logits, static_cast<cudaStream_t>(stream));
+}
+
+int psvae_train_fwd_bwd_consistency(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const float* x,
+                                    const int64_t* y, const float* eps, uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, float kl_weight,
+                                    float clf_weight, int32_t use_cos_loss, int32_t compute_grads, int32_t precision, float* x_hat, float* mu,
+                                    float* log_sigma, float* losses, void* workspace, int64_t workspace_bytes, void* stream,
+                                    const psvae_consistency_desc* cons, const float* cons_params, const int64_t* cons_y, float cons_weight) {
+  PSVAE_TRY(check_desc(desc, precision));
+  if (!cons) { set_error("consistency desc is NULL (use psvae_train_fwd_bwd for a step without the consistency term)"); return -1; }
+  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, x, y, eps, seed, offset, row0, rows, kl_weight, clf_weight,
+             use_cos_loss ? 1 : 0, 1, compute_grads ? 1 : 0, x_hat, mu, log_sigma, losses, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)};
+  a.cons = cons; a.cons_params = cons_params; a.cons_y = cons_y; a.cons_w = cons_weight;
   return precision == PSVAE_BF16 ? run_step<bf16>(a) : run_step<float>(a);
 }
 

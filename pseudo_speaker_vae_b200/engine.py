@@ -214,10 +214,11 @@ class HotPath:
                 f"pseudo_speaker_vae_b200 runs on a B200 only (module is on {dev}); move it with .to('cuda'). There is no CPU fallback.")
         return dev
 
-    def _workspace(self, dev: torch.device, rows: int, mode: int) -> torch.Tensor:
+    def _workspace(self, dev: torch.device, rows: int, mode: int, extra: int = 0) -> torch.Tensor:
         need = int(L.lib().psvae_workspace_bytes(self._dref, rows, self.precision, mode))
         if need < 0:
             raise ValueError(L.last_error())
+        need += extra
         ws = self._ws.get(dev)
         if ws is None or ws.numel() < need:
             self._ws[dev] = ws = torch.empty(need, dtype=torch.uint8, device=dev)
@@ -317,10 +318,12 @@ class HotPath:
         return y.contiguous()
 
     def step(self, x: torch.Tensor, y=None, eps: Optional[torch.Tensor] = None, *, kl_weight: float = 1.0, clf_weight: float = 1.0,
-             use_cos_loss: bool = False, compute_grads: bool = True, grads: Optional[torch.Tensor] = None, want_outputs: bool = False):
+             use_cos_loss: bool = False, compute_grads: bool = True, grads: Optional[torch.Tensor] = None, want_outputs: bool = False,
+             consistency: Optional[nn.Module] = None, consistency_y: Optional[torch.Tensor] = None, consistency_weight: float = 1.0):
         """One fused forward(+backward).  Returns (losses[16] device tensor, flat grads or None, outputs or None).
 
-        losses slots: _lib.LOSS_*; nothing here synchronises with the host."""
+        ``consistency``: a frozen ``EmbeddingClassifier`` whose ``consistency_weight * CE(consistency(x_hat), consistency_y)``
+        joins the loss (lightning.py:100-108, 119-124).  losses slots: _lib.LOSS_*; nothing here synchronises with the host."""
         dev = self._device()
         flat = self.arena.ensure()
         D, Lz = self.desc.input_dim, self.desc.latent_dim
@@ -348,12 +351,30 @@ class HotPath:
             mu = torch.empty(B, Lz, dtype=torch.float32, device=dev)
             ls = torch.empty(B, Lz, dtype=torch.float32, device=dev)
             outs = (xh, mu, ls)
-        ws = self._workspace(dev, B, L.MODE_TRAIN if compute_grads else L.MODE_FORWARD)
-        rc = L.lib().psvae_train_fwd_bwd(self._dref, flat.data_ptr(), self._shadow(), L.ptr(grads) if compute_grads else None, x.data_ptr(), L.ptr(yy),
-                                         L.ptr(eps), seed, off, self.row0, B, float(kl_weight), float(clf_weight), int(bool(use_cos_loss)),
-                                         int(bool(compute_grads)), self.precision, L.ptr(xh), L.ptr(mu), L.ptr(ls), losses.data_ptr(),
-                                         ws.data_ptr(), ws.numel(), _stream_ptr(dev))
-        L.check(rc, "psvae_train_fwd_bwd")
+        mode = L.MODE_TRAIN if compute_grads else L.MODE_FORWARD
+        args = (self._dref, flat.data_ptr(), self._shadow(), L.ptr(grads) if compute_grads else None, x.data_ptr(), L.ptr(yy),
+                L.ptr(eps), seed, off, self.row0, B, float(kl_weight), float(clf_weight), int(bool(use_cos_loss)),
+                int(bool(compute_grads)), self.precision, L.ptr(xh), L.ptr(mu), L.ptr(ls), losses.data_ptr())
+        if consistency is None:
+            ws = self._workspace(dev, B, mode)
+            rc = L.lib().psvae_train_fwd_bwd(*args, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            L.check(rc, "psvae_train_fwd_bwd")
+        else:
+            if consistency.input_dim != D:
+                raise ValueError(f"consistency classifier input_dim={consistency.input_dim} must equal the VAE input_dim={D}")
+            if consistency_y is None or isinstance(consistency_y, dict):
+                raise ValueError("the consistency classifier needs single-label targets (a tensor)")
+            cy = consistency_y.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+            if cy.numel() != B:
+                raise ValueError(f"labels have {cy.numel()} rows, x has {B}")
+            cdesc, cflat = consistency.flat_params(dev)
+            extra = int(L.lib().psvae_consistency_workspace_bytes(C.byref(cdesc), B, mode))
+            if extra < 0:
+                raise ValueError(L.last_error())
+            ws = self._workspace(dev, B, mode, extra)
+            rc = L.lib().psvae_train_fwd_bwd_consistency(*args, ws.data_ptr(), ws.numel(), _stream_ptr(dev), C.byref(cdesc), cflat.data_ptr(),
+                                                         cy.data_ptr(), float(consistency_weight))
+            L.check(rc, "psvae_train_fwd_bwd_consistency")
         return losses, (grads if compute_grads else None), outs
 
     def loss_with_grad(self, losses: torch.Tensor, gflat: torch.Tensor) -> torch.Tensor:

@@ -14,99 +14,24 @@ optimisation, gradient accumulation and DDP hooks keep working); ``configure_opt
 (one vectorised pass) with the stock ``CosineAnnealingLR``.
 
 Extra hparams (additive): ``precision`` ('fp32' parity mode / 'bf16' tensor-core mode), and ``model`` accepts
-``hidden_dim`` / ``num_hidden_layers``.  ``consistency_classifier_ckpt`` (lightning.py:44-52) is outside this
-round's scope and raises ``NotImplementedError`` rather than being ignored.
+``hidden_dim`` / ``num_hidden_layers``.  ``consistency_classifier_ckpt`` (lightning.py:44-52) loads the frozen
+``EmbeddingClassifier`` whose cross entropy on ``x_hat`` joins the loss inside the same fused call.
 """
 from __future__ import annotations
 
-import inspect
-from typing import Any, Dict, Optional
+from typing import Optional
 
 import torch
 import torch.nn as nn
 
 from . import _lib as L
+from .embedding_classifier import EmbeddingClassifier
 from .engine import HotPath
 from .latent_classifier import LatentClassifier
 from .model import VAEModel
 from .optim import FusedAdam
 
-try:  # pragma: no cover - not installed in the build image
-    import pytorch_lightning as _pl
-
-    _Base = _pl.LightningModule
-    HAVE_LIGHTNING = True
-except Exception:  # noqa: BLE001
-    _pl = None
-    HAVE_LIGHTNING = False
-
-    class _AttrDict(dict):
-        """``hparams.model['latent_dim']`` and ``hparams["optimizer"]`` both work (inference.py:22, lightning.py:205)."""
-
-        def __getattr__(self, k):
-            try:
-                return self[k]
-            except KeyError as e:
-                raise AttributeError(k) from e
-
-        def __setattr__(self, k, v):
-            self[k] = v
-
-    class _Base(nn.Module):
-        """The slice of LightningModule the reference touches: save_hyperparameters, hparams, log, device,
-        load_from_checkpoint (checkpoint dict keys ``hyper_parameters`` / ``state_dict``)."""
-
-        def __init__(self, *a, **k):
-            super().__init__()
-            self._hparams = _AttrDict()
-            self.logged: Dict[str, Any] = {}
-
-        def save_hyperparameters(self, *args, **kwargs):
-            frame = inspect.currentframe().f_back
-            hp = {}
-            for name, val in frame.f_locals.items():
-                if name in ("self", "__class__"):
-                    continue
-                if isinstance(val, dict) and name in ("hparams", "kwargs"):
-                    hp.update(val)
-                else:
-                    hp[name] = val
-            self._hparams = _AttrDict(hp)
-
-        @property
-        def hparams(self):
-            return self._hparams
-
-        @property
-        def device(self) -> torch.device:
-            try:
-                return next(self.parameters()).device
-            except StopIteration:
-                return torch.device("cpu")
-
-        def log(self, name, value, **kw):
-            self.logged[name] = value
-
-        @classmethod
-        def load_from_checkpoint(cls, checkpoint_path, map_location=None, **overrides):
-            ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
-            hp = dict(ckpt.get("hyper_parameters", {}))
-            hp.update(overrides)
-            module = cls(**hp)
-            module.load_state_dict(ckpt["state_dict"])
-            return module
-
-
-class _Accuracy(nn.Module):
-    """Stand-in for ``torchmetrics.Accuracy(task='multiclass')``: mean(argmax == y).  (The fused step computes the
-    same number in-kernel; this object exists so ``module.accuracy`` keeps its place in the attribute surface.)"""
-
-    def __init__(self, task: str = "multiclass", num_classes: Optional[int] = None):
-        super().__init__()
-        self.task, self.num_classes = task, num_classes
-
-    def forward(self, preds: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
-        return (preds.argmax(dim=-1) == target).float().mean()
+from ._compat import HAVE_LIGHTNING, _Accuracy, _Base  # noqa: F401  (Lightning base class or its stand-in)
 
 
 class PseudoSpeakerVAE(_Base):
@@ -142,8 +67,13 @@ class PseudoSpeakerVAE(_Base):
             self.classifier = None
 
         if "consistency_classifier_ckpt" in hparams:
-            raise NotImplementedError("consistency_classifier_ckpt (ps_vae/lightning.py:44-52) is not part of the B200 hot path yet")
-        self.consistency_classifier = None
+            # lightning.py:44-52: a frozen EmbeddingClassifier in eval mode; its CE on x_hat joins the loss (lightning.py:100-108)
+            self.consistency_classifier = EmbeddingClassifier.load_from_checkpoint(hparams["consistency_classifier_ckpt"])
+            for param in self.consistency_classifier.parameters():
+                param.requires_grad = False
+            self.consistency_classifier.eval()
+        else:
+            self.consistency_classifier = None
 
         self.kl_loss_weight = hparams.get("kl_loss_weight", 1.0)
         self.classifier_loss_weight = hparams.get("classifier_loss_weight", 1.0)
@@ -168,13 +98,19 @@ class PseudoSpeakerVAE(_Base):
 
     def _shared_step(self, batch, prefix: str, compute_grads: bool, eps: Optional[torch.Tensor], **log_kw) -> dict:
         x, y = batch
+        cons = self.consistency_classifier
+        if cons is not None and isinstance(y, dict):
+            # the reference calls cross_entropy(y_hat_consistency, y) with the batch's y (lightning.py:102): a single label tensor
+            raise ValueError("the consistency classifier needs single-label targets (a tensor), got a dict of labels")
+        cons_y = y if cons is not None else None
         if self.classifier is None:
             y = None
         hot = self._hot
         train_vae = any(p.requires_grad for p in self.model.parameters())
         need_grads = compute_grads and torch.is_grad_enabled() and (train_vae or self.classifier is not None)
         losses, gflat, _ = hot.step(x, y, eps, kl_weight=self.kl_loss_weight, clf_weight=self.classifier_loss_weight,
-                                    use_cos_loss=self.use_cos_loss, compute_grads=need_grads)
+                                    use_cos_loss=self.use_cos_loss, compute_grads=need_grads, consistency=cons, consistency_y=cons_y,
+                                    consistency_weight=self.consitency_loss_weight)
         if self.classifier is not None:
             if not self.multilabel:
                 self.log(f"{prefix}_classifier_acc", losses[L.LOSS_ACC_HEAD0], sync_dist=True)
@@ -185,6 +121,9 @@ class PseudoSpeakerVAE(_Base):
                     running = running + losses[L.LOSS_CLF_HEAD0 + h]      # the reference logs the running sum (lightning.py:88-93)
                     self.log(f"{prefix}_classifier_acc_{name}", losses[L.LOSS_ACC_HEAD0 + h], sync_dist=True)
                     self.log(f"{prefix}_classifier_loss_{name}", running, sync_dist=True)
+        if cons is not None:
+            self.log(f"{prefix}_consistency", losses[L.LOSS_CONS_ACC], sync_dist=True)          # lightning.py:105-106 / 167-168
+            self.log(f"{prefix}_consistency_loss", losses[L.LOSS_CONS], sync_dist=True)
         self.log(f"{prefix}_loss", losses[L.LOSS_TOTAL], sync_dist=True, **log_kw)
         self.log(f"{prefix}_recon_loss", losses[L.LOSS_RECON], sync_dist=True, **log_kw)
         self.log(f"{prefix}_kl_loss", losses[L.LOSS_KL], sync_dist=True, **log_kw)
@@ -205,7 +144,9 @@ class PseudoSpeakerVAE(_Base):
         self.model.load_state_dict(vae_state_dict)
 
     def configure_optimizers(self):
-        params = [p for p in self.parameters()]
+        # the frozen consistency classifier never receives a gradient (lightning.py:48-49): torch's Adam skips it, the fused pass leaves it out
+        in_arena = {id(p) for p in self._hot.parameters()}
+        params = [p for p in self.parameters() if id(p) in in_arena]
         optimizer = FusedAdam(params, **self.hparams["optimizer"], arena=self._hot.arena)
         scheduler = torch.optim.lr_scheduler.CosineAnnealingLR(optimizer, **self.hparams["scheduler"])
         return {

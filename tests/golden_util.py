@@ -32,6 +32,15 @@ def case_params(cfg, dtype=np.float32):
     return {k: v.astype(np.float32).astype(dtype) for k, v in p.items()}
 
 
+def case_consistency_params(cfg, dtype=np.float32):
+    """Synthetic weights of the frozen consistency classifier of a golden case (None when the case has none)."""
+    c = cfg.get("cons")
+    if not c:
+        return None
+    p = O.synth_params(O.embedding_classifier_param_shapes(cfg["D"], c["num_classes"], c.get("hidden_dim", 128)), seed=c["wseed"], dtype=np.float64)
+    return {k: v.astype(np.float32).astype(dtype) for k, v in p.items()}
+
+
 def case_batch(cfg, step, dtype=np.float32):
     nc = cfg["clf"]["num_classes"] if cfg.get("clf") else 2
     x, y, eps = O.synth_batch(cfg["B"], cfg["D"], cfg["L"], nc, seed=cfg["dseed"] + step)

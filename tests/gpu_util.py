@@ -12,7 +12,7 @@ if ROOT not in sys.path:
 
 from pseudo_speaker_vae_b200 import _lib as L  # noqa: E402
 import pseudo_speaker_vae_b200 as P  # noqa: E402
-from tests.golden_util import case_params  # noqa: E402
+from tests.golden_util import case_consistency_params, case_params  # noqa: E402
 
 DEV = "cuda:0"
 
@@ -25,7 +25,8 @@ def module_from_cfg(cfg, precision="fp32", params=None, device=DEV, **extra):
     """PseudoSpeakerVAE carrying the synthetic parameters of a golden case (tests/golden_util.case_params)."""
     hp = dict(model=dict(input_dim=cfg["D"], latent_dim=cfg["L"], normalize_decoder=cfg.get("normalize_decoder", False)),
               optimizer=dict(cfg.get("optimizer", dict(lr=1e-3))), scheduler=dict(T_max=200), precision=precision,
-              kl_loss_weight=cfg.get("kl_w", 1.0), classifier_loss_weight=cfg.get("clf_w", 1.0), use_cos_loss=cfg.get("use_cos_loss", False))
+              kl_loss_weight=cfg.get("kl_w", 1.0), classifier_loss_weight=cfg.get("clf_w", 1.0), use_cos_loss=cfg.get("use_cos_loss", False),
+              consistency_loss_weight=cfg.get("cons_w", 1.0))
     if "H" in cfg:
         hp["model"].update(hidden_dim=cfg["H"], num_hidden_layers=cfg["nh"])
     if cfg.get("clf"):
@@ -35,7 +36,17 @@ def module_from_cfg(cfg, precision="fp32", params=None, device=DEV, **extra):
     if params is None:
         params = case_params(cfg, np.float32)
     sd = {k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in params.items()}
-    m.load_state_dict(sd)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("consistency_classifier.") for k in missing), (missing, unexpected)
+    if cfg.get("cons"):
+        # what `consistency_classifier_ckpt` does (lightning.py:44-52), with the golden case's synthetic weights instead of a checkpoint file
+        c = cfg["cons"]
+        ec = P.EmbeddingClassifier(input_dim=cfg["D"], num_classes=c["num_classes"], hidden_dim=c.get("hidden_dim", 128))
+        ec.load_state_dict({k: torch.from_numpy(np.ascontiguousarray(v)) for k, v in case_consistency_params(cfg, np.float32).items()})
+        for p in ec.parameters():
+            p.requires_grad = False
+        ec.eval()
+        m.consistency_classifier = ec
     return m.to(device)
 
 

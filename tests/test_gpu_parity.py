@@ -23,12 +23,13 @@ import torch
 
 from oracle import philox_ref as PR
 from oracle import ps_vae_oracle as O
-from tests.golden_util import GOLDEN, case_batch, case_params, check_summary, load, rel_err
+from tests.golden_util import GOLDEN, case_batch, case_consistency_params, case_params, check_summary, load, rel_err
 
 pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-TRAIN_CASES = ["train_d256_c2", "train_d192_noclf", "train_d512_c3_mlp", "train_d256_norm_cos"]
+TRAIN_CASES = ["train_d256_c2", "train_d192_noclf", "train_d512_c3_mlp", "train_d256_norm_cos", "train_d256_c2_cons",
+               "train_d192_c3_cons_norm_cos"]       # the last two: + the frozen consistency classifier on x_hat (lightning.py:44-52,100-108)
 SAMPLE_CASES = ["sample_single", "sample_c3_mlp", "sample_multilabel", "sample_multilabel_1layer"]
 FP32_TOL = 1e-5
 BF16_FWD_TOL, BF16_LOSS_TOL, BF16_GRAD_TOL, BF16_GRAD_TOL_SMALL = 1e-2, 3e-3, 3e-2, 1e-1
@@ -172,10 +173,16 @@ def test_tcgen05_gemm_cta_pair_variant(v):
 # ------------------------------------------------------------------------------------------------
 def _oracle_at(module, cfg, x, y, eps):
     """fp64 oracle evaluated at the module's CURRENT parameters (same inputs, same parameters, same eps)."""
-    params = {k: v.detach().cpu().double().numpy() for k, v in module.state_dict().items()}
+    params = {k: v.detach().cpu().double().numpy() for k, v in module.state_dict().items() if not k.startswith("consistency_classifier.")}
     return O.train_loss_and_grads(params, x.astype(np.float64), y, eps.astype(np.float64), kl_loss_weight=cfg.get("kl_w", 1.0),
                                   classifier_loss_weight=cfg.get("clf_w", 1.0), normalize_decoder=cfg.get("normalize_decoder", False),
-                                  use_cos_loss=cfg.get("use_cos_loss", False), classifier_activation=(cfg.get("clf") or {}).get("activation", "relu"))
+                                  use_cos_loss=cfg.get("use_cos_loss", False), classifier_activation=(cfg.get("clf") or {}).get("activation", "relu"),
+                                  consistency_params=case_consistency_params(cfg, np.float64), consistency_loss_weight=cfg.get("cons_w", 1.0))
+
+
+def _trainable(module):
+    """(name, parameter) of everything the step trains: the frozen consistency classifier is left out (lightning.py:48-49)."""
+    return [(k, p) for k, p in module.named_parameters() if not k.startswith("consistency_classifier.")]
 
 
 def _train_case(name, precision, tol_fwd, tol_loss, tol_grad, check_params):
@@ -208,7 +215,8 @@ def _train_case(name, precision, tol_fwd, tol_loss, tol_grad, check_params):
         loss.backward()
         logged = {k: float(v) for k, v in module.logged.items()}
         for ours, okey in (("train_loss", "loss"), ("train_recon_loss", "recon_loss"), ("train_kl_loss", "kl_loss")) + \
-                ((("train_classifier_loss", "classifier_loss"),) if cfg.get("clf") else ()):
+                ((("train_classifier_loss", "classifier_loss"),) if cfg.get("clf") else ()) + \
+                ((("train_consistency_loss", "consistency_loss"),) if cfg.get("cons") else ()):
             ref = float(z[f"{st}/log/{ours}"])
             e = abs(logged[ours] - ref) / max(1.0, abs(ref))
             worst[ours] = max(worst.get(ours, 0), e)
@@ -217,15 +225,18 @@ def _train_case(name, precision, tol_fwd, tol_loss, tol_grad, check_params):
         assert abs(float(loss.detach()) - logged["train_loss"]) == 0
         if cfg.get("clf") and precision == "fp32":
             assert abs(logged["train_classifier_acc"] - float(z[f"{st}/log/train_classifier_acc"])) <= 1e-6
+        if cfg.get("cons") and precision == "fp32":
+            assert abs(logged["train_consistency"] - float(z[f"{st}/log/train_consistency"])) <= 1e-6
+            assert all(p.grad is None for p in module.consistency_classifier.parameters())
         errs = {}
-        for k, p in module.named_parameters():
+        for k, p in _trainable(module):
             worst["grad_traj"] = max(worst.get("grad_traj", 0), check_summary(z, f"{st}/grad", k, p.grad.cpu().numpy(), traj * tol_grad))
             errs[k] = rel_err(p.grad.cpu().numpy(), grads[k])
         worst["grad"] = max(worst.get("grad", 0), max(errs.values()))
         assert max(errs.values()) <= tol_grad, (name, precision, s, {k: f"{v:.1e}" for k, v in errs.items()})
         opt.step()
         if check_params:
-            for k, p in module.named_parameters():
+            for k, p in _trainable(module):
                 worst["param"] = max(worst.get("param", 0), check_summary(z, f"{st}/param", k, p.detach().cpu().numpy(), tol_grad))
     return worst
 
@@ -251,20 +262,79 @@ def test_train_step_bf16_vs_reference_golden(name):
     for nm, got in (("x_hat", x_hat), ("mu", mu), ("ls", ls)):
         assert rel_err(got.cpu().numpy(), z[f"f64/step0/{nm}"]) <= BF16_FWD_TOL, (name, nm)
     module.training_step((xt, yt), 0, eps=et)["loss"].backward()
-    for ours in ("train_loss", "train_recon_loss", "train_kl_loss") + (("train_classifier_loss",) if cfg.get("clf") else ()):
+    for ours in ("train_loss", "train_recon_loss", "train_kl_loss") + (("train_classifier_loss",) if cfg.get("clf") else ()) + \
+            (("train_consistency_loss",) if cfg.get("cons") else ()):
         ref = float(z[f"f64/step0/log/{ours}"])
         assert abs(float(module.logged[ours]) - ref) <= BF16_LOSS_TOL * max(1.0, abs(ref)), (name, ours)
     params = case_params(cfg, np.float64)
     _, _, grads = O.train_loss_and_grads(params, x.astype(np.float64), y, eps.astype(np.float64), kl_loss_weight=cfg.get("kl_w", 1.0),
                                          classifier_loss_weight=cfg.get("clf_w", 1.0), normalize_decoder=cfg.get("normalize_decoder", False),
-                                         use_cos_loss=cfg.get("use_cos_loss", False), classifier_activation=(cfg.get("clf") or {}).get("activation", "relu"))
-    errs = {k: rel_err(p.grad.cpu().numpy(), grads[k]) for k, p in module.named_parameters()}
+                                         use_cos_loss=cfg.get("use_cos_loss", False), classifier_activation=(cfg.get("clf") or {}).get("activation", "relu"),
+                                         consistency_params=case_consistency_params(cfg, np.float64), consistency_loss_weight=cfg.get("cons_w", 1.0))
+    errs = {k: rel_err(p.grad.cpu().numpy(), grads[k]) for k, p in _trainable(module)}
     assert max(errs.values()) <= BF16_GRAD_TOL_SMALL, {k: f"{v:.1e}" for k, v in errs.items()}
     opt = module.configure_optimizers()["optimizer"]
     before = module.hot_path.arena.flat.clone()
     opt.step()
     assert torch.equal(module.hot_path.arena.shadow, module.hot_path.arena.flat.to(torch.bfloat16))     # Adam keeps the tcgen05 operand copy current
     assert not torch.equal(before, module.hot_path.arena.flat)
+
+
+def test_consistency_classifier_forward_validation_and_checkpoint(tmp_path):
+    """EmbeddingClassifier.forward through the library vs the oracle; `consistency_classifier_ckpt` end to end (Lightning checkpoint
+    layout -> frozen module -> the fused step); validation metric names (lightning.py:164-168); a VAE without latent classifier;
+    and a 1000-row batch in both precisions against the fp64 oracle."""
+    import pseudo_speaker_vae_b200 as P
+
+    G = _gu()
+    z, cfg = load("train_d256_c2_cons")
+    cp = case_consistency_params(cfg, np.float32)
+    ec = P.EmbeddingClassifier(input_dim=256, num_classes=2, hidden_dim=128)
+    ec.load_state_dict({k: torch.from_numpy(v) for k, v in cp.items()})
+    path = str(tmp_path / "cons.ckpt")
+    torch.save({"state_dict": ec.state_dict(), "hyper_parameters": dict(ec.hparams)}, path)
+    x, y, eps = case_batch(cfg, 0, np.float32)
+    xt, et, yt = torch.from_numpy(x).to(G.DEV), torch.from_numpy(eps).to(G.DEV), G.labels_to_torch(y)
+    logits = ec.to(G.DEV)(xt)
+    ref, _ = O.embedding_classifier_forward({k: v.astype(np.float64) for k, v in cp.items()}, x.astype(np.float64))
+    assert rel_err(logits.cpu().numpy(), ref) <= FP32_TOL
+    # the checkpoint route reproduces the golden step
+    plain = dict(cfg)
+    plain.pop("cons")
+    module = G.module_from_cfg(plain, "fp32", consistency_classifier_ckpt=path, consistency_loss_weight=cfg["cons_w"])
+    module.training_step((xt, yt), 0, eps=et)["loss"].backward()
+    for ours in ("train_loss", "train_consistency_loss", "train_consistency"):
+        assert abs(float(module.logged[ours]) - float(z[f"f64/step0/log/{ours}"])) <= FP32_TOL, ours
+    for k, p in _trainable(module):
+        check_summary(z, "f64/step0/grad", k, p.grad.cpu().numpy(), FP32_TOL)
+    module.validation_step((xt, yt), 0, eps=et)
+    assert abs(float(module.logged["val_consistency_loss"]) - float(z["f64/step0/log/train_consistency_loss"])) <= FP32_TOL
+    assert abs(float(module.logged["val_loss"]) - float(z["f64/step0/log/train_loss"])) <= FP32_TOL
+    assert float(module.logged["val_consistency"]) == float(module.logged["train_consistency"])
+    with pytest.raises(ValueError):
+        module.training_step((xt, {"gender": yt}), 0, eps=et)
+    # no latent classifier: the consistency term alone steers the decoder
+    nc = dict(plain)
+    nc.pop("clf")
+    m2 = G.module_from_cfg(nc, "fp32", params={k: v for k, v in case_params(cfg, np.float32).items() if not k.startswith("classifier.")},
+                           consistency_classifier_ckpt=path, consistency_loss_weight=cfg["cons_w"])
+    m2.training_step((xt, yt), 0, eps=et)["loss"].backward()
+    p64 = {k: v for k, v in case_params(cfg, np.float64).items() if not k.startswith("classifier.")}
+    scal, _, grads = O.train_loss_and_grads(p64, x.astype(np.float64), y, eps.astype(np.float64),
+                                            consistency_params=case_consistency_params(cfg, np.float64), consistency_loss_weight=cfg["cons_w"])
+    assert abs(float(m2.logged["train_loss"]) - float(scal["loss"])) <= FP32_TOL
+    assert max(rel_err(p.grad.cpu().numpy(), grads[k]) for k, p in _trainable(m2)) <= FP32_TOL
+    # 1000 rows (ragged tiles), both precisions, normalised decoder + MSE: the gradient passes through the L2 normalisation
+    big = dict(cfg, B=1000, normalize_decoder=True)
+    xb, yb, eb = O.synth_batch(1000, 256, 64, 2, seed=77)
+    for precision, tl, tg in (("fp32", FP32_TOL, FP32_FLIP_TOL), ("bf16", BF16_LOSS_TOL, BF16_GRAD_TOL_SMALL)):
+        m3 = G.module_from_cfg(big, precision)
+        m3.training_step((torch.from_numpy(xb).to(G.DEV), torch.from_numpy(yb).to(G.DEV)), 0, eps=torch.from_numpy(eb).to(G.DEV))["loss"].backward()
+        scal, _, grads = _oracle_at(m3, big, xb, yb, eb)
+        for ours, okey in (("train_loss", "loss"), ("train_consistency_loss", "consistency_loss"), ("train_recon_loss", "recon_loss")):
+            assert abs(float(m3.logged[ours]) - float(scal[okey])) <= tl * max(1.0, abs(float(scal[okey]))), (precision, ours)
+        errs = {k: rel_err(p.grad.cpu().numpy(), grads[k]) for k, p in _trainable(m3)}
+        assert max(errs.values()) <= tg, (precision, {k: f"{v:.1e}" for k, v in errs.items()})
 
 
 def test_validation_step_and_no_grad():

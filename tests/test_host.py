@@ -181,8 +181,40 @@ def test_configure_optimizers_surface_and_state_dict():
     assert opt.state[next(iter(m.parameters()))]["exp_avg"].data_ptr() == opt._m.data_ptr()
     with pytest.raises(NotImplementedError):
         P.FusedAdam(m.parameters(), amsgrad=True, arena=m.hot_path.arena)
+
+
+def test_consistency_classifier_surface(tmp_path):
+    """lightning.py:44-52: `consistency_classifier_ckpt` loads a frozen EmbeddingClassifier (state-dict keys fc1/fc2/fc3, Lightning
+    checkpoint layout) in eval mode; its weights stay out of the optimiser's arena; the flat layout the library reads is 16-byte aligned."""
+    ec = P.EmbeddingClassifier(input_dim=256, num_classes=2, hidden_dim=128)
+    assert list(ec.state_dict().keys()) == ["fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias", "fc3.weight", "fc3.bias"]
+    assert (ec.input_dim, ec.num_classes, ec.hidden_dim, ec.optimizer_cfg) == (256, 2, 128, {})
+    path = str(tmp_path / "cons.ckpt")
+    torch.save({"state_dict": ec.state_dict(), "hyper_parameters": dict(ec.hparams)}, path)
+    m = _module(consistency_classifier_ckpt=path, consistency_loss_weight=0.7)
+    cc = m.consistency_classifier
+    assert isinstance(cc, P.EmbeddingClassifier) and not cc.training and not any(p.requires_grad for p in cc.parameters())
+    assert all(torch.equal(a, b) for a, b in zip(ec.state_dict().values(), cc.state_dict().values()))
+    assert m.consitency_loss_weight == 0.7
+    opt = m.configure_optimizers()["optimizer"]
+    assert sum(len(g["params"]) for g in opt.param_groups) == 20          # the VAE's 18 + the latent classifier's 2, no fc1..fc3
+    d, flat = cc.flat_params(torch.device("cpu"))
+    assert (d.input_dim, d.hidden_dim, d.num_classes) == (256, 128, 2)
+    assert all(o % 4 == 0 for o in list(d.w) + list(d.b)) and d.total_numel % 64 == 0 and flat.numel() == d.total_numel
+    assert torch.equal(flat[d.w[2]:d.w[2] + 2 * 128].view(2, 128), cc.fc3.weight) and torch.equal(flat[d.b[0]:d.b[0] + 128], cc.fc1.bias)
+    assert cc.flat_params(torch.device("cpu"))[1] is flat                 # cached until a weight changes
+    with torch.no_grad():
+        cc.fc2.bias.add_(1.0)
+    assert cc.flat_params(torch.device("cpu"))[1] is not flat
+    for bad in (dict(input_dim=6, hidden_dim=128, num_classes=2), dict(input_dim=256, hidden_dim=128, num_classes=1)):
+        with pytest.raises(ValueError):
+            P.EmbeddingClassifier(**bad).consistency_desc()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cc(torch.randn(4, 256))
     with pytest.raises(NotImplementedError):
-        _module(consistency_classifier_ckpt="x.ckpt")
+        cc.training_step((torch.randn(4, 256), torch.zeros(4, dtype=torch.long)), 0)
+    lib = L.lib()
+    assert lib.psvae_consistency_workspace_bytes(C.byref(d), 1000, L.MODE_TRAIN) > lib.psvae_consistency_workspace_bytes(C.byref(d), 1000, L.MODE_FORWARD) > 0
 
 
 def test_attribute_surface_of_the_lightning_module():

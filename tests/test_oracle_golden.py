@@ -8,9 +8,10 @@ import pytest
 
 from oracle import philox_ref as P
 from oracle import ps_vae_oracle as O
-from tests.golden_util import GOLDEN, case_batch, case_params, check_summary, load, rel_err
+from tests.golden_util import GOLDEN, case_batch, case_consistency_params, case_params, check_summary, load, rel_err
 
-TRAIN_CASES = ["train_d256_c2", "train_d192_noclf", "train_d512_c3_mlp", "train_d256_norm_cos"]
+TRAIN_CASES = ["train_d256_c2", "train_d192_noclf", "train_d512_c3_mlp", "train_d256_norm_cos", "train_d256_c2_cons",
+               "train_d192_c3_cons_norm_cos"]
 SAMPLE_CASES = ["sample_single", "sample_c3_mlp", "sample_multilabel", "sample_multilabel_1layer"]
 
 
@@ -20,12 +21,13 @@ def _run_train(cfg, z, dtype, tag, tol_out, tol_grad):
     v = {k: np.zeros_like(p) for k, p in params.items()}
     opt = cfg.get("optimizer", dict(lr=1e-3))
     act = (cfg.get("clf") or {}).get("activation", "relu")
+    cons = case_consistency_params(cfg, dtype)
     for s in range(cfg.get("steps", 3)):
         x, y, eps = case_batch(cfg, s, dtype)
         scal, out, grads = O.train_loss_and_grads(
             params, x, y, eps, kl_loss_weight=cfg.get("kl_w", 1.0), classifier_loss_weight=cfg.get("clf_w", 1.0),
             normalize_decoder=cfg.get("normalize_decoder", False), use_cos_loss=cfg.get("use_cos_loss", False),
-            classifier_activation=act)
+            classifier_activation=act, consistency_params=cons, consistency_loss_weight=cfg.get("cons_w", 1.0))
         st = f"{tag}/step{s}"
         assert rel_err(out["x_hat"], z[f"{st}/x_hat"]) <= tol_out
         assert rel_err(out["mu"], z[f"{st}/mu"]) <= tol_out
@@ -36,6 +38,9 @@ def _run_train(cfg, z, dtype, tag, tol_out, tol_grad):
         if cfg.get("clf"):
             assert abs(float(scal["classifier_loss"]) - float(z[f"{st}/log/train_classifier_loss"])) <= tol_out
             assert abs(float(scal["classifier_acc"]) - float(z[f"{st}/log/train_classifier_acc"])) <= 1e-7
+        if cons is not None:
+            assert abs(float(scal["consistency_loss"]) - float(z[f"{st}/log/train_consistency_loss"])) <= tol_out
+            assert abs(float(scal["consistency_acc"]) - float(z[f"{st}/log/train_consistency"])) <= 1e-7
         for k in params:
             check_summary(z, f"{st}/grad", k, grads[k], tol_grad)
         for k in params:
