@@ -10,7 +10,8 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpsvae_b200.so")
+# PSVAE_B200_LIB: load another build of the same ABI instead (A/B timing of two kernel versions in one process tree; tools only)
+LIB_PATH = os.environ.get("PSVAE_B200_LIB") or os.path.join(HERE, "libpsvae_b200.so")
 
 PSVAE_ABI_VERSION = 2
 MAX_LAYERS = 8

@@ -115,14 +115,16 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
 template <typename TAct>
 __global__ void __launch_bounds__(256) latent_fwd_kernel(const float* __restrict__ mu, const float* __restrict__ ls, const float* __restrict__ eps,
                                                          uint64_t seed, uint64_t offset, int64_t first_elem, int64_t n_elems,
-                                                         TAct* __restrict__ z, float* __restrict__ z_f32, float* __restrict__ kl_partials) {
+                                                         TAct* __restrict__ z, float* __restrict__ z_f32, float* __restrict__ kl_partials,
+                                                         TAct* __restrict__ hs) {
+  // hs (optional): sigma * eps / 2 = d z / d log_sigma, stashed for the backward pass (which then needs neither eps nor exp(ls / 2))
   PSVAE_GRID_DEP();
   __shared__ float scratch[32];
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t nq = n_elems >> 2;
   float kl = 0.f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
-    float m[4], l[4], e[4], zz[4];
+    float m[4], l[4], e[4], zz[4], hh[4];
     load_vec<4>(mu + (i << 2), m);
     load_vec<4>(ls + (i << 2), l);
     if (eps) {
@@ -135,20 +137,21 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const float* __restrict
     for (int j = 0; j < 4; ++j) {
       const float sigma = expf(0.5f * l[j]);
       zz[j] = fmaf(sigma, e[j], m[j]);
-      kl += 1.f + l[j] - m[j] * m[j] - expf(l[j]);
+      hh[j] = 0.5f * sigma * e[j];
+      kl += 1.f + l[j] - m[j] * m[j] - sigma * sigma;          // exp(ls) = sigma^2: one exponential per element
     }
     if (z) store_vec<4>(z + (i << 2), zz);
     if (z_f32) store_vec<4>(z_f32 + (i << 2), zz);
+    if (hs) store_vec<4>(hs + (i << 2), hh);
   }
   const float s = block_sum(kl, scratch);
   if (threadIdx.x == 0 && kl_partials) kl_partials[blockIdx.x] = s;
 }
 
-// dmu = dz + (kl_w/B) mu + dmu_clf ;  dls = dz * eps * 0.5 sigma + (kl_w/2B)(exp(ls) - 1)
+// dmu = dz + (kl_w/B) mu + dmu_clf ;  dls = dz * (eps * 0.5 sigma) + (kl_w/2B)(exp(ls) - 1); hs = eps * 0.5 sigma from the forward pass
 template <typename TAct>
 __global__ void __launch_bounds__(256) latent_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
-                                                         const float* __restrict__ eps, uint64_t seed, uint64_t offset, int64_t first_elem,
-                                                         int64_t n_elems, const float* __restrict__ dmu_clf, float kl_over_b,
+                                                         const TAct* __restrict__ hs, int64_t n_elems, const float* __restrict__ dmu_clf, float kl_over_b,
                                                          TAct* __restrict__ dmu, TAct* __restrict__ dls, int qpr, int64_t ld_d) {
   // dmu / dls are [rows][L] views with row stride ld_d (the two halves of one [rows][2L] buffer); qpr = L / 4
   PSVAE_GRID_DEP();
@@ -160,17 +163,11 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const float* __restrict
     load_vec<4>(mu + (i << 2), m);
     load_vec<4>(ls + (i << 2), l);
     if (dmu_clf) load_vec<4>(dmu_clf + (i << 2), c);
-    if (eps) {
-      load_vec<4>(eps + (i << 2), e);
-    } else {
-      const float4 t = philox_normal4(((uint64_t)first_elem >> 2) + (uint64_t)i, seed, offset);
-      e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
-    }
+    load_vec<4>(hs + (i << 2), e);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float sigma = expf(0.5f * l[j]);
       om[j] = g[j] + kl_over_b * m[j] + c[j];
-      ol[j] = g[j] * e[j] * (0.5f * sigma) + 0.5f * kl_over_b * expm1f(l[j]);   // expm1: no cancellation for ls ~ 0
+      ol[j] = fmaf(g[j], e[j], 0.5f * kl_over_b * expm1f(l[j]));   // expm1: no cancellation for ls ~ 0
     }
     const int64_t o = (int64_t)((uint32_t)i / (uint32_t)qpr) * ld_d + (((uint32_t)i % (uint32_t)qpr) << 2);
     store_vec<4>(dmu + o, om);
@@ -300,26 +297,32 @@ struct LossPartials {
 
 __global__ void __launch_bounds__(1024) finalize_losses_kernel(LossPartials lp, float* __restrict__ losses) {
   PSVAE_GRID_DEP();
-  // single block of 1024 threads; each sum is taken in a fixed order (thread-strided partials, then the fixed block tree)
-  __shared__ float scratch[32];
-  const int lane = threadIdx.x;
-  auto sum = [&](const float* p, int n, int stride = 1) {
-    float t = 0.f;
-    for (int i = lane; i < n; i += 1024) t += p[(int64_t)i * stride];
-    const float r = block_sum(t, scratch);
-    __syncthreads();
-    return r;
-  };
-  const float sse = lp.sse ? sum(lp.sse, lp.n_sse) : 0.f;
-  const float kls = lp.kl ? sum(lp.kl, lp.n_kl) : 0.f;
+  // single block of 32 warps; the 12 sums (sse, kl, 4 x nll, 4 x acc, consistency nll / acc) are taken concurrently: sum j belongs to warps
+  // j and j + 16 (even / odd 32-element chunks), each lane adds its strided elements in order, then the fixed shuffle tree -- the
+  // result depends only on the partials, not on timing
+  __shared__ float part[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int job = warp & 15, half = warp >> 4;
+  const float* p = nullptr;
+  int n = 0, stride = 1;
+  if (job == 0) { p = lp.sse; n = lp.n_sse; }
+  else if (job == 1) { p = lp.kl; n = lp.n_kl; }
+  else if (job < 6) { if (job - 2 < lp.n_heads) { p = lp.nll[job - 2]; n = lp.n_ce; stride = lp.ce_stride; } }
+  else if (job < 10) { if (job - 6 < lp.n_heads) { p = lp.acc[job - 6]; n = lp.n_ce; stride = lp.ce_stride; } }
+  else if (job == 10) { p = lp.cons_nll; n = lp.n_cons; }
+  else if (job == 11) { p = lp.cons_acc; n = lp.n_cons; }
+  float t = 0.f;
+  if (p)
+    for (int i = half * 32 + lane; i < n; i += 64) t += p[(int64_t)i * stride];
+  t = warp_sum(t);
+  if (lane == 0) part[warp] = t;
+  __syncthreads();
+  auto total = [&](int j) { return part[j] + part[j + 16]; };
+  const float sse = total(0), kls = total(1);
   float nll[4], acc[4];
-  for (int h = 0; h < 4; ++h) {
-    nll[h] = (h < lp.n_heads) ? sum(lp.nll[h], lp.n_ce, lp.ce_stride) : 0.f;
-    acc[h] = (h < lp.n_heads) ? sum(lp.acc[h], lp.n_ce, lp.ce_stride) : 0.f;
-  }
-  const float cons_nll = lp.n_cons > 0 ? sum(lp.cons_nll, lp.n_cons) : 0.f;
-  const float cons_acc = lp.n_cons > 0 ? sum(lp.cons_acc, lp.n_cons) : 0.f;
-  if (lane == 0) {
+  for (int h = 0; h < 4; ++h) { nll[h] = total(2 + h); acc[h] = total(6 + h); }
+  const float cons_nll = total(10), cons_acc = total(11);
+  if (threadIdx.x == 0) {
     const float recon = sse * lp.recon_scale;
     const float kl = -0.5f * kls * lp.inv_b;
     float clf = 0.f;
@@ -461,6 +464,7 @@ struct ReparamArgs {
   int64_t first_quad;           // global index of this shard's first group of 4 latent elements (row0 * L / 4)
   void* z;                      // [B][L] TZ
   float* kl_part;               // one slot per block
+  void* hs;                     // optional [B][L] TZ: sigma * eps / 2, stashed for the backward pass
 };
 __host__ __device__ __forceinline__ int clf_part_len(int L) { return 8 + CLF_MAXC * L + CLF_MAXC; }   // nll[4] acc[4] dW[8][L] db[8]
 
@@ -532,14 +536,16 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
             if (rp.eps) e = __ldg(reinterpret_cast<const float4*>(rp.eps + el));
             else e = philox_normal4((uint64_t)rp.first_quad + (uint64_t)(el >> 2), rp.seed, rp.offset);
             const float m[4] = {v[j].x, v[j].y, v[j].z, v[j].w}, l[4] = {lv[j].x, lv[j].y, lv[j].z, lv[j].w}, ee[4] = {e.x, e.y, e.z, e.w};
-            float zz[4];
+            float zz[4], hh[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float sigma = expf(0.5f * l[q]);
               zz[q] = fmaf(sigma, ee[q], m[q]);
-              kl += 1.f + l[q] - m[q] * m[q] - expf(l[q]);
+              hh[q] = 0.5f * sigma * ee[q];
+              kl += 1.f + l[q] - m[q] * m[q] - sigma * sigma;      // exp(ls) = sigma^2: one exponential per element
             }
             store_vec<4>(static_cast<TZ*>(rp.z) + el, zz);
+            if (rp.hs) store_vec<4>(static_cast<TZ*>(rp.hs) + el, hh);
           }
         }
       }
@@ -660,7 +666,7 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
     return nullptr;
   };
   if (a.atomic_out) {
-    for (int h = 0; h < 4; ++h) {
+    for (int h = 0; h < a.n_heads; ++h) {
       const float s1 = block_sum(nll[h], scratch);
       const float s2 = block_sum(acc[h], scratch);
       if (t == 0) { part[(int64_t)blockIdx.x * PART + h] = s1; part[(int64_t)blockIdx.x * PART + 4 + h] = s2; }   // losses stay order-fixed: summed by finalize_losses
@@ -747,8 +753,7 @@ __global__ void __launch_bounds__(1024) clf_fused_finish_kernel(const float* __r
 // owns the same 4 latent columns (the grid stride is a multiple of L/4), so it sums them privately; block partials [blocks][2L].
 template <typename TAct>
 __global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
-                                                            const float* __restrict__ eps, uint64_t seed, uint64_t offset, int64_t first_elem,
-                                                            int64_t n_elems, int L, const float* __restrict__ dmu_clf, float kl_over_b,
+                                                            const TAct* __restrict__ hs, int64_t n_elems, int L, const float* __restrict__ dmu_clf, float kl_over_b,
                                                             TAct* __restrict__ dmu, TAct* __restrict__ dls, float* __restrict__ partials,
                                                             float* __restrict__ bias_grad, int64_t ld_d) {
   // dmu / dls: [rows][L] views with row stride ld_d (the two halves of one [rows][2L] buffer)
@@ -765,17 +770,11 @@ __global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restr
     load_vec<4>(mu + (i << 2), m);
     load_vec<4>(ls + (i << 2), l);
     if (dmu_clf) load_vec<4>(dmu_clf + (i << 2), c);
-    if (eps) {
-      load_vec<4>(eps + (i << 2), e);
-    } else {
-      const float4 t = philox_normal4(((uint64_t)first_elem >> 2) + (uint64_t)i, seed, offset);
-      e[0] = t.x; e[1] = t.y; e[2] = t.z; e[3] = t.w;
-    }
+    load_vec<4>(hs + (i << 2), e);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float sigma = expf(0.5f * l[j]);
       om[j] = g[j] + kl_over_b * m[j] + c[j];
-      ol[j] = g[j] * e[j] * (0.5f * sigma) + 0.5f * kl_over_b * expm1f(l[j]);
+      ol[j] = fmaf(g[j], e[j], 0.5f * kl_over_b * expm1f(l[j]));
       sm_[j] += om[j];
       sl_[j] += ol[j];
     }

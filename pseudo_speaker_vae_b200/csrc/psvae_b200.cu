@@ -388,6 +388,7 @@ template <typename TAct> struct StepBufs {
   TAct* he[PSVAE_MAX_LAYERS] = {};
   float *mu = nullptr, *ls = nullptr;
   TAct* z = nullptr;
+  TAct* hs = nullptr;             // sigma * eps / 2 (training): what the backward pass needs of the reparameterisation
   TAct* hd[PSVAE_MAX_LAYERS] = {};
   float* u = nullptr;
   TAct* dxh = nullptr;
@@ -470,6 +471,7 @@ static void plan(const psvae_model_desc* d, int64_t rows, int mode, Bump& b, Ste
       w.mhd[j] = b.take<uint32_t>((int64_t)(n.H / 32) * rows);
     }
   }
+  w.hs = b.take<TAct>(rows * n.L);
   w.dxh = b.take<TAct>(rows * n.D);
   for (int i = 0; i < 2; ++i) w.gd[i] = b.take<TAct>(rows * n.H);
   w.dz = b.take<float>(rows * n.L);
@@ -813,7 +815,8 @@ static int run_step(const StepArgs& a) {
   const bool fuse_latent = clf_fused && a.want_loss;
   int n_kl_used = (int)w.n_kl;
   if (!fuse_latent) {
-    launch_dep(latent_fwd_kernel<TAct>, dim3((unsigned)w.n_kl), dim3(256), 0, st, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, w.z, nullptr, w.kl_part);
+    launch_dep(latent_fwd_kernel<TAct>, dim3((unsigned)w.n_kl), dim3(256), 0, st, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, w.z, nullptr, w.kl_part,
+                                                                  a.want_grads ? w.hs : nullptr);
     count_launch();
     PSVAE_LAUNCH_CHECK("latent_fwd_kernel");
   } else {
@@ -836,7 +839,7 @@ static int run_step(const StepArgs& a) {
     const int blocks = clf_fused_blocks(B);
     const size_t smem = clf_fused_smem_bytes(n.L);
     float* dmu_out = a.want_grads ? w.dmu_clf : nullptr;
-    ReparamArgs rp{ls, a.eps, a.seed, a.offset, first_elem >> 2, w.z, w.kl_part};
+    ReparamArgs rp{ls, a.eps, a.seed, a.offset, first_elem >> 2, w.z, w.kl_part, a.want_grads ? w.hs : nullptr};
     n_kl_used = blocks;
     switch (n.L) {
 #define PSVAE_CLF_CASE(LL)                                                                                                              \
@@ -1024,14 +1027,14 @@ static int run_step(const StepArgs& a) {
     int blocks = ew_grid(B * n.L / 4);
     if (blocks > 4 * PSVAE_NUM_SMS) blocks = 4 * PSVAE_NUM_SMS;
     float* bias_atomic = g_opt.deterministic ? nullptr : G + d->enc_b[n.nh];      // fast mode: atomics into the zeroed gradient, no reduce launch
-    launch_dep(latent_bwd_cs_kernel<TAct>, dim3(blocks), dim3(256), 256 * 8 * sizeof(float), st, w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, n.L, dmu_clf,
+    launch_dep(latent_bwd_cs_kernel<TAct>, dim3(blocks), dim3(256), 256 * 8 * sizeof(float), st, w.dz, mu, ls, w.hs, B * n.L, n.L, dmu_clf,
                                                                              a.kl_w / (float)B, w.dmu, w.dls, w.cpart, bias_atomic, (int64_t)2 * n.L);
     count_launch();
     PSVAE_LAUNCH_CHECK("latent_bwd_cs_kernel");
     if (!bias_atomic) PSVAE_TRY(launch_reduce(w.cpart, 2 * n.L, blocks, G + d->enc_b[n.nh], st));
     last_bias_done = true;
   } else {
-    launch_dep(latent_bwd_kernel<TAct>, dim3(ew_grid(B * n.L / 4)), dim3(256), 0, st, w.dz, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, dmu_clf, a.kl_w / (float)B,
+    launch_dep(latent_bwd_kernel<TAct>, dim3(ew_grid(B * n.L / 4)), dim3(256), 0, st, w.dz, mu, ls, w.hs, B * n.L, dmu_clf, a.kl_w / (float)B,
                                                                   w.dmu, w.dls, n.L / 4, (int64_t)2 * n.L);
     count_launch();
     PSVAE_LAUNCH_CHECK("latent_bwd_kernel");
