@@ -510,32 +510,28 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
   for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const int64_t row0 = tile * CLF_TILE;
     __syncthreads();                                    // previous pass is done with the tile buffers (and W_s is loaded)
-#pragma unroll
-    for (int base = 0; base < CLF_TILE * QPR; base += 8 * CLF_TILE) {     // 8 independent 16-byte loads in flight per thread
-      float4 v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = base + j * CLF_TILE + t;
-        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (i < CLF_TILE * QPR && row0 + i / QPR < B) v[j] = __ldg(reinterpret_cast<const float4*>(mu + (row0 + i / QPR) * L + 4 * (i % QPR)));
-      }
-      if constexpr (REPARAM) {
-        float4 lv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int i = base + j * CLF_TILE + t;
-          lv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (i < CLF_TILE * QPR && row0 + i / QPR < B) lv[j] = __ldg(reinterpret_cast<const float4*>(rp.ls + (row0 + i / QPR) * L + 4 * (i % QPR)));
+    {
+      // phase 1: thread t owns quads t, t + CLF_TILE, ... of the tile (QPR of them).  The loop is kept ROLLED (two quads per trip, the
+      // next trip's mu / log_sigma loads issued before this trip's arithmetic): fully unrolled, 16 copies of Philox + Box-Muller were
+      // 64 KB of code and the warps mostly waited for instruction fetch (ncu: no_instruction was the top stall reason).
+      auto load_q = [&](int j, float4& mv, float4& lv) {
+        const int i = j * CLF_TILE + t;
+        mv = make_float4(0.f, 0.f, 0.f, 0.f);
+        lv = mv;
+        if (row0 + i / QPR < B) {
+          mv = __ldg(reinterpret_cast<const float4*>(mu + (row0 + i / QPR) * L + 4 * (i % QPR)));
+          if constexpr (REPARAM) lv = __ldg(reinterpret_cast<const float4*>(rp.ls + (row0 + i / QPR) * L + 4 * (i % QPR)));
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int i = base + j * CLF_TILE + t;
-          if (i < CLF_TILE * QPR && row0 + i / QPR < B) {
+      };
+      auto do_q = [&](int j, const float4& mv, const float4& lv) {
+        const int i = j * CLF_TILE + t;
+        if constexpr (REPARAM) {
+          if (row0 + i / QPR < B) {
             const int64_t el = (row0 + i / QPR) * L + 4 * (i % QPR);
             float4 e;
             if (rp.eps) e = __ldg(reinterpret_cast<const float4*>(rp.eps + el));
             else e = philox_normal4((uint64_t)rp.first_quad + (uint64_t)(el >> 2), rp.seed, rp.offset);
-            const float m[4] = {v[j].x, v[j].y, v[j].z, v[j].w}, l[4] = {lv[j].x, lv[j].y, lv[j].z, lv[j].w}, ee[4] = {e.x, e.y, e.z, e.w};
+            const float m[4] = {mv.x, mv.y, mv.z, mv.w}, l[4] = {lv.x, lv.y, lv.z, lv.w}, ee[4] = {e.x, e.y, e.z, e.w};
             float zz[4], hh[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -548,11 +544,22 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
             if (rp.hs) store_vec<4>(static_cast<TZ*>(rp.hs) + el, hh);
           }
         }
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int i = base + j * CLF_TILE + t;
-        if (i < CLF_TILE * QPR) *reinterpret_cast<float4*>(mu_s + (i / QPR) * ldm + 4 * (i % QPR)) = v[j];
+        *reinterpret_cast<float4*>(mu_s + (i / QPR) * ldm + 4 * (i % QPR)) = mv;
+      };
+      static_assert(QPR % 2 == 0, "two quads per trip");
+      float4 m0, l0, m1, l1;
+      load_q(0, m0, l0);
+      load_q(1, m1, l1);
+#pragma unroll 1
+      for (int j = 0; j < QPR; j += 2) {
+        float4 nm0 = m0, nl0 = l0, nm1 = m1, nl1 = l1;
+        if (j + 2 < QPR) {
+          load_q(j + 2, nm0, nl0);
+          load_q(j + 3, nm1, nl1);
+        }
+        do_q(j, m0, l0);
+        do_q(j + 1, m1, l1);
+        m0 = nm0; l0 = nl0; m1 = nm1; l1 = nl1;
       }
     }
     __syncthreads();

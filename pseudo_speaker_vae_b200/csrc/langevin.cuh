@@ -246,6 +246,9 @@ namespace psvae {
 // ONE THREAD PER SAMPLE: z lives in registers for all steps, the head weights are broadcast reads from shared memory, the noise comes
 // from the same counter-based generator with the same counters as the generic kernel (so both produce the same z up to fp32 summation
 // order).  No __syncthreads and no shared-memory traffic for z inside the loop: the step is pure ALU/SFU work (Philox + Box-Muller).
+// The generator runs in a ROLLED loop (two Philox blocks per trip) that parks the step's L normals in the thread's own column of a
+// shared-memory buffer; the fully unrolled form (L/4 inlined copies of Philox + Box-Muller per step, > 50 KB of code) ran out of
+// instruction cache -- the same "no_instruction" stall ncu showed on the train step's classifier pass.
 // ------------------------------------------------------------------------------------------------
 constexpr int LGF_THREADS = 128;
 
@@ -258,6 +261,7 @@ __global__ void __launch_bounds__(LGF_THREADS) langevin_fast_kernel(LangevinClf 
   __shared__ __align__(16) float W[CLF_LG_MAXC * L];
   __shared__ float bias[CLF_LG_MAXC];
   __shared__ int cls_head[CLF_LG_MAXC];
+  __shared__ float4 nz_s[L / 4][LGF_THREADS];            // this thread's normals of the current step: column threadIdx.x (conflict-free 16-byte accesses)
   // flatten the targeted heads' rows: class index cc -> (head, class)
   int n_cls = 0;
   for (int h = 0; h < c.n_heads; ++h) {
@@ -275,10 +279,15 @@ __global__ void __launch_bounds__(LGF_THREADS) langevin_fast_kernel(LangevinClf 
   const int64_t rr = live ? r : rows - 1;                 // dead lanes shadow the last row (no stores) so that warp-collectives stay converged
   const uint64_t q0 = (uint64_t)((row0 + rr) * L) >> 2;   // first Philox block of this row
   float z[L];
+  auto draw = [&](uint64_t offset) {
+#pragma unroll 2
+    for (int q = 0; q < L / 4; ++q) nz_s[q][threadIdx.x] = philox_normal4(q0 + q, seed, offset);
+  };
   if (init_from_philox) {
+    draw(offset0);
 #pragma unroll
     for (int q = 0; q < L / 4; ++q) {
-      const float4 t = philox_normal4(q0 + q, seed, offset0);
+      const float4 t = nz_s[q][threadIdx.x];
       z[4 * q] = t.x; z[4 * q + 1] = t.y; z[4 * q + 2] = t.z; z[4 * q + 3] = t.w;
     }
   } else {
@@ -346,14 +355,12 @@ __global__ void __launch_bounds__(LGF_THREADS) langevin_fast_kernel(LangevinClf 
       }
     }
     // z <- z + 0.5 s^2 (W^T coef - z) + s * noise_weight * N(0, I)
+    if (!noise) draw(offset0 + 1 + (uint64_t)step);
 #pragma unroll
     for (int q = 0; q < L / 4; ++q) {
       float nz[4];
-      if (noise) {
-        const float4 t = *reinterpret_cast<const float4*>(noise + ((int64_t)step * rows + rr) * L + 4 * q);
-        nz[0] = t.x; nz[1] = t.y; nz[2] = t.z; nz[3] = t.w;
-      } else {
-        const float4 t = philox_normal4(q0 + q, seed, offset0 + 1 + (uint64_t)step);
+      {
+        const float4 t = noise ? *reinterpret_cast<const float4*>(noise + ((int64_t)step * rows + rr) * L + 4 * q) : nz_s[q][threadIdx.x];
         nz[0] = t.x; nz[1] = t.y; nz[2] = t.z; nz[3] = t.w;
       }
       float g[4] = {0.f, 0.f, 0.f, 0.f};
