@@ -293,9 +293,9 @@ def main():
     value = B * n_gpus * K / (ms * 1e-3)
     tflops = value * FLOPS_PER_SAMPLE / 1e12
     peak = peaks["bf16_sustained"] * n_gpus
-    # dram__bytes_read.sum + dram__bytes_write.sum over the 29 launches of one step, from the ncu pass of this same command
-    # (profiles/r01_launches_v11_time_dram.csv: 1.961 GB read + 0.261 GB written at B = 65,536, bf16, one GPU); null for any other config
-    traffic = 2_222_543_104 if (B == 65536 and args.precision == "bf16" and not args.opt) else None
+    # dram__bytes_read.sum + dram__bytes_write.sum over the 24 launches of one step, from the ncu pass of this same command
+    # (profiles/r01_launches_v15_time_dram.csv at B = 65,536, bf16, one GPU); null for any other config
+    traffic = 2_397_704_192 if (B == 65536 and args.precision == "bf16" and not args.opt) else None
     roofline = dict(bound="tensor", achieved=tflops, peak=peak, unit="TFLOP/s", frac=tflops / peak, traffic=traffic,
                     note=f"whole fused step (all launches): {FLOPS_PER_SAMPLE} algorithmic FLOP/sample x {B * n_gpus} samples / measured step time; "
                          f"peak = sustained bf16 {peaks['source']}" + ("" if args.precision == "bf16" else " [fp32 parity mode runs on CUDA cores]"))
@@ -307,6 +307,30 @@ def main():
                             global_batch=B * n_gpus, parallelism=f"dp{n_gpus}", l2="4 distinct 67 MB input batches rotated (268 MB > 126 MB L2)",
                             eps="in-kernel Philox4x32-10", options={kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt}, allreduce="1 bucket, flat fp32 grads 5.13 MB, NCCL" if dist_on else "none (1 GPU)"),
                 clocks=clocks, gpu_launches=launches, roofline=roofline)
+
+    if not args.no_secondary and args.precision == "bf16":
+        # ---- the dominant kernel alone (hidden Linear 512 x 512 + bias + ReLU + mask: the shape of 6 of the step's GEMMs), timed live with
+        #      CUDA events on rotating operand sets (3 x 67 MB in, 3 x 67 MB out: every launch streams from HBM as inside the step)
+        hk = HID
+        a_sets = [(torch.randn(B, hk, device=dev) * 0.1).to(torch.bfloat16) for _ in range(3)]
+        o_sets = [torch.empty(B, hk, device=dev, dtype=torch.bfloat16) for _ in range(3)]
+        wk = (torch.randn(hk, hk, device=dev) * 0.05).to(torch.bfloat16)
+        bk = torch.zeros(hk, device=dev)
+        mk = torch.empty(hk // 32 * B, device=dev, dtype=torch.int32)
+        stp = torch.cuda.current_stream().cuda_stream
+
+        def probe(n):
+            for i in range(n):
+                L.check(L.lib().psvae_gemm_probe(a_sets[i % 3].data_ptr(), wk.data_ptr(), bk.data_ptr(), o_sets[i % 3].data_ptr(), mk.data_ptr(), None,
+                                                 B, hk, hk, 0, stp))
+        probe(6)
+        torch.cuda.synchronize()
+        us_k = time_events(lambda: probe(30), torch, False) * 1e3 / 30
+        fl_k = 2.0 * B * hk * hk
+        roofline["dominant_kernel"] = dict(name="gemm_tc_kernel<256, K-major, K-major, EpiBiasAct<bf16, relu>, cta_group::2> (hidden Linear 512x512)",
+                                           flops_per_launch=fl_k, us_per_launch=us_k, achieved=fl_k / us_k / 1e6, unit="TFLOP/s",
+                                           frac=fl_k / us_k / 1e6 / peaks["bf16_sustained"], frac_of_burst_peak=fl_k / us_k / 1e6 / peaks["bf16_burst"])
+        del a_sets, o_sets
 
     if not args.no_secondary:
         # ---- e2e: the public Lightning-style API with host inputs every step -----------------------------------------

@@ -96,8 +96,11 @@ class DataParallelTrainer:
         """One optimiser step on this rank's shard.  Returns the device tensor of local loss scalars."""
         m, hot = self.module, self.hot
         gflat = hot.arena.stage_buffer() if self._views_of is None else self._views_of
-        losses, gflat, _ = hot.step(x_local, y_local, eps_local, kl_weight=m.kl_loss_weight, clf_weight=m.classifier_loss_weight,
-                                    use_cos_loss=m.use_cos_loss, compute_grads=True, grads=gflat)
+        cons = getattr(m, "consistency_classifier", None)
+        losses, gflat, _ = hot.step(x_local, y_local if m.classifier is not None else None, eps_local, kl_weight=m.kl_loss_weight,
+                                    clf_weight=m.classifier_loss_weight, use_cos_loss=m.use_cos_loss, compute_grads=True, grads=gflat,
+                                    consistency=cons, consistency_y=y_local if cons is not None else None,
+                                    consistency_weight=m.consitency_loss_weight)
         all_reduce_flat(gflat, self.bucket_bytes, self.group)
         if self._views_of is not gflat:        # bind .grad views once; the same flat buffer is reused every step
             for (p, _), v in zip(hot.arena.entries, hot.arena.grad_views(gflat)):

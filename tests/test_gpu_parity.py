@@ -652,6 +652,37 @@ def test_data_parallel_trainer_single_process_matches_manual_steps():
             check_summary(z, f"f64/step{s}/param", k, p.detach().cpu().numpy(), FP32_TOL)
 
 
+def test_pinned_batch_loader_feeds_the_fused_step(tmp_path):
+    """Data plane on the device: the double-buffered pinned loader delivers exactly the rows the host loader delivers,
+    while a training loop consumes them (copy of batch k+1 under the step of batch k), including a ragged last batch."""
+    import pseudo_speaker_vae_b200 as P
+
+    G = _gu()
+    n, dim = 1000, 256
+    x, y, _ = O.synth_batch(n, dim, 64, 2, seed=21)
+    st = P.PackedEmbeddingStore.build(str(tmp_path / "packed"), ((torch.from_numpy(x[i]), int(y[i])) for i in range(n)), n, dim, ["gender"])
+    host = list(P.PinnedBatchLoader(st, 384, device="cpu", shuffle=True, seed=4))
+    z, cfg = load("train_d256_c2")
+    module = G.module_from_cfg(cfg, "bf16")
+    opt = module.configure_optimizers()["optimizer"]
+    dev_loader = P.PinnedBatchLoader(st, 384, device=G.DEV, shuffle=True, seed=4)
+    assert len(dev_loader) == len(host) == 3
+    losses = []
+    for (hx, hy), (dx, dy) in zip(host, dev_loader):
+        assert dx.is_cuda and torch.equal(dx.cpu(), hx) and torch.equal(dy.cpu(), hy)
+        opt.zero_grad()
+        loss = module.training_step((dx, dy), 0)["loss"]
+        loss.backward()
+        opt.step()
+        losses.append(loss)
+    torch.cuda.synchronize()
+    assert all(torch.isfinite(l) for l in losses) and [b[0].shape[0] for b in host] == [384, 384, 232]
+    # a second epoch reuses the staging buffers and reshuffles
+    dev_loader.set_epoch(1)
+    second = [dx.cpu() for dx, _ in dev_loader]
+    assert not torch.equal(second[0], host[0][0]) and sum(b.shape[0] for b in second) == n
+
+
 def test_deterministic_option_and_fast_mode_agree():
     """Default (fast) tcgen05 mode accumulates split-K / bias partials with TMA reduce-add and atomics (order not fixed);
     the "deterministic" option routes them through ordered two-stage sums: bit-identical from run to run, and within fp32

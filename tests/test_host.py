@@ -285,3 +285,84 @@ def test_target_lookup_and_sharding_arithmetic():
     sl = parallel.bucket_slices(1281600, 1 << 20)
     assert sl[0] == (0, 262144) and sl[-1][1] == 1281600 and all(a1 == b0 for (_, a1), (b0, _) in zip(sl, sl[1:]))
     assert len(parallel.bucket_slices(1281600)) == 1 and len(parallel.bucket_slices(41313026)) == 7
+
+
+# ------------------------------------------------------------------------------------------------
+# data plane: packed store + batch loader, host side
+# ------------------------------------------------------------------------------------------------
+def _fake_cv(tmp_path, n=37, dim=24):
+    """A Common-Voice-style tree as ps_vae/data/cv.py:31-52 expects it: <root>/<split>.tsv + <root>/embeds_sb/<split>/*.pth"""
+    root = tmp_path / "cv"
+    (root / "embeds_sb" / "train").mkdir(parents=True)
+    g = torch.Generator().manual_seed(5)
+    genders, ages = ["male", "female", "other", "n/a"], ["teens", "thirties", "sixties", "nineties", "unknown"]
+    rows, truth = ["client_id\tpath\tage\tgender"], {}
+    for i in range(n):
+        name = f"common_voice_{i:04d}"
+        e = torch.randn(1, dim, 1, generator=g)                       # FreeVC speaker embeddings are stored as (1, D, 1)
+        torch.save(e, root / "embeds_sb" / "train" / f"{name}.pth")
+        ge, ag = genders[i % len(genders)], ages[i % len(ages)]
+        rows.append(f"c{i}\t{name}.mp3\t{ag}\t{ge}")
+        truth[f"{name}.pth"] = (e.squeeze(), ge, ag)
+    rows.append("c_extra\tnot_exported.mp3\tteens\tmale")               # metadata without an embedding file is ignored (cv.py:50-52)
+    (root / "train.tsv").write_text("\n".join(rows) + "\n", encoding="utf-8")
+    return str(root), truth
+
+
+def test_packed_store_serves_what_the_reference_dataset_serves(tmp_path):
+    from pseudo_speaker_vae_b200 import data as D
+
+    root, truth = _fake_cv(tmp_path)
+    st = D.PackedEmbeddingStore.from_cv(root, str(tmp_path / "packed_g"), split="train", se_model="sb", metadata_transform="gender")
+    assert len(st) == 37 and st.dim == 24 and st.label_names == ["gender"] and not st.multilabel
+    for i in (0, 5, 36):
+        e, y = st[i]
+        ref_e, ge, _ = truth[st.files[i]]
+        assert torch.equal(e, ref_e) and y == P.map_cv_gender_to_label(ge)       # unknown gender 'n/a' -> -1, bit-exact table
+    ml = D.PackedEmbeddingStore.from_cv(root, str(tmp_path / "packed_ag"), metadata_transform="age_and_gender")
+    e, y = ml[7]
+    _, ge, ag = truth[ml.files[7]]
+    assert y == {"age": P.map_cv_age_to_label(ag), "gender": P.map_cv_gender_to_label(ge)} and ml.multilabel
+    bare = D.PackedEmbeddingStore.from_cv(root, str(tmp_path / "packed_none"))
+    assert bare[3][1] == {} and bare.label_names == []
+    with pytest.raises(AssertionError):
+        D.PackedEmbeddingStore.from_cv(root, str(tmp_path / "x"), metadata_transform="height")
+    reopened = D.PackedEmbeddingStore(str(tmp_path / "packed_g"))
+    assert np.array_equal(reopened.embeddings, st.embeddings) and np.array_equal(reopened.labels, st.labels)
+
+
+def test_batch_loader_order_sharding_and_split(tmp_path):
+    from pseudo_speaker_vae_b200 import data as D
+
+    root, _ = _fake_cv(tmp_path)
+    st = D.PackedEmbeddingStore.from_cv(root, str(tmp_path / "packed"), metadata_transform="age_and_gender")
+    X, Y = torch.from_numpy(np.array(st.embeddings)), torch.from_numpy(np.array(st.labels))
+    seq = D.PinnedBatchLoader(st, 16, device="cpu", shuffle=False)
+    batches = list(seq)
+    assert len(seq) == 3 and [b[0].shape[0] for b in batches] == [16, 16, 5]            # ragged last batch kept
+    assert torch.equal(torch.cat([b[0] for b in batches]), X) and torch.equal(torch.cat([b[1]["gender"] for b in batches]), Y[1])
+    assert len(D.PinnedBatchLoader(st, 16, device="cpu", shuffle=False, drop_last=True)) == 2
+    # the shards are exactly torch's DistributedSampler's (same permutation, same padding), epoch by epoch
+    from torch.utils.data import DistributedSampler
+
+    for epoch in (0, 3):
+        seen = []
+        for r in range(2):
+            ld = D.PinnedBatchLoader(st, 8, device="cpu", shuffle=True, seed=11, rank=r, world_size=2)
+            ld.set_epoch(epoch)
+            ds = DistributedSampler(st, num_replicas=2, rank=r, shuffle=True, seed=11)
+            ds.set_epoch(epoch)
+            want = np.array(list(ds))
+            got_x = torch.cat([b[0] for b in ld])
+            assert torch.equal(got_x, X[want])
+            seen.append(want)
+        assert len(seen[0]) == len(seen[1]) == 19 and set(np.concatenate(seen)) == set(range(37))
+    both = D.get_packed_dataloaders(st, batch_size=8, train_frac=0.8, device="cpu", seed=3)
+    tr = np.concatenate([b[0].numpy() for b in both["train"]])
+    va = np.concatenate([b[0].numpy() for b in both["val"]])
+    assert len(tr) == int(37 * 0.8) and len(tr) + len(va) == 37
+    rows = {tuple(r) for r in np.round(X.numpy(), 6).tolist()}
+    assert {tuple(r) for r in np.round(tr, 6).tolist()} | {tuple(r) for r in np.round(va, 6).tolist()} == rows       # a partition of the store
+    single = D.PackedEmbeddingStore.from_cv(root, str(tmp_path / "packed1"), metadata_transform="gender")
+    x, y = next(iter(D.PinnedBatchLoader(single, 4, device="cpu", shuffle=False)))
+    assert y.dtype == torch.int64 and y.tolist() == single.labels[0, :4].tolist()
