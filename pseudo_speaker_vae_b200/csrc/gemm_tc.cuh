@@ -49,7 +49,11 @@ constexpr int TC_MAX_STAGES = 12;          // barrier slots of the operand ring
 // the CTA's row tiles (every CTA keeps one N tile: the grid is a multiple of the number of N tiles); only the activation tile streams
 // through the ring.  Per 256 x 256 x 512 tile this takes the weight re-read (256 KB per tile and pair) out of the L2 -> SM traffic, which
 // is what bounds these GEMMs.  The staged output block shrinks to 32 columns to make room.
-template <int BN, class Epi, int CG = 1, bool BRES = false> struct TcCfg {
+// ALIAS (split-K / wgrad launches in which no CTA gets more than one tile): the epilogue staging blocks overlay the first stages of the
+// operand ring -- the single epilogue of the CTA starts after its last MMA has retired and no further load is issued, so the ring is dead
+// by then -- and the ring gets the 64 KB back: 7 stages (224 KB in flight per SM) instead of 5 for the HBM-latency-bound wgrad form.
+template <int BN, class Epi, int CG = 1, bool BRES = false, bool ALIAS = false> struct TcCfg {
+  static_assert(!(ALIAS && BRES), "ALIAS: streaming operands only");
   static constexpr int kEpiWarps = tc_epi_warps(BN);
   static constexpr int kThreads = 32 * (2 + kEpiWarps);
   static constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
@@ -67,14 +71,15 @@ template <int BN, class Epi, int CG = 1, bool BRES = false> struct TcCfg {
   static constexpr int kTmemCols = 2 * BN;     // power of two >= 32 for BN in {64,128,256}
   // layout: [barriers][epilogue staging][resident B (BRES; runtime size)][operand ring]
   static constexpr int kBarOff = 0;
-  static constexpr int kEpiOff = TC_BAR_BYTES;
-  static constexpr int kOpOff = kEpiOff + kEpiBytes;
+  static constexpr int kOpOff = ALIAS ? TC_BAR_BYTES : TC_BAR_BYTES + kEpiBytes;
+  static constexpr int kEpiOff = ALIAS ? kOpOff : TC_BAR_BYTES;
   static_assert(kOpOff % 1024 == 0, "operand tiles need 1024-byte alignment");
   static constexpr int kOpBudget = TC_SMEM_MAX - 1024 /*align slack*/ - kOpOff;
-  static constexpr int kMaxStages = BRES ? TC_MAX_STAGES : (CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
+  static constexpr int kMaxStages = (BRES || ALIAS) ? TC_MAX_STAGES : (CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int kFit = kOpBudget / kStageBytes;          // !BRES: stages that fit
   static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
   static_assert(BRES || kStages >= 2, "operand ring too shallow");
+  static_assert(!ALIAS || kStages * kStageBytes >= kEpiBytes, "ALIAS: the staging blocks must fit inside the ring");
   static constexpr int kSmemBytes = BRES ? TC_SMEM_MAX : kOpOff + kStages * kStageBytes + 1024 /*align slack*/;
   // BRES: ring depth left after kb_total resident k-blocks of B (host side; < 3 means: use the streaming kernel)
   static constexpr int res_stages(int64_t kb_total) {
@@ -119,11 +124,12 @@ template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
 // CL = 2 (only with CG = 2, K-major A, streaming B): clusters of two CTA pairs that work on the same row tile and adjacent N tiles; every CTA
 // loads HALF of its 128 activation rows per k-block and multicasts them to its twin in the other pair, so the activation tile crosses the
 // L2 -> SM fabric once per cluster instead of once per pair (-25 % operand traffic per pair, ring depth unchanged).
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL, bool ALIAS = false>
 __global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
                const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_apf, TcShape s, Epi epi) {
-  using Cfg = TcCfg<BN, Epi, CG, BRES>;
+  using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS>;
+  static_assert(!ALIAS || (Epi::kSplit && Epi::kAuxBytes == 0 && CL == 1), "ALIAS: split-K store epilogue, one tile per CTA (host-checked)");
   using TOut = typename Epi::TOut;
   constexpr int STAGES = TC_MAX_STAGES;                    // barrier slots; s.stages of them are in use
   constexpr int EPI_WARPS = Cfg::kEpiWarps;
@@ -740,6 +746,7 @@ int tc_tile_prefetch();   // option "tc_tile_prefetch"
 int tc_pair_cluster();    // option "tc_pair_cluster": clusters of two CTA pairs with the activation tile multicast between them
 int tc_b_stable();        // set by the train step / decode around GEMMs whose B operand is the (long since written) weight arena
 int tc_prefetch_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out);
+int tc_alias_staging();   // option "tc_alias_staging": wgrad launches with one tile per CTA overlay the epilogue staging on the operand ring
 int tc_b_resident();      // option "tc_b_resident": keep the weight block of the CTA's N tile in shared memory where it fits
 // does this shape run as CTA pairs?  (BN = 256 tiles and more than one 128-row block of M)
 static inline bool tc_use_pair(int64_t M, int N, int force_bn = 0) {
@@ -774,10 +781,10 @@ template <class Epi> struct epi_split_stride<Epi, std::enable_if_t<Epi::kSplit>>
 template <class Epi, class = void> struct epi_cs_atomic { static bool get(const Epi&) { return false; } };
 template <class Epi> struct epi_cs_atomic<Epi, std::enable_if_t<Epi::kColSum>> { static bool get(const Epi& e) { return e.colsum_atomic != 0; } };
 
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false, int CL = 1>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false, int CL = 1, bool ALIAS = false>
 int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st,
                       const TcGroup& grp = TcGroup()) {
-  using Cfg = TcCfg<BN, Epi, CG, BRES>;
+  using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS>;
   using TOut = typename Epi::TOut;
   CUtensorMap ta, tb, tout, taux, tapf;
   // grouped: K is one group's contraction length; A spans all groups' k ranges, an MN-major B all groups' k rows
@@ -813,7 +820,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   } else {
     taux = ta;
   }
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, BRES, CL>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, BRES, CL, ALIAS>;
   static unsigned long long attr_mask = 0;   // per instantiation, one bit per device
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
@@ -827,6 +834,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   const int64_t cs_rows = (tiles < grid ? tiles : (int64_t)grid) * CG * 4;     // = 4 * tc_ctas(): what the caller's ordered reduce reads
   if (BRES) grid = (int)((grid / n_tiles) * n_tiles);     // every CTA (pair) keeps one N tile: its weight block is loaded once
   if (tiles < grid) grid = (int)tiles;
+  if (ALIAS && tiles > grid) { set_error("gemm_tc: staging/ring overlay needs at most one tile per CTA (%lld tiles, %d CTAs)", (long long)tiles, grid); return -2; }
   grid = grid / CL * CL;                     // whole clusters of CL pairs (the caller guarantees an even tile count for CL = 2)
   grid *= CG;
   if (grid < 1) return 0;
@@ -888,6 +896,12 @@ int gemm_tc_launch_pick(const TcOperand& A, const TcOperand& B, int64_t M, int N
     if (tc_b_resident() && grp.groups == 1 && splits <= 1 && (tc_grid_size() / CG) % n_tiles == 0 && ceil_div64(M, TC_BM * CG) * n_tiles >= tc_grid_size() / CG &&
         CfgR::res_stages(ceil_div64(K, TC_BK)) >= 3)
       return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, true>(A, B, M, N, K, splits, epi, st);
+  }
+  if constexpr (A_MN && Epi::kSplit && Epi::kAuxBytes == 0) {
+    // wgrad form, at most one tile per CTA (pair): the epilogue staging overlays the operand ring (two more stages in flight)
+    const int64_t tiles = ceil_div64(M, TC_BM * CG) * ceil_div64(N, BN) * (splits < 1 ? 1 : splits);
+    if (tc_alias_staging() && grp.groups == 1 && tiles <= tc_grid_size() / CG)
+      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 1, true>(A, B, M, N, K, splits, epi, st, grp);
   }
   if constexpr (!A_MN && CG == 2) {
     // clusters of two pairs sharing the activation tile: an even number of N tiles, whole clusters, and enough tiles to fill the grid

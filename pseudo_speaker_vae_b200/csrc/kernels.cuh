@@ -97,9 +97,17 @@ __global__ void __launch_bounds__(256) philox_normal_kernel(T* __restrict__ out,
 }
 
 // ---------------------------------------------------------------- casts
-__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+// zero_buf (optional): `zero_n` floats (a multiple of 4) cleared by the same pass -- the train step's gradient buffer, which the
+// backward kernels then accumulate into; a separate memset node would also break the programmatic-launch chain between the optimiser
+// pass of the previous step and this kernel
+__global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n, float* __restrict__ zero_buf,
+                                                        int64_t zero_n) {
   PSVAE_GRID_DEP();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (zero_buf) {
+    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < (zero_n >> 2); i += stride) reinterpret_cast<float4*>(zero_buf)[i] = z4;
+  }
   const int64_t n8 = n >> 3;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
     float v[8];

@@ -63,6 +63,8 @@ struct Options {
   int64_t tc_tile_prefetch = 0;        // 1: the producer pulls the NEXT tile's whole activation panel into L2 with wide-box prefetches at the start of each tile
   int64_t tc_pair_cluster = 0;         // 1: forward / dgrad GEMMs with an even number of N tiles run as clusters of two CTA pairs (activation tile multicast).
                                        //    Measured: +7 % per SM, but only 33 clusters of 4 are co-resident (132 of 148 SMs) -> 39.3 vs 37.4 us; off by default
+  int64_t tc_alias_staging = 0;        // 1: split-K (wgrad) launches with at most one tile per CTA overlay the epilogue staging on the operand ring (7 stages instead of 5).
+                                       //    Measured neutral (31.4 vs 31.7 us for the 512 x 512 wgrad): the wgrad form is not bound by bytes in flight; off by default
   int64_t tc_grouped = 1;              // 1: layers 1..n of the two encoders run as ONE block-diagonal launch each (forward and dgrad) instead of one per encoder
   int64_t pdl = 1;                     // 1: kernels are launched with programmatic stream serialization (their prologue overlaps the predecessor's tail)
   int64_t tc_trace_ptr = 0;            // profiling: device pointer of gridDim.x * 16 cycle counters the GEMM kernels fill (0 = off)
@@ -111,6 +113,7 @@ int tc_prefetch_distance() { return (int)g_opt.tc_prefetch; }
 int tc_two_cta() { return (int)g_opt.tc_two_cta; }
 int tc_max_stages() { return (int)g_opt.tc_max_stages; }
 int tc_b_resident() { return (int)g_opt.tc_b_resident; }
+int tc_alias_staging() { return (int)g_opt.tc_alias_staging; }
 bool pdl_enabled() { return g_opt.pdl != 0; }
 int tc_pair_cluster() { return (int)g_opt.tc_pair_cluster; }
 static thread_local int g_b_stable = 0;
@@ -754,7 +757,9 @@ static int run_step(const StepArgs& a) {
   const TAct* Wt = weights_of<TAct>(a);
   const float* P = a.params;
   // gradients are accumulated into (TMA reduce-add / atomics in fast tcgen05 mode) or written into a zeroed buffer; padding reads as zero
-  if (a.want_grads) PSVAE_CUDA(cudaMemsetAsync(a.grads, 0, (size_t)d->total_numel * sizeof(float), st));
+  // (tcgen05 mode: the operand cast of x below clears the buffer in the same pass -- total_numel is a multiple of 64 and the buffer 16-byte aligned)
+  const bool zero_in_cast = sizeof(TAct) == 2 && a.want_grads && (reinterpret_cast<uintptr_t>(a.grads) & 15) == 0;
+  if (a.want_grads && !zero_in_cast) PSVAE_CUDA(cudaMemsetAsync(a.grads, 0, (size_t)d->total_numel * sizeof(float), st));
   float* mu = a.mu ? a.mu : w.mu;
   float* ls = a.ls ? a.ls : w.ls;
   const int64_t first_elem = a.row0 * n.L;
@@ -762,7 +767,8 @@ static int run_step(const StepArgs& a) {
   // ---- encoders (model.py:54-55).  Layer 0 of both encoders is one [2H, D] GEMM.
   const TAct* xa;
   if constexpr (sizeof(TAct) == 2) {
-    launch_dep(cast_bf16_kernel, dim3(ew_grid(B * n.D / 8)), dim3(256), 0, st, a.x, w.xa, B * n.D);
+    launch_dep(cast_bf16_kernel, dim3(ew_grid(B * n.D / 8)), dim3(256), 0, st, a.x, w.xa, B * n.D, zero_in_cast ? a.grads : (float*)nullptr,
+               zero_in_cast ? d->total_numel : (int64_t)0);
     count_launch();
     PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
     xa = w.xa;
@@ -1143,7 +1149,7 @@ static int run_decode(const psvae_model_desc* d, const float* params, const bf16
     const TAct* zin;
     if (z) {
       if constexpr (sizeof(TAct) == 2) {
-        launch_dep(cast_bf16_kernel, dim3(ew_grid(nel / 8)), dim3(256), 0, st, z + r0 * n.L, w.z, nel);
+        launch_dep(cast_bf16_kernel, dim3(ew_grid(nel / 8)), dim3(256), 0, st, z + r0 * n.L, w.z, nel, (float*)nullptr, (int64_t)0);
         count_launch();
         PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
         zin = w.z;
@@ -1158,7 +1164,7 @@ static int run_decode(const psvae_model_desc* d, const float* params, const bf16
         count_launch();
         PSVAE_LAUNCH_CHECK("philox_normal_kernel");
         if constexpr (sizeof(TAct) == 2) {
-          launch_dep(cast_bf16_kernel, dim3(ew_grid(nel / 8)), dim3(256), 0, st, z_out + r0 * n.L, w.z, nel);
+          launch_dep(cast_bf16_kernel, dim3(ew_grid(nel / 8)), dim3(256), 0, st, z_out + r0 * n.L, w.z, nel, (float*)nullptr, (int64_t)0);
           count_launch();
           PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
           zin = w.z;
@@ -1217,6 +1223,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_trace_ptr")) { g_opt.tc_trace_ptr = value; return 0; }
   if (!strcmp(name, "pdl")) { g_opt.pdl = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_grouped")) { g_opt.tc_grouped = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_alias_staging")) { g_opt.tc_alias_staging = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_pair_cluster")) { g_opt.tc_pair_cluster = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
@@ -1238,6 +1245,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_b_resident")) return g_opt.tc_b_resident;
   if (!strcmp(name, "pdl")) return g_opt.pdl;
   if (!strcmp(name, "tc_grouped")) return g_opt.tc_grouped;
+  if (!strcmp(name, "tc_alias_staging")) return g_opt.tc_alias_staging;
   if (!strcmp(name, "tc_pair_cluster")) return g_opt.tc_pair_cluster;
   if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;
@@ -1368,7 +1376,8 @@ int psvae_refresh_shadow(const psvae_model_desc* desc, const float* params, void
   PSVAE_TRY(tc_device_check());
   if (!desc || !params || !shadow_bf16) { set_error("desc, params, shadow must not be NULL"); return -1; }
   const int64_t n = desc->total_numel;
-  launch_dep(cast_bf16_kernel, dim3(ew_grid(n / 8 + 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), params, static_cast<bf16*>(shadow_bf16), n);
+  launch_dep(cast_bf16_kernel, dim3(ew_grid(n / 8 + 1)), dim3(256), 0, static_cast<cudaStream_t>(stream), params, static_cast<bf16*>(shadow_bf16), n,
+             (float*)nullptr, (int64_t)0);
   count_launch();
   PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
   return 0;

@@ -719,11 +719,11 @@ def test_deterministic_option_and_fast_mode_agree():
 
 
 @pytest.mark.parametrize("opts", [dict(tc_pair_cluster=1), dict(tc_b_resident=1), dict(tc_b_resident=1, tc_tile_prefetch=1), dict(pdl=0),
-                                  dict(tc_two_cta=0), dict(tc_max_stages=2), dict(tc_grouped=0)])
+                                  dict(tc_two_cta=0), dict(tc_max_stages=2), dict(tc_grouped=0), dict(tc_alias_staging=1)])
 def test_engine_variants_reproduce_the_default_path(opts):
     """The tuning variants of the tcgen05 engine (clusters of two CTA pairs with the activation tile multicast, weight block resident in
     shared memory, next-tile L2 prefetch, no programmatic dependent launch, 1-CTA tiles, a 2-deep ring, one launch per encoder instead of
-    the grouped block-diagonal launches) change the schedule, not the
+    the grouped block-diagonal launches, wgrad staging blocks overlaid on the operand ring) change the schedule, not the
     arithmetic: in deterministic mode the forward outputs must be bit-identical to the default configuration and the losses / gradients
     identical up to the order of the per-CTA partial sums, at a batch with ragged tiles."""
     G = _gu()
