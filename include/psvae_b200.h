@@ -165,6 +165,16 @@ int psvae_train_fwd_bwd(const psvae_model_desc* desc, const float* params, const
                         int32_t compute_grads, int32_t precision, float* x_hat, float* mu, float* log_sigma,
                         float* losses, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- backward of VAEModel.forward for a caller's OWN loss (autograd through ps_vae/model.py:38-63) --------- */
+/* Recomputes the forward pass (same x, same eps or the same (seed, offset, row0) Philox draw as the psvae_forward call it mirrors) and
+ * back-propagates the given d loss / d x_hat [rows][D], d loss / d mu, d loss / d log_sigma [rows][L] (each may be NULL = zero) into
+ * `grads` (written, not accumulated; the classifier's entries stay zero).  No loss term is added inside.  workspace >=
+ * psvae_workspace_bytes(desc, rows, precision, PSVAE_MODE_TRAIN). */
+int psvae_vae_backward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const float* x,
+                       const float* eps, uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, int32_t precision,
+                       const float* g_x_hat, const float* g_mu, const float* g_log_sigma, void* workspace, int64_t workspace_bytes,
+                       void* stream);
+
 /* ---- the same step with the consistency term (lightning.py:44-52, 100-108, 119-124) ------------ */
 int psvae_consistency_desc_init(psvae_consistency_desc* cons, int32_t input_dim, int32_t hidden_dim, int32_t num_classes);
 /* scratch the consistency chain needs ON TOP of psvae_workspace_bytes(...) for the same rows / mode (TRAIN or FORWARD) */

@@ -377,6 +377,26 @@ def train_loss_and_grads(
     return scal, outputs, grads
 
 
+def vae_backward(params: Params, x: np.ndarray, eps: np.ndarray, g_x_hat=None, g_mu=None, g_log_sigma=None, normalize_decoder: bool = False) -> Params:
+    """Gradients of an arbitrary scalar loss w.r.t. the VAE's parameters, given d loss / d (x_hat, mu, log_sigma) of
+    ``VAEModel.forward`` (model.py:38-63) -- what autograd does when a caller builds a loss of its own on the outputs.
+    Same chain as the backward half of ``train_loss_and_grads`` without any built-in loss term."""
+    x_hat, mu, ls, c = vae_forward(params, x, eps, normalize_decoder)
+    zero = lambda like: np.zeros_like(like)
+    dxh = zero(x_hat) if g_x_hat is None else g_x_hat
+    if normalize_decoder:
+        du = (dxh - x_hat * (x_hat * dxh).sum(axis=1, keepdims=True)) / c["den"]
+    else:
+        du = dxh
+    grads: Params = {}
+    dz = mlp_backward(params, "model.decoder", c["c_dec"], du, grads)
+    dmu = dz + (0 if g_mu is None else g_mu)
+    dls = dz * eps * (x.dtype.type(0.5) * c["sigma"]) + (0 if g_log_sigma is None else g_log_sigma)
+    mlp_backward(params, "model.encoder_mu", c["c_mu"], dmu, grads, need_dx=False)
+    mlp_backward(params, "model.encoder_sigma", c["c_ls"], dls, grads, need_dx=False)
+    return grads
+
+
 # --------------------------------------------------------------------------------------------
 # Adam + cosine LR (torch.optim semantics, driven from lightning.py:204-214)
 # --------------------------------------------------------------------------------------------

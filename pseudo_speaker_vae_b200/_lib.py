@@ -30,7 +30,7 @@ EXPORTS = [
     "psvae_flops_per_sample", "psvae_set_option", "psvae_get_option", "psvae_adam_step", "psvae_philox_uint32", "psvae_philox_normal",
     "psvae_refresh_shadow", "psvae_forward", "psvae_decode", "psvae_train_fwd_bwd", "psvae_langevin", "psvae_gemm_bf16",
     "psvae_gemm_fp32", "psvae_gemm_probe", "psvae_launch_count", "psvae_consistency_desc_init", "psvae_consistency_workspace_bytes",
-    "psvae_consistency_forward", "psvae_train_fwd_bwd_consistency",
+    "psvae_consistency_forward", "psvae_train_fwd_bwd_consistency", "psvae_vae_backward",
 ]
 
 
@@ -94,6 +94,8 @@ def _declare(l: C.CDLL) -> None:
     l.psvae_decode.argtypes = [D, VP, VP, VP, U64, U64, I64, I64, I32, VP, VP, VP, I64, VP]
     l.psvae_train_fwd_bwd.restype = C.c_int
     l.psvae_train_fwd_bwd.argtypes = [D, VP, VP, VP, VP, VP, VP, U64, U64, I64, I64, F, F, I32, I32, I32, VP, VP, VP, VP, VP, I64, VP]
+    l.psvae_vae_backward.restype = C.c_int
+    l.psvae_vae_backward.argtypes = [D, VP, VP, VP, VP, VP, U64, U64, I64, I64, I32, VP, VP, VP, VP, I64, VP]
     CD = P(ConsistencyDesc)
     l.psvae_consistency_desc_init.restype = C.c_int
     l.psvae_consistency_desc_init.argtypes = [CD, I32, I32, I32]

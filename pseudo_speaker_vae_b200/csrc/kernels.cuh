@@ -160,7 +160,9 @@ __global__ void __launch_bounds__(256) latent_fwd_kernel(const float* __restrict
 template <typename TAct>
 __global__ void __launch_bounds__(256) latent_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
                                                          const TAct* __restrict__ hs, int64_t n_elems, const float* __restrict__ dmu_clf, float kl_over_b,
-                                                         TAct* __restrict__ dmu, TAct* __restrict__ dls, int qpr, int64_t ld_d) {
+                                                         TAct* __restrict__ dmu, TAct* __restrict__ dls, int qpr, int64_t ld_d,
+                                                         const float* __restrict__ dls_ext) {
+  // dmu_clf / dls_ext (optional, [rows][L] fp32): gradients reaching mu / log_sigma from outside the VAE -- the latent classifier, or a caller's own loss
   // dmu / dls are [rows][L] views with row stride ld_d (the two halves of one [rows][2L] buffer); qpr = L / 4
   PSVAE_GRID_DEP();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -172,10 +174,12 @@ __global__ void __launch_bounds__(256) latent_bwd_kernel(const float* __restrict
     load_vec<4>(ls + (i << 2), l);
     if (dmu_clf) load_vec<4>(dmu_clf + (i << 2), c);
     load_vec<4>(hs + (i << 2), e);
+    float x4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (dls_ext) load_vec<4>(dls_ext + (i << 2), x4);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       om[j] = g[j] + kl_over_b * m[j] + c[j];
-      ol[j] = fmaf(g[j], e[j], 0.5f * kl_over_b * expm1f(l[j]));   // expm1: no cancellation for ls ~ 0
+      ol[j] = fmaf(g[j], e[j], 0.5f * kl_over_b * expm1f(l[j])) + x4[j];   // expm1: no cancellation for ls ~ 0
     }
     const int64_t o = (int64_t)((uint32_t)i / (uint32_t)qpr) * ld_d + (((uint32_t)i % (uint32_t)qpr) << 2);
     store_vec<4>(dmu + o, om);
@@ -387,6 +391,19 @@ __global__ void __launch_bounds__(256) recon_rows_kernel(const float* __restrict
     }
     if (x_hat)
       for (int c = lane; c < D; c += 32) x_hat[r * D + c] = ur[c] * inv_den;
+    if (!xr && gx && du) {
+      // no reconstruction term: only an incoming d loss / d x_hat (a caller's own loss on the outputs of VAEModel.forward) goes back
+      float hd = 0.f;
+      if (normalize) {
+        for (int c = lane; c < D; c += 32) hd = fmaf(ur[c] * inv_den, gx[r * D + c], hd);
+        hd = warp_sum(hd);
+      }
+      for (int c = lane; c < D; c += 32) {
+        float g = gx[r * D + c];
+        if (normalize) g = (g - ur[c] * inv_den * hd) * inv_den;
+        du[r * D + c] = from_f32<TAct>(g);
+      }
+    }
     if (xr) {
       float dot = 0.f, m1 = 0.f, m2 = 0.f, sse = 0.f;
       for (int c = lane; c < D; c += 32) {
@@ -770,7 +787,7 @@ template <typename TAct>
 __global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
                                                             const TAct* __restrict__ hs, int64_t n_elems, int L, const float* __restrict__ dmu_clf, float kl_over_b,
                                                             TAct* __restrict__ dmu, TAct* __restrict__ dls, float* __restrict__ partials,
-                                                            float* __restrict__ bias_grad, int64_t ld_d) {
+                                                            float* __restrict__ bias_grad, int64_t ld_d, const float* __restrict__ dls_ext) {
   // dmu / dls: [rows][L] views with row stride ld_d (the two halves of one [rows][2L] buffer)
   // bias_grad != nullptr (fast mode): the block's 2L column sums are added straight into the zeroed [mu | sigma] bias gradient with atomics;
   // otherwise one partial row per block for the ordered reduce
@@ -786,10 +803,12 @@ __global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restr
     load_vec<4>(ls + (i << 2), l);
     if (dmu_clf) load_vec<4>(dmu_clf + (i << 2), c);
     load_vec<4>(hs + (i << 2), e);
+    float x4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (dls_ext) load_vec<4>(dls_ext + (i << 2), x4);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       om[j] = g[j] + kl_over_b * m[j] + c[j];
-      ol[j] = fmaf(g[j], e[j], 0.5f * kl_over_b * expm1f(l[j]));
+      ol[j] = fmaf(g[j], e[j], 0.5f * kl_over_b * expm1f(l[j])) + x4[j];
       sm_[j] += om[j];
       sl_[j] += ol[j];
     }

@@ -698,6 +698,11 @@ struct StepArgs {
   const float* cons_params = nullptr;
   const int64_t* cons_y = nullptr;
   float cons_w = 0.f;
+  // backward of VAEModel.forward for a caller's own loss (want_loss = 0, want_grads = 1): d loss / d (x_hat, mu, log_sigma), each optional
+  int ext = 0;
+  const float* ext_gx = nullptr;
+  const float* ext_gmu = nullptr;
+  const float* ext_gls = nullptr;
 };
 
 template <typename TAct> static const TAct* weights_of(const StepArgs& a);
@@ -914,7 +919,17 @@ static int run_step(const StepArgs& a) {
     float* u = general_tail ? w.u : (a.x_hat ? a.x_hat : w.u);
     EpiBiasAct<float, ACT_NONE> e{P + d->dec_b[n.nh], u, n.D, nullptr};
     PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st, (a.want_grads && w.mhd[0]) ? w.mhd : nullptr));
-    if (general_tail) {
+    if (a.ext) {
+      // no loss inside: x_hat (if asked for) and d loss / d u from the caller's d loss / d x_hat, through the normalisation when it is on
+      const int blocks = (int)ceil_div64(B * 32, 256);
+      if (a.ext_gx || (general_tail && a.x_hat)) {
+        launch_dep(recon_rows_kernel<TAct>, dim3(blocks), dim3(256), 0, st, u, (const float*)nullptr, B, n.D, d->normalize_decoder, 0, 0.f,
+                                                        general_tail ? a.x_hat : (float*)nullptr, a.ext_gx ? w.dxh : (TAct*)nullptr, (float*)nullptr, a.ext_gx);
+        count_launch();
+        PSVAE_LAUNCH_CHECK("recon_rows_kernel");
+      }
+      if (!a.ext_gx) PSVAE_CUDA(cudaMemsetAsync(w.dxh, 0, (size_t)B * n.D * sizeof(TAct), st));
+    } else if (general_tail) {
       const float gscale = a.use_cos ? 1.f / (float)B : 2.f / ((float)B * (float)n.D * 10.f);
       const int blocks = (int)ceil_div64(B * 32, 256);
       const float* gx = nullptr;
@@ -973,8 +988,9 @@ static int run_step(const StepArgs& a) {
   float* G = a.grads;
 
   // ---- classifier backward -> dmu_clf (the fused kernel already produced it together with the classifier's gradients)
-  const float* dmu_clf = clf_fused ? w.dmu_clf : nullptr;
-  if (n.has_clf() && !clf_fused) {
+  const float* dmu_clf = (clf_fused && a.want_loss) ? w.dmu_clf : nullptr;
+  if (a.ext) dmu_clf = a.ext_gmu;                      // the caller's d loss / d mu takes the classifier gradient's place
+  if (n.has_clf() && !clf_fused && a.want_loss) {
     const int T = d->clf_num_trunk;
     const float* featp = T > 0 ? w.clf_act[T - 1] : mu;
     for (int h = 0; h < d->clf_num_heads; ++h) {
@@ -1034,14 +1050,14 @@ static int run_step(const StepArgs& a) {
     if (blocks > 4 * PSVAE_NUM_SMS) blocks = 4 * PSVAE_NUM_SMS;
     float* bias_atomic = g_opt.deterministic ? nullptr : G + d->enc_b[n.nh];      // fast mode: atomics into the zeroed gradient, no reduce launch
     launch_dep(latent_bwd_cs_kernel<TAct>, dim3(blocks), dim3(256), 256 * 8 * sizeof(float), st, w.dz, mu, ls, w.hs, B * n.L, n.L, dmu_clf,
-                                                                             a.kl_w / (float)B, w.dmu, w.dls, w.cpart, bias_atomic, (int64_t)2 * n.L);
+                                                                             a.kl_w / (float)B, w.dmu, w.dls, w.cpart, bias_atomic, (int64_t)2 * n.L, a.ext ? a.ext_gls : (const float*)nullptr);
     count_launch();
     PSVAE_LAUNCH_CHECK("latent_bwd_cs_kernel");
     if (!bias_atomic) PSVAE_TRY(launch_reduce(w.cpart, 2 * n.L, blocks, G + d->enc_b[n.nh], st));
     last_bias_done = true;
   } else {
     launch_dep(latent_bwd_kernel<TAct>, dim3(ew_grid(B * n.L / 4)), dim3(256), 0, st, w.dz, mu, ls, w.hs, B * n.L, dmu_clf, a.kl_w / (float)B,
-                                                                  w.dmu, w.dls, n.L / 4, (int64_t)2 * n.L);
+                                                                  w.dmu, w.dls, n.L / 4, (int64_t)2 * n.L, a.ext ? a.ext_gls : (const float*)nullptr);
     count_launch();
     PSVAE_LAUNCH_CHECK("latent_bwd_kernel");
   }
@@ -1448,6 +1464,16 @@ int psvae_train_fwd_bwd_consistency(const psvae_model_desc* desc, const float* p
   StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, x, y, eps, seed, offset, row0, rows, kl_weight, clf_weight,
              use_cos_loss ? 1 : 0, 1, compute_grads ? 1 : 0, x_hat, mu, log_sigma, losses, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)};
   a.cons = cons; a.cons_params = cons_params; a.cons_y = cons_y; a.cons_w = cons_weight;
+  return precision == PSVAE_BF16 ? run_step<bf16>(a) : run_step<float>(a);
+}
+
+int psvae_vae_backward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const float* x, const float* eps,
+                       uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, int32_t precision, const float* g_x_hat, const float* g_mu,
+                       const float* g_log_sigma, void* workspace, int64_t workspace_bytes, void* stream) {
+  PSVAE_TRY(check_desc(desc, precision));
+  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, x, nullptr, eps, seed, offset, row0, rows, 0.f, 0.f,
+             0, 0, 1, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)};
+  a.ext = 1; a.ext_gx = g_x_hat; a.ext_gmu = g_mu; a.ext_gls = g_log_sigma;
   return precision == PSVAE_BF16 ? run_step<bf16>(a) : run_step<float>(a);
 }
 

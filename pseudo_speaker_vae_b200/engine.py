@@ -148,6 +148,35 @@ class _FusedLoss(torch.autograd.Function):
         return (None, None, None) + tuple(v if need else None for v, need in zip(views, ctx.needs))
 
 
+class _VAEForward(torch.autograd.Function):
+    """``VAEModel.forward`` with a graph (ps_vae/model.py:38-63 under autograd): the forward pass is one library call; the backward pass
+    is ``psvae_vae_backward``, which recomputes the activations from the saved input and the same noise draw and back-propagates the
+    caller's d loss / d (x_hat, mu, log_sigma) through decoder, reparameterisation and both encoders in the fused kernels."""
+
+    @staticmethod
+    def forward(ctx, hot: "HotPath", x: torch.Tensor, eps: Optional[torch.Tensor], *params):
+        x_hat, mu, ls, saved = hot._forward_raw(x, eps)
+        ctx.hot, ctx.saved = hot, saved
+        ctx.needs = [p.requires_grad for p in params]
+        return x_hat, mu, ls
+
+    @staticmethod
+    def backward(ctx, g_xhat, g_mu, g_ls):
+        hot = ctx.hot
+        x, eps, seed, off, row0 = ctx.saved
+        dev = x.device
+        flat = hot.arena.ensure()
+        B = x.shape[0]
+        gflat = torch.empty(hot.arena.numel, dtype=torch.float32, device=dev)        # a buffer of its own: autograd adopts / accumulates the views
+        gs = [None if g is None else g.detach().to(torch.float32).contiguous() for g in (g_xhat, g_mu, g_ls)]
+        ws = hot._workspace(dev, B, L.MODE_TRAIN)
+        rc = L.lib().psvae_vae_backward(hot._dref, flat.data_ptr(), hot._shadow(), gflat.data_ptr(), x.data_ptr(), L.ptr(eps), seed, off, row0, B,
+                                        hot.precision, L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(gs[2]), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        L.check(rc, "psvae_vae_backward")
+        views = [gflat[o:o + p.numel()].view(p.shape) for p, o in hot.vae_entries()]
+        return (None, None, None) + tuple(v if need else None for v, need in zip(views, ctx.needs))
+
+
 class HotPath:
     """Everything the drop-in modules ask of the CUDA library, for one (VAE [+ latent classifier]) pair."""
 
@@ -244,7 +273,23 @@ class HotPath:
         return t.detach().to(torch.float32).contiguous()
 
     # ---- VAEModel.forward (ps_vae/model.py:38-63) -------------------------------------------------
+    def vae_entries(self) -> List[Tuple[nn.Parameter, int]]:
+        """(parameter, arena offset) of the VAE's own parameters (the classifier's follow them in the arena)."""
+        return [(p, o) for p, o in self.arena.entries if o < int(self.desc.vae_numel)]
+
     def forward(self, x: torch.Tensor, eps: Optional[torch.Tensor] = None):
+        """(x_hat, mu, log_sigma).  With autograd on and trainable VAE parameters the outputs carry a graph, as the reference's do: a
+        caller's own loss on them back-propagates through ``psvae_vae_backward``.  (``training_step`` does not come through here: it
+        computes its loss and every gradient in one fused call.)"""
+        entries = self.vae_entries()
+        if torch.is_grad_enabled() and x.dim() == 2 and x.shape[0] > 0 and any(p.requires_grad for p, _ in entries):
+            if x.requires_grad:
+                raise NotImplementedError("the gradient with respect to the input x is not computed by the B200 path (model parameters only)")
+            return _VAEForward.apply(self, x, eps, *[p for p, _ in entries])
+        x_hat, mu, ls, _ = self._forward_raw(x, eps)
+        return x_hat, mu, ls
+
+    def _forward_raw(self, x: torch.Tensor, eps: Optional[torch.Tensor] = None):
         dev = self._device()
         flat = self.arena.ensure()
         if x.dim() != 2 or x.shape[1] != self.desc.input_dim:
@@ -256,7 +301,7 @@ class HotPath:
         mu = torch.empty(B, Lz, dtype=torch.float32, device=dev)
         ls = torch.empty(B, Lz, dtype=torch.float32, device=dev)
         if B == 0:
-            return x_hat, mu, ls
+            return x_hat, mu, ls, None
         if eps is not None:
             eps = self._f32(eps, dev, "eps")
             if tuple(eps.shape) != (B, Lz):
@@ -268,7 +313,7 @@ class HotPath:
         rc = L.lib().psvae_forward(self._dref, flat.data_ptr(), self._shadow(), x.data_ptr(), L.ptr(eps), seed, off, self.row0, B, self.precision,
                                    x_hat.data_ptr(), mu.data_ptr(), ls.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
         L.check(rc, "psvae_forward")
-        return x_hat, mu, ls
+        return x_hat, mu, ls, (x, eps, seed, off, self.row0)      # what the backward pass needs to redo this exact forward
 
     # ---- VAEModel.decode (model.py:65-69) / unconditional_synthesis (inference.py:22-25) ----------
     def decode(self, z: Optional[torch.Tensor], num_samples: Optional[int] = None, out: Optional[torch.Tensor] = None,

@@ -11,8 +11,10 @@ Additive keyword arguments (reference values are the defaults): ``hidden_dim=512
 Differences a caller can observe:
   * the reparameterisation noise comes from the library's counter-based Philox generator (seeded from
     ``torch.initial_seed()``), not from torch's global generator; pass ``eps=`` to inject the draw;
-  * outputs carry no autograd graph -- training goes through ``PseudoSpeakerVAE.training_step`` (lightning.py),
-    which computes loss and all gradients in one fused call;
+  * with autograd on, the outputs carry a graph whose backward pass is one fused library call (``psvae_vae_backward``: the
+    activations are recomputed, nothing is kept between the two calls); the gradient with respect to ``x`` itself is not
+    computed.  ``PseudoSpeakerVAE.training_step`` (lightning.py) does not use this route: it computes its loss and all
+    gradients in one fused call;
   * the module must live on a CUDA (B200) device: there is no CPU path.
 """
 from __future__ import annotations

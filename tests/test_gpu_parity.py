@@ -204,7 +204,7 @@ def _train_case(name, precision, tol_fwd, tol_loss, tol_grad, check_params):
         yt = G.labels_to_torch(y) if cfg.get("clf") else torch.zeros(x.shape[0], dtype=torch.int64, device=G.DEV)
         st = f"{tag}/step{s}"
         scal, out, grads = _oracle_at(module, cfg, x, y, eps)
-        x_hat, mu, ls = module(xt, eps=et)
+        x_hat, mu, ls = (t.detach() for t in module(xt, eps=et))
         for nm, got, onm in (("x_hat", x_hat, "x_hat"), ("mu", mu, "mu"), ("ls", ls, "log_sigma")):
             e = rel_err(got.cpu().numpy(), z[f"{st}/{nm}"])
             worst[nm] = max(worst.get(nm, 0), e)
@@ -258,7 +258,7 @@ def test_train_step_bf16_vs_reference_golden(name):
     x, y, eps = case_batch(cfg, 0, np.float32)
     xt, et = torch.from_numpy(x).to(G.DEV), torch.from_numpy(eps).to(G.DEV)
     yt = G.labels_to_torch(y) if cfg.get("clf") else torch.zeros(x.shape[0], dtype=torch.int64, device=G.DEV)
-    x_hat, mu, ls = module(xt, eps=et)
+    x_hat, mu, ls = (t.detach() for t in module(xt, eps=et))
     for nm, got in (("x_hat", x_hat), ("mu", mu), ("ls", ls)):
         assert rel_err(got.cpu().numpy(), z[f"f64/step0/{nm}"]) <= BF16_FWD_TOL, (name, nm)
     module.training_step((xt, yt), 0, eps=et)["loss"].backward()
@@ -630,11 +630,66 @@ def test_reference_shape_smoke_784_20():
     model = P.VAEModel(784, 20).to(G.DEV)
     x = torch.randn(32, 784, device=G.DEV)
     eps = torch.randn(32, 20, device=G.DEV)
-    x_hat, mu, sigma = model(x, eps=eps)
+    x_hat, mu, sigma = (t.detach() for t in model(x, eps=eps))
     assert x_hat.shape == (32, 784) and mu.shape == (32, 20) and sigma.shape == (32, 20)
     params = {"model." + k: v.detach().cpu().double().numpy() for k, v in model.state_dict().items()}
     xr, mr, lr_, _ = O.vae_forward(params, x.cpu().double().numpy(), eps.cpu().double().numpy())
     assert rel_err(x_hat.cpu().numpy(), xr) <= FP32_TOL and rel_err(mu.cpu().numpy(), mr) <= FP32_TOL
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_GRAD_TOL_SMALL)])
+def test_autograd_through_forward_for_a_callers_own_loss(precision, tol):
+    """x_hat, mu, log_sigma = module(x) carry a graph (as the reference's outputs do): a loss built by the caller back-propagates through
+    psvae_vae_backward.  Random linear functionals of the three outputs, injected eps and in-kernel Philox eps, normalised decoder too."""
+    G = _gu()
+    z, cfg = load("train_d256_norm_cos")           # normalize_decoder = True
+    for normalize in (True, False):
+        c = dict(cfg, normalize_decoder=normalize)
+        module = G.module_from_cfg(c, precision)
+        x, y, eps = case_batch(c, 0, np.float32)
+        rng = np.random.default_rng(9)
+        gx, gm, gl = (rng.standard_normal(s).astype(np.float32) for s in ((x.shape[0], c["D"]), (x.shape[0], c["L"]), (x.shape[0], c["L"])))
+        xt, et = torch.from_numpy(x).to(G.DEV), torch.from_numpy(eps).to(G.DEV)
+        x_hat, mu, ls = module(xt, eps=et)
+        assert x_hat.requires_grad and mu.requires_grad and ls.requires_grad
+        loss = (x_hat * torch.from_numpy(gx).to(G.DEV)).sum() + (mu * torch.from_numpy(gm).to(G.DEV)).sum() + (ls * torch.from_numpy(gl).to(G.DEV)).sum()
+        loss.backward()
+        params = {k: v.astype(np.float64) for k, v in case_params(c, np.float32).items() if k.startswith("model.")}
+        ref = O.vae_backward(params, x.astype(np.float64), eps.astype(np.float64), gx.astype(np.float64), gm.astype(np.float64), gl.astype(np.float64),
+                             normalize_decoder=normalize)
+        errs = {k: rel_err(p.grad.cpu().numpy(), ref[k]) for k, p in module.named_parameters() if k.startswith("model.")}
+        assert max(errs.values()) <= tol, (precision, normalize, {k: f"{v:.1e}" for k, v in errs.items()})
+        assert all(p.grad is None for k, p in module.named_parameters() if k.startswith("classifier."))
+        # only d loss / d mu given: nothing reaches the decoder or the sigma encoder
+        for p in module.parameters():
+            p.grad = None
+        module(xt, eps=et)[1].sum().backward()
+        assert all(float(p.grad.abs().max()) == 0 for k, p in module.named_parameters() if "decoder" in k or "encoder_sigma" in k)
+        assert float(module.model.encoder_mu[0].weight.grad.abs().max()) > 0
+        # Philox draw: the backward pass regenerates the forward pass's noise (same seed / offset): equals the injected-eps run with that draw
+        for p in module.parameters():
+            p.grad = None
+        module.hot_path.manual_seed(77, 3)
+        xh2 = module(xt)[0]
+        (xh2 * torch.from_numpy(gx).to(G.DEV)).sum().backward()
+        g_philox = {k: p.grad.clone() for k, p in module.named_parameters() if p.grad is not None}
+        drawn = torch.empty(x.shape[0], c["L"], device=G.DEV)
+        G.L.check(G.L.lib().psvae_philox_normal(drawn.data_ptr(), x.shape[0], c["L"], 77, 3, 0, G.stream()))
+        for p in module.parameters():
+            p.grad = None
+        (module(xt, eps=drawn)[0] * torch.from_numpy(gx).to(G.DEV)).sum().backward()
+        for k, p in module.named_parameters():
+            if p.grad is not None:
+                assert rel_err(g_philox[k].cpu().numpy(), p.grad.cpu().numpy()) <= (1e-6 if precision == "fp32" else 2e-2), k
+        with torch.no_grad():
+            assert not module(xt, eps=et)[0].requires_grad
+        with pytest.raises(NotImplementedError):
+            module(xt.clone().requires_grad_(True), eps=et)
+        # the optimiser accepts gradients that did not come from the fused step
+        opt = module.configure_optimizers()["optimizer"]
+        before = module.hot_path.arena.flat.clone()
+        opt.step()
+        assert not torch.equal(before, module.hot_path.arena.flat)
 
 
 def test_data_parallel_trainer_single_process_matches_manual_steps():

@@ -183,3 +183,49 @@ def test_torch_port_matches_golden():
         for k, p in mod.named_parameters():
             key = k.replace("classifier.", "classifier.layers.0.") if k.startswith("classifier.") else k
             check_summary(z, f"f64/step{s}/param", key, p.detach().numpy(), 1e-10)
+
+
+@pytest.mark.parametrize("normalize", [False, True])
+def test_vae_backward_for_a_callers_own_loss_vs_torch_autograd(normalize):
+    """oracle.vae_backward (gradients for given d loss / d outputs of VAEModel.forward) against torch autograd on the same network
+    (nn.Linear / ReLU / exp / F.normalize, the ops of ps_vae/model.py:14-63; the live reference module when /root/reference is present)."""
+    import torch
+
+    from oracle.ref_loader import injected_normals, load_reference, reference_available
+
+    D, L, B = 192, 64, 12
+    params = O.synth_params(O.vae_param_shapes(D, L), seed=41, dtype=np.float64)
+    x, _, eps = O.synth_batch(B, D, L, 2, seed=42, dtype=np.float64)
+    rng = np.random.default_rng(43)
+    gx, gm, gl = rng.standard_normal((B, D)), rng.standard_normal((B, L)), rng.standard_normal((B, L))
+    ours = O.vae_backward(params, x, eps, gx, gm, gl, normalize_decoder=normalize)
+    sd = {k[len("model."):]: torch.from_numpy(v) for k, v in params.items()}
+    if reference_available():
+        model = load_reference().VAEModel(input_dim=D, latent_dim=L, normalize_decoder=normalize).double()
+        model.load_state_dict(sd)
+        with injected_normals([torch.from_numpy(eps)]):
+            x_hat, mu, ls = model(torch.from_numpy(x))
+    else:
+        def mlp(prefix, h):
+            n = len([k for k in sd if k.startswith(prefix) and k.endswith(".weight")])
+            for j in range(n):
+                h = torch.nn.functional.linear(h, sd[f"{prefix}.{2 * j}.weight"], sd[f"{prefix}.{2 * j}.bias"])
+                if j + 1 < n:
+                    h = torch.relu(h)
+            return h
+        for v in sd.values():
+            v.requires_grad_(True)
+        xt = torch.from_numpy(x)
+        mu, ls = mlp("encoder_mu", xt), mlp("encoder_sigma", xt)
+        x_hat = mlp("decoder", mu + torch.exp(0.5 * ls) * torch.from_numpy(eps))
+        if normalize:
+            x_hat = torch.nn.functional.normalize(x_hat, p=2, dim=1)
+        model = None
+    loss = (x_hat * torch.from_numpy(gx)).sum() + (mu * torch.from_numpy(gm)).sum() + (ls * torch.from_numpy(gl)).sum()
+    loss.backward()
+    named = dict(model.named_parameters()) if model is not None else sd
+    for k, g in ours.items():
+        ref = named[k[len("model."):]].grad.numpy()
+        assert rel_err(g, ref) <= 1e-12, k
+    only_mu = O.vae_backward(params, x, eps, None, gm, None, normalize_decoder=normalize)
+    assert all(np.abs(v).max() == 0 for k, v in only_mu.items() if "decoder" in k or "encoder_sigma" in k)     # nothing reaches them
