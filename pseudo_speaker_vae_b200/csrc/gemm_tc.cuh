@@ -52,11 +52,16 @@ constexpr int TC_MAX_STAGES = 12;          // barrier slots of the operand ring
 // ALIAS (split-K / wgrad launches in which no CTA gets more than one tile): the epilogue staging blocks overlay the first stages of the
 // operand ring -- the single epilogue of the CTA starts after its last MMA has retired and no further load is issued, so the ring is dead
 // by then -- and the ring gets the 64 KB back: 7 stages (224 KB in flight per SM) instead of 5 for the HBM-latency-bound wgrad form.
-template <int BN, class Epi, int CG = 1, bool BRES = false, bool ALIAS = false> struct TcCfg {
+// EG2 ("two epilogue groups", BN = 256 only): the 16 epilogue warps form two groups of 8 that take ALTERNATE tiles -- group g owns the
+// accumulator buffer g -- each warp draining 128 columns instead of 64.  While one group stages and stores its tile the other group's
+// tcgen05.ld stream keeps the TMEM read port busy: for the thin (K <= 128) layers, which are bound by the accumulator drain
+// (profiles/r01_epilogue_phase_trace_v16.txt: 3.4 k of 4.9 k cycles per tile in the drain, 0.8-1.6 k in staging + store with the port idle).
+template <int BN, class Epi, int CG = 1, bool BRES = false, bool ALIAS = false, bool EG2 = false> struct TcCfg {
   static_assert(!(ALIAS && BRES), "ALIAS: streaming operands only");
+  static_assert(!EG2 || (BN == 256 && Epi::kAuxBytes == 0 && !Epi::kSplit), "EG2: 16 epilogue warps, no auxiliary tile, no split-K");
   static constexpr int kEpiWarps = tc_epi_warps(BN);
   static constexpr int kThreads = 32 * (2 + kEpiWarps);
-  static constexpr int kColsPerWarp = BN / (kEpiWarps / 4);
+  static constexpr int kColsPerWarp = EG2 ? BN / (kEpiWarps / 8) : BN / (kEpiWarps / 4);
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = (BN / CG) * TC_BK * 2;
   static constexpr int kStageBytes = BRES ? kABytes : kABytes + kBBytes;
@@ -124,12 +129,13 @@ template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
 // CL = 2 (only with CG = 2, K-major A, streaming B): clusters of two CTA pairs that work on the same row tile and adjacent N tiles; every CTA
 // loads HALF of its 128 activation rows per k-block and multicasts them to its twin in the other pair, so the activation tile crosses the
 // L2 -> SM fabric once per cluster instead of once per pair (-25 % operand traffic per pair, ring depth unchanged).
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL, bool ALIAS = false>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL, bool ALIAS = false, bool EG2 = false>
 __global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
                const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_apf, TcShape s, Epi epi) {
-  using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS>;
+  using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS, EG2>;
   static_assert(!ALIAS || (Epi::kSplit && Epi::kAuxBytes == 0 && CL == 1), "ALIAS: split-K store epilogue, one tile per CTA (host-checked)");
+  static_assert(!EG2 || (CL == 1 && !BRES && !ALIAS), "EG2: plain streaming kernel");
   using TOut = typename Epi::TOut;
   constexpr int STAGES = TC_MAX_STAGES;                    // barrier slots; s.stages of them are in use
   constexpr int EPI_WARPS = Cfg::kEpiWarps;
@@ -177,7 +183,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
-      ptx::mbar_init(&tempty_bar[i], EPI_WARPS * CG);      // CG = 2: the peer's epilogue warps arrive remotely on the leader's barrier
+      ptx::mbar_init(&tempty_bar[i], (EG2 ? EPI_WARPS / 2 : EPI_WARPS) * CG);      // CG = 2: the peer's epilogue warps arrive remotely on the leader's barrier; EG2: buffer i belongs to epilogue group i
     }
     for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
     ptx::mbar_init(bfull_bar, 1);
@@ -447,7 +453,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ============================ epilogue ================================
     const int ew = warp - 2;                 // 0..EPI_WARPS-1
     const int quarter = warp & 3;            // TMEM lane quarter this warp may touch (warp id % 4)
-    const int half = ew >> 2;                // which column group of the BN columns
+    const int half = EG2 ? (ew >> 2) & 1 : ew >> 2;      // which column group of the BN columns
+    const int egrp = ew >> 3;                // EG2: this warp's epilogue group (= the accumulator buffer it drains)
     constexpr int COLS_PER_WARP = Cfg::kColsPerWarp;
     constexpr int CH = COLS_PER_WARP / 32;   // 32-column blocks per tile for this warp
     uint8_t* const obuf0 = smem + Cfg::kEpiOff + ew * Cfg::kEpiWarpBytes;   // staged output block(s)
@@ -488,6 +495,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                       sp = tile_sp(tile);
       const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
       const int acc = (int)(it & 1);
+      if constexpr (EG2) {
+        if (acc != egrp) continue;           // the other group's tile
+      }
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const int32_t row_base = (int32_t)(m_t * TM) + (int32_t)cta_rank * TC_BM + quarter * 32;
       const int64_t row = (int64_t)row_base + lane;
@@ -746,6 +756,7 @@ int tc_tile_prefetch();   // option "tc_tile_prefetch"
 int tc_pair_cluster();    // option "tc_pair_cluster": clusters of two CTA pairs with the activation tile multicast between them
 int tc_b_stable();        // set by the train step / decode around GEMMs whose B operand is the (long since written) weight arena
 int tc_prefetch_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out);
+int tc_epi_groups();      // option "tc_epi_groups": K <= 128 forward / dgrad launches with BN = 256 run two epilogue groups on alternate tiles (EG2)
 int tc_alias_staging();   // option "tc_alias_staging": wgrad launches with one tile per CTA overlay the epilogue staging on the operand ring
 int tc_b_resident();      // option "tc_b_resident": keep the weight block of the CTA's N tile in shared memory where it fits
 // does this shape run as CTA pairs?  (BN = 256 tiles and more than one 128-row block of M)
@@ -781,10 +792,10 @@ template <class Epi> struct epi_split_stride<Epi, std::enable_if_t<Epi::kSplit>>
 template <class Epi, class = void> struct epi_cs_atomic { static bool get(const Epi&) { return false; } };
 template <class Epi> struct epi_cs_atomic<Epi, std::enable_if_t<Epi::kColSum>> { static bool get(const Epi& e) { return e.colsum_atomic != 0; } };
 
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false, int CL = 1, bool ALIAS = false>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false, int CL = 1, bool ALIAS = false, bool EG2 = false>
 int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st,
                       const TcGroup& grp = TcGroup()) {
-  using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS>;
+  using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS, EG2>;
   using TOut = typename Epi::TOut;
   CUtensorMap ta, tb, tout, taux, tapf;
   // grouped: K is one group's contraction length; A spans all groups' k ranges, an MN-major B all groups' k rows
@@ -820,7 +831,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   } else {
     taux = ta;
   }
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, BRES, CL, ALIAS>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, BRES, CL, ALIAS, EG2>;
   static unsigned long long attr_mask = 0;   // per instantiation, one bit per device
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
@@ -896,6 +907,14 @@ int gemm_tc_launch_pick(const TcOperand& A, const TcOperand& B, int64_t M, int N
     if (tc_b_resident() && grp.groups == 1 && splits <= 1 && (tc_grid_size() / CG) % n_tiles == 0 && ceil_div64(M, TC_BM * CG) * n_tiles >= tc_grid_size() / CG &&
         CfgR::res_stages(ceil_div64(K, TC_BK)) >= 3)
       return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, true>(A, B, M, N, K, splits, epi, st);
+  }
+  if constexpr (BN == 256 && !A_MN && !Epi::kSplit && Epi::kAuxBytes == 0) {
+    // thin layers (K <= 128): two epilogue groups on alternate tiles keep the TMEM read port busy through the store phase
+    // (not with the ordered column-sum partials of deterministic mode: both groups' warps of a lane quarter would share one partial slot)
+    bool ordered_colsum = false;
+    if constexpr (Epi::kColSum) ordered_colsum = !epi_cs_atomic<Epi>::get(epi);
+    if (tc_epi_groups() && K <= 128 && !ordered_colsum)
+      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 1, false, true>(A, B, M, N, K, splits, epi, st, grp);
   }
   if constexpr (A_MN && Epi::kSplit && Epi::kAuxBytes == 0) {
     // wgrad form, at most one tile per CTA (pair): the epilogue staging overlays the operand ring (two more stages in flight)

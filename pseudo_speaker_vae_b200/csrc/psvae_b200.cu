@@ -63,6 +63,8 @@ struct Options {
   int64_t tc_tile_prefetch = 0;        // 1: the producer pulls the NEXT tile's whole activation panel into L2 with wide-box prefetches at the start of each tile
   int64_t tc_pair_cluster = 0;         // 1: forward / dgrad GEMMs with an even number of N tiles run as clusters of two CTA pairs (activation tile multicast).
                                        //    Measured: +7 % per SM, but only 33 clusters of 4 are co-resident (132 of 148 SMs) -> 39.3 vs 37.4 us; off by default
+  int64_t tc_epi_groups = 0;           // 1: thin (K <= 128) BN = 256 forward / dgrad launches use two epilogue groups on alternate tiles (EG2).  Written from the
+                                       //    epilogue phase trace at the end of round 1; NOT yet run on hardware -- off until it has passed the engine-variant test
   int64_t tc_alias_staging = 0;        // 1: split-K (wgrad) launches with at most one tile per CTA overlay the epilogue staging on the operand ring (7 stages instead of 5).
                                        //    Measured neutral (31.4 vs 31.7 us for the 512 x 512 wgrad): the wgrad form is not bound by bytes in flight; off by default
   int64_t tc_grouped = 1;              // 1: layers 1..n of the two encoders run as ONE block-diagonal launch each (forward and dgrad) instead of one per encoder
@@ -114,6 +116,7 @@ int tc_two_cta() { return (int)g_opt.tc_two_cta; }
 int tc_max_stages() { return (int)g_opt.tc_max_stages; }
 int tc_b_resident() { return (int)g_opt.tc_b_resident; }
 int tc_alias_staging() { return (int)g_opt.tc_alias_staging; }
+int tc_epi_groups() { return (int)g_opt.tc_epi_groups; }
 bool pdl_enabled() { return g_opt.pdl != 0; }
 int tc_pair_cluster() { return (int)g_opt.tc_pair_cluster; }
 static thread_local int g_b_stable = 0;
@@ -1240,6 +1243,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "pdl")) { g_opt.pdl = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_grouped")) { g_opt.tc_grouped = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_alias_staging")) { g_opt.tc_alias_staging = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_epi_groups")) { g_opt.tc_epi_groups = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_pair_cluster")) { g_opt.tc_pair_cluster = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
@@ -1262,6 +1266,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "pdl")) return g_opt.pdl;
   if (!strcmp(name, "tc_grouped")) return g_opt.tc_grouped;
   if (!strcmp(name, "tc_alias_staging")) return g_opt.tc_alias_staging;
+  if (!strcmp(name, "tc_epi_groups")) return g_opt.tc_epi_groups;
   if (!strcmp(name, "tc_pair_cluster")) return g_opt.tc_pair_cluster;
   if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;
