@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SRC = os.path.join(ROOT, "pseudo_speaker_vae_b200", "csrc")
-TMP = "/tmp/psvae_trace_src"
+TMP = os.path.join(ROOT, "build", "ab", "src_trace")       # scratch copy inside the (git-ignored) build directory
 OUT = os.path.join(ROOT, "build", "ab", "libpsvae_trace.so")
 
 
