@@ -479,6 +479,9 @@ struct ClfFusedArgs {
   int atomic_out;
   float* grads;
   float* sums;
+  // option "clf_grad_in_bwd" (fast mode): only d loss / d logits leaves this pass, as g_rows[B][CLF_MAXC]; d loss / d mu and the classifier's
+  // own weight / bias gradients are then formed by the latent backward kernel, which streams mu anyway (no [B][L] dmu buffer round trip)
+  float* g_rows;
 };
 // REPARAM: the same pass over mu also does the reparameterisation (model.py:56-57) and the KL partial sums (lightning.py:115-117):
 // z = mu + exp(ls/2) * eps with eps from `eps` or the counter-based Philox stream (counter = global quad index), one read of ls, z written once
@@ -503,7 +506,8 @@ static inline size_t clf_fused_smem_bytes(int L) { return ((size_t)CLF_TILE * (L
 //   phase 3: dmu_clf[row][k] = sum_c dlogits[row][c] W[c][k] written coalesced; thread = (class, latent dim): dW[c][k] += sum_rows dlogits[row][c] mu[row][k].
 // L is a template parameter (16/32/64/128) so that the row/column index arithmetic is shifts and everything moves as float4; class
 // loops run over the classes that exist (2..3 per head), not over the CLF_MAXC slots.
-template <int L, typename TZ, bool REPARAM>
+// GROWS (option "clf_grad_in_bwd"): only g_rows leaves the pass; phase 3 and the classifier-gradient tail are compiled out
+template <int L, typename TZ, bool REPARAM, bool GROWS = false>
 __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __restrict__ params, const float* __restrict__ mu, const int64_t* __restrict__ y,
                                                              int64_t B, ClfFusedArgs a, float* __restrict__ dmu_clf, float* __restrict__ part, ReparamArgs rp) {
   PSVAE_GRID_DEP();
@@ -637,9 +641,15 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
       }
       *reinterpret_cast<float4*>(g_s + t * CLF_MAXC) = make_float4(g[0], g[1], g[2], g[3]);
       *reinterpret_cast<float4*>(g_s + t * CLF_MAXC + 4) = make_float4(g[4], g[5], g[6], g[7]);
+      if constexpr (GROWS) {
+        if (a.write_grad && r < B) {
+          *reinterpret_cast<float4*>(a.g_rows + r * CLF_MAXC) = make_float4(g[0], g[1], g[2], g[3]);
+          *reinterpret_cast<float4*>(a.g_rows + r * CLF_MAXC + 4) = make_float4(g[4], g[5], g[6], g[7]);
+        }
+      }
     }
     __syncthreads();
-    if (a.write_grad) {
+    if (a.write_grad && !GROWS) {
       if (dmu_clf) {
         for (int i = t; i < CLF_TILE * QPR; i += CLF_TILE) {      // thread = (row, 4 latent dims): one 16-byte coalesced store
           const int r = i / QPR, k = 4 * (i % QPR);
@@ -703,7 +713,7 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
       const float s2 = block_sum(acc[h], scratch);
       if (t == 0) { part[(int64_t)blockIdx.x * PART + h] = s1; part[(int64_t)blockIdx.x * PART + 4 + h] = s2; }   // losses stay order-fixed: summed by finalize_losses
     }
-    if (!a.write_grad) return;
+    if (!a.write_grad || GROWS) return;
     if (n_parts > 1) {
       __syncthreads();
       float* comb = clf_smem;
@@ -827,6 +837,117 @@ __global__ void __launch_bounds__(256) latent_bwd_cs_kernel(const float* __restr
     for (int th = quad; th < 256; th += qpr) t += lb_smem[th * 8 + which * 4 + j];
     if (bias_grad) atomicAdd(bias_grad + threadIdx.x, t);
     else partials[(int64_t)blockIdx.x * 2 * L + threadIdx.x] = t;
+  }
+}
+
+// ---------------------------------------------------------------- latent backward + the linear-head classifier's backward from d loss / d logits
+// latent_bwd_cs_kernel plus (option "clf_grad_in_bwd", fast mode): g_rows[B][CLF_MAXC] = d loss / d logits of the fused classifier pass;
+//   dmu_clf[r][k] = sum_c g[r][c] W[c][k]      (formed in registers: the thread's 4 columns of W are loaded once)
+//   dW[c][k]     += sum_r g[r][c] mu[r][k]     (private partial per thread, block-reduced like the bias sums, then atomics)
+//   db[c]        += sum_r g[r][c]
+// NC = classes summed over all heads (2..CLF_MAXC): registers scale with it.
+struct ClfBwdArgs {
+  int n_heads, total_classes;
+  int head_classes[4], head_off[4];
+  int64_t w_off[4], b_off[4];
+  const float* params;
+  float* grads;
+  const float* g_rows;
+};
+template <typename TAct, int NC>
+__global__ void __launch_bounds__(256) latent_bwd_clf_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
+                                                             const TAct* __restrict__ hs, int64_t n_elems, int L, float kl_over_b, TAct* __restrict__ dmu,
+                                                             TAct* __restrict__ dls, float* __restrict__ bias_grad, int64_t ld_d, ClfBwdArgs ca) {
+  PSVAE_GRID_DEP();
+  extern __shared__ float lb_smem[];        // [256][8]
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t nq = n_elems >> 2;
+  const uint32_t qpr_ = (uint32_t)L >> 2;   // quads per row; the grid stride is a multiple of it: a thread keeps its 4 columns
+  const int col4 = (int)(((uint32_t)blockIdx.x * blockDim.x + threadIdx.x) % qpr_) << 2;
+  const int nc = ca.total_classes;
+  auto head_of = [&](int cc) {
+    int h = 0;
+    for (int i = 0; i < ca.n_heads; ++i)
+      if (cc >= ca.head_off[i] && cc < ca.head_off[i] + ca.head_classes[i]) h = i;
+    return h;
+  };
+  float Wc[NC][4], accW[NC][4], accb[NC];
+#pragma unroll
+  for (int cc = 0; cc < NC; ++cc) {
+    accb[cc] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { Wc[cc][j] = 0.f; accW[cc][j] = 0.f; }
+    if (cc < nc) {
+      const int h = head_of(cc);
+      load_vec<4>(ca.params + ca.w_off[h] + (int64_t)(cc - ca.head_off[h]) * L + col4, Wc[cc]);
+    }
+  }
+  float sm_[4] = {0.f, 0.f, 0.f, 0.f}, sl_[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
+    float g[4], m[4], l[4], e[4], c[4] = {0.f, 0.f, 0.f, 0.f}, om[4], ol[4];
+    load_vec<4>(dz + (i << 2), g);
+    load_vec<4>(mu + (i << 2), m);
+    load_vec<4>(ls + (i << 2), l);
+    load_vec<4>(hs + (i << 2), e);
+    const int64_t row = (int64_t)((uint32_t)i / qpr_);
+    float gr[CLF_MAXC];
+    load_vec<4>(ca.g_rows + row * CLF_MAXC, *reinterpret_cast<float(*)[4]>(&gr[0]));
+    if (NC > 4) load_vec<4>(ca.g_rows + row * CLF_MAXC + 4, *reinterpret_cast<float(*)[4]>(&gr[4]));
+    const bool first_quad = ((uint32_t)i % qpr_) == 0;
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) {
+      if (cc < nc) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          c[j] = fmaf(gr[cc], Wc[cc][j], c[j]);
+          accW[cc][j] = fmaf(gr[cc], m[j], accW[cc][j]);
+        }
+        if (first_quad) accb[cc] += gr[cc];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      om[j] = g[j] + kl_over_b * m[j] + c[j];
+      ol[j] = fmaf(g[j], e[j], 0.5f * kl_over_b * expm1f(l[j]));
+      sm_[j] += om[j];
+      sl_[j] += ol[j];
+    }
+    const int64_t o = row * ld_d + (((uint32_t)i % qpr_) << 2);
+    store_vec<4>(dmu + o, om);
+    store_vec<4>(dls + o, ol);
+  }
+  const int qpr = L >> 2;
+  // bias gradients of the encoders' last Linear: as latent_bwd_cs_kernel (atomics into the zeroed [mu | sigma] bias gradient)
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { lb_smem[threadIdx.x * 8 + j] = sm_[j]; lb_smem[threadIdx.x * 8 + 4 + j] = sl_[j]; }
+  __syncthreads();
+  if ((int)threadIdx.x < 2 * L) {
+    const int which = threadIdx.x / L, col = threadIdx.x % L, quad = col >> 2, j = col & 3;
+    float t = 0.f;
+    for (int th = quad; th < 256; th += qpr) t += lb_smem[th * 8 + which * 4 + j];
+    atomicAdd(bias_grad + threadIdx.x, t);
+  }
+  // the classifier's own gradients, one class at a time through the same staging array
+#pragma unroll
+  for (int cc = 0; cc < NC; ++cc) {
+    if (cc < nc) {            // block-uniform
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) lb_smem[threadIdx.x * 8 + j] = accW[cc][j];
+      lb_smem[threadIdx.x * 8 + 4] = accb[cc];
+      __syncthreads();
+      const int h = head_of(cc), lc = cc - ca.head_off[h];
+      if ((int)threadIdx.x < L) {
+        const int col = threadIdx.x, quad = col >> 2, j = col & 3;
+        float t = 0.f;
+        for (int th = quad; th < 256; th += qpr) t += lb_smem[th * 8 + j];
+        atomicAdd(ca.grads + ca.w_off[h] + (int64_t)lc * L + col, t);
+      } else if ((int)threadIdx.x == L) {
+        float t = 0.f;
+        for (int th = 0; th < 256; ++th) t += lb_smem[th * 8 + 4];      // only the threads that own a row's first quad added to it
+        atomicAdd(ca.grads + ca.b_off[h] + lc, t);
+      }
+    }
   }
 }
 

@@ -63,6 +63,9 @@ struct Options {
   int64_t tc_tile_prefetch = 0;        // 1: the producer pulls the NEXT tile's whole activation panel into L2 with wide-box prefetches at the start of each tile
   int64_t tc_pair_cluster = 0;         // 1: forward / dgrad GEMMs with an even number of N tiles run as clusters of two CTA pairs (activation tile multicast).
                                        //    Measured: +7 % per SM, but only 33 clusters of 4 are co-resident (132 of 148 SMs) -> 39.3 vs 37.4 us; off by default
+  int64_t clf_grad_in_bwd = 0;         // 1 (fast mode, linear-head classifier): the fused classifier pass hands only d loss / d logits [B][8] to the backward; d loss / d mu and
+                                       //    the classifier's weight / bias gradients are formed by the latent backward kernel (no [B][L] fp32 round trip).  Written at the end of
+                                       //    round 1, NOT yet run on hardware: off until it has passed tests/test_gpu_parity.py::test_experimental_engine_variants
   int64_t tc_epi_groups = 0;           // 1: thin (K <= 128) BN = 256 forward / dgrad launches use two epilogue groups on alternate tiles (EG2).  Written from the
                                        //    epilogue phase trace at the end of round 1; NOT yet run on hardware -- off until it has passed the engine-variant test
   int64_t tc_alias_staging = 0;        // 1: split-K (wgrad) launches with at most one tile per CTA overlay the epilogue staging on the operand ring (7 stages instead of 5).
@@ -407,6 +410,7 @@ template <typename TAct> struct StepBufs {
   float* clf_g[2] = {};
   float *wpart = nullptr, *cpart = nullptr;
   float *clf_part = nullptr, *clf_sums = nullptr;
+  float* clf_grows = nullptr;      // option clf_grad_in_bwd: d loss / d logits [rows][CLF_MAXC]
   uint32_t* mhe[PSVAE_MAX_LAYERS] = {};   // ReLU bit masks of the hidden activations (tcgen05 training): [features/32][rows]
   uint32_t* mhd[PSVAE_MAX_LAYERS] = {};     // fused classifier: per-block partials, summed nll/acc
   float *sse_part = nullptr, *kl_part = nullptr, *nll_part[PSVAE_MAX_CLF_HEADS] = {}, *acc_part[PSVAE_MAX_CLF_HEADS] = {};
@@ -493,6 +497,7 @@ static void plan(const psvae_model_desc* d, int64_t rows, int mode, Bump& b, Ste
   for (int j = 1; j <= n.nh; ++j) upd(n.enc_out(j), n.enc_in(j), false);
   for (int j = 0; j <= n.nh; ++j) upd(n.dec_out(j), n.dec_in(j), false);
   if (n.has_clf()) {
+    if (clf_fused_ok(d) && g_opt.clf_grad_in_bwd) w.clf_grows = b.take<float>(rows * CLF_MAXC);
     w.dmu_clf = b.take<float>(rows * n.L);
     if (!clf_fused_ok(d)) {
       const int gw = d->clf_hidden > n.L ? d->clf_hidden : n.L;
@@ -850,6 +855,8 @@ static int run_step(const StepArgs& a) {
     ca.atomic_out = g_opt.deterministic ? 0 : 1;
     ca.grads = a.want_grads ? a.grads : nullptr;
     ca.sums = w.clf_sums;
+    // the classifier's backward moves into the latent backward kernel (fast mode only: it adds with atomics)
+    ca.g_rows = (g_opt.clf_grad_in_bwd && a.want_grads && ca.atomic_out && w.clf_grows && latent_cs_ok(n.L)) ? w.clf_grows : nullptr;
     const int blocks = clf_fused_blocks(B);
     const size_t smem = clf_fused_smem_bytes(n.L);
     float* dmu_out = a.want_grads ? w.dmu_clf : nullptr;
@@ -858,6 +865,11 @@ static int run_step(const StepArgs& a) {
     switch (n.L) {
 #define PSVAE_CLF_CASE(LL)                                                                                                              \
       case LL:                                                                                                                          \
+        if (ca.g_rows) {                                                                                                                \
+          PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<LL, TAct, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+          launch_dep(clf_fused_kernel<LL, TAct, true, true>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part, rp); \
+          break;                                                                                                                        \
+        }                                                                                                                               \
         PSVAE_CUDA(cudaFuncSetAttribute(clf_fused_kernel<LL, TAct, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
         launch_dep(clf_fused_kernel<LL, TAct, true>, dim3(blocks), dim3(CLF_TILE), smem, st, P, mu, a.y, B, ca, dmu_out, w.clf_part, rp); \
         break;
@@ -1048,7 +1060,34 @@ static int run_step(const StepArgs& a) {
   }
   // ---- through the reparameterisation and the KL term (+ the bias gradients of the encoders' last Linear)
   bool last_bias_done = false;
-  if (latent_cs_ok(n.L)) {
+  const bool clf_in_bwd = !a.ext && clf_fused && a.want_loss && g_opt.clf_grad_in_bwd && !g_opt.deterministic && w.clf_grows && latent_cs_ok(n.L);
+  if (clf_in_bwd) {
+    int blocks = ew_grid(B * n.L / 4);
+    if (blocks > 4 * PSVAE_NUM_SMS) blocks = 4 * PSVAE_NUM_SMS;
+    ClfBwdArgs cb;
+    memset(&cb, 0, sizeof(cb));
+    cb.n_heads = d->clf_num_heads;
+    for (int h = 0; h < d->clf_num_heads; ++h) {
+      cb.head_classes[h] = d->clf_head_classes[h];
+      cb.head_off[h] = cb.total_classes;
+      cb.total_classes += d->clf_head_classes[h];
+      cb.w_off[h] = d->clf_head_w[h];
+      cb.b_off[h] = d->clf_head_b[h];
+    }
+    cb.params = P; cb.grads = G; cb.g_rows = w.clf_grows;
+    const size_t smem = 256 * 8 * sizeof(float);
+    float* bias_grad = G + d->enc_b[n.nh];
+#define PSVAE_LBC(NCV)                                                                                                                          \
+    launch_dep(latent_bwd_clf_kernel<TAct, NCV>, dim3(blocks), dim3(256), smem, st, w.dz, mu, ls, w.hs, B * n.L, n.L, a.kl_w / (float)B, w.dmu, w.dls, \
+               bias_grad, (int64_t)2 * n.L, cb)
+    if (cb.total_classes <= 2) PSVAE_LBC(2);
+    else if (cb.total_classes == 3) PSVAE_LBC(3);
+    else PSVAE_LBC(CLF_MAXC);
+#undef PSVAE_LBC
+    count_launch();
+    PSVAE_LAUNCH_CHECK("latent_bwd_clf_kernel");
+    last_bias_done = true;
+  } else if (latent_cs_ok(n.L)) {
     int blocks = ew_grid(B * n.L / 4);
     if (blocks > 4 * PSVAE_NUM_SMS) blocks = 4 * PSVAE_NUM_SMS;
     float* bias_atomic = g_opt.deterministic ? nullptr : G + d->enc_b[n.nh];      // fast mode: atomics into the zeroed gradient, no reduce launch
@@ -1244,6 +1283,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_grouped")) { g_opt.tc_grouped = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_alias_staging")) { g_opt.tc_alias_staging = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_epi_groups")) { g_opt.tc_epi_groups = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "clf_grad_in_bwd")) { g_opt.clf_grad_in_bwd = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_pair_cluster")) { g_opt.tc_pair_cluster = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
@@ -1267,6 +1307,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_grouped")) return g_opt.tc_grouped;
   if (!strcmp(name, "tc_alias_staging")) return g_opt.tc_alias_staging;
   if (!strcmp(name, "tc_epi_groups")) return g_opt.tc_epi_groups;
+  if (!strcmp(name, "clf_grad_in_bwd")) return g_opt.clf_grad_in_bwd;
   if (!strcmp(name, "tc_pair_cluster")) return g_opt.tc_pair_cluster;
   if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;
