@@ -228,4 +228,39 @@ struct EpiStore {
   }
 };
 
+// Fused encoder head (option "fused_head", tcgen05 engine only; see gemm_tc.cuh, kLat): ONE kernel computes mu = he[:, :H] W_mu^T and
+// log_sigma = he[:, H:] W_sigma^T into one 128-column accumulator tile laid out [mu 0-31 | ls 0-31 | mu 32-63 | ls 32-63], and its epilogue
+// does what clf_fused_kernel<REPARAM> does today -- biases, eps (Philox or injected), z = mu + sigma eps, sigma eps / 2, the KL partial sum,
+// the linear-head classifier on mu, cross entropy, accuracy, d loss / d logits -- with a row's mu AND log_sigma in one thread's registers
+// (model.py:54-57, lightning.py:73-83,115-117).  Outputs: mu / log_sigma (fp32) and z / sigma eps / 2 (TZ) through TMA stores, d loss / d logits
+// rows for the backward (latent_bwd_clf_kernel), one (kl, nll, acc) partial per CTA.  Single classifier head with <= 4 classes, or none.
+template <typename TZ>
+struct EpiLatent {
+  using TOut = float;
+  static constexpr bool kReduce = false, kColSum = false, kSplit = false;
+  static constexpr bool kBias = false, kReluPack = false;
+  static constexpr int kAuxBytes = 0;
+  static constexpr bool kLatent = true;
+  float* out;            // mu [M][L]; log_sigma is the second slice of the 3D output map
+  int64_t ldo;
+  const float* bias;     // [2L]: mu biases, then log_sigma biases
+  TZ* z;                 // z [M][L]; sigma eps / 2 is the second slice of the 3D aux map
+  const float* eps;      // optional injected noise [M][L]
+  uint64_t seed, offset;
+  int64_t first_quad;    // global index of this shard's first Philox block (row0 * L / 4)
+  int L;
+  int nc;                // classes of the (single) linear head on mu; 0: no classifier
+  const float* clf_w;    // [nc][L]
+  const float* clf_b;    // [nc]
+  const int64_t* y;      // [M]
+  float gscale;          // clf_weight / B
+  float* g_rows;         // [M][8] d loss / d logits (nullptr: no gradients wanted)
+  float* kl_part;        // [CTAs]
+  float* nll_part;       // [CTAs]
+  float* acc_part;       // [CTAs]
+  // the generic epilogue loop is never entered for this functor (the kernel's kLat branch takes every tile); these keep it compilable
+  __device__ __forceinline__ uint32_t tc_pre(int64_t, int, bool) const { return 0u; }
+  __device__ __forceinline__ void tc_transform(int64_t, int, int, bool, float (&)[32], const float (&)[32], uint32_t, float&) const {}
+};
+
 }  // namespace psvae

@@ -28,6 +28,7 @@
 
 #include "common.cuh"
 #include "epilogue.cuh"
+#include "philox.cuh"
 #include "ptx.cuh"
 
 namespace psvae {
@@ -49,6 +50,12 @@ constexpr int TC_MAX_STAGES = 12;          // barrier slots of the operand ring
 // the CTA's row tiles (every CTA keeps one N tile: the grid is a multiple of the number of N tiles); only the activation tile streams
 // through the ring.  Per 256 x 256 x 512 tile this takes the weight re-read (256 KB per tile and pair) out of the L2 -> SM traffic, which
 // is what bounds these GEMMs.  The staged output block shrinks to 32 columns to make room.
+// kLat: the fused encoder-head kernel (EpiLatent, option "fused_head"): see the kLat branches of gemm_tc_kernel
+template <class Epi, class = void> struct epi_latent { static constexpr bool value = false; };
+template <class Epi> struct epi_latent<Epi, std::void_t<decltype(Epi::kLatent)>> { static constexpr bool value = Epi::kLatent; };
+constexpr int TC_LAT_L = 64;                     // latent width the fused head is written for
+constexpr int TC_LAT_WARP_BYTES = 13 * 1024;     // per epilogue warp: mu block / Philox scratch 4 KB | log_sigma 4 KB | z 2 KB | sigma eps / 2 2 KB | logit exchange 1 KB
+
 // ALIAS (split-K / wgrad launches in which no CTA gets more than one tile): the epilogue staging blocks overlay the first stages of the
 // operand ring -- the single epilogue of the CTA starts after its last MMA has retired and no further load is issued, so the ring is dead
 // by then -- and the ring gets the 64 KB back: 7 stages (224 KB in flight per SM) instead of 5 for the HBM-latency-bound wgrad form.
@@ -62,8 +69,10 @@ template <int BN, class Epi, int CG = 1, bool BRES = false, bool ALIAS = false, 
   static constexpr int kEpiWarps = tc_epi_warps(BN);
   static constexpr int kThreads = 32 * (2 + kEpiWarps);
   static constexpr int kColsPerWarp = EG2 ? BN / (kEpiWarps / 8) : BN / (kEpiWarps / 4);
+  static constexpr bool kLat = epi_latent<Epi>::value;
+  static_assert(!kLat || (BN == 128 && CG == 1 && !BRES && !ALIAS && !EG2), "fused head: 128-column tiles on one CTA");
   static constexpr int kABytes = TC_BM * TC_BK * 2;
-  static constexpr int kBBytes = (BN / CG) * TC_BK * 2;
+  static constexpr int kBBytes = kLat ? TC_LAT_L * TC_BK * 2 : (BN / CG) * TC_BK * 2;      // kLat: one group's 64 weight rows per k-block
   static constexpr int kStageBytes = BRES ? kABytes : kABytes + kBBytes;
   // staged output block of one epilogue warp: 32 rows x 128 bytes (fp32: 32 columns; bf16: 64 columns = two tcgen05.ld chunks per
   // fence / TMA store) -- except BN = 64 with bf16 output, where a warp owns only 32 columns (32 rows x 64 bytes)
@@ -71,7 +80,7 @@ template <int BN, class Epi, int CG = 1, bool BRES = false, bool ALIAS = false, 
   static constexpr int kBlockCols = kWide ? 64 : 32;
   static constexpr int kOutBytes = 32 * kBlockCols * (int)sizeof(typename Epi::TOut);
   static constexpr int kOutBufs = 1;
-  static constexpr int kEpiWarpBytes = kOutBufs * kOutBytes + Epi::kAuxBytes;
+  static constexpr int kEpiWarpBytes = kLat ? TC_LAT_WARP_BYTES : kOutBufs * kOutBytes + Epi::kAuxBytes;
   static constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
   static constexpr int kTmemCols = 2 * BN;     // power of two >= 32 for BN in {64,128,256}
   // layout: [barriers][epilogue staging][resident B (BRES; runtime size)][operand ring]
@@ -143,6 +152,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   constexpr bool WIDE = Cfg::kWide;
   constexpr int ROWB = Cfg::kBlockCols * (int)sizeof(TOut);   // bytes per staged row: 128, or 64 (bf16 at BN = 64)
   constexpr bool kAux = Epi::kAuxBytes > 0;
+  constexpr bool kLat = Cfg::kLat;
+  static_assert(!kLat || (!A_MN && !B_MN && CL == 1), "fused head: both operands K-major");
   static_assert(Epi::kAuxBytes == 0 || Epi::kAuxBytes == 2048 || Epi::kAuxBytes == 4096, "aux block: 32x32 bf16 or fp32");
   static_assert(!(Epi::kColSum && sizeof(TOut) != 2), "column sums are read back from a bf16 block");
   extern __shared__ uint8_t smem_raw[];
@@ -254,6 +265,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   auto tile_g = [&](int64_t n_t) { return s.groups > 1 ? (int32_t)(((uint32_t)n_t * (uint32_t)BN) / (uint32_t)s.grp_n) : 0; };
 
   float red = 0.f;
+  float lat_kl = 0.f, lat_nll = 0.f, lat_acc = 0.f;      // kLat: this thread's share of the KL sum, the NLL sum and the correct-prediction count
   // profiling: cycles this warp spent inside a class of barrier waits (accumulated per warp, written by lane 0 at the end)
   const bool tracing = s.trace != nullptr;
   long long tw0 = 0, tw1 = 0, tw2 = 0;
@@ -303,10 +315,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
         }
+        int32_t kb_b = k_el_b, row_b = b_row;
+        if constexpr (kLat) {
+          // two groups concatenated along K: the second half of the k-blocks belongs to log_sigma; a group's 64 weight rows are rows
+          // [64 g, 64 g + 64) of the stacked [2L][H] weight matrix and its k range restarts at 0
+          const int32_t kbg = (int32_t)(kb_total >> 1), gg = (int32_t)kb >= kbg ? 1 : 0;
+          kb_b = ((int32_t)kb - gg * kbg) * TC_BK;
+          row_b = gg * TC_LAT_L;
+        }
         if (want_b) {
           if constexpr (!B_MN) {
-            if (sb) ld(sb, &tma_b, k_el_b, b_row);
-            else ptx::tma_prefetch_2d(&tma_b, k_el_b, b_row);
+            if (sb) ld(sb, &tma_b, kb_b, row_b);
+            else ptx::tma_prefetch_2d(&tma_b, kb_b, row_b);
           } else {
 #pragma unroll
             for (int j = 0; j < (BN / CG) / 64; ++j) {
@@ -427,6 +447,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const uint64_t soff = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
           const uint64_t boff = BRES ? (uint64_t)((uint32_t)(kb * Cfg::kBBytes) >> 4) : soff;
           if (ptx::elect_one()) {
+            if constexpr (kLat) {
+              // accumulator columns [mu 0-31 | ls 0-31 | mu 32-63 | ls 32-63]: group gg's weight rows 0-31 / 32-63 go to two 32-column
+              // MMAs, so that one epilogue warp finds mu AND log_sigma of the same 32 latent dims in its 64 columns
+              const int64_t kbg = kb_total >> 1;
+              const uint32_t gg = kb >= kbg ? 1u : 0u;
+              const bool first_kb = (kb == 0 || kb == kbg);
+              const uint32_t idesc_lat = ptx::make_idesc_bf16(TM, 32, 0, 0);
+#pragma unroll
+              for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
+#pragma unroll
+                for (int hh = 0; hh < 2; ++hh) {
+                  const uint64_t da = da0 + soff + (uint64_t)((kk * a_kstep) >> 4);
+                  const uint64_t db = db0 + boff + (uint64_t)((kk * b_kstep + hh * 32 * 128) >> 4);
+                  ptx::umma_f16(tmem_d + (uint32_t)(hh * 64) + gg * 32u, da, db, idesc_lat, (first_kb && kk == 0) ? 0u : 1u);
+                }
+              }
+            } else {
 #pragma unroll
             for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
               const uint64_t da = da0 + soff + (uint64_t)((kk * a_kstep) >> 4);
@@ -434,6 +471,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
               const uint32_t accum = (kb > kb0 || kk > 0) ? 1u : 0u;
               if constexpr (CG == 2) ptx::umma_f16_cg2(tmem_d, da, db, idesc, accum);
               else ptx::umma_f16(tmem_d, da, db, idesc, accum);
+            }
             }
             // smem slot free (in both CTAs of a pair) once these MMAs retire
             if constexpr (CG == 2) ptx::umma_commit_cg2_mc(&empty_bar[stage], (uint16_t)(CL == 2 ? 0xF : 3));
@@ -503,6 +541,142 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const int64_t row = (int64_t)row_base + lane;
       const bool valid = row < s.M;
       const int col_base = (int)(n_t * BN) + half * COLS_PER_WARP;
+      if constexpr (kLat) {
+        // ---- fused encoder head: this warp owns rows [row_base, +32) and latent dims [32 half, 32 half + 32); its 64 accumulator
+        //      columns are [mu | log_sigma] of exactly those dims
+        static_assert(sizeof(decltype(*epi.z)) == 2, "fused head: bf16 z");
+        uint8_t* const st_mu = obuf0;                                  // 32 x 32 fp32 (128-byte swizzled rows); first: Philox scratch [8][32] float4
+        uint8_t* const st_ls = obuf0 + 4096;
+        uint8_t* const st_z = obuf0 + 8192;                            // 32 x 32 bf16 (64-byte swizzled rows)
+        uint8_t* const st_hs = obuf0 + 10240;
+        float* const xch = reinterpret_cast<float*>(obuf0 + 12288);    // [2 parities][32 lanes][4] partial logits for the sibling warp
+        const float* const xch_sib = reinterpret_cast<const float*>(smem + Cfg::kEpiOff + (ew ^ 4) * Cfg::kEpiWarpBytes + 12288);
+        const int lat0 = half * 32;
+        twait(&tfull_bar[acc], acc_phase, 4, tw0);
+        ptx::tc_fence_after();
+        uint32_t r_mu[32], r_ls[32];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 64);
+        ptx::tmem_ld_32x32_issue(taddr, r_mu);
+        ptx::tmem_ld_32x32_issue(taddr + 32, r_ls);
+        float mu_v[32], ls_v[32];
+        load_vec<32>(epi.bias + lat0, mu_v);                           // biases, fetched while the TMEM reads are in flight
+        load_vec<32>(epi.bias + epi.L + lat0, ls_v);
+        ptx::tmem_ld_wait(r_mu);
+        ptx::tmem_ld_wait(r_ls);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mu_v[i] += __uint_as_float(r_mu[i]);
+          ls_v[i] += __uint_as_float(r_ls[i]);
+        }
+        // the accumulator buffer is free again: everything this warp needs is in registers
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+        // noise: injected, or the counter-based generator (rolled loop: the scratch block keeps the code small, see langevin.cuh)
+        if (lane == 0) ptx::bulk_wait_read0();                         // the previous tile's TMA stores have finished reading this warp's blocks
+        __syncwarp();
+        float e[32];
+        if (epi.eps) {
+          if (valid) {
+            load_vec<32>(epi.eps + row * epi.L + lat0, e);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) e[i] = 0.f;
+          }
+        } else {
+          float4* const scratch = reinterpret_cast<float4*>(st_mu);
+          const uint64_t q0 = (uint64_t)epi.first_quad + (((uint64_t)row * (uint64_t)epi.L + (uint64_t)lat0) >> 2);
+#pragma unroll 2
+          for (int q = 0; q < 8; ++q) scratch[q * 32 + lane] = philox_normal4(q0 + (uint64_t)q, epi.seed, epi.offset);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 t = scratch[q * 32 + lane];
+            e[4 * q] = t.x; e[4 * q + 1] = t.y; e[4 * q + 2] = t.z; e[4 * q + 3] = t.w;
+          }
+          __syncwarp();                                                // every lane holds its normals before the block becomes the mu staging block
+        }
+        // mu / log_sigma blocks (fp32)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          *reinterpret_cast<float4*>(st_mu + swz_off<128>(lane, j)) = make_float4(mu_v[j * 4], mu_v[j * 4 + 1], mu_v[j * 4 + 2], mu_v[j * 4 + 3]);
+          *reinterpret_cast<float4*>(st_ls + swz_off<128>(lane, j)) = make_float4(ls_v[j * 4], ls_v[j * 4 + 1], ls_v[j * 4 + 2], ls_v[j * 4 + 3]);
+        }
+        // reparameterisation (model.py:56-57), sigma eps / 2 for the backward pass, KL partial (lightning.py:115-117)
+        float klv = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float zz[8], hh[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float m = mu_v[j * 8 + i], l = ls_v[j * 8 + i], ee = e[j * 8 + i];
+            const float sigma = expf(0.5f * l);
+            zz[i] = fmaf(sigma, ee, m);
+            hh[i] = 0.5f * sigma * ee;
+            klv += 1.f + l - m * m - sigma * sigma;
+          }
+          uint4 uz, uh;
+          uz.x = pack_bf16x2(zz[0], zz[1]); uz.y = pack_bf16x2(zz[2], zz[3]); uz.z = pack_bf16x2(zz[4], zz[5]); uz.w = pack_bf16x2(zz[6], zz[7]);
+          uh.x = pack_bf16x2(hh[0], hh[1]); uh.y = pack_bf16x2(hh[2], hh[3]); uh.z = pack_bf16x2(hh[4], hh[5]); uh.w = pack_bf16x2(hh[6], hh[7]);
+          *reinterpret_cast<uint4*>(st_z + swz_off<64>(lane, j)) = uz;
+          *reinterpret_cast<uint4*>(st_hs + swz_off<64>(lane, j)) = uh;
+        }
+        if (valid) lat_kl += klv;
+        // linear-head classifier on mu (lightning.py:73-83): this warp's 32 dims give partial logits; the sibling warp (same rows, the
+        // other 32 dims) supplies the rest through shared memory
+        if (epi.nc > 0) {
+          float lp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int cc = 0; cc < 4; ++cc) {
+            if (cc < epi.nc) {
+              const float* wrow = epi.clf_w + (int64_t)cc * epi.L + lat0;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) lp[cc] = fmaf(mu_v[i], __ldg(wrow + i), lp[cc]);
+            }
+          }
+          *reinterpret_cast<float4*>(xch + acc * 128 + lane * 4) = make_float4(lp[0], lp[1], lp[2], lp[3]);
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");        // the two warps of this lane quarter
+          const float4 o = *reinterpret_cast<const float4*>(xch_sib + acc * 128 + lane * 4);
+          float logit[4] = {lp[0] + o.x, lp[1] + o.y, lp[2] + o.z, lp[3] + o.w};
+          if (half == 0 && valid) {
+            const int tgt = (int)epi.y[row];
+            float mx = -INFINITY, lt = 0.f;
+            int arg = 0;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+              if (cc < epi.nc) {
+                logit[cc] += __ldg(epi.clf_b + cc);
+                if (logit[cc] > mx) { mx = logit[cc]; arg = cc; }      // first maximum, like torch.argmax
+                if (cc == tgt) lt = logit[cc];
+              }
+            }
+            float se = 0.f;
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc)
+              if (cc < epi.nc) se += expf(logit[cc] - mx);
+            const float lse = logf(se);
+            lat_nll += -(lt - mx - lse);
+            lat_acc += (arg == tgt) ? 1.f : 0.f;
+            if (epi.g_rows) {
+              float g[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int cc = 0; cc < 4; ++cc)
+                if (cc < epi.nc) g[cc] = (expf(logit[cc] - mx - lse) - (cc == tgt ? 1.f : 0.f)) * epi.gscale;
+              *reinterpret_cast<float4*>(epi.g_rows + row * 8) = make_float4(g[0], g[1], g[2], g[3]);
+              *reinterpret_cast<float4*>(epi.g_rows + row * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_store_3d(&tma_out, st_mu, lat0, row_base, 0);
+          ptx::tma_store_3d(&tma_out, st_ls, lat0, row_base, 1);
+          ptx::tma_store_3d(&tma_aux, st_z, lat0, row_base, 0);
+          ptx::tma_store_3d(&tma_aux, st_hs, lat0, row_base, 1);
+          ptx::bulk_commit();
+        }
+        continue;
+      }
       if constexpr (Epi::kColSum) {
         if (n_t != cs_nt) { cs_flush(); cs_nt = n_t; }
       }
@@ -697,6 +871,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   ptx::tc_fence_before();
   if constexpr (CG == 2) ptx::cluster_sync();     // neither CTA may retire while the pair's MMAs / multicast commits can still touch it
   else __syncthreads();
+  if constexpr (kLat) {
+    // one (KL sum, NLL sum, correct count) record per CTA, summed in a fixed order (warps, then the three values one after the other)
+    float* const outs[3] = {epi.kl_part, epi.nll_part, epi.acc_part};
+    const float vals[3] = {lat_kl, lat_nll, lat_acc};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const float ws = warp_sum(vals[k]);
+      if (lane == 0) red_smem[warp] = ws;
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < Cfg::kThreads / 32; ++w) t += red_smem[w];
+        if (outs[k]) outs[k][blockIdx.x] = t;
+      }
+      __syncthreads();
+    }
+  }
   if constexpr (Epi::kReduce) {
     const float ws = warp_sum(red);
     if (lane == 0) red_smem[warp] = ws;
@@ -893,6 +1084,66 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   }
   count_launch();
   PSVAE_LAUNCH_CHECK("gemm_tc_kernel");
+  return 0;
+}
+
+// Fused encoder head (EpiLatent): he [M][2H] bf16 (mu half | sigma half), Wstack [2L][H] bf16 (W_mu rows, then W_sigma rows).  One CTA per
+// 128-row tile; outputs through 3D maps (slice 0 / 1 = mu / log_sigma, z / sigma eps / 2).  Returns the CTAs launched in *ctas.
+template <typename TZ>
+int gemm_tc_launch_latent(const void* he, int64_t ldhe, const void* Wstack, int H, int64_t M, const EpiLatent<TZ>& epi, float* mu, float* ls, TZ* z, TZ* hs,
+                          cudaStream_t st, int* ctas) {
+  using Epi = EpiLatent<TZ>;
+  constexpr int BN = 128;
+  using Cfg = TcCfg<BN, Epi, 1, false>;
+  const int Lz = TC_LAT_L;
+  if (epi.L != Lz || H % TC_BK != 0 || epi.nc > 4 || ls <= mu || hs <= z) { set_error("fused head: needs latent_dim 64, hidden_dim %% 64 == 0, <= 4 classes"); return -2; }
+  CUtensorMap ta, tb, tout, taux;
+  TcOperand a{he, M, ldhe, false};
+  TcOperand b{Wstack, (int64_t)2 * Lz, (int64_t)H, false};
+  PSVAE_TRY(tc_tensor_map(a, (int64_t)2 * H, TC_BM, &ta));
+  PSVAE_TRY(tc_tensor_map(b, (int64_t)H, Lz, &tb));
+  PSVAE_TRY(tc_block_map(mu, 4, M, Lz, Lz, 2, (int64_t)(ls - mu), &tout, 32));
+  PSVAE_TRY(tc_block_map(z, (int)sizeof(TZ), M, Lz, Lz, 2, (int64_t)(hs - z), &taux, 32));
+  TcShape s;
+  memset(&s, 0, sizeof(s));
+  s.M = M; s.N = BN; s.K = (int64_t)2 * H; s.splits = 1;
+  tc_desc_strides(false, &s.a_lbo, &s.a_sbo);
+  tc_desc_strides(false, &s.b_lbo, &s.b_sbo);
+  s.stages = Cfg::kStages;
+  if (tc_max_stages() >= 2 && tc_max_stages() < s.stages) s.stages = tc_max_stages();
+  s.trace = tc_trace_ptr();
+  s.groups = 1;
+  auto kern = gemm_tc_kernel<BN, false, false, Epi, 1, false, 1, false, false>;
+  static unsigned long long attr_mask = 0;
+  int dev = 0;
+  PSVAE_CUDA(cudaGetDevice(&dev));
+  if (!(attr_mask >> (dev & 63) & 1ull)) {
+    PSVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_mask |= 1ull << (dev & 63);
+  }
+  const int64_t tiles = ceil_div64(M, TC_BM);
+  int grid = tc_grid_size();
+  if (tiles < grid) grid = (int)tiles;
+  if (grid < 1) return 0;
+  if (ctas) *ctas = grid;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  int na = 0;
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, ta, s, epi));
+  count_launch();
+  PSVAE_LAUNCH_CHECK("gemm_tc_kernel<EpiLatent>");
   return 0;
 }
 

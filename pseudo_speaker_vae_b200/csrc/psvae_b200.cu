@@ -63,6 +63,9 @@ struct Options {
   int64_t tc_tile_prefetch = 0;        // 1: the producer pulls the NEXT tile's whole activation panel into L2 with wide-box prefetches at the start of each tile
   int64_t tc_pair_cluster = 0;         // 1: forward / dgrad GEMMs with an even number of N tiles run as clusters of two CTA pairs (activation tile multicast).
                                        //    Measured: +7 % per SM, but only 33 clusters of 4 are co-resident (132 of 148 SMs) -> 39.3 vs 37.4 us; off by default
+  int64_t fused_head = 0;              // 1 (training, tcgen05 fast mode, latent 64, at most one linear head of <= 4 classes; needs clf_grad_in_bwd when there is a classifier):
+                                       //    encoder heads + reparameterisation + KL + classifier forward in ONE kernel (EpiLatent).  Written at the end of round 1, NOT yet
+                                       //    run on hardware
   int64_t clf_grad_in_bwd = 0;         // 1 (fast mode, linear-head classifier): the fused classifier pass hands only d loss / d logits [B][8] to the backward; d loss / d mu and
                                        //    the classifier's weight / bias gradients are formed by the latent backward kernel (no [B][L] fp32 round trip).  Written at the end of
                                        //    round 1, NOT yet run on hardware: off until it has passed tests/test_gpu_parity.py::test_experimental_engine_variants
@@ -815,8 +818,37 @@ static int run_step(const StepArgs& a) {
     }
   }
   bool head_done = false;
+  // option fused_head: encoder heads + reparameterisation + KL + classifier forward in one kernel (training, fast mode)
+  bool fused_head = false;
+  int fused_ctas = 0;
   if constexpr (sizeof(TAct) == 2) {
-    if (grouped_head) {
+    const bool clf_shape_ok = !n.has_clf() || (clf_fused_ok(d) && d->clf_num_heads == 1 && d->clf_head_classes[0] <= 4);
+    const bool clf_bwd_ok = !n.has_clf() || (g_opt.clf_grad_in_bwd && w.clf_grows != nullptr && latent_cs_ok(n.L));
+    fused_head = g_opt.fused_head && a.want_loss && a.want_grads && !g_opt.deterministic && n.L == TC_LAT_L && n.H % TC_BK == 0 && clf_shape_ok && clf_bwd_ok &&
+                 ls > mu && ((ls - mu) % 4) == 0 && w.hs > w.z;
+    if (fused_head) {
+      EpiLatent<TAct> e;
+      memset(&e, 0, sizeof(e));
+      e.out = mu; e.ldo = n.L;
+      e.bias = P + d->enc_b[n.nh];
+      e.z = w.z;
+      e.eps = a.eps; e.seed = a.seed; e.offset = a.offset; e.first_quad = first_elem >> 2;
+      e.L = n.L;
+      e.nc = n.has_clf() ? d->clf_head_classes[0] : 0;
+      e.clf_w = n.has_clf() ? P + d->clf_head_w[0] : nullptr;
+      e.clf_b = n.has_clf() ? P + d->clf_head_b[0] : nullptr;
+      e.y = a.y;
+      e.gscale = a.clf_w / (float)B;
+      e.g_rows = n.has_clf() ? w.clf_grows : nullptr;
+      e.kl_part = w.kl_part;
+      e.nll_part = n.has_clf() ? w.clf_part : nullptr;
+      e.acc_part = n.has_clf() ? w.clf_part + PSVAE_NUM_SMS : nullptr;
+      PSVAE_TRY(gemm_tc_launch_latent<TAct>(w.he[n.nh - 1], 2 * n.H, Wt + d->enc_w[n.nh], n.H, B, e, mu, ls, w.z, w.hs, st, &fused_ctas));
+      head_done = true;
+    }
+  }
+  if constexpr (sizeof(TAct) == 2) {
+    if (grouped_head && !head_done) {
       EpiBiasAct<float, ACT_NONE> e{P + d->enc_b[n.nh], mu, n.L, nullptr};
       PSVAE_TRY((Engine<TAct>::template gemm_grouped<G_FWD>(w.he[n.nh - 1], 2 * n.H, Wt + d->enc_w[n.nh], n.H, B, 2, n.L, n.H, (int64_t)(ls - mu), e, st)));
       head_done = true;
@@ -833,7 +865,9 @@ static int run_step(const StepArgs& a) {
   const bool clf_fused = n.has_clf() && clf_fused_ok(d);
   const bool fuse_latent = clf_fused && a.want_loss;
   int n_kl_used = (int)w.n_kl;
-  if (!fuse_latent) {
+  if (fused_head) {
+    n_kl_used = fused_ctas;            // the fused kernel wrote one KL / NLL / accuracy record per CTA
+  } else if (!fuse_latent) {
     launch_dep(latent_fwd_kernel<TAct>, dim3((unsigned)w.n_kl), dim3(256), 0, st, mu, ls, a.eps, a.seed, a.offset, first_elem, B * n.L, w.z, nullptr, w.kl_part,
                                                                   a.want_grads ? w.hs : nullptr);
     count_launch();
@@ -889,7 +923,7 @@ static int run_step(const StepArgs& a) {
       PSVAE_LAUNCH_CHECK("clf_fused_finish_kernel");
     }
   }
-  if (fuse_latent) {
+  if (fuse_latent || fused_head) {
   } else if (n.has_clf() && a.want_loss) {
     for (int t = 0; t < d->clf_num_trunk; ++t) {
       PSVAE_TRY(clf_linear(d->clf_activation, feat, t == 0 ? n.L : d->clf_hidden, P + d->clf_trunk_w[t], P + d->clf_trunk_b[t], w.clf_act[t], B,
@@ -991,6 +1025,7 @@ static int run_step(const StepArgs& a) {
     }
     lp.recon_scale = a.use_cos ? 1.f / (float)B : 1.f / ((float)B * (float)n.D * 10.f);
     lp.inv_b = 1.f / (float)B;
+    if (fused_head && lp.n_heads > 0) { lp.nll[0] = w.clf_part; lp.acc[0] = w.clf_part + PSVAE_NUM_SMS; lp.n_ce = fused_ctas; lp.ce_stride = 1; }
     lp.kl_w = a.kl_w; lp.clf_w = a.clf_w;
     if (cons_on) { lp.cons_nll = cw.nll_part; lp.cons_acc = cw.acc_part; lp.n_cons = (int)cw.n_ce; lp.cons_w = a.cons_w; }
     launch_dep(finalize_losses_kernel, dim3(1), dim3(1024), 0, st, lp, a.losses);
@@ -1284,6 +1319,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_alias_staging")) { g_opt.tc_alias_staging = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_epi_groups")) { g_opt.tc_epi_groups = value ? 1 : 0; return 0; }
   if (!strcmp(name, "clf_grad_in_bwd")) { g_opt.clf_grad_in_bwd = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "fused_head")) { g_opt.fused_head = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_pair_cluster")) { g_opt.tc_pair_cluster = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
@@ -1308,6 +1344,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_alias_staging")) return g_opt.tc_alias_staging;
   if (!strcmp(name, "tc_epi_groups")) return g_opt.tc_epi_groups;
   if (!strcmp(name, "clf_grad_in_bwd")) return g_opt.clf_grad_in_bwd;
+  if (!strcmp(name, "fused_head")) return g_opt.fused_head;
   if (!strcmp(name, "tc_pair_cluster")) return g_opt.tc_pair_cluster;
   if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;

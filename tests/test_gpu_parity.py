@@ -815,12 +815,13 @@ def test_engine_variants_reproduce_the_default_path(opts):
 
 
 @pytest.mark.skipif(os.environ.get("PSVAE_TEST_EXPERIMENTAL") != "1", reason="engine variants written but not yet run on hardware (set PSVAE_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("opts", [dict(tc_epi_groups=1), dict(clf_grad_in_bwd=1)])
+@pytest.mark.parametrize("opts", [dict(tc_epi_groups=1), dict(clf_grad_in_bwd=1), dict(clf_grad_in_bwd=1, fused_head=1)])
 def test_experimental_engine_variants(opts):
     """Variants that have not passed on a B200 yet stay out of the default run.  tc_epi_groups (two epilogue groups on alternate tiles for
     the K <= 128 layers): forward outputs must be bit-identical to the default path, losses / gradients equal up to summation order
     (fast mode: the variant does not apply to the ordered column sums of deterministic mode).  clf_grad_in_bwd: the classifier's backward
-    formed in the latent backward kernel from d loss / d logits."""
+    formed in the latent backward kernel from d loss / d logits.  fused_head: encoder heads + reparameterisation + KL + classifier forward in
+    one kernel (its accumulators come from 32-column MMAs: outputs are compared to 1e-5, not bit for bit)."""
     G = _gu()
     module, cfg = _big_module(G, "bf16")
     hot = module.hot_path
@@ -840,8 +841,12 @@ def test_experimental_engine_variants(opts):
         for k, v in opts.items():
             G.L.set_option(k, v)
         g1, l1, o1 = run()
-        assert all(torch.equal(a, b) for a, b in zip(o0, o1))
-        assert torch.allclose(l0, l1, rtol=2e-6, atol=1e-7)
+        if "fused_head" in opts:
+            assert all(((a.double() - b.double()).norm() / a.double().norm()).item() <= 1e-5 for a, b in zip(o0, o1))
+            assert torch.allclose(l0, l1, rtol=1e-5, atol=1e-6)
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(o0, o1))
+            assert torch.allclose(l0, l1, rtol=2e-6, atol=1e-7)
         assert ((g1.double() - g0.double()).norm() / g0.double().norm()).item() <= 1e-5
     finally:
         for k, v in defaults.items():
