@@ -108,6 +108,10 @@ struct TcGroup {
   int groups = 1;
   int grp_n = 0, grp_k = 0;
   int64_t out_group_stride = 0;      // elements between the groups' output buffers; 0: column ranges of one [M][groups * grp_n] buffer
+  // wgrad form (GBM, "grouped by m"): the groups' output blocks are stacked along M ([groups * grp_m][N], e.g. [W_mu; W_sigma]); group g's A
+  // columns are the natural [g * grp_m, (g+1) * grp_m) of dY and its B operand starts b_off columns further per group (the activation buffer
+  // [rows][groups * b_off] shared by the two encoders)
+  int by_m = 0, grp_m = 0, b_off = 0;
 };
 
 struct TcShape {
@@ -138,13 +142,14 @@ template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
 // CL = 2 (only with CG = 2, K-major A, streaming B): clusters of two CTA pairs that work on the same row tile and adjacent N tiles; every CTA
 // loads HALF of its 128 activation rows per k-block and multicasts them to its twin in the other pair, so the activation tile crosses the
 // L2 -> SM fabric once per cluster instead of once per pair (-25 % operand traffic per pair, ring depth unchanged).
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL, bool ALIAS = false, bool EG2 = false>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL, bool ALIAS = false, bool EG2 = false, bool GBM = false>
 __global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
                const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_apf, TcShape s, Epi epi) {
   using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS, EG2>;
   static_assert(!ALIAS || (Epi::kSplit && Epi::kAuxBytes == 0 && CL == 1), "ALIAS: split-K store epilogue, one tile per CTA (host-checked)");
   static_assert(!EG2 || (CL == 1 && !BRES && !ALIAS), "EG2: plain streaming kernel");
+  static_assert(!GBM || (A_MN && B_MN && CL == 1 && !BRES), "GBM: the wgrad form");
   using TOut = typename Epi::TOut;
   constexpr int STAGES = TC_MAX_STAGES;                    // barrier slots; s.stages of them are in use
   constexpr int EPI_WARPS = Cfg::kEpiWarps;
@@ -330,8 +335,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           } else {
 #pragma unroll
             for (int j = 0; j < (BN / CG) / 64; ++j) {
+              if constexpr (GBM) {
+                // wgrad form grouped by m: the group of this M tile picks the B columns (s.grp_n = rows of C per group, s.grp_k = B column offset per group)
+                const int32_t gb = b_row + (int32_t)(((uint32_t)m_t * (uint32_t)TM) / (uint32_t)s.grp_n) * s.grp_k;
+                if (sb) ld(sb + j * (64 * TC_BK * 2), &tma_b, gb + j * 64, k_el_b);
+                else ptx::tma_prefetch_2d(&tma_b, gb + j * 64, k_el_b);
+              } else {
               if (sb) ld(sb + j * (64 * TC_BK * 2), &tma_b, b_row + j * 64, k_el_b);
               else ptx::tma_prefetch_2d(&tma_b, b_row + j * 64, k_el_b);
+              }
             }
           }
         }
@@ -983,19 +995,19 @@ template <class Epi> struct epi_split_stride<Epi, std::enable_if_t<Epi::kSplit>>
 template <class Epi, class = void> struct epi_cs_atomic { static bool get(const Epi&) { return false; } };
 template <class Epi> struct epi_cs_atomic<Epi, std::enable_if_t<Epi::kColSum>> { static bool get(const Epi& e) { return e.colsum_atomic != 0; } };
 
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false, int CL = 1, bool ALIAS = false, bool EG2 = false>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false, int CL = 1, bool ALIAS = false, bool EG2 = false, bool GBM = false>
 int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st,
                       const TcGroup& grp = TcGroup()) {
   using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS, EG2>;
   using TOut = typename Epi::TOut;
   CUtensorMap ta, tb, tout, taux, tapf;
   // grouped: K is one group's contraction length; A spans all groups' k ranges, an MN-major B all groups' k rows
-  PSVAE_TRY(tc_tensor_map(A, K * grp.groups, A_MN ? TC_BK : TC_BM / CL, &ta));      // CL = 2: every CTA loads (and multicasts) half of its 128 rows
+  PSVAE_TRY(tc_tensor_map(A, GBM ? K : K * grp.groups, A_MN ? TC_BK : TC_BM / CL, &ta));      // CL = 2: every CTA loads (and multicasts) half of its 128 rows
   tapf = ta;
   if constexpr (!A_MN) {
     if (tc_tile_prefetch()) PSVAE_TRY(tc_prefetch_map(A, K, TC_BM, &tapf));
   }
-  PSVAE_TRY(tc_tensor_map(B, B_MN ? K * grp.groups : K, B_MN ? TC_BK : BN / CG, &tb));
+  PSVAE_TRY(tc_tensor_map(B, (B_MN && !GBM) ? K * grp.groups : K, B_MN ? TC_BK : BN / CG, &tb));
   TcShape s;
   s.M = M; s.N = N; s.K = K; s.splits = splits < 1 ? 1 : splits;
   tc_desc_strides(A_MN, &s.a_lbo, &s.a_sbo);
@@ -1005,7 +1017,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   if (tc_max_stages() >= 2 && tc_max_stages() < s.stages) s.stages = tc_max_stages();
   s.reverse = tc_next_direction();
   s.trace = tc_trace_ptr();
-  s.groups = grp.groups; s.grp_n = grp.grp_n; s.grp_k = grp.grp_k;
+  s.groups = GBM ? 1 : grp.groups; s.grp_n = GBM ? (grp.grp_m > 0 ? grp.grp_m : 1) : grp.grp_n; s.grp_k = GBM ? grp.b_off : grp.grp_k;
   s.out3d = (grp.groups > 1 && grp.out_group_stride != 0) ? 1 : 0;
   s.b_stable = (BRES && tc_b_stable()) ? 1 : 0;
   s.tile_pf = (!A_MN && tc_tile_prefetch() && grp.groups == 1) ? 1 : 0;
@@ -1022,7 +1034,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   } else {
     taux = ta;
   }
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, BRES, CL, ALIAS, EG2>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, BRES, CL, ALIAS, EG2, GBM>;
   static unsigned long long attr_mask = 0;   // per instantiation, one bit per device
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
@@ -1167,6 +1179,9 @@ int gemm_tc_launch_pick(const TcOperand& A, const TcOperand& B, int64_t M, int N
     if (tc_epi_groups() && K <= 128 && !ordered_colsum)
       return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 1, false, true>(A, B, M, N, K, splits, epi, st, grp);
   }
+  if constexpr (A_MN && B_MN && Epi::kSplit) {
+    if (grp.by_m) return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 1, false, false, true>(A, B, M, N, K, splits, epi, st, grp);
+  }
   if constexpr (A_MN && Epi::kSplit && Epi::kAuxBytes == 0) {
     // wgrad form, at most one tile per CTA (pair): the epilogue staging overlays the operand ring (two more stages in flight)
     const int64_t tiles = ceil_div64(M, TC_BM * CG) * ceil_div64(N, BN) * (splits < 1 ? 1 : splits);
@@ -1190,7 +1205,14 @@ template <bool A_MN, bool B_MN, class Epi>
 int gemm_tc_launch(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st, int force_bn = 0,
                    const TcGroup& grp = TcGroup()) {
   if (N % 8 != 0) { set_error("gemm_tc: N=%d must be a multiple of 8", N); return -2; }
-  const int bn = force_bn ? force_bn : tc_pick_bn(grp.groups > 1 ? grp.grp_n : N);      // a tile never straddles two groups
+  const int bn = force_bn ? force_bn : tc_pick_bn((grp.groups > 1 && !grp.by_m) ? grp.grp_n : N);      // a tile never straddles two groups
+  if (grp.by_m) {
+    const int tm = TC_BM * (tc_use_pair(M, N, bn) ? 2 : 1);
+    if (!(A_MN && B_MN) || grp.grp_m % tm != 0 || M != (int64_t)grp.groups * grp.grp_m) {
+      set_error("gemm_tc: a launch grouped by m needs the wgrad form and grp_m %% %d == 0", tm);
+      return -2;
+    }
+  } else
   if (grp.groups > 1 && (A_MN || splits > 1 || grp.grp_n % bn != 0 || grp.grp_k % TC_BK != 0 || N != grp.groups * grp.grp_n)) {
     set_error("gemm_tc: grouped launch needs K-major A, no split-K, grp_n %% %d == 0 and grp_k %% %d == 0", bn, TC_BK);
     return -2;

@@ -63,6 +63,8 @@ struct Options {
   int64_t tc_tile_prefetch = 0;        // 1: the producer pulls the NEXT tile's whole activation panel into L2 with wide-box prefetches at the start of each tile
   int64_t tc_pair_cluster = 0;         // 1: forward / dgrad GEMMs with an even number of N tiles run as clusters of two CTA pairs (activation tile multicast).
                                        //    Measured: +7 % per SM, but only 33 clusters of 4 are co-resident (132 of 148 SMs) -> 39.3 vs 37.4 us; off by default
+  int64_t tc_grouped_wgrad = 0;        // 1 (fast mode): the two encoders' hidden-layer wgrads run as ONE launch grouped by m ([W_mu; W_sigma] stacked along the output rows).
+                                       //    Written at the end of round 1, NOT yet run on hardware
   int64_t fused_head = 0;              // 1 (training, tcgen05 fast mode, latent 64, at most one linear head of <= 4 classes; needs clf_grad_in_bwd when there is a classifier):
                                        //    encoder heads + reparameterisation + KL + classifier forward in ONE kernel (EpiLatent).  Written at the end of round 1, NOT yet
                                        //    run on hardware
@@ -314,6 +316,16 @@ template <> struct Engine<bf16> {
     TcGroup g;
     g.groups = groups; g.grp_n = Ng; g.grp_k = Kg; g.out_group_stride = out_group_stride;
     return gemm_tc_launch<false, b_mn, Epi>(a, b, M, groups * Ng, Kg, 1, epi, st, (int)g_opt.tc_force_bn, g);
+  }
+  // both encoders' wgrad of one hidden layer in one launch: dY [rows][groups * out_g], act [rows][groups * in] -> [groups * out_g][in] (stacked)
+  template <class Epi>
+  static int wgrad_grouped(const bf16* dY, int64_t ldy, const bf16* act, int64_t lda, int64_t rows, int groups, int out_g, int in, int splits, const Epi& epi,
+                           cudaStream_t st) {
+    TcOperand a{dY, (int64_t)groups * out_g, ldy, true};
+    TcOperand b{act, (int64_t)groups * in, lda, true};
+    TcGroup g;
+    g.groups = groups; g.by_m = 1; g.grp_m = out_g; g.b_off = in;
+    return gemm_tc_launch<true, true, Epi>(a, b, (int64_t)groups * out_g, in, rows, splits, epi, st, (int)g_opt.tc_force_bn, g);
   }
   static bool grouped_ok(int Ng, int Kg) {
     const int bn = g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(Ng);
@@ -1179,7 +1191,18 @@ static int run_step(const StepArgs& a) {
                                    G + d->enc_b[n.nh - 1] + s * n.H, w, &bias_done[s], st));
     }
     for (int j = n.nh - 1; j >= 1; --j) {
-      for (int s = 0; s < 2; ++s) {
+      bool wgrad_pair_done = false;
+      if constexpr (sizeof(TAct) == 2) {
+        // option tc_grouped_wgrad: one launch for both encoders ([W_mu_j; W_sigma_j] is one [2H][H] block of the gradient buffer)
+        const int tm = TC_BM * (tc_use_pair(2 * n.H, n.H, (int)g_opt.tc_force_bn) ? 2 : 1);
+        if (g_opt.tc_grouped_wgrad && !g_opt.deterministic && bias_done[0] && bias_done[1] && n.H % tm == 0) {
+          const int splits = Engine<TAct>::wgrad_splits(2 * n.H, n.H, B);
+          EpiStore e{G + d->enc_w[j], n.H, 0, 1.f, 0.f, nullptr, 1};
+          PSVAE_TRY((Engine<TAct>::wgrad_grouped(w.ge[pp], 2 * n.H, w.he[j - 1], 2 * n.H, B, 2, n.H, n.H, splits, e, st)));
+          wgrad_pair_done = true;
+        }
+      }
+      for (int s = 0; s < 2 && !wgrad_pair_done; ++s) {
         const TAct* dY = w.ge[pp] + s * n.H;
         PSVAE_TRY(wgrad<TAct>(dY, 2 * n.H, w.he[j - 1] + s * n.H, 2 * n.H, B, n.H, n.H, G + d->enc_w[j] + (int64_t)s * n.H * n.H,
                               bias_done[s] ? nullptr : G + d->enc_b[j] + s * n.H, w, st));
@@ -1320,6 +1343,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_epi_groups")) { g_opt.tc_epi_groups = value ? 1 : 0; return 0; }
   if (!strcmp(name, "clf_grad_in_bwd")) { g_opt.clf_grad_in_bwd = value ? 1 : 0; return 0; }
   if (!strcmp(name, "fused_head")) { g_opt.fused_head = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_grouped_wgrad")) { g_opt.tc_grouped_wgrad = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_pair_cluster")) { g_opt.tc_pair_cluster = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
@@ -1345,6 +1369,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_epi_groups")) return g_opt.tc_epi_groups;
   if (!strcmp(name, "clf_grad_in_bwd")) return g_opt.clf_grad_in_bwd;
   if (!strcmp(name, "fused_head")) return g_opt.fused_head;
+  if (!strcmp(name, "tc_grouped_wgrad")) return g_opt.tc_grouped_wgrad;
   if (!strcmp(name, "tc_pair_cluster")) return g_opt.tc_pair_cluster;
   if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;

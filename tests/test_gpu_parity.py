@@ -815,7 +815,8 @@ def test_engine_variants_reproduce_the_default_path(opts):
 
 
 @pytest.mark.skipif(os.environ.get("PSVAE_TEST_EXPERIMENTAL") != "1", reason="engine variants written but not yet run on hardware (set PSVAE_TEST_EXPERIMENTAL=1)")
-@pytest.mark.parametrize("opts", [dict(tc_epi_groups=1), dict(clf_grad_in_bwd=1), dict(clf_grad_in_bwd=1, fused_head=1)])
+@pytest.mark.parametrize("opts", [dict(tc_epi_groups=1), dict(clf_grad_in_bwd=1), dict(clf_grad_in_bwd=1, fused_head=1),
+                                  dict(tc_grouped_wgrad=1)])
 def test_experimental_engine_variants(opts):
     """Variants that have not passed on a B200 yet stay out of the default run.  tc_epi_groups (two epilogue groups on alternate tiles for
     the K <= 128 layers): forward outputs must be bit-identical to the default path, losses / gradients equal up to summation order
