@@ -366,3 +366,12 @@ def test_batch_loader_order_sharding_and_split(tmp_path):
     single = D.PackedEmbeddingStore.from_cv(root, str(tmp_path / "packed1"), metadata_transform="gender")
     x, y = next(iter(D.PinnedBatchLoader(single, 4, device="cpu", shuffle=False)))
     assert y.dtype == torch.int64 and y.tolist() == single.labels[0, :4].tolist()
+
+
+def test_variants_not_yet_run_on_hardware_are_off_by_default():
+    """Engine variants written without GPU time must not be on the default path until their gated equivalence test
+    (tests/test_gpu_parity.py::test_experimental_engine_variants, tools/validate_experimental.sh) has passed on a B200."""
+    for name in ("tc_epi_groups", "clf_grad_in_bwd", "fused_head", "tc_grouped_wgrad"):
+        assert L.get_option(name) == 0, name
+    for name, default in (("tc_alias_staging", 0), ("tc_grouped", 1), ("pdl", 1), ("tc_two_cta", 1), ("deterministic", 0)):
+        assert L.get_option(name) == default, name
