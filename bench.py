@@ -8,7 +8,9 @@ throughputs of configs[3] as secondary lines inside the same JSON object.
 One JSON line on stdout (rank 0).  `value` = whole-job samples/s with inputs resident in HBM; `e2e` = the same metric
 through the Lightning-style public API (training_step -> loss.backward() -> optimizer.step()) with the batch coming
 from pinned host memory every step and the loss read back; `roofline` = algorithmic FLOPs of the step / measured step
-time against the measured bf16 peak; `cpu_baseline` = oracle/torch_port.py (the reference's own torch CPU path,
+time against the measured bf16 peak (the WHOLE step, all 24 launches: the strict figure), with `roofline.dominant_kernel` =
+the hidden-layer GEMM alone (algorithmic FLOPs per launch / its launch time, CUDA events on rotating operand sets) and
+`roofline.traffic` = DRAM bytes of one step from the committed ncu pass; `cpu_baseline` = oracle/torch_port.py (the reference's own torch CPU path,
 restated) on this box's host cores.  `--impl reference` times only that CPU path.
 """
 from __future__ import annotations
