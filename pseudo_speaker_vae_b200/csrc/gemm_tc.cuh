@@ -79,7 +79,8 @@ template <int BN, class Epi, int CG = 1, bool BRES = false, bool ALIAS = false, 
   static constexpr bool kWide = sizeof(typename Epi::TOut) == 2 && BN >= 128 && !BRES;
   static constexpr int kBlockCols = kWide ? 64 : 32;
   static constexpr int kOutBytes = 32 * kBlockCols * (int)sizeof(typename Epi::TOut);
-  static constexpr int kOutBufs = 1;
+  static constexpr int kOutBufs = EG2 ? 2 : 1;      // EG2: a warp stages two 64-column blocks per tile back to back -- two buffers, so the second does not wait
+                                                     // for the first one's TMA store (K <= 128: the ring needs no depth, the 64 KB are free)
   static constexpr int kEpiWarpBytes = kLat ? TC_LAT_WARP_BYTES : kOutBufs * kOutBytes + Epi::kAuxBytes;
   static constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
   static constexpr int kTmemCols = 2 * BN;     // power of two >= 32 for BN in {64,128,256}
@@ -780,12 +781,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
           // WIDE (bf16, BN >= 128): two consecutive 32-column chunks share one 32 x 128-byte block, one fence and one TMA store
-          uint8_t* const obuf = obuf0;
+          uint8_t* const obuf = obuf0 + (Cfg::kOutBufs == 2 ? ((WIDE ? (c >> 1) : c) & 1) * Cfg::kOutBytes : 0);
           const int part = WIDE ? (c & 1) : 0;
           const bool opens = !WIDE || part == 0;
           const bool closes = !WIDE || part == 1 || col + 32 >= s.N || c + 1 == CH;
           if (opens) {          // the TMA store that last used this staging block must have finished reading it
-            if (lane == 0) ptx::bulk_wait_read0();
+            if (lane == 0) {
+              if constexpr (Cfg::kOutBufs == 2) ptx::bulk_wait_read1();      // two blocks alternate: only the store before the last one must be done
+              else ptx::bulk_wait_read0();
+            }
             __syncwarp();
           }
           if constexpr (sizeof(TOut) == 2) {
