@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PSVAE_ABI_VERSION 2
+#define PSVAE_ABI_VERSION 3
 #define PSVAE_MAX_LAYERS 8      /* Linear layers per MLP (num_hidden + 1) */
 #define PSVAE_MAX_CLF_TRUNK 4   /* hidden Linear layers of the latent classifier */
 #define PSVAE_MAX_CLF_HEADS 4   /* output heads of the latent classifier */
@@ -38,6 +38,11 @@ extern "C" {
 /* precision of the GEMM chains */
 #define PSVAE_FP32 0 /* CUDA-core FFMA, fp32 storage: the 1e-5 parity mode                       */
 #define PSVAE_BF16 1 /* tcgen05 kind::f16 (bf16 operands, fp32 accumulate in TMEM), bf16 storage */
+
+/* element type of the input batch x: the reference's DataLoader yields fp32 (ps_vae/data/cv.py:51-76); a bf16 embedding store
+ * (pseudo_speaker_vae_b200/data.py) hands its rows over as they are (tensor-core mode only: no cast pass, half the H2D bytes) */
+#define PSVAE_X_F32 0
+#define PSVAE_X_BF16 1
 
 /* classifier activations (ps_vae/latent_classifier.py:18-23) */
 #define PSVAE_ACT_RELU 0
@@ -140,12 +145,18 @@ int psvae_philox_uint32(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset
 int psvae_philox_normal(float* out, int64_t n_rows, int32_t n_cols, uint64_t seed, uint64_t offset, int64_t row0,
                         void* stream);
 
+/* ---- batch assembly out of an HBM-resident packed store: replaces the DataLoader collate of ps_vae/data/cv.py:73-76, :111-123 ---- */
+/* dst[i][:] = src[idx[i]][:], rows of row_bytes bytes (a multiple of 16; src and dst 16-byte aligned), idx a DEVICE int64 array of n
+ * entries (an index outside [0, src_rows) gives a zero row).  The whole Common Voice train split is 345 MB in bf16: it lives in HBM
+ * and the per-step traffic over PCIe is the index list. */
+int psvae_gather_rows(const void* src, int64_t src_rows, int64_t row_bytes, const int64_t* idx, int64_t n, void* dst, void* stream);
+
 /* ---- bf16 operand copy of the parameters (call after any out-of-band parameter change) -------- */
 int psvae_refresh_shadow(const psvae_model_desc* desc, const float* params, void* shadow_bf16, void* stream);
 
 /* ---- VAEModel.forward (ps_vae/model.py:38-63) -------------------------------------------------- */
 /* eps == NULL: in-kernel Philox draw with (seed, offset), element index (row0 + r)*L + c. */
-int psvae_forward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, const float* x,
+int psvae_forward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, const void* x, int32_t x_dtype,
                   const float* eps, uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, int32_t precision,
                   float* x_hat, float* mu, float* log_sigma, void* workspace, int64_t workspace_bytes, void* stream);
 
@@ -158,9 +169,12 @@ int psvae_decode(const psvae_model_desc* desc, const float* params, const void* 
 /* ---- PseudoSpeakerVAE.training_step + loss.backward() (lightning.py:67-131 + autograd) -------- */
 /* Computes the losses and ALL parameter gradients (written, not accumulated, into `grads`, same layout
  * as `params`).  y: int64 [num_heads][rows] (NULL without classifier).  use_cos_loss: lightning.py:110-111.
- * compute_grads = 0 gives validation_step (lightning.py:133-197).  x_hat / mu / log_sigma are optional. */
+ * compute_grads = 0 gives validation_step (lightning.py:133-197).  x_hat / mu / log_sigma are optional.
+ * x: [rows][D] fp32 (x_dtype = PSVAE_X_F32) or bf16 (PSVAE_X_BF16: precision PSVAE_BF16 and the plain MSE tail only -- the bf16
+ * values are then both the first GEMM's operand and the reconstruction target).
+ * A class label outside [0, classes) makes the classifier loss (and the total) NaN, where torch's cross_entropy raises. */
 int psvae_train_fwd_bwd(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads,
-                        const float* x, const int64_t* y, const float* eps, uint64_t seed, uint64_t offset,
+                        const void* x, int32_t x_dtype, const int64_t* y, const float* eps, uint64_t seed, uint64_t offset,
                         int64_t row0, int64_t rows, float kl_weight, float clf_weight, int32_t use_cos_loss,
                         int32_t compute_grads, int32_t precision, float* x_hat, float* mu, float* log_sigma,
                         float* losses, void* workspace, int64_t workspace_bytes, void* stream);
@@ -170,8 +184,8 @@ int psvae_train_fwd_bwd(const psvae_model_desc* desc, const float* params, const
  * back-propagates the given d loss / d x_hat [rows][D], d loss / d mu, d loss / d log_sigma [rows][L] (each may be NULL = zero) into
  * `grads` (written, not accumulated; the classifier's entries stay zero).  No loss term is added inside.  workspace >=
  * psvae_workspace_bytes(desc, rows, precision, PSVAE_MODE_TRAIN). */
-int psvae_vae_backward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const float* x,
-                       const float* eps, uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, int32_t precision,
+int psvae_vae_backward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const void* x,
+                       int32_t x_dtype, const float* eps, uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, int32_t precision,
                        const float* g_x_hat, const float* g_mu, const float* g_log_sigma, void* workspace, int64_t workspace_bytes,
                        void* stream);
 
@@ -188,7 +202,7 @@ int psvae_consistency_forward(const psvae_consistency_desc* cons, const float* c
  * the batch).  losses[PSVAE_LOSS_CONS], [PSVAE_LOSS_CONS_ACC] are filled.  workspace >= psvae_workspace_bytes(...) +
  * psvae_consistency_workspace_bytes(...).  The classifier runs in fp32 on the CUDA cores in both precisions. */
 int psvae_train_fwd_bwd_consistency(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads,
-                                    const float* x, const int64_t* y, const float* eps, uint64_t seed, uint64_t offset,
+                                    const void* x, int32_t x_dtype, const int64_t* y, const float* eps, uint64_t seed, uint64_t offset,
                                     int64_t row0, int64_t rows, float kl_weight, float clf_weight, int32_t use_cos_loss,
                                     int32_t compute_grads, int32_t precision, float* x_hat, float* mu, float* log_sigma,
                                     float* losses, void* workspace, int64_t workspace_bytes, void* stream,

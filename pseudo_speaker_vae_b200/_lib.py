@@ -13,12 +13,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # PSVAE_B200_LIB: load another build of the same ABI instead (A/B timing of two kernel versions in one process tree; tools only)
 LIB_PATH = os.environ.get("PSVAE_B200_LIB") or os.path.join(HERE, "libpsvae_b200.so")
 
-PSVAE_ABI_VERSION = 2
+PSVAE_ABI_VERSION = 3
 MAX_LAYERS = 8
 MAX_CLF_TRUNK = 4
 MAX_CLF_HEADS = 4
 NUM_LOSSES = 16
 FP32, BF16 = 0, 1
+X_F32, X_BF16 = 0, 1
 MODE_TRAIN, MODE_FORWARD, MODE_DECODE = 0, 1, 2
 ACTIVATIONS = {"relu": 0, "tanh": 1, "sigmoid": 2, "leaky_relu": 3}
 LOSS_TOTAL, LOSS_RECON, LOSS_KL, LOSS_CLF, LOSS_CLF_HEAD0, LOSS_ACC_HEAD0 = 0, 1, 2, 3, 4, 8
@@ -30,7 +31,7 @@ EXPORTS = [
     "psvae_flops_per_sample", "psvae_set_option", "psvae_get_option", "psvae_adam_step", "psvae_philox_uint32", "psvae_philox_normal",
     "psvae_refresh_shadow", "psvae_forward", "psvae_decode", "psvae_train_fwd_bwd", "psvae_langevin", "psvae_gemm_bf16",
     "psvae_gemm_fp32", "psvae_gemm_probe", "psvae_launch_count", "psvae_consistency_desc_init", "psvae_consistency_workspace_bytes",
-    "psvae_consistency_forward", "psvae_train_fwd_bwd_consistency", "psvae_vae_backward",
+    "psvae_consistency_forward", "psvae_train_fwd_bwd_consistency", "psvae_vae_backward", "psvae_gather_rows",
 ]
 
 
@@ -86,16 +87,18 @@ def _declare(l: C.CDLL) -> None:
     l.psvae_philox_uint32.argtypes = [VP, I64, U64, U64, I64, VP]
     l.psvae_philox_normal.restype = C.c_int
     l.psvae_philox_normal.argtypes = [VP, I64, I32, U64, U64, I64, VP]
+    l.psvae_gather_rows.restype = C.c_int
+    l.psvae_gather_rows.argtypes = [VP, I64, I64, VP, I64, VP, VP]
     l.psvae_refresh_shadow.restype = C.c_int
     l.psvae_refresh_shadow.argtypes = [D, VP, VP, VP]
     l.psvae_forward.restype = C.c_int
-    l.psvae_forward.argtypes = [D, VP, VP, VP, VP, U64, U64, I64, I64, I32, VP, VP, VP, VP, I64, VP]
+    l.psvae_forward.argtypes = [D, VP, VP, VP, I32, VP, U64, U64, I64, I64, I32, VP, VP, VP, VP, I64, VP]
     l.psvae_decode.restype = C.c_int
     l.psvae_decode.argtypes = [D, VP, VP, VP, U64, U64, I64, I64, I32, VP, VP, VP, I64, VP]
     l.psvae_train_fwd_bwd.restype = C.c_int
-    l.psvae_train_fwd_bwd.argtypes = [D, VP, VP, VP, VP, VP, VP, U64, U64, I64, I64, F, F, I32, I32, I32, VP, VP, VP, VP, VP, I64, VP]
+    l.psvae_train_fwd_bwd.argtypes = [D, VP, VP, VP, VP, I32, VP, VP, U64, U64, I64, I64, F, F, I32, I32, I32, VP, VP, VP, VP, VP, I64, VP]
     l.psvae_vae_backward.restype = C.c_int
-    l.psvae_vae_backward.argtypes = [D, VP, VP, VP, VP, VP, U64, U64, I64, I64, I32, VP, VP, VP, VP, I64, VP]
+    l.psvae_vae_backward.argtypes = [D, VP, VP, VP, VP, I32, VP, U64, U64, I64, I64, I32, VP, VP, VP, VP, I64, VP]
     CD = P(ConsistencyDesc)
     l.psvae_consistency_desc_init.restype = C.c_int
     l.psvae_consistency_desc_init.argtypes = [CD, I32, I32, I32]

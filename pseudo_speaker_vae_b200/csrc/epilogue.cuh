@@ -89,16 +89,17 @@ struct EpiBiasAct {
 };
 
 // CS: the tcgen05 engine also emits the column sums of the stored gradient (= the bias gradient of the last decoder layer)
-template <typename TOut_, bool CS = false>
+// TX: type of the reconstruction target (float: the caller's fp32 batch; bf16: a batch that arrived in bf16, psvae_b200.h PSVAE_X_BF16)
+template <typename TOut_, bool CS = false, typename TX = float>
 struct EpiMse {
   using TOut = TOut_;
   static constexpr bool kReduce = true, kColSum = CS, kSplit = false;
   static constexpr bool kBias = true, kReluPack = false;
-  static constexpr int kAuxBytes = 4096;      // tcgen05 engine: the fp32 target tile x[32 rows][32 cols] arrives by TMA
+  static constexpr int kAuxBytes = 1024 * (int)sizeof(TX);      // tcgen05 engine: the target tile x[32 rows][32 cols] arrives by TMA (4 KB fp32 / 2 KB bf16)
   __host__ const void* aux_ptr() const { return x; }
   __host__ int64_t aux_ld() const { return ldx; }
   const float* bias;   // [N]
-  const float* x;      // [M, ldx] fp32 target
+  const TX* x;         // [M, ldx] target
   int64_t ldx;
   float* x_hat;        // optional fp32 output [M, ldxh]
   int64_t ldxh;

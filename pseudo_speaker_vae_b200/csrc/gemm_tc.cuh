@@ -651,8 +651,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           const float4 o = *reinterpret_cast<const float4*>(xch_sib + acc * 128 + lane * 4);
           float logit[4] = {lp[0] + o.x, lp[1] + o.y, lp[2] + o.z, lp[3] + o.w};
           if (half == 0 && valid) {
-            const int tgt = (int)epi.y[row];
-            float mx = -INFINITY, lt = 0.f;
+            const int64_t ty = epi.y[row];
+            const int tgt = (ty < 0 || ty >= (int64_t)epi.nc) ? -1 : (int)ty;
+            float mx = -INFINITY, lt = (tgt < 0) ? __int_as_float(0x7fc00000) : 0.f;      // label out of range: NaN loss (see ce_kernel)
             int arg = 0;
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {

@@ -118,6 +118,25 @@ __global__ void __launch_bounds__(256) cast_bf16_kernel(const float* __restrict_
   if (t < n) out[t] = __float2bfloat16_rn(in[t]);
 }
 
+// ---------------------------------------------------------------- batch gather out of an HBM-resident embedding store
+// dst[i][:] = src[idx[i]][:] for rows of `vec_per_row` 16-byte vectors (a 256-d bf16 row = 32 vectors = one warp-wide 512-byte read):
+// the DataLoader's collate (ps_vae/data/cv.py:73-76 + default_collate) when the packed store lives in HBM.  An index outside [0, src_rows)
+// yields a zero row.  HBM-bound: rows are >= 256 B, so every sector fetched is used.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const uint4* __restrict__ src, int64_t src_rows, int vec_per_row, const int64_t* __restrict__ idx,
+                                                          int64_t n, uint4* __restrict__ dst) {
+  PSVAE_GRID_DEP();
+  const int64_t total = n * vec_per_row;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int64_t r = i / vec_per_row;
+    const int v = (int)(i - r * vec_per_row);
+    const int64_t s = __ldg(idx + r);
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (s >= 0 && s < src_rows) val = __ldg(src + s * vec_per_row + v);
+    dst[i] = val;
+  }
+}
+
 // ---------------------------------------------------------------- latent forward / backward
 // Thread = 4 consecutive latent elements (= one Philox block).  KL partial: one slot per block.
 template <typename TAct>
@@ -204,9 +223,13 @@ __global__ void __launch_bounds__(256) ce_kernel(float* __restrict__ logits, con
     float se = 0.f;
     for (int c = 0; c < C; ++c) se += expf(lg[c] - mx);
     const float lse = logf(se);
-    const int t = (int)y[r];
-    nll = -(lg[t] - mx - lse);
-    correct = (arg == t) ? 1.f : 0.f;
+    // a label outside [0, C) (utils.map_cv_*_to_label returns -1 for unknown metadata; torch's cross_entropy raises): no out-of-bounds
+    // read, and the loss is poisoned with NaN instead of a plausible-looking value
+    const int64_t ty = y[r];
+    const bool bad = ty < 0 || ty >= (int64_t)C;
+    const int t = bad ? 0 : (int)ty;
+    nll = bad ? __int_as_float(0x7fc00000) : -(lg[t] - mx - lse);
+    correct = (!bad && arg == t) ? 1.f : 0.f;
     if (write_grad) {
       for (int c = 0; c < C; ++c) {
         const float p = expf(lg[c] - mx - lse);
@@ -617,8 +640,9 @@ __global__ void __launch_bounds__(CLF_TILE) clf_fused_kernel(const float* __rest
         for (int h = 0; h < 4; ++h) {
           if (h < a.n_heads) {
             const int c0 = a.head_off[h], C = a.head_classes[h];
-            const int tgt = (int)y[(int64_t)h * B + r];
-            float mx = -INFINITY, lt = 0.f;
+            const int64_t ty = y[(int64_t)h * B + r];
+            const int tgt = (ty < 0 || ty >= (int64_t)C) ? -1 : (int)ty;
+            float mx = -INFINITY, lt = (tgt < 0) ? __int_as_float(0x7fc00000) : 0.f;      // label out of range: NaN loss (see ce_kernel)
             int arg = 0;
 #pragma unroll
             for (int c = 0; c < CLF_MAXC; ++c)

@@ -63,16 +63,16 @@ struct Options {
   int64_t tc_tile_prefetch = 0;        // 1: the producer pulls the NEXT tile's whole activation panel into L2 with wide-box prefetches at the start of each tile
   int64_t tc_pair_cluster = 0;         // 1: forward / dgrad GEMMs with an even number of N tiles run as clusters of two CTA pairs (activation tile multicast).
                                        //    Measured: +7 % per SM, but only 33 clusters of 4 are co-resident (132 of 148 SMs) -> 39.3 vs 37.4 us; off by default
-  int64_t tc_grouped_wgrad = 0;        // 1 (fast mode): the two encoders' hidden-layer wgrads run as ONE launch grouped by m ([W_mu; W_sigma] stacked along the output rows).
-                                       //    Written at the end of round 1, NOT yet run on hardware
-  int64_t fused_head = 0;              // 1 (training, tcgen05 fast mode, latent 64, at most one linear head of <= 4 classes; needs clf_grad_in_bwd when there is a classifier):
-                                       //    encoder heads + reparameterisation + KL + classifier forward in ONE kernel (EpiLatent).  Written at the end of round 1, NOT yet
-                                       //    run on hardware
-  int64_t clf_grad_in_bwd = 0;         // 1 (fast mode, linear-head classifier): the fused classifier pass hands only d loss / d logits [B][8] to the backward; d loss / d mu and
-                                       //    the classifier's weight / bias gradients are formed by the latent backward kernel (no [B][L] fp32 round trip).  Written at the end of
-                                       //    round 1, NOT yet run on hardware: off until it has passed tests/test_gpu_parity.py::test_experimental_engine_variants
-  int64_t tc_epi_groups = 0;           // 1: thin (K <= 128) BN = 256 forward / dgrad launches use two epilogue groups on alternate tiles (EG2).  Written from the
-                                       //    epilogue phase trace at the end of round 1; NOT yet run on hardware -- off until it has passed the engine-variant test
+  int64_t tc_grouped_wgrad = 1;        // 1 (fast mode): the two encoders' hidden-layer wgrads run as ONE launch grouped by m ([W_mu; W_sigma] stacked along the output rows).
+                                       //    Measured (round 2, A/B on one box, three alternating pairs): 0.7837 -> 0.7769 ms/step
+  int64_t fused_head = 1;              // 1 (training, tcgen05 fast mode, latent 64, at most one linear head of <= 4 classes): encoder heads + reparameterisation + KL +
+                                       //    classifier forward in ONE kernel (EpiLatent); the classifier's backward then runs inside the latent backward kernel.
+                                       //    Measured (round 2, A/B): 0.7867 -> 0.7758 ms/step
+  int64_t clf_grad_in_bwd = 0;         // 1 (fast mode, linear-head classifier, also where the fused head does not apply): the fused classifier pass hands only d loss / d logits
+                                       //    [B][8] to the backward; d loss / d mu and the classifier's weight / bias gradients are formed by the latent backward kernel.
+                                       //    Measured on its own (round 2, A/B): 0.7840 -> 0.7887 ms/step -- slower, so off; the fused head uses the same backward regardless
+  int64_t tc_epi_groups = 1;           // 1: thin (K <= 128) BN = 256 forward / dgrad launches use two epilogue groups on alternate tiles (EG2).
+                                       //    Measured (round 2, A/B): 0.7832 -> 0.7733 ms/step
   int64_t tc_alias_staging = 0;        // 1: split-K (wgrad) launches with at most one tile per CTA overlay the epilogue staging on the operand ring (7 stages instead of 5).
                                        //    Measured neutral (31.4 vs 31.7 us for the 512 x 512 wgrad): the wgrad form is not bound by bytes in flight; off by default
   int64_t tc_grouped = 1;              // 1: layers 1..n of the two encoders run as ONE block-diagonal launch each (forward and dgrad) instead of one per encoder
@@ -446,6 +446,16 @@ static int clf_fused_blocks(int64_t rows) {
   return b < 1 ? 1 : (int)b;
 }
 static bool latent_cs_ok(int L) { return L % 4 == 0 && 256 % (L / 4) == 0 && 2 * L <= 256; }
+// Does the tcgen05 train step of this model use the fused encoder-head kernel (EpiLatent)?  Decided from the model shape and the options only
+// (so that the workspace plan and the step agree): latent 64, hidden a multiple of 64, no classifier or ONE linear head of <= 4 classes.
+static bool fused_head_shape_ok(const psvae_model_desc* d) {
+  if (!g_opt.fused_head || g_opt.deterministic) return false;
+  if (d->latent_dim != TC_LAT_L || d->hidden_dim % TC_BK != 0) return false;
+  if (d->clf_num_heads > 0 && !(clf_fused_ok(d) && d->clf_num_heads == 1 && d->clf_head_classes[0] <= 4 && latent_cs_ok(d->latent_dim))) return false;
+  return true;
+}
+// the [rows][CLF_MAXC] d loss / d logits buffer exists when the classifier's backward runs inside the latent backward kernel
+static bool clf_rows_wanted(const psvae_model_desc* d) { return clf_fused_ok(d) && (g_opt.clf_grad_in_bwd || fused_head_shape_ok(d)); }
 
 static int64_t sse_slots(int64_t rows, int D) {
   int64_t a = sgemm_red_slots(rows, D);
@@ -512,7 +522,7 @@ static void plan(const psvae_model_desc* d, int64_t rows, int mode, Bump& b, Ste
   for (int j = 1; j <= n.nh; ++j) upd(n.enc_out(j), n.enc_in(j), false);
   for (int j = 0; j <= n.nh; ++j) upd(n.dec_out(j), n.dec_in(j), false);
   if (n.has_clf()) {
-    if (clf_fused_ok(d) && g_opt.clf_grad_in_bwd) w.clf_grows = b.take<float>(rows * CLF_MAXC);
+    if (clf_rows_wanted(d)) w.clf_grows = b.take<float>(rows * CLF_MAXC);
     w.dmu_clf = b.take<float>(rows * n.L);
     if (!clf_fused_ok(d)) {
       const int gw = d->clf_hidden > n.L ? d->clf_hidden : n.L;
@@ -705,7 +715,7 @@ struct StepArgs {
   const float* params;
   const bf16* shadow;
   float* grads;
-  const float* x;
+  const float* x;            // fp32 input [rows][D] ...
   const int64_t* y;
   const float* eps;
   uint64_t seed, offset;
@@ -726,6 +736,9 @@ struct StepArgs {
   const float* ext_gx = nullptr;
   const float* ext_gmu = nullptr;
   const float* ext_gls = nullptr;
+  // ... or the same batch already in bf16 (PSVAE_X_BF16; tensor-core mode only): the operand of the first GEMM as it is, no cast pass, and the
+  // reconstruction target of the MSE epilogue (the data ARE these bf16 values: a bf16 embedding store, data.py)
+  const bf16* x16 = nullptr;
 };
 
 template <typename TAct> static const TAct* weights_of(const StepArgs& a);
@@ -754,7 +767,12 @@ static int run_step(const StepArgs& a) {
   const int64_t B = a.rows;
   cudaStream_t st = a.st;
   if (B <= 0) { set_error("rows=%lld must be positive", (long long)B); return -2; }
-  if (!a.params || !a.x) { set_error("params and x must not be NULL"); return -1; }
+  if (!a.params || !(a.x || a.x16)) { set_error("params and x must not be NULL"); return -1; }
+  if (a.x16 && sizeof(TAct) != 2) { set_error("a bf16 input batch needs precision PSVAE_BF16 (the fp32 parity engine takes fp32 x)"); return -2; }
+  if (a.x16 && a.want_loss && (d->normalize_decoder || a.use_cos || a.cons)) {
+    set_error("a bf16 input batch is supported by the fused MSE tail only (no normalize_decoder / use_cos_loss / consistency classifier): pass fp32 x");
+    return -2;
+  }
   if (sizeof(TAct) == 2 && !a.shadow) { set_error("PSVAE_BF16 needs the bf16 shadow copy of the parameters (psvae_refresh_shadow)"); return -1; }
   if (a.want_grads && !a.grads) { set_error("grads must not be NULL when compute_grads != 0"); return -1; }
   if (a.want_loss && !a.losses) { set_error("losses must not be NULL"); return -1; }
@@ -788,18 +806,32 @@ static int run_step(const StepArgs& a) {
   // (tcgen05 mode: the operand cast of x below clears the buffer in the same pass -- total_numel is a multiple of 64 and the buffer 16-byte aligned)
   const bool zero_in_cast = sizeof(TAct) == 2 && a.want_grads && (reinterpret_cast<uintptr_t>(a.grads) & 15) == 0;
   if (a.want_grads && !zero_in_cast) PSVAE_CUDA(cudaMemsetAsync(a.grads, 0, (size_t)d->total_numel * sizeof(float), st));
-  float* mu = a.mu ? a.mu : w.mu;
-  float* ls = a.ls ? a.ls : w.ls;
+  // option fused_head (training, fast mode): encoder heads + reparameterisation + KL + classifier forward in one kernel.  Its 3D output maps
+  // step from mu to log_sigma (and from z to sigma eps / 2) by one stride, so it writes the workspace buffers; a caller's mu / log_sigma get a copy.
+  bool fused_head = false;
+  if constexpr (sizeof(TAct) == 2)
+    fused_head = fused_head_shape_ok(d) && a.want_loss && a.want_grads && !a.ext && (!n.has_clf() || w.clf_grows != nullptr) && w.hs > w.z && w.ls > w.mu;
+  float* mu = (a.mu && !fused_head) ? a.mu : w.mu;
+  float* ls = (a.ls && !fused_head) ? a.ls : w.ls;
   const int64_t first_elem = a.row0 * n.L;
 
   // ---- encoders (model.py:54-55).  Layer 0 of both encoders is one [2H, D] GEMM.
   const TAct* xa;
   if constexpr (sizeof(TAct) == 2) {
-    launch_dep(cast_bf16_kernel, dim3(ew_grid(B * n.D / 8)), dim3(256), 0, st, a.x, w.xa, B * n.D, zero_in_cast ? a.grads : (float*)nullptr,
-               zero_in_cast ? d->total_numel : (int64_t)0);
-    count_launch();
-    PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
-    xa = w.xa;
+    if (a.x16) {
+      xa = a.x16;
+      if (zero_in_cast) {      // no cast pass: the same kernel only clears the gradient buffer (5 MB, L2-resident)
+        launch_dep(cast_bf16_kernel, dim3(ew_grid(d->total_numel / 4)), dim3(256), 0, st, (const float*)nullptr, (bf16*)nullptr, (int64_t)0, a.grads, d->total_numel);
+        count_launch();
+        PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
+      }
+    } else {
+      launch_dep(cast_bf16_kernel, dim3(ew_grid(B * n.D / 8)), dim3(256), 0, st, a.x, w.xa, B * n.D, zero_in_cast ? a.grads : (float*)nullptr,
+                 zero_in_cast ? d->total_numel : (int64_t)0);
+      count_launch();
+      PSVAE_LAUNCH_CHECK("cast_bf16_kernel");
+      xa = w.xa;
+    }
   } else {
     xa = a.x;
   }
@@ -831,13 +863,8 @@ static int run_step(const StepArgs& a) {
   }
   bool head_done = false;
   // option fused_head: encoder heads + reparameterisation + KL + classifier forward in one kernel (training, fast mode)
-  bool fused_head = false;
   int fused_ctas = 0;
   if constexpr (sizeof(TAct) == 2) {
-    const bool clf_shape_ok = !n.has_clf() || (clf_fused_ok(d) && d->clf_num_heads == 1 && d->clf_head_classes[0] <= 4);
-    const bool clf_bwd_ok = !n.has_clf() || (g_opt.clf_grad_in_bwd && w.clf_grows != nullptr && latent_cs_ok(n.L));
-    fused_head = g_opt.fused_head && a.want_loss && a.want_grads && !g_opt.deterministic && n.L == TC_LAT_L && n.H % TC_BK == 0 && clf_shape_ok && clf_bwd_ok &&
-                 ls > mu && ((ls - mu) % 4) == 0 && w.hs > w.z;
     if (fused_head) {
       EpiLatent<TAct> e;
       memset(&e, 0, sizeof(e));
@@ -857,6 +884,8 @@ static int run_step(const StepArgs& a) {
       e.acc_part = n.has_clf() ? w.clf_part + PSVAE_NUM_SMS : nullptr;
       PSVAE_TRY(gemm_tc_launch_latent<TAct>(w.he[n.nh - 1], 2 * n.H, Wt + d->enc_w[n.nh], n.H, B, e, mu, ls, w.z, w.hs, st, &fused_ctas));
       head_done = true;
+      if (a.mu) PSVAE_CUDA(cudaMemcpyAsync(a.mu, mu, (size_t)B * n.L * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      if (a.ls) PSVAE_CUDA(cudaMemcpyAsync(a.ls, ls, (size_t)B * n.L * sizeof(float), cudaMemcpyDeviceToDevice, st));
     }
   }
   if constexpr (sizeof(TAct) == 2) {
@@ -963,11 +992,22 @@ static int run_step(const StepArgs& a) {
     if constexpr (sizeof(TAct) == 2) {
       if (a.want_grads && tc_colsum_ok(n.D)) {     // + column sums of dxh = bias gradient of the last decoder layer
         const bool atomic = !g_opt.deterministic;
-        EpiMse<TAct, true> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, w.dxh, n.D, scale, w.sse_part, atomic ? a.grads + d->dec_b[n.nh] : w.cpart,
-                             atomic ? 1 : 0};
-        PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st, (a.want_grads && w.mhd[0]) ? w.mhd : nullptr));
+        if (a.x16) {
+          EpiMse<TAct, true, bf16> e{P + d->dec_b[n.nh], a.x16, n.D, a.x_hat, n.D, w.dxh, n.D, scale, w.sse_part, atomic ? a.grads + d->dec_b[n.nh] : w.cpart,
+                                     atomic ? 1 : 0};
+          PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st, (a.want_grads && w.mhd[0]) ? w.mhd : nullptr));
+        } else {
+          EpiMse<TAct, true> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, w.dxh, n.D, scale, w.sse_part, atomic ? a.grads + d->dec_b[n.nh] : w.cpart,
+                               atomic ? 1 : 0};
+          PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st, (a.want_grads && w.mhd[0]) ? w.mhd : nullptr));
+        }
         launched = dec_last_bias_done = true;
         dec_last_bias_reduce = !atomic;
+      }
+      if (!launched && a.x16) {
+        EpiMse<TAct, false, bf16> e{P + d->dec_b[n.nh], a.x16, n.D, a.x_hat, n.D, a.want_grads ? w.dxh : nullptr, n.D, scale, w.sse_part, nullptr, 0};
+        PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st, (a.want_grads && w.mhd[0]) ? w.mhd : nullptr));
+        launched = true;
       }
     }
     if (!launched) {
@@ -1107,7 +1147,7 @@ static int run_step(const StepArgs& a) {
   }
   // ---- through the reparameterisation and the KL term (+ the bias gradients of the encoders' last Linear)
   bool last_bias_done = false;
-  const bool clf_in_bwd = !a.ext && clf_fused && a.want_loss && g_opt.clf_grad_in_bwd && !g_opt.deterministic && w.clf_grows && latent_cs_ok(n.L);
+  const bool clf_in_bwd = !a.ext && clf_fused && a.want_loss && (g_opt.clf_grad_in_bwd || fused_head) && !g_opt.deterministic && w.clf_grows && latent_cs_ok(n.L);
   if (clf_in_bwd) {
     int blocks = ew_grid(B * n.L / 4);
     if (blocks > 4 * PSVAE_NUM_SMS) blocks = 4 * PSVAE_NUM_SMS;
@@ -1496,6 +1536,22 @@ int psvae_philox_normal(float* out, int64_t n_rows, int32_t n_cols, uint64_t see
   return 0;
 }
 
+int psvae_gather_rows(const void* src, int64_t src_rows, int64_t row_bytes, const int64_t* idx, int64_t n, void* dst, void* stream) {
+  PSVAE_TRY(tc_device_check());
+  if (!src || !idx || !dst) { set_error("src, idx, dst must not be NULL"); return -1; }
+  if (n <= 0) return 0;
+  if (row_bytes <= 0 || row_bytes % 16 || ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) != 0) {
+    set_error("gather: rows must be a multiple of 16 bytes and 16-byte aligned (row_bytes=%lld)", (long long)row_bytes);
+    return -2;
+  }
+  const int vpr = (int)(row_bytes / 16);
+  launch_dep(gather_rows_kernel, dim3(ew_grid(n * vpr)), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const uint4*>(src), src_rows, vpr, idx, n,
+             static_cast<uint4*>(dst));
+  count_launch();
+  PSVAE_LAUNCH_CHECK("gather_rows_kernel");
+  return 0;
+}
+
 int psvae_refresh_shadow(const psvae_model_desc* desc, const float* params, void* shadow_bf16, void* stream) {
   PSVAE_TRY(tc_device_check());
   if (!desc || !params || !shadow_bf16) { set_error("desc, params, shadow must not be NULL"); return -1; }
@@ -1507,13 +1563,23 @@ int psvae_refresh_shadow(const psvae_model_desc* desc, const float* params, void
   return 0;
 }
 
-int psvae_train_fwd_bwd(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const float* x, const int64_t* y,
+// x arrives as fp32 or (PSVAE_X_BF16) bf16
+static int set_x(StepArgs& a, const void* x, int32_t x_dtype) {
+  a.x = nullptr; a.x16 = nullptr;
+  if (x_dtype == PSVAE_X_F32) a.x = static_cast<const float*>(x);
+  else if (x_dtype == PSVAE_X_BF16) a.x16 = static_cast<const bf16*>(x);
+  else { set_error("unknown x_dtype %d", x_dtype); return -2; }
+  return 0;
+}
+
+int psvae_train_fwd_bwd(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const void* x, int32_t x_dtype, const int64_t* y,
                         const float* eps, uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, float kl_weight, float clf_weight,
                         int32_t use_cos_loss, int32_t compute_grads, int32_t precision, float* x_hat, float* mu, float* log_sigma, float* losses,
                         void* workspace, int64_t workspace_bytes, void* stream) {
   PSVAE_TRY(check_desc(desc, precision));
-  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, x, y, eps, seed, offset, row0, rows, kl_weight, clf_weight,
+  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, nullptr, y, eps, seed, offset, row0, rows, kl_weight, clf_weight,
              use_cos_loss ? 1 : 0, 1, compute_grads ? 1 : 0, x_hat, mu, log_sigma, losses, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)};
+  PSVAE_TRY(set_x(a, x, x_dtype));
   return precision == PSVAE_BF16 ? run_step<bf16>(a) : run_step<float>(a);
 }
 
@@ -1562,36 +1628,39 @@ int psvae_consistency_forward(const psvae_consistency_desc* cons, const float* c
   return cons_forward(cons, cons_params, x, rows, w, logits, static_cast<cudaStream_t>(stream));
 }
 
-int psvae_train_fwd_bwd_consistency(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const float* x,
+int psvae_train_fwd_bwd_consistency(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const void* x, int32_t x_dtype,
                                     const int64_t* y, const float* eps, uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, float kl_weight,
                                     float clf_weight, int32_t use_cos_loss, int32_t compute_grads, int32_t precision, float* x_hat, float* mu,
                                     float* log_sigma, float* losses, void* workspace, int64_t workspace_bytes, void* stream,
                                     const psvae_consistency_desc* cons, const float* cons_params, const int64_t* cons_y, float cons_weight) {
   PSVAE_TRY(check_desc(desc, precision));
   if (!cons) { set_error("consistency desc is NULL (use psvae_train_fwd_bwd for a step without the consistency term)"); return -1; }
-  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, x, y, eps, seed, offset, row0, rows, kl_weight, clf_weight,
+  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, nullptr, y, eps, seed, offset, row0, rows, kl_weight, clf_weight,
              use_cos_loss ? 1 : 0, 1, compute_grads ? 1 : 0, x_hat, mu, log_sigma, losses, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)};
+  PSVAE_TRY(set_x(a, x, x_dtype));
   a.cons = cons; a.cons_params = cons_params; a.cons_y = cons_y; a.cons_w = cons_weight;
   return precision == PSVAE_BF16 ? run_step<bf16>(a) : run_step<float>(a);
 }
 
-int psvae_vae_backward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const float* x, const float* eps,
+int psvae_vae_backward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const void* x, int32_t x_dtype, const float* eps,
                        uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, int32_t precision, const float* g_x_hat, const float* g_mu,
                        const float* g_log_sigma, void* workspace, int64_t workspace_bytes, void* stream) {
   PSVAE_TRY(check_desc(desc, precision));
-  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, x, nullptr, eps, seed, offset, row0, rows, 0.f, 0.f,
+  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), grads, nullptr, nullptr, eps, seed, offset, row0, rows, 0.f, 0.f,
              0, 0, 1, nullptr, nullptr, nullptr, nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)};
+  PSVAE_TRY(set_x(a, x, x_dtype));
   a.ext = 1; a.ext_gx = g_x_hat; a.ext_gmu = g_mu; a.ext_gls = g_log_sigma;
   return precision == PSVAE_BF16 ? run_step<bf16>(a) : run_step<float>(a);
 }
 
-int psvae_forward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, const float* x, const float* eps, uint64_t seed,
+int psvae_forward(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, const void* x, int32_t x_dtype, const float* eps, uint64_t seed,
                   uint64_t offset, int64_t row0, int64_t rows, int32_t precision, float* x_hat, float* mu, float* log_sigma, void* workspace,
                   int64_t workspace_bytes, void* stream) {
   PSVAE_TRY(check_desc(desc, precision));
   if (!x_hat) { set_error("x_hat must not be NULL"); return -1; }
-  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), nullptr, x, nullptr, eps, seed, offset, row0, rows, 0.f, 0.f,
+  StepArgs a{desc, params, static_cast<const bf16*>(shadow_bf16), nullptr, nullptr, nullptr, eps, seed, offset, row0, rows, 0.f, 0.f,
              0, 0, 0, x_hat, mu, log_sigma, nullptr, workspace, workspace_bytes, static_cast<cudaStream_t>(stream)};
+  PSVAE_TRY(set_x(a, x, x_dtype));
   return precision == PSVAE_BF16 ? run_step<bf16>(a) : run_step<float>(a);
 }
 

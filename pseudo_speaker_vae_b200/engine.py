@@ -11,7 +11,9 @@ the Adam update and the data-parallel all-reduce each become one pass over one b
 """
 from __future__ import annotations
 
+import copy
 import ctypes as C
+import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
@@ -27,6 +29,21 @@ def _stream_ptr(device: torch.device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
+def _on(device: torch.device):
+    """Device guard for a library call: the library launches on the CURRENT device (cudaGetDevice), so a module on cuda:1 must make
+    cuda:1 current for the duration of the call whatever the caller's current device is."""
+    return torch.cuda.device(device)
+
+
+class _Token:
+    """Marks a staging buffer as owned by a loss whose backward has not run yet (weakly held by the arena)."""
+
+    __slots__ = ("buf", "__weakref__")
+
+    def __init__(self, buf: torch.Tensor):
+        self.buf = buf
+
+
 class ParamArena:
     """One flat fp32 buffer holding every parameter; the modules' ``nn.Parameter``s are views into it."""
 
@@ -35,7 +52,8 @@ class ParamArena:
         self.entries: List[Tuple[nn.Parameter, int]] = list(entries)
         self.numel = int(desc.total_numel)
         self.flat: Optional[torch.Tensor] = None
-        self._gbuf: List[Optional[torch.Tensor]] = [None, None]   # two gradient buffers (see stage_buffer)
+        self._gbuf: List[torch.Tensor] = []                      # gradient staging buffers (see stage_buffer); two in steady state
+        self._inflight: "weakref.WeakSet[_Token]" = weakref.WeakSet()
         self.shadow: Optional[torch.Tensor] = None               # bf16 operand copy for the tcgen05 engine
         self._shadow_versions: Optional[Tuple[int, ...]] = None
         self._shadow_epoch = -1
@@ -51,9 +69,20 @@ class ParamArena:
                 flat[off:off + n].copy_(p.detach().reshape(-1).to(device=device, dtype=torch.float32))
                 p.data = flat[off:off + n].view(p.shape)
         self.flat = flat
-        self._gbuf = [None, None]
+        self._gbuf = []
         self.shadow = None
         self._shadow_versions = None
+
+    # transient state (staging buffers, the bf16 operand copy, ownership tokens) is per instance and rebuilt on demand: it is neither
+    # pickled (torch.save(module)) nor deep-copied (SWA / EMA callbacks, ddp_spawn)
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.update(_gbuf=[], _inflight=None, shadow=None, _shadow_versions=None, _shadow_epoch=-1)
+        return st
+
+    def __setstate__(self, st):
+        self.__dict__.update(st)
+        self._inflight = weakref.WeakSet()
 
     def attached(self) -> bool:
         base = self.flat.data_ptr()
@@ -78,20 +107,25 @@ class ParamArena:
 
     # ---- gradients ------------------------------------------------------------------------------
     def stage_buffer(self) -> torch.Tensor:
-        """A flat gradient buffer no live ``p.grad`` aliases (gradient accumulation keeps the other one alive)."""
+        """A flat gradient buffer that no live ``p.grad`` aliases (gradient accumulation keeps that one alive) and that no
+        loss whose ``backward()`` is still to come owns (two ``training_step`` calls before one backward each get their own)."""
         dev = self.flat.device
-        live = None
-        for p, _ in self.entries:
-            if p.grad is not None:
-                live = p.grad.data_ptr()
-                break
-        for i in range(2):
-            g = self._gbuf[i]
-            if g is None or g.device != dev:
-                g = self._gbuf[i] = torch.zeros(self.numel, dtype=torch.float32, device=dev)
-            if live is None or not (g.data_ptr() <= live < g.data_ptr() + 4 * self.numel):
-                return g
-        raise RuntimeError("both gradient buffers are aliased by live .grad tensors")
+        self._gbuf = [g for g in self._gbuf if g.device == dev]
+        live = {p.grad.data_ptr() for p, _ in self.entries if p.grad is not None}
+        busy = [t.buf for t in self._inflight]
+        for g in self._gbuf:
+            lo, hi = g.data_ptr(), g.data_ptr() + 4 * self.numel
+            if any(lo <= q < hi for q in live) or any(b is g for b in busy):
+                continue
+            return g
+        g = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        self._gbuf.append(g)
+        return g
+
+    def own(self, gflat: torch.Tensor) -> _Token:
+        tok = _Token(gflat)
+        self._inflight.add(tok)
+        return tok
 
     def grad_views(self, gflat: torch.Tensor) -> List[torch.Tensor]:
         return [gflat[off:off + p.numel()].view(p.shape) for p, off in self.entries]
@@ -99,8 +133,6 @@ class ParamArena:
     def flat_grad(self) -> Optional[torch.Tensor]:
         """The flat buffer the current ``.grad`` tensors live in (None if they do not all alias one buffer)."""
         for g in self._gbuf:
-            if g is None:
-                continue
             base = g.data_ptr()
             ok = True
             for p, off in self.entries:
@@ -118,8 +150,9 @@ class ParamArena:
         if self.shadow is None or self.shadow.device != self.flat.device or versions != self._shadow_versions or self._shadow_epoch != self.epoch:
             if self.shadow is None or self.shadow.device != self.flat.device:
                 self.shadow = torch.empty(self.numel, dtype=torch.bfloat16, device=self.flat.device)
-            L.check(L.lib().psvae_refresh_shadow(desc_ref, self.flat.data_ptr(), self.shadow.data_ptr(), _stream_ptr(self.flat.device)),
-                    "psvae_refresh_shadow")
+            with _on(self.flat.device):
+                L.check(L.lib().psvae_refresh_shadow(desc_ref, self.flat.data_ptr(), self.shadow.data_ptr(), _stream_ptr(self.flat.device)),
+                        "psvae_refresh_shadow")
             self._shadow_versions = versions
             self._shadow_epoch = self.epoch
         return self.shadow.data_ptr()
@@ -137,15 +170,24 @@ class _FusedLoss(torch.autograd.Function):
     def forward(ctx, loss_value: torch.Tensor, gflat: torch.Tensor, arena: ParamArena, *params):
         ctx.arena = arena
         ctx.gflat = gflat
+        ctx.token = arena.own(gflat)      # the staging buffer is this loss's until its backward has run (or the loss is dropped)
         ctx.needs = [p.requires_grad for p in params]
         return loss_value.clone()
 
     @staticmethod
     def backward(ctx, gout):
         g = ctx.gflat
+        if g is None:
+            raise RuntimeError("the fused gradients of this loss were already handed to autograd (backward through the same training_step "
+                               "output twice); call training_step again")
+        ctx.gflat = ctx.token = None
         g.mul_(gout)     # d(total)/d(loss); a ones tensor for a plain loss.backward()
         views = ctx.arena.grad_views(g)   # fresh views: AccumulateGrad adopts them without a copy
         return (None, None, None) + tuple(v if need else None for v, need in zip(views, ctx.needs))
+
+
+def _xflag(x: torch.Tensor) -> int:
+    return L.X_BF16 if x.dtype == torch.bfloat16 else L.X_F32
 
 
 class _VAEForward(torch.autograd.Function):
@@ -169,9 +211,10 @@ class _VAEForward(torch.autograd.Function):
         B = x.shape[0]
         gflat = torch.empty(hot.arena.numel, dtype=torch.float32, device=dev)        # a buffer of its own: autograd adopts / accumulates the views
         gs = [None if g is None else g.detach().to(torch.float32).contiguous() for g in (g_xhat, g_mu, g_ls)]
-        ws = hot._workspace(dev, B, L.MODE_TRAIN)
-        rc = L.lib().psvae_vae_backward(hot._dref, flat.data_ptr(), hot._shadow(), gflat.data_ptr(), x.data_ptr(), L.ptr(eps), seed, off, row0, B,
-                                        hot.precision, L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(gs[2]), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        with _on(dev):
+            ws = hot._workspace(dev, B, L.MODE_TRAIN)
+            rc = L.lib().psvae_vae_backward(hot._dref, flat.data_ptr(), hot._shadow(), gflat.data_ptr(), x.data_ptr(), _xflag(x), L.ptr(eps), seed, off,
+                                            row0, B, hot.precision, L.ptr(gs[0]), L.ptr(gs[1]), L.ptr(gs[2]), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
         L.check(rc, "psvae_vae_backward")
         views = [gflat[o:o + p.numel()].view(p.shape) for p, o in hot.vae_entries()]
         return (None, None, None) + tuple(v if need else None for v, need in zip(views, ctx.needs))
@@ -198,7 +241,6 @@ class HotPath:
                 raise ValueError(f"classifier input_dim={classifier.input_dim} must equal the VAE latent_dim={vae.latent_dim}")
         self.desc = L.make_desc(vae.input_dim, vae.latent_dim, vae.hidden_dim, vae.num_hidden_layers, vae.normalize_decoder,
                                 n_trunk, c_hidden, act, heads, single)
-        self._dref = C.byref(self.desc)
         self.arena = ParamArena(self.desc, self._entries())
         self._ws: Dict[torch.device, torch.Tensor] = {}
         self._losses: Dict[torch.device, torch.Tensor] = {}
@@ -209,7 +251,37 @@ class HotPath:
         self.flops_forward = int(L.lib().psvae_flops_per_sample(self._dref, 1))
         self.flops_decode = int(L.lib().psvae_flops_per_sample(self._dref, 2))
 
+    # ---- copies ---------------------------------------------------------------------------------
+    def __deepcopy__(self, memo):
+        """A copy of the owning module gets a HotPath of its own around the COPIED sub-modules: fresh arena (nn.Parameter copies are
+        clones, not views), no shared scratch."""
+        new = object.__new__(HotPath)
+        memo[id(self)] = new
+        # the sub-modules may still be under construction at this point (the module being copied reaches its HotPath through its own
+        # attributes): the arena is laid out on first use instead (__getattr__)
+        new.__dict__["_pending"] = (copy.deepcopy(self.vae, memo), copy.deepcopy(self.classifier, memo), self.precision_name, self.seed, self.offset, self.row0)
+        return new
+
+    def __getattr__(self, name):          # reached only when normal lookup fails: a deep copy that has not been laid out yet
+        pend = self.__dict__.get("_pending")
+        if pend is None or name.startswith("__"):
+            raise AttributeError(name)
+        del self.__dict__["_pending"]
+        self.__init__(*pend[:3])
+        self.seed, self.offset, self.row0 = pend[3:]
+        return getattr(self, name)
+
+    def __getstate__(self):
+        st = dict(self.__dict__)
+        st.update(_ws={}, _losses={})
+        return st
+
     # ---- plumbing -------------------------------------------------------------------------------
+    @property
+    def _dref(self):
+        """byref of the model description, built per call (a cached ctypes CArgObject would make the owning module un-copyable / un-picklable)."""
+        return C.byref(self.desc)
+
     def set_precision(self, precision: str) -> None:
         key = str(precision).lower()
         if key not in PRECISIONS:
@@ -272,6 +344,15 @@ class HotPath:
             raise ValueError(f"{what} is on {t.device}, the model on {dev}")
         return t.detach().to(torch.float32).contiguous()
 
+    def _x_in(self, x: torch.Tensor, dev: torch.device, plain_tail: bool = True) -> torch.Tensor:
+        """The input batch as the library takes it: fp32, or -- tensor-core mode with the plain MSE tail -- bf16 as it is (a batch from a
+        bf16 embedding store: no cast pass on the device, half the H2D bytes; the bf16 values are the data)."""
+        if x.device != dev:
+            raise ValueError(f"x is on {x.device}, the model on {dev}")
+        if x.dtype == torch.bfloat16 and self.precision == L.BF16 and plain_tail:
+            return x.detach().contiguous()
+        return x.detach().to(torch.float32).contiguous()
+
     # ---- VAEModel.forward (ps_vae/model.py:38-63) -------------------------------------------------
     def vae_entries(self) -> List[Tuple[nn.Parameter, int]]:
         """(parameter, arena offset) of the VAE's own parameters (the classifier's follow them in the arena)."""
@@ -294,7 +375,7 @@ class HotPath:
         flat = self.arena.ensure()
         if x.dim() != 2 or x.shape[1] != self.desc.input_dim:
             raise ValueError(f"x must be [batch, {self.desc.input_dim}], got {tuple(x.shape)}")
-        x = self._f32(x, dev, "x")
+        x = self._x_in(x, dev)
         B = x.shape[0]
         D, Lz = self.desc.input_dim, self.desc.latent_dim
         x_hat = torch.empty(B, D, dtype=torch.float32, device=dev)
@@ -309,9 +390,10 @@ class HotPath:
             seed, off = 0, 0
         else:
             seed, off = self._rng()
-        ws = self._workspace(dev, B, L.MODE_FORWARD)
-        rc = L.lib().psvae_forward(self._dref, flat.data_ptr(), self._shadow(), x.data_ptr(), L.ptr(eps), seed, off, self.row0, B, self.precision,
-                                   x_hat.data_ptr(), mu.data_ptr(), ls.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+        with _on(dev):
+            ws = self._workspace(dev, B, L.MODE_FORWARD)
+            rc = L.lib().psvae_forward(self._dref, flat.data_ptr(), self._shadow(), x.data_ptr(), _xflag(x), L.ptr(eps), seed, off, self.row0, B,
+                                       self.precision, x_hat.data_ptr(), mu.data_ptr(), ls.data_ptr(), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
         L.check(rc, "psvae_forward")
         return x_hat, mu, ls, (x, eps, seed, off, self.row0)      # what the backward pass needs to redo this exact forward
 
@@ -336,9 +418,10 @@ class HotPath:
             raise ValueError(f"out must be a contiguous float32 [{N}, {D}] tensor on {dev}")
         z_out = torch.empty(N, Lz, dtype=torch.float32, device=dev) if (return_z and z is None) else None
         if N > 0:
-            ws = self._workspace(dev, N, L.MODE_DECODE)
-            rc = L.lib().psvae_decode(self._dref, flat.data_ptr(), self._shadow(), L.ptr(z), seed, off, self.row0 if row0 is None else row0, N,
-                                      self.precision, out.data_ptr(), L.ptr(z_out), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            with _on(dev):
+                ws = self._workspace(dev, N, L.MODE_DECODE)
+                rc = L.lib().psvae_decode(self._dref, flat.data_ptr(), self._shadow(), L.ptr(z), seed, off, self.row0 if row0 is None else row0, N,
+                                          self.precision, out.data_ptr(), L.ptr(z_out), ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             L.check(rc, "psvae_decode")
         if return_z:
             return out, (z if z is not None else z_out)
@@ -374,7 +457,7 @@ class HotPath:
         D, Lz = self.desc.input_dim, self.desc.latent_dim
         if x.dim() != 2 or x.shape[1] != D:
             raise ValueError(f"x must be [batch, {D}], got {tuple(x.shape)}")
-        x = self._f32(x, dev, "x")
+        x = self._x_in(x, dev, plain_tail=not (self.desc.normalize_decoder or use_cos_loss or consistency is not None))
         B = x.shape[0]
         if B == 0:
             raise ValueError("empty batch")
@@ -397,12 +480,13 @@ class HotPath:
             ls = torch.empty(B, Lz, dtype=torch.float32, device=dev)
             outs = (xh, mu, ls)
         mode = L.MODE_TRAIN if compute_grads else L.MODE_FORWARD
-        args = (self._dref, flat.data_ptr(), self._shadow(), L.ptr(grads) if compute_grads else None, x.data_ptr(), L.ptr(yy),
+        args = (self._dref, flat.data_ptr(), self._shadow(), L.ptr(grads) if compute_grads else None, x.data_ptr(), _xflag(x), L.ptr(yy),
                 L.ptr(eps), seed, off, self.row0, B, float(kl_weight), float(clf_weight), int(bool(use_cos_loss)),
                 int(bool(compute_grads)), self.precision, L.ptr(xh), L.ptr(mu), L.ptr(ls), losses.data_ptr())
         if consistency is None:
-            ws = self._workspace(dev, B, mode)
-            rc = L.lib().psvae_train_fwd_bwd(*args, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
+            with _on(dev):
+                ws = self._workspace(dev, B, mode)
+                rc = L.lib().psvae_train_fwd_bwd(*args, ws.data_ptr(), ws.numel(), _stream_ptr(dev))
             L.check(rc, "psvae_train_fwd_bwd")
         else:
             if consistency.input_dim != D:
@@ -416,9 +500,10 @@ class HotPath:
             extra = int(L.lib().psvae_consistency_workspace_bytes(C.byref(cdesc), B, mode))
             if extra < 0:
                 raise ValueError(L.last_error())
-            ws = self._workspace(dev, B, mode, extra)
-            rc = L.lib().psvae_train_fwd_bwd_consistency(*args, ws.data_ptr(), ws.numel(), _stream_ptr(dev), C.byref(cdesc), cflat.data_ptr(),
-                                                         cy.data_ptr(), float(consistency_weight))
+            with _on(dev):
+                ws = self._workspace(dev, B, mode, extra)
+                rc = L.lib().psvae_train_fwd_bwd_consistency(*args, ws.data_ptr(), ws.numel(), _stream_ptr(dev), C.byref(cdesc), cflat.data_ptr(),
+                                                             cy.data_ptr(), float(consistency_weight))
             L.check(rc, "psvae_train_fwd_bwd_consistency")
         return losses, (grads if compute_grads else None), outs
 
@@ -482,9 +567,10 @@ class HotPath:
         hist = torch.empty(num_steps, N, Lz, dtype=torch.float32, device=dev) if return_history else None
         stats = torch.empty(num_steps, 2, dtype=torch.float32, device=dev) if return_stats else None
         if N > 0:
-            rc = L.lib().psvae_langevin(self._dref, flat.data_ptr(), z.data_ptr(), N, tarr, float(step_size), int(num_steps), float(noise_weight),
-                                        self.seed, off0, self.row0 if row0 is None else row0, init, L.ptr(noise), L.ptr(hist), L.ptr(stats),
-                                        _stream_ptr(dev))
+            with _on(dev):
+                rc = L.lib().psvae_langevin(self._dref, flat.data_ptr(), z.data_ptr(), N, tarr, float(step_size), int(num_steps), float(noise_weight),
+                                            self.seed, off0, self.row0 if row0 is None else row0, init, L.ptr(noise), L.ptr(hist), L.ptr(stats),
+                                            _stream_ptr(dev))
             L.check(rc, "psvae_langevin")
         if stats is not None and N > 0:
             stats = stats / N

@@ -17,7 +17,7 @@ from typing import Iterable, List, Optional, Tuple
 import torch
 
 from . import _lib as L
-from .engine import ParamArena, _stream_ptr
+from .engine import ParamArena, _on, _stream_ptr
 
 
 class FusedAdam(torch.optim.Optimizer):
@@ -89,12 +89,13 @@ class FusedAdam(torch.optim.Optimizer):
             self._bind_state()
 
     # ---- ranges -----------------------------------------------------------------------------------
-    @staticmethod
-    def _ranges(spans: List[Tuple[int, int]]) -> List[Tuple[int, int]]:
-        """Merge [offset, end) spans whose gap is arena padding (< 64 elements, zero-valued, zero-gradient)."""
+    def _ranges(self, spans: List[Tuple[int, int]]) -> List[Tuple[int, int]]:
+        """Merge [offset, end) spans whose gap holds nothing but arena padding (zero-valued, zero-gradient).  A gap in which a
+        parameter lives that is NOT being updated (frozen, or without a gradient this step) is never bridged."""
+        owned = sorted(off for _, off in self.arena.entries)
         out: List[List[int]] = []
         for a, b in sorted(spans):
-            if out and a - out[-1][1] < 64:
+            if out and a - out[-1][1] < 64 and not any(out[-1][1] <= o < a for o in owned):
                 out[-1][1] = max(out[-1][1], b)
             else:
                 out.append([a, b])
@@ -122,6 +123,7 @@ class FusedAdam(torch.optim.Optimizer):
             if gflat is None:
                 # gradients were produced outside the fused step (plain autograd on a caller's own loss): gather them
                 gflat = self.arena.stage_buffer()
+                gflat.zero_()          # padding between merged spans must read as zero gradient
                 for p in with_grad:
                     off = self._offsets[id(p)]
                     gflat[off:off + p.numel()].copy_(p.grad.reshape(-1))
@@ -133,9 +135,10 @@ class FusedAdam(torch.optim.Optimizer):
                 shadow = None
                 if self.arena.shadow is not None and self.arena.shadow.device == dev:
                     shadow = self.arena.shadow.data_ptr() + 2 * a
-                rc = lib.psvae_adam_step(flat.data_ptr() + 4 * a, gflat.data_ptr() + 4 * a, m.data_ptr() + 4 * a, v.data_ptr() + 4 * a, b - a,
-                                         float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
-                                         step, float(self.grad_scale), shadow, stream)
+                with _on(dev):
+                    rc = lib.psvae_adam_step(flat.data_ptr() + 4 * a, gflat.data_ptr() + 4 * a, m.data_ptr() + 4 * a, v.data_ptr() + 4 * a, b - a,
+                                             float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
+                                             step, float(self.grad_scale), shadow, stream)
                 L.check(rc, "psvae_adam_step")
                 touched = True
             step_t += 1

@@ -72,17 +72,21 @@ class DataParallelTrainer:
     """The per-batch body of the reference's fit loop as three device-side calls:
     fused fwd+bwd  ->  bucketed all-reduce  ->  fused Adam.  Nothing in ``train_step`` synchronises with the host."""
 
-    def __init__(self, module, optimizer=None, bucket_bytes: int = DEFAULT_BUCKET_BYTES, group=None):
+    def __init__(self, module, optimizer=None, bucket_bytes: int = DEFAULT_BUCKET_BYTES, group=None, local_only: bool = False):
+        """``local_only``: a trainer that never talks to the other ranks even inside an initialised process group (the single-process
+        twin ``verify_data_parallel_step`` compares the data-parallel run with)."""
         self.module = module
         self.hot = module.hot_path
         self.group = group
-        self.rank, self.world_size = world()
+        self.local_only = bool(local_only)
+        self.rank, self.world_size = (0, 1) if self.local_only else world()
         self.bucket_bytes = bucket_bytes
         if optimizer is None:
             optimizer = module.configure_optimizers()["optimizer"]
         self.optimizer = optimizer
         self.optimizer.grad_scale = 1.0 / self.world_size
-        broadcast_parameters(self.hot.arena.ensure(), 0, group)
+        if not self.local_only:
+            broadcast_parameters(self.hot.arena.ensure(), 0, group)
         self.hot.arena.epoch += 1          # the bf16 operand copy must follow the broadcast values
         self._views = None
         self._views_of = None
@@ -101,10 +105,70 @@ class DataParallelTrainer:
                                     clf_weight=m.classifier_loss_weight, use_cos_loss=m.use_cos_loss, compute_grads=True, grads=gflat,
                                     consistency=cons, consistency_y=y_local if cons is not None else None,
                                     consistency_weight=m.consitency_loss_weight)
-        all_reduce_flat(gflat, self.bucket_bytes, self.group)
+        if not self.local_only:
+            all_reduce_flat(gflat, self.bucket_bytes, self.group)
         if self._views_of is not gflat:        # bind .grad views once; the same flat buffer is reused every step
             for (p, _), v in zip(hot.arena.entries, hot.arena.grad_views(gflat)):
                 p.grad = v if p.requires_grad else None
             self._views_of = gflat
         self.optimizer.step()
         return losses
+
+
+def verify_data_parallel_step(device, steps: int = 3, global_batch: int = 8192, input_dim: int = 256, latent_dim: int = 64, num_classes: int = 2,
+                              precision: str = "fp32", seed: int = 4321, group=None) -> dict:
+    """Numerical self-check of the data-parallel path on the ranks that are actually running (what ``DDPStrategy`` guarantees for the
+    reference, ps_vae/training.py:78): ``steps`` optimiser steps through ``DataParallelTrainer`` on this rank's shard of a seeded global
+    batch with injected eps, then
+
+      * every rank must hold BIT-identical parameters (all-gather of the flat buffer's checksum and of a strided sample), and
+      * they must equal a single-process run on the whole global batch from the same initial parameters
+        (``||p_dp - p_1|| / ||p_1||`` over the flat parameter buffer; gradients of the last step likewise).
+
+    Runs in the deterministic summation mode (ordered split-K / bias sums) so that the only difference between the two runs is the
+    grouping of fp32 partial sums.  Collective: call on every rank.  Returns the measured errors (rank 0 decides what to do with them)."""
+    from . import _lib as L
+    from .lightning import PseudoSpeakerVAE
+
+    rank, ws = world()
+    dev = torch.device(device)
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(steps, global_batch, input_dim, generator=g)
+    x = x / x.norm(dim=2, keepdim=True)
+    y = torch.randint(0, num_classes, (steps, global_batch), generator=g)
+    eps = torch.randn(steps, global_batch, latent_dim, generator=g)
+    hp = dict(model=dict(input_dim=input_dim, latent_dim=latent_dim), classifier=dict(input_dim=latent_dim, num_classes=num_classes),
+              optimizer=dict(lr=1e-3), scheduler=dict(T_max=200), precision=precision)
+    prev = L.get_option("deterministic")
+    L.set_option("deterministic", 1)
+    try:
+        torch.manual_seed(seed)                     # same initial weights on every rank and in the single-process twin
+        dp = PseudoSpeakerVAE(**hp).to(dev)
+        torch.manual_seed(seed)
+        one = PseudoSpeakerVAE(**hp).to(dev)
+        tr = DataParallelTrainer(dp, group=group)
+        row0, rows = tr.set_shard(global_batch)
+        solo = DataParallelTrainer(one, local_only=True)           # the twin: same three device-side calls, world of one, no collective
+        for s in range(steps):
+            xs, ys, es = (t[s].to(dev) for t in (x, y, eps))
+            tr.train_step(xs[row0:row0 + rows], ys[row0:row0 + rows], es[row0:row0 + rows])
+            solo.hot.row0 = 0
+            solo.train_step(xs, ys, es)
+        p_dp = dp.hot_path.arena.flat.detach().double()
+        p_1 = one.hot_path.arena.flat.detach().double()
+        g_dp = dp.hot_path.arena.flat_grad().detach().double() / ws       # the all-reduced SUM over ranks
+        g_1 = one.hot_path.arena.flat_grad().detach().double()
+        out = dict(world_size=ws, steps=steps, global_batch=global_batch, precision=precision,
+                   param_rel_err=float((p_dp - p_1).norm() / p_1.norm()), grad_rel_err=float((g_dp - g_1).norm() / g_1.norm()),
+                   param_max_abs=float((p_dp - p_1).abs().max()))
+        flat32 = dp.hot_path.arena.flat.detach()
+        sig = torch.cat([flat32.view(torch.int32).sum(dtype=torch.int64).reshape(1), flat32.view(torch.int32)[::997].to(torch.int64)])
+        if ws > 1:
+            sigs = [torch.empty_like(sig) for _ in range(ws)]
+            dist.all_gather(sigs, sig, group=group)
+            out["ranks_identical"] = bool(all(torch.equal(s, sigs[0]) for s in sigs))
+        else:
+            out["ranks_identical"] = True
+        return out
+    finally:
+        L.set_option("deterministic", prev)
