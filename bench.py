@@ -477,42 +477,50 @@ def main():
         tmp = tempfile.mkdtemp(prefix=f"psvae_bench_r{rank}_")
         store = PD.PackedEmbeddingStore.from_arrays(tmp, np.concatenate(xs_np), np.concatenate(ys_np), ["gender"], dtype=x_dtype if args.precision == "bf16" else "f32")
 
-        def e2e_steps(n, loader):
+        def e2e_steps(n, loader, lightning):
             done = 0
             while done < n:
                 for x, y in loader:
-                    opt.zero_grad()
-                    loss = module.training_step((x, y), done)["loss"]
-                    loss.backward()
-                    if dist_on:
-                        P.parallel.all_reduce_flat(hot.arena.flat_grad())
-                    opt.step()
-                    loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+                    if lightning:          # what Lightning's automatic optimisation runs per batch
+                        opt.zero_grad()
+                        loss = module.training_step((x, y), done)["loss"]
+                        loss.backward()
+                        if dist_on:
+                            P.parallel.all_reduce_flat(hot.arena.flat_grad())
+                        opt.step()
+                        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+                    else:                  # the repo's own fit-loop body: fused step -> all-reduce -> fused Adam, three device-side calls
+                        losses = trainer.train_step(x, y)
+                        loss_host.copy_(losses[:1], non_blocking=True)
                     done += 1
                     if done >= n:
                         break
             torch.cuda.current_stream().synchronize()
 
         Ke = max(5, min(K, 100))
-        for name, resident in (("e2e", False), ("e2e_resident_store", True)):
+        legs = (("e2e", False, False), ("e2e_resident_store", True, False), ("e2e_lightning_api", False, True))
+        for name, resident, lightning in legs:
             try:
                 if not resident:
                     store.pin()
                 loader = PD.PinnedBatchLoader(store, B, device=dev, shuffle=resident, seed=3, resident=resident)
-                e2e_steps(2 * NB + 2, loader)       # touch every pinned page and let the copy path warm up (the first H2D copies of a process are slow)
-                ms_e = time_events(lambda: e2e_steps(Ke, loader), torch, dist_on)
+                e2e_steps(2 * NB + 2, loader, lightning)       # touch every pinned page and let the copy path warm up (the first H2D copies of a process are slow)
+                ms_e = time_events(lambda: e2e_steps(Ke, loader, lightning), torch, dist_on)
                 rec = dict(value=B * n_gpus * Ke / (ms_e * 1e-3), unit=UNIT, h2d_bytes_per_step=int(loader.h2d_bytes_per_batch), d2h_bytes_per_step=4,
                            ms_per_step=ms_e / Ke)
-                if resident:
-                    rec["api"] = ("PinnedBatchLoader(resident=True): the packed store lives in HBM (uploaded once), each step's shuffled index list is copied "
-                                  "from pinned host memory and the batch is assembled on the device (psvae_gather_rows) -> training_step -> backward -> FusedAdam.step()")
-                    sec[name] = rec
-                else:
-                    rec["api"] = (f"PinnedBatchLoader over a pinned {x_dtype} PackedEmbeddingStore (every step's batch DMA'd from pinned host memory on a copy stream, "
-                                  "one batch ahead) -> PseudoSpeakerVAE.training_step -> loss.backward() -> FusedAdam.step(), loss read back to the host")
+                src = (f"PinnedBatchLoader over a pinned {x_dtype} PackedEmbeddingStore (every step's batch DMA'd from pinned host memory on a copy stream, one batch ahead)"
+                       if not resident else
+                       "PinnedBatchLoader(resident=True): the packed store lives in HBM (uploaded once), each step's shuffled index list is copied from pinned host "
+                       "memory and the batch is assembled on the device (psvae_gather_rows)")
+                body = ("PseudoSpeakerVAE.training_step -> loss.backward() -> FusedAdam.step() (the calls Lightning's fit loop makes)" if lightning else
+                        "DataParallelTrainer.train_step (fused fwd+bwd -> gradient all-reduce -> FusedAdam)")
+                rec["api"] = f"{src} -> {body}, loss read back to the host every step"
+                if name == "e2e":
                     line[name] = rec
+                else:
+                    sec[name] = rec
             except Exception as e:  # noqa: BLE001
-                (sec if resident else line)[name] = dict(value=None, unit=UNIT, error=repr(e), h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+                (line if name == "e2e" else sec)[name] = dict(value=None, unit=UNIT, error=repr(e), h2d_bytes_per_step=0, d2h_bytes_per_step=0)
         del store
 
         # ---- secondary: sampling (BASELINE configs[3]: 100 M embeddings over 8 GPUs = 12.5 M per GPU, fp32 [N,256] left in a 12.8 GB buffer) ----

@@ -197,6 +197,15 @@ int64_t psvae_consistency_workspace_bytes(const psvae_consistency_desc* cons, in
  * the CUDA cores.  workspace >= psvae_consistency_workspace_bytes(cons, rows, PSVAE_MODE_FORWARD). */
 int psvae_consistency_forward(const psvae_consistency_desc* cons, const float* cons_params, const float* x, int64_t rows,
                               float* logits, void* workspace, int64_t workspace_bytes, void* stream);
+/* The stand-alone trainer of the same classifier (embedding_classifier.py:64-100: training_step / validation_step): logits,
+ * CrossEntropyLoss (mean) and multiclass accuracy, and -- compute_grads != 0 -- the gradients of the six tensors in the layout of
+ * psvae_consistency_desc (written, not accumulated).  losses[0] = the cross entropy, losses[13] = the accuracy (losses has
+ * PSVAE_NUM_LOSSES slots).  logits_out (optional) [rows][num_classes].  fp32 on the CUDA cores.
+ * workspace >= psvae_embedding_classifier_workspace_bytes(cons, rows).  A label outside [0, num_classes) gives a NaN loss. */
+int64_t psvae_embedding_classifier_workspace_bytes(const psvae_consistency_desc* cons, int64_t rows);
+int psvae_embedding_classifier_step(const psvae_consistency_desc* cons, const float* params, float* grads, const float* x,
+                                    const int64_t* y, int64_t rows, int32_t compute_grads, float* logits_out, float* losses,
+                                    void* workspace, int64_t workspace_bytes, void* stream);
 /* psvae_train_fwd_bwd plus  cons_weight * CE(consistency_classifier(x_hat), cons_y)  in the total loss; its gradient reaches the
  * decoder through x_hat (through the L2 normalisation when normalize_decoder is set).  cons_y: int64 [rows] (the single-label y of
  * the batch).  losses[PSVAE_LOSS_CONS], [PSVAE_LOSS_CONS_ACC] are filled.  workspace >= psvae_workspace_bytes(...) +
@@ -214,11 +223,17 @@ int psvae_train_fwd_bwd_consistency(const psvae_model_desc* desc, const float* p
  * offset `offset0`; step s uses offset `offset0 + 1 + s` unless `noise` ([num_steps][rows][L]) is given.
  * targets[h] = class index of head h, or -1 to leave head h out (a dict target naming only some labels).
  * history (optional) receives z after every step: [num_steps][rows][L].  stats (optional) [num_steps][2] =
- * mean log p(z|y), mean p(y|z) as printed by the reference's progress bar (inference.py:103). */
+ * mean log p(z|y), mean p(y|z) as printed by the reference's progress bar (inference.py:103).
+ * The variant of analysis/sample_gender_transformation.py:61-99 uses the same loop with three differences, all arguments here:
+ * prior_weight scales the log p(z) term (PRIOR_WEIGHT; 1 for inference.py), threshold > 0 stops a sample after the update of the
+ * first step whose p(y|z) exceeded it (THRESHOLD; 0 = never), and the start latent is the caller's (z_io = the encoder mean of a real
+ * embedding, init_from_philox = 0).  stop_step (optional, int32 [rows]) = that step, num_steps if the sample never stopped;
+ * last_prob (optional, [rows]) = p(y|z) of the sample's last evaluated step. */
 int psvae_langevin(const psvae_model_desc* desc, const float* params, float* z_io, int64_t rows,
                    const int32_t* targets_host, float step_size, int32_t num_steps, float noise_weight,
                    uint64_t seed, uint64_t offset0, int64_t row0, int32_t init_from_philox, const float* noise,
-                   float* history, float* stats, void* stream);
+                   float* history, float* stats, float prior_weight, float threshold, int32_t* stop_step, float* last_prob,
+                   void* stream);
 
 /* ---- building block exposed for tests and profiling: C = A[M,K] * B[N,K]^T (+bias) ------------- */
 /* a_mn / b_mn: operand stored MN-major (A as [K][M], B as [K][N]).  bf16 in, fp32 out, tcgen05. */

@@ -145,6 +145,96 @@ def sampling_case(ref, name, cfg):
     print("wrote", name, len(store))
 
 
+def transformation_case(ref, name, cfg):
+    """The Langevin variant of analysis/sample_gender_transformation.py:57-99, run per sample exactly as that script does (batch of one,
+    torch autograd through the reference's own modules): start from the encoded embedding (`_, z, _ = vae_model(embed)`: z = mu),
+    ascend log p(y|z) + PRIOR_WEIGHT * log p(z) with step 0.5 * STEP_SIZE^2, optional noise, stop after the update of the first step
+    whose p(y|z) exceeded THRESHOLD.  Stored: the inputs, the start latents, the final latents, the step at which each sample stopped
+    (max_steps if it never did) and the classifier probability of its last evaluated step."""
+    import torch.nn.functional as F
+
+    store = {"cfg": json.dumps(cfg)}
+    N, L, D = cfg["N"], cfg["L"], cfg["D"]
+    x, _, _ = O.synth_batch(N, D, L, 2, seed=cfg["dseed"])
+    rng = np.random.default_rng(cfg["dseed"] + 1)
+    noises = rng.standard_normal((cfg["max_steps"], N, L)).astype(np.float32)
+    store["x"] = x
+    store["noises"] = noises
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        vae_model = build_module(ref, cfg, dtype)
+        vae_model.eval()
+        z_start, z_final, stops, probs = [], [], [], []
+        for i in range(N):
+            emebd = torch.from_numpy(x[i]).to(dtype)
+            with torch.no_grad():
+                _, z, _ = vae_model(emebd.unsqueeze(0))
+                z.requires_grad_()
+            z_start.append(z.detach().numpy()[0].copy())
+            classifier_target = cfg["target"]
+            stop = cfg["max_steps"]
+            for step in range(cfg["max_steps"]):
+                logits = vae_model.classifier(z)
+                log_probs = F.log_softmax(logits, dim=-1)
+                log_p_y_given_z = log_probs[:, classifier_target]
+                log_p_z = -0.5 * (z ** 2).sum(dim=1)
+                log_p_z_given_y = log_p_y_given_z + cfg["prior_weight"] * log_p_z
+                grad = torch.autograd.grad(log_p_z_given_y.sum(), z)[0]
+                noise = torch.from_numpy(noises[step, i:i + 1]).to(dtype)
+                p_y_given_z = log_p_y_given_z.clone().exp()
+                z = z + 0.5 * (cfg["step_size"] ** 2) * grad + cfg["step_size"] * cfg["noise_weight"] * noise
+                z.requires_grad_()
+                if p_y_given_z.item() > cfg["threshold"]:
+                    stop = step
+                    break
+            z_final.append(z.detach().numpy()[0].copy())
+            stops.append(stop)
+            probs.append(float(p_y_given_z.item()))
+        store[f"{tag}/z_start"] = np.stack(z_start)
+        store[f"{tag}/z_final"] = np.stack(z_final)
+        store[f"{tag}/stop"] = np.array(stops, dtype=np.int64)
+        store[f"{tag}/prob"] = np.array(probs, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **store)
+    print("wrote", name, "stops", store["f64/stop"].tolist())
+
+
+def embedding_classifier_case(name, cfg):
+    """The stand-alone EmbeddingClassifier trainer (ps_vae/embedding_classifier/embedding_classifier.py:38-100): the unmodified module's
+    training_step -> backward -> its own configure_optimizers() Adam, a validation_step on the next batch; logits, logged metrics, every
+    gradient and the post-step parameters."""
+    import importlib
+
+    load_reference()
+    EC = importlib.import_module("ps_vae.embedding_classifier.embedding_classifier").EmbeddingClassifier
+    store = {"cfg": json.dumps(cfg)}
+    for dtype, tag in ((torch.float32, "f32"), (torch.float64, "f64")):
+        m = EC(cfg["D"], cfg["num_classes"], cfg["hidden_dim"], optimizer_cfg=dict(cfg["optimizer"]))
+        cp = O.synth_params(O.embedding_classifier_param_shapes(cfg["D"], cfg["num_classes"], cfg["hidden_dim"]), seed=cfg["wseed"], dtype=np.float64)
+        m.load_state_dict({k: torch.from_numpy(v.astype(np.float32)) for k, v in cp.items()})
+        m = m.to(dtype)
+        opt = m.configure_optimizers()
+        for s in range(cfg["steps"]):
+            x, y, _ = O.synth_batch(cfg["B"], cfg["D"], 64, cfg["num_classes"], seed=cfg["dseed"] + s)
+            xt, yt = torch.from_numpy(x).to(dtype), torch.from_numpy(y)
+            opt.zero_grad()
+            loss = m.training_step((xt, yt), s)
+            loss.backward()
+            st = f"{tag}/step{s}"
+            store[f"{st}/logits"] = m(xt).detach().numpy()
+            for k, v in m.logged.items():
+                store[f"{st}/log/{k}"] = float(v)
+            for pn, p in m.named_parameters():
+                store[f"{st}/grad/{pn}"] = p.grad.detach().numpy().copy()
+            opt.step()
+            for pn, p in m.named_parameters():
+                store[f"{st}/param/{pn}"] = p.detach().numpy().copy()
+        x, y, _ = O.synth_batch(cfg["B"], cfg["D"], 64, cfg["num_classes"], seed=cfg["dseed"] + 99)
+        m.validation_step((torch.from_numpy(x).to(dtype), torch.from_numpy(y)), 0)
+        for k in ("val_acc", "val_loss"):
+            store[f"{tag}/val/{k}"] = float(m.logged[k])
+    np.savez_compressed(os.path.join(OUT, f"{name}.npz"), **store)
+    print("wrote", name, len(store))
+
+
 def adam_case():
     store = {}
     rng = np.random.default_rng(77)
@@ -209,6 +299,17 @@ def main():
     torch.manual_seed(0)
     os.makedirs(OUT, exist_ok=True)
     ref = load_reference()
+    if "--only-embclf" in sys.argv:
+        embedding_classifier_case("embclf_d256_c3", dict(D=256, num_classes=3, hidden_dim=128, B=48, wseed=51, dseed=1300, steps=2,
+                                                          optimizer=dict(lr=2e-3, weight_decay=0.01)))
+        embedding_classifier_case("embclf_d192_c2", dict(D=192, num_classes=2, hidden_dim=64, B=33, wseed=52, dseed=1400, steps=2, optimizer=dict()))
+        return
+    if "--only-transform" in sys.argv:
+        transformation_case(ref, "transform_prior_threshold", dict(D=256, L=64, N=12, wseed=41, dseed=1100, max_steps=40, step_size=0.5, noise_weight=0.0,
+                                                                   prior_weight=0.5, threshold=0.64, target=1, clf=dict(input_dim=64, num_classes=2)))
+        transformation_case(ref, "transform_noise_c3", dict(D=192, L=64, N=10, wseed=42, dseed=1200, max_steps=30, step_size=0.9, noise_weight=0.2,
+                                                            prior_weight=0.25, threshold=0.5, target=2, clf=dict(input_dim=64, num_classes=3)))
+        return
     # consistency-classifier cases (lightning.py:44-52,100-108), added after the first fixture set: `--only-cons` writes just these
     train_case(ref, "train_d256_c2_cons", dict(D=256, L=64, B=24, wseed=15, dseed=910, steps=2, cons_w=0.7,
                                                clf=dict(input_dim=64, num_classes=2), cons=dict(num_classes=2, hidden_dim=128, wseed=31)))
@@ -217,6 +318,16 @@ def main():
                                                         cons=dict(num_classes=3, hidden_dim=64, wseed=32)))
     if "--only-cons" in sys.argv:
         return
+    # the analysis Langevin variant (analysis/sample_gender_transformation.py:57-99), added in round 2: `--only-transform` writes just these
+    transformation_case(ref, "transform_prior_threshold", dict(D=256, L=64, N=12, wseed=41, dseed=1100, max_steps=40, step_size=0.5, noise_weight=0.0,
+                                                               prior_weight=0.5, threshold=0.64, target=1, clf=dict(input_dim=64, num_classes=2)))
+    transformation_case(ref, "transform_noise_c3", dict(D=192, L=64, N=10, wseed=42, dseed=1200, max_steps=30, step_size=0.9, noise_weight=0.2,
+                                                        prior_weight=0.25, threshold=0.5, target=2, clf=dict(input_dim=64, num_classes=3)))
+    if "--only-transform" in sys.argv:
+        return
+    embedding_classifier_case("embclf_d256_c3", dict(D=256, num_classes=3, hidden_dim=128, B=48, wseed=51, dseed=1300, steps=2,
+                                                      optimizer=dict(lr=2e-3, weight_decay=0.01)))
+    embedding_classifier_case("embclf_d192_c2", dict(D=192, num_classes=2, hidden_dim=64, B=33, wseed=52, dseed=1400, steps=2, optimizer=dict()))
     train_case(ref, "train_d256_c2", dict(D=256, L=64, B=32, wseed=11, dseed=100, clf=dict(input_dim=64, num_classes=2)))
     train_case(ref, "train_d192_noclf", dict(D=192, L=64, B=16, wseed=12, dseed=200, kl_w=0.5, steps=2))
     train_case(ref, "train_d512_c3_mlp", dict(D=512, L=64, B=24, wseed=13, dseed=300, clf_w=2.0, steps=2,

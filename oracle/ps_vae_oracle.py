@@ -575,3 +575,53 @@ def synth_batch(B: int, D: int, L: int, num_classes=2, seed: int = 1234, dtype=n
         y = rng.choice(num_classes, size=B, p=probs.get(num_classes)).astype(np.int64)
     eps = rng.standard_normal((B, L))
     return x.astype(dtype), y, eps.astype(dtype)
+
+
+# --------------------------------------------------------------------------------------------
+# the analysis Langevin variant (analysis/sample_gender_transformation.py:57-99)
+# --------------------------------------------------------------------------------------------
+def latent_transformation(params: Params, z_start: np.ndarray, noises: Sequence[np.ndarray], target, step_size: float = 0.02, noise_weight: float = 0.0,
+                          prior_weight: float = 0.5, threshold: float = 0.95, activation: str = "relu"):
+    """Per-sample restatement of the script's loop, batched: every sample ascends log p(y|z) + prior_weight * log p(z) from its start latent
+    (the script starts from the encoder mean of a real embedding, :57-60) and stops after the update of the first step whose p(y|z)
+    exceeded ``threshold`` (:97-98).  Returns (z_final [N,L], stop_step [N] (len(noises) if never), last evaluated p(y|z) [N])."""
+    dt = z_start.dtype.type
+    z = z_start.copy()
+    N = z.shape[0]
+    active = np.ones(N, dtype=bool)
+    stop = np.full(N, len(noises), dtype=np.int64)
+    prob = np.zeros(N, dtype=z.dtype)
+    for step, noise in enumerate(noises):
+        g, log_p_y, _ = langevin_grad(params, z, target, activation)          # d/dz [log p(y|z)] - z
+        grad = g + z - dt(prior_weight) * z                                     # prior term weighted
+        p = np.exp(log_p_y)
+        upd = z + dt(0.5 * step_size ** 2) * grad + dt(step_size * noise_weight) * noise
+        z = np.where(active[:, None], upd, z)
+        prob = np.where(active, p, prob)
+        hit = active & (p > threshold)
+        stop[hit] = step
+        active &= ~hit
+        if not active.any():
+            break
+    return z, stop, prob
+
+
+# --------------------------------------------------------------------------------------------
+# the stand-alone EmbeddingClassifier trainer (ps_vae/embedding_classifier/embedding_classifier.py:64-100)
+# --------------------------------------------------------------------------------------------
+def embedding_classifier_loss_and_grads(params: Params, x: np.ndarray, y: np.ndarray, compute_grads: bool = True):
+    """training_step / validation_step of the reference's EmbeddingClassifier: CrossEntropyLoss(fc3(relu(fc2(relu(fc1(x))))), y) (mean) and
+    the multiclass accuracy; closed-form gradients of the six tensors.  Returns (dict(loss, acc), logits, grads | None)."""
+    logits, (a1, a2) = embedding_classifier_forward(params, x)
+    loss, dlog = cross_entropy(logits, y)
+    scal = dict(loss=loss, acc=(logits.argmax(-1) == y).mean())
+    if not compute_grads:
+        return scal, logits, None
+    g = {"fc3.weight": dlog.T @ a2, "fc3.bias": dlog.sum(axis=0)}
+    d2 = (dlog @ params["fc3.weight"]) * (a2 > 0)
+    g["fc2.weight"] = d2.T @ a1
+    g["fc2.bias"] = d2.sum(axis=0)
+    d1 = (d2 @ params["fc2.weight"]) * (a1 > 0)
+    g["fc1.weight"] = d1.T @ x
+    g["fc1.bias"] = d1.sum(axis=0)
+    return scal, logits, g

@@ -32,6 +32,7 @@ EXPORTS = [
     "psvae_refresh_shadow", "psvae_forward", "psvae_decode", "psvae_train_fwd_bwd", "psvae_langevin", "psvae_gemm_bf16",
     "psvae_gemm_fp32", "psvae_gemm_probe", "psvae_launch_count", "psvae_consistency_desc_init", "psvae_consistency_workspace_bytes",
     "psvae_consistency_forward", "psvae_train_fwd_bwd_consistency", "psvae_vae_backward", "psvae_gather_rows",
+    "psvae_embedding_classifier_workspace_bytes", "psvae_embedding_classifier_step",
 ]
 
 
@@ -106,10 +107,14 @@ def _declare(l: C.CDLL) -> None:
     l.psvae_consistency_workspace_bytes.argtypes = [CD, I64, I32]
     l.psvae_consistency_forward.restype = C.c_int
     l.psvae_consistency_forward.argtypes = [CD, VP, VP, I64, VP, VP, I64, VP]
+    l.psvae_embedding_classifier_workspace_bytes.restype = I64
+    l.psvae_embedding_classifier_workspace_bytes.argtypes = [CD, I64]
+    l.psvae_embedding_classifier_step.restype = C.c_int
+    l.psvae_embedding_classifier_step.argtypes = [CD, VP, VP, VP, VP, I64, I32, VP, VP, VP, I64, VP]
     l.psvae_train_fwd_bwd_consistency.restype = C.c_int
     l.psvae_train_fwd_bwd_consistency.argtypes = l.psvae_train_fwd_bwd.argtypes + [CD, VP, VP, F]
     l.psvae_langevin.restype = C.c_int
-    l.psvae_langevin.argtypes = [D, VP, VP, I64, P(I32), F, I32, F, U64, U64, I64, I32, VP, VP, VP, VP]
+    l.psvae_langevin.argtypes = [D, VP, VP, I64, P(I32), F, I32, F, U64, U64, I64, I32, VP, VP, VP, F, F, VP, VP, VP]
     l.psvae_gemm_bf16.restype = C.c_int
     l.psvae_gemm_bf16.argtypes = [VP, VP, VP, VP, I64, I32, I64, I32, I32, I32, I32, VP, I64, VP]
     l.psvae_gemm_probe.restype = C.c_int
@@ -160,8 +165,14 @@ def ptr(t) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
 
+#: bumped by every set_option(): cached workspace sizes (engine.HotPath._workspace) depend on the tuning options
+OPTIONS_EPOCH = 0
+
+
 def set_option(name: str, value: int) -> None:
+    global OPTIONS_EPOCH
     check(lib().psvae_set_option(name.encode(), int(value)), "psvae_set_option")
+    OPTIONS_EPOCH += 1
 
 
 def get_option(name: str) -> int:

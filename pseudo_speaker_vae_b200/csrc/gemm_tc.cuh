@@ -134,6 +134,21 @@ struct TcShape {
   int32_t reverse;  // walk the M tiles (and the split-K ranges) from the end: the rows the previous kernel wrote last are still in L2
 };
 
+// MULTI ("merged wgrad"): ONE persistent launch works through a list of wgrad problems dW_p[M_p][N_p] += dY_p^T act_p that share the contraction
+// length K (the batch rows) and the split factor.  Every (problem, tile, k-split) item costs the same number of k-blocks; the static
+// round-robin schedule hands ~12 of them to each CTA pair, so every epilogue but the last overlaps the next item's mainloop and the
+// per-launch fixed cost (pipeline fill, one exposed accumulator drain + reduce-add, teardown: ~8 us of a 20-35 us wgrad launch,
+// tools/wgrad_probe.py) is paid once per step instead of once per layer.  The problems' tensor maps travel in kernel-parameter space.
+constexpr int TC_MAX_PROBLEMS = 20;
+struct TcMulti {
+  CUtensorMap ta[TC_MAX_PROBLEMS], tb[TC_MAX_PROBLEMS], tout[TC_MAX_PROBLEMS];
+  int64_t M[TC_MAX_PROBLEMS];
+  int32_t N[TC_MAX_PROBLEMS];
+  int32_t m_tiles[TC_MAX_PROBLEMS], n_tiles[TC_MAX_PROBLEMS];
+  int32_t tile_begin[TC_MAX_PROBLEMS + 1];      // prefix sums of m_tiles * n_tiles * splits
+  int32_t count;
+};
+
 // byte offset of 16-byte chunk j of row r inside a staged 32-row block whose rows are ROWB bytes (TMA swizzle = ROWB)
 template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
   if constexpr (ROWB == 128) return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));       // SWIZZLE_128B: addr[4:6] ^= addr[7:9]
@@ -143,11 +158,11 @@ template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
 // CL = 2 (only with CG = 2, K-major A, streaming B): clusters of two CTA pairs that work on the same row tile and adjacent N tiles; every CTA
 // loads HALF of its 128 activation rows per k-block and multicasts them to its twin in the other pair, so the activation tile crosses the
 // L2 -> SM fabric once per cluster instead of once per pair (-25 % operand traffic per pair, ring depth unchanged).
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL, bool ALIAS = false, bool EG2 = false, bool GBM = false>
-__global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
-               const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_apf, TcShape s, Epi epi) {
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL, bool ALIAS = false, bool EG2 = false, bool GBM = false, bool MULTI = false>
+__device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const CUtensorMap& tma_out, const CUtensorMap& tma_aux,
+                                             const CUtensorMap& tma_apf, const TcMulti* mp, TcShape s, Epi epi) {
   using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS, EG2>;
+  static_assert(!MULTI || (A_MN && B_MN && Epi::kSplit && Epi::kAuxBytes == 0 && !BRES && CL == 1 && !ALIAS && !EG2 && !GBM), "MULTI: the plain wgrad form");
   static_assert(!ALIAS || (Epi::kSplit && Epi::kAuxBytes == 0 && CL == 1), "ALIAS: split-K store epilogue, one tile per CTA (host-checked)");
   static_assert(!EG2 || (CL == 1 && !BRES && !ALIAS), "EG2: plain streaming kernel");
   static_assert(!GBM || (A_MN && B_MN && CL == 1 && !BRES), "GBM: the wgrad form");
@@ -190,9 +205,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int64_t work_stride = CG == 2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&tma_a);
-    ptx::prefetch_tensormap(&tma_b);
-    ptx::prefetch_tensormap(&tma_out);
+    if constexpr (!MULTI) {
+      ptx::prefetch_tensormap(&tma_a);
+      ptx::prefetch_tensormap(&tma_b);
+      ptx::prefetch_tensormap(&tma_out);
+    }
     if constexpr (kAux) ptx::prefetch_tensormap(&tma_aux);
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
@@ -259,14 +276,44 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
   const int64_t n_tiles = (s.N + BN - 1) / BN;
   const int64_t kb_total = (s.K + TC_BK - 1) / TC_BK;
   const int64_t kb_per_split = (kb_total + s.splits - 1) / s.splits;
-  const int64_t num_tiles = m_tiles * n_tiles * s.splits;
+  const int64_t num_tiles = MULTI ? (int64_t)mp->tile_begin[mp->count] : m_tiles * n_tiles * s.splits;
+  // MULTI: global item index -> (problem, tile inside the problem); n fastest, then m, then the k-split (as below)
+  auto item_problem = [&](int64_t t) {
+    int p = 0;
+    while (p + 1 < mp->count && (int32_t)t >= mp->tile_begin[p + 1]) ++p;
+    return p;
+  };
   // tile order: n fastest -- the CTAs that share an A (row) tile run at the same time, so its second..n-th reads hit L2 instead of HBM;
   // with gridDim.x a multiple of n_tiles every CTA keeps one n_t for all of its tiles
   // (32-bit arithmetic: a 64-bit division here cost 7 % of the epilogue warps' issue slots)
   const uint32_t m_tiles32 = (uint32_t)m_tiles, n_tiles32 = (uint32_t)n_tiles;
-  auto tile_m = [&](int64_t t) { const uint32_t m = ((uint32_t)t / n_tiles32) % m_tiles32; return (int64_t)(s.reverse ? m_tiles32 - 1 - m : m); };
-  auto tile_n = [&](int64_t t) { return (int64_t)((uint32_t)t % n_tiles32); };
-  auto tile_sp = [&](int64_t t) { const uint32_t sp = (uint32_t)t / (n_tiles32 * m_tiles32); return (int64_t)(s.reverse ? (uint32_t)s.splits - 1 - sp : sp); };
+  auto tile_m = [&](int64_t t) {
+    if constexpr (MULTI) {
+      const int p = item_problem(t);
+      const uint32_t l = (uint32_t)t - (uint32_t)mp->tile_begin[p];
+      return (int64_t)((l / (uint32_t)mp->n_tiles[p]) % (uint32_t)mp->m_tiles[p]);
+    } else {
+      const uint32_t m = ((uint32_t)t / n_tiles32) % m_tiles32;
+      return (int64_t)(s.reverse ? m_tiles32 - 1 - m : m);
+    }
+  };
+  auto tile_n = [&](int64_t t) {
+    if constexpr (MULTI) {
+      const int p = item_problem(t);
+      return (int64_t)(((uint32_t)t - (uint32_t)mp->tile_begin[p]) % (uint32_t)mp->n_tiles[p]);
+    } else {
+      return (int64_t)((uint32_t)t % n_tiles32);
+    }
+  };
+  auto tile_sp = [&](int64_t t) {
+    if constexpr (MULTI) {
+      const int p = item_problem(t);
+      return (int64_t)(((uint32_t)t - (uint32_t)mp->tile_begin[p]) / ((uint32_t)mp->n_tiles[p] * (uint32_t)mp->m_tiles[p]));
+    } else {
+      const uint32_t sp = (uint32_t)t / (n_tiles32 * m_tiles32);
+      return (int64_t)(s.reverse ? (uint32_t)s.splits - 1 - sp : sp);
+    }
+  };
 
   auto tile_g = [&](int64_t n_t) { return s.groups > 1 ? (int32_t)(((uint32_t)n_t * (uint32_t)BN) / (uint32_t)s.grp_n) : 0; };
 
@@ -291,6 +338,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     // ============================ TMA producer ============================
     // warp-uniform loop; the TMA instructions of one k-block are issued by one elected lane
     {
+      const CUtensorMap* pa = &tma_a;        // MULTI: the current item's problem maps
+      const CUtensorMap* pb = &tma_b;
       // issue (load into sa / sb) or prefetch-to-L2 (null destination with want_* set) the operand boxes of k-block kb of a tile
       auto fetch = [&](int64_t m_t, int64_t n_t, int64_t kb, uint8_t* sa, uint8_t* sb, uint64_t* bar, bool want_a, bool want_b) {
         const int32_t g = tile_g(n_t);
@@ -307,17 +356,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (want_a) {
           if constexpr (CL == 2) {
             // this CTA's half (64 rows) of the pair-rank's 128 rows, delivered to itself and to its twin in the other pair
-            if (sa) ptx::tma_load_2d_cg2_mc(sa + pidx * (64 * TC_BK * 2), &tma_a, bar_addr, k_el, a_row + (int32_t)pidx * 64,
+            if (sa) ptx::tma_load_2d_cg2_mc(sa + pidx * (64 * TC_BK * 2), pa, bar_addr, k_el, a_row + (int32_t)pidx * 64,
                                             (uint16_t)((1u << cta_rank) | (1u << (cta_rank + 2))));
-            else ptx::tma_prefetch_2d(&tma_a, k_el, a_row + (int32_t)pidx * 64);
+            else ptx::tma_prefetch_2d(pa, k_el, a_row + (int32_t)pidx * 64);
           } else if constexpr (!A_MN) {
-            if (sa) ld(sa, &tma_a, k_el, a_row);
-            else ptx::tma_prefetch_2d(&tma_a, k_el, a_row);
+            if (sa) ld(sa, pa, k_el, a_row);
+            else ptx::tma_prefetch_2d(pa, k_el, a_row);
           } else {
 #pragma unroll
             for (int j = 0; j < TC_BM / 64; ++j) {
-              if (sa) ld(sa + j * (64 * TC_BK * 2), &tma_a, a_row + j * 64, k_el);
-              else ptx::tma_prefetch_2d(&tma_a, a_row + j * 64, k_el);
+              if (sa) ld(sa + j * (64 * TC_BK * 2), pa, a_row + j * 64, k_el);
+              else ptx::tma_prefetch_2d(pa, a_row + j * 64, k_el);
             }
           }
         }
@@ -331,19 +380,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         if (want_b) {
           if constexpr (!B_MN) {
-            if (sb) ld(sb, &tma_b, kb_b, row_b);
-            else ptx::tma_prefetch_2d(&tma_b, kb_b, row_b);
+            if (sb) ld(sb, pb, kb_b, row_b);
+            else ptx::tma_prefetch_2d(pb, kb_b, row_b);
           } else {
 #pragma unroll
             for (int j = 0; j < (BN / CG) / 64; ++j) {
               if constexpr (GBM) {
                 // wgrad form grouped by m: the group of this M tile picks the B columns (s.grp_n = rows of C per group, s.grp_k = B column offset per group)
                 const int32_t gb = b_row + (int32_t)(((uint32_t)m_t * (uint32_t)TM) / (uint32_t)s.grp_n) * s.grp_k;
-                if (sb) ld(sb + j * (64 * TC_BK * 2), &tma_b, gb + j * 64, k_el_b);
-                else ptx::tma_prefetch_2d(&tma_b, gb + j * 64, k_el_b);
+                if (sb) ld(sb + j * (64 * TC_BK * 2), pb, gb + j * 64, k_el_b);
+                else ptx::tma_prefetch_2d(pb, gb + j * 64, k_el_b);
               } else {
-              if (sb) ld(sb + j * (64 * TC_BK * 2), &tma_b, b_row + j * 64, k_el_b);
-              else ptx::tma_prefetch_2d(&tma_b, b_row + j * 64, k_el_b);
+              if (sb) ld(sb + j * (64 * TC_BK * 2), pb, b_row + j * 64, k_el_b);
+              else ptx::tma_prefetch_2d(pb, b_row + j * 64, k_el_b);
               }
             }
           }
@@ -381,6 +430,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int64_t m_t = tile_m(tile), n_t = tile_n(tile),
                       sp = tile_sp(tile);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
+        if constexpr (MULTI) {
+          const int p = item_problem(tile);
+          pa = &mp->ta[p];
+          pb = &mp->tb[p];
+        }
         if constexpr (!A_MN) {
           // next tile's activation panel -> L2, whole rows at a time (DRAM-page order; the ring's narrow 128-byte-per-row boxes then hit L2)
           const int64_t nxt = tile + work_stride;
@@ -552,7 +606,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
       const int32_t row_base = (int32_t)(m_t * TM) + (int32_t)cta_rank * TC_BM + quarter * 32;
       const int64_t row = (int64_t)row_base + lane;
-      const bool valid = row < s.M;
+      int64_t pM = s.M;                       // this item's output extent and map (MULTI: its problem's)
+      int pN = s.N;
+      const CUtensorMap* pout = &tma_out;
+      if constexpr (MULTI) {
+        const int p = item_problem(tile);
+        pM = mp->M[p];
+        pN = mp->N[p];
+        pout = &mp->tout[p];
+      }
+      const bool valid = row < pM;
       const int col_base = (int)(n_t * BN) + half * COLS_PER_WARP;
       if constexpr (kLat) {
         // ---- fused encoder head: this warp owns rows [row_base, +32) and latent dims [32 half, 32 half + 32); its 64 accumulator
@@ -695,7 +758,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (n_t != cs_nt) { cs_flush(); cs_nt = n_t; }
       }
       if constexpr (kAux) {                  // fetch the first auxiliary block while the MMAs of this tile are still running
-        if (col_base < s.N && lane == 0) {
+        if (col_base < pN && lane == 0) {
           ptx::mbar_arrive_expect_tx(&aux_bar[ew], Epi::kAuxBytes);
           ptx::tma_load_2d(abuf, &tma_aux, &aux_bar[ew], col_base, row_base);
         }
@@ -704,12 +767,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         if (nxt < num_tiles && lane < CH) {
           const int32_t nrow = (int32_t)(tile_m(nxt) * TM) + (int32_t)cta_rank * TC_BM + quarter * 32;
           const int ncol = (int)(tile_n(nxt) * BN) + half * COLS_PER_WARP + lane * 32;
-          if (ncol < s.N) ptx::tma_prefetch_2d(&tma_aux, ncol, nrow);
+          if (ncol < pN) ptx::tma_prefetch_2d(&tma_aux, ncol, nrow);
         }
       }
       uint32_t pre[CH];                      // per-block words the functor wants early (EpiActGrad: the ReLU bit masks)
 #pragma unroll
-      for (int c = 0; c < CH; ++c) pre[c] = (col_base + c * 32 < s.N) ? epi.tc_pre(row, col_base + c * 32, valid) : 0u;
+      for (int c = 0; c < CH; ++c) pre[c] = (col_base + c * 32 < pN) ? epi.tc_pre(row, col_base + c * 32, valid) : 0u;
       twait(&tfull_bar[acc], acc_phase, 4, tw0);
       ptx::tc_fence_after();
       const bool zero_acc = kb0 >= kb1;
@@ -717,17 +780,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
       for (int c = 0; c < CH; ++c) {
         const int col_in_tile = half * COLS_PER_WARP + c * 32;
         const int col = col_base + c * 32;
-        if (col >= s.N) continue;            // warp-uniform
+        if (col >= pN) continue;            // warp-uniform
         uint32_t acc_r[32];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_in_tile);
         ptx::tmem_ld_32x32_issue(taddr, acc_r);
         float bv[32];                        // the block's bias values: loaded while the TMEM read is in flight
         if constexpr (Epi::kBias) {
-          if (epi.bias && col + 32 <= s.N) {
+          if (epi.bias && col + 32 <= pN) {
             load_vec<32>(epi.bias + col, bv);
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) bv[i] = (epi.bias && col + i < s.N) ? __ldg(epi.bias + col + i) : 0.f;
+            for (int i = 0; i < 32; ++i) bv[i] = (epi.bias && col + i < pN) ? __ldg(epi.bias + col + i) : 0.f;
           }
         }
         ptx::tmem_ld_wait(acc_r);
@@ -760,7 +823,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             }
           }
         }
-        epi.tc_transform(row, col, s.N, valid, v, aux, pre[c], red);
+        epi.tc_transform(row, col, pN, valid, v, aux, pre[c], red);
         if constexpr (kAux) {
           // The staged auxiliary block may be overwritten by the next TMA load only once every lane HOLDS its values: issuing the loads from
           // shared memory is not enough (the last 16-byte chunk of a row was occasionally still in the LSU queue when the next block landed --
@@ -769,7 +832,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           static_assert(Epi::kReduce, "the release of the auxiliary block is ordered through the functor's reduction value");
           asm volatile("" ::"f"(red) : "memory");
           __syncwarp();
-          if (col + 32 < s.N && c + 1 < CH && lane == 0) {
+          if (col + 32 < pN && c + 1 < CH && lane == 0) {
             ptx::mbar_arrive_expect_tx(&aux_bar[ew], Epi::kAuxBytes);
             ptx::tma_load_2d(abuf, &tma_aux, &aux_bar[ew], col + 32, row_base);
           }
@@ -785,7 +848,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
           uint8_t* const obuf = obuf0 + (Cfg::kOutBufs == 2 ? ((WIDE ? (c >> 1) : c) & 1) * Cfg::kOutBytes : 0);
           const int part = WIDE ? (c & 1) : 0;
           const bool opens = !WIDE || part == 0;
-          const bool closes = !WIDE || part == 1 || col + 32 >= s.N || c + 1 == CH;
+          const bool closes = !WIDE || part == 1 || col + 32 >= pN || c + 1 == CH;
           if (opens) {          // the TMA store that last used this staging block must have finished reading it
             if (lane == 0) {
               if constexpr (Cfg::kOutBufs == 2) ptx::bulk_wait_read1();      // two blocks alternate: only the store before the last one must be done
@@ -850,13 +913,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             if (lane == 0) {
               const int bcol = WIDE ? col - part * 32 : col;
               if constexpr (Epi::kSplit) {
-                if (epi.reduce_add) ptx::tma_reduce_add_2d(&tma_out, obuf, bcol, row_base);
-                else ptx::tma_store_3d(&tma_out, obuf, bcol, row_base, (int32_t)sp);
+                if (epi.reduce_add) ptx::tma_reduce_add_2d(pout, obuf, bcol, row_base);
+                else ptx::tma_store_3d(pout, obuf, bcol, row_base, (int32_t)sp);
               } else if (s.out3d) {
                 const int32_t g = tile_g(n_t);
-                ptx::tma_store_3d(&tma_out, obuf, bcol - g * s.grp_n, row_base, g);
+                ptx::tma_store_3d(pout, obuf, bcol - g * s.grp_n, row_base, g);
               } else {
-                ptx::tma_store_2d(&tma_out, obuf, bcol, row_base);
+                ptx::tma_store_2d(pout, obuf, bcol, row_base);
               }
               ptx::bulk_commit();
             }
@@ -922,6 +985,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     else ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
     if (tracing && lane == 0) s.trace[(size_t)blockIdx.x * 16 + 15] = ptx::globaltimer_ns();     // kernel exit
   }
+}
+
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL, bool ALIAS = false, bool EG2 = false, bool GBM = false>
+__global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
+               const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_apf, TcShape s, Epi epi) {
+  gemm_tc_body<BN, A_MN, B_MN, Epi, CG, BRES, CL, ALIAS, EG2, GBM, false>(tma_a, tma_b, tma_out, tma_aux, tma_apf, nullptr, s, epi);
+}
+
+// the merged wgrad launch (MULTI): the problem list, tensor maps included, is one __grid_constant__ kernel parameter
+template <int BN, class Epi, int CG>
+__global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
+gemm_tc_multi_kernel(const __grid_constant__ TcMulti mp, TcShape s, Epi epi) {
+  gemm_tc_body<BN, true, true, Epi, CG, false, 1, false, false, false, true>(mp.ta[0], mp.tb[0], mp.tout[0], mp.ta[0], mp.ta[0], &mp, s, epi);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1161,6 +1238,99 @@ int gemm_tc_launch_latent(const void* he, int64_t ldhe, const void* Wstack, int 
   PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, ta, s, epi));
   count_launch();
   PSVAE_LAUNCH_CHECK("gemm_tc_kernel<EpiLatent>");
+  return 0;
+}
+
+// One wgrad problem of the merged launch: out[M][N] (fp32, accumulated by TMA reduce-add) += dY[rows][M]^T * act[rows][N]
+struct TcWgradProblem {
+  const void* dY; int64_t ldy;
+  const void* act; int64_t lda;
+  float* out; int64_t ldo;
+  int M, N;
+};
+
+// All of a step's wgrads in ONE persistent launch (see TcMulti).  256 x 256 tiles on CTA pairs for every problem: a problem narrower than the
+// tile (the 64-wide latent layers) reads only its valid columns (TMA zero-fills the rest without DRAM traffic) -- these launches are bound by
+// streaming the batch, not by the MMAs.
+static inline int gemm_tc_launch_multi_wgrad(const TcWgradProblem* probs, int count, int64_t rows, cudaStream_t st) {
+  using Epi = EpiStore;
+  constexpr int BN = 256, CG = 2;
+  using Cfg = TcCfg<BN, Epi, CG, false>;
+  if (count <= 0) return 0;
+  if (count > TC_MAX_PROBLEMS) { set_error("merged wgrad: %d problems, at most %d", count, TC_MAX_PROBLEMS); return -2; }
+  static thread_local TcMulti mp;      // 8 KB: not on the stack of every caller
+  memset(&mp, 0, sizeof(mp));
+  int64_t tiles = 0;
+  for (int p = 0; p < count; ++p) {
+    const TcWgradProblem& q = probs[p];
+    if (q.M % 8 != 0 || q.N % 8 != 0) { set_error("merged wgrad: M=%d, N=%d must be multiples of 8", q.M, q.N); return -2; }
+    TcOperand a{q.dY, (int64_t)q.M, q.ldy, true};
+    TcOperand b{q.act, (int64_t)q.N, q.lda, true};
+    PSVAE_TRY(tc_tensor_map(a, rows, TC_BK, &mp.ta[p]));
+    PSVAE_TRY(tc_tensor_map(b, rows, TC_BK, &mp.tb[p]));
+    PSVAE_TRY(tc_block_map(q.out, 4, q.M, q.N, q.ldo, 0, 0, &mp.tout[p], Cfg::kBlockCols));
+    mp.M[p] = q.M; mp.N[p] = q.N;
+    mp.m_tiles[p] = (int32_t)ceil_div64(q.M, TC_BM * CG);
+    mp.n_tiles[p] = (int32_t)ceil_div64(q.N, BN);
+    tiles += (int64_t)mp.m_tiles[p] * mp.n_tiles[p];
+  }
+  // split factor: ~12 items per CTA pair, at least 8 k-blocks (512 batch rows) per item, no empty split
+  const int pairs = tc_grid_size() / CG;
+  const int64_t kb = ceil_div64(rows, TC_BK);
+  int64_t S = (12ll * pairs + tiles / 2) / tiles;
+  if (S > kb / 8) S = kb / 8;
+  if (S < 1) S = 1;
+  const int64_t per = ceil_div64(kb, S);
+  S = ceil_div64(kb, per);
+  int32_t begin = 0;
+  for (int p = 0; p < count; ++p) {
+    mp.tile_begin[p] = begin;
+    begin += (int32_t)(mp.m_tiles[p] * mp.n_tiles[p] * S);
+  }
+  mp.tile_begin[count] = begin;
+  mp.count = count;
+  TcShape s;
+  memset(&s, 0, sizeof(s));
+  s.M = probs[0].M; s.N = probs[0].N; s.K = rows; s.splits = (int32_t)S;
+  tc_desc_strides(true, &s.a_lbo, &s.a_sbo);
+  tc_desc_strides(true, &s.b_lbo, &s.b_sbo);
+  s.stages = Cfg::kStages;
+  if (tc_max_stages() >= 2 && tc_max_stages() < s.stages) s.stages = tc_max_stages();
+  s.trace = tc_trace_ptr();
+  s.groups = 1;
+  EpiStore epi{probs[0].out, probs[0].ldo, 0, 1.f, 0.f, nullptr, 1};
+  auto kern = gemm_tc_multi_kernel<BN, Epi, CG>;
+  static unsigned long long attr_mask = 0;
+  int dev = 0;
+  PSVAE_CUDA(cudaGetDevice(&dev));
+  if (!(attr_mask >> (dev & 63) & 1ull)) {
+    PSVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_mask |= 1ull << (dev & 63);
+  }
+  int grid = pairs;
+  if (begin < grid) grid = begin;
+  grid *= CG;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[2];
+  int na = 0;
+  at[na].id = cudaLaunchAttributeClusterDimension;
+  at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+  ++na;
+  if (pdl_enabled()) {
+    at[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = na;
+  PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, mp, s, epi));
+  count_launch();
+  PSVAE_LAUNCH_CHECK("gemm_tc_multi_kernel");
   return 0;
 }
 

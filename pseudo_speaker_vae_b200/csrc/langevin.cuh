@@ -5,6 +5,11 @@
 // samples (z, activations, classifier weights) in shared memory for the whole loop, the noise comes from
 // the counter-based generator (philox.cuh), and nothing goes back to the host between steps (the
 // reference does a D2H copy of z and two .item() syncs per step).
+//
+// The analysis variant of the same loop (analysis/sample_gender_transformation.py:61-99) is covered by three more arguments:
+// `prior_weight` scales the log p(z) term (the script's PRIOR_WEIGHT; inference.py has 1), `threshold` > 0 stops a sample after the update
+// of the first step whose p(y|z) exceeded it (the script's per-sample `break`), and `stop_step` / `last_prob` report, per sample, the step
+// at which that happened (num_steps if never) and the classifier probability of its last evaluated step.  A stopped sample keeps its z.
 #pragma once
 #include "common.cuh"
 #include "epilogue.cuh"
@@ -57,9 +62,13 @@ static inline size_t langevin_smem_bytes(const LangevinClf& c) {
 __global__ void __launch_bounds__(LG_THREADS) langevin_kernel(LangevinClf c, const float* __restrict__ params, float* __restrict__ z_io,
                                                               int64_t rows, float step_size, int num_steps, float noise_weight, uint64_t seed,
                                                               uint64_t offset0, int64_t row0, int init_from_philox, const float* __restrict__ noise,
-                                                              float* __restrict__ history, float* __restrict__ stats) {
+                                                              float* __restrict__ history, float* __restrict__ stats, float prior_weight, float threshold,
+                                                              int32_t* __restrict__ stop_step, float* __restrict__ last_prob) {
   PSVAE_GRID_DEP();
   extern __shared__ float lg_smem[];
+  __shared__ int lg_done[LG_TILE], lg_hit[LG_TILE];      // per sample: stopped (threshold reached at an earlier step) / reaches it at this step
+  __shared__ int lg_stop[LG_TILE];
+  __shared__ float lg_prob[LG_TILE];
   const int L = c.L, H = c.hidden;
   const int ldz = L + 1, ldh = H + 1, ldd = (H > L ? ldh : ldz), ldc = LG_MAXC + 1;
   float* W = lg_smem;
@@ -102,6 +111,7 @@ __global__ void __launch_bounds__(LG_THREADS) langevin_kernel(LangevinClf c, con
 #pragma unroll
     for (int j = 0; j < 4; ++j) zs[qs * ldz + qk + j] = v[j];
   }
+  if (tid < LG_TILE) { lg_done[tid] = 0; lg_hit[tid] = 0; lg_stop[tid] = num_steps; lg_prob[tid] = 0.f; }
   __syncthreads();
 
   const float half_s2 = 0.5f * step_size * step_size;
@@ -157,6 +167,11 @@ __global__ void __launch_bounds__(LG_THREADS) langevin_kernel(LangevinClf c, con
         lp_y += lg[c.targets[h]] - mx - lse;
         for (int k = 0; k < C; ++k) lg[k] = (k == c.targets[h] ? 1.f : 0.f) - expf(lg[k] - mx - lse);
       }
+      if (!lg_done[s]) {
+        const float p = expf(lp_y);
+        lg_prob[s] = p;
+        if (threshold > 0.f && p > threshold) { lg_hit[s] = 1; lg_stop[s] = step; }
+      }
       if (stats) {
         float lp_z = 0.f;
         for (int k = 0; k < L; ++k) lp_z = fmaf(zs[s * ldz + k], zs[s * ldz + k], lp_z);
@@ -206,10 +221,19 @@ __global__ void __launch_bounds__(LG_THREADS) langevin_kernel(LangevinClf c, con
       const int qs = q / (L >> 2), qk = (q % (L >> 2)) << 2;
       const int64_t r = tile_row0 + qs;
       if (r >= rows) continue;
-      float nz[4];
+      if (lg_done[qs]) {                     // a stopped sample keeps its z (the history repeats it)
+        if (history) {
+          float zk[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) zk[j] = zs[qs * ldz + qk + j];
+          store_vec<4>(history + ((int64_t)step * rows + r) * L + qk, zk);
+        }
+        continue;
+      }
+      float nz[4] = {0.f, 0.f, 0.f, 0.f};
       if (noise) {
         load_vec<4>(noise + ((int64_t)step * rows + r) * L + qk, nz);
-      } else {
+      } else if (nscale != 0.f) {
         const float4 t = philox_normal4((uint64_t)((row0 + r) * L + qk) >> 2, seed, offset0 + 1 + (uint64_t)step);
         nz[0] = t.x; nz[1] = t.y; nz[2] = t.z; nz[3] = t.w;
       }
@@ -217,13 +241,20 @@ __global__ void __launch_bounds__(LG_THREADS) langevin_kernel(LangevinClf c, con
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float zv = zs[qs * ldz + qk + j];
-        const float grad = dcur[qs * ldd + qk + j] - zv;
+        const float grad = dcur[qs * ldd + qk + j] - prior_weight * zv;
         zn[j] = zv + half_s2 * grad + nscale * nz[j];
         zs[qs * ldz + qk + j] = zn[j];
       }
       if (history) store_vec<4>(history + ((int64_t)step * rows + r) * L + qk, zn);
     }
     __syncthreads();
+    if (tid < LG_TILE && lg_hit[tid]) { lg_done[tid] = 1; lg_hit[tid] = 0; }
+    const int all_done = __syncthreads_and(tid >= LG_TILE || lg_done[tid] || tile_row0 + tid >= rows);
+    if (all_done && !history && !stats) break;
+  }
+  if (tid < LG_TILE && tile_row0 + tid < rows) {
+    if (stop_step) stop_step[tile_row0 + tid] = lg_stop[tid];
+    if (last_prob) last_prob[tile_row0 + tid] = lg_prob[tid];
   }
 
   for (int q = tid; q < quads; q += LG_THREADS) {
@@ -256,7 +287,8 @@ template <int L>
 __global__ void __launch_bounds__(LGF_THREADS) langevin_fast_kernel(LangevinClf c, const float* __restrict__ params, float* __restrict__ z_io, int64_t rows,
                                                                     float step_size, int num_steps, float noise_weight, uint64_t seed, uint64_t offset0,
                                                                     int64_t row0, int init_from_philox, const float* __restrict__ noise,
-                                                                    float* __restrict__ history, float* __restrict__ stats) {
+                                                                    float* __restrict__ history, float* __restrict__ stats, float prior_weight, float threshold,
+                                                                    int32_t* __restrict__ stop_step, float* __restrict__ last_prob) {
   PSVAE_GRID_DEP();
   __shared__ __align__(16) float W[CLF_LG_MAXC * L];
   __shared__ float bias[CLF_LG_MAXC];
@@ -299,7 +331,11 @@ __global__ void __launch_bounds__(LGF_THREADS) langevin_fast_kernel(LangevinClf 
   }
   const float half_s2 = 0.5f * step_size * step_size;
   const float nscale = step_size * noise_weight;
+  bool active = true;                    // false once p(y|z) has exceeded the threshold (this sample's z is final)
+  int stop = num_steps;
+  float prob = 0.f;
   for (int step = 0; step < num_steps; ++step) {
+    if (!history && !stats && !__any_sync(0xffffffffu, active && live)) break;      // the whole warp has stopped
     // logits of the targeted heads
     float coef[CLF_LG_MAXC];
 #pragma unroll
@@ -354,13 +390,20 @@ __global__ void __launch_bounds__(LGF_THREADS) langevin_fast_kernel(LangevinClf 
         atomicAdd(stats + 2 * step + 1, b);
       }
     }
-    // z <- z + 0.5 s^2 (W^T coef - z) + s * noise_weight * N(0, I)
-    if (!noise) draw(offset0 + 1 + (uint64_t)step);
+    bool hit = false;
+    if (active) {
+      prob = expf(lp_y);
+      hit = threshold > 0.f && prob > threshold;
+    }
+    // z <- z + 0.5 s^2 (W^T coef - prior_weight z) + s * noise_weight * N(0, I)
+    if (!noise && nscale != 0.f) draw(offset0 + 1 + (uint64_t)step);
 #pragma unroll
     for (int q = 0; q < L / 4; ++q) {
       float nz[4];
       {
-        const float4 t = noise ? *reinterpret_cast<const float4*>(noise + ((int64_t)step * rows + rr) * L + 4 * q) : nz_s[q][threadIdx.x];
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (noise) t = *reinterpret_cast<const float4*>(noise + ((int64_t)step * rows + rr) * L + 4 * q);
+        else if (nscale != 0.f) t = nz_s[q][threadIdx.x];
         nz[0] = t.x; nz[1] = t.y; nz[2] = t.z; nz[3] = t.w;
       }
       float g[4] = {0.f, 0.f, 0.f, 0.f};
@@ -373,13 +416,16 @@ __global__ void __launch_bounds__(LGF_THREADS) langevin_fast_kernel(LangevinClf 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float zv = z[4 * q + j];
-        z[4 * q + j] = zv + half_s2 * (g[j] - zv) + nscale * nz[j];
+        if (active) z[4 * q + j] = zv + half_s2 * (g[j] - prior_weight * zv) + nscale * nz[j];
       }
       if (history && live)
         *reinterpret_cast<float4*>(history + ((int64_t)step * rows + r) * L + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);
     }
+    if (hit) { active = false; stop = step; }
   }
   if (live) {
+    if (stop_step) stop_step[r] = stop;
+    if (last_prob) last_prob[r] = prob;
 #pragma unroll
     for (int q = 0; q < L / 4; ++q)
       *reinterpret_cast<float4*>(z_io + r * L + 4 * q) = make_float4(z[4 * q], z[4 * q + 1], z[4 * q + 2], z[4 * q + 3]);

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "gemm_tc.cuh"
+#include "decoder_chain.cuh"
 #include "kernels.cuh"
 #include "langevin.cuh"
 #include "philox.cuh"
@@ -75,6 +76,10 @@ struct Options {
                                        //    Measured (round 2, A/B): 0.7832 -> 0.7733 ms/step
   int64_t tc_alias_staging = 0;        // 1: split-K (wgrad) launches with at most one tile per CTA overlay the epilogue staging on the operand ring (7 stages instead of 5).
                                        //    Measured neutral (31.4 vs 31.7 us for the 512 x 512 wgrad): the wgrad form is not bound by bytes in flight; off by default
+  int64_t tc_merged_wgrad = 1;         // 1 (fast tcgen05 mode): every wgrad of the step runs in ONE persistent launch at the end of the backward pass (gemm_tc_launch_multi_wgrad):
+                                       //    the ~8 us fixed cost of a wgrad launch is paid once instead of 8 times
+  int64_t decode_chain = 0;            // 1 (tcgen05 mode, two hidden layers <= 512 wide, latent 64, <= 256 outputs, no normalize_decoder): psvae_decode runs the chained
+                                       //    decoder kernel (decoder_chain.cuh): z from Philox in-kernel, hidden activations on-chip, one launch for all rows
   int64_t tc_grouped = 1;              // 1: layers 1..n of the two encoders run as ONE block-diagonal launch each (forward and dgrad) instead of one per encoder
   int64_t pdl = 1;                     // 1: kernels are launched with programmatic stream serialization (their prologue overlaps the predecessor's tail)
   int64_t tc_trace_ptr = 0;            // profiling: device pointer of gridDim.x * 16 cycle counters the GEMM kernels fill (0 = off)
@@ -430,7 +435,20 @@ template <typename TAct> struct StepBufs {
   uint32_t* mhd[PSVAE_MAX_LAYERS] = {};     // fused classifier: per-block partials, summed nll/acc
   float *sse_part = nullptr, *kl_part = nullptr, *nll_part[PSVAE_MAX_CLF_HEADS] = {}, *acc_part[PSVAE_MAX_CLF_HEADS] = {};
   int64_t n_sse = 0, n_kl = 0, n_ce = 0;
+  // option tc_merged_wgrad: the wgrad problems collected during the backward pass, launched together (flushed earlier only before a
+  // ping-pong gradient buffer they read is overwritten: more than two hidden layers)
+  TcWgradProblem pending[TC_MAX_PROBLEMS];
+  int n_pending = 0;
+  bool merge_wgrads = false;
 };
+
+template <typename TAct>
+static int flush_wgrads(StepBufs<TAct>& w, int64_t rows, cudaStream_t st) {
+  if (w.n_pending == 0) return 0;
+  const int n = w.n_pending;
+  w.n_pending = 0;
+  return gemm_tc_launch_multi_wgrad(w.pending, n, rows, st);
+}
 
 // the fused classifier kernel covers the common shape: heads directly on mu (no trunk), L = 32/64/96/128, <= 8 classes in total
 static bool clf_fused_ok(const psvae_model_desc* d) {
@@ -571,6 +589,12 @@ static int launch_reduce(const float* partials, int64_t n, int S, float* out, cu
 template <typename TAct>
 static int wgrad(const TAct* dY, int64_t ldy, const TAct* A, int64_t lda, int64_t rows, int out, int in, float* gW, float* gb,
                  StepBufs<TAct>& w, cudaStream_t st) {
+  if (sizeof(TAct) == 2 && w.merge_wgrads) {
+    if (w.n_pending == TC_MAX_PROBLEMS) PSVAE_TRY(flush_wgrads(w, rows, st));
+    w.pending[w.n_pending++] = TcWgradProblem{dY, ldy, A, lda, gW, (int64_t)in, out, in};
+    if (!gb) return 0;
+    return launch_colsum<TAct>(dY, ldy, rows, out, w.cpart, gb, st);
+  }
   const int splits = Engine<TAct>::wgrad_splits(out, in, rows);
   if (sizeof(TAct) == 2 && !g_opt.deterministic) {
     // fast mode: every split-K tile adds its block into the (zeroed) gradient with a TMA reduce-add -- no partial buffers, no second pass
@@ -1088,6 +1112,14 @@ static int run_step(const StepArgs& a) {
 
   // =================================== backward ===================================
   float* G = a.grads;
+  w.merge_wgrads = sizeof(TAct) == 2 && g_opt.tc_merged_wgrad && !g_opt.deterministic;
+  // a gradient buffer that a collected (not yet launched) wgrad problem reads must not be overwritten: launch what is pending first
+  auto before_write = [&](const void* buf) -> int {
+    for (int i = 0; i < w.n_pending; ++i)
+      if (w.pending[i].dY == buf || static_cast<const char*>(w.pending[i].dY) == static_cast<const char*>(buf) + (size_t)n.H * sizeof(TAct))
+        return flush_wgrads(w, B, st);
+    return 0;
+  };
 
   // ---- classifier backward -> dmu_clf (the fused kernel already produced it together with the classifier's gradients)
   const float* dmu_clf = (clf_fused && a.want_loss) ? w.dmu_clf : nullptr;
@@ -1134,6 +1166,7 @@ static int run_step(const StepArgs& a) {
       const int in_dim = n.dec_in(j);
       PSVAE_TRY(wgrad<TAct>(dY, out_dim, ain, in_dim, B, out_dim, in_dim, G + d->dec_w[j], bias_done ? nullptr : G + d->dec_b[j], w, st));
       if (j > 0) {
+        PSVAE_TRY(before_write(w.gd[pp]));
         PSVAE_TRY(dgrad_hidden<TAct>(dY, out_dim, Wt + d->dec_w[j], out_dim, in_dim, w.hd[j - 1], n.H, w.mhd[j - 1], w.gd[pp], n.H, B,
                                      G + d->dec_b[j - 1], w, &bias_done, st));
         dY = w.gd[pp];
@@ -1235,7 +1268,7 @@ static int run_step(const StepArgs& a) {
       if constexpr (sizeof(TAct) == 2) {
         // option tc_grouped_wgrad: one launch for both encoders ([W_mu_j; W_sigma_j] is one [2H][H] block of the gradient buffer)
         const int tm = TC_BM * (tc_use_pair(2 * n.H, n.H, (int)g_opt.tc_force_bn) ? 2 : 1);
-        if (g_opt.tc_grouped_wgrad && !g_opt.deterministic && bias_done[0] && bias_done[1] && n.H % tm == 0) {
+        if (g_opt.tc_grouped_wgrad && !w.merge_wgrads && !g_opt.deterministic && bias_done[0] && bias_done[1] && n.H % tm == 0) {
           const int splits = Engine<TAct>::wgrad_splits(2 * n.H, n.H, B);
           EpiStore e{G + d->enc_w[j], n.H, 0, 1.f, 0.f, nullptr, 1};
           PSVAE_TRY((Engine<TAct>::wgrad_grouped(w.ge[pp], 2 * n.H, w.he[j - 1], 2 * n.H, B, 2, n.H, n.H, splits, e, st)));
@@ -1248,6 +1281,7 @@ static int run_step(const StepArgs& a) {
                               bias_done[s] ? nullptr : G + d->enc_b[j] + s * n.H, w, st));
       }
       bool pair_done = false;
+      PSVAE_TRY(before_write(w.ge[pp ^ 1]));
       if constexpr (sizeof(TAct) == 2) {
         if (grouped_hidden && w.mhe[j - 1] && tc_colsum_ok(n.H)) {
           PSVAE_TRY(dgrad_pair(w.ge[pp], 2 * n.H, n.H, j, w.ge[pp ^ 1]));
@@ -1269,7 +1303,7 @@ static int run_step(const StepArgs& a) {
       PSVAE_TRY(wgrad<TAct>(w.ge[pp], 2 * n.H, xa, n.D, B, 2 * n.H, n.D, G + d->enc_w[0], G + d->enc_b[0], w, st));
     }
   }
-  return 0;
+  return flush_wgrads(w, B, st);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1284,6 +1318,20 @@ static int run_decode(const psvae_model_desc* d, const float* params, const bf16
   if (rows <= 0) { set_error("rows=%lld must be positive", (long long)rows); return -2; }
   if (!params || !x_hat) { set_error("params and x_hat must not be NULL"); return -1; }
   if (sizeof(TAct) == 2 && !shadow) { set_error("PSVAE_BF16 needs the bf16 shadow copy of the parameters (psvae_refresh_shadow)"); return -1; }
+  if constexpr (sizeof(TAct) == 2) {
+    // the chained kernel: no scratch, no chunking -- every hidden activation stays on the SM that produced it
+    if (g_opt.decode_chain && !d->normalize_decoder && decoder_chain_ok(n.D, n.L, n.H, n.nh) && (reinterpret_cast<uintptr_t>(x_hat) & 15) == 0 &&
+        (!z || (reinterpret_cast<uintptr_t>(z) & 15) == 0) && (!z_out || (reinterpret_cast<uintptr_t>(z_out) & 15) == 0)) {
+      DcArgs a;
+      memset(&a, 0, sizeof(a));
+      a.rows = rows; a.H = n.H; a.D = n.D;
+      a.b0 = params + d->dec_b[0]; a.b1 = params + d->dec_b[1]; a.b2 = params + d->dec_b[2];
+      a.z_in = z; a.z_out = (z_out && z_out != z) ? z_out : nullptr;
+      a.seed = seed; a.offset = offset; a.first_row = row0;
+      a.trace = tc_trace_ptr();
+      return decoder_chain_launch(shadow + d->dec_w[0], shadow + d->dec_w[1], shadow + d->dec_w[2], x_hat, a, st);
+    }
+  }
   const int64_t chunk = rows < g_opt.decode_chunk ? rows : g_opt.decode_chunk;
   StepBufs<TAct> w;
   {
@@ -1384,6 +1432,8 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "clf_grad_in_bwd")) { g_opt.clf_grad_in_bwd = value ? 1 : 0; return 0; }
   if (!strcmp(name, "fused_head")) { g_opt.fused_head = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_grouped_wgrad")) { g_opt.tc_grouped_wgrad = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_merged_wgrad")) { g_opt.tc_merged_wgrad = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "decode_chain")) { g_opt.decode_chain = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_pair_cluster")) { g_opt.tc_pair_cluster = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
@@ -1410,6 +1460,8 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "clf_grad_in_bwd")) return g_opt.clf_grad_in_bwd;
   if (!strcmp(name, "fused_head")) return g_opt.fused_head;
   if (!strcmp(name, "tc_grouped_wgrad")) return g_opt.tc_grouped_wgrad;
+  if (!strcmp(name, "tc_merged_wgrad")) return g_opt.tc_merged_wgrad;
+  if (!strcmp(name, "decode_chain")) return g_opt.decode_chain;
   if (!strcmp(name, "tc_pair_cluster")) return g_opt.tc_pair_cluster;
   if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;
@@ -1628,6 +1680,84 @@ int psvae_consistency_forward(const psvae_consistency_desc* cons, const float* c
   return cons_forward(cons, cons_params, x, rows, w, logits, static_cast<cudaStream_t>(stream));
 }
 
+// scratch of the stand-alone EmbeddingClassifier step on top of the forward / input-gradient chain (plan_cons): split-K and bias partials
+struct EmbClfBufs {
+  float *wpart = nullptr, *cpart = nullptr;
+};
+static void plan_embclf(const psvae_consistency_desc* c, int64_t rows, Bump& b, EmbClfBufs& w) {
+  int64_t wmax = 0;
+  const int64_t outs[3] = {c->hidden_dim, c->hidden_dim, c->num_classes}, ins[3] = {c->input_dim, c->hidden_dim, c->hidden_dim};
+  for (int j = 0; j < 3; ++j) {
+    const int64_t sp = Engine<float>::wgrad_splits(outs[j], ins[j], rows);
+    if (sp * outs[j] * ins[j] > wmax) wmax = sp * outs[j] * ins[j];
+  }
+  w.wpart = b.take<float>(wmax);
+  const int64_t cmax = c->hidden_dim > c->num_classes ? c->hidden_dim : c->num_classes;
+  w.cpart = b.take<float>(ceil_div64(rows, g_opt.colsum_rows) * cmax);
+}
+
+int64_t psvae_embedding_classifier_workspace_bytes(const psvae_consistency_desc* cons, int64_t rows) {
+  if (check_cons(cons) != 0) return -1;
+  if (rows <= 0) { set_error("bad rows"); return -1; }
+  Bump b(nullptr);
+  ConsBufs w;
+  EmbClfBufs e;
+  plan_cons(cons, rows, true, b, w);
+  plan_embclf(cons, rows, b, e);
+  return b.used + 256;
+}
+
+int psvae_embedding_classifier_step(const psvae_consistency_desc* cons, const float* params, float* grads, const float* x, const int64_t* y, int64_t rows,
+                                    int32_t compute_grads, float* logits_out, float* losses, void* workspace, int64_t workspace_bytes, void* stream) {
+  PSVAE_TRY(tc_device_check());
+  PSVAE_TRY(check_cons(cons));
+  if (rows <= 0) { set_error("rows=%lld must be positive", (long long)rows); return -2; }
+  if (!params || !x || !y || !losses) { set_error("params, x, y and losses must not be NULL"); return -1; }
+  if (compute_grads && !grads) { set_error("grads must not be NULL when compute_grads != 0"); return -1; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  ConsBufs w;
+  EmbClfBufs e;
+  {
+    Bump sz(nullptr);
+    ConsBufs t1;
+    EmbClfBufs t2;
+    plan_cons(cons, rows, true, sz, t1);
+    plan_embclf(cons, rows, sz, t2);
+    if (sz.used > workspace_bytes || !workspace) {
+      set_error("workspace too small: need %lld bytes, got %lld", (long long)sz.used, (long long)workspace_bytes);
+      return -2;
+    }
+    Bump b(workspace);
+    plan_cons(cons, rows, true, b, w);
+    plan_embclf(cons, rows, b, e);
+  }
+  const int Dm = cons->input_dim, Hm = cons->hidden_dim, C = cons->num_classes;
+  PSVAE_TRY(cons_forward(cons, params, x, rows, w, w.logits, st));
+  if (logits_out) PSVAE_CUDA(cudaMemcpyAsync(logits_out, w.logits, (size_t)rows * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  // CrossEntropyLoss (mean) + multiclass accuracy; logits become d loss / d logits in place
+  launch_dep(ce_kernel, dim3((unsigned)w.n_ce), dim3(256), 0, st, w.logits, y, rows, C, 1.f / (float)rows, compute_grads ? 1 : 0, w.nll_part, w.acc_part);
+  count_launch();
+  PSVAE_LAUNCH_CHECK("ce_kernel");
+  LossPartials lp;
+  memset(&lp, 0, sizeof(lp));
+  lp.inv_b = 1.f / (float)rows;
+  lp.cons_nll = w.nll_part; lp.cons_acc = w.acc_part; lp.n_cons = (int)w.n_ce; lp.cons_w = 1.f;
+  launch_dep(finalize_losses_kernel, dim3(1), dim3(1024), 0, st, lp, losses);      // losses[0] = losses[12] = CE, losses[13] = accuracy
+  count_launch();
+  PSVAE_LAUNCH_CHECK("finalize_losses_kernel");
+  if (!compute_grads) return 0;
+  PSVAE_CUDA(cudaMemsetAsync(grads, 0, (size_t)cons->total_numel * sizeof(float), st));
+  StepBufs<float> sb;
+  sb.wpart = e.wpart; sb.cpart = e.cpart;
+  // fc3, then back through the two ReLU layers (embedding_classifier.py:50-62 under autograd)
+  PSVAE_TRY(wgrad_clf<float>(w.logits, C, w.a2, Hm, rows, C, Hm, grads + cons->w[2], grads + cons->b[2], sb, st));
+  PSVAE_TRY(clf_dgrad(ACT_RELU, w.logits, C, params + cons->w[2], Hm, w.a2, w.g2, 0.f, rows, st));
+  PSVAE_TRY(wgrad_clf<float>(w.g2, Hm, w.a1, Hm, rows, Hm, Hm, grads + cons->w[1], grads + cons->b[1], sb, st));
+  PSVAE_TRY(clf_dgrad(ACT_RELU, w.g2, Hm, params + cons->w[1], Hm, w.a1, w.g1, 0.f, rows, st));
+  PSVAE_TRY(wgrad_clf<float>(w.g1, Hm, x, Dm, rows, Hm, Dm, grads + cons->w[0], grads + cons->b[0], sb, st));
+  return 0;
+}
+
 int psvae_train_fwd_bwd_consistency(const psvae_model_desc* desc, const float* params, const void* shadow_bf16, float* grads, const void* x, int32_t x_dtype,
                                     const int64_t* y, const float* eps, uint64_t seed, uint64_t offset, int64_t row0, int64_t rows, float kl_weight,
                                     float clf_weight, int32_t use_cos_loss, int32_t compute_grads, int32_t precision, float* x_hat, float* mu,
@@ -1675,7 +1805,8 @@ int psvae_decode(const psvae_model_desc* desc, const float* params, const void* 
 
 int psvae_langevin(const psvae_model_desc* desc, const float* params, float* z_io, int64_t rows, const int32_t* targets_host, float step_size,
                    int32_t num_steps, float noise_weight, uint64_t seed, uint64_t offset0, int64_t row0, int32_t init_from_philox,
-                   const float* noise, float* history, float* stats, void* stream) {
+                   const float* noise, float* history, float* stats, float prior_weight, float threshold, int32_t* stop_step, float* last_prob,
+                   void* stream) {
   PSVAE_TRY(check_desc(desc, PSVAE_FP32));
   PSVAE_TRY(tc_device_check());
   if (!params || !z_io || !targets_host) { set_error("params, z_io, targets must not be NULL"); return -1; }
@@ -1714,9 +1845,9 @@ int psvae_langevin(const psvae_model_desc* desc, const float* params, float* z_i
   if (c.n_trunk == 0 && targeted_classes <= CLF_LG_MAXC && (n.L == 16 || n.L == 32 || n.L == 64) && !g_opt.langevin_generic) {
     const unsigned gridf = (unsigned)ceil_div64(rows, LGF_THREADS);
     switch (n.L) {
-      case 16: launch_dep(langevin_fast_kernel<16>, dim3(gridf), dim3(LGF_THREADS), 0, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
-      case 32: launch_dep(langevin_fast_kernel<32>, dim3(gridf), dim3(LGF_THREADS), 0, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
-      default: launch_dep(langevin_fast_kernel<64>, dim3(gridf), dim3(LGF_THREADS), 0, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats); break;
+      case 16: launch_dep(langevin_fast_kernel<16>, dim3(gridf), dim3(LGF_THREADS), 0, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats, prior_weight, threshold, stop_step, last_prob); break;
+      case 32: launch_dep(langevin_fast_kernel<32>, dim3(gridf), dim3(LGF_THREADS), 0, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats, prior_weight, threshold, stop_step, last_prob); break;
+      default: launch_dep(langevin_fast_kernel<64>, dim3(gridf), dim3(LGF_THREADS), 0, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox, noise, history, stats, prior_weight, threshold, stop_step, last_prob); break;
     }
     count_launch();
     PSVAE_LAUNCH_CHECK("langevin_fast_kernel");
@@ -1727,7 +1858,7 @@ int psvae_langevin(const psvae_model_desc* desc, const float* params, float* z_i
   PSVAE_CUDA(cudaFuncSetAttribute(langevin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const unsigned grid = (unsigned)ceil_div64(rows, LG_TILE);
   launch_dep(langevin_kernel, dim3(grid), dim3(LG_THREADS), smem, st, c, params, z_io, rows, step_size, num_steps, noise_weight, seed, offset0, row0, init_from_philox,
-                                                  noise, history, stats);
+                                                  noise, history, stats, prior_weight, threshold, stop_step, last_prob);
   count_launch();
   PSVAE_LAUNCH_CHECK("langevin_kernel");
   return 0;

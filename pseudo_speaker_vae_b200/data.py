@@ -233,21 +233,23 @@ class PackedEmbeddingStore(torch.utils.data.Dataset):
         key = str(torch.device(device))
         if key not in self._resident:
             e = self.pin().to(device, non_blocking=False)
-            y = torch.from_numpy(np.ascontiguousarray(self.labels)).to(device) if self.label_names else torch.zeros(1, self.n, dtype=torch.int64, device=device)
+            y = torch.from_numpy(np.array(self.labels)).to(device) if self.label_names else torch.zeros(1, self.n, dtype=torch.int64, device=device)
             self._resident[key] = (e, y)
         return self._resident[key]
 
-    def gather(self, indices: np.ndarray, out_x: torch.Tensor, out_y: Optional[torch.Tensor] = None) -> None:
-        """Rows ``indices`` -> ``out_x[:len]`` ([*, D] in the store's dtype) and ``out_y[:, :len]`` (int64 [n_label_columns, *]), host tensors."""
+    def gather(self, indices: np.ndarray, out_x: Optional[torch.Tensor], out_y: Optional[torch.Tensor] = None) -> None:
+        """Rows ``indices`` -> ``out_x[:len]`` ([*, D] in the store's dtype; None: labels only) and ``out_y[:, :len]`` (int64
+        [n_label_columns, *]), host tensors."""
         k = len(indices)
-        if out_x.dtype != self.torch_dtype:
-            raise TypeError(f"out_x must be {self.torch_dtype} for this store, got {out_x.dtype}")
-        xs = out_x.view(torch.int16).numpy().view(np.uint16) if self.dtype_name == "bf16" else out_x.numpy()
         srt = np.all(indices[1:] == indices[:-1] + 1) if k > 1 else True
-        if srt:                                   # a contiguous run of the store: one memcpy out of the page cache
-            xs[:k] = self.embeddings[indices[0]:indices[0] + k]
-        else:
-            np.take(self.embeddings, indices, axis=0, out=xs[:k])
+        if out_x is not None:
+            if out_x.dtype != self.torch_dtype:
+                raise TypeError(f"out_x must be {self.torch_dtype} for this store, got {out_x.dtype}")
+            xs = out_x.view(torch.int16).numpy().view(np.uint16) if self.dtype_name == "bf16" else out_x.numpy()
+            if srt:                                   # a contiguous run of the store: one memcpy out of the page cache
+                xs[:k] = self.embeddings[indices[0]:indices[0] + k]
+            else:
+                np.take(self.embeddings, indices, axis=0, out=xs[:k])
         if out_y is not None and self.label_names:
             ys = out_y.numpy()
             for c in range(len(self.label_names)):
@@ -372,7 +374,7 @@ class PinnedBatchLoader:
             else:
                 run = k > 0 and pinned is not None and bool(np.all(idx[1:] == idx[:-1] + 1))
                 if run:
-                    self.store.gather(idx, self._hx[slot][:0], self._hy[slot])      # labels only (a few hundred KB)
+                    self.store.gather(idx, None, self._hy[slot])      # labels only (a few hundred KB)
                 else:
                     self.store.gather(idx, self._hx[slot], self._hy[slot])
             with torch.cuda.stream(self._copy_stream):

@@ -243,6 +243,7 @@ class HotPath:
                                 n_trunk, c_hidden, act, heads, single)
         self.arena = ParamArena(self.desc, self._entries())
         self._ws: Dict[torch.device, torch.Tensor] = {}
+        self._ws_need: Dict[Tuple[int, int, int, int], int] = {}      # psvae_workspace_bytes by (rows, precision, mode, options epoch)
         self._losses: Dict[torch.device, torch.Tensor] = {}
         self.seed: Optional[int] = None
         self.offset = 0            # Philox offset: one per stochastic call
@@ -316,9 +317,15 @@ class HotPath:
         return dev
 
     def _workspace(self, dev: torch.device, rows: int, mode: int, extra: int = 0) -> torch.Tensor:
-        need = int(L.lib().psvae_workspace_bytes(self._dref, rows, self.precision, mode))
-        if need < 0:
-            raise ValueError(L.last_error())
+        key = (rows, self.precision, mode, L.OPTIONS_EPOCH)
+        need = self._ws_need.get(key)
+        if need is None:
+            need = int(L.lib().psvae_workspace_bytes(self._dref, rows, self.precision, mode))
+            if need < 0:
+                raise ValueError(L.last_error())
+            if len(self._ws_need) > 64:
+                self._ws_need.clear()
+            self._ws_need[key] = need
         need += extra
         ws = self._ws.get(dev)
         if ws is None or ws.numel() < need:
@@ -541,7 +548,10 @@ class HotPath:
 
     def langevin(self, num_samples: int, classifier_target, step_size: float = 0.01, num_steps: int = 100, noise_weight: float = 1.0,
                  z0: Optional[torch.Tensor] = None, noise: Optional[torch.Tensor] = None, return_history: bool = False, return_stats: bool = False,
-                 row0: Optional[int] = None):
+                 row0: Optional[int] = None, prior_weight: float = 1.0, threshold: float = 0.0, return_stop: bool = False):
+        """The Langevin loop of inference.py:72-103 in one launch.  ``prior_weight`` / ``threshold`` / ``return_stop`` cover the analysis variant
+        (analysis/sample_gender_transformation.py:61-99): the log p(z) term scaled by ``prior_weight``, a sample frozen after the update of the
+        first step whose p(y|z) exceeded ``threshold`` (0 = never); with ``return_stop`` the third result is ``(stats, stop_step, last_prob)``."""
         dev = self._device()
         flat = self.arena.ensure()
         Lz = self.desc.latent_dim
@@ -566,12 +576,16 @@ class HotPath:
         self.offset += num_steps + 1
         hist = torch.empty(num_steps, N, Lz, dtype=torch.float32, device=dev) if return_history else None
         stats = torch.empty(num_steps, 2, dtype=torch.float32, device=dev) if return_stats else None
+        stop = torch.full((N,), int(num_steps), dtype=torch.int32, device=dev) if return_stop else None
+        prob = torch.zeros(N, dtype=torch.float32, device=dev) if return_stop else None
         if N > 0:
             with _on(dev):
                 rc = L.lib().psvae_langevin(self._dref, flat.data_ptr(), z.data_ptr(), N, tarr, float(step_size), int(num_steps), float(noise_weight),
                                             self.seed, off0, self.row0 if row0 is None else row0, init, L.ptr(noise), L.ptr(hist), L.ptr(stats),
-                                            _stream_ptr(dev))
+                                            float(prior_weight), float(threshold), L.ptr(stop), L.ptr(prob), _stream_ptr(dev))
             L.check(rc, "psvae_langevin")
         if stats is not None and N > 0:
             stats = stats / N
+        if return_stop:
+            return z, hist, (stats, stop, prob)
         return z, hist, stats

@@ -87,14 +87,77 @@ def conditional_synthesis(vae_model, num_samples: int, classifier_target: Union[
     return x_hat
 
 
-def save_samples(x_hat: Tensor, save_dir: str) -> List[str]:
-    """Row i -> ``sample_{i}.pt`` (inference.py:154-156)."""
-    os.makedirs(save_dir, exist_ok=True)
+def latent_transformation(vae_model, embeddings: Tensor, classifier_target: Union[int, dict], step_size: float = 0.02, max_steps: int = 10000,
+                          noise_weight: float = 0.0, prior_weight: float = 0.5, threshold: float = 0.95, return_history: bool = False,
+                          noise: Optional[Tensor] = None):
+    """The attribute-transformation loop of analysis/sample_gender_transformation.py:57-99, batched: every embedding is encoded
+    (``_, z, _ = vae_model(embed)``: z = the encoder mean), its latent ascends ``log p(y|z) + prior_weight * log p(z)`` with steps of
+    ``0.5 * step_size**2`` (plus ``step_size * noise_weight * N(0, I)``) and is frozen after the update of the first step whose
+    ``p(y|z)`` exceeded ``threshold`` -- one kernel launch for all samples and all steps instead of a Python loop with two ``.item()`` syncs per
+    step.  Returns ``(x_hat [N, D] cpu, z [N, L] cpu, stop_step [N] cpu int32 (max_steps: never stopped), prob [N] cpu)``, plus the list of
+    per-step latents with ``return_history``."""
+    hot = _hot(vae_model)
+    dev = hot.arena.device
+    with torch.no_grad():
+        _, mu, _ = hot.forward(embeddings.to(dev))
+    z, hist, (_, stop, prob) = hot.langevin(mu.shape[0], classifier_target, step_size, max_steps, noise_weight, z0=mu, noise=noise,
+                                             return_history=return_history, prior_weight=prior_weight, threshold=threshold, return_stop=True)
+    x_hat = hot.decode(z).detach().cpu()
+    out = (x_hat, z.cpu(), stop.cpu(), prob.cpu())
+    if return_history:
+        h = hist.cpu().numpy()
+        return out + ([h[i] for i in range(h.shape[0])],)
+    return out
+
+
+def _write_rows(rows: Tensor, first: int, save_dir: str) -> List[str]:
     paths = []
-    for i, x in enumerate(x_hat):
-        path = os.path.join(save_dir, sample_filename(i))
-        torch.save(x.clone(), path)
+    for j in range(rows.shape[0]):
+        path = os.path.join(save_dir, sample_filename(first + j))
+        torch.save(rows[j].clone(), path)
         paths.append(path)
+    return paths
+
+
+def save_samples(x_hat: Tensor, save_dir: str, workers: int = 0, chunk: int = 4096) -> List[str]:
+    """Row i -> ``sample_{i}.pt`` (inference.py:154-156), file contents identical to the reference's ``torch.save(x, path)``.
+
+    The reference writes one file per row in a serial loop after the whole batch has been copied to the host.  Here a device batch is
+    brought over in chunks of ``chunk`` rows on a copy stream into pinned memory while ``workers`` threads (default: 8, or 0 for the
+    caller's thread when the batch is small) serialise the previous chunk -- the D2H copy, the pickling and the file system calls overlap."""
+    os.makedirs(save_dir, exist_ok=True)
+    n = int(x_hat.shape[0])
+    if workers <= 0:
+        workers = 8 if n >= 256 else 0
+    if workers == 0 and not x_hat.is_cuda:
+        return _write_rows(x_hat, 0, save_dir)
+    from concurrent.futures import ThreadPoolExecutor
+
+    futures = []
+    with ThreadPoolExecutor(max_workers=max(1, workers)) as pool:
+        if x_hat.is_cuda:
+            stream = torch.cuda.Stream(x_hat.device)
+            stream.wait_stream(torch.cuda.current_stream(x_hat.device))
+            for a in range(0, n, chunk):
+                b = min(n, a + chunk)
+                host = torch.empty((b - a,) + tuple(x_hat.shape[1:]), dtype=x_hat.dtype, pin_memory=True)
+                with torch.cuda.stream(stream):
+                    host.copy_(x_hat[a:b], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(stream)
+
+                def job(host=host, a=a, ev=ev):
+                    ev.synchronize()
+                    return _write_rows(host, a, save_dir)
+
+                futures.append(pool.submit(job))
+        else:
+            per = max(1, -(-n // (4 * max(1, workers))))
+            for a in range(0, n, per):
+                futures.append(pool.submit(_write_rows, x_hat[a:a + per], a, save_dir))
+        paths: List[str] = []
+        for f in futures:
+            paths += f.result()
     return paths
 
 

@@ -763,12 +763,14 @@ def test_deterministic_option_and_fast_mode_agree():
         f1, lf = run()
         f2, _ = run()
         assert torch.equal(lf, l1)
+        # fast mode sums 37 split-K partials per weight-gradient tile through TMA reduce-add (the merged wgrad launch) where the
+        # ordered mode sums 2-18 in a fixed tree: fp32 summation order only (measured 6e-6 on the 8192-row layer-0 gradient)
         for f in (f1, f2):
-            assert ((f.double() - g1.double()).norm() / g1.double().norm()).item() <= 1e-6
+            assert ((f.double() - g1.double()).norm() / g1.double().norm()).item() <= 5e-6
         names = G.flat_to_dict(module, f1)
         det = G.flat_to_dict(module, g1)
         for k in names:
-            assert rel_err(names[k], det[k]) <= 2e-6, k
+            assert rel_err(names[k], det[k]) <= 1e-5, k
     finally:
         G.L.set_option("deterministic", 0)
 
@@ -814,18 +816,18 @@ def test_engine_variants_reproduce_the_default_path(opts):
             G.L.set_option(k, v)
 
 
-FAST_VARIANTS_OFF = dict(tc_epi_groups=0, clf_grad_in_bwd=0, fused_head=0, tc_grouped_wgrad=0)
+FAST_VARIANTS_OFF = dict(tc_epi_groups=0, clf_grad_in_bwd=0, fused_head=0, tc_grouped_wgrad=0, tc_merged_wgrad=0)
 
 
-@pytest.mark.parametrize("opts", [dict(tc_epi_groups=1), dict(clf_grad_in_bwd=1), dict(fused_head=1), dict(tc_grouped_wgrad=1),
-                                  dict(tc_epi_groups=1, fused_head=1, tc_grouped_wgrad=1)])
+@pytest.mark.parametrize("opts", [dict(tc_epi_groups=1), dict(clf_grad_in_bwd=1), dict(fused_head=1), dict(tc_grouped_wgrad=1), dict(tc_merged_wgrad=1),
+                                  dict(tc_epi_groups=1, fused_head=1, tc_grouped_wgrad=1, tc_merged_wgrad=1)])
 def test_fast_mode_engine_variants_agree_with_the_plain_path(opts):
     """The fast-mode variants that are ON by default since round 2 (validated on a B200 by tools/validate_experimental.sh, then A/B-timed)
     against the path with all of them off.  tc_epi_groups (two epilogue groups on alternate tiles for the K <= 128 layers): forward outputs
     bit-identical, losses / gradients equal up to summation order.  clf_grad_in_bwd: the classifier's backward formed in the latent backward
     kernel from d loss / d logits.  fused_head: encoder heads + reparameterisation + KL + classifier forward in one kernel (its
     accumulators come from 32-column MMAs: outputs are compared to 1e-5, not bit for bit).  tc_grouped_wgrad: both encoders' hidden-layer
-    wgrads in one launch."""
+    wgrads in one launch.  tc_merged_wgrad: every wgrad of the step in one persistent launch at the end of the backward pass."""
     G = _gu()
     module, cfg = _big_module(G, "bf16")
     hot = module.hot_path

@@ -211,9 +211,10 @@ def test_consistency_classifier_surface(tmp_path):
             P.EmbeddingClassifier(**bad).consistency_desc()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cc(torch.randn(4, 256))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):          # the stand-alone trainer exists (GPU parity: tests/test_gpu_round2.py) and has no CPU path either
         cc.training_step((torch.randn(4, 256), torch.zeros(4, dtype=torch.long)), 0)
     lib = L.lib()
+    assert lib.psvae_embedding_classifier_workspace_bytes(C.byref(d), 1000) > lib.psvae_consistency_workspace_bytes(C.byref(d), 1000, L.MODE_TRAIN)
     assert lib.psvae_consistency_workspace_bytes(C.byref(d), 1000, L.MODE_TRAIN) > lib.psvae_consistency_workspace_bytes(C.byref(d), 1000, L.MODE_FORWARD) > 0
 
 
@@ -371,7 +372,7 @@ def test_batch_loader_order_sharding_and_split(tmp_path):
 def test_engine_option_defaults():
     """The defaults of the engine options: variants validated and A/B-timed on a B200 in round 2 are on (tc_epi_groups, fused_head,
     tc_grouped_wgrad); clf_grad_in_bwd on its own measured slower and stays off (the fused head uses that backward regardless)."""
-    for name, default in (("tc_epi_groups", 1), ("fused_head", 1), ("tc_grouped_wgrad", 1), ("clf_grad_in_bwd", 0), ("tc_grouped", 1), ("pdl", 1),
+    for name, default in (("tc_epi_groups", 1), ("fused_head", 1), ("tc_grouped_wgrad", 1), ("tc_merged_wgrad", 1), ("clf_grad_in_bwd", 0), ("tc_grouped", 1), ("pdl", 1),
                           ("tc_two_cta", 1), ("deterministic", 0)):
         assert L.get_option(name) == default, name
 

@@ -229,3 +229,45 @@ def test_vae_backward_for_a_callers_own_loss_vs_torch_autograd(normalize):
         assert rel_err(g, ref) <= 1e-12, k
     only_mu = O.vae_backward(params, x, eps, None, gm, None, normalize_decoder=normalize)
     assert all(np.abs(v).max() == 0 for k, v in only_mu.items() if "decoder" in k or "encoder_sigma" in k)     # nothing reaches them
+
+
+@pytest.mark.parametrize("name", ["transform_prior_threshold", "transform_noise_c3"])
+def test_latent_transformation_matches_reference_golden(name):
+    """The analysis Langevin variant (analysis/sample_gender_transformation.py:57-99: start from the encoded embedding, PRIOR_WEIGHT,
+    per-sample stop at p(y|z) > THRESHOLD) against fixtures produced by running that loop on the unmodified reference modules."""
+    from tests.golden_util import case_params, load, rel_err
+
+    z, cfg = load(name)
+    for dt, tag, tol in ((np.float64, "f64", 1e-12), (np.float32, "f32", 1e-5)):
+        p = case_params(cfg, dt)
+        _, mu, _, _ = O.vae_forward(p, z["x"].astype(dt), np.zeros((cfg["N"], cfg["L"]), dt))
+        assert rel_err(mu, z[f"{tag}/z_start"]) <= tol
+        zf, stop, prob = O.latent_transformation(p, z[f"{tag}/z_start"].astype(dt), list(z["noises"].astype(dt)), cfg["target"], cfg["step_size"],
+                                                 cfg["noise_weight"], cfg["prior_weight"], cfg["threshold"])
+        assert rel_err(zf, z[f"{tag}/z_final"]) <= tol
+        if dt is np.float64:
+            assert np.array_equal(stop, z[f"{tag}/stop"])
+        assert np.abs(prob - z[f"{tag}/prob"]).max() <= (1e-12 if dt is np.float64 else 1e-5)
+    assert len(set(z["f64/stop"].tolist())) > 1
+
+
+@pytest.mark.parametrize("name", ["embclf_d256_c3", "embclf_d192_c2"])
+def test_embedding_classifier_trainer_matches_reference_golden(name):
+    """The stand-alone EmbeddingClassifier trainer (embedding_classifier.py:64-100) restated: loss, accuracy, logits and the six gradient
+    tensors of step 0 against fixtures from the unmodified module; Adam is pinned separately (adam_cosine.npz)."""
+    from tests.golden_util import load, rel_err
+
+    z, cfg = load(name)
+    p = {k: v.astype(np.float32).astype(np.float64) for k, v in
+         O.synth_params(O.embedding_classifier_param_shapes(cfg["D"], cfg["num_classes"], cfg["hidden_dim"]), seed=cfg["wseed"], dtype=np.float64).items()}
+    x, y, _ = O.synth_batch(cfg["B"], cfg["D"], 64, cfg["num_classes"], seed=cfg["dseed"])
+    scal, logits, g = O.embedding_classifier_loss_and_grads(p, x.astype(np.float64), y)
+    assert abs(float(scal["loss"]) - float(z["f64/step0/log/train_loss"])) <= 1e-12
+    assert abs(float(scal["acc"]) - float(z["f64/step0/log/train_acc"])) <= 1e-7
+    for k, v in g.items():
+        assert rel_err(v, z[f"f64/step0/grad/{k}"]) <= 1e-10, k
+    # one Adam step with the module's own optimizer settings reproduces the post-step parameters
+    opt = dict(cfg["optimizer"])
+    for k in g:
+        new, _, _ = O.adam_step(p[k], g[k], np.zeros_like(p[k]), np.zeros_like(p[k]), 1, lr=opt.get("lr", 1e-3), weight_decay=opt.get("weight_decay", 0.0))
+        assert rel_err(new, z[f"f64/step0/param/{k}"]) <= 1e-10, k
