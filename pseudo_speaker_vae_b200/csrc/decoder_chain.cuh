@@ -13,6 +13,12 @@
 //   L1  chunk c = 0..NC-1      acc[c & 1]  = hd0 (K = H) x W1[c]                                H/64 B each
 //   L2  after L1(c), c >= 1:   out        += hd1 chunk c-1 (2 K-blocks) x W2[:, chunk c-1]      4 B each;   L2(NC-1) after the loop
 // so that the epilogue of one chunk always runs under the MMAs of the next.  TMEM: acc[2] = 2 x 128 columns, out = 256 columns.
+//
+// TRAIN = true is the decoder half of the training forward pass (ps_vae/model.py:58 + the reconstruction term of ps_vae/lightning.py:113) on
+// the same schedule: z arrives in bf16 from the fused encoder-head kernel, every hidden K-block is ALSO written to HBM straight out of its
+// operand buffer by TMA (the backward pass needs the activations: wgrad operands) together with its 1-bit ReLU mask, and the output phase
+// does what EpiMse does -- bias, sum of squared errors, d x_hat = 2 (x_hat - x) / (B D 10) in bf16 by TMA store, its column sums (= the bias
+// gradient of the last layer) -- instead of storing x_hat.  The hidden activations are written once and never read back in the forward pass.
 #pragma once
 #include <cuda.h>
 
@@ -48,14 +54,27 @@ struct DcArgs {
   uint64_t seed, offset;
   int64_t first_row;      // Philox element index = (first_row + r) * 64 + c: independent of how the rows are sharded
   unsigned long long* trace;   // profiling (option "tc_trace_ptr"): per CTA 16 cycle counters, see tools/chain_trace.py; nullptr = off
+  // ---- TRAIN
+  const bf16* z16;        // z [rows][64] bf16 (written by the fused encoder head)
+  uint32_t* mask0;        // ReLU bit masks of the two hidden layers, [H/32][mask_ld]
+  uint32_t* mask1;
+  int64_t mask_ld;
+  const void* x;          // reconstruction target [rows][D], fp32 or (x_bf16) bf16
+  int32_t x_bf16;
+  float scale;            // 2 / (B * D * 10)
+  float* sse_part;        // [CTAs]: sum of squared errors
+  float* bias_grad;       // [D]: += column sums of d x_hat (atomics into the zeroed gradient)
 };
 
 __device__ __forceinline__ uint32_t dc_swz128(int r, int j) { return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4)); }
 __device__ __forceinline__ uint32_t dc_swz64(int r, int j) { return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4)); }
 
+template <bool TRAIN, bool TRACE>
 __global__ void __launch_bounds__(DC_THREADS, 1)
 decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1, const __grid_constant__ CUtensorMap tm_w2,
-                     const __grid_constant__ CUtensorMap tm_out, DcArgs a) {
+                     const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_hd0, const __grid_constant__ CUtensorMap tm_hd1,
+                     DcArgs a) {
+  // tm_out: sampling: x_hat fp32 [rows][D], box 16 x 32;  TRAIN: d x_hat bf16 [rows][D], box 32 x 32.  tm_hd0 / tm_hd1 (TRAIN): [rows][H] bf16, box 64 x 32
   extern __shared__ uint8_t dc_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(dc_smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
   const int KB = a.H / DC_BK;            // K-blocks of a hidden layer
@@ -74,6 +93,7 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
   uint64_t* out_full = hd1_empty + 1;            // output accumulator complete (both CTAs)
   uint64_t* out_empty = out_full + 1;            // output accumulator drained (leader; 2 x 16 warps)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(out_empty + 1);
+  float* red_smem = reinterpret_cast<float*>(smem + 512);      // [DC_EPI_WARPS]: per-warp sums of squared errors (TRAIN)
   uint8_t* const hd0 = smem + DC_BAR_BYTES;
   uint8_t* const hd1 = hd0 + KB * DC_KBLOCK_BYTES;
   uint8_t* const zbuf = hd1 + 2 * DC_KBLOCK_BYTES;
@@ -116,11 +136,11 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
   // shared::cluster address of a barrier in the leader CTA (remote arrive)
   auto lead = [&](uint64_t* bar) { return ptx::mapa_u32(ptx::smem_u32(bar), 0u); };
   // profiling: cycles a role spent inside each class of barrier wait (slot = class), written by lane 0 of the MMA warp / epilogue warp 2 / z warp
-  const bool tracing = a.trace != nullptr;
-  long long tw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  constexpr bool tracing = TRACE;          // a template parameter: the counters cost 16 registers the product instantiation does not have
+  long long tw[TRACE ? 8 : 1] = {};
   const long long t_begin = tracing ? clock64() : 0;
   auto wait = [&](uint64_t* bar, uint32_t parity, int tag, int slot) {
-    if (tracing) {
+    if constexpr (TRACE) {
       const long long t0 = clock64();
       ptx::mbar_wait(bar, parity, tag);
       tw[slot] += clock64() - t0;
@@ -238,6 +258,8 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
     const int cg = ew >> 2;                    // 32-column group of the 128-column chunk
     const int r_in = quarter * 32 + lane;      // row inside this CTA's 128
     uint32_t chunk_n = 0, l1_n = 0, tile_n = 0;
+    float sse = 0.f;                           // TRAIN: this thread's share of the sum of squared errors
+    float cs_acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};   // TRAIN: column sums of d x_hat, this lane's two columns of each 32-column block
     // Output staging: 32 rows x 16 fp32 (64-byte rows, 2 KB).  It lives inside the 4 KB of the hd1 chunk that this warp and its partner
     // (same lane quarter, the other 32-column group of the same K-block) are the only writers of, so the only cross-warp ordering the
     // region needs is between those two: a 64-thread named barrier before the next tile's first hd1 write.
@@ -266,12 +288,22 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
             dst = hd0 + (c * 2 + (cg >> 1)) * DC_KBLOCK_BYTES;
           } else {
             wait(hd1_empty, (l1_n & 1) ^ 1, 12, 2);                    // the previous chunk's L2 MMAs have read hd1
-            if (c == 0) {                                                      // ... and the pair's output stores have read their staging blocks
-              if (lane == 0) ptx::bulk_wait_read0();
-              __syncwarp();
-              asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
-            }
             dst = hd1 + (cg >> 1) * DC_KBLOCK_BYTES;
+          }
+          // the pair's TMA stores out of the region about to be rewritten (TRAIN: the activation write-out of the K-block's previous
+          // use; sampling: the output staging blocks, which alias the hd1 chunk) have finished reading it
+          if (TRAIN || (layer == 1 && c == 0)) {
+            if (lane == 0) ptx::bulk_wait_read0();
+            __syncwarp();
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+          }
+          if constexpr (TRAIN) {
+            // 1-bit ReLU mask of this warp's 32 columns, one word per row: what the backward pass multiplies the gradient with
+            uint32_t bits = 0;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) bits |= ((__uint_as_float(r[i]) + bv[i]) > 0.f ? 1u : 0u) << i;
+            const int64_t grow = (int64_t)row_base + lane;
+            if (grow < a.rows) (layer == 0 ? a.mask0 : a.mask1)[(int64_t)(c * 4 + cg) * a.mask_ld + grow] = bits;
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -284,6 +316,14 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
           }
           ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
           __syncwarp();
+          if constexpr (TRAIN) {
+            // both halves of the 128-byte rows are in place: one TMA store of the pair's [32 rows x 64 columns] writes the activation out
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+            if ((cg & 1) == 0 && lane == 0) {
+              ptx::tma_store_2d(layer == 0 ? &tm_hd0 : &tm_hd1, dst + quarter * 4096, (c * 2 + (cg >> 1)) * DC_BK, row_base);
+              ptx::bulk_commit();
+            }
+          }
           if (lane == 0) ptx::mbar_arrive_cluster(lead(layer == 0 ? &hd0_ready[c * 2 + (cg >> 1)] : &hd1_ready[cg >> 1]));
           if (layer == 1) ++l1_n;
         }
@@ -292,6 +332,87 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
       wait(out_full, tile_n & 1, 13, 3);
       ptx::tc_fence_after();
       const int ocg = ew >> 2;                   // 64-column group of the output
+      if constexpr (TRAIN) {
+        // the staging block aliases the hd1 chunk region whose write-out the pair's issuer may still be reading
+        if (lane == 0) ptx::bulk_wait_read0();
+        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
+        const int64_t grow = (int64_t)row_base + lane;
+        const bool valid = grow < a.rows;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int col0 = ocg * 64 + half * 32;
+          if (col0 >= a.D) continue;             // warp-uniform
+          uint32_t r[32];
+          ptx::tmem_ld_32x32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(256 + col0), r);
+          // the target tile: a bf16 batch is fetched NOW, packed (16 registers), so that its latency hides under the accumulator read; an fp32
+          // batch is read 8 columns at a time inside the loop (the slower path: 32 more registers would spill)
+          const bool full = valid && col0 + 32 <= a.D;
+          uint4 xq[4] = {make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u), make_uint4(0u, 0u, 0u, 0u)};
+          if (full && a.x_bf16) {
+            const uint4* xp = reinterpret_cast<const uint4*>(static_cast<const bf16*>(a.x) + grow * a.D + col0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xq[j] = __ldg(xp + j);
+          }
+          ptx::tmem_ld_wait(r);
+          if (lane == 0) ptx::bulk_wait_read0();
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float xv[8];
+            if (full && a.x_bf16) {
+              const uint32_t wv[4] = {xq[j].x, xq[j].y, xq[j].z, xq[j].w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                xv[2 * q] = __uint_as_float(wv[q] << 16);
+                xv[2 * q + 1] = __uint_as_float(wv[q] & 0xFFFF0000u);
+              }
+            } else if (full) {
+              load_vec<8>(static_cast<const float*>(a.x) + grow * a.D + col0 + 8 * j, xv);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int cc = col0 + 8 * j + i;
+                xv[i] = 0.f;
+                if (valid && cc < a.D) xv[i] = a.x_bf16 ? __bfloat162float(static_cast<const bf16*>(a.x)[grow * a.D + cc]) : static_cast<const float*>(a.x)[grow * a.D + cc];
+              }
+            }
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int cc = col0 + 8 * j + i;
+              const bool in = valid && cc < a.D;
+              const float dd = in ? (__uint_as_float(r[8 * j + i]) + __ldg(a.b2 + min(cc, a.D - 1)) - xv[i]) : 0.f;
+              sse = fmaf(dd, dd, sse);
+              o[i] = dd * a.scale;
+            }
+            uint4 u;
+            u.x = pack_bf16x2(o[0], o[1]); u.y = pack_bf16x2(o[2], o[3]); u.z = pack_bf16x2(o[4], o[5]); u.w = pack_bf16x2(o[6], o[7]);
+            *reinterpret_cast<uint4*>(stage_out + dc_swz64(lane, j)) = u;
+          }
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          {   // column sums of the ROUNDED gradient (= bias gradient of the last layer): lanes 0-15 walk the even rows, 16-31 the odd rows
+            const int hw = lane >> 4, w2 = lane & 15;
+            float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 16; ++rr) {
+              const int row = 2 * rr + hw;
+              const uint32_t u = *reinterpret_cast<const uint32_t*>(stage_out + dc_swz64(row, w2 >> 2) + (w2 & 3) * 4);
+              s0 += __uint_as_float(u << 16);
+              s1 += __uint_as_float(u & 0xFFFF0000u);
+            }
+            s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+            s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+            cs_acc[half][0] += s0;
+            cs_acc[half][1] += s1;
+          }
+          if (lane == 0) {
+            ptx::tma_store_2d(&tm_out, stage_out, col0, row_base);
+            ptx::bulk_commit();
+          }
+        }
+      } else {
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int col0 = ocg * 64 + half * 32;
@@ -322,9 +443,27 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
           }
         }
       }
+      }
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(lead(out_empty));
+    }
+    if constexpr (TRAIN) {
+      // bias gradient of the last layer: this warp always owned the same 64 output columns
+      if (lane < 16) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int col = (ew >> 2) * 64 + half * 32 + 2 * lane;
+          if (col + 1 < a.D) {
+            atomicAdd(a.bias_grad + col, cs_acc[half][0]);
+            atomicAdd(a.bias_grad + col + 1, cs_acc[half][1]);
+          } else if (col < a.D) {
+            atomicAdd(a.bias_grad + col, cs_acc[half][0]);
+          }
+        }
+      }
+      const float ws = warp_sum(sse);
+      if (lane == 0) red_smem[ew] = ws;
     }
     if (lane == 0) ptx::bulk_wait_all();
   } else {
@@ -341,6 +480,12 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
         const uint64_t q0 = (uint64_t)(a.first_row + row) * (DC_L / 4);
 #pragma unroll 1
         for (int j = 0; j < DC_L / 8; ++j) {
+          if constexpr (TRAIN) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) u = __ldg(reinterpret_cast<const uint4*>(a.z16 + row * DC_L + 8 * j));
+            *reinterpret_cast<uint4*>(zbuf + dc_swz128(zr, j)) = u;
+            continue;
+          }
           float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
           if (valid) {
             if (a.z_in) {
@@ -367,7 +512,7 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
   }
 
   // ============================ teardown ============================
-  if (tracing && lane == 0) {
+  if constexpr (TRACE) if (lane == 0) {
     unsigned long long* t = a.trace + (size_t)blockIdx.x * 24;
     const long long total = clock64() - t_begin;
     // MMA warp: [0] total, [1] weights, [2] acc_empty, [3] hd0_ready, [4] hd1_ready, [5] out_empty, [6] z_full
@@ -380,6 +525,13 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
   }
   ptx::tc_fence_before();
   ptx::cluster_sync();               // neither CTA may retire while the pair's MMAs / remote arrives can still touch it
+  if constexpr (TRAIN) {
+    if (threadIdx.x == 0) {          // fixed order: the loss is reproducible for a given grid
+      float t = 0.f;
+      for (int w = 0; w < DC_EPI_WARPS; ++w) t += red_smem[w];
+      a.sse_part[blockIdx.x] = t;
+    }
+  }
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_cg2(tmem_base, 512);
@@ -400,29 +552,42 @@ static inline bool decoder_chain_ok(int D, int L, int H, int num_hidden) {
   return num_hidden == 2 && L == DC_L && H % DC_CHUNK == 0 && H >= DC_CHUNK && H <= DC_MAX_H && D % 16 == 0 && D >= 16 && D <= 256;
 }
 
-// W0 [H][64], W1 [H][H], W2 [D][H]: bf16, row-major (the shadow copy of the parameter arena); out [rows][D] fp32
-static inline int decoder_chain_launch(const bf16* W0, const bf16* W1, const bf16* W2, float* out, const DcArgs& a, cudaStream_t st) {
-  CUtensorMap t0, t1, t2, to;
+// W0 [H][64], W1 [H][H], W2 [D][H]: bf16, row-major (the shadow copy of the parameter arena).  Sampling: out = x_hat [rows][D] fp32.
+// TRAIN: out = d x_hat [rows][D] bf16, hd0 / hd1 = the hidden activations [rows][H] bf16 (written for the backward pass).  *ctas = CTAs launched
+// (= sum-of-squared-error partials written to a.sse_part).
+template <bool TRAIN>
+static inline int decoder_chain_launch(const bf16* W0, const bf16* W1, const bf16* W2, void* out, bf16* hd0, bf16* hd1, const DcArgs& a, cudaStream_t st,
+                                       int* ctas = nullptr) {
+  CUtensorMap t0, t1, t2, to, th0, th1;
   TcOperand o0{W0, (int64_t)a.H, (int64_t)DC_L, false};
   TcOperand o1{W1, (int64_t)a.H, (int64_t)a.H, false};
   TcOperand o2{W2, (int64_t)a.D, (int64_t)a.H, false};
   PSVAE_TRY(tc_tensor_map(o0, DC_L, 64, &t0));
   PSVAE_TRY(tc_tensor_map(o1, a.H, 64, &t1));
   PSVAE_TRY(tc_tensor_map(o2, a.H, 64, &t2));
-  PSVAE_TRY(tc_block_map(out, 4, a.rows, a.D, a.D, 0, 0, &to, 16));
+  if constexpr (TRAIN) {
+    PSVAE_TRY(tc_block_map(out, 2, a.rows, a.D, a.D, 0, 0, &to, 32));
+    PSVAE_TRY(tc_block_map(hd0, 2, a.rows, a.H, a.H, 0, 0, &th0, 64));
+    PSVAE_TRY(tc_block_map(hd1, 2, a.rows, a.H, a.H, 0, 0, &th1, 64));
+  } else {
+    PSVAE_TRY(tc_block_map(out, 4, a.rows, a.D, a.D, 0, 0, &to, 16));
+    th0 = to;
+    th1 = to;
+  }
   const int smem = dc_smem_bytes(a.H);
-  static unsigned long long attr_mask = 0;
+  auto kern = a.trace ? decoder_chain_kernel<TRAIN, true> : decoder_chain_kernel<TRAIN, false>;
+  static unsigned long long attr_mask[2] = {0, 0};
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
-  if (!(attr_mask >> (dev & 63) & 1ull)) {
-    PSVAE_CUDA(cudaFuncSetAttribute(decoder_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DC_BAR_BYTES + (DC_MAX_H / DC_BK + 3) * DC_KBLOCK_BYTES +
-                                                                                                        DC_STAGES * DC_STAGE_BYTES + 1024));
-    attr_mask |= 1ull << (dev & 63);
+  if (!(attr_mask[a.trace ? 1 : 0] >> (dev & 63) & 1ull)) {
+    PSVAE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dc_smem_bytes(DC_MAX_H)));
+    attr_mask[a.trace ? 1 : 0] |= 1ull << (dev & 63);
   }
   const int64_t tiles = (a.rows + 2 * DC_ROWS - 1) / (2 * DC_ROWS);
   int64_t pairs = tc_grid_size() / 2;
   if (tiles < pairs) pairs = tiles;
   if (pairs < 1) return 0;
+  if (ctas) *ctas = (int)(2 * pairs);
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((unsigned)(2 * pairs));
@@ -441,7 +606,7 @@ static inline int decoder_chain_launch(const bf16* W0, const bf16* W1, const bf1
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  PSVAE_CUDA(cudaLaunchKernelEx(&cfg, decoder_chain_kernel, t0, t1, t2, to, a));
+  PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, t0, t1, t2, to, th0, th1, a));
   count_launch();
   PSVAE_LAUNCH_CHECK("decoder_chain_kernel");
   return 0;

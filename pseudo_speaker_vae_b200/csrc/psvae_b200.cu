@@ -80,6 +80,8 @@ struct Options {
                                        //    the ~8 us fixed cost of a wgrad launch is paid once instead of 8 times
   int64_t decode_chain = 0;            // 1 (tcgen05 mode, two hidden layers <= 512 wide, latent 64, <= 256 outputs, no normalize_decoder): psvae_decode runs the chained
                                        //    decoder kernel (decoder_chain.cuh): z from Philox in-kernel, hidden activations on-chip, one launch for all rows
+  int64_t train_chain = 0;             // 1 (training, fast tcgen05 mode, decoder_chain_ok shapes, plain MSE tail, x_hat not requested): the decoder half of the forward pass
+                                       //    (dec L0 -> L1 -> last + MSE) runs as ONE chained kernel (decoder_chain.cuh, TRAIN): hidden activations written once, never re-read
   int64_t tc_grouped = 1;              // 1: layers 1..n of the two encoders run as ONE block-diagonal launch each (forward and dgrad) instead of one per encoder
   int64_t pdl = 1;                     // 1: kernels are launched with programmatic stream serialization (their prologue overlaps the predecessor's tail)
   int64_t tc_trace_ptr = 0;            // profiling: device pointer of gridDim.x * 16 cycle counters the GEMM kernels fill (0 = off)
@@ -1013,8 +1015,30 @@ static int run_step(const StepArgs& a) {
   if (a.want_loss && !general_tail) {
     const float scale = 2.f / ((float)B * (float)n.D * 10.f);
     bool launched = false;
+    int chain_ctas = 0;
     if constexpr (sizeof(TAct) == 2) {
-      if (a.want_grads && tc_colsum_ok(n.D)) {     // + column sums of dxh = bias gradient of the last decoder layer
+      // option train_chain: the whole decoder + MSE epilogue as one chained kernel (hidden activations stay on-chip for the forward pass)
+      if (g_opt.train_chain && a.want_grads && !g_opt.deterministic && !a.x_hat && decoder_chain_ok(n.D, n.L, n.H, n.nh) && w.mhd[0] && w.mhd[1]) {
+        DcArgs ca;
+        memset(&ca, 0, sizeof(ca));
+        ca.rows = B; ca.H = n.H; ca.D = n.D;
+        ca.b0 = P + d->dec_b[0]; ca.b1 = P + d->dec_b[1]; ca.b2 = P + d->dec_b[2];
+        ca.trace = tc_trace_ptr();
+        ca.z16 = w.z;
+        ca.mask0 = w.mhd[0]; ca.mask1 = w.mhd[1]; ca.mask_ld = B;
+        ca.x = a.x16 ? static_cast<const void*>(a.x16) : static_cast<const void*>(a.x);
+        ca.x_bf16 = a.x16 ? 1 : 0;
+        ca.scale = scale;
+        ca.sse_part = w.sse_part;
+        ca.bias_grad = a.grads + d->dec_b[n.nh];
+        int ctas = 0;
+        PSVAE_TRY(decoder_chain_launch<true>(Wt + d->dec_w[0], Wt + d->dec_w[1], Wt + d->dec_w[2], w.dxh, w.hd[0], w.hd[1], ca, st, &ctas));
+        launched = dec_last_bias_done = true;
+        chain_ctas = ctas;
+      }
+    }
+    if constexpr (sizeof(TAct) == 2) {
+      if (!launched && a.want_grads && tc_colsum_ok(n.D)) {     // + column sums of dxh = bias gradient of the last decoder layer
         const bool atomic = !g_opt.deterministic;
         if (a.x16) {
           EpiMse<TAct, true, bf16> e{P + d->dec_b[n.nh], a.x16, n.D, a.x_hat, n.D, w.dxh, n.D, scale, w.sse_part, atomic ? a.grads + d->dec_b[n.nh] : w.cpart,
@@ -1038,7 +1062,7 @@ static int run_step(const StepArgs& a) {
       EpiMse<TAct> e{P + d->dec_b[n.nh], a.x, n.D, a.x_hat, n.D, a.want_grads ? w.dxh : nullptr, n.D, scale, w.sse_part, nullptr, 0};
       PSVAE_TRY(decoder_forward<TAct>(n, Wt, P, w.z, w.hd, B, e, st, (a.want_grads && w.mhd[0]) ? w.mhd : nullptr));
     }
-    n_sse_used = sizeof(TAct) == 2 ? (int)tc_ctas(B, n.D, 1, (int)g_opt.tc_force_bn) : (int)sgemm_red_slots(B, n.D);   // one slot per CTA / per tile
+    n_sse_used = chain_ctas > 0 ? chain_ctas : (sizeof(TAct) == 2 ? (int)tc_ctas(B, n.D, 1, (int)g_opt.tc_force_bn) : (int)sgemm_red_slots(B, n.D));   // one slot per CTA / per tile
     if (dec_last_bias_reduce) PSVAE_TRY(launch_reduce(w.cpart, n.D, n_sse_used * 4, a.grads + d->dec_b[n.nh], st));
   } else {
     float* u = general_tail ? w.u : (a.x_hat ? a.x_hat : w.u);
@@ -1329,7 +1353,7 @@ static int run_decode(const psvae_model_desc* d, const float* params, const bf16
       a.z_in = z; a.z_out = (z_out && z_out != z) ? z_out : nullptr;
       a.seed = seed; a.offset = offset; a.first_row = row0;
       a.trace = tc_trace_ptr();
-      return decoder_chain_launch(shadow + d->dec_w[0], shadow + d->dec_w[1], shadow + d->dec_w[2], x_hat, a, st);
+      return decoder_chain_launch<false>(shadow + d->dec_w[0], shadow + d->dec_w[1], shadow + d->dec_w[2], x_hat, nullptr, nullptr, a, st);
     }
   }
   const int64_t chunk = rows < g_opt.decode_chunk ? rows : g_opt.decode_chunk;
@@ -1434,6 +1458,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_grouped_wgrad")) { g_opt.tc_grouped_wgrad = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_merged_wgrad")) { g_opt.tc_merged_wgrad = value ? 1 : 0; return 0; }
   if (!strcmp(name, "decode_chain")) { g_opt.decode_chain = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "train_chain")) { g_opt.train_chain = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_pair_cluster")) { g_opt.tc_pair_cluster = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
@@ -1462,6 +1487,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_grouped_wgrad")) return g_opt.tc_grouped_wgrad;
   if (!strcmp(name, "tc_merged_wgrad")) return g_opt.tc_merged_wgrad;
   if (!strcmp(name, "decode_chain")) return g_opt.decode_chain;
+  if (!strcmp(name, "train_chain")) return g_opt.train_chain;
   if (!strcmp(name, "tc_pair_cluster")) return g_opt.tc_pair_cluster;
   if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;

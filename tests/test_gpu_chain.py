@@ -89,3 +89,49 @@ def test_chained_decoder_shards_are_bit_identical():
     finally:
         G.L.set_option("decode_chain", 0)
     assert torch.equal(torch.cat(parts), full)
+
+
+@pytest.mark.parametrize("B", [300, 256 * 74 * 2 + 77, 65536])
+@pytest.mark.parametrize("xdt", ["fp32", "bf16"])
+def test_train_chain_matches_layer_by_layer_step(B, xdt):
+    """Option train_chain: the decoder half of the training forward pass as one chained kernel (decoder_chain.cuh, TRAIN) against the per-layer
+    GEMM path: same losses (fp32 summation order), same gradients, and -- at the small batch -- the bf16-emulating twin."""
+    G = _gu()
+    from oracle import bf16_twin as T
+
+    cfg = dict(D=256, L=64, wseed=3, clf=dict(input_dim=64, num_classes=2))
+    module = G.module_from_cfg(cfg, "bf16")
+    hot = module.hot_path
+    x, y, eps = O.synth_batch(B, 256, 64, 2, seed=31)
+    xt = torch.from_numpy(x).to(G.DEV)
+    if xdt == "bf16":
+        xt = xt.to(torch.bfloat16)
+    yt, et = torch.from_numpy(y).to(G.DEV), torch.from_numpy(eps).to(G.DEV)
+
+    def run():
+        g = torch.empty(hot.arena.numel, device=G.DEV)
+        losses, _, _ = hot.step(xt, yt, et, grads=g)
+        torch.cuda.synchronize()
+        return g, losses
+
+    try:
+        G.L.set_option("train_chain", 0)
+        g0, l0 = run()
+        G.L.set_option("train_chain", 1)
+        n0 = G.L.lib().psvae_launch_count()
+        g1, l1 = run()
+        n1 = G.L.lib().psvae_launch_count()
+    finally:
+        G.L.set_option("train_chain", 0)
+    assert torch.allclose(l0, l1, rtol=2e-6, atol=1e-7), (l0[:4], l1[:4])
+    e = ((g1.double() - g0.double()).norm() / g0.double().norm()).item()
+    assert e <= 1e-5, e
+    gd0, gd1 = G.flat_to_dict(module, g0), G.flat_to_dict(module, g1)
+    worst = max(rel_err(gd1[k], gd0[k]) for k in gd0)
+    assert worst <= 2e-5, {k: f"{rel_err(gd1[k], gd0[k]):.1e}" for k in gd0}
+    if B == 300:
+        xin = xt.float().cpu().numpy()
+        scal, out, grads = T.train_loss_and_grads_bf16(case_params(cfg, np.float32), xin, y, eps)
+        assert abs(float(l1[0]) - float(scal["loss"])) <= 2e-5
+        assert max(rel_err(gd1[k], grads[k]) for k in grads) <= 1e-3
+    print(f"train_chain B={B} x={xdt}: launches {n1 - n0}, grad diff {e:.1e}, worst tensor {worst:.1e}")
