@@ -265,10 +265,9 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
     // region needs is between those two: a 64-thread named barrier before the next tile's first hd1 write.
     const int pair = (cg >> 1) * 4 + (ew & 3);
     uint8_t* const stage_out = hd1 + (cg >> 1) * DC_KBLOCK_BYTES + quarter * 4096 + (cg & 1) * 2048;
-    for (int64_t tile = pair_id; tile < tiles; tile += pairs, ++tile_n) {
+    // One layer's NC accumulator chunks of one tile: L0 -> hd0, L1 -> the hd1 chunk buffer.  `tn` = this CTA pair's running index of `tile`.
+    auto hidden = [&](const int layer, const int64_t tile, const uint32_t tile_n) {
       const int32_t row_base = (int32_t)(tile * 2 * DC_ROWS) + (int32_t)cta_rank * DC_ROWS + quarter * 32;
-      // ---- hidden chunks: L0 c = 0..NC-1 -> hd0, L1 c = 0..NC-1 -> hd1
-      for (int layer = 0; layer < 2; ++layer) {
         for (int c = 0; c < NC; ++c, ++chunk_n) {
           const uint32_t buf = chunk_n & 1;
           wait(&acc_full[buf], (chunk_n >> 1) & 1, 10, 0);
@@ -292,11 +291,22 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
           }
           // the pair's TMA stores out of the region about to be rewritten (TRAIN: the activation write-out of the K-block's previous
           // use; sampling: the output staging blocks, which alias the hd1 chunk) have finished reading it
+#ifdef DC_EXP_NOSTORE
+          if (layer == 1 && c == 0) {
+#else
           if (TRAIN || (layer == 1 && c == 0)) {
-            if (lane == 0) ptx::bulk_wait_read0();
+#endif
+            if (lane == 0) {
+              // TRAIN, first hidden layer: the K-block about to be rewritten was stored one whole tile ago -- 2 NC + 2 bulk groups back in
+              // the issuing warp's sequence (NC + NC activation blocks, 2 output blocks per tile); only the hd1 chunk (rewritten every
+              // chunk) and the sampling path's staging need the most recent store to have finished reading
+              if (TRAIN && layer == 0) ptx::bulk_wait_read_n<4>();
+              else ptx::bulk_wait_read0();
+            }
             __syncwarp();
             asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
           }
+#ifndef DC_EXP_NOMASK
           if constexpr (TRAIN) {
             // 1-bit ReLU mask of this warp's 32 columns, one word per row: what the backward pass multiplies the gradient with
             uint32_t bits = 0;
@@ -305,6 +315,7 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
             const int64_t grow = (int64_t)row_base + lane;
             if (grow < a.rows) (layer == 0 ? a.mask0 : a.mask1)[(int64_t)(c * 4 + cg) * a.mask_ld + grow] = bits;
           }
+#endif
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             uint4 u;
@@ -316,6 +327,7 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
           }
           ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
           __syncwarp();
+#ifndef DC_EXP_NOSTORE
           if constexpr (TRAIN) {
             // both halves of the 128-byte rows are in place: one TMA store of the pair's [32 rows x 64 columns] writes the activation out
             asm volatile("bar.sync %0, 64;" ::"r"(1 + pair) : "memory");
@@ -324,10 +336,13 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
               ptx::bulk_commit();
             }
           }
+#endif
           if (lane == 0) ptx::mbar_arrive_cluster(lead(layer == 0 ? &hd0_ready[c * 2 + (cg >> 1)] : &hd1_ready[cg >> 1]));
           if (layer == 1) ++l1_n;
         }
-      }
+    };
+    auto output = [&](const int64_t tile, const uint32_t tile_n) {
+      const int32_t row_base = (int32_t)(tile * 2 * DC_ROWS) + (int32_t)cta_rank * DC_ROWS + quarter * 32;
       // ---- output: 256 accumulator columns, this warp's 64 (4 sub-blocks of 16 columns through the 2 KB staging block)
       wait(out_full, tile_n & 1, 13, 3);
       ptx::tc_fence_after();
@@ -447,6 +462,17 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive_cluster(lead(out_empty));
+    };
+    // Order: the NEXT tile's first hidden layer is drained before this tile's output, so that the second layer's MMAs of the next tile can
+    // start while the output accumulator (which is not needed again before the next tile's second L2 chunk) is still being stored
+    {
+      int64_t tile = pair_id;
+      if (tile < tiles) hidden(0, tile, 0u);
+      for (; tile < tiles; tile += pairs, ++tile_n) {
+        hidden(1, tile, tile_n);
+        if (tile + pairs < tiles) hidden(0, tile + pairs, tile_n + 1);
+        output(tile, tile_n);
+      }
     }
     if constexpr (TRAIN) {
       // bias gradient of the last layer: this warp always owned the same 64 output columns

@@ -46,37 +46,29 @@ constexpr int TC_MAX_STAGES = 12;          // barrier slots of the operand ring
 // followed by the auxiliary block (Epi::kAuxBytes: 2 KB bf16 activation tile, 4 KB fp32 target tile); the operand ring gets the rest.
 // CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on one 256 x BN tile: each CTA stages its own 128 rows of A and its
 // half of the B tile (BN/2 rows), so the operand bytes per SM and per FLOP drop by a third and the ring gets 6 stages instead of 4.
-// BRES ("B resident"): the whole [BN/CG x K] weight block of the CTA's N tile is loaded ONCE into shared memory and stays there for all of
-// the CTA's row tiles (every CTA keeps one N tile: the grid is a multiple of the number of N tiles); only the activation tile streams
-// through the ring.  Per 256 x 256 x 512 tile this takes the weight re-read (256 KB per tile and pair) out of the L2 -> SM traffic, which
-// is what bounds these GEMMs.  The staged output block shrinks to 32 columns to make room.
 // kLat: the fused encoder-head kernel (EpiLatent, option "fused_head"): see the kLat branches of gemm_tc_kernel
 template <class Epi, class = void> struct epi_latent { static constexpr bool value = false; };
 template <class Epi> struct epi_latent<Epi, std::void_t<decltype(Epi::kLatent)>> { static constexpr bool value = Epi::kLatent; };
 constexpr int TC_LAT_L = 64;                     // latent width the fused head is written for
 constexpr int TC_LAT_WARP_BYTES = 13 * 1024;     // per epilogue warp: mu block / Philox scratch 4 KB | log_sigma 4 KB | z 2 KB | sigma eps / 2 2 KB | logit exchange 1 KB
 
-// ALIAS (split-K / wgrad launches in which no CTA gets more than one tile): the epilogue staging blocks overlay the first stages of the
-// operand ring -- the single epilogue of the CTA starts after its last MMA has retired and no further load is issued, so the ring is dead
-// by then -- and the ring gets the 64 KB back: 7 stages (224 KB in flight per SM) instead of 5 for the HBM-latency-bound wgrad form.
 // EG2 ("two epilogue groups", BN = 256 only): the 16 epilogue warps form two groups of 8 that take ALTERNATE tiles -- group g owns the
 // accumulator buffer g -- each warp draining 128 columns instead of 64.  While one group stages and stores its tile the other group's
 // tcgen05.ld stream keeps the TMEM read port busy: for the thin (K <= 128) layers, which are bound by the accumulator drain
 // (profiles/r01_epilogue_phase_trace_v16.txt: 3.4 k of 4.9 k cycles per tile in the drain, 0.8-1.6 k in staging + store with the port idle).
-template <int BN, class Epi, int CG = 1, bool BRES = false, bool ALIAS = false, bool EG2 = false> struct TcCfg {
-  static_assert(!(ALIAS && BRES), "ALIAS: streaming operands only");
+template <int BN, class Epi, int CG = 1, bool EG2 = false> struct TcCfg {
   static_assert(!EG2 || (BN == 256 && Epi::kAuxBytes == 0 && !Epi::kSplit), "EG2: 16 epilogue warps, no auxiliary tile, no split-K");
   static constexpr int kEpiWarps = tc_epi_warps(BN);
   static constexpr int kThreads = 32 * (2 + kEpiWarps);
   static constexpr int kColsPerWarp = EG2 ? BN / (kEpiWarps / 8) : BN / (kEpiWarps / 4);
   static constexpr bool kLat = epi_latent<Epi>::value;
-  static_assert(!kLat || (BN == 128 && CG == 1 && !BRES && !ALIAS && !EG2), "fused head: 128-column tiles on one CTA");
+  static_assert(!kLat || (BN == 128 && CG == 1 && !EG2), "fused head: 128-column tiles on one CTA");
   static constexpr int kABytes = TC_BM * TC_BK * 2;
   static constexpr int kBBytes = kLat ? TC_LAT_L * TC_BK * 2 : (BN / CG) * TC_BK * 2;      // kLat: one group's 64 weight rows per k-block
-  static constexpr int kStageBytes = BRES ? kABytes : kABytes + kBBytes;
+  static constexpr int kStageBytes = kABytes + kBBytes;
   // staged output block of one epilogue warp: 32 rows x 128 bytes (fp32: 32 columns; bf16: 64 columns = two tcgen05.ld chunks per
   // fence / TMA store) -- except BN = 64 with bf16 output, where a warp owns only 32 columns (32 rows x 64 bytes)
-  static constexpr bool kWide = sizeof(typename Epi::TOut) == 2 && BN >= 128 && !BRES;
+  static constexpr bool kWide = sizeof(typename Epi::TOut) == 2 && BN >= 128;
   static constexpr int kBlockCols = kWide ? 64 : 32;
   static constexpr int kOutBytes = 32 * kBlockCols * (int)sizeof(typename Epi::TOut);
   static constexpr int kOutBufs = EG2 ? 2 : 1;      // EG2: a warp stages two 64-column blocks per tile back to back -- two buffers, so the second does not wait
@@ -84,24 +76,17 @@ template <int BN, class Epi, int CG = 1, bool BRES = false, bool ALIAS = false, 
   static constexpr int kEpiWarpBytes = kLat ? TC_LAT_WARP_BYTES : kOutBufs * kOutBytes + Epi::kAuxBytes;
   static constexpr int kEpiBytes = kEpiWarps * kEpiWarpBytes;
   static constexpr int kTmemCols = 2 * BN;     // power of two >= 32 for BN in {64,128,256}
-  // layout: [barriers][epilogue staging][resident B (BRES; runtime size)][operand ring]
+  // layout: [barriers][epilogue staging][operand ring]
   static constexpr int kBarOff = 0;
-  static constexpr int kOpOff = ALIAS ? TC_BAR_BYTES : TC_BAR_BYTES + kEpiBytes;
-  static constexpr int kEpiOff = ALIAS ? kOpOff : TC_BAR_BYTES;
+  static constexpr int kOpOff = TC_BAR_BYTES + kEpiBytes;
+  static constexpr int kEpiOff = TC_BAR_BYTES;
   static_assert(kOpOff % 1024 == 0, "operand tiles need 1024-byte alignment");
   static constexpr int kOpBudget = TC_SMEM_MAX - 1024 /*align slack*/ - kOpOff;
-  static constexpr int kMaxStages = (BRES || ALIAS) ? TC_MAX_STAGES : (CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
-  static constexpr int kFit = kOpBudget / kStageBytes;          // !BRES: stages that fit
+  static constexpr int kMaxStages = CG == 2 ? 8 : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int kFit = kOpBudget / kStageBytes;          // stages that fit
   static constexpr int kStages = kFit < kMaxStages ? kFit : kMaxStages;
-  static_assert(BRES || kStages >= 2, "operand ring too shallow");
-  static_assert(!ALIAS || kStages * kStageBytes >= kEpiBytes, "ALIAS: the staging blocks must fit inside the ring");
-  static constexpr int kSmemBytes = BRES ? TC_SMEM_MAX : kOpOff + kStages * kStageBytes + 1024 /*align slack*/;
-  // BRES: ring depth left after kb_total resident k-blocks of B (host side; < 3 means: use the streaming kernel)
-  static constexpr int res_stages(int64_t kb_total) {
-    const int64_t left = (int64_t)kOpBudget - kb_total * kBBytes;
-    const int64_t st = left / kABytes;
-    return st < 0 ? 0 : (st > TC_MAX_STAGES ? TC_MAX_STAGES : (int)st);
-  }
+  static_assert(kStages >= 2, "operand ring too shallow");
+  static constexpr int kSmemBytes = kOpOff + kStages * kStageBytes + 1024 /*align slack*/;
 };
 
 // host-side description of a grouped launch (see TcShape::groups)
@@ -109,10 +94,6 @@ struct TcGroup {
   int groups = 1;
   int grp_n = 0, grp_k = 0;
   int64_t out_group_stride = 0;      // elements between the groups' output buffers; 0: column ranges of one [M][groups * grp_n] buffer
-  // wgrad form (GBM, "grouped by m"): the groups' output blocks are stacked along M ([groups * grp_m][N], e.g. [W_mu; W_sigma]); group g's A
-  // columns are the natural [g * grp_m, (g+1) * grp_m) of dY and its B operand starts b_off columns further per group (the activation buffer
-  // [rows][groups * b_off] shared by the two encoders)
-  int by_m = 0, grp_m = 0, b_off = 0;
 };
 
 struct TcShape {
@@ -121,7 +102,6 @@ struct TcShape {
   int64_t K;
   int32_t splits;   // split-K factor (>= 1)
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // UMMA smem-descriptor strides (bytes)
-  int32_t pf_dist;  // k-blocks the L2 prefetch cursor leads the load cursor by (0 = off)
   int32_t stages;   // depth of the operand ring actually used (<= the compiled kStages; option "tc_max_stages")
   unsigned long long* trace;   // profiling (option "tc_trace_ptr"): per CTA 16 cycle counters -- see tools/tc_trace.py; nullptr = off
   // grouped (block-diagonal) launch: `groups` independent GEMMs laid side by side.  A is [M][groups * grp_k] (group g owns the k range
@@ -129,9 +109,6 @@ struct TcShape {
   // [groups * grp_n][grp_k] (forward Linear) or MN-major B [groups * grp_k][grp_n] (dgrad).  K above is grp_k.  out3d: the groups' outputs
   // are separate [M][grp_n] buffers a fixed stride apart (third coordinate of the output map) instead of column ranges of one buffer.
   int32_t groups, grp_n, grp_k, out3d;
-  int32_t b_stable; // BRES: B was written at least two kernels before this one (weights): its resident block is loaded before griddepcontrol.wait
-  int32_t tile_pf;  // 1: prefetch the next tile's A panel into L2 (tma_apf) at the start of each tile
-  int32_t reverse;  // walk the M tiles (and the split-K ranges) from the end: the rows the previous kernel wrote last are still in L2
 };
 
 // MULTI ("merged wgrad"): ONE persistent launch works through a list of wgrad problems dW_p[M_p][N_p] += dY_p^T act_p that share the contraction
@@ -155,17 +132,11 @@ template <int ROWB> __device__ __forceinline__ uint32_t swz_off(int r, int j) {
   else return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));                      // SWIZZLE_64B:  addr[4:5] ^= addr[7:8]
 }
 
-// CL = 2 (only with CG = 2, K-major A, streaming B): clusters of two CTA pairs that work on the same row tile and adjacent N tiles; every CTA
-// loads HALF of its 128 activation rows per k-block and multicasts them to its twin in the other pair, so the activation tile crosses the
-// L2 -> SM fabric once per cluster instead of once per pair (-25 % operand traffic per pair, ring depth unchanged).
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL, bool ALIAS = false, bool EG2 = false, bool GBM = false, bool MULTI = false>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool EG2 = false, bool MULTI = false>
 __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUtensorMap& tma_b, const CUtensorMap& tma_out, const CUtensorMap& tma_aux,
-                                             const CUtensorMap& tma_apf, const TcMulti* mp, TcShape s, Epi epi) {
-  using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS, EG2>;
-  static_assert(!MULTI || (A_MN && B_MN && Epi::kSplit && Epi::kAuxBytes == 0 && !BRES && CL == 1 && !ALIAS && !EG2 && !GBM), "MULTI: the plain wgrad form");
-  static_assert(!ALIAS || (Epi::kSplit && Epi::kAuxBytes == 0 && CL == 1), "ALIAS: split-K store epilogue, one tile per CTA (host-checked)");
-  static_assert(!EG2 || (CL == 1 && !BRES && !ALIAS), "EG2: plain streaming kernel");
-  static_assert(!GBM || (A_MN && B_MN && CL == 1 && !BRES), "GBM: the wgrad form");
+                                             const TcMulti* mp, TcShape s, Epi epi) {
+  using Cfg = TcCfg<BN, Epi, CG, EG2>;
+  static_assert(!MULTI || (A_MN && B_MN && Epi::kSplit && Epi::kAuxBytes == 0 && !EG2), "MULTI: the plain wgrad form");
   using TOut = typename Epi::TOut;
   constexpr int STAGES = TC_MAX_STAGES;                    // barrier slots; s.stages of them are in use
   constexpr int EPI_WARPS = Cfg::kEpiWarps;
@@ -174,7 +145,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
   constexpr int ROWB = Cfg::kBlockCols * (int)sizeof(TOut);   // bytes per staged row: 128, or 64 (bf16 at BN = 64)
   constexpr bool kAux = Epi::kAuxBytes > 0;
   constexpr bool kLat = Cfg::kLat;
-  static_assert(!kLat || (!A_MN && !B_MN && CL == 1), "fused head: both operands K-major");
+  static_assert(!kLat || (!A_MN && !B_MN), "fused head: both operands K-major");
   static_assert(Epi::kAuxBytes == 0 || Epi::kAuxBytes == 2048 || Epi::kAuxBytes == 4096, "aux block: 32x32 bf16 or fp32");
   static_assert(!(Epi::kColSum && sizeof(TOut) != 2), "column sums are read back from a bf16 block");
   extern __shared__ uint8_t smem_raw[];
@@ -186,20 +157,14 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
   uint64_t* tfull_bar = bars + 2 * STAGES;   // [2]       MMA -> epilogue
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2]   epilogue -> MMA
   uint64_t* aux_bar = bars + 2 * STAGES + 4;     // [EPI_WARPS] aux tile landed
-  uint64_t* bfull_bar = bars + 2 * STAGES + 4 + EPI_WARPS;       // BRES: resident B landed
-  uint64_t* bempty_bar = bfull_bar + 1;                          // BRES: every MMA that reads the resident B has retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bempty_bar + 1);
-  uint8_t* const sres = smem + Cfg::kOpOff;                                        // resident B (BRES)
-  uint8_t* const sring = sres + (BRES ? (int)((s.K + TC_BK - 1) / TC_BK) * Cfg::kBBytes : 0);   // operand ring
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4 + EPI_WARPS);
+  uint8_t* const sring = smem + Cfg::kOpOff;                                       // operand ring
   float* red_smem = reinterpret_cast<float*>(tmem_slot + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (s.trace != nullptr && threadIdx.x == 0) s.trace[(size_t)blockIdx.x * 16 + 12] = ptx::globaltimer_ns();      // kernel entry
-  static_assert(CL == 1 || (CL == 2 && CG == 2 && !A_MN && !BRES), "pair clusters: CTA pairs, K-major A, streaming B");
-  const uint32_t crank = CG == 2 ? ptx::cluster_ctarank() : 0u;       // cluster dims (2 * CL,1,1): rank = blockIdx.x % (2 * CL)
-  const uint32_t cta_rank = crank & 1u;                                // rank inside the CTA pair
-  const uint32_t pidx = crank >> 1;                                    // pair inside the cluster (CL = 2)
-  const uint32_t lead_rank = crank & ~1u;                              // cluster rank of this pair's leader
+  const uint32_t cta_rank = CG == 2 ? ptx::cluster_ctarank() : 0u;    // rank inside the CTA pair (cluster dims (2,1,1))
+  constexpr uint32_t lead_rank = 0u;                                   // cluster rank of the pair's leader
   const bool leader = cta_rank == 0;
   const int64_t work_id = CG == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
   const int64_t work_stride = CG == 2 ? (int64_t)(gridDim.x >> 1) : (int64_t)gridDim.x;
@@ -213,15 +178,13 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
     if constexpr (kAux) ptx::prefetch_tensormap(&tma_aux);
     for (int i = 0; i < STAGES; ++i) {
       ptx::mbar_init(&full_bar[i], 1);
-      ptx::mbar_init(&empty_bar[i], CL);                   // CL = 2: both pairs' MMAs must have released the stage (the twin writes into it)
+      ptx::mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&tfull_bar[i], 1);
       ptx::mbar_init(&tempty_bar[i], (EG2 ? EPI_WARPS / 2 : EPI_WARPS) * CG);      // CG = 2: the peer's epilogue warps arrive remotely on the leader's barrier; EG2: buffer i belongs to epilogue group i
     }
     for (int i = 0; i < EPI_WARPS; ++i) ptx::mbar_init(&aux_bar[i], 1);
-    ptx::mbar_init(bfull_bar, 1);
-    ptx::mbar_init(bempty_bar, 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -238,35 +201,6 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
   else __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // BRES + b_stable: B (the weights) was written at least two kernels ago, so under PDL it is safe to pull the CTA's resident weight block
-  // in NOW, while the predecessor kernel is still draining -- the one-off 256 KB load per CTA pair then costs nothing on the critical path
-  if constexpr (BRES) {
-    if (s.b_stable && warp == 0) {
-      const int64_t n_tiles0 = (s.N + BN - 1) / BN;
-      const int64_t w0 = CG == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
-      const int64_t kbt = (s.K + TC_BK - 1) / TC_BK;
-      if (ptx::elect_one()) {
-        const int32_t b_row = (int32_t)((w0 % n_tiles0) * BN) + (int32_t)cta_rank * (BN / CG);
-        const uint32_t bar_addr = CG == 2 ? ptx::mapa_u32(ptx::smem_u32(bfull_bar), lead_rank) : 0u;
-        if (leader) ptx::mbar_arrive_expect_tx(bfull_bar, (uint32_t)kbt * Cfg::kBBytes * CG);
-        for (int64_t kb = 0; kb < kbt; ++kb) {
-          uint8_t* sb = sres + kb * Cfg::kBBytes;
-          const int32_t k_el = (int32_t)(kb * TC_BK);
-          if constexpr (!B_MN) {
-            if constexpr (CG == 2) ptx::tma_load_2d_cg2(sb, &tma_b, bar_addr, k_el, b_row);
-            else ptx::tma_load_2d(sb, &tma_b, bfull_bar, k_el, b_row);
-          } else {
-#pragma unroll
-            for (int j = 0; j < (BN / CG) / 64; ++j) {
-              if constexpr (CG == 2) ptx::tma_load_2d_cg2(sb + j * (64 * TC_BK * 2), &tma_b, bar_addr, b_row + j * 64, k_el);
-              else ptx::tma_load_2d(sb + j * (64 * TC_BK * 2), &tma_b, bfull_bar, b_row + j * 64, k_el);
-            }
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
   // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the previous kernel's tail; its results
   // may only be touched from here on.  The successor may be scheduled once every CTA has passed this point.
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -294,7 +228,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
       return (int64_t)((l / (uint32_t)mp->n_tiles[p]) % (uint32_t)mp->m_tiles[p]);
     } else {
       const uint32_t m = ((uint32_t)t / n_tiles32) % m_tiles32;
-      return (int64_t)(s.reverse ? m_tiles32 - 1 - m : m);
+      return (int64_t)m;
     }
   };
   auto tile_n = [&](int64_t t) {
@@ -311,7 +245,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
       return (int64_t)(((uint32_t)t - (uint32_t)mp->tile_begin[p]) / ((uint32_t)mp->n_tiles[p] * (uint32_t)mp->m_tiles[p]));
     } else {
       const uint32_t sp = (uint32_t)t / (n_tiles32 * m_tiles32);
-      return (int64_t)(s.reverse ? (uint32_t)s.splits - 1 - sp : sp);
+      return (int64_t)sp;
     }
   };
 
@@ -354,12 +288,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
           else ptx::tma_load_2d(d, m, bar, c0, c1);
         };
         if (want_a) {
-          if constexpr (CL == 2) {
-            // this CTA's half (64 rows) of the pair-rank's 128 rows, delivered to itself and to its twin in the other pair
-            if (sa) ptx::tma_load_2d_cg2_mc(sa + pidx * (64 * TC_BK * 2), pa, bar_addr, k_el, a_row + (int32_t)pidx * 64,
-                                            (uint16_t)((1u << cta_rank) | (1u << (cta_rank + 2))));
-            else ptx::tma_prefetch_2d(pa, k_el, a_row + (int32_t)pidx * 64);
-          } else if constexpr (!A_MN) {
+          if constexpr (!A_MN) {
             if (sa) ld(sa, pa, k_el, a_row);
             else ptx::tma_prefetch_2d(pa, k_el, a_row);
           } else {
@@ -385,47 +314,14 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
           } else {
 #pragma unroll
             for (int j = 0; j < (BN / CG) / 64; ++j) {
-              if constexpr (GBM) {
-                // wgrad form grouped by m: the group of this M tile picks the B columns (s.grp_n = rows of C per group, s.grp_k = B column offset per group)
-                const int32_t gb = b_row + (int32_t)(((uint32_t)m_t * (uint32_t)TM) / (uint32_t)s.grp_n) * s.grp_k;
-                if (sb) ld(sb + j * (64 * TC_BK * 2), pb, gb + j * 64, k_el_b);
-                else ptx::tma_prefetch_2d(pb, gb + j * 64, k_el_b);
-              } else {
               if (sb) ld(sb + j * (64 * TC_BK * 2), pb, b_row + j * 64, k_el_b);
               else ptx::tma_prefetch_2d(pb, b_row + j * 64, k_el_b);
-              }
             }
           }
         }
       };
-      // L2 prefetch cursor: runs s.pf_dist k-blocks ahead of the load cursor through this CTA's (tile, k-block) sequence, so the loads
-      // that fill the smem ring hit L2 (~700 cycles) instead of HBM (~2000+): the 4-stage ring alone cannot cover DRAM latency
-      int64_t p_tile = work_id, p_kb = 0, p_kb1 = 0;
-      bool p_live = s.pf_dist > 0 && p_tile < num_tiles;
-      auto p_range = [&]() {
-        const int64_t sp = tile_sp(p_tile);
-        p_kb = sp * kb_per_split;
-        p_kb1 = min(kb_total, p_kb + kb_per_split);
-      };
-      auto p_step = [&]() {         // prefetch the cursor's k-block, then advance it
-        while (p_live && p_kb >= p_kb1) {
-          p_tile += work_stride;
-          p_live = p_tile < num_tiles;
-          if (p_live) p_range();
-        }
-        if (!p_live) return;
-        if (ptx::elect_one()) fetch(tile_m(p_tile), tile_n(p_tile), p_kb, nullptr, nullptr, nullptr, true, !BRES);
-        __syncwarp();
-        ++p_kb;
-      };
-      if (p_live) {
-        p_range();
-        for (int i = 0; i < s.pf_dist; ++i) p_step();
-      }
       int stage = 0;
       uint32_t phase = 0;
-      int64_t res_nt = (BRES && s.b_stable) ? tile_n(work_id) : -1;     // BRES: the N tile whose weights are resident (b_stable: preloaded above)
-      uint32_t res_loads = (BRES && s.b_stable) ? 1 : 0;
       for (int64_t tile = work_id; tile < num_tiles; tile += work_stride) {
         const int64_t m_t = tile_m(tile), n_t = tile_n(tile),
                       sp = tile_sp(tile);
@@ -435,34 +331,12 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
           pa = &mp->ta[p];
           pb = &mp->tb[p];
         }
-        if constexpr (!A_MN) {
-          // next tile's activation panel -> L2, whole rows at a time (DRAM-page order; the ring's narrow 128-byte-per-row boxes then hit L2)
-          const int64_t nxt = tile + work_stride;
-          if (s.tile_pf && nxt < num_tiles && ptx::elect_one()) {
-            const int32_t nrow = (int32_t)(tile_m(nxt) * TM) + (int32_t)cta_rank * TC_BM;
-            for (int32_t c = (int32_t)(kb0 * TC_BK); c < (int32_t)min(s.K, kb1 * TC_BK); c += 256) ptx::tma_prefetch_2d(&tma_apf, c, nrow);
-          }
-          __syncwarp();
-        }
-        if constexpr (BRES) {
-          if (n_t != res_nt) {             // (re)load the resident weight block: once per CTA when the grid is a multiple of n_tiles
-            if (res_loads > 0) twait(bempty_bar, (res_loads - 1) & 1, 6, tw1);      // the MMAs reading the old block have retired
-            if (ptx::elect_one()) {
-              if (leader) ptx::mbar_arrive_expect_tx(bfull_bar, (uint32_t)kb_total * Cfg::kBBytes * CG);
-              for (int64_t kb = 0; kb < kb_total; ++kb) fetch(m_t, n_t, kb, nullptr, sres + kb * Cfg::kBBytes, bfull_bar, false, true);
-            }
-            __syncwarp();
-            res_nt = n_t;
-            ++res_loads;
-          }
-        }
         for (int64_t kb = kb0; kb < kb1; ++kb) {
-          if (s.pf_dist > 0) p_step();
           twait(&empty_bar[stage], phase ^ 1, 1, tw0);
           if (ptx::elect_one()) {
             if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes * CG);
             uint8_t* const st_base = sring + stage * Cfg::kStageBytes;
-            fetch(m_t, n_t, kb, st_base, st_base + Cfg::kABytes, &full_bar[stage], true, !BRES);
+            fetch(m_t, n_t, kb, st_base, st_base + Cfg::kABytes, &full_bar[stage], true, true);
           }
           __syncwarp();
           if (++stage == s.stages) { stage = 0; phase ^= 1; }
@@ -478,33 +352,15 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
       constexpr uint32_t a_kstep = A_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;   // bytes to the next K=16 slice
       constexpr uint32_t b_kstep = B_MN ? TC_UMMA_K * 128 : TC_UMMA_K * 2;
       const uint64_t da0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sring), s.a_lbo, s.a_sbo);
-      const uint64_t db0 = ptx::make_smem_desc_sw128(BRES ? ptx::smem_u32(sres) : ptx::smem_u32(sring) + Cfg::kABytes, s.b_lbo, s.b_sbo);
+      const uint64_t db0 = ptx::make_smem_desc_sw128(ptx::smem_u32(sring) + Cfg::kABytes, s.b_lbo, s.b_sbo);
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
-      int64_t res_nt = -1;
-      uint32_t res_loads = 0;
       for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
         const int64_t sp = tile_sp(tile);
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         const int acc = (int)(it & 1);
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
-        if constexpr (BRES) {
-          const int64_t n_t = tile_n(tile);
-          if (n_t != res_nt) {
-            if (res_loads > 0) {           // hand the old block back once everything issued so far has retired
-              if (ptx::elect_one()) {
-                if constexpr (CG == 2) ptx::umma_commit_cg2_mc(bempty_bar, (uint16_t)(3u << lead_rank));
-                else ptx::umma_commit(bempty_bar);
-              }
-              __syncwarp();
-            }
-            twait(bfull_bar, res_loads & 1, 7, tw2);
-            ptx::tc_fence_after();
-            res_nt = n_t;
-            ++res_loads;
-          }
-        }
         twait(&tempty_bar[acc], acc_phase ^ 1, 2, tw1);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
@@ -512,7 +368,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
           twait(&full_bar[stage], phase, 3, tw0);
           ptx::tc_fence_after();
           const uint64_t soff = (uint64_t)((uint32_t)(stage * Cfg::kStageBytes) >> 4);
-          const uint64_t boff = BRES ? (uint64_t)((uint32_t)(kb * Cfg::kBBytes) >> 4) : soff;
+          const uint64_t boff = soff;
           if (ptx::elect_one()) {
             if constexpr (kLat) {
               // accumulator columns [mu 0-31 | ls 0-31 | mu 32-63 | ls 32-63]: group gg's weight rows 0-31 / 32-63 go to two 32-column
@@ -541,7 +397,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
             }
             }
             // smem slot free (in both CTAs of a pair) once these MMAs retire
-            if constexpr (CG == 2) ptx::umma_commit_cg2_mc(&empty_bar[stage], (uint16_t)(CL == 2 ? 0xF : 3));
+            if constexpr (CG == 2) ptx::umma_commit_cg2_mc(&empty_bar[stage], (uint16_t)3);
             else ptx::umma_commit(&empty_bar[stage]);
           }
           __syncwarp();
@@ -987,18 +843,18 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool BRES, int CL, bool ALIAS = false, bool EG2 = false, bool GBM = false>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG, bool EG2 = false>
 __global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const __grid_constant__ CUtensorMap tma_out,
-               const __grid_constant__ CUtensorMap tma_aux, const __grid_constant__ CUtensorMap tma_apf, TcShape s, Epi epi) {
-  gemm_tc_body<BN, A_MN, B_MN, Epi, CG, BRES, CL, ALIAS, EG2, GBM, false>(tma_a, tma_b, tma_out, tma_aux, tma_apf, nullptr, s, epi);
+               const __grid_constant__ CUtensorMap tma_aux, TcShape s, Epi epi) {
+  gemm_tc_body<BN, A_MN, B_MN, Epi, CG, EG2, false>(tma_a, tma_b, tma_out, tma_aux, nullptr, s, epi);
 }
 
 // the merged wgrad launch (MULTI): the problem list, tensor maps included, is one __grid_constant__ kernel parameter
 template <int BN, class Epi, int CG>
 __global__ void __launch_bounds__(32 * (2 + tc_epi_warps(BN)), 1)
 gemm_tc_multi_kernel(const __grid_constant__ TcMulti mp, TcShape s, Epi epi) {
-  gemm_tc_body<BN, true, true, Epi, CG, false, 1, false, false, false, true>(mp.ta[0], mp.tb[0], mp.tout[0], mp.ta[0], mp.ta[0], &mp, s, epi);
+  gemm_tc_body<BN, true, true, Epi, CG, false, true>(mp.ta[0], mp.tb[0], mp.tout[0], mp.ta[0], &mp, s, epi);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1017,7 +873,6 @@ int tc_tensor_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out
 int tc_block_map(const void* ptr, int elem_bytes, int64_t rows, int64_t cols, int64_t ld, int64_t splits, int64_t split_stride, CUtensorMap* out,
                  int box_cols = 32);
 int tc_grid_size();       // number of SMs of the current device (persistent grid)
-int tc_prefetch_distance();   // option "tc_prefetch": k-blocks of L2 prefetch lead
 int tc_device_check();    // 0 when the current device is sm_100
 void count_launch();
 
@@ -1033,23 +888,17 @@ static inline int tc_pick_bn(int N) {
   return 64;
 }
 // CTAs a launch uses (= rows / 4 of the kColSum partial buffer, = slots of a kReduce epilogue)
-int tc_next_direction();  // option "tc_zigzag": successive GEMM launches alternate the direction in which they walk the batch
 int tc_two_cta();         // option "tc_two_cta": use CTA pairs (cta_group::2) where the shape allows
 int tc_max_stages();      // option "tc_max_stages": cap of the operand ring depth (0 = none)
 unsigned long long* tc_trace_ptr();   // option "tc_trace_ptr": device buffer of gridDim.x * 16 counters, or nullptr
-int tc_tile_prefetch();   // option "tc_tile_prefetch"
-int tc_pair_cluster();    // option "tc_pair_cluster": clusters of two CTA pairs with the activation tile multicast between them
-int tc_b_stable();        // set by the train step / decode around GEMMs whose B operand is the (long since written) weight arena
-int tc_prefetch_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out);
+int tc_epi_groups_max_k();
 int tc_epi_groups();      // option "tc_epi_groups": K <= 128 forward / dgrad launches with BN = 256 run two epilogue groups on alternate tiles (EG2)
-int tc_alias_staging();   // option "tc_alias_staging": wgrad launches with one tile per CTA overlay the epilogue staging on the operand ring
-int tc_b_resident();      // option "tc_b_resident": keep the weight block of the CTA's N tile in shared memory where it fits
 // does this shape run as CTA pairs?  (BN = 256 tiles and more than one 128-row block of M)
 static inline bool tc_use_pair(int64_t M, int N, int force_bn = 0) {
   const int bn = force_bn ? force_bn : tc_pick_bn(N);
   return tc_two_cta() && bn == 256 && M > TC_BM;
 }
-// upper bound of the CTAs a launch uses (the B-resident variant may trim the grid to a multiple of the N tiles)
+// the CTAs a launch uses
 static inline int64_t tc_ctas(int64_t M, int N, int splits, int force_bn = 0) {
   const int bn = force_bn ? force_bn : tc_pick_bn(N);
   const int cg = tc_use_pair(M, N, force_bn) ? 2 : 1;
@@ -1077,32 +926,24 @@ template <class Epi> struct epi_split_stride<Epi, std::enable_if_t<Epi::kSplit>>
 template <class Epi, class = void> struct epi_cs_atomic { static bool get(const Epi&) { return false; } };
 template <class Epi> struct epi_cs_atomic<Epi, std::enable_if_t<Epi::kColSum>> { static bool get(const Epi& e) { return e.colsum_atomic != 0; } };
 
-template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool BRES = false, int CL = 1, bool ALIAS = false, bool EG2 = false, bool GBM = false>
+template <int BN, bool A_MN, bool B_MN, class Epi, int CG = 1, bool EG2 = false>
 int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st,
                       const TcGroup& grp = TcGroup()) {
-  using Cfg = TcCfg<BN, Epi, CG, BRES, ALIAS, EG2>;
+  using Cfg = TcCfg<BN, Epi, CG, EG2>;
   using TOut = typename Epi::TOut;
-  CUtensorMap ta, tb, tout, taux, tapf;
+  CUtensorMap ta, tb, tout, taux;
   // grouped: K is one group's contraction length; A spans all groups' k ranges, an MN-major B all groups' k rows
-  PSVAE_TRY(tc_tensor_map(A, GBM ? K : K * grp.groups, A_MN ? TC_BK : TC_BM / CL, &ta));      // CL = 2: every CTA loads (and multicasts) half of its 128 rows
-  tapf = ta;
-  if constexpr (!A_MN) {
-    if (tc_tile_prefetch()) PSVAE_TRY(tc_prefetch_map(A, K, TC_BM, &tapf));
-  }
-  PSVAE_TRY(tc_tensor_map(B, (B_MN && !GBM) ? K * grp.groups : K, B_MN ? TC_BK : BN / CG, &tb));
+  PSVAE_TRY(tc_tensor_map(A, K * grp.groups, A_MN ? TC_BK : TC_BM, &ta));
+  PSVAE_TRY(tc_tensor_map(B, B_MN ? K * grp.groups : K, B_MN ? TC_BK : BN / CG, &tb));
   TcShape s;
   s.M = M; s.N = N; s.K = K; s.splits = splits < 1 ? 1 : splits;
   tc_desc_strides(A_MN, &s.a_lbo, &s.a_sbo);
   tc_desc_strides(B_MN, &s.b_lbo, &s.b_sbo);
-  s.pf_dist = tc_prefetch_distance();
-  s.stages = BRES ? Cfg::res_stages(ceil_div64(K, TC_BK)) : Cfg::kStages;
+  s.stages = Cfg::kStages;
   if (tc_max_stages() >= 2 && tc_max_stages() < s.stages) s.stages = tc_max_stages();
-  s.reverse = tc_next_direction();
   s.trace = tc_trace_ptr();
-  s.groups = GBM ? 1 : grp.groups; s.grp_n = GBM ? (grp.grp_m > 0 ? grp.grp_m : 1) : grp.grp_n; s.grp_k = GBM ? grp.b_off : grp.grp_k;
+  s.groups = grp.groups; s.grp_n = grp.grp_n; s.grp_k = grp.grp_k;
   s.out3d = (grp.groups > 1 && grp.out_group_stride != 0) ? 1 : 0;
-  s.b_stable = (BRES && tc_b_stable()) ? 1 : 0;
-  s.tile_pf = (!A_MN && tc_tile_prefetch() && grp.groups == 1) ? 1 : 0;
   if (epi.out) {
     const bool split_slots = Epi::kSplit && !epi_split_stride<Epi>::reduce(epi);
     if (s.out3d) PSVAE_TRY(tc_block_map(epi.out, (int)sizeof(TOut), M, grp.grp_n, epi.ldo, grp.groups, grp.out_group_stride, &tout, Cfg::kBlockCols));
@@ -1116,7 +957,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   } else {
     taux = ta;
   }
-  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, BRES, CL, ALIAS, EG2, GBM>;
+  auto kern = gemm_tc_kernel<BN, A_MN, B_MN, Epi, CG, EG2>;
   static unsigned long long attr_mask = 0;   // per instantiation, one bit per device
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
@@ -1128,10 +969,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   const int64_t tiles = ceil_div64(M, TC_BM * CG) * n_tiles * s.splits;
   int grid = tc_grid_size() / CG;            // CG = 2: one CTA pair per tile
   const int64_t cs_rows = (tiles < grid ? tiles : (int64_t)grid) * CG * 4;     // = 4 * tc_ctas(): what the caller's ordered reduce reads
-  if (BRES) grid = (int)((grid / n_tiles) * n_tiles);     // every CTA (pair) keeps one N tile: its weight block is loaded once
   if (tiles < grid) grid = (int)tiles;
-  if (ALIAS && tiles > grid) { set_error("gemm_tc: staging/ring overlay needs at most one tile per CTA (%lld tiles, %d CTAs)", (long long)tiles, grid); return -2; }
-  grid = grid / CL * CL;                     // whole clusters of CL pairs (the caller guarantees an even tile count for CL = 2)
   grid *= CG;
   if (grid < 1) return 0;
   if constexpr (Epi::kColSum) {
@@ -1149,7 +987,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
     int na = 0;
     if constexpr (CG == 2) {
       at[na].id = cudaLaunchAttributeClusterDimension;
-      at[na].val.clusterDim.x = 2 * CL; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
+      at[na].val.clusterDim.x = 2; at[na].val.clusterDim.y = 1; at[na].val.clusterDim.z = 1;
       ++na;
     }
     if (pdl_enabled()) {
@@ -1159,22 +997,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
     }
     cfg.attrs = at;
     cfg.numAttrs = na;
-    if constexpr (CL == 2) {
-      // clusters of 4 must sit inside one GPC: fewer of them are co-resident than 148 / 4.  A persistent grid larger than that would run
-      // in two waves, so it is cut to what fits (queried once per instantiation and device).
-      static int max_clusters[64] = {0};
-      if (max_clusters[dev & 63] == 0) {
-        int nc = 0;
-        cudaLaunchConfig_t q = cfg;
-        q.numAttrs = CG == 2 ? 1 : 0;       // the cluster dimension only
-        PSVAE_CUDA(cudaOccupancyMaxActiveClusters(&nc, kern, &q));
-        max_clusters[dev & 63] = nc > 0 ? nc : 1;
-        if (getenv("PSVAE_DEBUG")) fprintf(stderr, "psvae: %d clusters of %d CTAs co-resident (BN=%d)\n", nc, 2 * CL, BN);
-      }
-      const int fit = max_clusters[dev & 63] * 2 * CL;
-      if (grid > fit) cfg.gridDim = dim3((unsigned)fit);
-    }
-    PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, tapf, s, epi));
+    PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, s, epi));
   }
   count_launch();
   PSVAE_LAUNCH_CHECK("gemm_tc_kernel");
@@ -1188,7 +1011,7 @@ int gemm_tc_launch_latent(const void* he, int64_t ldhe, const void* Wstack, int 
                           cudaStream_t st, int* ctas) {
   using Epi = EpiLatent<TZ>;
   constexpr int BN = 128;
-  using Cfg = TcCfg<BN, Epi, 1, false>;
+  using Cfg = TcCfg<BN, Epi, 1>;
   const int Lz = TC_LAT_L;
   if (epi.L != Lz || H % TC_BK != 0 || epi.nc > 4 || ls <= mu || hs <= z) { set_error("fused head: needs latent_dim 64, hidden_dim %% 64 == 0, <= 4 classes"); return -2; }
   CUtensorMap ta, tb, tout, taux;
@@ -1207,7 +1030,7 @@ int gemm_tc_launch_latent(const void* he, int64_t ldhe, const void* Wstack, int 
   if (tc_max_stages() >= 2 && tc_max_stages() < s.stages) s.stages = tc_max_stages();
   s.trace = tc_trace_ptr();
   s.groups = 1;
-  auto kern = gemm_tc_kernel<BN, false, false, Epi, 1, false, 1, false, false>;
+  auto kern = gemm_tc_kernel<BN, false, false, Epi, 1, false>;
   static unsigned long long attr_mask = 0;
   int dev = 0;
   PSVAE_CUDA(cudaGetDevice(&dev));
@@ -1235,7 +1058,7 @@ int gemm_tc_launch_latent(const void* he, int64_t ldhe, const void* Wstack, int 
   }
   cfg.attrs = at;
   cfg.numAttrs = na;
-  PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, ta, s, epi));
+  PSVAE_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, taux, s, epi));
   count_launch();
   PSVAE_LAUNCH_CHECK("gemm_tc_kernel<EpiLatent>");
   return 0;
@@ -1255,7 +1078,7 @@ struct TcWgradProblem {
 static inline int gemm_tc_launch_multi_wgrad(const TcWgradProblem* probs, int count, int64_t rows, cudaStream_t st) {
   using Epi = EpiStore;
   constexpr int BN = 256, CG = 2;
-  using Cfg = TcCfg<BN, Epi, CG, false>;
+  using Cfg = TcCfg<BN, Epi, CG>;
   if (count <= 0) return 0;
   if (count > TC_MAX_PROBLEMS) { set_error("merged wgrad: %d problems, at most %d", count, TC_MAX_PROBLEMS); return -2; }
   static thread_local TcMulti mp;      // 8 KB: not on the stack of every caller
@@ -1334,40 +1157,17 @@ static inline int gemm_tc_launch_multi_wgrad(const TcWgradProblem* probs, int co
   return 0;
 }
 
-// B-resident variant where it applies: forward / dgrad forms (A K-major), no split-K, no auxiliary tile, every N tile gets at least one
-// CTA (pair), and at least 3 ring stages are left next to the weight block
+// thin layers (K <= 128) on BN = 256 tiles take the two-epilogue-group kernel (EG2), everything else the plain one
 template <int BN, bool A_MN, bool B_MN, class Epi, int CG>
 int gemm_tc_launch_pick(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st,
                         const TcGroup& grp = TcGroup()) {
-  if constexpr (!A_MN && !Epi::kSplit && Epi::kAuxBytes == 0) {
-    using CfgR = TcCfg<BN, Epi, CG, true>;
-    const int64_t n_tiles = ceil_div64(N, BN);
-    if (tc_b_resident() && grp.groups == 1 && splits <= 1 && (tc_grid_size() / CG) % n_tiles == 0 && ceil_div64(M, TC_BM * CG) * n_tiles >= tc_grid_size() / CG &&
-        CfgR::res_stages(ceil_div64(K, TC_BK)) >= 3)
-      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, true>(A, B, M, N, K, splits, epi, st);
-  }
   if constexpr (BN == 256 && !A_MN && !Epi::kSplit && Epi::kAuxBytes == 0) {
-    // thin layers (K <= 128): two epilogue groups on alternate tiles keep the TMEM read port busy through the store phase
+    // two epilogue groups on alternate tiles keep the TMEM read port busy through the store phase
     // (not with the ordered column-sum partials of deterministic mode: both groups' warps of a lane quarter would share one partial slot)
     bool ordered_colsum = false;
     if constexpr (Epi::kColSum) ordered_colsum = !epi_cs_atomic<Epi>::get(epi);
-    if (tc_epi_groups() && K <= 128 && !ordered_colsum)
-      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 1, false, true>(A, B, M, N, K, splits, epi, st, grp);
-  }
-  if constexpr (A_MN && B_MN && Epi::kSplit) {
-    if (grp.by_m) return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 1, false, false, true>(A, B, M, N, K, splits, epi, st, grp);
-  }
-  if constexpr (A_MN && Epi::kSplit && Epi::kAuxBytes == 0) {
-    // wgrad form, at most one tile per CTA (pair): the epilogue staging overlays the operand ring (two more stages in flight)
-    const int64_t tiles = ceil_div64(M, TC_BM * CG) * ceil_div64(N, BN) * (splits < 1 ? 1 : splits);
-    if (tc_alias_staging() && grp.groups == 1 && tiles <= tc_grid_size() / CG)
-      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 1, true>(A, B, M, N, K, splits, epi, st, grp);
-  }
-  if constexpr (!A_MN && CG == 2) {
-    // clusters of two pairs sharing the activation tile: an even number of N tiles, whole clusters, and enough tiles to fill the grid
-    const int64_t n_tiles = ceil_div64(N, BN), m_tiles = ceil_div64(M, TC_BM * CG);
-    if (tc_pair_cluster() && grp.groups == 1 && splits <= 1 && n_tiles % 2 == 0 && (tc_grid_size() / CG) % 2 == 0 && m_tiles * n_tiles >= 2)
-      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false, 2>(A, B, M, N, K, splits, epi, st, grp);
+    if (tc_epi_groups() && K <= tc_epi_groups_max_k() && !ordered_colsum)
+      return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, true>(A, B, M, N, K, splits, epi, st, grp);
   }
   return gemm_tc_launch_bn<BN, A_MN, B_MN, Epi, CG, false>(A, B, M, N, K, splits, epi, st, grp);
 }
@@ -1380,14 +1180,7 @@ template <bool A_MN, bool B_MN, class Epi>
 int gemm_tc_launch(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st, int force_bn = 0,
                    const TcGroup& grp = TcGroup()) {
   if (N % 8 != 0) { set_error("gemm_tc: N=%d must be a multiple of 8", N); return -2; }
-  const int bn = force_bn ? force_bn : tc_pick_bn((grp.groups > 1 && !grp.by_m) ? grp.grp_n : N);      // a tile never straddles two groups
-  if (grp.by_m) {
-    const int tm = TC_BM * (tc_use_pair(M, N, bn) ? 2 : 1);
-    if (!(A_MN && B_MN) || grp.grp_m % tm != 0 || M != (int64_t)grp.groups * grp.grp_m) {
-      set_error("gemm_tc: a launch grouped by m needs the wgrad form and grp_m %% %d == 0", tm);
-      return -2;
-    }
-  } else
+  const int bn = force_bn ? force_bn : tc_pick_bn(grp.groups > 1 ? grp.grp_n : N);      // a tile never straddles two groups
   if (grp.groups > 1 && (A_MN || splits > 1 || grp.grp_n % bn != 0 || grp.grp_k % TC_BK != 0 || N != grp.groups * grp.grp_n)) {
     set_error("gemm_tc: grouped launch needs K-major A, no split-K, grp_n %% %d == 0 and grp_k %% %d == 0", bn, TC_BK);
     return -2;

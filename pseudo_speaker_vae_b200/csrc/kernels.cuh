@@ -879,7 +879,7 @@ struct ClfBwdArgs {
   const float* g_rows;
 };
 template <typename TAct, int NC>
-__global__ void __launch_bounds__(256) latent_bwd_clf_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
+__global__ void __launch_bounds__(256, 3) latent_bwd_clf_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
                                                              const TAct* __restrict__ hs, int64_t n_elems, int L, float kl_over_b, TAct* __restrict__ dmu,
                                                              TAct* __restrict__ dls, float* __restrict__ bias_grad, int64_t ld_d, ClfBwdArgs ca) {
   PSVAE_GRID_DEP();
@@ -907,17 +907,34 @@ __global__ void __launch_bounds__(256) latent_bwd_clf_kernel(const float* __rest
     }
   }
   float sm_[4] = {0.f, 0.f, 0.f, 0.f}, sl_[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += stride) {
-    float g[4], m[4], l[4], e[4], c[4] = {0.f, 0.f, 0.f, 0.f}, om[4], ol[4];
-    load_vec<4>(dz + (i << 2), g);
-    load_vec<4>(mu + (i << 2), m);
-    load_vec<4>(ls + (i << 2), l);
-    load_vec<4>(hs + (i << 2), e);
-    const int64_t row = (int64_t)((uint32_t)i / qpr_);
-    float gr[CLF_MAXC];
-    load_vec<4>(ca.g_rows + row * CLF_MAXC, *reinterpret_cast<float(*)[4]>(&gr[0]));
-    if (NC > 4) load_vec<4>(ca.g_rows + row * CLF_MAXC + 4, *reinterpret_cast<float(*)[4]>(&gr[4]));
-    const bool first_quad = ((uint32_t)i % qpr_) == 0;
+  // Two quads per trip, every load of both issued before any arithmetic (the kernel is latency-bound: ~7 trips per thread, 5 dependent-free
+  // loads each); d loss / d logits comes in as one or two float4 straight into registers (an indexed local array cost a stack frame)
+  struct Quad { float4 g, m, l, e, ga, gb; int64_t row; uint32_t q; bool on; };
+  auto load_quad = [&](int64_t i) {
+    Quad t;
+    t.on = i < nq;
+    t.g = t.m = t.l = t.e = t.ga = t.gb = make_float4(0.f, 0.f, 0.f, 0.f);
+    t.row = 0; t.q = 0;
+    if (t.on) {
+      t.g = __ldg(reinterpret_cast<const float4*>(dz) + i);
+      t.m = __ldg(reinterpret_cast<const float4*>(mu) + i);
+      t.l = __ldg(reinterpret_cast<const float4*>(ls) + i);
+      float hv[4];
+      load_vec<4>(hs + (i << 2), hv);
+      t.e = make_float4(hv[0], hv[1], hv[2], hv[3]);
+      t.row = (int64_t)((uint32_t)i / qpr_);
+      t.q = (uint32_t)i % qpr_;
+      t.ga = __ldg(reinterpret_cast<const float4*>(ca.g_rows + t.row * CLF_MAXC));
+      if (NC > 4) t.gb = __ldg(reinterpret_cast<const float4*>(ca.g_rows + t.row * CLF_MAXC + 4));
+    }
+    return t;
+  };
+  auto do_quad = [&](const Quad& t) {
+    if (!t.on) return;
+    const float g[4] = {t.g.x, t.g.y, t.g.z, t.g.w}, m[4] = {t.m.x, t.m.y, t.m.z, t.m.w}, l[4] = {t.l.x, t.l.y, t.l.z, t.l.w}, e[4] = {t.e.x, t.e.y, t.e.z, t.e.w};
+    const float gr[8] = {t.ga.x, t.ga.y, t.ga.z, t.ga.w, t.gb.x, t.gb.y, t.gb.z, t.gb.w};
+    float c[4] = {0.f, 0.f, 0.f, 0.f}, om[4], ol[4];
+    const bool first_quad = t.q == 0;
 #pragma unroll
     for (int cc = 0; cc < NC; ++cc) {
       if (cc < nc) {
@@ -936,9 +953,15 @@ __global__ void __launch_bounds__(256) latent_bwd_clf_kernel(const float* __rest
       sm_[j] += om[j];
       sl_[j] += ol[j];
     }
-    const int64_t o = row * ld_d + (((uint32_t)i % qpr_) << 2);
+    const int64_t o = t.row * ld_d + (t.q << 2);
     store_vec<4>(dmu + o, om);
     store_vec<4>(dls + o, ol);
+  };
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nq; i += 2 * stride) {
+    const Quad a0 = load_quad(i);
+    const Quad a1 = load_quad(i + stride);
+    do_quad(a0);
+    do_quad(a1);
   }
   const int qpr = L >> 2;
   // bias gradients of the encoders' last Linear: as latent_bwd_cs_kernel (atomics into the zeroed [mu | sigma] bias gradient)

@@ -56,16 +56,8 @@ struct Options {
   int64_t colsum_rows = 512;           // rows per bias-gradient partial
   int64_t tc_force_bn = 0;             // tests: force the N tile of the tcgen05 engine
   int64_t tc_grid_limit = 0;           // tests: cap the persistent grid
-  int64_t tc_prefetch = 0;             // k-blocks the operand L2 prefetch runs ahead of the smem ring (measured: 0.99 ms off vs 1.19-1.26 ms on -- the mainloop is L2->SM bandwidth-bound, not latency-bound; kept as an experiment knob)
   int64_t tc_two_cta = 1;              // 1: 256-row tiles on CTA pairs (tcgen05 cta_group::2) for BN = 256 shapes
-  int64_t tc_zigzag = 0;               // successive GEMM launches walk the batch in alternating directions (L2 reuse of the rows written last)
   int64_t langevin_generic = 0;        // tests: force the generic (tile-in-smem) Langevin kernel even where the thread-per-sample one applies
-  int64_t tc_b_resident = 0;           // 1: forward / dgrad GEMMs keep the weight block of their N tile resident in shared memory (where it fits)
-  int64_t tc_tile_prefetch = 0;        // 1: the producer pulls the NEXT tile's whole activation panel into L2 with wide-box prefetches at the start of each tile
-  int64_t tc_pair_cluster = 0;         // 1: forward / dgrad GEMMs with an even number of N tiles run as clusters of two CTA pairs (activation tile multicast).
-                                       //    Measured: +7 % per SM, but only 33 clusters of 4 are co-resident (132 of 148 SMs) -> 39.3 vs 37.4 us; off by default
-  int64_t tc_grouped_wgrad = 1;        // 1 (fast mode): the two encoders' hidden-layer wgrads run as ONE launch grouped by m ([W_mu; W_sigma] stacked along the output rows).
-                                       //    Measured (round 2, A/B on one box, three alternating pairs): 0.7837 -> 0.7769 ms/step
   int64_t fused_head = 1;              // 1 (training, tcgen05 fast mode, latent 64, at most one linear head of <= 4 classes): encoder heads + reparameterisation + KL +
                                        //    classifier forward in ONE kernel (EpiLatent); the classifier's backward then runs inside the latent backward kernel.
                                        //    Measured (round 2, A/B): 0.7867 -> 0.7758 ms/step
@@ -74,11 +66,10 @@ struct Options {
                                        //    Measured on its own (round 2, A/B): 0.7840 -> 0.7887 ms/step -- slower, so off; the fused head uses the same backward regardless
   int64_t tc_epi_groups = 1;           // 1: thin (K <= 128) BN = 256 forward / dgrad launches use two epilogue groups on alternate tiles (EG2).
                                        //    Measured (round 2, A/B): 0.7832 -> 0.7733 ms/step
-  int64_t tc_alias_staging = 0;        // 1: split-K (wgrad) launches with at most one tile per CTA overlay the epilogue staging on the operand ring (7 stages instead of 5).
-                                       //    Measured neutral (31.4 vs 31.7 us for the 512 x 512 wgrad): the wgrad form is not bound by bytes in flight; off by default
+  int64_t tc_epi_groups_max_k = 128;   // largest contraction length K that still takes the two-epilogue-group kernel
   int64_t tc_merged_wgrad = 1;         // 1 (fast tcgen05 mode): every wgrad of the step runs in ONE persistent launch at the end of the backward pass (gemm_tc_launch_multi_wgrad):
                                        //    the ~8 us fixed cost of a wgrad launch is paid once instead of 8 times
-  int64_t decode_chain = 0;            // 1 (tcgen05 mode, two hidden layers <= 512 wide, latent 64, <= 256 outputs, no normalize_decoder): psvae_decode runs the chained
+  int64_t decode_chain = 1;            // 1 (tcgen05 mode, two hidden layers <= 512 wide, latent 64, <= 256 outputs, no normalize_decoder): psvae_decode runs the chained
                                        //    decoder kernel (decoder_chain.cuh): z from Philox in-kernel, hidden activations on-chip, one launch for all rows
   int64_t train_chain = 0;             // 1 (training, fast tcgen05 mode, decoder_chain_ok shapes, plain MSE tail, x_hat not requested): the decoder half of the forward pass
                                        //    (dec L0 -> L1 -> last + MSE) runs as ONE chained kernel (decoder_chain.cuh, TRAIN): hidden activations written once, never re-read
@@ -126,24 +117,12 @@ int tc_device_check() {
   }
   return 0;
 }
-int tc_prefetch_distance() { return (int)g_opt.tc_prefetch; }
 int tc_two_cta() { return (int)g_opt.tc_two_cta; }
 int tc_max_stages() { return (int)g_opt.tc_max_stages; }
-int tc_b_resident() { return (int)g_opt.tc_b_resident; }
-int tc_alias_staging() { return (int)g_opt.tc_alias_staging; }
 int tc_epi_groups() { return (int)g_opt.tc_epi_groups; }
+int tc_epi_groups_max_k() { return (int)g_opt.tc_epi_groups_max_k; }
 bool pdl_enabled() { return g_opt.pdl != 0; }
-int tc_pair_cluster() { return (int)g_opt.tc_pair_cluster; }
-static thread_local int g_b_stable = 0;
-int tc_b_stable() { return g_b_stable && g_opt.pdl != 0; }
-struct StableWeights {        // RAII: GEMMs launched in this scope read weights that no kernel of the last two launches wrote
-  StableWeights() { g_b_stable = 1; }
-  ~StableWeights() { g_b_stable = 0; }
-};
-int tc_tile_prefetch() { return (int)g_opt.tc_tile_prefetch; }
 unsigned long long* tc_trace_ptr() { return reinterpret_cast<unsigned long long*>(static_cast<uintptr_t>(g_opt.tc_trace_ptr)); }
-static thread_local unsigned g_dir = 0;
-int tc_next_direction() { return g_opt.tc_zigzag ? (int)(g_dir++ & 1u) : 0; }
 int tc_grid_size() {
   DevInfo* d = nullptr;
   if (dev_info(&d) != 0) return PSVAE_NUM_SMS;
@@ -209,25 +188,6 @@ int tc_tensor_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out
     return -3;
   }
   if (g_tm_cache.size() > 8192) g_tm_cache.clear();
-  g_tm_cache[key] = tm;
-  *out = tm;
-  return 0;
-}
-
-// L2-prefetch map of a K-major operand: wide boxes ([box_rows][up to 256 columns], no swizzle -- nothing lands in shared memory) so that one
-// instruction pulls a whole row panel of the next tile from HBM in DRAM-page order
-int tc_prefetch_map(const TcOperand& op, int64_t K, int box_rows, CUtensorMap* out) {
-  std::lock_guard<std::mutex> lk(g_tm_mu);
-  if (!g_encode) { set_error("tc_prefetch_map before tc_tensor_map"); return -3; }
-  const TmKey key(op.ptr, op.rows, op.ld, K, 2, box_rows);
-  auto it = g_tm_cache.find(key);
-  if (it != g_tm_cache.end()) { *out = it->second; return 0; }
-  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)op.rows}, gstride[1] = {(cuuint64_t)op.ld * sizeof(bf16)};
-  cuuint32_t box[2] = {(cuuint32_t)(K < 256 ? K : 256), (cuuint32_t)box_rows}, estr[2] = {1, 1};
-  alignas(64) CUtensorMap tm;
-  CUresult r = g_encode(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(op.ptr), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled (prefetch map) failed (%d)", (int)r); return -3; }
   g_tm_cache[key] = tm;
   *out = tm;
   return 0;
@@ -323,16 +283,6 @@ template <> struct Engine<bf16> {
     TcGroup g;
     g.groups = groups; g.grp_n = Ng; g.grp_k = Kg; g.out_group_stride = out_group_stride;
     return gemm_tc_launch<false, b_mn, Epi>(a, b, M, groups * Ng, Kg, 1, epi, st, (int)g_opt.tc_force_bn, g);
-  }
-  // both encoders' wgrad of one hidden layer in one launch: dY [rows][groups * out_g], act [rows][groups * in] -> [groups * out_g][in] (stacked)
-  template <class Epi>
-  static int wgrad_grouped(const bf16* dY, int64_t ldy, const bf16* act, int64_t lda, int64_t rows, int groups, int out_g, int in, int splits, const Epi& epi,
-                           cudaStream_t st) {
-    TcOperand a{dY, (int64_t)groups * out_g, ldy, true};
-    TcOperand b{act, (int64_t)groups * in, lda, true};
-    TcGroup g;
-    g.groups = groups; g.by_m = 1; g.grp_m = out_g; g.b_off = in;
-    return gemm_tc_launch<true, true, Epi>(a, b, (int64_t)groups * out_g, in, rows, splits, epi, st, (int)g_opt.tc_force_bn, g);
   }
   static bool grouped_ok(int Ng, int Kg) {
     const int bn = g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(Ng);
@@ -787,7 +737,6 @@ static int decoder_forward(const Net& n, const TAct* Wt, const float* params, co
 template <typename TAct>
 static int run_step(const StepArgs& a) {
   PSVAE_TRY(tc_device_check());
-  StableWeights stable_weights;      // every GEMM below has at least one kernel between it and the last writer of the weights (Adam)
   const psvae_model_desc* d = a.d;
   Net n(d);
   const int64_t B = a.rows;
@@ -1207,7 +1156,7 @@ static int run_step(const StepArgs& a) {
   const bool clf_in_bwd = !a.ext && clf_fused && a.want_loss && (g_opt.clf_grad_in_bwd || fused_head) && !g_opt.deterministic && w.clf_grows && latent_cs_ok(n.L);
   if (clf_in_bwd) {
     int blocks = ew_grid(B * n.L / 4);
-    if (blocks > 4 * PSVAE_NUM_SMS) blocks = 4 * PSVAE_NUM_SMS;
+    if (blocks > 3 * PSVAE_NUM_SMS) blocks = 3 * PSVAE_NUM_SMS;      // 80 registers x 256 threads: three blocks per SM are resident -- one full wave
     ClfBwdArgs cb;
     memset(&cb, 0, sizeof(cb));
     cb.n_heads = d->clf_num_heads;
@@ -1288,18 +1237,7 @@ static int run_step(const StepArgs& a) {
                                    G + d->enc_b[n.nh - 1] + s * n.H, w, &bias_done[s], st));
     }
     for (int j = n.nh - 1; j >= 1; --j) {
-      bool wgrad_pair_done = false;
-      if constexpr (sizeof(TAct) == 2) {
-        // option tc_grouped_wgrad: one launch for both encoders ([W_mu_j; W_sigma_j] is one [2H][H] block of the gradient buffer)
-        const int tm = TC_BM * (tc_use_pair(2 * n.H, n.H, (int)g_opt.tc_force_bn) ? 2 : 1);
-        if (g_opt.tc_grouped_wgrad && !w.merge_wgrads && !g_opt.deterministic && bias_done[0] && bias_done[1] && n.H % tm == 0) {
-          const int splits = Engine<TAct>::wgrad_splits(2 * n.H, n.H, B);
-          EpiStore e{G + d->enc_w[j], n.H, 0, 1.f, 0.f, nullptr, 1};
-          PSVAE_TRY((Engine<TAct>::wgrad_grouped(w.ge[pp], 2 * n.H, w.he[j - 1], 2 * n.H, B, 2, n.H, n.H, splits, e, st)));
-          wgrad_pair_done = true;
-        }
-      }
-      for (int s = 0; s < 2 && !wgrad_pair_done; ++s) {
+      for (int s = 0; s < 2; ++s) {
         const TAct* dY = w.ge[pp] + s * n.H;
         PSVAE_TRY(wgrad<TAct>(dY, 2 * n.H, w.he[j - 1] + s * n.H, 2 * n.H, B, n.H, n.H, G + d->enc_w[j] + (int64_t)s * n.H * n.H,
                               bias_done[s] ? nullptr : G + d->enc_b[j] + s * n.H, w, st));
@@ -1337,7 +1275,6 @@ template <typename TAct>
 static int run_decode(const psvae_model_desc* d, const float* params, const bf16* shadow, const float* z, uint64_t seed, uint64_t offset, int64_t row0,
                       int64_t rows, float* x_hat, float* z_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
   PSVAE_TRY(tc_device_check());
-  StableWeights stable_weights;      // the Philox / cast kernel of each chunk sits between the weights' last writer and the first GEMM
   Net n(d);
   if (rows <= 0) { set_error("rows=%lld must be positive", (long long)rows); return -2; }
   if (!params || !x_hat) { set_error("params and x_hat must not be NULL"); return -1; }
@@ -1443,24 +1380,18 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_grid_limit")) { g_opt.tc_grid_limit = value < 0 ? 0 : value; return 0; }
   if (!strcmp(name, "deterministic")) { g_opt.deterministic = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_two_cta")) { g_opt.tc_two_cta = value ? 1 : 0; return 0; }
-  if (!strcmp(name, "tc_zigzag")) { g_opt.tc_zigzag = value ? 1 : 0; return 0; }
   if (!strcmp(name, "langevin_generic")) { g_opt.langevin_generic = value ? 1 : 0; return 0; }
-  if (!strcmp(name, "tc_prefetch")) { g_opt.tc_prefetch = value < 0 ? 0 : (value > 64 ? 64 : value); return 0; }
   if (!strcmp(name, "tc_max_stages")) { g_opt.tc_max_stages = value < 0 ? 0 : value; return 0; }
-  if (!strcmp(name, "tc_b_resident")) { g_opt.tc_b_resident = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_trace_ptr")) { g_opt.tc_trace_ptr = value; return 0; }
   if (!strcmp(name, "pdl")) { g_opt.pdl = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_grouped")) { g_opt.tc_grouped = value ? 1 : 0; return 0; }
-  if (!strcmp(name, "tc_alias_staging")) { g_opt.tc_alias_staging = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_epi_groups")) { g_opt.tc_epi_groups = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "tc_epi_groups_max_k")) { g_opt.tc_epi_groups_max_k = value < 0 ? 0 : value; return 0; }
   if (!strcmp(name, "clf_grad_in_bwd")) { g_opt.clf_grad_in_bwd = value ? 1 : 0; return 0; }
   if (!strcmp(name, "fused_head")) { g_opt.fused_head = value ? 1 : 0; return 0; }
-  if (!strcmp(name, "tc_grouped_wgrad")) { g_opt.tc_grouped_wgrad = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_merged_wgrad")) { g_opt.tc_merged_wgrad = value ? 1 : 0; return 0; }
   if (!strcmp(name, "decode_chain")) { g_opt.decode_chain = value ? 1 : 0; return 0; }
   if (!strcmp(name, "train_chain")) { g_opt.train_chain = value ? 1 : 0; return 0; }
-  if (!strcmp(name, "tc_pair_cluster")) { g_opt.tc_pair_cluster = value ? 1 : 0; return 0; }
-  if (!strcmp(name, "tc_tile_prefetch")) { g_opt.tc_tile_prefetch = value ? 1 : 0; return 0; }
   set_error("unknown option '%s'", name);
   return -2;
 }
@@ -1473,23 +1404,17 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_grid_limit")) return g_opt.tc_grid_limit;
   if (!strcmp(name, "deterministic")) return g_opt.deterministic;
   if (!strcmp(name, "tc_two_cta")) return g_opt.tc_two_cta;
-  if (!strcmp(name, "tc_zigzag")) return g_opt.tc_zigzag;
   if (!strcmp(name, "langevin_generic")) return g_opt.langevin_generic;
-  if (!strcmp(name, "tc_prefetch")) return g_opt.tc_prefetch;
   if (!strcmp(name, "tc_max_stages")) return g_opt.tc_max_stages;
-  if (!strcmp(name, "tc_b_resident")) return g_opt.tc_b_resident;
   if (!strcmp(name, "pdl")) return g_opt.pdl;
   if (!strcmp(name, "tc_grouped")) return g_opt.tc_grouped;
-  if (!strcmp(name, "tc_alias_staging")) return g_opt.tc_alias_staging;
   if (!strcmp(name, "tc_epi_groups")) return g_opt.tc_epi_groups;
+  if (!strcmp(name, "tc_epi_groups_max_k")) return g_opt.tc_epi_groups_max_k;
   if (!strcmp(name, "clf_grad_in_bwd")) return g_opt.clf_grad_in_bwd;
   if (!strcmp(name, "fused_head")) return g_opt.fused_head;
-  if (!strcmp(name, "tc_grouped_wgrad")) return g_opt.tc_grouped_wgrad;
   if (!strcmp(name, "tc_merged_wgrad")) return g_opt.tc_merged_wgrad;
   if (!strcmp(name, "decode_chain")) return g_opt.decode_chain;
   if (!strcmp(name, "train_chain")) return g_opt.train_chain;
-  if (!strcmp(name, "tc_pair_cluster")) return g_opt.tc_pair_cluster;
-  if (!strcmp(name, "tc_tile_prefetch")) return g_opt.tc_tile_prefetch;
   return -1;
 }
 

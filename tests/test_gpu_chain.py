@@ -10,6 +10,8 @@ from tests.golden_util import case_params, rel_err
 
 pytestmark = pytest.mark.gpu
 
+DECODE_CHAIN_DEFAULT = 1       # on by default since round 2 (validated by this file, +28 % on unconditional sampling)
+
 
 def _gu():
     from tests import gpu_util
@@ -42,7 +44,7 @@ def test_chained_decoder_matches_layer_by_layer_path(N):
         got, zg = hot.decode(None, num_samples=N, return_z=True, row0=5)
         torch.cuda.synchronize()
     finally:
-        G.L.set_option("decode_chain", 0)
+        G.L.set_option("decode_chain", DECODE_CHAIN_DEFAULT)
     assert torch.equal(zr, zg)                                   # same Philox counters: bit-identical z
     e = ((got.double() - ref.double()).norm() / ref.double().norm()).item()
     assert torch.isfinite(got).all() and e <= 1e-5, e
@@ -63,7 +65,7 @@ def test_chained_decoder_vs_oracle_shapes(D, H):
         got = module.hot_path.decode(zt)
         torch.cuda.synchronize()
     finally:
-        G.L.set_option("decode_chain", 0)
+        G.L.set_option("decode_chain", DECODE_CHAIN_DEFAULT)
     want, _ = T._mlp_fwd({k: v.astype(np.float64) for k, v in params.items()}, "model.decoder", T.bf16_round(z))
     # a hidden activation whose fp32-accumulated value sits on a bf16 rounding boundary lands one bf16 ulp from the fp64-accumulating twin's
     assert rel_err(got.cpu().numpy(), want) <= 2e-4
@@ -87,7 +89,7 @@ def test_chained_decoder_shards_are_bit_identical():
             parts.append(P.sample_on_device(module, rows, row0=row0))
         torch.cuda.synchronize()
     finally:
-        G.L.set_option("decode_chain", 0)
+        G.L.set_option("decode_chain", DECODE_CHAIN_DEFAULT)
     assert torch.equal(torch.cat(parts), full)
 
 

@@ -775,13 +775,10 @@ def test_deterministic_option_and_fast_mode_agree():
         G.L.set_option("deterministic", 0)
 
 
-@pytest.mark.parametrize("opts", [dict(tc_pair_cluster=1), dict(tc_b_resident=1), dict(tc_b_resident=1, tc_tile_prefetch=1), dict(pdl=0),
-                                  dict(tc_two_cta=0), dict(tc_max_stages=2), dict(tc_grouped=0), dict(tc_alias_staging=1)])
+@pytest.mark.parametrize("opts", [dict(pdl=0), dict(tc_two_cta=0), dict(tc_max_stages=2), dict(tc_grouped=0)])
 def test_engine_variants_reproduce_the_default_path(opts):
-    """The tuning variants of the tcgen05 engine (clusters of two CTA pairs with the activation tile multicast, weight block resident in
-    shared memory, next-tile L2 prefetch, no programmatic dependent launch, 1-CTA tiles, a 2-deep ring, one launch per encoder instead of
-    the grouped block-diagonal launches, wgrad staging blocks overlaid on the operand ring) change the schedule, not the
-    arithmetic: in deterministic mode the forward outputs must be bit-identical to the default configuration and the losses / gradients
+    """The tuning variants of the tcgen05 engine (no programmatic dependent launch, 1-CTA tiles, a 2-deep ring, one launch per encoder
+    instead of the grouped block-diagonal launches) change the schedule, not the arithmetic: in deterministic mode the forward outputs must be bit-identical to the default configuration and the losses / gradients
     identical up to the order of the per-CTA partial sums, at a batch with ragged tiles."""
     G = _gu()
     module, cfg = _big_module(G, "bf16")
@@ -816,18 +813,17 @@ def test_engine_variants_reproduce_the_default_path(opts):
             G.L.set_option(k, v)
 
 
-FAST_VARIANTS_OFF = dict(tc_epi_groups=0, clf_grad_in_bwd=0, fused_head=0, tc_grouped_wgrad=0, tc_merged_wgrad=0)
+FAST_VARIANTS_OFF = dict(tc_epi_groups=0, clf_grad_in_bwd=0, fused_head=0, tc_merged_wgrad=0)
 
 
-@pytest.mark.parametrize("opts", [dict(tc_epi_groups=1), dict(clf_grad_in_bwd=1), dict(fused_head=1), dict(tc_grouped_wgrad=1), dict(tc_merged_wgrad=1),
-                                  dict(tc_epi_groups=1, fused_head=1, tc_grouped_wgrad=1, tc_merged_wgrad=1)])
+@pytest.mark.parametrize("opts", [dict(tc_epi_groups=1), dict(clf_grad_in_bwd=1), dict(fused_head=1), dict(tc_merged_wgrad=1),
+                                  dict(tc_epi_groups=1, fused_head=1, tc_merged_wgrad=1)])
 def test_fast_mode_engine_variants_agree_with_the_plain_path(opts):
     """The fast-mode variants that are ON by default since round 2 (validated on a B200 by tools/validate_experimental.sh, then A/B-timed)
     against the path with all of them off.  tc_epi_groups (two epilogue groups on alternate tiles for the K <= 128 layers): forward outputs
     bit-identical, losses / gradients equal up to summation order.  clf_grad_in_bwd: the classifier's backward formed in the latent backward
     kernel from d loss / d logits.  fused_head: encoder heads + reparameterisation + KL + classifier forward in one kernel (its
-    accumulators come from 32-column MMAs: outputs are compared to 1e-5, not bit for bit).  tc_grouped_wgrad: both encoders' hidden-layer
-    wgrads in one launch.  tc_merged_wgrad: every wgrad of the step in one persistent launch at the end of the backward pass."""
+    accumulators come from 32-column MMAs: outputs are compared to 1e-5, not bit for bit).  tc_merged_wgrad: every wgrad of the step in one persistent launch at the end of the backward pass."""
     G = _gu()
     module, cfg = _big_module(G, "bf16")
     hot = module.hot_path

@@ -33,7 +33,7 @@ def run(m, n, k, form, store=True, mask=True, colsum=True, nbuf=4, reps=40, opts
     e1.record()
     torch.cuda.synchronize()
     for kk in (opts or {}):
-        L.set_option(kk, 0 if kk not in ("tc_two_cta", "pdl", "tc_pair_cluster") else 1)
+        L.set_option(kk, 0 if kk not in ("tc_two_cta", "pdl") else 1)
     us = e0.elapsed_time(e1) * 1e3 / reps
     return us, 2.0 * m * n * k / us / 1e6
 
@@ -45,9 +45,6 @@ if __name__ == "__main__":
         us, tf = run(*a, **kw)
         print(f"{name:64s} {us:8.1f} us {tf:8.1f} TFLOP/s", flush=True)
     line("fwd 512x512 HBM full (store+mask)", B, 512, 512, 0)
-    line("fwd 512x512 HBM full, no pair clusters (no A multicast)", B, 512, 512, 0, opts={"tc_pair_cluster": 0})
-    line("fwd 512x512 HBM full, resident B (tc_b_resident=1)", B, 512, 512, 0, opts={"tc_b_resident": 1})
-    line("fwd 512x512 HBM full, tile prefetch", B, 512, 512, 0, opts={"tc_tile_prefetch": 1})
     line("fwd 512x512 HBM full, no PDL", B, 512, 512, 0, opts={"pdl": 0})
     line("fwd 512x512 HBM store, no mask", B, 512, 512, 0, mask=False)
     line("fwd 512x512 HBM no store, no mask", B, 512, 512, 0, store=False, mask=False)
@@ -58,15 +55,12 @@ if __name__ == "__main__":
     line("fwd 512x512 HBM full, cta_group::1", B, 512, 512, 0, opts={"tc_two_cta": 0})
     line("fwd 512x512 HBM full, BN=128", B, 512, 512, 0, opts={"tc_force_bn": 128})
     line("fwd K=256 N=1024 HBM full", B, 1024, 256, 0)
-    line("fwd K=256 N=1024 HBM full, no pair clusters", B, 1024, 256, 0, opts={"tc_pair_cluster": 0})
     line("fwd K=256 N=1024 HBM no store no mask", B, 1024, 256, 0, store=False, mask=False)
     line("fwd K=64 N=512 HBM full", B, 512, 64, 0)
     line("fwd K=64 N=512 HBM full, no PDL", B, 512, 64, 0, opts={"pdl": 0})
-    line("fwd K=64 N=512 HBM full, no pair clusters", B, 512, 64, 0, opts={"tc_pair_cluster": 0})
     line("fwd K=64 N=512 HBM no mask", B, 512, 64, 0, mask=False)
     line("fwd K=64 N=512 HBM no store no mask", B, 512, 64, 0, store=False, mask=False)
     line("dgrad 512x512 HBM full (mask+colsum)", B, 512, 512, 1)
-    line("dgrad 512x512 HBM full, no pair clusters", B, 512, 512, 1, opts={"tc_pair_cluster": 0})
     line("dgrad 512x512 HBM no colsum", B, 512, 512, 1, colsum=False)
     line("dgrad 512x512 HBM no store", B, 512, 512, 1, store=False)
     line("dgrad K=64 N=512 HBM full", B, 512, 64, 1)

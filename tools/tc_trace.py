@@ -35,7 +35,7 @@ def trace(m, n, k, form, store=True, mask=True, colsum=True, opts=None, label=""
     torch.cuda.synchronize()
     L.set_option("tc_trace_ptr", 0)
     for kk in (opts or {}):
-        L.set_option(kk, 0 if kk not in ("tc_two_cta", "tc_b_resident", "tc_tile_prefetch", "pdl") else 1)
+        L.set_option(kk, 0 if kk not in ("tc_two_cta", "pdl") else 1)
     t = tr.view(148, 16).double().cpu()
     t2 = tr2.view(148, 16).double().cpu()
     ent, beg, epi_end, ext = t[:, 12], t[:, 13], t[:, 14], t[0::2, 15]
@@ -97,8 +97,6 @@ if __name__ == "__main__":
     trace_wgrad(65536, 64, 512, label="wgrad 64x512")
     B = 65536
     trace(B, 512, 512, 0, label="fwd 512x512 full")
-    trace(B, 512, 512, 0, label="fwd 512x512 full streaming-B", opts={"tc_b_resident": 0})
-    trace(B, 512, 512, 0, label="fwd 512x512 full no tile prefetch", opts={"tc_tile_prefetch": 0})
     trace(B, 512, 512, 0, label="fwd 512x512 full no PDL", opts={"pdl": 0})
     trace(B, 512, 512, 0, store=False, mask=False, label="fwd 512x512 no store no mask")
     trace(B, 1024, 256, 0, label="fwd K=256 N=1024 full")
