@@ -14,6 +14,7 @@
 //       TMA load.  kColSum: the engine also emits the column sums of what was stored (bias gradients); kReduce: per-CTA sum of `red`.
 #pragma once
 #include "common.cuh"
+#include "ptx.cuh"
 
 namespace psvae {
 
@@ -66,9 +67,11 @@ struct EpiBiasAct {
         for (int k = 0; k < 4; ++k) {
           uint32_t b = 0;
 #pragma unroll
-          for (int i = 7; i >= 0; --i) {
-            const float ns = 0.f - v[8 * k + i];                     // sign bit set  <=>  v > 0  (exact, also for +-0)
-            b = __funnelshift_l(__float_as_uint(ns), b, 1);
+          for (int i = 6; i >= 0; i -= 2) {
+            float n0, n1;
+            ptx::sub2(n0, n1, 0.f, 0.f, v[8 * k + i], v[8 * k + i + 1]);      // sign bit set  <=>  v > 0  (exact, also for +-0); one FADD2 per pair
+            b = __funnelshift_l(__float_as_uint(n1), b, 1);
+            b = __funnelshift_l(__float_as_uint(n0), b, 1);
           }
           w[k] = b;
         }
@@ -130,12 +133,16 @@ struct EpiMse {
                                                float& red) const {
     if (valid && col + 32 <= N) {
       if (x_hat) store_vec<32>(x_hat + row * ldxh + col, v);
+      float r0 = 0.f, r1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const float d = v[i] - aux[i];
-        red = fmaf(d, d, red);
-        v[i] = d * scale;
+      for (int i = 0; i < 32; i += 2) {      // packed pairs: FADD2 / FFMA2 / FMUL2
+        float d0, d1;
+        ptx::sub2(d0, d1, v[i], v[i + 1], aux[i], aux[i + 1]);
+        ptx::fma2(r0, r1, d0, d1, d0, d1);
+        ptx::scale2(d0, d1, scale);
+        v[i] = d0; v[i + 1] = d1;
       }
+      red += r0 + r1;
     } else {
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
@@ -224,8 +231,10 @@ struct EpiStore {
   __device__ __forceinline__ uint32_t tc_pre(int64_t row, int col, bool valid) const { return 0u; }
   __device__ __forceinline__ void tc_transform(int64_t row, int col, int N, bool valid, float (&v)[32], const float (&aux)[32], uint32_t pre,
                                                float& red) const {
+    if (alpha != 1.f) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) v[i] *= alpha;
+      for (int i = 0; i < 32; i += 2) ptx::scale2(v[i], v[i + 1], alpha);
+    }
   }
 };
 

@@ -250,6 +250,30 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
   };
 
   auto tile_g = [&](int64_t n_t) { return s.groups > 1 ? (int32_t)(((uint32_t)n_t * (uint32_t)BN) / (uint32_t)s.grp_n) : 0; };
+  // (n, m, split) of the tiles work_id, work_id + work_stride, ...: advanced incrementally -- the three divisions per tile and role were 7 % of
+  // the warp instructions of the thin layers (ncu, profiles/r02_ncu_epilogue_inst_mix.txt).  MULTI keeps the problem-list lookup above.
+  struct TileWalk {
+    uint32_t n, m, sp, dn, dm, dsp, nt, mt;
+    __device__ __forceinline__ void init(uint32_t t0, uint32_t stride, uint32_t n_tiles_, uint32_t m_tiles_) {
+      nt = n_tiles_; mt = m_tiles_;
+      n = t0 % nt;
+      const uint32_t q = t0 / nt;
+      m = q % mt; sp = q / mt;
+      dn = stride % nt;
+      const uint32_t dq = stride / nt;
+      dm = dq % mt; dsp = dq / mt;
+    }
+    __device__ __forceinline__ void next() {
+      n += dn;
+      uint32_t carry = 0;
+      if (n >= nt) { n -= nt; carry = 1; }
+      m += dm + carry;
+      sp += dsp;
+      if (m >= mt) { m -= mt; ++sp; }
+    }
+  };
+  TileWalk walk;
+  if constexpr (!MULTI) walk.init((uint32_t)work_id, (uint32_t)work_stride, n_tiles32, m_tiles32);
 
   float red = 0.f;
   float lat_kl = 0.f, lat_nll = 0.f, lat_acc = 0.f;      // kLat: this thread's share of the KL sum, the NLL sum and the correct-prediction count
@@ -322,9 +346,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
       };
       int stage = 0;
       uint32_t phase = 0;
-      for (int64_t tile = work_id; tile < num_tiles; tile += work_stride) {
-        const int64_t m_t = tile_m(tile), n_t = tile_n(tile),
-                      sp = tile_sp(tile);
+      for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, walk.next()) {
+        const int64_t m_t = MULTI ? tile_m(tile) : (int64_t)walk.m, n_t = MULTI ? tile_n(tile) : (int64_t)walk.n,
+                      sp = MULTI ? tile_sp(tile) : (int64_t)walk.sp;
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         if constexpr (MULTI) {
           const int p = item_problem(tile);
@@ -356,8 +380,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
       int stage = 0;
       uint32_t phase = 0;
       int64_t it = 0;
-      for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
-        const int64_t sp = tile_sp(tile);
+      for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it, walk.next()) {
+        const int64_t sp = MULTI ? tile_sp(tile) : (int64_t)walk.sp;
         const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
         const int acc = (int)(it & 1);
         const uint32_t acc_phase = (uint32_t)((it >> 1) & 1);
@@ -419,6 +443,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
     constexpr int COLS_PER_WARP = Cfg::kColsPerWarp;
     constexpr int CH = COLS_PER_WARP / 32;   // 32-column blocks per tile for this warp
     uint8_t* const obuf0 = smem + Cfg::kEpiOff + ew * Cfg::kEpiWarpBytes;   // staged output block(s)
+    const uint32_t obuf0_s = ptx::smem_u32(obuf0);
     uint8_t* abuf = obuf0 + Cfg::kOutBufs * Cfg::kOutBytes;                  // staged auxiliary block
     uint32_t aux_phase = 0;
     const bool do_store = epi.out != nullptr;
@@ -451,9 +476,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
       }
     };
     int64_t it = 0;
-    for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it) {
-      const int64_t m_t = tile_m(tile), n_t = tile_n(tile),
-                      sp = tile_sp(tile);
+    for (int64_t tile = work_id; tile < num_tiles; tile += work_stride, ++it, walk.next()) {
+      const int64_t m_t = MULTI ? tile_m(tile) : (int64_t)walk.m, n_t = MULTI ? tile_n(tile) : (int64_t)walk.n,
+                      sp = MULTI ? tile_sp(tile) : (int64_t)walk.sp;
       const int64_t kb0 = sp * kb_per_split, kb1 = min(kb_total, kb0 + kb_per_split);
       const int acc = (int)(it & 1);
       if constexpr (EG2) {
@@ -650,11 +675,16 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
           }
         }
         ptx::tmem_ld_wait(acc_r);
+        if (zero_acc) {                      // empty K range (warp-uniform; a per-element select cost 32 instructions per block)
+#pragma unroll
+          for (int i = 0; i < 32; ++i) acc_r[i] = 0u;
+        }
         float v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          v[i] = zero_acc ? 0.f : __uint_as_float(acc_r[i]);
-          if constexpr (Epi::kBias) v[i] += bv[i];
+        for (int i = 0; i < 32; i += 2) {
+          v[i] = __uint_as_float(acc_r[i]);
+          v[i + 1] = __uint_as_float(acc_r[i + 1]);
+          if constexpr (Epi::kBias) ptx::add2(v[i], v[i + 1], bv[i], bv[i + 1]);
         }
         float aux[32];
         if constexpr (kAux) {
@@ -702,6 +732,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
           }
           // WIDE (bf16, BN >= 128): two consecutive 32-column chunks share one 32 x 128-byte block, one fence and one TMA store
           uint8_t* const obuf = obuf0 + (Cfg::kOutBufs == 2 ? ((WIDE ? (c >> 1) : c) & 1) * Cfg::kOutBytes : 0);
+          const uint32_t obuf_s = obuf0_s + (Cfg::kOutBufs == 2 ? ((WIDE ? (c >> 1) : c) & 1) * Cfg::kOutBytes : 0);
           const int part = WIDE ? (c & 1) : 0;
           const bool opens = !WIDE || part == 0;
           const bool closes = !WIDE || part == 1 || col + 32 >= pN || c + 1 == CH;
@@ -727,13 +758,14 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
                 u.z = pack_bf16x2(v[j * 8 + 4], v[j * 8 + 5]);
                 u.w = pack_bf16x2(v[j * 8 + 6], v[j * 8 + 7]);
               }
-              if constexpr (WIDE) *reinterpret_cast<uint4*>(obuf + swz_off<128>(lane, part * 4 + j)) = u;
-              else *reinterpret_cast<uint4*>(obuf + swz_off<64>(lane, j)) = u;
+              if constexpr (WIDE) ptx::sts128(obuf_s + swz_off<128>(lane, part * 4 + j), u.x, u.y, u.z, u.w);
+              else ptx::sts128(obuf_s + swz_off<64>(lane, j), u.x, u.y, u.z, u.w);
             }
           } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(obuf + swz_off<128>(lane, j)) = make_float4(v[j * 4], v[j * 4 + 1], v[j * 4 + 2], v[j * 4 + 3]);
+              ptx::sts128(obuf_s + swz_off<128>(lane, j), __float_as_uint(v[j * 4]), __float_as_uint(v[j * 4 + 1]), __float_as_uint(v[j * 4 + 2]),
+                          __float_as_uint(v[j * 4 + 3]));
           }
           if (closes) {
             ptx::fence_proxy_async_smem();     // generic-proxy writes -> visible to the TMA (async proxy)
@@ -745,7 +777,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
                 const bool have = part == 1 || lane < 16;
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
-                  const uint32_t u = *reinterpret_cast<const uint32_t*>(obuf + swz_off<128>(r, lane >> 2) + (lane & 3) * 4);
+                  const uint32_t u = ptx::lds32(obuf_s + swz_off<128>(r, lane >> 2) + (lane & 3) * 4);
                   s0 += __uint_as_float(u << 16);
                   s1 += __uint_as_float(u & 0xFFFF0000u);
                 }
@@ -756,7 +788,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
 #pragma unroll
                 for (int rr = 0; rr < 16; ++rr) {
                   const int r = 2 * rr + hw;
-                  const uint32_t u = *reinterpret_cast<const uint32_t*>(obuf + swz_off<64>(r, w >> 2) + (w & 3) * 4);
+                  const uint32_t u = ptx::lds32(obuf_s + swz_off<64>(r, w >> 2) + (w & 3) * 4);
                   s0 += __uint_as_float(u << 16);
                   s1 += __uint_as_float(u & 0xFFFF0000u);
                 }

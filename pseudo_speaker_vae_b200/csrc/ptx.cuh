@@ -232,6 +232,53 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t (&r)[32]) {
                :
                : "memory");
 }
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2 work on 64-bit register pairs; tcgen05.ld and 128-bit loads deliver aligned pairs, so the
+// mov.b64 packing below costs no instruction).  The epilogues are issue-bound (ncu: 370 warp instructions per 32 x 32 block, IPC 0.4-0.5 per
+// scheduler): element-wise fp32 work at one instruction per TWO elements.
+__device__ __forceinline__ uint64_t f2_pack(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void f2_unpack(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+// (a0, a1) += (b0, b1)
+__device__ __forceinline__ void add2(float& a0, float& a1, float b0, float b1) {
+  uint64_t a = f2_pack(a0, a1);
+  const uint64_t b = f2_pack(b0, b1);
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  f2_unpack(a, a0, a1);
+}
+// (d0, d1) = (a0, a1) - (b0, b1)
+__device__ __forceinline__ void sub2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  uint64_t d;
+  const uint64_t a = f2_pack(a0, a1), b = f2_pack(b0, b1);
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  f2_unpack(d, d0, d1);
+}
+// (a0, a1) *= (s, s)
+__device__ __forceinline__ void scale2(float& a0, float& a1, float s) {
+  uint64_t a = f2_pack(a0, a1);
+  const uint64_t b = f2_pack(s, s);
+  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(a) : "l"(b));
+  f2_unpack(a, a0, a1);
+}
+// (c0, c1) += (a0, a1) * (b0, b1)
+__device__ __forceinline__ void fma2(float& c0, float& c1, float a0, float a1, float b0, float b1) {
+  uint64_t c = f2_pack(c0, c1);
+  const uint64_t a = f2_pack(a0, a1), b = f2_pack(b0, b1);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+  f2_unpack(c, c0, c1);
+}
+// 16-byte store / 4-byte load with a 32-bit shared-memory address (a generic pointer makes the compiler emit generic ST / LD with 64-bit address math)
+__device__ __forceinline__ void sts128(uint32_t saddr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t saddr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(saddr) : "memory");
+  return v;
+}
+
 // two fp32 -> packed bf16x2 (lo in the low half), round to nearest even, negative values (and NaN) flushed to +0: ReLU for free
 __device__ __forceinline__ uint32_t pack_bf16x2_relu(float lo, float hi) {
   uint32_t d;
