@@ -103,6 +103,7 @@ struct TcShape {
   int32_t splits;   // split-K factor (>= 1)
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;   // UMMA smem-descriptor strides (bytes)
   int32_t stages;   // depth of the operand ring actually used (<= the compiled kStages; option "tc_max_stages")
+  int32_t rev_splits;   // MULTI: walk the batch ranges from the end (the rows the backward pass wrote last are the ones still in L2)
   unsigned long long* trace;   // profiling (option "tc_trace_ptr"): per CTA 16 cycle counters -- see tools/tc_trace.py; nullptr = off
   // grouped (block-diagonal) launch: `groups` independent GEMMs laid side by side.  A is [M][groups * grp_k] (group g owns the k range
   // [g * grp_k, (g+1) * grp_k)), C is [M][groups * grp_n]; B stacks the groups' weights along its row dimension: K-major B
@@ -242,7 +243,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
   auto tile_sp = [&](int64_t t) {
     if constexpr (MULTI) {
       const int p = item_problem(t);
-      return (int64_t)(((uint32_t)t - (uint32_t)mp->tile_begin[p]) / ((uint32_t)mp->n_tiles[p] * (uint32_t)mp->m_tiles[p]));
+      const uint32_t v = ((uint32_t)t - (uint32_t)mp->tile_begin[p]) / ((uint32_t)mp->n_tiles[p] * (uint32_t)mp->m_tiles[p]);
+      return (int64_t)(s.rev_splits ? (uint32_t)s.splits - 1u - v : v);      // reduce-add: any order of the batch ranges gives the same sum
     } else {
       const uint32_t sp = (uint32_t)t / (n_tiles32 * m_tiles32);
       return (int64_t)sp;
@@ -778,8 +780,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
 #pragma unroll
                 for (int r = 0; r < 32; ++r) {
                   const uint32_t u = ptx::lds32(obuf_s + swz_off<128>(r, lane >> 2) + (lane & 3) * 4);
-                  s0 += __uint_as_float(u << 16);
-                  s1 += __uint_as_float(u & 0xFFFF0000u);
+                  ptx::add2(s0, s1, __uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
                 }
                 if (have) { cs_acc[c >> 1][0] += s0; cs_acc[c >> 1][1] += s1; }
               } else {
@@ -789,8 +790,7 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
                 for (int rr = 0; rr < 16; ++rr) {
                   const int r = 2 * rr + hw;
                   const uint32_t u = ptx::lds32(obuf_s + swz_off<64>(r, w >> 2) + (w & 3) * 4);
-                  s0 += __uint_as_float(u << 16);
-                  s1 += __uint_as_float(u & 0xFFFF0000u);
+                  ptx::add2(s0, s1, __uint_as_float(u << 16), __uint_as_float(u & 0xFFFF0000u));
                 }
                 s0 += __shfl_xor_sync(0xffffffffu, s0, 16);
                 s1 += __shfl_xor_sync(0xffffffffu, s1, 16);
@@ -972,6 +972,7 @@ int gemm_tc_launch_bn(const TcOperand& A, const TcOperand& B, int64_t M, int N, 
   tc_desc_strides(A_MN, &s.a_lbo, &s.a_sbo);
   tc_desc_strides(B_MN, &s.b_lbo, &s.b_sbo);
   s.stages = Cfg::kStages;
+  s.rev_splits = 0;
   if (tc_max_stages() >= 2 && tc_max_stages() < s.stages) s.stages = tc_max_stages();
   s.trace = tc_trace_ptr();
   s.groups = grp.groups; s.grp_n = grp.grp_n; s.grp_k = grp.grp_k;
@@ -1107,7 +1108,7 @@ struct TcWgradProblem {
 // All of a step's wgrads in ONE persistent launch (see TcMulti).  256 x 256 tiles on CTA pairs for every problem: a problem narrower than the
 // tile (the 64-wide latent layers) reads only its valid columns (TMA zero-fills the rest without DRAM traffic) -- these launches are bound by
 // streaming the batch, not by the MMAs.
-static inline int gemm_tc_launch_multi_wgrad(const TcWgradProblem* probs, int count, int64_t rows, cudaStream_t st) {
+static inline int gemm_tc_launch_multi_wgrad(const TcWgradProblem* probs, int count, int64_t rows, cudaStream_t st, int rev_splits = 0) {
   using Epi = EpiStore;
   constexpr int BN = 256, CG = 2;
   using Cfg = TcCfg<BN, Epi, CG>;
@@ -1147,6 +1148,7 @@ static inline int gemm_tc_launch_multi_wgrad(const TcWgradProblem* probs, int co
   TcShape s;
   memset(&s, 0, sizeof(s));
   s.M = probs[0].M; s.N = probs[0].N; s.K = rows; s.splits = (int32_t)S;
+  s.rev_splits = rev_splits;
   tc_desc_strides(true, &s.a_lbo, &s.a_sbo);
   tc_desc_strides(true, &s.b_lbo, &s.b_sbo);
   s.stages = Cfg::kStages;

@@ -998,4 +998,146 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_clf_kernel(const float* __r
   }
 }
 
+// The same pass for the tcgen05 mode's common shape (bf16 sigma eps / 2 and outputs, L % 8 == 0, at most 4 classes in total): one thread owns
+// EIGHT consecutive latent columns of a row per trip and two rows are in flight (16 independent 16-byte loads per thread before the first use;
+// 128 registers at two blocks per SM).  The 4-column form above ran at 2.3 TB/s with spills at its 80-register cap
+// (profiles/r02_ncu_full_step_v20.csv: 26.7 us for 77 MB); d loss / d logits of a row arrives as one float4.
+template <int NC>
+__global__ void __launch_bounds__(256, 2) latent_bwd_clf8_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
+                                                                  const bf16* __restrict__ hs, int64_t rows, int L, float kl_over_b, bf16* __restrict__ dmu,
+                                                                  bf16* __restrict__ dls, float* __restrict__ bias_grad, int64_t ld_d, ClfBwdArgs ca) {
+  PSVAE_GRID_DEP();
+  static_assert(NC >= 1 && NC <= 4, "one float4 of d loss / d logits per row");
+  extern __shared__ float lb_smem[];        // [256][8]
+  const int tpr = L >> 3;                   // threads per row
+  const int rpb = 256 / tpr;                // rows per block and trip
+  const int cgp = (int)threadIdx.x % tpr, col8 = cgp << 3, rin = (int)threadIdx.x / tpr;
+  const int nc = ca.total_classes;
+  auto head_of = [&](int cc) {
+    int h = 0;
+    for (int i = 0; i < ca.n_heads; ++i)
+      if (cc >= ca.head_off[i] && cc < ca.head_off[i] + ca.head_classes[i]) h = i;
+    return h;
+  };
+  // the classifier weights live in shared memory behind the reduction array ([NC][L] floats, read back as two 16-byte loads per class and trip:
+  // 16 fewer live registers than a private copy)
+  float* const Wsh = lb_smem + 256 * 8;
+  for (int i = threadIdx.x; i < NC * L; i += 256) {
+    const int cc = i / L, k = i % L;
+    float wv = 0.f;
+    if (cc < nc) {
+      const int h = head_of(cc);
+      wv = ca.params[ca.w_off[h] + (int64_t)(cc - ca.head_off[h]) * L + k];
+    }
+    Wsh[i] = wv;
+  }
+  __syncthreads();
+  float accW[NC][8], accb[NC];
+#pragma unroll
+  for (int cc = 0; cc < NC; ++cc) {
+    accb[cc] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accW[cc][j] = 0.f;
+  }
+  float sm_[8], sl_[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sm_[j] = sl_[j] = 0.f;
+  struct Oct { float4 g0, g1, m0, m1, l0, l1, gr; uint4 e; };
+  auto load_oct = [&](int64_t row, Oct& t) {
+    const int64_t o = row * L + col8;
+    t.g0 = __ldg(reinterpret_cast<const float4*>(dz + o));
+    t.g1 = __ldg(reinterpret_cast<const float4*>(dz + o) + 1);
+    t.m0 = __ldg(reinterpret_cast<const float4*>(mu + o));
+    t.m1 = __ldg(reinterpret_cast<const float4*>(mu + o) + 1);
+    t.l0 = __ldg(reinterpret_cast<const float4*>(ls + o));
+    t.l1 = __ldg(reinterpret_cast<const float4*>(ls + o) + 1);
+    t.e = __ldg(reinterpret_cast<const uint4*>(hs + o));
+    t.gr = __ldg(reinterpret_cast<const float4*>(ca.g_rows + row * CLF_MAXC));
+  };
+  auto do_oct = [&](int64_t row, const Oct& t) {
+    const float g[8] = {t.g0.x, t.g0.y, t.g0.z, t.g0.w, t.g1.x, t.g1.y, t.g1.z, t.g1.w};
+    const float m[8] = {t.m0.x, t.m0.y, t.m0.z, t.m0.w, t.m1.x, t.m1.y, t.m1.z, t.m1.w};
+    const float l[8] = {t.l0.x, t.l0.y, t.l0.z, t.l0.w, t.l1.x, t.l1.y, t.l1.z, t.l1.w};
+    const uint32_t ew[4] = {t.e.x, t.e.y, t.e.z, t.e.w};
+    const float gr[4] = {t.gr.x, t.gr.y, t.gr.z, t.gr.w};
+    float c[8], om[8], ol[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = 0.f;
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) {
+      if (cc < nc) {
+        const float4 w0 = *reinterpret_cast<const float4*>(Wsh + cc * L + col8), w1 = *reinterpret_cast<const float4*>(Wsh + cc * L + col8 + 4);
+        const float wc[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          c[j] = fmaf(gr[cc], wc[j], c[j]);
+          accW[cc][j] = fmaf(gr[cc], m[j], accW[cc][j]);
+        }
+        if (cgp == 0) accb[cc] += gr[cc];
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float e = __uint_as_float((j & 1) ? (ew[j >> 1] & 0xFFFF0000u) : (ew[j >> 1] << 16));
+      om[j] = g[j] + kl_over_b * m[j] + c[j];
+      ol[j] = fmaf(g[j], e, 0.5f * kl_over_b * expm1f(l[j]));
+      sm_[j] += om[j];
+      sl_[j] += ol[j];
+    }
+    uint4 um, ul;
+    um.x = pack_bf16x2(om[0], om[1]); um.y = pack_bf16x2(om[2], om[3]); um.z = pack_bf16x2(om[4], om[5]); um.w = pack_bf16x2(om[6], om[7]);
+    ul.x = pack_bf16x2(ol[0], ol[1]); ul.y = pack_bf16x2(ol[2], ol[3]); ul.z = pack_bf16x2(ol[4], ol[5]); ul.w = pack_bf16x2(ol[6], ol[7]);
+    *reinterpret_cast<uint4*>(dmu + row * ld_d + col8) = um;
+    *reinterpret_cast<uint4*>(dls + row * ld_d + col8) = ul;
+  };
+  const int64_t step = (int64_t)gridDim.x * rpb;
+  for (int64_t r = (int64_t)blockIdx.x * rpb + rin; r < rows; r += 2 * step) {
+    Oct a, b;
+    const bool two = r + step < rows;
+    load_oct(r, a);
+    if (two) load_oct(r + step, b);
+    do_oct(r, a);
+    if (two) do_oct(r + step, b);
+  }
+  // bias gradients of the encoders' last Linear ([mu | sigma], atomics into the zeroed gradient): the tpr-strided threads own the same 8 columns
+#pragma unroll
+  for (int which = 0; which < 2; ++which) {
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) lb_smem[threadIdx.x * 8 + j] = which ? sl_[j] : sm_[j];
+    __syncthreads();
+    if ((int)threadIdx.x < L) {
+      const int col = threadIdx.x, grp = col >> 3, j = col & 7;
+      float t = 0.f;
+      for (int th = grp; th < 256; th += tpr) t += lb_smem[th * 8 + j];
+      atomicAdd(bias_grad + which * L + col, t);
+    }
+  }
+  // the classifier's own gradients, one class at a time through the same staging array
+#pragma unroll
+  for (int cc = 0; cc < NC; ++cc) {
+    if (cc < nc) {            // block-uniform
+      __syncthreads();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) lb_smem[threadIdx.x * 8 + j] = accW[cc][j];
+      __syncthreads();
+      const int h = head_of(cc), lc = cc - ca.head_off[h];
+      if ((int)threadIdx.x < L) {
+        const int col = threadIdx.x, grp = col >> 3, j = col & 7;
+        float t = 0.f;
+        for (int th = grp; th < 256; th += tpr) t += lb_smem[th * 8 + j];
+        atomicAdd(ca.grads + ca.w_off[h] + (int64_t)lc * L + col, t);
+      }
+      __syncthreads();
+      if (cgp == 0) lb_smem[rin] = accb[cc];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int th = 0; th < rpb; ++th) t += lb_smem[th];
+        atomicAdd(ca.grads + ca.b_off[h] + lc, t);
+      }
+    }
+  }
+}
+
 }  // namespace psvae

@@ -17,6 +17,7 @@
 
 #include <atomic>
 #include <map>
+#include <utility>
 #include <mutex>
 #include <tuple>
 
@@ -66,6 +67,8 @@ struct Options {
                                        //    Measured on its own (round 2, A/B): 0.7840 -> 0.7887 ms/step -- slower, so off; the fused head uses the same backward regardless
   int64_t tc_epi_groups = 1;           // 1: thin (K <= 128) BN = 256 forward / dgrad launches use two epilogue groups on alternate tiles (EG2).
                                        //    Measured (round 2, A/B): 0.7832 -> 0.7733 ms/step
+  int64_t wgrad_order = 1;             // merged wgrad: 0 = problems in the order the backward pass queued them, 1 = newest first (the gradients written last are
+                                       //    still in L2: 0.6826 -> 0.6778 ms/step, A/B round 2), 2 = newest first + batch ranges from the end (same as 1)
   int64_t tc_epi_groups_max_k = 128;   // largest contraction length K that still takes the two-epilogue-group kernel
   int64_t tc_merged_wgrad = 1;         // 1 (fast tcgen05 mode): every wgrad of the step runs in ONE persistent launch at the end of the backward pass (gemm_tc_launch_multi_wgrad):
                                        //    the ~8 us fixed cost of a wgrad launch is paid once instead of 8 times
@@ -399,7 +402,11 @@ static int flush_wgrads(StepBufs<TAct>& w, int64_t rows, cudaStream_t st) {
   if (w.n_pending == 0) return 0;
   const int n = w.n_pending;
   w.n_pending = 0;
-  return gemm_tc_launch_multi_wgrad(w.pending, n, rows, st);
+  // option wgrad_order: 1 = newest gradient first (the tensors the backward pass wrote last are the ones still in L2), 2 = and each problem's
+  // batch ranges from the end
+  if (g_opt.wgrad_order >= 1)
+    for (int i = 0; i < n / 2; ++i) std::swap(w.pending[i], w.pending[n - 1 - i]);
+  return gemm_tc_launch_multi_wgrad(w.pending, n, rows, st, g_opt.wgrad_order >= 2 ? 1 : 0);
 }
 
 // the fused classifier kernel covers the common shape: heads directly on mu (no trunk), L = 32/64/96/128, <= 8 classes in total
@@ -1170,10 +1177,28 @@ static int run_step(const StepArgs& a) {
     cb.params = P; cb.grads = G; cb.g_rows = w.clf_grows;
     const size_t smem = 256 * 8 * sizeof(float);
     float* bias_grad = G + d->enc_b[n.nh];
+    bool done8 = false;
+    if constexpr (sizeof(TAct) == 2) {
+      // the 8-columns-per-thread form: L a multiple of 8 with L / 8 dividing 256, at most 4 classes
+      if (n.L % 8 == 0 && 256 % (n.L / 8) == 0 && n.L <= 256 && cb.total_classes <= 4) {
+        const int rpb = 256 / (n.L / 8);
+        int64_t nb = ceil_div64(B, 2 * rpb);
+        if (nb > 2 * PSVAE_NUM_SMS) nb = 2 * PSVAE_NUM_SMS;
+        if (nb < 1) nb = 1;
+#define PSVAE_LBC8(NCV)                                                                                                                       \
+        launch_dep(latent_bwd_clf8_kernel<NCV>, dim3((unsigned)nb), dim3(256), smem + (size_t)NCV * n.L * sizeof(float), st, w.dz, mu, ls, w.hs, B, n.L, a.kl_w / (float)B, w.dmu, w.dls, \
+                   bias_grad, (int64_t)2 * n.L, cb)
+        if (cb.total_classes <= 2) PSVAE_LBC8(2);
+        else PSVAE_LBC8(4);
+#undef PSVAE_LBC8
+        done8 = true;
+      }
+    }
 #define PSVAE_LBC(NCV)                                                                                                                          \
     launch_dep(latent_bwd_clf_kernel<TAct, NCV>, dim3(blocks), dim3(256), smem, st, w.dz, mu, ls, w.hs, B * n.L, n.L, a.kl_w / (float)B, w.dmu, w.dls, \
                bias_grad, (int64_t)2 * n.L, cb)
-    if (cb.total_classes <= 2) PSVAE_LBC(2);
+    if (done8) {}
+    else if (cb.total_classes <= 2) PSVAE_LBC(2);
     else if (cb.total_classes == 3) PSVAE_LBC(3);
     else PSVAE_LBC(CLF_MAXC);
 #undef PSVAE_LBC
@@ -1386,6 +1411,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "pdl")) { g_opt.pdl = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_grouped")) { g_opt.tc_grouped = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_epi_groups")) { g_opt.tc_epi_groups = value ? 1 : 0; return 0; }
+  if (!strcmp(name, "wgrad_order")) { g_opt.wgrad_order = value; return 0; }
   if (!strcmp(name, "tc_epi_groups_max_k")) { g_opt.tc_epi_groups_max_k = value < 0 ? 0 : value; return 0; }
   if (!strcmp(name, "clf_grad_in_bwd")) { g_opt.clf_grad_in_bwd = value ? 1 : 0; return 0; }
   if (!strcmp(name, "fused_head")) { g_opt.fused_head = value ? 1 : 0; return 0; }
@@ -1409,6 +1435,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "pdl")) return g_opt.pdl;
   if (!strcmp(name, "tc_grouped")) return g_opt.tc_grouped;
   if (!strcmp(name, "tc_epi_groups")) return g_opt.tc_epi_groups;
+  if (!strcmp(name, "wgrad_order")) return g_opt.wgrad_order;
   if (!strcmp(name, "tc_epi_groups_max_k")) return g_opt.tc_epi_groups_max_k;
   if (!strcmp(name, "clf_grad_in_bwd")) return g_opt.clf_grad_in_bwd;
   if (!strcmp(name, "fused_head")) return g_opt.fused_head;

@@ -813,17 +813,19 @@ def test_engine_variants_reproduce_the_default_path(opts):
             G.L.set_option(k, v)
 
 
-FAST_VARIANTS_OFF = dict(tc_epi_groups=0, clf_grad_in_bwd=0, fused_head=0, tc_merged_wgrad=0)
+FAST_VARIANTS_OFF = dict(tc_epi_groups=0, clf_grad_in_bwd=0, fused_head=0, tc_merged_wgrad=0, wgrad_order=0)
 
 
 @pytest.mark.parametrize("opts", [dict(tc_epi_groups=1), dict(clf_grad_in_bwd=1), dict(fused_head=1), dict(tc_merged_wgrad=1),
-                                  dict(tc_epi_groups=1, fused_head=1, tc_merged_wgrad=1)])
+                                  dict(tc_epi_groups=1, fused_head=1, tc_merged_wgrad=1), dict(tc_merged_wgrad=1, wgrad_order=1),
+                                  dict(tc_merged_wgrad=1, wgrad_order=2)])
 def test_fast_mode_engine_variants_agree_with_the_plain_path(opts):
     """The fast-mode variants that are ON by default since round 2 (validated on a B200 by tools/validate_experimental.sh, then A/B-timed)
     against the path with all of them off.  tc_epi_groups (two epilogue groups on alternate tiles for the K <= 128 layers): forward outputs
     bit-identical, losses / gradients equal up to summation order.  clf_grad_in_bwd: the classifier's backward formed in the latent backward
     kernel from d loss / d logits.  fused_head: encoder heads + reparameterisation + KL + classifier forward in one kernel (its
-    accumulators come from 32-column MMAs: outputs are compared to 1e-5, not bit for bit).  tc_merged_wgrad: every wgrad of the step in one persistent launch at the end of the backward pass."""
+    accumulators come from 32-column MMAs: outputs are compared to 1e-5, not bit for bit).  tc_merged_wgrad: every wgrad of the step in one persistent launch at the end of the backward pass
+    (wgrad_order: its problems newest-first / batch ranges from the end)."""
     G = _gu()
     module, cfg = _big_module(G, "bf16")
     hot = module.hot_path
