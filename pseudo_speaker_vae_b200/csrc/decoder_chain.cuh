@@ -265,6 +265,7 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
     // region needs is between those two: a 64-thread named barrier before the next tile's first hd1 write.
     const int pair = (cg >> 1) * 4 + (ew & 3);
     uint8_t* const stage_out = hd1 + (cg >> 1) * DC_KBLOCK_BYTES + quarter * 4096 + (cg & 1) * 2048;
+    const uint32_t stage_out_s = ptx::smem_u32(stage_out);
     // One layer's NC accumulator chunks of one tile: L0 -> hd0, L1 -> the hd1 chunk buffer.  `tn` = this CTA pair's running index of `tile`.
     auto hidden = [&](const int layer, const int64_t tile, const uint32_t tile_n) {
       const int32_t row_base = (int32_t)(tile * 2 * DC_ROWS) + (int32_t)cta_rank * DC_ROWS + quarter * 32;
@@ -316,14 +317,21 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
             if (grow < a.rows) (layer == 0 ? a.mask0 : a.mask1)[(int64_t)(c * 4 + cg) * a.mask_ld + grow] = bits;
           }
 #endif
+          {
+            // bias add as packed fp32 pairs (FADD2), ReLU inside the bf16 pack, 16-byte stores through 32-bit shared addresses
+            const uint32_t dst_s = ptx::smem_u32(dst);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 u;
-            u.x = ptx::pack_bf16x2_relu(__uint_as_float(r[8 * j + 0]) + bv[8 * j + 0], __uint_as_float(r[8 * j + 1]) + bv[8 * j + 1]);
-            u.y = ptx::pack_bf16x2_relu(__uint_as_float(r[8 * j + 2]) + bv[8 * j + 2], __uint_as_float(r[8 * j + 3]) + bv[8 * j + 3]);
-            u.z = ptx::pack_bf16x2_relu(__uint_as_float(r[8 * j + 4]) + bv[8 * j + 4], __uint_as_float(r[8 * j + 5]) + bv[8 * j + 5]);
-            u.w = ptx::pack_bf16x2_relu(__uint_as_float(r[8 * j + 6]) + bv[8 * j + 6], __uint_as_float(r[8 * j + 7]) + bv[8 * j + 7]);
-            *reinterpret_cast<uint4*>(dst + dc_swz128(r_in, (cg & 1) * 4 + j)) = u;
+            for (int j = 0; j < 4; ++j) {
+              float v[8];
+#pragma unroll
+              for (int i = 0; i < 8; i += 2) {
+                v[i] = __uint_as_float(r[8 * j + i]);
+                v[i + 1] = __uint_as_float(r[8 * j + i + 1]);
+                ptx::add2(v[i], v[i + 1], bv[8 * j + i], bv[8 * j + i + 1]);
+              }
+              ptx::sts128(dst_s + dc_swz128(r_in, (cg & 1) * 4 + j), ptx::pack_bf16x2_relu(v[0], v[1]), ptx::pack_bf16x2_relu(v[2], v[3]),
+                          ptx::pack_bf16x2_relu(v[4], v[5]), ptx::pack_bf16x2_relu(v[6], v[7]));
+            }
           }
           ptx::fence_proxy_async_smem();           // generic-proxy writes -> visible to the tensor core's (async proxy) operand reads
           __syncwarp();
@@ -435,8 +443,12 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
         uint32_t r[32];
         ptx::tmem_ld_32x32_issue(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(256 + col0), r);
         float bv[32];
+        if (col0 + 32 <= a.D) {          // arena offsets are multiples of 8 floats: 16-byte loads
+          load_vec<32>(a.b2 + col0, bv);
+        } else {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) bv[i] = (col0 + i < a.D) ? __ldg(a.b2 + col0 + i) : 0.f;
+          for (int i = 0; i < 32; ++i) bv[i] = (col0 + i < a.D) ? __ldg(a.b2 + col0 + i) : 0.f;
+        }
         ptx::tmem_ld_wait(r);
 #pragma unroll
         for (int sb = 0; sb < 2; ++sb) {
@@ -447,8 +459,10 @@ decoder_chain_kernel(const __grid_constant__ CUtensorMap tm_w0, const __grid_con
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int i = sb * 16 + j * 4;
-            *reinterpret_cast<float4*>(stage_out + dc_swz64(lane, j)) =
-                make_float4(__uint_as_float(r[i]) + bv[i], __uint_as_float(r[i + 1]) + bv[i + 1], __uint_as_float(r[i + 2]) + bv[i + 2], __uint_as_float(r[i + 3]) + bv[i + 3]);
+            float v0 = __uint_as_float(r[i]), v1 = __uint_as_float(r[i + 1]), v2 = __uint_as_float(r[i + 2]), v3 = __uint_as_float(r[i + 3]);
+            ptx::add2(v0, v1, bv[i], bv[i + 1]);
+            ptx::add2(v2, v3, bv[i + 2], bv[i + 3]);
+            ptx::sts128(stage_out_s + dc_swz64(lane, j), __float_as_uint(v0), __float_as_uint(v1), __float_as_uint(v2), __float_as_uint(v3));
           }
           ptx::fence_proxy_async_smem();
           __syncwarp();

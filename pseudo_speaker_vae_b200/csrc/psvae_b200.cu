@@ -79,6 +79,8 @@ struct Options {
   int64_t tc_grouped = 1;              // 1: layers 1..n of the two encoders run as ONE block-diagonal launch each (forward and dgrad) instead of one per encoder
   int64_t pdl = 1;                     // 1: kernels are launched with programmatic stream serialization (their prologue overlaps the predecessor's tail)
   int64_t tc_trace_ptr = 0;            // profiling: device pointer of gridDim.x * 16 cycle counters the GEMM kernels fill (0 = off)
+  int64_t tc_trace_skip = 0;           // profiling: with tc_trace_select, tcgen05 launches to let pass before the one that gets the trace buffer
+  int64_t tc_trace_select = 0;         // profiling: 1 = only ONE launch is traced (set "tc_trace_skip" = k to pick the (k+1)-th launch from now on)
   int64_t tc_max_stages = 0;           // experiments: cap the depth of the operand ring (0 = what fits)
   int64_t deterministic = 0;           // 1: split-K / bias partials go through ordered two-stage sums instead of TMA reduce-add / atomics
 };
@@ -125,7 +127,16 @@ int tc_max_stages() { return (int)g_opt.tc_max_stages; }
 int tc_epi_groups() { return (int)g_opt.tc_epi_groups; }
 int tc_epi_groups_max_k() { return (int)g_opt.tc_epi_groups_max_k; }
 bool pdl_enabled() { return g_opt.pdl != 0; }
-unsigned long long* tc_trace_ptr() { return reinterpret_cast<unsigned long long*>(static_cast<uintptr_t>(g_opt.tc_trace_ptr)); }
+// profiling: the trace buffer goes to ONE launch -- the (tc_trace_skip + 1)-th tcgen05 launch after the option was set (0: every launch, as before)
+unsigned long long* tc_trace_ptr() {
+  if (!g_opt.tc_trace_ptr) return nullptr;
+  if (g_opt.tc_trace_skip < 0) return nullptr;                      // already delivered
+  if (g_opt.tc_trace_select) {
+    if (g_opt.tc_trace_skip > 0) { --g_opt.tc_trace_skip; return nullptr; }
+    g_opt.tc_trace_skip = -1;
+  }
+  return reinterpret_cast<unsigned long long*>(static_cast<uintptr_t>(g_opt.tc_trace_ptr));
+}
 int tc_grid_size() {
   DevInfo* d = nullptr;
   if (dev_info(&d) != 0) return PSVAE_NUM_SMS;
@@ -1408,6 +1419,8 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "langevin_generic")) { g_opt.langevin_generic = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_max_stages")) { g_opt.tc_max_stages = value < 0 ? 0 : value; return 0; }
   if (!strcmp(name, "tc_trace_ptr")) { g_opt.tc_trace_ptr = value; return 0; }
+  if (!strcmp(name, "tc_trace_skip")) { g_opt.tc_trace_skip = value; g_opt.tc_trace_select = 1; return 0; }
+  if (!strcmp(name, "tc_trace_select")) { g_opt.tc_trace_select = value ? 1 : 0; if (!value) g_opt.tc_trace_skip = 0; return 0; }
   if (!strcmp(name, "pdl")) { g_opt.pdl = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_grouped")) { g_opt.tc_grouped = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_epi_groups")) { g_opt.tc_epi_groups = value ? 1 : 0; return 0; }

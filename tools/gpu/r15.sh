@@ -1,0 +1,6 @@
+set -x
+TAG=${TAG:-r15}
+timeout 600 python -m pytest tests/test_gpu_chain.py -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
+timeout 200 python tools/sample_bench.py > gpurun_out/${TAG}_sample.log 2>&1; cat gpurun_out/${TAG}_sample.log
+timeout 200 python tools/chain_trace.py > gpurun_out/${TAG}_chain_trace.log 2>&1; cat gpurun_out/${TAG}_chain_trace.log
+timeout 200 python tools/langevin_bench.py > gpurun_out/${TAG}_langevin.log 2>&1; tail -12 gpurun_out/${TAG}_langevin.log
