@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define PSVAE_ABI_VERSION 3
+#define PSVAE_ABI_VERSION 4      /* 4: + psvae_adam_step_ex (amsgrad / maximize) */
 #define PSVAE_MAX_LAYERS 8      /* Linear layers per MLP (num_hidden + 1) */
 #define PSVAE_MAX_CLF_TRUNK 4   /* hidden Linear layers of the latent classifier */
 #define PSVAE_MAX_CLF_HEADS 4   /* output heads of the latent classifier */
@@ -141,6 +141,12 @@ int64_t psvae_get_option(const char* name);
  * reproduce them. */
 int psvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                     double eps, double weight_decay, int64_t step, double grad_scale, void* shadow_bf16, void* stream);
+/* The same update with the two torch.optim.Adam switches that `Adam(self.parameters(), **self.hparams["optimizer"])` (lightning.py:205) can
+ * reach: amsgrad (vmax = running maximum of v, [n] fp32, caller-allocated and zero-initialised; the denominator uses it) and maximize
+ * (the gradient is negated).  With both off this is psvae_adam_step. */
+int psvae_adam_step_ex(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, double lr, double beta1,
+                       double beta2, double eps, double weight_decay, int64_t step, double grad_scale, int32_t amsgrad,
+                       int32_t maximize, void* shadow_bf16, void* stream);
 
 /* ---- generator: replaces torch.randn / randn_like (model.py:57, inference.py:23,73,95) -------- */
 int psvae_philox_uint32(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, int64_t first_elem, void* stream);

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # PSVAE_B200_LIB: load another build of the same ABI instead (A/B timing of two kernel versions in one process tree; tools only)
 LIB_PATH = os.environ.get("PSVAE_B200_LIB") or os.path.join(HERE, "libpsvae_b200.so")
 
-PSVAE_ABI_VERSION = 3
+PSVAE_ABI_VERSION = 4
 MAX_LAYERS = 8
 MAX_CLF_TRUNK = 4
 MAX_CLF_HEADS = 4
@@ -28,7 +28,7 @@ LOSS_CONS, LOSS_CONS_ACC = 12, 13
 #: every symbol include/psvae_b200.h declares (tests check the library exports exactly these)
 EXPORTS = [
     "psvae_abi_version", "psvae_last_error_string", "psvae_model_desc_init", "psvae_workspace_bytes", "psvae_shadow_bytes",
-    "psvae_flops_per_sample", "psvae_set_option", "psvae_get_option", "psvae_adam_step", "psvae_philox_uint32", "psvae_philox_normal",
+    "psvae_flops_per_sample", "psvae_set_option", "psvae_get_option", "psvae_adam_step", "psvae_adam_step_ex", "psvae_philox_uint32", "psvae_philox_normal",
     "psvae_refresh_shadow", "psvae_forward", "psvae_decode", "psvae_train_fwd_bwd", "psvae_langevin", "psvae_gemm_bf16",
     "psvae_gemm_fp32", "psvae_gemm_probe", "psvae_launch_count", "psvae_consistency_desc_init", "psvae_consistency_workspace_bytes",
     "psvae_consistency_forward", "psvae_train_fwd_bwd_consistency", "psvae_vae_backward", "psvae_gather_rows",
@@ -84,6 +84,8 @@ def _declare(l: C.CDLL) -> None:
     l.psvae_flops_per_sample.argtypes = [D, I32]
     l.psvae_adam_step.restype = C.c_int
     l.psvae_adam_step.argtypes = [VP, VP, VP, VP, I64, DBL, DBL, DBL, DBL, DBL, I64, DBL, VP, VP]
+    l.psvae_adam_step_ex.restype = C.c_int
+    l.psvae_adam_step_ex.argtypes = [VP, VP, VP, VP, VP, I64, DBL, DBL, DBL, DBL, DBL, I64, DBL, C.c_int32, C.c_int32, VP, VP]
     l.psvae_philox_uint32.restype = C.c_int
     l.psvae_philox_uint32.argtypes = [VP, I64, U64, U64, I64, VP]
     l.psvae_philox_normal.restype = C.c_int

@@ -31,6 +31,31 @@ __device__ __forceinline__ void adam_one(float& p, float g, float& m, float& v, 
   const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
   p = p - a.lr_step * (m / denom);                        // addcdiv_(m, denom, value=-step_size)
 }
+// amsgrad (torch/optim/adam.py: max_exp_avg_sqs = maximum(max_exp_avg_sqs, exp_avg_sq); denom from the maximum) / maximize (grad = -grad)
+__device__ __forceinline__ void adam_one_ex(float& p, float g, float& m, float& v, float& vmax, const AdamArgs& a, bool amsgrad, bool maximize) {
+  g *= a.grad_scale;
+  if (maximize) g = -g;
+  if (a.weight_decay != 0.f) g = fmaf(a.weight_decay, p, g);
+  m = m + (g - m) * a.one_minus_beta1;
+  v = v * a.beta2 + a.one_minus_beta2 * g * g;
+  float vd = v;
+  if (amsgrad) { vmax = fmaxf(vmax, v); vd = vmax; }
+  const float denom = sqrtf(vd) / a.bc2_sqrt + a.eps;
+  p = p - a.lr_step * (m / denom);
+}
+// the general form: one element per thread and trip (these configurations are not on any benchmarked path)
+__global__ void __launch_bounds__(256) adam_ex_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                      float* __restrict__ vmax, int64_t n, AdamArgs a, int amsgrad, int maximize, bf16* __restrict__ shadow) {
+  PSVAE_GRID_DEP();
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    float pp = p[i], mm = m[i], vv = v[i], vx = amsgrad ? vmax[i] : 0.f;
+    adam_one_ex(pp, g[i], mm, vv, vx, a, amsgrad != 0, maximize != 0);
+    p[i] = pp; m[i] = mm; v[i] = vv;
+    if (amsgrad) vmax[i] = vx;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pp);
+  }
+}
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, int64_t n, AdamArgs a, bf16* __restrict__ shadow) {

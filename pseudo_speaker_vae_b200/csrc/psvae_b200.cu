@@ -1557,6 +1557,29 @@ int psvae_adam_step(float* p, const float* g, float* m, float* v, int64_t n, dou
   return 0;
 }
 
+int psvae_adam_step_ex(float* p, const float* g, float* m, float* v, float* vmax, int64_t n, double lr, double beta1, double beta2, double eps,
+                       double weight_decay, int64_t step, double grad_scale, int32_t amsgrad, int32_t maximize, void* shadow_bf16, void* stream) {
+  if (!amsgrad && !maximize) return psvae_adam_step(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, step, grad_scale, shadow_bf16, stream);
+  PSVAE_TRY(tc_device_check());
+  if (!p || !g || !m || !v || (amsgrad && !vmax)) { set_error("p, g, m, v (and vmax with amsgrad) must not be NULL"); return -1; }
+  if (n <= 0) return 0;
+  if (step < 1) { set_error("step=%lld must be >= 1 (count after increment)", (long long)step); return -2; }
+  const double bc1 = 1.0 - pow(beta1, (double)step);
+  const double bc2 = 1.0 - pow(beta2, (double)step);
+  AdamArgs a;
+  a.lr_step = (float)(lr / bc1);
+  a.bc2_sqrt = (float)sqrt(bc2);
+  a.beta1 = (float)beta1; a.beta2 = (float)beta2;
+  a.one_minus_beta1 = (float)(1.0 - beta1);
+  a.one_minus_beta2 = (float)(1.0 - beta2);
+  a.eps = (float)eps; a.weight_decay = (float)weight_decay; a.grad_scale = (float)grad_scale;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  launch_dep(adam_ex_kernel, dim3(ew_grid(n)), dim3(256), 0, st, p, g, m, v, vmax, n, a, (int)amsgrad, (int)maximize, static_cast<bf16*>(shadow_bf16));
+  count_launch();
+  PSVAE_LAUNCH_CHECK("adam_ex_kernel");
+  return 0;
+}
+
 int psvae_philox_uint32(uint32_t* out, int64_t n, uint64_t seed, uint64_t offset, int64_t first_elem, void* stream) {
   PSVAE_TRY(tc_device_check());
   if (!out) { set_error("out is NULL"); return -1; }

@@ -109,7 +109,7 @@ class ParamArena:
     def stage_buffer(self) -> torch.Tensor:
         """A flat gradient buffer that no live ``p.grad`` aliases (gradient accumulation keeps that one alive) and that no
         loss whose ``backward()`` is still to come owns (two ``training_step`` calls before one backward each get their own)."""
-        dev = self.flat.device
+        dev = self.ensure().device       # the arena follows the parameters first (a module moved with .to() re-attaches here, not on the CPU copy)
         self._gbuf = [g for g in self._gbuf if g.device == dev]
         live = {p.grad.data_ptr() for p, _ in self.entries if p.grad is not None}
         busy = [t.buf for t in self._inflight]

@@ -8,7 +8,9 @@ arena; gradients are consumed straight from the arena's flat gradient buffer (af
 all-reduce they hold the SUM over ranks: ``grad_scale = 1 / world_size`` folds the averaging into the pass).
 In bf16 mode the same pass also refreshes the bf16 operand copy the tcgen05 GEMMs read.
 
-``amsgrad`` / ``maximize`` / ``capturable`` / ``differentiable`` are not on the reference's path and raise.
+``amsgrad`` (state key ``max_exp_avg_sq``, a third flat buffer) and ``maximize`` -- both reachable through
+``Adam(self.parameters(), **self.hparams["optimizer"])`` -- take the general kernel (``psvae_adam_step_ex``);
+``capturable`` / ``differentiable`` are not on the reference's path and raise.
 """
 from __future__ import annotations
 
@@ -24,8 +26,8 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params: Iterable, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0, amsgrad: bool = False, *, arena: Optional[ParamArena] = None, maximize: bool = False,
                  foreach=None, capturable: bool = False, differentiable: bool = False, fused=None):
-        if amsgrad or maximize or capturable or differentiable:
-            raise NotImplementedError("FusedAdam implements the reference's configuration: plain Adam (no amsgrad/maximize/capturable)")
+        if capturable or differentiable:
+            raise NotImplementedError("FusedAdam implements eager torch.optim.Adam (no capturable / differentiable)")
         if lr < 0.0:
             raise ValueError(f"Invalid learning rate: {lr}")
         if eps < 0.0:
@@ -36,7 +38,7 @@ class FusedAdam(torch.optim.Optimizer):
             raise ValueError(f"Invalid beta parameter at index 1: {betas[1]}")
         if weight_decay < 0.0:
             raise ValueError(f"Invalid weight_decay value: {weight_decay}")
-        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False, foreach=None,
+        defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, amsgrad=bool(amsgrad), maximize=bool(maximize), foreach=None,
                         capturable=False, differentiable=False, fused=None)
         super().__init__(params, defaults)
         if arena is None:
@@ -45,6 +47,7 @@ class FusedAdam(torch.optim.Optimizer):
         self.grad_scale = 1.0          # 1 / world_size after a SUM all-reduce
         self._m: Optional[torch.Tensor] = None
         self._v: Optional[torch.Tensor] = None
+        self._vmax: Optional[torch.Tensor] = None      # amsgrad: running maximum of exp_avg_sq
         self._offsets = {id(p): off for p, off in arena.entries}
         for g in self.param_groups:
             for p in g["params"]:
@@ -56,11 +59,16 @@ class FusedAdam(torch.optim.Optimizer):
         flat = self.arena.ensure()
         if self._m is None or self._m.device != flat.device:
             old_m, old_v = self._m, self._v
+            old_x = self._vmax
             self._m = torch.zeros_like(flat)
             self._v = torch.zeros_like(flat)
+            if any(g["amsgrad"] for g in self.param_groups):
+                self._vmax = torch.zeros_like(flat)
             if old_m is not None:
                 self._m.copy_(old_m)
                 self._v.copy_(old_v)
+                if old_x is not None and self._vmax is not None:
+                    self._vmax.copy_(old_x)
             self._bind_state()
         return self._m, self._v
 
@@ -75,6 +83,11 @@ class FusedAdam(torch.optim.Optimizer):
                     mv.copy_(st["exp_avg"])
                     vv.copy_(st["exp_avg_sq"])
                 st["exp_avg"], st["exp_avg_sq"] = mv, vv
+                if g["amsgrad"] and self._vmax is not None:
+                    xv = self._vmax[off:off + n].view(p.shape)
+                    if "max_exp_avg_sq" in st and st["max_exp_avg_sq"].data_ptr() != xv.data_ptr():
+                        xv.copy_(st["max_exp_avg_sq"])
+                    st["max_exp_avg_sq"] = xv
             # one shared CPU step counter per group (torch keeps one per parameter; they always agree here)
             vals = {float(self.state[p]["step"]) for p in g["params"] if "step" in self.state[p]}
             if len(vals) > 1:
@@ -136,9 +149,15 @@ class FusedAdam(torch.optim.Optimizer):
                 if self.arena.shadow is not None and self.arena.shadow.device == dev:
                     shadow = self.arena.shadow.data_ptr() + 2 * a
                 with _on(dev):
-                    rc = lib.psvae_adam_step(flat.data_ptr() + 4 * a, gflat.data_ptr() + 4 * a, m.data_ptr() + 4 * a, v.data_ptr() + 4 * a, b - a,
-                                             float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
-                                             step, float(self.grad_scale), shadow, stream)
+                    if group["amsgrad"] or group["maximize"]:
+                        vmax = self._vmax.data_ptr() + 4 * a if group["amsgrad"] else None
+                        rc = lib.psvae_adam_step_ex(flat.data_ptr() + 4 * a, gflat.data_ptr() + 4 * a, m.data_ptr() + 4 * a, v.data_ptr() + 4 * a, vmax, b - a,
+                                                    float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
+                                                    step, float(self.grad_scale), int(bool(group["amsgrad"])), int(bool(group["maximize"])), shadow, stream)
+                    else:
+                        rc = lib.psvae_adam_step(flat.data_ptr() + 4 * a, gflat.data_ptr() + 4 * a, m.data_ptr() + 4 * a, v.data_ptr() + 4 * a, b - a,
+                                                 float(group["lr"]), float(beta1), float(beta2), float(group["eps"]), float(group["weight_decay"]),
+                                                 step, float(self.grad_scale), shadow, stream)
                 L.check(rc, "psvae_adam_step")
                 touched = True
             step_t += 1

@@ -97,6 +97,54 @@ def test_adam_matches_torch_golden():
     assert np.abs(p.cpu().numpy() - z["wd0/f32/p0"]).max() <= 1e-6 * np.abs(z["wd0/f32/p0"]).max()
 
 
+@pytest.mark.parametrize("amsgrad,maximize,wd", [(True, False, 0.0), (False, True, 0.01), (True, True, 0.01)])
+def test_adam_amsgrad_maximize_match_torch(amsgrad, maximize, wd):
+    """The two torch.optim.Adam switches `Adam(self.parameters(), **self.hparams["optimizer"])` (lightning.py:205) can reach, against
+    torch.optim.Adam itself (CPU, fp32, single-tensor path) on the same gradients: parameters <= 3e-7, moments and the running maximum <= 1e-6."""
+    G = _gu()
+    L = G.L
+    z = np.load(os.path.join(GOLDEN, "adam_cosine.npz"))
+    p0 = torch.from_numpy(z["p0"].copy())
+    ref_p = p0.clone().requires_grad_(True)
+    ref = torch.optim.Adam([ref_p], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd, amsgrad=amsgrad, maximize=maximize, foreach=False)
+    p = p0.clone().to(G.DEV)
+    m, v, vmax = torch.zeros_like(p), torch.zeros_like(p), torch.zeros_like(p)
+    shadow = torch.empty(p.numel(), dtype=torch.bfloat16, device=G.DEV)
+    for s, g in enumerate(z["grads"]):
+        gt = torch.from_numpy(g.astype(np.float32))
+        ref_p.grad = gt.clone()
+        ref.step()
+        gd = gt.to(G.DEV)
+        L.check(L.lib().psvae_adam_step_ex(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), vmax.data_ptr() if amsgrad else None, p.numel(), 3e-3, 0.9,
+                                           0.999, 1e-8, wd, s + 1, 1.0, int(amsgrad), int(maximize), shadow.data_ptr(), G.stream()))
+        want = ref_p.detach().numpy()
+        assert np.abs(p.cpu().numpy() - want).max() <= 3e-7 * np.abs(want).max(), s
+        assert torch.equal(shadow, p.to(torch.bfloat16))
+    st = ref.state[ref_p]
+    assert rel_err(m.cpu().numpy(), st["exp_avg"].numpy()) <= 1e-6 and rel_err(v.cpu().numpy(), st["exp_avg_sq"].numpy()) <= 1e-6
+    if amsgrad:
+        assert rel_err(vmax.cpu().numpy(), st["max_exp_avg_sq"].numpy()) <= 1e-6
+
+
+def test_fused_adam_amsgrad_through_the_module():
+    """hparams['optimizer'] = {amsgrad: True}: configure_optimizers hands it to FusedAdam; a train step + optimizer step runs and the state
+    carries torch's keys."""
+    G = _gu()
+    cfg = dict(D=256, L=64, wseed=1, clf=dict(input_dim=64, num_classes=2))
+    module = G.module_from_cfg(cfg, "bf16")
+    module.hparams["optimizer"] = dict(lr=1e-3, amsgrad=True)
+    opt = module.configure_optimizers()["optimizer"]
+    x, y, eps = O.synth_batch(512, 256, 64, 2, seed=3)
+    loss = module.training_step((torch.from_numpy(x).to(G.DEV), torch.from_numpy(y).to(G.DEV)), 0)["loss"]
+    loss.backward()
+    before = module.hot_path.arena.flat.clone()
+    opt.step()
+    torch.cuda.synchronize()
+    assert not torch.equal(before, module.hot_path.arena.flat)
+    st = opt.state[next(iter(module.parameters()))]
+    assert "max_exp_avg_sq" in st and float(st["max_exp_avg_sq"].abs().sum()) > 0
+
+
 # ------------------------------------------------------------------------------------------------
 # GEMM engines
 # ------------------------------------------------------------------------------------------------

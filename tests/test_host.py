@@ -180,7 +180,12 @@ def test_configure_optimizers_surface_and_state_dict():
     opt.load_state_dict(sd)
     assert opt.state[next(iter(m.parameters()))]["exp_avg"].data_ptr() == opt._m.data_ptr()
     with pytest.raises(NotImplementedError):
-        P.FusedAdam(m.parameters(), amsgrad=True, arena=m.hot_path.arena)
+        P.FusedAdam(m.parameters(), capturable=True, arena=m.hot_path.arena)
+    # amsgrad / maximize are reachable through **hparams["optimizer"] (lightning.py:205): accepted, with torch's state key
+    ams = P.FusedAdam(m.parameters(), amsgrad=True, maximize=True, arena=m.hot_path.arena)
+    assert ams.defaults["amsgrad"] is True and ams.defaults["maximize"] is True
+    ams._moments()
+    assert set(ams.state_dict()["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq", "max_exp_avg_sq"}
 
 
 def test_consistency_classifier_surface(tmp_path):
