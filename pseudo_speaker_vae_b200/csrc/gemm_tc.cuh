@@ -1,22 +1,26 @@
-// tcgen05 GEMM engine for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  through a fused epilogue.
+// tcgen05 GEMM engine for sm_100a:  C[M,N] = A[M,K] * B[N,K]^T  through a fused epilogue (DESIGN.md 4.1, 4.4).
 //
-//   * persistent, one CTA per SM, static round-robin tile schedule (n fastest: CTAs sharing a row tile run together);
-//   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one thread issues
-//     tcgen05.mma), warps 2..9 = epilogue;
-//   * operands bf16, staged by TMA (cp.async.bulk.tensor, 128B swizzle) through a STAGES-deep mbarrier
-//     ring; fp32 accumulators live in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i
-//     overlaps the MMAs of tile i+1;
-//   * both operands may be K-major (row-major [rows][K]) or MN-major (stored [K][rows]): dgrad consumes W
-//     as stored and wgrad contracts over the batch, so no transposed copies exist anywhere;
-//   * optional split-K (wgrad: K = batch) -- partials go to a [splits][M][N] buffer through a 3-D store map;
-//   * epilogue: TMEM -> registers (tcgen05.ld, lane = row) -> functor -> round to the output type -> 32x32 block
-//     staged in a per-warp swizzled shared-memory buffer -> ONE TMA store per block (coalesced 64/128-byte rows,
-//     clipped at the matrix edge by the hardware).  A row-per-lane st.global would cost 32 L1 wavefronts per
-//     instruction and made the first version of this kernel LSU-bound (profiles/r01_notes.md).  The auxiliary
-//     tile of EpiActGrad (the forward activation) comes in the same way by TMA load.  Bias-gradient column sums
-//     (kColSum) are read back out of the staged block and kept in registers across the CTA's tiles.
+//   * persistent, one CTA per SM, static round-robin tile schedule (n fastest: CTAs sharing a row tile run together), tiles walked
+//     incrementally (TileWalk: no divisions in the loop);
+//   * warp-specialised: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer (one elected thread issues tcgen05.mma),
+//     warps 2.. = epilogue: 16 warps for BN = 256, 8 for narrower tiles (tc_epi_warps);
+//   * CG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on one 256 x BN tile -- each CTA stages its own 128 rows of A and
+//     half of the B tile, the leader issues UMMA 256 x BN x 16; CG = 1: one CTA, 128 x BN tiles (BN = 64 / 128, or M <= 128);
+//   * operands bf16, staged by TMA (cp.async.bulk.tensor, 128B swizzle) through a ring of mbarrier stages (depth = what fits next to the
+//     epilogue staging: 5 at BN = 256 / CG = 2); fp32 accumulators live in TMEM, double-buffered (2 x BN columns), so the epilogue of tile
+//     i overlaps the MMAs of tile i+1.  EG2: two epilogue groups on alternate tiles for the thin (K <= 128) layers;
+//   * both operands may be K-major (row-major [rows][K]) or MN-major (stored [K][rows]): dgrad consumes W as stored and wgrad contracts
+//     over the batch, so no transposed copies exist anywhere;
+//   * split-K (wgrad: K = batch): every split tile adds its block into the zeroed gradient with a TMA reduce-add (deterministic mode:
+//     [splits][M][N] slots through a 3-D store map + an ordered reduce);
+//   * grouped (block-diagonal) launches for the two encoders' layers; MULTI: one launch for a whole list of wgrad problems;
+//   * epilogue: TMEM -> registers (tcgen05.ld, lane = row) -> functor in packed fp32 pairs -> round to the output type -> block staged in a
+//     per-warp swizzled shared-memory buffer -> ONE TMA store per 32 x 64 block (coalesced, clipped at the matrix edge by the hardware;
+//     a row-per-lane st.global cost 32 L1 wavefronts per instruction and made the first version LSU-bound).  The auxiliary tile of EpiMse
+//     (the reconstruction target) comes in the same way by TMA load.  Bias-gradient column sums (kColSum) are read back out of the staged
+//     block and kept in registers across the CTA's tiles.  kLat: the fused encoder head (EpiLatent).
 //
-// Tile: 128 x BN x 64 (UMMA 128 x BN x 16, cta_group::1).
+// Tile: (128 x CG) x BN x 64 (UMMA K = 16).
 #pragma once
 #include <cuda.h>
 
