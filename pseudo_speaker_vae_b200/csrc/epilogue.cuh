@@ -239,7 +239,7 @@ struct EpiStore {
 };
 
 // Fused encoder head (option "fused_head", tcgen05 engine only; see gemm_tc.cuh, kLat): ONE kernel computes mu = he[:, :H] W_mu^T and
-// log_sigma = he[:, H:] W_sigma^T into one 128-column accumulator tile laid out [mu 0-31 | ls 0-31 | mu 32-63 | ls 32-63], and its epilogue
+// log_sigma = he[:, H:] W_sigma^T into one 128-column accumulator tile laid out [mu 0-63 | ls 0-63] (one 64-column MMA per encoder and k-step), and its epilogue
 // does what clf_fused_kernel<REPARAM> does today -- biases, eps (Philox or injected), z = mu + sigma eps, sigma eps / 2, the KL partial sum,
 // the linear-head classifier on mu, cross entropy, accuracy, d loss / d logits -- with a row's mu AND log_sigma in one thread's registers
 // (model.py:54-57, lightning.py:73-83,115-117).  Outputs: mu / log_sigma (fp32) and z / sigma eps / 2 (TZ) through TMA stores, d loss / d logits

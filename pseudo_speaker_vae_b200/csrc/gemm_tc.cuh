@@ -401,20 +401,19 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
           const uint64_t boff = soff;
           if (ptx::elect_one()) {
             if constexpr (kLat) {
-              // accumulator columns [mu 0-31 | ls 0-31 | mu 32-63 | ls 32-63]: group gg's weight rows 0-31 / 32-63 go to two 32-column
-              // MMAs, so that one epilogue warp finds mu AND log_sigma of the same 32 latent dims in its 64 columns
+              // accumulator columns [mu 0-63 | ls 0-63]: group gg's 64 weight rows are ONE 64-column MMA per k-step (every MMA re-reads its
+              // 4 KB A slice from shared memory whatever its N: two 32-column MMAs per step made this kernel MMA-issue-bound -- 66 cycles per
+              // MMA, 34 k of its 54 k cycles, profiles/r02_step_trace_v22.txt); the epilogue warp reads mu and log_sigma of its 32 latent
+              // dims with two tcgen05.ld 64 columns apart
               const int64_t kbg = kb_total >> 1;
               const uint32_t gg = kb >= kbg ? 1u : 0u;
               const bool first_kb = (kb == 0 || kb == kbg);
-              const uint32_t idesc_lat = ptx::make_idesc_bf16(TM, 32, 0, 0);
+              const uint32_t idesc_lat = ptx::make_idesc_bf16(TM, TC_LAT_L, 0, 0);
 #pragma unroll
               for (int kk = 0; kk < TC_BK / TC_UMMA_K; ++kk) {
-#pragma unroll
-                for (int hh = 0; hh < 2; ++hh) {
-                  const uint64_t da = da0 + soff + (uint64_t)((kk * a_kstep) >> 4);
-                  const uint64_t db = db0 + boff + (uint64_t)((kk * b_kstep + hh * 32 * 128) >> 4);
-                  ptx::umma_f16(tmem_d + (uint32_t)(hh * 64) + gg * 32u, da, db, idesc_lat, (first_kb && kk == 0) ? 0u : 1u);
-                }
+                const uint64_t da = da0 + soff + (uint64_t)((kk * a_kstep) >> 4);
+                const uint64_t db = db0 + boff + (uint64_t)((kk * b_kstep) >> 4);
+                ptx::umma_f16(tmem_d + gg * (uint32_t)TC_LAT_L, da, db, idesc_lat, (first_kb && kk == 0) ? 0u : 1u);
               }
             } else {
 #pragma unroll
@@ -505,8 +504,8 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
       const bool valid = row < pM;
       const int col_base = (int)(n_t * BN) + half * COLS_PER_WARP;
       if constexpr (kLat) {
-        // ---- fused encoder head: this warp owns rows [row_base, +32) and latent dims [32 half, 32 half + 32); its 64 accumulator
-        //      columns are [mu | log_sigma] of exactly those dims
+        // ---- fused encoder head: this warp owns rows [row_base, +32) and latent dims [32 half, 32 half + 32): accumulator columns
+        //      [32 half, +32) hold their mu, columns [64 + 32 half, +32) their log_sigma
         static_assert(sizeof(decltype(*epi.z)) == 2, "fused head: bf16 z");
         uint8_t* const st_mu = obuf0;                                  // 32 x 32 fp32 (128-byte swizzled rows); first: Philox scratch [8][32] float4
         uint8_t* const st_ls = obuf0 + 4096;
@@ -518,9 +517,9 @@ __device__ __forceinline__ void gemm_tc_body(const CUtensorMap& tma_a, const CUt
         twait(&tfull_bar[acc], acc_phase, 4, tw0);
         ptx::tc_fence_after();
         uint32_t r_mu[32], r_ls[32];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 64);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 32);
         ptx::tmem_ld_32x32_issue(taddr, r_mu);
-        ptx::tmem_ld_32x32_issue(taddr + 32, r_ls);
+        ptx::tmem_ld_32x32_issue(taddr + TC_LAT_L, r_ls);
         float mu_v[32], ls_v[32];
         load_vec<32>(epi.bias + lat0, mu_v);                           // biases, fetched while the TMEM reads are in flight
         load_vec<32>(epi.bias + epi.L + lat0, ls_v);
