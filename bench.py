@@ -424,7 +424,9 @@ def main():
                             global_batch=B * n_gpus, parallelism=f"dp{n_gpus}",
                             l2=f"{NB} distinct input batches rotated; every step streams > 1 GB of activations through the 126 MB L2",
                             eps="in-kernel Philox4x32-10", options={kv.split("=")[0]: int(kv.split("=")[1]) for kv in args.opt},
-                            allreduce="1 bucket, flat fp32 grads 5.13 MB, NCCL" if dist_on else "none (1 GPU)"),
+                            allreduce=(f"1 bucket, flat fp32 grads 5.13 MB, {trainer.allreduce_kind}"
+                                       + (f" (timed at start-up, us: {getattr(trainer, 'allreduce_timings', {})})" if hasattr(trainer, "allreduce_timings") else ""))
+                            if dist_on else "none (1 GPU)"),
                 clocks=clocks, gpu_launches=launches, roofline=roofline)
 
     if dist_on:

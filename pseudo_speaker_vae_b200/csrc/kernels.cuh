@@ -1115,14 +1115,19 @@ __global__ void __launch_bounds__(256, 2) latent_bwd_clf8_kernel(const float* __
     *reinterpret_cast<uint4*>(dmu + row * ld_d + col8) = um;
     *reinterpret_cast<uint4*>(dls + row * ld_d + col8) = ul;
   };
+  // software pipeline: the NEXT row's eight 16-byte loads are issued before the current row's arithmetic (expm1f, 2 NC x 8 FMAs, packing), so
+  // that memory requests are in flight all the time -- with both rows loaded and then both computed the kernel alternated between the two
   const int64_t step = (int64_t)gridDim.x * rpb;
-  for (int64_t r = (int64_t)blockIdx.x * rpb + rin; r < rows; r += 2 * step) {
-    Oct a, b;
-    const bool two = r + step < rows;
-    load_oct(r, a);
-    if (two) load_oct(r + step, b);
-    do_oct(r, a);
-    if (two) do_oct(r + step, b);
+  int64_t r = (int64_t)blockIdx.x * rpb + rin;
+  if (r < rows) {
+    Oct cur, nxt;
+    load_oct(r, cur);
+    for (; r < rows; r += step) {
+      const bool more = r + step < rows;
+      if (more) load_oct(r + step, nxt);
+      do_oct(r, cur);
+      if (more) cur = nxt;
+    }
   }
   // bias gradients of the encoders' last Linear ([mu | sigma], atomics into the zeroed gradient): the tpr-strided threads own the same 8 columns
 #pragma unroll

@@ -1193,7 +1193,7 @@ static int run_step(const StepArgs& a) {
       // the 8-columns-per-thread form: L a multiple of 8 with L / 8 dividing 256, at most 4 classes
       if (n.L % 8 == 0 && 256 % (n.L / 8) == 0 && n.L <= 256 && cb.total_classes <= 4) {
         const int rpb = 256 / (n.L / 8);
-        int64_t nb = ceil_div64(B, 2 * rpb);
+        int64_t nb = ceil_div64(B, rpb);
         if (nb > 2 * PSVAE_NUM_SMS) nb = 2 * PSVAE_NUM_SMS;
         if (nb < 1) nb = 1;
 #define PSVAE_LBC8(NCV)                                                                                                                       \

@@ -14,6 +14,7 @@ gloo in the CPU tests).  This is what ``Trainer(strategy=DDPStrategy(...))`` doe
 """
 from __future__ import annotations
 
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -68,6 +69,67 @@ def reduce_losses(losses: torch.Tensor, group=None) -> torch.Tensor:
     return losses
 
 
+class SymmetricAllReduce:
+    """The flat gradient buffer in torch symmetric memory (P2P-mapped on every rank of the node) and its all-reduce through
+    ``torch.ops.symm_mem.two_shot_all_reduce_`` (reduce-scatter + all-gather over NVLink peer loads/stores) or ``multimem_all_reduce_``
+    (NVLS: the reduction happens inside the NVSwitch).  For the 5 MB gradient these are latency-bound like NCCL's ring, but with one
+    kernel and no proxy thread.  ``pick()`` TIMES the candidates on the running ranks (20 calls each) and keeps the fastest -- NCCL if it
+    wins or if anything about symmetric memory is unavailable on this node."""
+
+    def __init__(self, numel: int, device: torch.device, group=None):
+        import torch.distributed._symmetric_memory as symm
+
+        self.group = group if group is not None else dist.group.WORLD
+        self.gname = self.group.group_name
+        self.buf = symm.empty(numel, dtype=torch.float32, device=device)
+        symm.rendezvous(self.buf, self.gname)
+        self.buf.zero_()
+        self.kind = "nccl"
+        self.timings = {}
+
+    def _call(self, kind: str) -> None:
+        if kind == "two_shot":
+            torch.ops.symm_mem.two_shot_all_reduce_(self.buf, "sum", self.gname)
+        elif kind == "multimem":
+            torch.ops.symm_mem.multimem_all_reduce_(self.buf, "sum", self.gname)
+        else:
+            dist.all_reduce(self.buf, op=dist.ReduceOp.SUM, group=self.group)
+
+    def pick(self, iters: int = 20) -> str:
+        dev = self.buf.device
+        best = None
+        for kind in ("nccl", "two_shot", "multimem"):
+            ok = torch.ones(1, device=dev)
+            try:
+                for _ in range(3):
+                    self._call(kind)
+                torch.cuda.synchronize(dev)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                dist.barrier(group=self.group)
+                e0.record()
+                for _ in range(iters):
+                    self._call(kind)
+                e1.record()
+                torch.cuda.synchronize(dev)
+                t = torch.tensor([e0.elapsed_time(e1) / iters * 1e3], device=dev)
+            except Exception:  # noqa: BLE001 -- this kind is not available here
+                ok.zero_()
+                t = torch.tensor([float("inf")], device=dev)
+            # every rank must take the same decision: a kind counts only if it worked everywhere; its time is the slowest rank's
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            us = float(t) if float(ok) > 0 else float("inf")
+            self.timings[kind] = us
+            if best is None or us < 0.95 * self.timings[best]:        # a challenger must be 5 % faster than the incumbent (NCCL first)
+                best = kind
+        self.kind = best
+        self.buf.zero_()
+        return best
+
+    def all_reduce(self) -> None:
+        self._call(self.kind)
+
+
 class DataParallelTrainer:
     """The per-batch body of the reference's fit loop as three device-side calls:
     fused fwd+bwd  ->  bucketed all-reduce  ->  fused Adam.  Nothing in ``train_step`` synchronises with the host."""
@@ -90,6 +152,27 @@ class DataParallelTrainer:
         self.hot.arena.epoch += 1          # the bf16 operand copy must follow the broadcast values
         self._views = None
         self._views_of = None
+        # N > 1: the gradient buffer lives in symmetric memory when one of its all-reduce kernels beats NCCL on these ranks
+        # (PSVAE_ALLREDUCE = auto | nccl | two_shot | multimem)
+        self.symm: Optional[SymmetricAllReduce] = None
+        self.allreduce_kind = "nccl" if self.world_size > 1 else "none"
+        want = os.environ.get("PSVAE_ALLREDUCE", "auto")
+        if self.world_size > 1 and not self.local_only and want != "nccl" and self.hot.arena.flat.is_cuda:
+            sy = None
+            ok = torch.ones(1, device=self.hot.arena.flat.device)
+            try:
+                sy = SymmetricAllReduce(self.hot.arena.numel, self.hot.arena.flat.device, group)
+            except Exception:  # noqa: BLE001 -- no symmetric memory on this node / build
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            if float(ok) > 0:
+                kind = sy.pick() if want == "auto" else want
+                sy.kind = kind
+                if kind != "nccl":
+                    self.symm = sy
+                    self.allreduce_kind = kind
+                    self.hot.arena._gbuf.append(sy.buf)        # the arena must know the buffer the .grad views live in (FusedAdam.flat_grad)
+                self.allreduce_timings = dict(sy.timings)
 
     def set_shard(self, global_batch: int) -> Tuple[int, int]:
         row0, rows = shard_batch(global_batch, self.rank, self.world_size)
@@ -99,13 +182,15 @@ class DataParallelTrainer:
     def train_step(self, x_local: torch.Tensor, y_local=None, eps_local: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One optimiser step on this rank's shard.  Returns the device tensor of local loss scalars."""
         m, hot = self.module, self.hot
-        gflat = hot.arena.stage_buffer() if self._views_of is None else self._views_of
+        gflat = self.symm.buf if self.symm is not None else (hot.arena.stage_buffer() if self._views_of is None else self._views_of)
         cons = getattr(m, "consistency_classifier", None)
         losses, gflat, _ = hot.step(x_local, y_local if m.classifier is not None else None, eps_local, kl_weight=m.kl_loss_weight,
                                     clf_weight=m.classifier_loss_weight, use_cos_loss=m.use_cos_loss, compute_grads=True, grads=gflat,
                                     consistency=cons, consistency_y=y_local if cons is not None else None,
                                     consistency_weight=m.consitency_loss_weight)
-        if not self.local_only:
+        if self.symm is not None:
+            self.symm.all_reduce()
+        elif not self.local_only:
             all_reduce_flat(gflat, self.bucket_bytes, self.group)
         if self._views_of is not gflat:        # bind .grad views once; the same flat buffer is reused every step
             for (p, _), v in zip(hot.arena.entries, hot.arena.grad_views(gflat)):
