@@ -24,6 +24,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <algorithm>
+
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -927,6 +929,7 @@ int tc_two_cta();         // option "tc_two_cta": use CTA pairs (cta_group::2) w
 int tc_max_stages();      // option "tc_max_stages": cap of the operand ring depth (0 = none)
 unsigned long long* tc_trace_ptr();   // option "tc_trace_ptr": device buffer of gridDim.x * 16 counters, or nullptr
 int tc_epi_groups_max_k();
+int tc_wgrad_splits();           // option "wgrad_splits" (experiments): batch ranges per tile of the merged wgrad, 0 = chosen by gemm_tc_launch_multi_wgrad
 int tc_epi_groups();      // option "tc_epi_groups": K <= 128 forward / dgrad launches with BN = 256 run two epilogue groups on alternate tiles (EG2)
 // does this shape run as CTA pairs?  (BN = 256 tiles and more than one 128-row block of M)
 static inline bool tc_use_pair(int64_t M, int N, int force_bn = 0) {
@@ -1133,12 +1136,28 @@ static inline int gemm_tc_launch_multi_wgrad(const TcWgradProblem* probs, int co
     mp.n_tiles[p] = (int32_t)ceil_div64(q.N, BN);
     tiles += (int64_t)mp.m_tiles[p] * mp.n_tiles[p];
   }
-  // split factor: ~12 items per CTA pair, at least 8 k-blocks (512 batch rows) per item, no empty split
+  // Split factor.  Items (tile x batch range) are dealt round-robin to the CTA pairs, so the launch takes ceil(items / pairs) rounds: S is chosen so
+  // that tiles * S fills a whole number of rounds (r * pairs) from below -- e.g. 24 tiles on 74 pairs: S = 6 gives 144 items = 1.95 rounds
+  // (97 % full), S = 7 gives 168 = 2.27 -> 3 rounds (76 %).  Few, long ranges also mean few reduce-adds per tile.  Measured on the headline
+  // shape (ms/step): S = 6 0.643-0.655, S = 3 / 9 / 12 0.647-0.651, S = 7 0.669, S = 10 0.663, S = 40 (the old "12 items per pair") 0.673
+  // (profiles/r02_ab_runs.txt).  At least two rounds, so that thin and full-width tiles mix on every pair; at least 8 k-blocks per range.
   const int pairs = tc_grid_size() / CG;
   const int64_t kb = ceil_div64(rows, TC_BK);
-  int64_t S = (12ll * pairs + tiles / 2) / tiles;
-  if (S > kb / 8) S = kb / 8;
-  if (S < 1) S = 1;
+  int64_t S = 1;
+  {
+    const int64_t r0 = std::max<int64_t>(2, ceil_div64(tiles, pairs));
+    double best = -1.0;
+    for (int64_t r = r0; r < r0 + 4; ++r) {
+      int64_t cand = (r * pairs) / tiles;
+      if (cand < 1) cand = 1;
+      if (cand > kb / 8) cand = std::max<int64_t>(1, kb / 8);
+      const int64_t items = tiles * cand;
+      const double eff = (double)items / (double)(ceil_div64(items, pairs) * pairs);
+      if (eff > best + 1e-9) { best = eff; S = cand; }
+    }
+  }
+  if (tc_wgrad_splits() > 0) S = tc_wgrad_splits();
+  if (S > kb) S = kb;
   const int64_t per = ceil_div64(kb, S);
   S = ceil_div64(kb, per);
   int32_t begin = 0;

@@ -1,0 +1,7 @@
+set -x
+TAG=${TAG:-r25}
+run() { timeout 200 python bench.py --steps 100 --warmup 20 --no-secondary "$@" > gpurun_out/${TAG}_tmp.json 2>gpurun_out/${TAG}_b.err; python -c "
+import json,sys;d=json.loads(open('gpurun_out/${TAG}_tmp.json').read().strip().splitlines()[-1]);print('bench','$*',d['ms_per_step'],d['clocks']['sm_mhz'])"; }
+for rep in 1 2; do
+for k in 12 4 6 8 16 24; do run --opt wgrad_items_per_pair=$k; done
+done
