@@ -924,6 +924,22 @@ static inline int tc_pick_bn(int N) {
   if (N % 128 == 0) return 128;
   return 64;
 }
+// Tile width for an [M, N] output that is not split and not grouped.  N = 256 is ONE tile column: on CTA pairs the launch takes
+// ceil(M / 256 / pairs) rounds -- 3.46 -> 4 at M = 65,536 on 74 pairs (86 % full).  The same output as 128 x 128 one-CTA tiles takes
+// 6.92 -> 7 rounds of quarter-size tiles (99 % full), which wins when the tile time is the epilogue's (option "tc_bn_rounds").
+int tc_bn_rounds();
+int tc_two_cta();
+static inline int tc_pick_bn_mn(int64_t M, int N, int force_bn) {
+  if (force_bn) return force_bn;
+  const int bn = tc_pick_bn(N);
+  if (bn == 256 && N == 256 && tc_bn_rounds() && tc_two_cta() && M > TC_BM) {
+    const int64_t g = tc_grid_size(), pairs = g / 2;
+    const int64_t t256 = ceil_div64(M, 2 * TC_BM), t128 = ceil_div64(M, TC_BM) * 2;
+    const double e256 = (double)t256 / (double)(ceil_div64(t256, pairs) * pairs), e128 = (double)t128 / (double)(ceil_div64(t128, g) * g);
+    if (e256 < 0.9 && e128 > e256 + 0.08) return 128;
+  }
+  return bn;
+}
 // CTAs a launch uses (= rows / 4 of the kColSum partial buffer, = slots of a kReduce epilogue)
 int tc_two_cta();         // option "tc_two_cta": use CTA pairs (cta_group::2) where the shape allows
 int tc_max_stages();      // option "tc_max_stages": cap of the operand ring depth (0 = none)
@@ -933,12 +949,12 @@ int tc_wgrad_splits();           // option "wgrad_splits" (experiments): batch r
 int tc_epi_groups();      // option "tc_epi_groups": K <= 128 forward / dgrad launches with BN = 256 run two epilogue groups on alternate tiles (EG2)
 // does this shape run as CTA pairs?  (BN = 256 tiles and more than one 128-row block of M)
 static inline bool tc_use_pair(int64_t M, int N, int force_bn = 0) {
-  const int bn = force_bn ? force_bn : tc_pick_bn(N);
+  const int bn = tc_pick_bn_mn(M, N, force_bn);
   return tc_two_cta() && bn == 256 && M > TC_BM;
 }
 // the CTAs a launch uses
 static inline int64_t tc_ctas(int64_t M, int N, int splits, int force_bn = 0) {
-  const int bn = force_bn ? force_bn : tc_pick_bn(N);
+  const int bn = tc_pick_bn_mn(M, N, force_bn);
   const int cg = tc_use_pair(M, N, force_bn) ? 2 : 1;
   int64_t tiles = ceil_div64(M, TC_BM * cg) * ceil_div64(N, bn) * (splits < 1 ? 1 : splits);
   const int64_t g = tc_grid_size() / cg;
@@ -1236,7 +1252,8 @@ template <bool A_MN, bool B_MN, class Epi>
 int gemm_tc_launch(const TcOperand& A, const TcOperand& B, int64_t M, int N, int64_t K, int splits, const Epi& epi, cudaStream_t st, int force_bn = 0,
                    const TcGroup& grp = TcGroup()) {
   if (N % 8 != 0) { set_error("gemm_tc: N=%d must be a multiple of 8", N); return -2; }
-  const int bn = force_bn ? force_bn : tc_pick_bn(grp.groups > 1 ? grp.grp_n : N);      // a tile never straddles two groups
+  const int bn = (grp.groups > 1 || splits > 1 || A_MN) ? (force_bn ? force_bn : tc_pick_bn(grp.groups > 1 ? grp.grp_n : N))      // a tile never straddles two groups
+                                                        : tc_pick_bn_mn(M, N, force_bn);
   if (grp.groups > 1 && (A_MN || splits > 1 || grp.grp_n % bn != 0 || grp.grp_k % TC_BK != 0 || N != grp.groups * grp.grp_n)) {
     set_error("gemm_tc: grouped launch needs K-major A, no split-K, grp_n %% %d == 0 and grp_k %% %d == 0", bn, TC_BK);
     return -2;

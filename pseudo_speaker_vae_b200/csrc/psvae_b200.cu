@@ -70,6 +70,8 @@ struct Options {
   int64_t wgrad_order = 1;             // merged wgrad: 0 = problems in the order the backward pass queued them, 1 = newest first (the gradients written last are
                                        //    still in L2: 0.6826 -> 0.6778 ms/step, A/B round 2), 2 = newest first + batch ranges from the end (same as 1)
   int64_t wgrad_splits = 0;            // experiments: force the number of batch ranges per tile of the merged wgrad (0 = chosen by the launcher: whole rounds of the CTA pairs)
+  int64_t tc_bn_rounds = 1;            // 1: a single-tile-column output (N = 256) takes 128 x 128 one-CTA tiles when that fills the rounds of the persistent grid better
+                                       //    (dec out + MSE at B = 65,536: 3.46 -> 4 rounds of pair tiles vs 6.92 -> 7 rounds of quarter-size tiles; 0.6502 -> 0.6449 ms/step, A/B)
   int64_t tc_epi_groups_max_k = 128;   // largest contraction length K that still takes the two-epilogue-group kernel
   int64_t tc_merged_wgrad = 1;         // 1 (fast tcgen05 mode): every wgrad of the step runs in ONE persistent launch at the end of the backward pass (gemm_tc_launch_multi_wgrad):
                                        //    the ~8 us fixed cost of a wgrad launch is paid once instead of 8 times
@@ -127,6 +129,7 @@ int tc_two_cta() { return (int)g_opt.tc_two_cta; }
 int tc_max_stages() { return (int)g_opt.tc_max_stages; }
 int tc_epi_groups() { return (int)g_opt.tc_epi_groups; }
 int tc_wgrad_splits() { return (int)g_opt.wgrad_splits; }
+int tc_bn_rounds() { return (int)g_opt.tc_bn_rounds; }
 int tc_epi_groups_max_k() { return (int)g_opt.tc_epi_groups_max_k; }
 bool pdl_enabled() { return g_opt.pdl != 0; }
 // profiling: the trace buffer goes to ONE launch -- the (tc_trace_skip + 1)-th tcgen05 launch after the option was set (0: every launch, as before)
@@ -1427,6 +1430,7 @@ int psvae_set_option(const char* name, int64_t value) {
   if (!strcmp(name, "tc_grouped")) { g_opt.tc_grouped = value ? 1 : 0; return 0; }
   if (!strcmp(name, "tc_epi_groups")) { g_opt.tc_epi_groups = value ? 1 : 0; return 0; }
   if (!strcmp(name, "wgrad_order")) { g_opt.wgrad_order = value; return 0; }
+  if (!strcmp(name, "tc_bn_rounds")) { g_opt.tc_bn_rounds = value ? 1 : 0; return 0; }
   if (!strcmp(name, "wgrad_splits")) { g_opt.wgrad_splits = value < 0 ? 0 : value; return 0; }
   if (!strcmp(name, "tc_epi_groups_max_k")) { g_opt.tc_epi_groups_max_k = value < 0 ? 0 : value; return 0; }
   if (!strcmp(name, "clf_grad_in_bwd")) { g_opt.clf_grad_in_bwd = value ? 1 : 0; return 0; }
@@ -1452,6 +1456,7 @@ int64_t psvae_get_option(const char* name) {
   if (!strcmp(name, "tc_grouped")) return g_opt.tc_grouped;
   if (!strcmp(name, "tc_epi_groups")) return g_opt.tc_epi_groups;
   if (!strcmp(name, "wgrad_order")) return g_opt.wgrad_order;
+  if (!strcmp(name, "tc_bn_rounds")) return g_opt.tc_bn_rounds;
   if (!strcmp(name, "wgrad_splits")) return g_opt.wgrad_splits;
   if (!strcmp(name, "tc_epi_groups_max_k")) return g_opt.tc_epi_groups_max_k;
   if (!strcmp(name, "clf_grad_in_bwd")) return g_opt.clf_grad_in_bwd;

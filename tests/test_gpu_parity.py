@@ -823,7 +823,7 @@ def test_deterministic_option_and_fast_mode_agree():
         G.L.set_option("deterministic", 0)
 
 
-@pytest.mark.parametrize("opts", [dict(pdl=0), dict(tc_two_cta=0), dict(tc_max_stages=2), dict(tc_grouped=0)])
+@pytest.mark.parametrize("opts", [dict(pdl=0), dict(tc_two_cta=0), dict(tc_max_stages=2), dict(tc_grouped=0), dict(tc_bn_rounds=0)])
 def test_engine_variants_reproduce_the_default_path(opts):
     """The tuning variants of the tcgen05 engine (no programmatic dependent launch, 1-CTA tiles, a 2-deep ring, one launch per encoder
     instead of the grouped block-diagonal launches) change the schedule, not the arithmetic: in deterministic mode the forward outputs must be bit-identical to the default configuration and the losses / gradients
@@ -861,12 +861,12 @@ def test_engine_variants_reproduce_the_default_path(opts):
             G.L.set_option(k, v)
 
 
-FAST_VARIANTS_OFF = dict(tc_epi_groups=0, clf_grad_in_bwd=0, fused_head=0, tc_merged_wgrad=0, wgrad_order=0)
+FAST_VARIANTS_OFF = dict(tc_epi_groups=0, clf_grad_in_bwd=0, fused_head=0, tc_merged_wgrad=0, wgrad_order=0, wgrad_splits=0)
 
 
 @pytest.mark.parametrize("opts", [dict(tc_epi_groups=1), dict(clf_grad_in_bwd=1), dict(fused_head=1), dict(tc_merged_wgrad=1),
                                   dict(tc_epi_groups=1, fused_head=1, tc_merged_wgrad=1), dict(tc_merged_wgrad=1, wgrad_order=1),
-                                  dict(tc_merged_wgrad=1, wgrad_order=2)])
+                                  dict(tc_merged_wgrad=1, wgrad_order=2), dict(tc_merged_wgrad=1, wgrad_splits=40), dict(tc_merged_wgrad=1, wgrad_splits=1)])
 def test_fast_mode_engine_variants_agree_with_the_plain_path(opts):
     """The fast-mode variants that are ON by default since round 2 (validated on a B200 by tools/validate_experimental.sh, then A/B-timed)
     against the path with all of them off.  tc_epi_groups (two epilogue groups on alternate tiles for the K <= 128 layers): forward outputs

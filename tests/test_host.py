@@ -377,7 +377,7 @@ def test_batch_loader_order_sharding_and_split(tmp_path):
 def test_engine_option_defaults():
     """The defaults of the engine options: variants validated and A/B-timed on a B200 in round 2 are on (tc_epi_groups, fused_head,
     tc_merged_wgrad); clf_grad_in_bwd on its own measured slower and stays off (the fused head uses that backward regardless)."""
-    for name, default in (("tc_epi_groups", 1), ("fused_head", 1), ("tc_merged_wgrad", 1), ("wgrad_order", 1), ("decode_chain", 1), ("train_chain", 0), ("clf_grad_in_bwd", 0), ("tc_grouped", 1), ("pdl", 1),
+    for name, default in (("tc_epi_groups", 1), ("fused_head", 1), ("tc_merged_wgrad", 1), ("wgrad_order", 1), ("tc_bn_rounds", 1), ("wgrad_splits", 0), ("decode_chain", 1), ("train_chain", 0), ("clf_grad_in_bwd", 0), ("tc_grouped", 1), ("pdl", 1),
                           ("tc_two_cta", 1), ("deterministic", 0)):
         assert L.get_option(name) == default, name
 
