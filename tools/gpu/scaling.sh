@@ -1,9 +1,6 @@
-# 8-GPU box: all-reduce probe at N = 8 / 4, then the driver's scaling launches at N = 8, 4, 2, 1 (no secondary legs)
+# 8-GPU box: the driver's scaling launches at N = 8, 4, 2, 1 (no secondary legs)
 set -x
-TAG=${TAG:-r21}
-for n in 8 4; do
-  timeout 200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29600 + n)) tools/allreduce_probe.py 2>&1 | grep "allreduce" | tee -a gpurun_out/${TAG}_probe.log
-done
+TAG=${TAG:-r32}
 for n in 8 4 2; do
   timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port $((29500 + n)) bench.py --gpus $n --steps 100 --warmup 20 --no-secondary > gpurun_out/${TAG}_n${n}.json 2> gpurun_out/${TAG}_n${n}.err
   echo "N=$n rc=$?"; python -c "
