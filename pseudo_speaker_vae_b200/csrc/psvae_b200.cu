@@ -1250,7 +1250,9 @@ static int run_step(const StepArgs& a) {
                                                  atomic ? G + d->enc_b[layer - 1] : w.cpart, atomic ? 1 : 0};
         PSVAE_TRY((Engine<TAct>::template gemm_grouped<G_DGRAD>(dY, ldy, Wt + d->enc_w[layer], n.H, B, 2, n.H, Kg, 0, e, st)));
         if (!atomic) {
-          const int64_t ctas = tc_ctas(B, 2 * n.H, 1, (int)g_opt.tc_force_bn);
+          // the grouped launch tiles by ONE group's width (a tile never straddles the two encoders): count its CTAs with that tile width
+          const int bn_g = g_opt.tc_force_bn ? (int)g_opt.tc_force_bn : tc_pick_bn(n.H);
+          const int64_t ctas = tc_ctas(B, 2 * n.H, 1, bn_g);
           PSVAE_TRY(launch_reduce(w.cpart, 2 * n.H, (int)ctas * 4, G + d->enc_b[layer - 1], st));
         }
         bias_done[0] = bias_done[1] = true;

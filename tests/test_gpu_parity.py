@@ -823,6 +823,46 @@ def test_deterministic_option_and_fast_mode_agree():
         G.L.set_option("deterministic", 0)
 
 
+@pytest.mark.parametrize("H,B", [(128, 300), (256, 300), (128, 8192 + 77), (384, 1000)])
+def test_deterministic_mode_narrow_hidden_layers(H, B):
+    """Hidden widths whose grouped (block-diagonal) launches tile by 128 columns, at ragged batches smaller than the persistent grid: the ordered
+    bias-gradient reduce of deterministic mode must read exactly the partial rows the launch wrote (it counted them with the wrong tile width
+    before round 2's fix) -- deterministic and fast mode agree to fp32 summation noise, deterministic mode is bit-reproducible, and both match the
+    bf16-emulating oracle twin."""
+    G = _gu()
+    from oracle import bf16_twin as T
+
+    cfg = dict(D=256, L=64, H=H, nh=2, wseed=9, clf=dict(input_dim=64, num_classes=2))
+    shapes = O.vae_param_shapes(256, 64, H, 2) + O.classifier_param_shapes(64, 2)
+    params = {k: v.astype(np.float32) for k, v in O.synth_params(shapes, seed=9, dtype=np.float64).items()}
+    module = G.module_from_cfg(cfg, "bf16", params=params)
+    hot = module.hot_path
+    x, y, eps = O.synth_batch(B, 256, 64, 2, seed=31)
+    xt, yt, et = torch.from_numpy(x).to(G.DEV), torch.from_numpy(y).to(G.DEV), torch.from_numpy(eps).to(G.DEV)
+
+    def run():
+        g = torch.empty(hot.arena.numel, device=G.DEV)
+        losses, _, _ = hot.step(xt, yt, et, grads=g)
+        torch.cuda.synchronize()
+        return g, losses
+
+    try:
+        G.L.set_option("deterministic", 1)
+        g1, l1 = run()
+        g2, _ = run()
+        assert torch.equal(g1, g2)
+        G.L.set_option("deterministic", 0)
+        f1, lf = run()
+    finally:
+        G.L.set_option("deterministic", 0)
+    assert torch.allclose(lf, l1, rtol=2e-6, atol=1e-7)
+    det, fast = G.flat_to_dict(module, g1), G.flat_to_dict(module, f1)
+    _, _, want = T.train_loss_and_grads_bf16(params, x, y, eps)
+    for k in det:
+        assert rel_err(fast[k], det[k]) <= 2e-5, k
+        assert rel_err(det[k], want[k]) <= 2e-3, k
+
+
 @pytest.mark.parametrize("opts", [dict(pdl=0), dict(tc_two_cta=0), dict(tc_max_stages=2), dict(tc_grouped=0), dict(tc_bn_rounds=0)])
 def test_engine_variants_reproduce_the_default_path(opts):
     """The tuning variants of the tcgen05 engine (no programmatic dependent launch, 1-CTA tiles, a 2-deep ring, one launch per encoder
