@@ -128,7 +128,8 @@ int64_t psvae_flops_per_sample(const psvae_model_desc* desc, int32_t mode);
  * path (131072), "decode_chain" (1: psvae_decode runs the chained decoder kernel where the shape allows), "train_chain" (0), "wgrad_split_cap",
  * "colsum_rows", "deterministic" (0; 1: ordered two-stage sums instead of TMA reduce-add / atomics), "pdl" (1: programmatic dependent launch),
  * "tc_two_cta" (1: CTA pairs, tcgen05 cta_group::2), "tc_grouped" (1), "tc_epi_groups" (1) / "tc_epi_groups_max_k", "fused_head" (1),
- * "clf_grad_in_bwd" (0), "tc_merged_wgrad" (1), "tc_max_stages" (0 = what fits), "tc_trace_ptr" (0), and for tests "tc_force_bn"
+ * "clf_grad_in_bwd" (0), "tc_merged_wgrad" (1) / "wgrad_order" (1) / "wgrad_splits" (0 = auto), "tc_bn_rounds" (1), "tc_max_stages" (0 = what fits),
+ * "tc_trace_ptr" (0) / "tc_trace_skip", and for tests "tc_force_bn"
  * (0|64|128|256), "tc_grid_limit", "langevin_generic".  INTEGRATION.md lists what each one does.  Env PSVAE_OPT_<NAME>=<int> sets them at load. */
 int psvae_set_option(const char* name, int64_t value);
 int64_t psvae_get_option(const char* name);
