@@ -355,27 +355,28 @@ struct LossPartials {
   float cons_w;
 };
 
-__global__ void __launch_bounds__(1024) finalize_losses_kernel(LossPartials lp, float* __restrict__ losses) {
-  PSVAE_GRID_DEP();
-  // single block of 32 warps; the 12 sums (sse, kl, 4 x nll, 4 x acc, consistency nll / acc) are taken concurrently: sum j belongs to warps
-  // j and j + 16 (even / odd 32-element chunks), each lane adds its strided elements in order, then the fixed shuffle tree -- the
-  // result depends only on the partials, not on timing
-  __shared__ float part[32];
+// The 12 sums (sse, kl, 4 x nll, 4 x acc, consistency nll / acc) as 24 warp tasks: task t = (job t & 15, half t >> 4) adds the even / odd
+// 32-element chunks of its job's partials, each lane its strided elements in order, then the fixed shuffle tree -- the result depends only on
+// the partials, not on timing or on how many warps share the tasks (32 in finalize_losses_kernel, 8 in the block that latent_bwd_clf8_kernel
+// lends to it).  part: 32 floats of shared memory.
+__device__ __forceinline__ void finalize_losses_block(const LossPartials& lp, float* __restrict__ losses, float* part, int n_warps) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int job = warp & 15, half = warp >> 4;
-  const float* p = nullptr;
-  int n = 0, stride = 1;
-  if (job == 0) { p = lp.sse; n = lp.n_sse; }
-  else if (job == 1) { p = lp.kl; n = lp.n_kl; }
-  else if (job < 6) { if (job - 2 < lp.n_heads) { p = lp.nll[job - 2]; n = lp.n_ce; stride = lp.ce_stride; } }
-  else if (job < 10) { if (job - 6 < lp.n_heads) { p = lp.acc[job - 6]; n = lp.n_ce; stride = lp.ce_stride; } }
-  else if (job == 10) { p = lp.cons_nll; n = lp.n_cons; }
-  else if (job == 11) { p = lp.cons_acc; n = lp.n_cons; }
-  float t = 0.f;
-  if (p)
-    for (int i = half * 32 + lane; i < n; i += 64) t += p[(int64_t)i * stride];
-  t = warp_sum(t);
-  if (lane == 0) part[warp] = t;
+  for (int t = warp; t < 32; t += n_warps) {
+    const int job = t & 15, half = t >> 4;
+    const float* p = nullptr;
+    int n = 0, stride = 1;
+    if (job == 0) { p = lp.sse; n = lp.n_sse; }
+    else if (job == 1) { p = lp.kl; n = lp.n_kl; }
+    else if (job < 6) { if (job - 2 < lp.n_heads) { p = lp.nll[job - 2]; n = lp.n_ce; stride = lp.ce_stride; } }
+    else if (job < 10) { if (job - 6 < lp.n_heads) { p = lp.acc[job - 6]; n = lp.n_ce; stride = lp.ce_stride; } }
+    else if (job == 10) { p = lp.cons_nll; n = lp.n_cons; }
+    else if (job == 11) { p = lp.cons_acc; n = lp.n_cons; }
+    float v = 0.f;
+    if (p)
+      for (int i = half * 32 + lane; i < n; i += 64) v += p[(int64_t)i * stride];
+    v = warp_sum(v);
+    if (lane == 0) part[t] = v;
+  }
   __syncthreads();
   auto total = [&](int j) { return part[j] + part[j + 16]; };
   const float sse = total(0), kls = total(1);
@@ -403,6 +404,12 @@ __global__ void __launch_bounds__(1024) finalize_losses_kernel(LossPartials lp, 
       losses[13] = cons_acc * lp.inv_b;
     }
   }
+}
+
+__global__ void __launch_bounds__(1024) finalize_losses_kernel(LossPartials lp, float* __restrict__ losses) {
+  PSVAE_GRID_DEP();
+  __shared__ float part[32];
+  finalize_losses_block(lp, losses, part, 32);
 }
 
 }  // namespace psvae
@@ -1030,10 +1037,18 @@ __global__ void __launch_bounds__(256, 3) latent_bwd_clf_kernel(const float* __r
 template <int NC>
 __global__ void __launch_bounds__(256, 2) latent_bwd_clf8_kernel(const float* __restrict__ dz, const float* __restrict__ mu, const float* __restrict__ ls,
                                                                   const bf16* __restrict__ hs, int64_t rows, int L, float kl_over_b, bf16* __restrict__ dmu,
-                                                                  bf16* __restrict__ dls, float* __restrict__ bias_grad, int64_t ld_d, ClfBwdArgs ca) {
+                                                                  bf16* __restrict__ dls, float* __restrict__ bias_grad, int64_t ld_d, ClfBwdArgs ca,
+                                                                  LossPartials lp, float* __restrict__ losses) {
   PSVAE_GRID_DEP();
   static_assert(NC >= 1 && NC <= 4, "one float4 of d loss / d logits per row");
   extern __shared__ float lb_smem[];        // [256][8]
+  // losses != nullptr: the LAST block of the grid turns the forward pass's loss partials into the 16 loss scalars (what finalize_losses_kernel
+  // does as a launch of its own between the forward and the backward pass: one launch boundary less on the step's critical path)
+  const int n_blocks = (int)gridDim.x - (losses ? 1 : 0);
+  if (losses && (int)blockIdx.x == n_blocks) {
+    finalize_losses_block(lp, losses, lb_smem, 8);
+    return;
+  }
   const int tpr = L >> 3;                   // threads per row
   const int rpb = 256 / tpr;                // rows per block and trip
   const int cgp = (int)threadIdx.x % tpr, col8 = cgp << 3, rin = (int)threadIdx.x / tpr;
@@ -1117,7 +1132,7 @@ __global__ void __launch_bounds__(256, 2) latent_bwd_clf8_kernel(const float* __
   };
   // software pipeline: the NEXT row's eight 16-byte loads are issued before the current row's arithmetic (expm1f, 2 NC x 8 FMAs, packing), so
   // that memory requests are in flight all the time -- with both rows loaded and then both computed the kernel alternated between the two
-  const int64_t step = (int64_t)gridDim.x * rpb;
+  const int64_t step = (int64_t)n_blocks * rpb;
   int64_t r = (int64_t)blockIdx.x * rpb + rin;
   if (r < rows) {
     Oct cur, nxt;

@@ -438,6 +438,8 @@ static int clf_fused_blocks(int64_t rows) {
   if (b > 4 * PSVAE_NUM_SMS) b = 4 * PSVAE_NUM_SMS;
   return b < 1 ? 1 : (int)b;
 }
+// the 8-columns-per-thread latent backward (latent_bwd_clf8_kernel): L a multiple of 8 with L / 8 dividing 256, at most 4 classes in total
+static bool latent8_ok(int L, int total_classes) { return L % 8 == 0 && 256 % (L / 8) == 0 && L <= 256 && total_classes >= 1 && total_classes <= 4; }
 static bool latent_cs_ok(int L) { return L % 4 == 0 && 256 % (L / 4) == 0 && 2 * L <= 256; }
 // Does the tcgen05 train step of this model use the fused encoder-head kernel (EpiLatent)?  Decided from the model shape and the options only
 // (so that the workspace plan and the step agree): latent 64, hidden a multiple of 64, no classifier or ONE linear head of <= 4 classes.
@@ -1082,9 +1084,18 @@ static int run_step(const StepArgs& a) {
       n_sse_used = blocks;
     }
   }
+  // The loss scalars have no consumer on the device: when the backward pass runs the 8-column latent kernel, its last block computes them
+  // (one launch boundary less between the forward and the backward pass); otherwise finalize_losses_kernel does, right here.
+  LossPartials lp;
+  memset(&lp, 0, sizeof(lp));
+  bool finalize_in_latent = false;
+  if constexpr (sizeof(TAct) == 2) {
+    int total_classes = 0;
+    for (int h = 0; h < d->clf_num_heads; ++h) total_classes += d->clf_head_classes[h];
+    finalize_in_latent = a.want_loss && a.want_grads && !a.ext && clf_fused && (g_opt.clf_grad_in_bwd || fused_head) && !g_opt.deterministic &&
+                         w.clf_grows && latent_cs_ok(n.L) && latent8_ok(n.L, total_classes);
+  }
   if (a.want_loss) {
-    LossPartials lp;
-    memset(&lp, 0, sizeof(lp));
     lp.sse = w.sse_part; lp.n_sse = n_sse_used;
     lp.kl = w.kl_part; lp.n_kl = n_kl_used;
     const bool ce_from_blocks = clf_fused && !g_opt.deterministic;     // fused pass, fast mode: one (nll, acc) record per block
@@ -1100,9 +1111,11 @@ static int run_step(const StepArgs& a) {
     if (fused_head && lp.n_heads > 0) { lp.nll[0] = w.clf_part; lp.acc[0] = w.clf_part + PSVAE_NUM_SMS; lp.n_ce = fused_ctas; lp.ce_stride = 1; }
     lp.kl_w = a.kl_w; lp.clf_w = a.clf_w;
     if (cons_on) { lp.cons_nll = cw.nll_part; lp.cons_acc = cw.acc_part; lp.n_cons = (int)cw.n_ce; lp.cons_w = a.cons_w; }
-    launch_dep(finalize_losses_kernel, dim3(1), dim3(1024), 0, st, lp, a.losses);
-    count_launch();
-    PSVAE_LAUNCH_CHECK("finalize_losses_kernel");
+    if (!finalize_in_latent) {
+      launch_dep(finalize_losses_kernel, dim3(1), dim3(1024), 0, st, lp, a.losses);
+      count_launch();
+      PSVAE_LAUNCH_CHECK("finalize_losses_kernel");
+    }
   }
   if (!a.want_grads) return 0;
 
@@ -1196,14 +1209,14 @@ static int run_step(const StepArgs& a) {
     bool done8 = false;
     if constexpr (sizeof(TAct) == 2) {
       // the 8-columns-per-thread form: L a multiple of 8 with L / 8 dividing 256, at most 4 classes
-      if (n.L % 8 == 0 && 256 % (n.L / 8) == 0 && n.L <= 256 && cb.total_classes <= 4) {
+      if (latent8_ok(n.L, cb.total_classes)) {
         const int rpb = 256 / (n.L / 8);
         int64_t nb = ceil_div64(B, rpb);
         if (nb > 2 * PSVAE_NUM_SMS) nb = 2 * PSVAE_NUM_SMS;
         if (nb < 1) nb = 1;
 #define PSVAE_LBC8(NCV)                                                                                                                       \
-        launch_dep(latent_bwd_clf8_kernel<NCV>, dim3((unsigned)nb), dim3(256), smem + (size_t)NCV * n.L * sizeof(float), st, w.dz, mu, ls, w.hs, B, n.L, a.kl_w / (float)B, w.dmu, w.dls, \
-                   bias_grad, (int64_t)2 * n.L, cb)
+        launch_dep(latent_bwd_clf8_kernel<NCV>, dim3((unsigned)nb + (finalize_in_latent ? 1u : 0u)), dim3(256), smem + (size_t)NCV * n.L * sizeof(float), st, w.dz, mu, ls, \
+                   w.hs, B, n.L, a.kl_w / (float)B, w.dmu, w.dls, bias_grad, (int64_t)2 * n.L, cb, lp, finalize_in_latent ? a.losses : (float*)nullptr)
         if (cb.total_classes <= 2) PSVAE_LBC8(2);
         else PSVAE_LBC8(4);
 #undef PSVAE_LBC8
