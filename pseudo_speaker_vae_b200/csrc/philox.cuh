@@ -28,7 +28,22 @@ __host__ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1
 __device__ __forceinline__ void box_muller(uint32_t ra, uint32_t rb, float& n_even, float& n_odd) {
   const float u = fmaf(__uint2float_rn(ra), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
   const float t = fmaf(__uint2float_rn(rb), 4.6566128730773926e-10f, -1.0f);
+#ifndef PSVAE_ACCURATE_BOX_MULLER
+  // radius with the hardware log2 / sqrt approximations: 3 instructions instead of ~36 -- logf + IEEE sqrtf were 31 % of the Langevin kernel's
+  // instructions (profiles/r02_ncu_sampling_kernels.txt).  ln u carries an absolute error of ~1e-7, the radius s one of ~1e-7 / s: measured over
+  // 2^20 samples against the fp64 spec (oracle/philox_ref.py) mean 1.6e-7 (accurate form: 1.2e-7), 99.9th percentile 9.5e-7 (8.3e-7), maximum
+  // 7e-5 at the rare small-radius sample (1.3e-6).  eps is noise: its value is pinned by the counter, not by the last bits of the transform.
+  // Conditional sampling +35 %, bare generator +57 %, unconditional sampling +6 %, train step -5 us.  -DPSVAE_ACCURATE_BOX_MULLER restores logf / sqrtf.
+  float s;
+  {
+    float lg;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(u));
+    const float m2ln = -1.3862943611198906f * lg;          // -2 ln 2 * log2(u)
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(m2ln));
+  }
+#else
   const float s = sqrtf(-2.0f * logf(u));          // accurate log: keeps |error| ~1e-7 even for u -> 1
+#endif
   float sn, cs;
   __sincosf(3.14159265358979323846f * t, &sn, &cs);   // argument in [-pi, pi]: fast intrinsic is at its best
   n_even = s * sn;
